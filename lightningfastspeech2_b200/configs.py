@@ -1,0 +1,147 @@
+"""Constructor-kwarg presets for the BASELINE.json configs ("Config symbols").
+
+Every dict is a set of kwargs for ``FastSpeech2.__init__`` with the reference's names
+(reference litfass/fastspeech2/fastspeech2.py:46-130).  Anything not listed keeps the
+reference's constructor default.
+"""
+import copy
+
+# reference constructor defaults that matter on the hot path (fastspeech2.py:46-130)
+HOT_PATH_DEFAULTS = dict(
+    lr=1e-4,
+    warmup_steps=4000,
+    speaker_type="dvector",
+    max_length=32,
+    variances=["pitch", "energy", "snr"],
+    variance_levels=["frame", "frame", "frame"],
+    variance_transforms=["cwt", "none", "none"],
+    variance_losses=["mse", "mse", "mse"],
+    variance_nlayers=[5, 5, 5, 5],
+    variance_loss_weights=[5e-2, 5e-2, 5e-2, 5e-2],
+    variance_kernel_size=[3, 3, 3, 3],
+    variance_dropout=[0.5, 0.5, 0.5, 0.5],
+    variance_filter_size=256,
+    variance_nbins=256,
+    variance_depthwise_conv=True,
+    duration_nlayers=2,
+    duration_loss="mse",
+    duration_loss_weight=5e-1,
+    duration_stochastic=False,
+    duration_kernel_size=3,
+    duration_dropout=0.5,
+    duration_filter_size=256,
+    duration_depthwise_conv=True,
+    mel_loss="l1",
+    speaker_embedding_every_layer=False,
+    prior_embedding_every_layer=False,
+    priors=[],
+    mel_loss_weight=1,
+    n_mels=80,
+    sampling_rate=22050,
+    hop_length=256,
+    encoder_hidden=256,
+    encoder_head=2,
+    encoder_layers=4,
+    encoder_dropout=0.1,
+    encoder_kernel_sizes=[5, 25, 13, 9],
+    encoder_conformer=True,
+    encoder_depthwise_conv=True,
+    encoder_conv_filter_size=1024,
+    decoder_hidden=256,
+    decoder_head=2,
+    decoder_layers=4,
+    decoder_dropout=0.1,
+    decoder_kernel_sizes=[17, 21, 9, 13],
+    decoder_conformer=True,
+    decoder_depthwise_conv=True,
+    decoder_conv_filter_size=1024,
+    fastdiff_variances=True,
+)
+
+_TWO_VARS = dict(
+    variances=["pitch", "energy"],
+    variance_levels=["frame", "frame"],
+    variance_transforms=["none", "none"],
+    variance_losses=["mse", "mse"],
+    variance_nlayers=[5, 5],
+    variance_loss_weights=[5e-2, 5e-2],
+    variance_kernel_size=[3, 3],
+    variance_dropout=[0.5, 0.5],
+    fastdiff_variances=False,
+)
+
+# C1: ming024-like dense-conv FastSpeech2 (24.5 M params); B=1, Tp=128
+C1 = dict(
+    _TWO_VARS,
+    variance_nlayers=[2, 2],
+    encoder_kernel_sizes=[9, 9, 9, 9],
+    decoder_kernel_sizes=[9, 9, 9, 9],
+    encoder_depthwise_conv=False,
+    decoder_depthwise_conv=False,
+    variance_depthwise_conv=False,
+    duration_depthwise_conv=False,
+)
+
+# C2: LightSpeech depthwise-separable variant = the reference's constructor defaults
+# with two frame-level variances (7.4 M params); B=64, Tp in [32, 512]
+C2 = dict(_TWO_VARS)
+
+# C3/C4: "76 M" reconstruction (75 061 329 params): d=768, F=3072, 4 enc + 5 dec
+C3 = dict(
+    variances=["pitch", "energy", "snr"],
+    variance_levels=["frame", "frame", "frame"],
+    variance_transforms=["none", "none", "none"],
+    variance_losses=["mse", "mse", "mse"],
+    variance_nlayers=[5, 5, 5],
+    variance_loss_weights=[5e-2, 5e-2, 5e-2],
+    variance_kernel_size=[3, 3, 3],
+    variance_dropout=[0.5, 0.5, 0.5],
+    fastdiff_variances=False,
+    encoder_hidden=768,
+    decoder_hidden=768,
+    variance_filter_size=768,
+    duration_filter_size=768,
+    encoder_conv_filter_size=3072,
+    decoder_conv_filter_size=3072,
+    decoder_layers=5,
+    decoder_kernel_sizes=[17, 21, 9, 13, 9],
+)
+
+# tiny shapes used only to pin the oracle against the reference (tests/golden/)
+TINY_DW = dict(
+    _TWO_VARS,
+    encoder_hidden=32,
+    decoder_hidden=32,
+    variance_filter_size=32,
+    duration_filter_size=32,
+    encoder_conv_filter_size=64,
+    decoder_conv_filter_size=64,
+    encoder_layers=2,
+    decoder_layers=2,
+    encoder_kernel_sizes=[5, 9],
+    decoder_kernel_sizes=[7, 3],
+    variance_nlayers=[3, 2],
+    variance_nbins=16,
+)
+TINY_DENSE = dict(
+    TINY_DW,
+    encoder_depthwise_conv=False,
+    decoder_depthwise_conv=False,
+    variance_depthwise_conv=False,
+    duration_depthwise_conv=False,
+)
+
+PRESETS = {"C1": C1, "C2": C2, "C3": C3, "TINY_DW": TINY_DW, "TINY_DENSE": TINY_DENSE}
+
+
+def resolve(kwargs):
+    """kwargs merged over the reference's constructor defaults."""
+    hp = copy.deepcopy(HOT_PATH_DEFAULTS)
+    hp.update(copy.deepcopy(kwargs))
+    return hp
+
+
+def max_frames(hp):
+    """LengthRegulator cap handed to the VarianceAdaptor (reference fastspeech2.py:341-343):
+    a *float*, max_length * sampling_rate / hop_length = 2756.25 by default."""
+    return hp["max_length"] * hp["sampling_rate"] / hp["hop_length"]
