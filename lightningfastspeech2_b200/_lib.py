@@ -1,0 +1,67 @@
+"""ctypes binding of liblfs2.so (the C ABI declared in include/lfs2.h).
+
+There is deliberately no fallback: if the CUDA library is missing or a call fails, the
+product path raises.  Build it with ``python -m lightningfastspeech2_b200.build`` (or
+``__graft_entry__.build()``).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblfs2.so")
+
+_vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+
+# name -> argtypes; every function returns int except lfs2_last_error
+SIGNATURES = {
+    "lfs2_version": [],
+    "lfs2_device_arch": [],
+    "lfs2_speaker_proj": [_vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "lfs2_embed_pe_spk": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "lfs2_add_pe_spk": [_vp, _vp, _vp, _i, _i, _i, _vp],
+    "lfs2_linear": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "lfs2_conv1d_dense": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
+    "lfs2_dwconv1d": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "lfs2_attention": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "lfs2_add_layernorm": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
+    "lfs2_rowdot_mask": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "lfs2_bucket_embed_add": [_vp, _vp, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "lfs2_duration_round_guard": [_vp, _vp, _vp, _i, _i, _vp],
+    "lfs2_length_regulate_scan": [_vp, _i, _vp, _vp, _vp, _i, _i, _vp],
+    "lfs2_length_regulate_scatter": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+}
+
+_lib = None
+
+
+class Lfs2Error(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle; raises if liblfs2.so is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise Lfs2Error(
+            f"{LIB_PATH} not found: the CUDA library has not been built "
+            "(python -m lightningfastspeech2_b200.build). There is no CPU fallback.")
+    h = ctypes.CDLL(LIB_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(h, name)  # AttributeError if the .so does not export a declared symbol
+        fn.argtypes = argtypes
+        fn.restype = ctypes.c_int
+    h.lfs2_last_error.argtypes = []
+    h.lfs2_last_error.restype = ctypes.c_char_p
+    _lib = h
+    return h
+
+
+def check(rc, name):
+    if rc != 0:
+        msg = lib().lfs2_last_error().decode(errors="replace")
+        codes = {-1: "INVALID_ARG", -2: "UNSUPPORTED", -3: "CUDA"}
+        if rc == -2:
+            raise NotImplementedError(f"{name}: {msg}")
+        raise Lfs2Error(f"{name} failed ({codes.get(rc, rc)}): {msg}")

@@ -1,0 +1,413 @@
+// HBM-bound glue kernels of the mel-generation path: front end (embedding + positional
+// encoding + speaker term), residual LayerNorm, depthwise Conv1d, predictor head, duration
+// rounding + zero-duration guard, bucketize + embedding add.  All are pure streaming
+// kernels: 16-byte coalesced accesses, warp-shuffle reductions, no shared-memory staging
+// (no reuse to exploit beyond L1/L2).
+#include <math.h>
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace lfs2 {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// ---------------------------------------------------------------------------------------
+// spk[b, j] = relu(dot(w[j, :], dvec[b, :]) + bias[j]); one warp per output element
+__global__ void speaker_proj_kernel(const float* __restrict__ dvec, const float* __restrict__ w,
+                                    const float* __restrict__ bias, float* __restrict__ spk, int batch,
+                                    int in_dim, int d) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (warp >= batch * d) return;
+  int b = warp / d, j = warp % d;
+  const float* wr = w + (size_t)j * in_dim;
+  const float* xr = dvec + (size_t)b * in_dim;
+  float acc = 0.f;
+  for (int i = lane; i < in_dim; i += 32) acc = fmaf(wr[i], xr[i], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) spk[warp] = fmaxf(acc + bias[j], 0.f);
+}
+
+// x[b,t,:] = emb[phones[b,t],:] + pe[t,:] + spk[b,:]; one thread per float4
+__global__ void embed_pe_spk_kernel(const int64_t* __restrict__ phones, const float4* __restrict__ emb,
+                                    const float4* __restrict__ pe, const float4* __restrict__ spk,
+                                    float4* __restrict__ x, uint8_t* __restrict__ src_mask, int batch, int t,
+                                    int d4, int vocab) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)batch * t * d4;
+  if (i >= total) return;
+  int c = (int)(i % d4);
+  size_t row = i / d4;
+  int tt = (int)(row % t);
+  int b = (int)(row / t);
+  long long ph = phones[row];
+  if (c == 0) src_mask[row] = (ph == 0);
+  ph = ph < 0 ? 0 : (ph >= vocab ? vocab - 1 : ph);  // never read out of the table
+  float4 e = emb[(size_t)ph * d4 + c];
+  float4 p = pe[(size_t)tt * d4 + c];
+  float4 s = spk[(size_t)b * d4 + c];
+  // same association as the reference: (emb + pe) + spk
+  float4 o;
+  o.x = (e.x + p.x) + s.x;
+  o.y = (e.y + p.y) + s.y;
+  o.z = (e.z + p.z) + s.z;
+  o.w = (e.w + p.w) + s.w;
+  x[i] = o;
+}
+
+__global__ void add_pe_spk_kernel(float4* __restrict__ x, const float4* __restrict__ pe,
+                                  const float4* __restrict__ spk, int batch, int t, int d4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)batch * t * d4;
+  if (i >= total) return;
+  int c = (int)(i % d4);
+  size_t row = i / d4;
+  int tt = (int)(row % t);
+  int b = (int)(row / t);
+  float4 v = x[i];
+  float4 p = pe[(size_t)tt * d4 + c];
+  float4 s = spk[(size_t)b * d4 + c];
+  v.x = (v.x + p.x) + s.x;
+  v.y = (v.y + p.y) + s.y;
+  v.z = (v.z + p.z) + s.z;
+  v.w = (v.w + p.w) + s.w;
+  x[i] = v;
+}
+
+// ---------------------------------------------------------------------------------------
+// out[m,:] = LN(x[m,:] + y[m,:]); one warp per row, row kept in registers (d <= 1024),
+// two-pass mean / centred variance like torch's CPU kernel.
+constexpr int kLnMaxVec = 8;  // float4 per lane -> d <= 1024
+__global__ void add_layernorm_kernel(const float4* __restrict__ x, const float4* __restrict__ y,
+                                     const float4* __restrict__ gamma, const float4* __restrict__ beta,
+                                     float4* __restrict__ out, int m, int d4, float eps) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= m) return;
+  const float4* xr = x + (size_t)row * d4;
+  const float4* yr = y ? y + (size_t)row * d4 : nullptr;
+  float4 v[kLnMaxVec];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    int c = lane + 32 * i;
+    if (c < d4) {
+      float4 a = xr[c];
+      if (yr) {
+        float4 b = yr[c];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      v[i] = a;
+      s += (a.x + a.y) + (a.z + a.w);
+    }
+  }
+  float inv_d = 1.f / (float)(d4 * 4);
+  float mean = warp_sum(s) * inv_d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    int c = lane + 32 * i;
+    if (c < d4) {
+      float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, dd = v[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + dd * dd);
+    }
+  }
+  float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+  float4* orow = out + (size_t)row * d4;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    int c = lane + 32 * i;
+    if (c < d4) {
+      float4 g = gamma[c], bt = beta[c], o;
+      o.x = (v[i].x - mean) * rstd * g.x + bt.x;
+      o.y = (v[i].y - mean) * rstd * g.y + bt.y;
+      o.z = (v[i].z - mean) * rstd * g.z + bt.z;
+      o.w = (v[i].w - mean) * rstd * g.w + bt.w;
+      orow[c] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// depthwise conv, channels-last: out[b,t,c] = bias[c] + sum_j wt[j,c] * x[b,t+j-h,c]
+// thread = 4 channels x kDwT consecutive frames (sliding window held in registers)
+constexpr int kDwT = 8;
+__global__ void dwconv1d_kernel(const float4* __restrict__ x, const float4* __restrict__ wt,
+                                const float4* __restrict__ bias, float4* __restrict__ out, int batch, int t,
+                                int d4, int ksize, int nchunk) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t total = (size_t)batch * nchunk * d4;
+  if (i >= total) return;
+  int c = (int)(i % d4);
+  int chunk = (int)((i / d4) % nchunk);
+  int b = (int)(i / ((size_t)d4 * nchunk));
+  int t0 = chunk * kDwT;
+  int h = (ksize - 1) / 2;
+  const float4* xb = x + (size_t)b * t * d4 + c;
+  float4 acc[kDwT];
+  float4 bz = bias[c];
+#pragma unroll
+  for (int o = 0; o < kDwT; ++o) acc[o] = bz;
+  // input frame t0 - h + j contributes to output o = j - tap for tap in [0, ksize)
+  for (int j = 0; j < kDwT + ksize - 1; ++j) {
+    int ti = t0 - h + j;
+    if (ti < 0 || ti >= t) continue;
+    float4 xv = xb[(size_t)ti * d4];
+#pragma unroll
+    for (int o = 0; o < kDwT; ++o) {
+      int tap = j - o;
+      if (tap >= 0 && tap < ksize) {
+        float4 w = wt[(size_t)tap * d4 + c];
+        acc[o].x = fmaf(w.x, xv.x, acc[o].x);
+        acc[o].y = fmaf(w.y, xv.y, acc[o].y);
+        acc[o].z = fmaf(w.z, xv.z, acc[o].z);
+        acc[o].w = fmaf(w.w, xv.w, acc[o].w);
+      }
+    }
+  }
+  float4* ob = out + (size_t)b * t * d4 + c;
+#pragma unroll
+  for (int o = 0; o < kDwT; ++o)
+    if (t0 + o < t) ob[(size_t)(t0 + o) * d4] = acc[o];
+}
+
+// ---------------------------------------------------------------------------------------
+// out[m] = mask[m] ? 0 : dot(z[m,:], w) + bias ; one warp per row
+__global__ void rowdot_mask_kernel(const float4* __restrict__ z, const float4* __restrict__ w,
+                                   const float* __restrict__ bias, const uint8_t* __restrict__ mask,
+                                   float* __restrict__ out, int m, int f4) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= m) return;
+  const float4* zr = z + (size_t)row * f4;
+  float acc = 0.f;
+  for (int c = lane; c < f4; c += 32) {
+    float4 a = zr[c], b = w[c];
+    acc += (a.x * b.x + a.y * b.y) + (a.z * b.z + a.w * b.w);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[row] = (mask && mask[row]) ? 0.f : acc + bias[0];
+}
+
+// ---------------------------------------------------------------------------------------
+// inference durations + zero-duration guard; one CTA per utterance
+__global__ void duration_round_guard_kernel(const float* __restrict__ log_dur, const uint8_t* __restrict__ src_mask,
+                                            int32_t* __restrict__ dur, int tp) {
+  int b = blockIdx.x;
+  const float* p = log_dur + (size_t)b * tp;
+  const uint8_t* mk = src_mask + (size_t)b * tp;
+  int32_t* o = dur + (size_t)b * tp;
+  long long total = 0;
+  int nvalid = 0;
+  for (int i = threadIdx.x; i < tp; i += blockDim.x) {
+    float v = rintf(expf(p[i]) - 1.f);  // torch.round = round-half-even
+    v = fmaxf(v, 0.f);                   // clamp(min=0); NaN -> 0 differs from torch only for NaN inputs
+    int32_t di = v >= 2147483520.f ? 2147483647 : (int32_t)v;
+    o[i] = di;
+    if (!mk[i]) {
+      total += di;
+      ++nvalid;
+    }
+  }
+  __shared__ long long s_total[32];
+  __shared__ int s_nvalid[32];
+  int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    total += __shfl_xor_sync(0xffffffffu, total, off);
+    nvalid += __shfl_xor_sync(0xffffffffu, nvalid, off);
+  }
+  if (lane == 0) {
+    s_total[w] = total;
+    s_nvalid[w] = nvalid;
+  }
+  __syncthreads();
+  total = 0;
+  nvalid = 0;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) {
+    total += s_total[i];
+    nvalid += s_nvalid[i];
+  }
+  if (total <= (long long)(nvalid / 2)) {
+    for (int i = threadIdx.x; i < tp; i += blockDim.x)
+      if (!mk[i]) o[i] = 1;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// bucketize (right=False, torch's lower-bound loop incl. its NaN behaviour) + embedding add
+__global__ void bucket_embed_add_kernel(float4* __restrict__ x, const float* __restrict__ val, float stdv,
+                                        float meanv, const float* __restrict__ bins, int nb,
+                                        const float4* __restrict__ emb, const int64_t* __restrict__ idx_forced,
+                                        int64_t* __restrict__ idx_out, float4* __restrict__ acc, int acc_mode,
+                                        int m, int d4) {
+  int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= m) return;
+  int idx;
+  if (idx_forced) {
+    idx = (int)idx_forced[row];
+  } else {
+    // two roundings (mul then add), exactly like `prediction * std + mean` in torch
+    float v = __fadd_rn(__fmul_rn(val[row], stdv), meanv);
+    int lo = 0, hi = nb;
+    while (lo < hi) {
+      int mid = lo + ((hi - lo) >> 1);
+      if (!(bins[mid] >= v)) lo = mid + 1;
+      else hi = mid;
+    }
+    idx = lo;
+  }
+  if (lane == 0 && idx_out) idx_out[row] = idx;
+  const float4* e = emb + (size_t)idx * d4;
+  float4* xr = x + (size_t)row * d4;
+  float4* ar = acc ? acc + (size_t)row * d4 : nullptr;
+  for (int c = lane; c < d4; c += 32) {
+    float4 ev = e[c], xv = xr[c];
+    xv.x += ev.x; xv.y += ev.y; xv.z += ev.z; xv.w += ev.w;
+    xr[c] = xv;
+    if (acc_mode == 1) {
+      ar[c] = ev;
+    } else if (acc_mode == 2) {
+      float4 av = ar[c];
+      av.x += ev.x; av.y += ev.y; av.z += ev.z; av.w += ev.w;
+      ar[c] = av;
+    }
+  }
+}
+
+}  // namespace lfs2
+
+using namespace lfs2;
+
+extern "C" {
+
+int lfs2_version(void) { return 100; }
+const char* lfs2_last_error(void) { return lfs2::g_err; }
+
+int lfs2_device_arch(void) {
+  int dev = 0, major = 0, minor = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return LFS2_ERR_CUDA;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+  return major * 10 + minor;
+}
+
+int lfs2_speaker_proj(const float* dvec, const float* w, const float* bias, float* spk, int batch, int in_dim,
+                      int d, void* stream) {
+  LFS2_REQUIRE(dvec && w && bias && spk, LFS2_ERR_INVALID_ARG, "speaker_proj: null pointer");
+  LFS2_REQUIRE(batch > 0 && in_dim > 0 && d > 0, LFS2_ERR_INVALID_ARG, "speaker_proj: bad shape");
+  int threads = 256;
+  int blocks = ceil_div((long long)batch * d * 32, threads);
+  speaker_proj_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(dvec, w, bias, spk, batch, in_dim, d);
+  LFS2_CHECK_LAUNCH("speaker_proj");
+  return LFS2_OK;
+}
+
+int lfs2_embed_pe_spk(const int64_t* phones, const float* emb, const float* pe, const float* spk, float* x,
+                      uint8_t* src_mask, int batch, int t, int d, int vocab, void* stream) {
+  LFS2_REQUIRE(phones && emb && pe && spk && x && src_mask, LFS2_ERR_INVALID_ARG, "embed_pe_spk: null pointer");
+  LFS2_REQUIRE(batch > 0 && t > 0 && vocab > 0, LFS2_ERR_INVALID_ARG, "embed_pe_spk: bad shape");
+  LFS2_REQUIRE(d > 0 && d % 4 == 0, LFS2_ERR_UNSUPPORTED, "embed_pe_spk: d=%d must be a multiple of 4", d);
+  LFS2_REQUIRE(aligned16(emb) && aligned16(pe) && aligned16(spk) && aligned16(x), LFS2_ERR_INVALID_ARG,
+               "embed_pe_spk: pointers must be 16-byte aligned");
+  size_t total = (size_t)batch * t * (d / 4);
+  embed_pe_spk_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      phones, (const float4*)emb, (const float4*)pe, (const float4*)spk, (float4*)x, src_mask, batch, t, d / 4,
+      vocab);
+  LFS2_CHECK_LAUNCH("embed_pe_spk");
+  return LFS2_OK;
+}
+
+int lfs2_add_pe_spk(float* x, const float* pe, const float* spk, int batch, int t, int d, void* stream) {
+  LFS2_REQUIRE(x && pe && spk, LFS2_ERR_INVALID_ARG, "add_pe_spk: null pointer");
+  if (batch == 0 || t == 0) return LFS2_OK;
+  LFS2_REQUIRE(d > 0 && d % 4 == 0, LFS2_ERR_UNSUPPORTED, "add_pe_spk: d=%d must be a multiple of 4", d);
+  LFS2_REQUIRE(aligned16(x) && aligned16(pe) && aligned16(spk), LFS2_ERR_INVALID_ARG,
+               "add_pe_spk: pointers must be 16-byte aligned");
+  size_t total = (size_t)batch * t * (d / 4);
+  add_pe_spk_kernel<<<ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>((float4*)x, (const float4*)pe,
+                                                                          (const float4*)spk, batch, t, d / 4);
+  LFS2_CHECK_LAUNCH("add_pe_spk");
+  return LFS2_OK;
+}
+
+int lfs2_add_layernorm(const float* x, const float* y, const float* gamma, const float* beta, float* out, int m,
+                       int d, float eps, void* stream) {
+  LFS2_REQUIRE(x && gamma && beta && out, LFS2_ERR_INVALID_ARG, "add_layernorm: null pointer");
+  if (m == 0) return LFS2_OK;
+  LFS2_REQUIRE(d > 0 && d % 4 == 0 && d <= 128 * kLnMaxVec, LFS2_ERR_UNSUPPORTED,
+               "add_layernorm: d=%d must be a multiple of 4 and <= %d", d, 128 * kLnMaxVec);
+  LFS2_REQUIRE(aligned16(x) && aligned16(gamma) && aligned16(beta) && aligned16(out) && (!y || aligned16(y)),
+               LFS2_ERR_INVALID_ARG, "add_layernorm: pointers must be 16-byte aligned");
+  int threads = 256;
+  add_layernorm_kernel<<<ceil_div((long long)m * 32, threads), threads, 0, (cudaStream_t)stream>>>(
+      (const float4*)x, (const float4*)y, (const float4*)gamma, (const float4*)beta, (float4*)out, m, d / 4, eps);
+  LFS2_CHECK_LAUNCH("add_layernorm");
+  return LFS2_OK;
+}
+
+int lfs2_dwconv1d(const float* x, const float* wt, const float* bias, float* out, int batch, int t, int d,
+                  int ksize, void* stream) {
+  LFS2_REQUIRE(x && wt && bias && out, LFS2_ERR_INVALID_ARG, "dwconv1d: null pointer");
+  if (batch == 0 || t == 0) return LFS2_OK;
+  LFS2_REQUIRE(d > 0 && d % 4 == 0, LFS2_ERR_UNSUPPORTED, "dwconv1d: d=%d must be a multiple of 4", d);
+  LFS2_REQUIRE(ksize > 0 && ksize % 2 == 1, LFS2_ERR_UNSUPPORTED,
+               "dwconv1d: kernel size %d must be odd ('same' padding is asymmetric otherwise)", ksize);
+  LFS2_REQUIRE(aligned16(x) && aligned16(wt) && aligned16(bias) && aligned16(out), LFS2_ERR_INVALID_ARG,
+               "dwconv1d: pointers must be 16-byte aligned");
+  int nchunk = ceil_div(t, kDwT);
+  size_t total = (size_t)batch * nchunk * (d / 4);
+  dwconv1d_kernel<<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(
+      (const float4*)x, (const float4*)wt, (const float4*)bias, (float4*)out, batch, t, d / 4, ksize, nchunk);
+  LFS2_CHECK_LAUNCH("dwconv1d");
+  return LFS2_OK;
+}
+
+int lfs2_rowdot_mask(const float* z, const float* w, const float* bias, const uint8_t* mask, float* out, int m,
+                     int f, void* stream) {
+  LFS2_REQUIRE(z && w && bias && out, LFS2_ERR_INVALID_ARG, "rowdot_mask: null pointer");
+  if (m == 0) return LFS2_OK;
+  LFS2_REQUIRE(f > 0 && f % 4 == 0, LFS2_ERR_UNSUPPORTED, "rowdot_mask: f=%d must be a multiple of 4", f);
+  LFS2_REQUIRE(aligned16(z) && aligned16(w), LFS2_ERR_INVALID_ARG, "rowdot_mask: pointers must be 16-byte aligned");
+  int threads = 256;
+  rowdot_mask_kernel<<<ceil_div((long long)m * 32, threads), threads, 0, (cudaStream_t)stream>>>(
+      (const float4*)z, (const float4*)w, bias, mask, out, m, f / 4);
+  LFS2_CHECK_LAUNCH("rowdot_mask");
+  return LFS2_OK;
+}
+
+int lfs2_duration_round_guard(const float* log_dur, const uint8_t* src_mask, int32_t* dur, int batch, int tp,
+                              void* stream) {
+  LFS2_REQUIRE(log_dur && src_mask && dur, LFS2_ERR_INVALID_ARG, "duration_round_guard: null pointer");
+  if (batch == 0 || tp == 0) return LFS2_OK;
+  duration_round_guard_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(log_dur, src_mask, dur, tp);
+  LFS2_CHECK_LAUNCH("duration_round_guard");
+  return LFS2_OK;
+}
+
+int lfs2_bucket_embed_add(float* x, const float* val, float stdv, float meanv, const float* bins, int nbins,
+                          const float* emb, const int64_t* idx_forced, int64_t* idx_out, float* acc, int acc_mode,
+                          int m, int d, void* stream) {
+  LFS2_REQUIRE(x && emb && (idx_forced || (val && bins)), LFS2_ERR_INVALID_ARG, "bucket_embed_add: null pointer");
+  if (m == 0) return LFS2_OK;
+  LFS2_REQUIRE(d > 0 && d % 4 == 0 && nbins >= 1, LFS2_ERR_UNSUPPORTED, "bucket_embed_add: bad d/nbins");
+  LFS2_REQUIRE(acc_mode == 0 || acc, LFS2_ERR_INVALID_ARG, "bucket_embed_add: acc_mode without acc");
+  LFS2_REQUIRE(aligned16(x) && aligned16(emb) && (!acc || aligned16(acc)), LFS2_ERR_INVALID_ARG,
+               "bucket_embed_add: pointers must be 16-byte aligned");
+  int threads = 256;
+  bucket_embed_add_kernel<<<ceil_div((long long)m * 32, threads), threads, 0, (cudaStream_t)stream>>>(
+      (float4*)x, val, stdv, meanv, bins, nbins - 1, (const float4*)emb, idx_forced, idx_out, (float4*)acc,
+      acc ? acc_mode : 0, m, d / 4);
+  LFS2_CHECK_LAUNCH("bucket_embed_add");
+  return LFS2_OK;
+}
+
+}  // extern "C"

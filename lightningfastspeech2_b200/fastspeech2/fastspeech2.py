@@ -1,0 +1,368 @@
+"""Host-side mirror of ``litfass.fastspeech2.fastspeech2.FastSpeech2``
+(reference litfass/fastspeech2/fastspeech2.py:45-1323): same constructor kwargs, same
+``forward(targets, inference=False) -> dict`` contract and result keys (:636-784), same
+state_dict layout and checkpoint hooks (:530-634), same optimizer/scheduler recipe
+(:1166-1182).  The mel-generation hot path -- Encoder -> VarianceAdaptor -> Decoder -> mel
+Linear -- runs entirely in the hand-written sm_100a kernels of liblfs2.so.
+
+Out of scope here: dataset construction (pass a prebuilt dataset object or
+``stats=`` / ``phone2id=``), W&B logging, GMM priors, vocoders, FastDiff adaptor, CWT,
+stochastic durations.  Those kwargs are accepted and stored in ``hparams`` so callers'
+code keeps working, and raise NotImplementedError where they would change the path.
+"""
+import argparse
+import inspect
+import multiprocessing
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import ops
+from .loss import FastSpeech2Loss
+from .model import ConformerEncoderLayer, PositionalEncoding, SpeakerEmbedding, VarianceAdaptor
+from .noam import NoamLR
+
+try:  # the real Lightning base class when it is installed (it is not in this image)
+    from pytorch_lightning import LightningModule as _Base
+except Exception:  # pragma: no cover - exercised in this image
+
+    class _Base(nn.Module):
+        """Just enough of pl.LightningModule for FastSpeech2 to be driven by a plain loop."""
+
+        def __init__(self):
+            super().__init__()
+            self.current_epoch = 0
+            self.logged = {}
+
+        @property
+        def device(self):
+            for p in self.parameters():
+                return p.device
+            return torch.device("cpu")
+
+        def save_hyperparameters(self, ignore=()):
+            frame = inspect.currentframe().f_back
+            args, _, _, values = inspect.getargvalues(frame)
+            self._hparams = argparse.Namespace(**{k: values[k] for k in args if k != "self" and k not in ignore})
+
+        @property
+        def hparams(self):
+            return self._hparams
+
+        def log_dict(self, d, **kw):
+            self.logged.update(d)
+
+        @classmethod
+        def load_from_checkpoint(cls, path, strict=True, map_location=None, **kwargs):
+            ckpt = torch.load(path, map_location=map_location or "cpu", weights_only=False)
+            hp = dict(ckpt.get("hyper_parameters", {}))
+            hp.update(kwargs)
+            accepted = inspect.signature(cls.__init__).parameters
+            model = cls(**{k: v for k, v in hp.items() if k in accepted})
+            model.on_load_checkpoint(ckpt)
+            model.load_state_dict(ckpt["state_dict"], strict=strict)
+            return model
+
+
+num_cpus = multiprocessing.cpu_count()
+
+
+class TransformerStack(nn.Module):
+    """Stands in for nn.TransformerEncoder(num_layers) as the reference uses it
+    (fastspeech2.py:249-286, 347-374): a ``layers`` ModuleList driven in order, norm=None.
+    (torch>=2's TransformerEncoder.forward cannot drive ConformerEncoderLayer -- quirk 3.)"""
+
+    def __init__(self, layers):
+        super().__init__()
+        self.layers = nn.ModuleList(layers)
+
+    def forward(self, src, mask=None, src_key_padding_mask=None):
+        out = src
+        for mod in self.layers:
+            out = mod(out, src_mask=mask, src_key_padding_mask=src_key_padding_mask)
+        return out
+
+
+class FastSpeech2(_Base):
+    def __init__(
+        self,
+        train_ds=None,
+        valid_ds=None,
+        lr=1e-04,
+        warmup_steps=4000,
+        batch_size=6,
+        speaker_type="dvector",
+        min_length=0.5,
+        max_length=32,
+        augment_duration=0.1,
+        layer_dropout=0.1,
+        variances=["pitch", "energy", "snr"],
+        variance_levels=["frame", "frame", "frame"],
+        variance_transforms=["cwt", "none", "none"],
+        variance_losses=["mse", "mse", "mse"],
+        variance_nlayers=[5, 5, 5, 5],
+        variance_loss_weights=[5e-2, 5e-2, 5e-2, 5e-2],
+        variance_kernel_size=[3, 3, 3, 3],
+        variance_dropout=[0.5, 0.5, 0.5, 0.5],
+        variance_filter_size=256,
+        variance_nbins=256,
+        variance_depthwise_conv=True,
+        duration_nlayers=2,
+        duration_loss="mse",
+        duration_loss_weight=5e-1,
+        duration_stochastic=False,
+        duration_kernel_size=3,
+        duration_dropout=0.5,
+        duration_filter_size=256,
+        duration_depthwise_conv=True,
+        mel_loss="l1",
+        soft_dtw_gamma=0.1,
+        soft_dtw_chunk_size=256,
+        speaker_embedding_every_layer=False,
+        prior_embedding_every_layer=False,
+        priors=[],
+        mel_loss_weight=1,
+        n_mels=80,
+        sampling_rate=22050,
+        n_fft=1024,
+        win_length=1024,
+        hop_length=256,
+        train_ds_kwargs=None,
+        valid_ds_kwargs=None,
+        encoder_hidden=256,
+        encoder_head=2,
+        encoder_layers=4,
+        encoder_dropout=0.1,
+        encoder_kernel_sizes=[5, 25, 13, 9],
+        encoder_dim_feedforward=None,
+        encoder_conformer=True,
+        encoder_depthwise_conv=True,
+        encoder_conv_filter_size=1024,
+        decoder_hidden=256,
+        decoder_head=2,
+        decoder_layers=4,
+        decoder_dropout=0.1,
+        decoder_kernel_sizes=[17, 21, 9, 13],
+        decoder_dim_feedforward=None,
+        decoder_conformer=True,
+        decoder_depthwise_conv=True,
+        decoder_conv_filter_size=1024,
+        valid_nexamples=10,
+        valid_example_directory=None,
+        variance_early_stopping="none",
+        variance_early_stopping_patience=4,
+        variance_early_stopping_directory="variance_encoders",
+        num_workers=num_cpus,
+        cache_path=None,
+        priors_gmm=False,
+        priors_gmm_max_components=5,
+        priors_gmm_min_samples_per_component=20,
+        priors_gmm_reg_covar=1e-3,
+        priors_gmm_logs=[0, 1, 2, 3],
+        dvector_gmm=False,
+        fastdiff_model=None,
+        fastdiff_schedule=[0, 1],
+        fastdiff_schedule_start=0,
+        fastdiff_schedule_end=20,
+        sort_data_by_length=False,
+        fastdiff_variances=True,
+        fastdiff_speakers=False,
+        fastdiff_speakers_loss_weight=1,
+        # additions for dataset-free construction (synthetic weights / benchmarks)
+        stats=None,
+        phone2id=None,
+        fastdiff_head=False,
+    ):
+        super().__init__()
+        self.lr = lr
+        self.warmup_steps = warmup_steps
+        self.num_workers = num_workers
+        self.valid_nexamples = valid_nexamples
+        self.valid_example_directory = valid_example_directory
+        self.batch_size = batch_size
+        self.save_hyperparameters(ignore=[
+            "train_ds", "valid_ds", "train_ds_kwargs", "valid_ds_kwargs", "valid_nexamples",
+            "valid_example_directory", "batch_size", "variance_early_stopping_directory", "num_workers",
+            "fastdiff_model", "stats", "phone2id", "fastdiff_head"])
+        hp = self.hparams
+
+        # -- what the reference would reject or what is outside the hot path ------------------
+        if fastdiff_variances:
+            raise NotImplementedError("fastdiff_variances=True (FastDiff variance adaptor) is out of scope; "
+                                      "pass fastdiff_variances=False for the VarianceAdaptor named by the path")
+        if fastdiff_model is not None or fastdiff_speakers:
+            raise NotImplementedError("joint FastDiff vocoder / speaker generator")
+        if "dvector" not in speaker_type:
+            raise NotImplementedError("only d-vector speakers work at the reference HEAD (SURVEY 8, quirk 2)")
+        if speaker_embedding_every_layer or prior_embedding_every_layer:
+            raise NotImplementedError("*_embedding_every_layer (TypeError in the reference, quirk 4)")
+        if len(priors) > 0:
+            raise NotImplementedError("prior embeddings (SURVEY 8f N3)")
+        if not (encoder_conformer and decoder_conformer):
+            raise NotImplementedError("plain TransformerEncoderLayer stacks")
+        if encoder_hidden != decoder_hidden:
+            raise NotImplementedError("encoder_hidden != decoder_hidden")
+        self.fastdiff_model = None
+        self.fastdiff_speaker_generator = None
+
+        # -- dataset-derived metadata (reference :236-245); dataset building itself is out of scope
+        if train_ds is not None:
+            self.train_ds = train_ds
+            self.stats = train_ds.stats
+            self.phone2id = train_ds.phone2id
+            if "dvector" in getattr(train_ds, "speaker_type", speaker_type):
+                self.speaker2dvector = getattr(train_ds, "speaker2dvector", {})
+        if valid_ds is not None:
+            self.valid_ds = valid_ds
+        if stats is not None:
+            self.stats = stats
+        if phone2id is not None:
+            self.phone2id = phone2id
+
+        if hasattr(self, "phone2id"):
+            self.phone_embedding = nn.Embedding(len(self.phone2id), hp.encoder_hidden, padding_idx=0)
+
+        def stack(hidden, head, nlayers, ksizes, fsz, dropout, depthwise):
+            return TransformerStack([
+                ConformerEncoderLayer(hidden, head, conv_in=hidden, conv_filter_size=fsz,
+                                      conv_kernel=(ksizes[i], 1), batch_first=True, dropout=dropout,
+                                      conv_depthwise=depthwise)
+                for i in range(nlayers)])
+
+        self.encoder = stack(hp.encoder_hidden, hp.encoder_head, hp.encoder_layers, hp.encoder_kernel_sizes,
+                             hp.encoder_conv_filter_size, hp.encoder_dropout, hp.encoder_depthwise_conv)
+        self.positional_encoding = PositionalEncoding(hp.encoder_hidden, dropout=hp.encoder_dropout)
+        if hasattr(self, "stats"):
+            self.variance_adaptor = self._make_variance_adaptor()
+        self.decoder = stack(hp.decoder_hidden, hp.decoder_head, hp.decoder_layers, hp.decoder_kernel_sizes,
+                             hp.decoder_conv_filter_size, hp.decoder_dropout, hp.decoder_depthwise_conv)
+        self.linear = nn.Linear(hp.decoder_hidden, hp.n_mels)
+        if fastdiff_head:  # same shape as the reference's head (:393-402); feeds only result["fastdiff_var"]
+            self.fastdiff_linear = nn.Sequential(nn.Linear(hp.decoder_hidden, hp.decoder_hidden),
+                                                 nn.Linear(hp.decoder_hidden, hp.n_mels))
+        self.speaker_embedding = SpeakerEmbedding(hp.encoder_hidden, hp.speaker_type)
+
+        loss_weights = {"mel": hp.mel_loss_weight, "duration": hp.duration_loss_weight,
+                        "speakers": hp.fastdiff_speakers_loss_weight}
+        for i, var in enumerate(hp.variances):
+            loss_weights[var] = hp.variance_loss_weights[i]
+        self.loss = FastSpeech2Loss(hp.variances, hp.variance_levels, hp.variance_transforms, hp.variance_losses,
+                                    hp.mel_loss, hp.duration_loss, hp.duration_stochastic, self._max_frames(),
+                                    loss_weights)
+
+    # ------------------------------------------------------------------------------------
+    def _max_frames(self):
+        hp = self.hparams
+        return hp.max_length * hp.sampling_rate / hp.hop_length  # float, 2756.25 by default
+
+    def _make_variance_adaptor(self):
+        hp = self.hparams
+        return VarianceAdaptor(
+            self.stats, hp.variances, hp.variance_levels, hp.variance_transforms, hp.variance_nlayers,
+            hp.variance_kernel_size, hp.variance_dropout, hp.variance_filter_size, hp.variance_nbins,
+            hp.variance_depthwise_conv, hp.duration_nlayers, hp.duration_stochastic, hp.duration_kernel_size,
+            hp.duration_dropout, hp.duration_filter_size, hp.duration_depthwise_conv, hp.encoder_hidden,
+            self._max_frames()).to(self.device)
+
+    # -- checkpoint hooks (reference :530-634) -----------------------------------------------
+    def on_load_checkpoint(self, checkpoint):
+        self.stats = checkpoint["stats"]
+        if not hasattr(self, "variance_adaptor"):
+            self.variance_adaptor = self._make_variance_adaptor()
+        self.phone2id = checkpoint["phone2id"]
+        if not hasattr(self, "phone_embedding"):
+            self.phone_embedding = nn.Embedding(len(self.phone2id), self.hparams.encoder_hidden, padding_idx=0)
+        for key in ("speaker2dvector", "speaker2priors", "speaker_gmms", "dvector_gmms"):
+            if key in checkpoint:
+                setattr(self, key, checkpoint[key])
+        state_dict = checkpoint["state_dict"]
+        if any(k.startswith("fastdiff_linear.") for k in state_dict) and not hasattr(self, "fastdiff_linear"):
+            d = self.hparams.decoder_hidden
+            self.fastdiff_linear = nn.Sequential(nn.Linear(d, d), nn.Linear(d, self.hparams.n_mels))
+        model_state = self.state_dict()
+        changed = False
+        for k in list(state_dict):
+            if k in model_state:
+                if state_dict[k].shape != model_state[k].shape:
+                    print(f"Skip loading parameter: {k}, required shape: {model_state[k].shape}, "
+                          f"loaded shape: {state_dict[k].shape}")
+                    state_dict[k] = model_state[k]
+                    changed = True
+            else:
+                print(f"Dropping parameter {k}")
+                changed = True
+        if changed:
+            checkpoint.pop("optimizer_states", None)
+
+    def on_save_checkpoint(self, checkpoint):
+        checkpoint["stats"] = self.stats
+        checkpoint["phone2id"] = self.phone2id
+        for key in ("speaker2id", "speaker2dvector", "speaker2priors", "speaker_gmms", "dvector_gmms"):
+            if hasattr(self, key):
+                checkpoint[key] = getattr(self, key)
+
+    # -- THE hot path (reference :636-784) ---------------------------------------------------
+    def forward(self, targets, inference=False, force=None, control=None):
+        """``force`` (optional, not in the reference): {"duration_rounded", "bucket_idx":{var:..},
+        "want_idx": bool} teacher-forces / reports the two discrete decisions for parity runs."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise ops._lib.Lfs2Error("FastSpeech2.forward needs the model on a CUDA device: there is no CPU path")
+        hp = self.hparams
+        phones = targets["phones"].to(dev, non_blocking=True).contiguous()
+        speakers = targets["speaker"].to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+        spk = self.speaker_embedding.project(speakers)                       # (B, d)
+        pe = self.positional_encoding.pe
+        if self.training and hp.encoder_dropout > 0:
+            raise NotImplementedError("dropout in training mode")
+        output, src_mask = ops.embed_pe_spk(phones, self.phone_embedding.weight, pe, spk)
+        output = self.encoder(output, src_key_padding_mask=src_mask)
+
+        variance_output = self.variance_adaptor(output, src_mask, targets, inference=inference, force=force,
+                                                control=control)
+        output = ops.add_pe_spk_(variance_output["x"], pe, spk)
+        tgt_mask = variance_output["tgt_mask"]
+        output = self.decoder(output, src_key_padding_mask=tgt_mask)
+        mel = ops.linear(output, self.linear.weight, self.linear.bias)
+
+        result = {
+            "mel": mel,
+            "duration_prediction": variance_output["duration_prediction"],
+            "duration_rounded": variance_output["duration_rounded"],
+            "src_mask": src_mask,
+            "tgt_mask": tgt_mask,
+        }
+        if hasattr(self, "fastdiff_linear") and variance_output["out"] is not None:
+            zero_pe = torch.zeros(1, mel.shape[1], hp.decoder_hidden, device=dev)
+            h = ops.add_pe_spk_(variance_output["out"], zero_pe, spk)
+            h = ops.linear(h, self.fastdiff_linear[0].weight, self.fastdiff_linear[0].bias)
+            h = ops.linear(h, self.fastdiff_linear[1].weight, self.fastdiff_linear[1].bias)
+            result["fastdiff_var"] = h * 0.1
+        for var in hp.variances:
+            result[f"variances_{var}"] = variance_output[f"variances_{var}"]
+            if f"_bucket_{var}" in variance_output:
+                result[f"_bucket_{var}"] = variance_output[f"_bucket_{var}"]
+        return result
+
+    # -- train / validation steps (reference :786-807) ---------------------------------------
+    def training_step(self, batch, batch_idx, optimizer_idx=0):
+        result = self(batch, optimizer_idx)
+        losses = self.loss(result, batch)
+        self.log_dict({f"train/{k}_loss": v.item() for k, v in losses.items()}, batch_size=self.batch_size,
+                      sync_dist=True)
+        return losses["total"]
+
+    def validation_step(self, batch, batch_idx):
+        result = self(batch)
+        losses = self.loss(result, batch)
+        self.log_dict({f"eval/{k}_loss": v.item() for k, v in losses.items()}, batch_size=self.batch_size,
+                      sync_dist=True)
+        return self(batch, inference=True)
+
+    def configure_optimizers(self):
+        self.optimizer = torch.optim.AdamW(self.parameters(), lr=self.hparams.lr, betas=[0.9, 0.98], eps=1e-8,
+                                           weight_decay=0.01)
+        self.scheduler = NoamLR(self.optimizer, self.hparams.warmup_steps)
+        return [self.optimizer], [{"scheduler": self.scheduler, "interval": "step"}]

@@ -1,0 +1,367 @@
+"""Host-side mirror of ``litfass.fastspeech2.model`` (reference litfass/fastspeech2/model.py).
+
+Same class names, constructor signatures and state_dict keys as the reference, so
+reference checkpoints load unchanged and callers (fastspeech2.py, on_load_checkpoint)
+need no edits.  The torch.nn sub-modules (Conv1d, Linear, LayerNorm, MultiheadAttention,
+Embedding) are used ONLY as parameter containers -- that is what pins the key names,
+shapes and default initialisation -- their forward() is never called: every forward here
+launches the hand-written sm_100a kernels of liblfs2.so through ``ops``.
+
+Inference only computes forward; dropout layers of the reference are identity in eval
+mode and with p=0, which is the parity protocol.  Modules raise if dropout
+would be active (train mode with p>0) rather than silently ignoring it.
+"""
+import math
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import ops
+
+
+def _version_key(*tensors):
+    return tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+
+
+class _PackCache:
+    """Kernel-friendly weight repacks, rebuilt when a parameter changes
+    (keyed on data_ptr/_version, so load_state_dict / optimizer steps invalidate them)."""
+
+    def __init__(self):
+        self._key = None
+        self._val = None
+
+    def get(self, params, builder):
+        key = _version_key(*params)
+        if key != self._key:
+            with torch.no_grad():
+                self._val = builder()
+            self._key = key
+        return self._val
+
+
+def _require_inference(module, p, what):
+    if module.training and p > 0:
+        raise NotImplementedError(
+            f"{what}: dropout p={p} in training mode is not implemented by the CUDA path "
+            "(call .eval() or construct with dropout 0)")
+
+
+class PositionalEncoding(nn.Module):
+    """reference model.py:38-55; the add itself is fused into the front-end kernels
+    (ops.embed_pe_spk / ops.add_pe_spk_), forward() here serves stand-alone use."""
+
+    def __init__(self, d_model, max_len=5000, dropout=0.1):
+        super().__init__()
+        self.dropout = nn.Dropout(p=dropout)
+        pe = torch.zeros(max_len, d_model)
+        position = torch.arange(0, max_len, dtype=torch.float).unsqueeze(1)
+        div_term = torch.exp(torch.arange(0, d_model, 2).float() * (-math.log(10000.0) / d_model))
+        pe[:, 0::2] = torch.sin(position * div_term)
+        pe[:, 1::2] = torch.cos(position * div_term)
+        self.register_buffer("pe", pe.unsqueeze(0))
+
+    def forward(self, x):
+        _require_inference(self, self.dropout.p, "PositionalEncoding")
+        zero = torch.zeros(x.shape[0], x.shape[2], device=x.device, dtype=torch.float32)
+        return ops.add_pe_spk_(x.contiguous().clone(), self.pe, zero)
+
+
+class Transpose(nn.Module):
+    """reference model.py:58-64 -- kept for state_dict key compatibility (``.module``)."""
+
+    def __init__(self, module):
+        super().__init__()
+        self.module = module
+
+
+class ConformerEncoderLayer(nn.Module):
+    """FFTBlock, reference model.py:67-122 (post-norm, relu, LayerNorm eps 1e-5).
+
+    Constructor mirrors ``ConformerEncoderLayer(d_model, nhead, conv_in=, conv_filter_size=,
+    conv_kernel=(k1,k2), batch_first=True, dropout=, conv_depthwise=)``."""
+
+    def __init__(self, d_model, nhead, dim_feedforward=2048, dropout=0.1, activation="relu",
+                 layer_norm_eps=1e-5, batch_first=False, norm_first=False, **kwargs):
+        super().__init__()
+        if not batch_first:
+            raise NotImplementedError("batch_first=False")
+        if norm_first:
+            raise NotImplementedError("norm_first=True (the reference never uses it)")
+        if activation not in ("relu", torch.nn.functional.relu):
+            raise NotImplementedError("only relu")
+        conv_in, fsz = kwargs["conv_in"], kwargs["conv_filter_size"]
+        k1, k2 = kwargs["conv_kernel"]
+        self.depthwise = bool(kwargs.get("conv_depthwise", False))
+        self.nhead = nhead
+        self.p_drop = dropout
+        self.eps = layer_norm_eps
+        self.self_attn = nn.MultiheadAttention(d_model, nhead, dropout=dropout, batch_first=True)
+        self.norm1 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        self.norm2 = nn.LayerNorm(d_model, eps=layer_norm_eps)
+        if self.depthwise:
+            self.conv1 = nn.Sequential(nn.Conv1d(conv_in, conv_in, kernel_size=k1, padding="same", groups=conv_in),
+                                       nn.Conv1d(conv_in, fsz, 1))
+            self.conv2 = nn.Sequential(nn.Conv1d(fsz, fsz, kernel_size=k2, padding="same", groups=conv_in),
+                                       nn.Conv1d(fsz, conv_in, 1))
+        else:
+            self.conv1 = nn.Conv1d(conv_in, fsz, kernel_size=k1, padding="same")
+            self.conv2 = nn.Conv1d(fsz, conv_in, kernel_size=k2, padding="same")
+        self._pack = _PackCache()
+
+    # -- weight repacks -------------------------------------------------------------------
+    def _build_pack(self):
+        p = {}
+        if self.depthwise:
+            dw, pw = self.conv1[0], self.conv1[1]
+            gc, pw2 = self.conv2[0], self.conv2[1]
+            if gc.kernel_size[0] != 1:
+                raise NotImplementedError("grouped conv2.0 with kernel > 1")
+            d, fsz = dw.weight.shape[0], pw.weight.shape[0]
+            g = fsz // d
+            p["dw_wt"] = dw.weight[:, 0, :].t().contiguous()           # (k, d)
+            p["pw1_w"] = pw.weight[:, :, 0].contiguous()               # (F, d)
+            # conv2.0 (F->F, groups=d, 1x1) followed by conv2.1 (F->d, 1x1) with nothing in
+            # between is one linear map: W_eff = W21 . blockdiag(W20), b_eff = W21.b20 + b21
+            w21 = pw2.weight[:, :, 0].double().reshape(d, d, g)        # (n, G, o)
+            w20 = gc.weight[:, :, 0].double().reshape(d, g, g)         # (G, o, i)
+            p["w_eff"] = torch.einsum("ngo,goi->ngi", w21, w20).reshape(d, fsz).float().contiguous()
+            p["b_eff"] = (pw2.weight[:, :, 0].double() @ gc.bias.double() + pw2.bias.double()).float().contiguous()
+        else:
+            fsz, d, k1 = self.conv1.weight.shape
+            p["c1_wp"] = self.conv1.weight.permute(0, 2, 1).reshape(fsz, k1 * d).contiguous()
+            d2, f2, k2 = self.conv2.weight.shape
+            p["c2_wp"] = self.conv2.weight.permute(0, 2, 1).reshape(d2, k2 * f2).contiguous()
+        return p
+
+    def _packed(self):
+        params = [q for q in self.conv1.parameters()] + [q for q in self.conv2.parameters()]
+        return self._pack.get(params, self._build_pack)
+
+    def forward(self, src, src_mask=None, src_key_padding_mask=None):
+        if src_mask is not None:
+            raise NotImplementedError("attention src_mask (the reference never passes one)")
+        _require_inference(self, self.p_drop, "ConformerEncoderLayer")
+        x = src
+        sa = self.self_attn
+        qkv = ops.linear(x, sa.in_proj_weight, sa.in_proj_bias)
+        ctx = ops.attention(qkv, src_key_padding_mask, self.nhead)
+        a = ops.linear(ctx, sa.out_proj.weight, sa.out_proj.bias)
+        x1 = ops.add_layernorm(x, a, self.norm1.weight, self.norm1.bias, self.eps)
+        y = self._ff_block(x1)
+        return ops.add_layernorm(x1, y, self.norm2.weight, self.norm2.bias, self.eps)
+
+    def _ff_block(self, x):
+        p = self._packed()
+        if self.depthwise:
+            u = ops.dwconv1d(x, p["dw_wt"], self.conv1[0].bias)
+            v = ops.linear(u, p["pw1_w"], self.conv1[1].bias, relu=True)
+            return ops.linear(v, p["w_eff"], p["b_eff"])
+        v = ops.conv1d_dense(x, p["c1_wp"], self.conv1.bias, self.conv1.kernel_size[0], relu=True)
+        return ops.conv1d_dense(v, p["c2_wp"], self.conv2.bias, self.conv2.kernel_size[0])
+
+
+class SpeakerEmbedding(nn.Module):
+    """reference model.py:125-143.  Only d-vector speakers work at the reference HEAD
+    (SURVEY 8 quirk 2); forward returns the (B, d) term, broadcast over time is fused
+    into the consumer kernels when called through FastSpeech2.forward."""
+
+    def __init__(self, embedding_dim, speaker_type, nspeakers=None):
+        super().__init__()
+        self.speaker_type = speaker_type
+        self.embedding_dim = embedding_dim
+        if "dvector" in speaker_type:
+            self.projection = nn.Linear(256, embedding_dim)
+            self.has_projection = True
+        elif speaker_type == "id":
+            self.speaker_embedding = nn.Embedding(nspeakers, embedding_dim)
+        self.relu = nn.ReLU()
+
+    def project(self, x):
+        if not getattr(self, "has_projection", False):
+            raise NotImplementedError("speaker_type='id' (raises AttributeError in the reference too)")
+        return ops.speaker_proj(x.contiguous(), self.projection.weight, self.projection.bias)
+
+    def forward(self, x, input_length, output_shape):
+        out = self.project(x)
+        return out.reshape(-1, 1, output_shape).expand(-1, input_length, -1)
+
+
+class VarianceConvolutionLayer(nn.Module):
+    """reference model.py:524-561: Transpose(conv) -> ReLU -> LayerNorm(filter) -> Dropout."""
+
+    def __init__(self, in_channels, filter_size, kernel_size, dropout, depthwise):
+        super().__init__()
+        self.depthwise = depthwise
+        self.kernel_size = kernel_size
+        if not depthwise:
+            conv = nn.Conv1d(in_channels, filter_size, kernel_size, padding=(kernel_size - 1) // 2)
+        else:
+            conv = nn.Sequential(
+                nn.Conv1d(in_channels, in_channels, kernel_size, padding=(kernel_size - 1) // 2, groups=in_channels),
+                nn.Conv1d(in_channels, filter_size, 1))
+        self.layers = nn.Sequential(Transpose(conv), nn.ReLU(), nn.LayerNorm(filter_size), nn.Dropout(dropout))
+        self._pack = _PackCache()
+
+    def _build_pack(self):
+        conv = self.layers[0].module
+        if self.depthwise:
+            return {"dw_wt": conv[0].weight[:, 0, :].t().contiguous(), "pw_w": conv[1].weight[:, :, 0].contiguous()}
+        f, d, k = conv.weight.shape
+        return {"wp": conv.weight.permute(0, 2, 1).reshape(f, k * d).contiguous()}
+
+    def forward(self, x):
+        _require_inference(self, self.layers[3].p, "VarianceConvolutionLayer")
+        conv, ln = self.layers[0].module, self.layers[2]
+        p = self._pack.get(list(conv.parameters()), self._build_pack)
+        if self.depthwise:
+            u = ops.dwconv1d(x, p["dw_wt"], conv[0].bias)
+            h = ops.linear(u, p["pw_w"], conv[1].bias, relu=True)
+        else:
+            h = ops.conv1d_dense(x, p["wp"], conv.bias, self.kernel_size, relu=True)
+        return ops.add_layernorm(h, None, ln.weight, ln.bias, ln.eps)
+
+
+class VariancePredictor(nn.Module):
+    """reference model.py:482-522."""
+
+    def __init__(self, nlayers, in_channels, filter_size, kernel_size, dropout, depthwise=False, cwt=False):
+        super().__init__()
+        if cwt:
+            raise NotImplementedError("cwt variance transform (needs scipy.signal.cwt, removed upstream)")
+        self.layers = nn.Sequential(*[
+            VarianceConvolutionLayer(in_channels, filter_size, kernel_size, dropout, depthwise)
+            for _ in range(nlayers)])
+        self.cwt = cwt
+        self.linear = nn.Linear(filter_size, 1)
+
+    def forward(self, x, mask=None, return_conv=False):
+        z = x
+        for layer in self.layers:
+            z = layer(z)
+        out = ops.rowdot_mask(z, self.linear.weight, self.linear.bias, mask)
+        return (out, z) if return_conv else out
+
+
+class VarianceEncoder(nn.Module):
+    """reference model.py:373-461 (non-CWT branch)."""
+
+    def __init__(self, nlayers, in_channels, filter_size, kernel_size, dropout, depthwise, min, max, mean, std,
+                 nbins, cwt):
+        super().__init__()
+        if cwt:
+            raise NotImplementedError("cwt variance transform")
+        self.cwt = cwt
+        self.predictor = VariancePredictor(nlayers, in_channels, filter_size, kernel_size, dropout, depthwise, cwt)
+        self.bins = nn.Parameter(torch.linspace(min, max, nbins - 1), requires_grad=False)
+        self.embedding = nn.Embedding(nbins, in_channels)
+        self.mean = mean
+        self.std = std
+
+    def encode_(self, x, tgt, mask, control=1.0, acc=None, acc_init=False, forced_idx=None, want_idx=False):
+        """Fused form used by VarianceAdaptor: predicts, bucketizes and does ``x += emb``
+        in place (and ``acc (+)= emb``).  Returns (prediction, bucket indices or None)."""
+        prediction = self.predictor(x, mask)
+        val = prediction if tgt is None else tgt.to(device=x.device, dtype=torch.float32).contiguous()
+        idx = ops.bucket_embed_add_(x, val, self.std, self.mean, self.bins, self.embedding.weight,
+                                    idx_forced=forced_idx, acc=acc, acc_init=acc_init, want_idx=want_idx)
+        if tgt is None and control != 1.0:
+            prediction = prediction * control
+        return prediction, idx
+
+    def forward(self, x, tgt, mask, control=1.0):
+        """Reference signature: returns (prediction, embedding)."""
+        # stand-alone use: compute the embedding into a zero tensor without touching x
+        emb = torch.zeros_like(x)
+        prediction = self.predictor(x, mask)
+        val = prediction if tgt is None else tgt.to(device=x.device, dtype=torch.float32).contiguous()
+        ops.bucket_embed_add_(emb, val, self.std, self.mean, self.bins, self.embedding.weight)
+        if tgt is None:
+            prediction = prediction * control
+        return prediction, emb
+
+
+class LengthRegulator(nn.Module):
+    """reference model.py:344-370."""
+
+    def __init__(self, pad_to_multiple_of=None):
+        super().__init__()
+        if pad_to_multiple_of is not None:
+            raise NotImplementedError("pad_to_multiple_of (only the FastDiff adaptor uses it)")
+        self.pad_to_multiple_of = pad_to_multiple_of
+
+    def forward(self, x, durations, max_length=None):
+        return ops.length_regulate(x.contiguous(), durations.to(x.device), max_length)
+
+
+class VarianceAdaptor(nn.Module):
+    """reference model.py:167-341."""
+
+    def __init__(self, stats, variances, variance_levels, variance_transforms, variance_nlayers,
+                 variance_kernel_size, variance_dropout, variance_filter_size, variance_nbins,
+                 variance_depthwise_conv, duration_nlayers, duration_stochastic, duration_kernel_size,
+                 duration_dropout, duration_filter_size, duration_depthwise_conv, encoder_hidden, max_length):
+        super().__init__()
+        self.variances = variances
+        self.variance_levels = variance_levels
+        self.variance_transforms = variance_transforms
+        self.duration_stochastic = duration_stochastic
+        self.max_length = max_length
+        if duration_stochastic:
+            raise NotImplementedError("stochastic duration predictor (RNG-dependent; out of scope)")
+        self.duration_predictor = VariancePredictor(duration_nlayers, encoder_hidden, duration_filter_size,
+                                                    duration_kernel_size, duration_dropout, duration_depthwise_conv)
+        self.length_regulator = LengthRegulator()
+        encoders = {}
+        for i, var in enumerate(variances):
+            encoders[var] = VarianceEncoder(variance_nlayers[i], encoder_hidden, variance_filter_size,
+                                            variance_kernel_size[i], variance_dropout[i], variance_depthwise_conv,
+                                            stats[var]["min"], stats[var]["max"], stats[var]["mean"],
+                                            stats[var]["std"], variance_nbins,
+                                            cwt=variance_transforms[i] == "cwt")
+        self.encoders = nn.ModuleDict(encoders)
+        self.frozen_components = []
+
+    def freeze(self, component):
+        mod = self.duration_predictor if component == "duration" else self.encoders[component]
+        for param in mod.parameters():
+            param.requires_grad = False
+        self.frozen_components.append(component)
+
+    def forward(self, x, src_mask, targets, inference=False, tf_ratio=1.0, oracles=[], force=None, control=None):
+        force = force or {}
+        control = control or {}
+        if any(level == "phone" for level in self.variance_levels):
+            raise NotImplementedError("phone-level variances")
+        duration_pred = self.duration_predictor(x, src_mask)
+        result = {}
+        tf_val = np.random.uniform(0, 1) <= tf_ratio  # reference model.py:272
+        if "duration_rounded" in force:
+            duration_rounded = force["duration_rounded"].to(x.device)
+        elif not inference:
+            duration_rounded = targets["duration"].to(x.device)
+        else:
+            duration_rounded = ops.duration_round_guard(duration_pred, src_mask)
+
+        x, tgt_mask = self.length_regulator(x, duration_rounded, self.max_length)
+
+        out_val = torch.empty_like(x) if len(self.variances) else None
+        for i, var in enumerate(self.variances):
+            teacher = (not inference and tf_val) or var in oracles
+            tgt = targets[f"variances_{var}"] if teacher else None
+            forced = force.get("bucket_idx", {}).get(var)
+            pred, idx = self.encoders[var].encode_(
+                x, tgt, tgt_mask, control.get(var, 1.0), acc=out_val, acc_init=(i == 0),
+                forced_idx=None if forced is None else forced.to(x.device),
+                want_idx=force.get("want_idx", False))
+            result[f"variances_{var}"] = pred
+            if idx is not None:
+                result[f"_bucket_{var}"] = idx
+
+        result["x"] = x
+        result["duration_prediction"] = duration_pred
+        result["duration_rounded"] = duration_rounded
+        result["tgt_mask"] = tgt_mask
+        result["out"] = out_val
+        return result

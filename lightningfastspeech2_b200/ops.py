@@ -1,0 +1,180 @@
+"""Tensor-level wrappers over the C ABI (include/lfs2.h).
+
+PyTorch is plumbing here: it owns device memory and the stream; every function below
+validates shapes/dtypes, allocates outputs with torch.empty and hands raw pointers to the
+hand-written kernels.  Nothing in this file computes on the host or falls back to ATen.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+LN_EPS = 1e-5
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _s():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t, dtype, name, ndim=None):
+    if not (torch.is_tensor(t) and t.is_cuda):
+        raise _lib.Lfs2Error(f"{name}: expected a CUDA tensor (no CPU fallback exists)")
+    if t.dtype != dtype:
+        raise TypeError(f"{name}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{name}: tensor must be contiguous")
+    if ndim is not None and t.dim() != ndim:
+        raise ValueError(f"{name}: expected {ndim} dims, got {tuple(t.shape)}")
+    return t
+
+
+def speaker_proj(dvec, w, b):
+    _chk(dvec, torch.float32, "speaker", 2); _chk(w, torch.float32, "projection.weight", 2)
+    out = torch.empty(dvec.shape[0], w.shape[0], device=dvec.device, dtype=torch.float32)
+    _lib.check(_lib.lib().lfs2_speaker_proj(_p(dvec), _p(w), _p(b), _p(out), dvec.shape[0], dvec.shape[1],
+                                            w.shape[0], _s()), "lfs2_speaker_proj")
+    return out
+
+
+def embed_pe_spk(phones, emb, pe, spk):
+    _chk(phones, torch.int64, "phones", 2); _chk(emb, torch.float32, "phone_embedding.weight", 2)
+    b, t = phones.shape
+    d = emb.shape[1]
+    if t > pe.shape[-2]:
+        raise ValueError(f"sequence length {t} exceeds the positional table ({pe.shape[-2]})")
+    x = torch.empty(b, t, d, device=phones.device, dtype=torch.float32)
+    mask = torch.empty(b, t, device=phones.device, dtype=torch.bool)
+    _lib.check(_lib.lib().lfs2_embed_pe_spk(_p(phones), _p(emb), _p(pe), _p(spk), _p(x), _p(mask), b, t, d,
+                                            emb.shape[0], _s()), "lfs2_embed_pe_spk")
+    return x, mask
+
+
+def add_pe_spk_(x, pe, spk):
+    _chk(x, torch.float32, "x", 3)
+    b, t, d = x.shape
+    if t > pe.shape[-2]:
+        raise ValueError(f"sequence length {t} exceeds the positional table ({pe.shape[-2]})")
+    _lib.check(_lib.lib().lfs2_add_pe_spk(_p(x), _p(pe), _p(spk), b, t, d, _s()), "lfs2_add_pe_spk")
+    return x
+
+
+def linear(a, w, bias, relu=False, out=None):
+    """a (..., k) . w (n, k)^T + bias -> (..., n)"""
+    _chk(a, torch.float32, "linear input"); _chk(w, torch.float32, "linear weight", 2)
+    k = a.shape[-1]
+    m = a.numel() // k
+    n = w.shape[0]
+    if w.shape[1] != k:
+        raise ValueError(f"linear: weight {tuple(w.shape)} does not match input features {k}")
+    if out is None:
+        out = torch.empty(*a.shape[:-1], n, device=a.device, dtype=torch.float32)
+    _lib.check(_lib.lib().lfs2_linear(_p(a), _p(w), _p(bias), _p(out), m, n, k, int(relu), _s()), "lfs2_linear")
+    return out
+
+
+def conv1d_dense(x, wp, bias, ksize, relu=False):
+    """x (B,T,d), wp (n, ksize*d) tap-major -> (B,T,n)"""
+    _chk(x, torch.float32, "conv input", 3); _chk(wp, torch.float32, "conv weight", 2)
+    b, t, d = x.shape
+    n = wp.shape[0]
+    if wp.shape[1] != ksize * d:
+        raise ValueError("conv1d_dense: packed weight shape mismatch")
+    out = torch.empty(b, t, n, device=x.device, dtype=torch.float32)
+    _lib.check(_lib.lib().lfs2_conv1d_dense(_p(x), _p(wp), _p(bias), _p(out), b, t, d, n, ksize, int(relu), _s()),
+               "lfs2_conv1d_dense")
+    return out
+
+
+def dwconv1d(x, wt, bias):
+    """x (B,T,d), wt (ksize, d) -> (B,T,d)"""
+    _chk(x, torch.float32, "dwconv input", 3); _chk(wt, torch.float32, "dwconv weight", 2)
+    b, t, d = x.shape
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().lfs2_dwconv1d(_p(x), _p(wt), _p(bias), _p(out), b, t, d, wt.shape[0], _s()),
+               "lfs2_dwconv1d")
+    return out
+
+
+def attention(qkv, kpm, nhead):
+    """qkv (B,T,3d) packed [q|k|v], kpm (B,T) bool True=PAD -> ctx (B,T,d)"""
+    _chk(qkv, torch.float32, "qkv", 3)
+    b, t, d3 = qkv.shape
+    d = d3 // 3
+    if kpm is not None:
+        _chk(kpm, torch.bool, "key_padding_mask", 2)
+    ctx = torch.empty(b, t, d, device=qkv.device, dtype=torch.float32)
+    _lib.check(_lib.lib().lfs2_attention(_p(qkv), _p(kpm), _p(ctx), b, t, d, nhead, _s()), "lfs2_attention")
+    return ctx
+
+
+def add_layernorm(x, y, gamma, beta, eps=LN_EPS):
+    _chk(x, torch.float32, "layernorm input")
+    if y is not None:
+        _chk(y, torch.float32, "layernorm residual")
+    d = x.shape[-1]
+    m = x.numel() // d
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().lfs2_add_layernorm(_p(x), _p(y), _p(gamma), _p(beta), _p(out), m, d, eps, _s()),
+               "lfs2_add_layernorm")
+    return out
+
+
+def rowdot_mask(z, w, bias, mask):
+    _chk(z, torch.float32, "predictor hidden", 3)
+    b, t, f = z.shape
+    out = torch.empty(b, t, device=z.device, dtype=torch.float32)
+    _lib.check(_lib.lib().lfs2_rowdot_mask(_p(z), _p(w), _p(bias), _p(mask), _p(out), b * t, f, _s()),
+               "lfs2_rowdot_mask")
+    return out
+
+
+def bucket_embed_add_(x, val, std, mean, bins, emb, idx_forced=None, acc=None, acc_init=False, want_idx=False):
+    _chk(x, torch.float32, "x", 3)
+    b, t, d = x.shape
+    if idx_forced is not None:
+        _chk(idx_forced, torch.int64, "forced bucket indices")
+    else:
+        _chk(val, torch.float32, "variance values")
+    idx_out = torch.empty(b, t, device=x.device, dtype=torch.int64) if want_idx else None
+    mode = 0 if acc is None else (1 if acc_init else 2)
+    _lib.check(_lib.lib().lfs2_bucket_embed_add(_p(x), _p(val), float(std), float(mean), _p(bins),
+                                                emb.shape[0], _p(emb), _p(idx_forced), _p(idx_out), _p(acc), mode,
+                                                b * t, d, _s()), "lfs2_bucket_embed_add")
+    return idx_out
+
+
+def duration_round_guard(log_dur, src_mask):
+    _chk(log_dur, torch.float32, "duration_prediction", 2); _chk(src_mask, torch.bool, "src_mask", 2)
+    dur = torch.empty(log_dur.shape, device=log_dur.device, dtype=torch.int32)
+    _lib.check(_lib.lib().lfs2_duration_round_guard(_p(log_dur), _p(src_mask), _p(dur), log_dur.shape[0],
+                                                    log_dur.shape[1], _s()), "lfs2_duration_round_guard")
+    return dur
+
+
+def length_regulate(x, durations, max_length):
+    """LengthRegulator.forward: x (B,Tp,d) any dtype, durations (B,Tp) int32/int64 ->
+    (out (B,L,d), mask (B,L) bool).  One host read-back (the maximum length)."""
+    if not (x.is_cuda and x.is_contiguous() and x.dim() == 3):
+        raise _lib.Lfs2Error("length_regulate: x must be a contiguous CUDA (B,Tp,d) tensor")
+    if durations.dtype not in (torch.int32, torch.int64):
+        raise TypeError("length_regulate: durations must be int32 or int64")
+    durations = durations.contiguous()
+    b, tp, d = x.shape
+    dev = x.device
+    cum = torch.empty(b, tp, device=dev, dtype=torch.int64)
+    lengths = torch.empty(b, device=dev, dtype=torch.int64)
+    mx = torch.empty(1, device=dev, dtype=torch.int64)
+    _lib.check(_lib.lib().lfs2_length_regulate_scan(_p(durations), int(durations.dtype == torch.int64), _p(cum),
+                                                    _p(lengths), _p(mx), b, tp, _s()), "lfs2_length_regulate_scan")
+    longest = int(mx.item())  # the single device->host sync of the path
+    l = min(longest, int(max_length)) if max_length is not None else longest
+    out = torch.empty(b, l, d, device=dev, dtype=x.dtype)
+    mask = torch.empty(b, l, device=dev, dtype=torch.bool)
+    _lib.check(_lib.lib().lfs2_length_regulate_scatter(_p(x), _p(cum), _p(lengths), _p(out), _p(mask), b, tp, l,
+                                                       d * x.element_size(), _s()), "lfs2_length_regulate_scatter")
+    return out, mask

@@ -1,0 +1,112 @@
+"""CPU-side checks of the boundary: the C-ABI library loads, exports every symbol that
+include/lfs2.h declares, and the host mirror keeps the reference's state_dict layout.
+No compute calls are made (no GPU here)."""
+import os
+import re
+
+import pytest
+import torch
+
+from lightningfastspeech2_b200 import _lib, configs
+from lightningfastspeech2_b200.fastspeech2.fastspeech2 import FastSpeech2
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "lfs2.h")).read()
+    return sorted(set(re.findall(r"LFS2_API\s+[\w\s\*]+?\b(lfs2_\w+)\s*\(", src)))
+
+
+def test_header_and_binding_agree():
+    declared = _declared()
+    assert len(declared) >= 15
+    bound = set(_lib.SIGNATURES) | {"lfs2_last_error"}
+    assert set(declared) == bound, (set(declared) ^ bound)
+
+
+def test_library_exports_every_declared_symbol():
+    from lightningfastspeech2_b200 import build
+
+    build.build()
+    h = _lib.lib()
+    for name in _declared():
+        assert hasattr(h, name), name
+    assert h.lfs2_version() >= 100
+    assert isinstance(h.lfs2_last_error(), bytes)
+
+
+def test_invalid_args_are_reported_not_thrown():
+    h = _lib.lib()
+    rc = h.lfs2_linear(None, None, None, None, 4, 4, 16, 0, None)
+    assert rc == -1
+    assert b"linear" in h.lfs2_last_error()
+    with pytest.raises(_lib.Lfs2Error):
+        _lib.check(rc, "lfs2_linear")
+
+
+def test_no_cpu_fallback():
+    from lightningfastspeech2_b200 import ops
+
+    with pytest.raises(_lib.Lfs2Error):
+        ops.linear(torch.zeros(4, 16), torch.zeros(8, 16), torch.zeros(8))
+
+
+def _mk(preset):
+    kw = configs.PRESETS[preset]
+    stats = {v: {"min": -3.0, "max": 3.0, "mean": 0.0, "std": 1.0} for v in kw["variances"]}
+    return FastSpeech2(stats=stats, phone2id={f"p{i}": i for i in range(80)}, fastdiff_head=True, num_workers=0, **kw)
+
+
+@pytest.mark.parametrize("preset,golden", [("C1", "c1_infer"), ("C2", "c2_small_infer"),
+                                           ("TINY_DW", "tiny_dw_infer"), ("TINY_DENSE", "tiny_dense_infer")])
+def test_state_dict_layout_matches_reference(golden_dir, preset, golden):
+    g = torch.load(os.path.join(golden_dir, golden + ".pt"), weights_only=False)
+    sd = _mk(preset).state_dict()
+    assert set(sd) == set(g["shapes"])
+    for k, v in sd.items():
+        assert tuple(v.shape) == tuple(g["shapes"][k]), k
+
+
+def test_param_counts_match_survey():
+    for preset, count in (("C1", 24518737), ("C2", 7436881), ("C3", 75061329)):
+        m = _mk(preset)
+        n = sum(p.numel() for p in m.parameters()) - sum(p.numel() for p in m.fastdiff_linear.parameters())
+        assert n == count, preset
+
+
+def test_unsupported_configs_raise():
+    with pytest.raises(NotImplementedError):
+        FastSpeech2(stats={}, phone2id={"a": 0}, num_workers=0)  # reference default fastdiff_variances=True
+    with pytest.raises(NotImplementedError):
+        FastSpeech2(stats={}, phone2id={"a": 0}, num_workers=0, **dict(configs.C2, speaker_type="id"))
+
+
+def test_conv2_fold_is_exact_linear_map():
+    """W_eff/b_eff (grouped 1x1 conv folded into the following pointwise conv) reproduce
+    conv2 of the reference layer on CPU."""
+    from lightningfastspeech2_b200.fastspeech2.model import ConformerEncoderLayer
+
+    torch.manual_seed(0)
+    layer = ConformerEncoderLayer(32, 2, conv_in=32, conv_filter_size=128, conv_kernel=(5, 1), batch_first=True,
+                                  dropout=0.0, conv_depthwise=True)
+    p = layer._build_pack()
+    v = torch.randn(3, 128, 11)
+    ref = layer.conv2(v)
+    got = torch.einsum("nf,bft->bnt", p["w_eff"], v) + p["b_eff"][None, :, None]
+    assert (ref - got).abs().max() < 1e-5
+
+
+def test_noam_and_optimizer_recipe():
+    m = _mk("TINY_DW")
+    (opt,), (sched,) = m.configure_optimizers()
+    g = opt.param_groups[0]
+    assert g["betas"] == [0.9, 0.98] or tuple(g["betas"]) == (0.9, 0.98)
+    assert g["eps"] == 1e-8 and g["weight_decay"] == 0.01
+    assert sched["interval"] == "step"
+    from oracle import fs2_oracle as O
+
+    for step in (1, 10, 4000, 10000):
+        from lightningfastspeech2_b200.fastspeech2.noam import noam_scale
+
+        assert noam_scale(step, 4000) == pytest.approx(O.noam_scale(step, 4000))

@@ -1,0 +1,98 @@
+"""End-to-end mel parity of FastSpeech2.forward on the GPU against (a) the committed
+reference goldens and (b) the oracle on larger seeded batches.
+
+Tolerance (BASELINE.json north_star): LengthRegulator indices bit-exact; mel within
+1e-3 abs (fp32 mode) on every position the reference defines.  Discrete decisions
+(rounded durations, bucket indices) are compared exactly; should they flip, the
+comparison is repeated with the reference's decisions forced."""
+import os
+
+import pytest
+import torch
+
+from lightningfastspeech2_b200 import configs, synthetic
+from lightningfastspeech2_b200.fastspeech2.fastspeech2 import FastSpeech2
+from oracle import fs2_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+MEL_TOL = 1e-3
+
+
+def build(preset, seed, stats=None, shapes=None):
+    kw = configs.PRESETS[preset]
+    hp = configs.resolve(kw)
+    st = {v: dict(stats or {"min": -3.0, "max": 3.0, "mean": 0.0, "std": 1.0}) for v in hp["variances"]}
+    model = FastSpeech2(stats=st, phone2id={f"p{i}": i for i in range(80)}, fastdiff_head=True, num_workers=0, **kw)
+    sd = synthetic.fill_state_dict(shapes or model.state_dict(), seed=seed, stats=stats)
+    model.load_state_dict(sd, strict=True)
+    hp["stats"] = st
+    return model.eval().to(DEV), sd, hp
+
+
+def compare(model, ref, batch, hp):
+    with torch.no_grad():
+        r = model(batch, inference=True, force={"want_idx": True})
+    flips_d = (r["duration_rounded"].cpu() != ref["duration_rounded"]).sum().item()
+    flips_b = 0
+    same_shape = r["mel"].shape == ref["mel"].shape
+    if same_shape:
+        flips_b = sum((r[f"_bucket_{v}"].cpu() != ref[f"_bucket_{v}"]).sum().item() for v in hp["variances"])
+    if flips_d or flips_b or not same_shape:
+        force = {"duration_rounded": ref["duration_rounded"],
+                 "bucket_idx": {v: ref[f"_bucket_{v}"] for v in hp["variances"]}, "want_idx": True}
+        with torch.no_grad():
+            r = model(batch, inference=True, force=force)
+    return r, flips_d, flips_b
+
+
+@pytest.mark.parametrize("name", ["c1_infer", "c2_small_infer"])
+def test_against_reference_goldens(golden_dir, name):
+    g = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+    model, sd, hp = build(g["preset"], g["seed"], g["stats"], g["shapes"])
+    ref = dict(g["out"])
+    for v in hp["variances"]:
+        ref[f"_bucket_{v}"] = g["bucket_idx"][v]
+    r, flips_d, flips_b = compare(model, ref, g["batch"], hp)
+    assert flips_d == 0 and flips_b == 0, (flips_d, flips_b)
+    assert r["duration_rounded"].dtype == torch.int32
+    assert torch.equal(r["tgt_mask"].cpu(), ref["tgt_mask"])
+    assert torch.equal(r["src_mask"].cpu(), ref["src_mask"])
+    err = (r["mel"].cpu() - ref["mel"]).abs()
+    assert err.max() < MEL_TOL, float(err.max())  # all positions, PAD rows included
+    assert (r["duration_prediction"].cpu() - ref["duration_prediction"]).abs().max() < 1e-4
+    for v in hp["variances"]:
+        assert (r[f"variances_{v}"].cpu() - ref[f"variances_{v}"]).abs().max() < 1e-4
+    assert (r["fastdiff_var"].cpu() - ref["fastdiff_var"]).abs().max() < 1e-4
+    if g["out64_mel"] is not None:  # error attribution against the fp64 reference
+        assert (r["mel"].cpu().double() - g["out64_mel"]).abs().max() < MEL_TOL
+
+
+@pytest.mark.parametrize("preset,bsz,lo,hi,seed", [("C2", 8, 32, 160, 3), ("C3", 3, 20, 70, 4), ("C1", 2, 40, 90, 5)])
+def test_against_oracle(preset, bsz, lo, hi, seed):
+    model, sd, hp = build(preset, seed)
+    batch = synthetic.make_batch(bsz, lo, hi, seed=seed)
+    ref = O.forward(sd, hp, batch, inference=True)
+    r, flips_d, flips_b = compare(model, ref, batch, hp)
+    total_b = sum(ref[f"_bucket_{v}"].numel() for v in hp["variances"])
+    assert flips_d <= 1 and flips_b <= max(2, total_b // 2000), (flips_d, flips_b)
+    assert torch.equal(r["tgt_mask"].cpu(), ref["tgt_mask"])
+    err = (r["mel"].cpu() - ref["mel"]).abs()
+    assert err.max() < MEL_TOL, float(err.max())
+    assert (r["_bucket_%s" % hp["variances"][0]].cpu() == ref["_bucket_%s" % hp["variances"][0]]).all()
+
+
+def test_deterministic_and_forward_teacher_forced():
+    model, sd, hp = build("C2", 6)
+    batch = synthetic.add_train_targets(synthetic.make_batch(4, 16, 48, seed=6), hp["variances"], seed=6)
+    with torch.no_grad():
+        r1 = model(batch, inference=False)
+        r2 = model(batch, inference=False)
+    assert torch.equal(r1["mel"], r2["mel"])
+    ref = O.forward(sd, hp, batch, inference=False)
+    assert torch.equal(r1["duration_rounded"].cpu(), batch["duration"])
+    assert (r1["mel"].cpu() - ref["mel"]).abs().max() < MEL_TOL
+    ls = model.loss(r1, batch)
+    lo = O.loss(hp, ref, batch)
+    for k in lo:
+        assert abs(float(ls[k]) - float(lo[k])) < 1e-4 * max(1.0, abs(float(lo[k]))), k
