@@ -1,0 +1,336 @@
+#!/usr/bin/env python
+"""bench.py -- synthesis throughput of the B200-native mel-generation path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl lfs2|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], "C2"): LightSpeech depthwise-separable FastSpeech2
+(reference constructor defaults, 2 frame-level variances, 7.4 M params), batch of 64
+synthetic utterances with 32..512 phonemes, `model(batch, inference=True)`.
+One step = one forward of the whole hot path (Encoder -> VarianceAdaptor incl.
+LengthRegulator -> Decoder -> mel Linear) over the batch.  Metric = valid mel frames
+((~tgt_mask).sum()) per second, whole job (all ranks).  N>1 = one process per GPU, each
+rank synthesising its own 64-utterance shard (weak scaling, no data-path collective).
+
+Keys beyond the base contract: `roofline` (dominant kernel, CUDA-event timed inside this
+script), `cpu_baseline` (the oracle port on host cores, bounded sample), `e2e` (same
+metric through the public module API with HOST inputs: pinned H2D + D2H of the mel inside
+the timed region).  `--impl reference` times the CPU port (oracle/) of the reference path.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from lightningfastspeech2_b200 import configs, synthetic  # noqa: E402
+
+METRIC = "valid mel-frames/sec (synthesis)"
+UNIT = "mel-frames/s"
+PRESET = "C2"
+BATCH, MIN_LEN, MAX_LEN = 64, 32, 512
+WORKLOAD = (f"C2 LightSpeech depthwise FastSpeech2 (7.4M params) synthesis, batch={BATCH} utterances/GPU, "
+            f"phoneme len U[{MIN_LEN},{MAX_LEN}], fp32-parity mode")
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm": d["hbm_gbs"], "tensor": d["bf16_tflops"], "tensor_sustained": d["bf16_tflops_sustained"],
+                "src": "measured"}
+    return {"hbm": 6650.0, "tensor": 1590.0, "tensor_sustained": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.path = f"/tmp/lfs2_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in open(self.path):
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if sm:
+            top = sorted(sm)[len(sm) // 2:]  # samples under load = upper half
+            out = {"sm_mhz": statistics.median(top), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    return rank, world, local
+
+
+def build_model(device):
+    from lightningfastspeech2_b200.fastspeech2.fastspeech2 import FastSpeech2
+
+    kw = configs.PRESETS[PRESET]
+    hp = configs.resolve(kw)
+    stats = {v: {"min": -3.0, "max": 3.0, "mean": 0.0, "std": 1.0} for v in hp["variances"]}
+    model = FastSpeech2(stats=stats, phone2id={f"p{i}": i for i in range(80)}, num_workers=0, **kw)
+    sd = synthetic.fill_state_dict(model.state_dict(), seed=0)
+    model.load_state_dict(sd)
+    hp["stats"] = stats
+    return model.eval().to(device), sd, hp
+
+
+def cpu_port_throughput(sd, hp, batch, nutt, repeats=1):
+    """Oracle port (torch CPU ops = what the reference's nn.Modules dispatch to) on the first
+    `nutt` utterances of the batch, all host threads.  Returns (frames/s, seconds, frames)."""
+    from oracle import fs2_oracle as O
+
+    torch.set_num_threads(os.cpu_count())
+    sub = {"phones": batch["phones"][:nutt].contiguous(), "speaker": batch["speaker"][:nutt].contiguous()}
+    keep = int((sub["phones"] != 0).sum(1).max())
+    sub["phones"] = sub["phones"][:, :keep].contiguous()
+    best = None
+    frames = 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            r = O.forward(sd, hp, sub, inference=True)
+        dt = time.perf_counter() - t0
+        frames = int((~r["tgt_mask"]).sum())
+        best = dt if best is None else min(best, dt)
+    return frames / best, best, frames
+
+
+def run_reference(args):
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    kw = configs.PRESETS[PRESET]
+    hp = configs.resolve(kw)
+    stats = {v: {"min": -3.0, "max": 3.0, "mean": 0.0, "std": 1.0} for v in hp["variances"]}
+    hp["stats"] = stats
+    from lightningfastspeech2_b200.fastspeech2.fastspeech2 import FastSpeech2
+
+    model = FastSpeech2(stats=stats, phone2id={f"p{i}": i for i in range(80)}, num_workers=0, **kw)
+    sd = synthetic.fill_state_dict(model.state_dict(), seed=0)
+    batch = synthetic.make_batch(BATCH, MIN_LEN, MAX_LEN, seed=2)
+    nutt = args.ref_utts
+    for _ in range(args.warmup):
+        cpu_port_throughput(sd, hp, batch, min(2, nutt))
+    times, frames = [], 0
+    for _ in range(args.steps):
+        _, dt, frames = cpu_port_throughput(sd, hp, batch, nutt)
+        times.append(dt)
+    total = sum(times)
+    value = frames * len(times) / total
+    sample = (f"first {nutt} of the {BATCH} utterances of the C2 batch (seed 2) per step, padded to their own max "
+              f"length; oracle/fs2_oracle.py (torch CPU conv1d/linear/softmax/layer_norm), no_grad")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_lfs2(args):
+    import torch.distributed as dist
+
+    from lightningfastspeech2_b200 import _lib, ops
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (the lfs2 path has no CPU fallback); "
+                         "use --impl reference for the CPU port")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+    model, sd, hp = build_model(dev)
+    host_batch = synthetic.make_batch(BATCH, MIN_LEN, MAX_LEN, seed=2 + rank)
+    pinned = {k: v.pin_memory() for k, v in host_batch.items() if k in ("phones", "speaker")}
+    resident = {k: v.to(dev) for k, v in pinned.items()}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        with torch.no_grad():
+            return model(resident, inference=True)
+
+    frames = None
+    for _ in range(max(args.warmup, 3)):
+        r = step_resident()
+    frames = int((~r["tgt_mask"]).sum())
+    mel_shape = tuple(r["mel"].shape)
+    tp = resident["phones"].shape[1]
+
+    # ---- timed region: inputs resident in HBM -------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    calls0 = _lib.CALLS
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step_resident()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.CALLS - calls0
+
+    # ---- e2e: host inputs, pinned H2D + D2H of mel / mask inside the timed region ---------
+    mel_host = torch.empty(mel_shape, dtype=torch.float32).pin_memory()
+    mask_host = torch.empty(mel_shape[:2], dtype=torch.bool).pin_memory()
+
+    def step_e2e():
+        with torch.no_grad():
+            out = model(pinned, inference=True)
+        mel_host.copy_(out["mel"], non_blocking=True)
+        mask_host.copy_(out["tgt_mask"], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return int((~mask_host).sum())
+
+    step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    e2e_frames = 0
+    for _ in range(args.steps):
+        e2e_frames += step_e2e()
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- per-kernel CUDA-event pass (same inputs, after the timed region) -----------------
+    ops.PROFILE = {}
+    for _ in range(min(args.steps, 3)):
+        step_resident()
+    torch.cuda.synchronize()
+    prof = ops.collect_profile()
+    ops.PROFILE = None
+
+    # ---- reduce over ranks ------------------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+        c = torch.tensor([frames, e2e_frames], device=dev, dtype=torch.int64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        frames_all, e2e_all = int(c[0]), int(c[1])
+    else:
+        frames_all, e2e_all = frames, e2e_frames
+
+    if rank == 0:
+        pk = peaks()
+        total_ms = sum(v["ms"] for v in prof.values())
+        top_name = max(prof, key=lambda k: prof[k]["ms"])
+        top = prof[top_name]
+        per_launch_s = top["ms"] * 1e-3 / top["launches"]
+        if top["bound"] == "tensor":
+            achieved = top["flops"] / top["launches"] / per_launch_s / 1e12
+            peak, unit = pk["tensor"], "TFLOP/s"
+        else:
+            achieved = top["bytes"] / top["launches"] / per_launch_s / 1e9
+            peak, unit = pk["hbm"], "GB/s"
+        roofline = {"kernel": top_name, "bound": "hbm" if top["bound"] == "hbm" else "tensor",
+                    "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                    "traffic": None, "peak_source": pk["src"], "us_per_launch": per_launch_s * 1e6,
+                    "share_of_step": top["ms"] / total_ms,
+                    "kernel_shares": {k: round(v["ms"] / total_ms, 4) for k, v in sorted(
+                        prof.items(), key=lambda kv: -kv[1]["ms"])}}
+        cpu_fps, cpu_s, cpu_frames = cpu_port_throughput(sd, hp, host_batch, args.ref_utts)
+        sample = (f"first {args.ref_utts} of the {BATCH} utterances of the same batch, 1 run of {cpu_s:.1f} s "
+                  f"({cpu_frames} valid frames)")
+        value = frames_all * args.steps / (ms * 1e-3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "preset": PRESET, "utterances_per_gpu": BATCH, "padded_phones": tp,
+                       "mel_shape_rank0": list(mel_shape), "valid_frames_per_step": frames_all,
+                       "l2": "no flush: every activation tensor of a step (>=168 MB) exceeds the 126 MB L2",
+                       "parallelism": f"utterance-sharded x{world}, no collective"},
+            "clocks": clocks,
+            "e2e": {"value": e2e_all / (ms_e2e * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pinned.values()) * world,
+                    "d2h_bytes_per_step": (mel_host.numel() * 4 + mask_host.numel() + 8) * world,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": sample},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="lfs2", choices=["lfs2", "reference"])
+    ap.add_argument("--ref-utts", type=int, default=4, help="utterances in the bounded CPU sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_lfs2(args)
+
+
+if __name__ == "__main__":
+    main()

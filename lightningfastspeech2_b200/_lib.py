@@ -32,6 +32,7 @@ SIGNATURES = {
 }
 
 _lib = None
+CALLS = 0  # C-ABI launches issued by this process (bench.py reports the per-step count)
 
 
 class Lfs2Error(RuntimeError):

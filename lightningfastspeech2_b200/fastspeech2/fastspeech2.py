@@ -325,7 +325,7 @@ class FastSpeech2(_Base):
         output = ops.add_pe_spk_(variance_output["x"], pe, spk)
         tgt_mask = variance_output["tgt_mask"]
         output = self.decoder(output, src_key_padding_mask=tgt_mask)
-        mel = ops.linear(output, self.linear.weight, self.linear.bias)
+        mel = ops.linear(output, self.linear.weight, self.linear.bias, tag="mel_linear")
 
         result = {
             "mel": mel,

@@ -145,9 +145,9 @@ class ConformerEncoderLayer(nn.Module):
         _require_inference(self, self.p_drop, "ConformerEncoderLayer")
         x = src
         sa = self.self_attn
-        qkv = ops.linear(x, sa.in_proj_weight, sa.in_proj_bias)
+        qkv = ops.linear(x, sa.in_proj_weight, sa.in_proj_bias, tag="qkv_gemm")
         ctx = ops.attention(qkv, src_key_padding_mask, self.nhead)
-        a = ops.linear(ctx, sa.out_proj.weight, sa.out_proj.bias)
+        a = ops.linear(ctx, sa.out_proj.weight, sa.out_proj.bias, tag="out_proj_gemm")
         x1 = ops.add_layernorm(x, a, self.norm1.weight, self.norm1.bias, self.eps)
         y = self._ff_block(x1)
         return ops.add_layernorm(x1, y, self.norm2.weight, self.norm2.bias, self.eps)
@@ -156,8 +156,8 @@ class ConformerEncoderLayer(nn.Module):
         p = self._packed()
         if self.depthwise:
             u = ops.dwconv1d(x, p["dw_wt"], self.conv1[0].bias)
-            v = ops.linear(u, p["pw1_w"], self.conv1[1].bias, relu=True)
-            return ops.linear(v, p["w_eff"], p["b_eff"])
+            v = ops.linear(u, p["pw1_w"], self.conv1[1].bias, relu=True, tag="ffn1_gemm")
+            return ops.linear(v, p["w_eff"], p["b_eff"], tag="ffn2_gemm")
         v = ops.conv1d_dense(x, p["c1_wp"], self.conv1.bias, self.conv1.kernel_size[0], relu=True)
         return ops.conv1d_dense(v, p["c2_wp"], self.conv2.bias, self.conv2.kernel_size[0])
 
@@ -217,7 +217,7 @@ class VarianceConvolutionLayer(nn.Module):
         p = self._pack.get(list(conv.parameters()), self._build_pack)
         if self.depthwise:
             u = ops.dwconv1d(x, p["dw_wt"], conv[0].bias)
-            h = ops.linear(u, p["pw_w"], conv[1].bias, relu=True)
+            h = ops.linear(u, p["pw_w"], conv[1].bias, relu=True, tag="predictor_pw_gemm")
         else:
             h = ops.conv1d_dense(x, p["wp"], conv.bias, self.kernel_size, relu=True)
         return ops.add_layernorm(h, None, ln.weight, ln.bias, ln.eps)

@@ -12,6 +12,38 @@ from . import _lib
 
 LN_EPS = 1e-5
 
+# When bench.py sets PROFILE = {} every launch is bracketed by CUDA events on the launching
+# stream and tagged with its algorithmic flops / HBM bytes (SURVEY 8d definitions).
+PROFILE = None
+
+
+def _launch(cname, *args, tag=None, flops=0.0, nbytes=0.0):
+    fn = getattr(_lib.lib(), cname)
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROFILE.setdefault(tag or cname, []).append((e0, e1, float(flops), float(nbytes)))
+    else:
+        rc = fn(*args)
+    _lib.CALLS += 1
+    _lib.check(rc, cname)
+
+
+def collect_profile(hbm_gbs=6548.2, tensor_tflops=1680.6):
+    """{tag: {ms, launches, flops, bytes, bound}} summed over the recorded launches; `bound` is
+    whichever of (bytes / HBM peak, flops / tensor peak) is the longer time."""
+    torch.cuda.synchronize()
+    out = {}
+    for tag, recs in (PROFILE or {}).items():
+        ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
+        fl = sum(r[2] for r in recs)
+        by = sum(r[3] for r in recs)
+        bound = "tensor" if fl / (tensor_tflops * 1e12) > by / (hbm_gbs * 1e9) else "hbm"
+        out[tag] = {"ms": ms, "launches": len(recs), "flops": fl, "bytes": by, "bound": bound}
+    return out
+
 
 def _p(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
@@ -36,8 +68,8 @@ def _chk(t, dtype, name, ndim=None):
 def speaker_proj(dvec, w, b):
     _chk(dvec, torch.float32, "speaker", 2); _chk(w, torch.float32, "projection.weight", 2)
     out = torch.empty(dvec.shape[0], w.shape[0], device=dvec.device, dtype=torch.float32)
-    _lib.check(_lib.lib().lfs2_speaker_proj(_p(dvec), _p(w), _p(b), _p(out), dvec.shape[0], dvec.shape[1],
-                                            w.shape[0], _s()), "lfs2_speaker_proj")
+    _launch("lfs2_speaker_proj", _p(dvec), _p(w), _p(b), _p(out), dvec.shape[0], dvec.shape[1],
+                                            w.shape[0], _s())
     return out
 
 
@@ -49,8 +81,8 @@ def embed_pe_spk(phones, emb, pe, spk):
         raise ValueError(f"sequence length {t} exceeds the positional table ({pe.shape[-2]})")
     x = torch.empty(b, t, d, device=phones.device, dtype=torch.float32)
     mask = torch.empty(b, t, device=phones.device, dtype=torch.bool)
-    _lib.check(_lib.lib().lfs2_embed_pe_spk(_p(phones), _p(emb), _p(pe), _p(spk), _p(x), _p(mask), b, t, d,
-                                            emb.shape[0], _s()), "lfs2_embed_pe_spk")
+    _launch("lfs2_embed_pe_spk", _p(phones), _p(emb), _p(pe), _p(spk), _p(x), _p(mask), b, t, d,
+                                            emb.shape[0], _s())
     return x, mask
 
 
@@ -59,11 +91,11 @@ def add_pe_spk_(x, pe, spk):
     b, t, d = x.shape
     if t > pe.shape[-2]:
         raise ValueError(f"sequence length {t} exceeds the positional table ({pe.shape[-2]})")
-    _lib.check(_lib.lib().lfs2_add_pe_spk(_p(x), _p(pe), _p(spk), b, t, d, _s()), "lfs2_add_pe_spk")
+    _launch("lfs2_add_pe_spk", _p(x), _p(pe), _p(spk), b, t, d, _s(), nbytes=2 * x.numel() * 4)
     return x
 
 
-def linear(a, w, bias, relu=False, out=None):
+def linear(a, w, bias, relu=False, out=None, tag=None):
     """a (..., k) . w (n, k)^T + bias -> (..., n)"""
     _chk(a, torch.float32, "linear input"); _chk(w, torch.float32, "linear weight", 2)
     k = a.shape[-1]
@@ -73,11 +105,12 @@ def linear(a, w, bias, relu=False, out=None):
         raise ValueError(f"linear: weight {tuple(w.shape)} does not match input features {k}")
     if out is None:
         out = torch.empty(*a.shape[:-1], n, device=a.device, dtype=torch.float32)
-    _lib.check(_lib.lib().lfs2_linear(_p(a), _p(w), _p(bias), _p(out), m, n, k, int(relu), _s()), "lfs2_linear")
+    _launch("lfs2_linear", _p(a), _p(w), _p(bias), _p(out), m, n, k, int(relu), _s(), tag=tag or f"linear_n{n}_k{k}",
+            flops=2.0 * m * n * k, nbytes=4.0 * (m * k + n * k + m * n))
     return out
 
 
-def conv1d_dense(x, wp, bias, ksize, relu=False):
+def conv1d_dense(x, wp, bias, ksize, relu=False, tag=None):
     """x (B,T,d), wp (n, ksize*d) tap-major -> (B,T,n)"""
     _chk(x, torch.float32, "conv input", 3); _chk(wp, torch.float32, "conv weight", 2)
     b, t, d = x.shape
@@ -85,8 +118,9 @@ def conv1d_dense(x, wp, bias, ksize, relu=False):
     if wp.shape[1] != ksize * d:
         raise ValueError("conv1d_dense: packed weight shape mismatch")
     out = torch.empty(b, t, n, device=x.device, dtype=torch.float32)
-    _lib.check(_lib.lib().lfs2_conv1d_dense(_p(x), _p(wp), _p(bias), _p(out), b, t, d, n, ksize, int(relu), _s()),
-               "lfs2_conv1d_dense")
+    _launch("lfs2_conv1d_dense", _p(x), _p(wp), _p(bias), _p(out), b, t, d, n, ksize, int(relu), _s(),
+            tag=tag or f"conv_dense_k{ksize}_n{n}", flops=2.0 * b * t * n * ksize * d,
+            nbytes=4.0 * (b * t * d + n * ksize * d + b * t * n))
     return out
 
 
@@ -95,8 +129,8 @@ def dwconv1d(x, wt, bias):
     _chk(x, torch.float32, "dwconv input", 3); _chk(wt, torch.float32, "dwconv weight", 2)
     b, t, d = x.shape
     out = torch.empty_like(x)
-    _lib.check(_lib.lib().lfs2_dwconv1d(_p(x), _p(wt), _p(bias), _p(out), b, t, d, wt.shape[0], _s()),
-               "lfs2_dwconv1d")
+    _launch("lfs2_dwconv1d", _p(x), _p(wt), _p(bias), _p(out), b, t, d, wt.shape[0], _s(),
+            flops=2.0 * b * t * d * wt.shape[0], nbytes=8.0 * b * t * d)
     return out
 
 
@@ -108,7 +142,12 @@ def attention(qkv, kpm, nhead):
     if kpm is not None:
         _chk(kpm, torch.bool, "key_padding_mask", 2)
     ctx = torch.empty(b, t, d, device=qkv.device, dtype=torch.float32)
-    _lib.check(_lib.lib().lfs2_attention(_p(qkv), _p(kpm), _p(ctx), b, t, d, nhead, _s()), "lfs2_attention")
+    fl = 0.0
+    if PROFILE is not None:  # algorithmic flops: every query row x the utterance's VALID keys
+        nkeys = (~kpm).sum(1).double() if kpm is not None else torch.full((b,), float(t))
+        fl = float(4.0 * d * t * nkeys.sum())
+    _launch("lfs2_attention", _p(qkv), _p(kpm), _p(ctx), b, t, d, nhead, _s(), flops=fl,
+            nbytes=4.0 * (qkv.numel() + ctx.numel()))
     return ctx
 
 
@@ -119,8 +158,8 @@ def add_layernorm(x, y, gamma, beta, eps=LN_EPS):
     d = x.shape[-1]
     m = x.numel() // d
     out = torch.empty_like(x)
-    _lib.check(_lib.lib().lfs2_add_layernorm(_p(x), _p(y), _p(gamma), _p(beta), _p(out), m, d, eps, _s()),
-               "lfs2_add_layernorm")
+    _launch("lfs2_add_layernorm", _p(x), _p(y), _p(gamma), _p(beta), _p(out), m, d, eps, _s(),
+            nbytes=4.0 * m * d * (3 if y is not None else 2))
     return out
 
 
@@ -128,8 +167,7 @@ def rowdot_mask(z, w, bias, mask):
     _chk(z, torch.float32, "predictor hidden", 3)
     b, t, f = z.shape
     out = torch.empty(b, t, device=z.device, dtype=torch.float32)
-    _lib.check(_lib.lib().lfs2_rowdot_mask(_p(z), _p(w), _p(bias), _p(mask), _p(out), b * t, f, _s()),
-               "lfs2_rowdot_mask")
+    _launch("lfs2_rowdot_mask", _p(z), _p(w), _p(bias), _p(mask), _p(out), b * t, f, _s(), nbytes=4.0 * b * t * (f + 1))
     return out
 
 
@@ -142,17 +180,17 @@ def bucket_embed_add_(x, val, std, mean, bins, emb, idx_forced=None, acc=None, a
         _chk(val, torch.float32, "variance values")
     idx_out = torch.empty(b, t, device=x.device, dtype=torch.int64) if want_idx else None
     mode = 0 if acc is None else (1 if acc_init else 2)
-    _lib.check(_lib.lib().lfs2_bucket_embed_add(_p(x), _p(val), float(std), float(mean), _p(bins),
+    _launch("lfs2_bucket_embed_add", _p(x), _p(val), float(std), float(mean), _p(bins),
                                                 emb.shape[0], _p(emb), _p(idx_forced), _p(idx_out), _p(acc), mode,
-                                                b * t, d, _s()), "lfs2_bucket_embed_add")
+                                                b * t, d, _s(), nbytes=4.0 * b * t * d * (2 + (acc is not None)))
     return idx_out
 
 
 def duration_round_guard(log_dur, src_mask):
     _chk(log_dur, torch.float32, "duration_prediction", 2); _chk(src_mask, torch.bool, "src_mask", 2)
     dur = torch.empty(log_dur.shape, device=log_dur.device, dtype=torch.int32)
-    _lib.check(_lib.lib().lfs2_duration_round_guard(_p(log_dur), _p(src_mask), _p(dur), log_dur.shape[0],
-                                                    log_dur.shape[1], _s()), "lfs2_duration_round_guard")
+    _launch("lfs2_duration_round_guard", _p(log_dur), _p(src_mask), _p(dur), log_dur.shape[0],
+                                                    log_dur.shape[1], _s())
     return dur
 
 
@@ -169,12 +207,13 @@ def length_regulate(x, durations, max_length):
     cum = torch.empty(b, tp, device=dev, dtype=torch.int64)
     lengths = torch.empty(b, device=dev, dtype=torch.int64)
     mx = torch.empty(1, device=dev, dtype=torch.int64)
-    _lib.check(_lib.lib().lfs2_length_regulate_scan(_p(durations), int(durations.dtype == torch.int64), _p(cum),
-                                                    _p(lengths), _p(mx), b, tp, _s()), "lfs2_length_regulate_scan")
+    _launch("lfs2_length_regulate_scan", _p(durations), int(durations.dtype == torch.int64), _p(cum),
+                                                    _p(lengths), _p(mx), b, tp, _s())
     longest = int(mx.item())  # the single device->host sync of the path
     l = min(longest, int(max_length)) if max_length is not None else longest
     out = torch.empty(b, l, d, device=dev, dtype=x.dtype)
     mask = torch.empty(b, l, device=dev, dtype=torch.bool)
-    _lib.check(_lib.lib().lfs2_length_regulate_scatter(_p(x), _p(cum), _p(lengths), _p(out), _p(mask), b, tp, l,
-                                                       d * x.element_size(), _s()), "lfs2_length_regulate_scatter")
+    _launch("lfs2_length_regulate_scatter", _p(x), _p(cum), _p(lengths), _p(out), _p(mask), b, tp, l,
+                                                       d * x.element_size(), _s(),
+            nbytes=float(b * tp * (d * x.element_size() + 8) + b * l * (d * x.element_size() + 1)))
     return out, mask
