@@ -127,6 +127,26 @@ LFS2_API int lfs2_length_regulate_scatter(const void* x, const int64_t* cum, con
                                  void* out, uint8_t* mask, int batch, int tp, int l, int row_bytes,
                                  void* stream);
 
+/* ---- tensor-core (tcgen05) GEMM / Conv1d with fused epilogues ---------------------------
+ * Operands are bf16 "hi/lo" planes of fp32 values (x = hi + lo, see lfs2_split_bf16):
+ *   a_hi/a_lo : (batch, t, d)      row-major bf16   (activations)
+ *   w_hi/w_lo : (n, taps*d)        row-major bf16   (weights, tap-major for taps > 1)
+ * acc[b,tt,:] = sum_j a[b, tt + j - (taps-1)/2, :] . w[:, j*d:(j+1)*d]^T   (rows outside [0,t) are zero)
+ * npass = 3: hi.hi + lo.hi + hi.lo (fp32-parity, ~2^-16 relative); npass = 1: hi.hi only.
+ * Epilogue, in fp32:  v = acc + bias ; relu ? max(v,0) ; if gamma: v = LayerNorm(v + residual)
+ * (LayerNorm needs n == 256); written to out_f32 (batch*t, n) and/or as hi/lo planes.
+ * taps = 1 replaces the Linear / pointwise Conv1d GEMMs (model.py:82,92,111-114,552;
+ * fastspeech2.py:723); taps = k replaces the dense Conv1d(d, n, k) (model.py:95-106,529-536);
+ * the LayerNorm epilogue replaces norm1/norm2 + residual (model.py:114-115) and the predictor
+ * ReLU -> LayerNorm (model.py:537-538,555-556). */
+LFS2_API int lfs2_gemm_tc(const void* a_hi, const void* a_lo, int batch, int t, int d, int taps,
+                          const void* w_hi, const void* w_lo, int n, const float* bias, int relu,
+                          const float* residual, const float* gamma, const float* beta, float eps,
+                          float* out_f32, void* out_hi, void* out_lo, int npass, void* stream);
+
+/* hi = bf16(x), lo = bf16(x - hi) for n fp32 values (n % 4 == 0) */
+LFS2_API int lfs2_split_bf16(const float* x, void* hi, void* lo, long long n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -217,3 +217,64 @@ def length_regulate(x, durations, max_length):
                                                        d * x.element_size(), _s(),
             nbytes=float(b * tp * (d * x.element_size() + 8) + b * l * (d * x.element_size() + 1)))
     return out, mask
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core path: bf16 hi/lo planes + tcgen05 GEMM with fused epilogues
+class Planes:
+    """bf16 hi/lo planes of an fp32 tensor (x = hi + lo): the operand format of lfs2_gemm_tc."""
+
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo):
+        self.hi, self.lo = hi, lo
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    def float(self):  # for tests
+        return self.hi.float() + self.lo.float()
+
+
+def split_bf16(x):
+    _chk(x, torch.float32, "split_bf16 input")
+    hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    lo = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    _launch("lfs2_split_bf16", _p(x), _p(hi), _p(lo), x.numel(), _s(), nbytes=8.0 * x.numel())
+    return Planes(hi, lo)
+
+
+def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None, eps=LN_EPS, want_f32=True,
+            want_planes=False, npass=3, tag=None):
+    """a: Planes (B,T,d) [taps>1: Conv1d over T per utterance] or (...,d) for taps == 1;
+    w: Planes (n, taps*d).  Returns (out_f32 or None, Planes or None), shaped like a with last dim n."""
+    if not isinstance(a, Planes) or not isinstance(w, Planes):
+        raise TypeError("gemm_tc: operands must be Planes (see split_bf16)")
+    d = a.shape[-1]
+    n = w.shape[0]
+    if w.shape[1] != taps * d:
+        raise ValueError(f"gemm_tc: weight {tuple(w.shape)} does not match taps*d = {taps * d}")
+    if taps == 1:
+        batch, t = 1, a.hi.numel() // d
+    else:
+        if a.hi.dim() != 3:
+            raise ValueError("gemm_tc: conv mode needs a (B,T,d) operand")
+        batch, t = a.shape[0], a.shape[1]
+    for x_ in (a.hi, a.lo, w.hi, w.lo):
+        _chk(x_, torch.bfloat16, "gemm_tc operand plane")
+    out_shape = tuple(a.shape[:-1]) + (n,)
+    dev = a.hi.device
+    out = torch.empty(out_shape, device=dev, dtype=torch.float32) if want_f32 else None
+    po = Planes(torch.empty(out_shape, device=dev, dtype=torch.bfloat16),
+                torch.empty(out_shape, device=dev, dtype=torch.bfloat16)) if want_planes else None
+    if residual is not None:
+        _chk(residual, torch.float32, "gemm_tc residual")
+    m = batch * t
+    _launch("lfs2_gemm_tc", _p(a.hi), _p(a.lo), batch, t, d, taps, _p(w.hi), _p(w.lo), n, _p(bias), int(relu),
+            _p(residual), _p(gamma), _p(beta), float(eps), _p(out), _p(po.hi if po else None),
+            _p(po.lo if po else None), npass, _s(), tag=tag or f"gemm_tc_n{n}_k{taps * d}",
+            flops=2.0 * m * n * taps * d,
+            nbytes=4.0 * m * d + 4.0 * n * taps * d + 4.0 * m * n * (int(want_f32) + int(want_planes))
+            + (4.0 * m * n if residual is not None else 0.0))
+    return out, po

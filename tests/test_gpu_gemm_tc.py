@@ -1,0 +1,89 @@
+"""tcgen05 GEMM / Conv1d (lfs2_gemm_tc) against fp64 torch on the same seeded inputs.
+
+npass=3 (bf16 hi/lo split, three MMAs per k-step) is the fp32-parity mode: tolerance 2e-4
+abs on O(1) outputs with K <= 1024 (theory: ~2^-16 relative per product).  npass=1 is the
+bf16 mode: tolerance 3e-2."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from lightningfastspeech2_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = np.random.default_rng(seed)
+    return torch.from_numpy((g.standard_normal(shape) * scale).astype(np.float32))
+
+
+def test_split_bf16_reconstructs_to_2e_minus_16():
+    x = rnd(1000, 256, seed=1, scale=3.0).to(DEV)
+    p = ops.split_bf16(x)
+    rel = ((p.float() - x).abs() / x.abs().clamp_min(1e-20)).max()
+    assert rel < 2.0 ** -15
+    assert torch.equal(p.hi, x.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 256, 256), (300, 768, 256), (1000, 1024, 256), (257, 256, 1024),
+                                   (129, 80, 256), (5, 2304, 768), (20000, 256, 256)])
+@pytest.mark.parametrize("npass", [3, 1])
+def test_linear(m, n, k, npass):
+    a, w, b = rnd(m, k, seed=1), rnd(n, k, seed=2, scale=k ** -0.5), rnd(n, seed=3, scale=0.1)
+    ref = F.linear(a.double(), w.double(), b.double())
+    out, planes = ops.gemm_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV), npass=npass,
+                              want_planes=True)
+    tol = 2e-4 if npass == 3 else 3e-2
+    err = (out.cpu() - ref).abs().max()
+    assert err < tol, float(err)
+    assert (planes.float().cpu() - out.cpu()).abs().max() < 1e-4
+
+
+def test_relu_and_planes_only():
+    a, w, b = rnd(333, 256, seed=4), rnd(1024, 256, seed=5, scale=1 / 16), rnd(1024, seed=6, scale=0.1)
+    ref = torch.relu(F.linear(a.double(), w.double(), b.double()))
+    out, planes = ops.gemm_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV), relu=True,
+                              want_f32=False, want_planes=True)
+    assert out is None
+    assert (planes.float().cpu() - ref).abs().max() < 2e-4
+
+
+@pytest.mark.parametrize("bsz,t,d,n,ks", [(2, 37, 64, 128, 9), (3, 130, 256, 1024, 9), (1, 5, 32, 256, 3),
+                                          (4, 260, 256, 256, 3)])
+def test_conv1d_taps(bsz, t, d, n, ks):
+    x, w, b = rnd(bsz, t, d, seed=7), rnd(n, d, ks, seed=8, scale=(d * ks) ** -0.5), rnd(n, seed=9, scale=0.1)
+    ref = F.conv1d(x.double().transpose(1, 2), w.double(), b.double(), padding=(ks - 1) // 2).transpose(1, 2)
+    wp = w.permute(0, 2, 1).reshape(n, ks * d).contiguous()
+    out, _ = ops.gemm_tc(ops.split_bf16(x.to(DEV)), ops.split_bf16(wp.to(DEV)), b.to(DEV), taps=ks)
+    err = (out.cpu() - ref).abs().max()
+    assert err < 2e-4, float(err)
+
+
+@pytest.mark.parametrize("m,k,relu,res", [(300, 256, False, True), (1000, 1024, False, True), (260, 256, True, False)])
+def test_layernorm_epilogue(m, k, relu, res):
+    n = 256
+    a, w, b = rnd(m, k, seed=10), rnd(n, k, seed=11, scale=k ** -0.5), rnd(n, seed=12, scale=0.1)
+    r = rnd(m, n, seed=13)
+    g, bt = 1 + rnd(n, seed=14, scale=0.1), rnd(n, seed=15, scale=0.1)
+    v = F.linear(a.double(), w.double(), b.double())
+    if relu:
+        v = torch.relu(v)
+    if res:
+        v = v + r.double()
+    ref = F.layer_norm(v, (n,), g.double(), bt.double(), 1e-5)
+    out, planes = ops.gemm_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV), relu=relu,
+                              residual=r.to(DEV) if res else None, gamma=g.to(DEV), beta=bt.to(DEV),
+                              want_planes=True)
+    err = (out.cpu() - ref).abs().max()
+    assert err < 3e-4, float(err)
+    assert (planes.float().cpu() - out.cpu()).abs().max() < 1e-4
+
+
+def test_matches_fp32_simt_gemm_closely():
+    """same inputs through the exact-fp32 CUDA-core GEMM: the split path must agree to ~1e-5"""
+    a, w, b = rnd(4096, 256, seed=16), rnd(768, 256, seed=17, scale=1 / 16), rnd(768, seed=18, scale=0.1)
+    ref = ops.linear(a.to(DEV), w.to(DEV), b.to(DEV))
+    out, _ = ops.gemm_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV))
+    assert (out - ref).abs().max() < 1e-4
