@@ -81,6 +81,10 @@ LFS2_API int lfs2_conv1d_dense(const float* x, const float* wp, const float* bia
  * of the reference's (d,1,ksize) weight.  replaces model.py:75-81 and model.py:545-551. */
 LFS2_API int lfs2_dwconv1d(const float* x, const float* wt, const float* bias, float* out,
                   int batch, int t, int d, int ksize, void* stream);
+/* same, writing the result as fp32 (out, may be NULL) and/or as bf16 hi/lo planes (the A
+ * operand of the following pointwise lfs2_gemm_tc) */
+LFS2_API int lfs2_dwconv1d_planes(const float* x, const float* wt, const float* bias, float* out, void* out_hi,
+                                  void* out_lo, int batch, int t, int d, int ksize, void* stream);
 
 /* Multi-head self attention core on a packed qkv (B,T,3d) tensor [q | k | v], heads =
  * contiguous d/nhead column blocks, q scaled by (d/nhead)^-1/2, PAD keys get -inf,
@@ -143,6 +147,19 @@ LFS2_API int lfs2_gemm_tc(const void* a_hi, const void* a_lo, int batch, int t, 
                           const void* w_hi, const void* w_lo, int n, const float* bias, int relu,
                           const float* residual, const float* gamma, const float* beta, float eps,
                           float* out_f32, void* out_hi, void* out_lo, int npass, void* stream);
+
+/* tensor-core multi-head self attention (head_dim 128) on the bf16 hi/lo planes of the packed
+ * qkv (B,T,3d) tensor [q | k | v] written by lfs2_gemm_tc: flash-style streaming softmax,
+ * S = Q.K^T and O = P.V on tcgen05 with Q/P read from tensor memory, K/V tiles by TMA.
+ * Semantics identical to lfs2_attention (q scaled by head_dim^-1/2, PAD keys -inf, fp32
+ * softmax, fully masked rows NaN).  npass = 3: hi.hi + lo.hi + hi.lo (fp32-parity mode);
+ * npass = 1: bf16 operands.  Outputs: ctx as hi/lo planes (B,T,d) and/or fp32.
+ * workspace: lfs2_attention_tc_workspace_bytes(batch) bytes of device memory.
+ * replaces torch _sa_block / nn.MultiheadAttention as used at model.py:111-114. */
+LFS2_API int lfs2_attention_tc_workspace_bytes(int batch);
+LFS2_API int lfs2_attention_tc(const void* qkv_hi, const void* qkv_lo, const uint8_t* key_padding_mask,
+                               void* ctx_hi, void* ctx_lo, float* ctx_f32, void* workspace, int batch, int t,
+                               int d, int nhead, int npass, void* stream);
 
 /* hi = bf16(x), lo = bf16(x - hi) for n fp32 values (n % 4 == 0) */
 LFS2_API int lfs2_split_bf16(const float* x, void* hi, void* lo, long long n, void* stream);

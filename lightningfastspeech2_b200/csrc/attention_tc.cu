@@ -1,0 +1,465 @@
+// tcgen05 flash attention for the FFTBlock (head_dim 128), operands as bf16 hi/lo planes.
+//
+//   one CTA = 128 queries of one (utterance, head); key tiles of 64 stream through shared
+//   memory by TMA; S = Q.K^T and O += P.V run on the 5th-gen tensor cores with both A
+//   operands (Q, P) read from TENSOR MEMORY (tcgen05.mma "TS" form), so shared memory only
+//   feeds the B operands (K K-major, V MN-major straight from the row-major qkv tensor --
+//   no transposed copy of V exists anywhere).
+//
+//   TMEM columns (512):  [0,128)   Q   bf16 pairs: hi plane cols 0..63, lo plane cols 64..127
+//                        [128,256) S/P two 64-column buffers: S_j fp32 (64 keys) is
+//                                  overwritten in place by P_j (hi: 32 cols, lo: 32 cols)
+//                        [256,384) O   fp32 accumulator (128 head-dim columns)
+//
+//   warps: 0 = TMA producer (K and V rings, 3 stages each), 1 = MMA issuer (one thread),
+//   2..5 = softmax (thread = query row; TMEM lane quadrant = warp & 3).
+//   tensor-pipe order:  QK_0 QK_1 | PV_0 QK_2 | PV_1 QK_3 | ...   so softmax_{j+1} overlaps
+//   PV_j + QK_{j+2}.  The running maximum only moves upwards (exact online softmax); the O
+//   accumulator is rescaled in TMEM by the softmax warps only when some row's maximum grew.
+//
+//   NPASS = 3: hi.hi + lo.hi + hi.lo for both products (fp32-parity mode); NPASS = 1: hi.hi.
+//   The softmax itself (max, exp2, sum, 1/l) is fp32.  PAD keys (key_padding_mask) and keys
+//   beyond T get -inf; rows whose keys are all masked produce NaN like the reference.
+#include <math.h>
+
+#include "tc_common.cuh"
+
+namespace lfs2 {
+namespace tc {
+
+constexpr int kAQ = 128;        // queries per CTA (UMMA M)
+constexpr int kAK = 64;         // keys per tile
+constexpr int kDH = 128;        // head dim
+constexpr int kKVStages = 3;
+constexpr int kAttnTcThreads = 192;
+constexpr int kTileBytes = kAK * kDH * 2;          // one plane of a K or V tile: 16 KB
+constexpr uint32_t kColQ = 0, kColS = 128, kColO = 256;
+
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// 32 lanes x 32 columns without the trailing wait (caller batches the wait)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_st32_u(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,"
+      "%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+struct AttnTcParams {
+  const __nv_bfloat16* qkv_hi;  // (B, T, 3d)
+  const __nv_bfloat16* qkv_lo;
+  const uint8_t* kpm;           // (B, T) 1 = PAD, or null
+  const int* kend;              // (B): 1 + index of the last non-PAD key (0 = all masked)
+  __nv_bfloat16* ctx_hi;        // (B, T, d)
+  __nv_bfloat16* ctx_lo;
+  float* ctx_f32;               // (B, T, d) or null
+  int t, d;
+  float scale_log2e;            // head_dim^-1/2 * log2(e)
+};
+
+// last valid key + 1 per utterance; one warp per utterance
+__global__ void attn_kend_kernel(const uint8_t* __restrict__ kpm, int* __restrict__ kend, int batch, int t) {
+  int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= batch) return;
+  int last = 0;
+  if (!kpm) {
+    last = t;
+  } else {
+    for (int i = lane; i < t; i += 32)
+      if (!kpm[(size_t)b * t + i]) last = i + 1;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) last = max(last, __shfl_xor_sync(0xffffffffu, last, o));
+  }
+  if (lane == 0) kend[b] = last;
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(kAttnTcThreads, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                    const AttnTcParams p) {
+  constexpr int kPlanes = NPASS == 3 ? 2 : 1;
+  constexpr int kStageBytes = kPlanes * kTileBytes;  // K (or V) tile, hi [+ lo]
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + kKVStages * kStageBytes;
+  __shared__ __align__(8) uint64_t k_full[kKVStages], k_empty[kKVStages], v_full[kKVStages], v_empty[kKVStages];
+  __shared__ __align__(8) uint64_t q_full, s_full[2], p_full[2], pv_done, o_final;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * kAQ, h = blockIdx.y, b = blockIdx.z;
+  const int kend = p.kend[b];
+  const int ntiles = (kend + kAK - 1) / kAK;
+  const int col_q = h * kDH, col_k = p.d + h * kDH, col_v = 2 * p.d + h * kDH;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_hi);
+    if (NPASS == 3) prefetch_tmap(&map_lo);
+    for (int s = 0; s < kKVStages; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+    }
+    mbar_init(&q_full, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+    }
+    mbar_init(&pv_done, 1);
+    mbar_init(&o_final, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer: K_j then V_j =====================
+    if (lane == 0) {
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % kKVStages;
+        const uint32_t ph = (j / kKVStages) & 1;
+        const int key0 = j * kAK;
+        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_expect_tx(&k_full[st], kStageBytes);
+        uint8_t* dk = sK + st * kStageBytes;
+#pragma unroll
+        for (int c = 0; c < kDH / 32; ++c) {
+          tma_load_3d(dk + c * 4096, &map_hi, &k_full[st], col_k + c * 32, key0, b);
+          if (NPASS == 3) tma_load_3d(dk + kTileBytes + c * 4096, &map_lo, &k_full[st], col_k + c * 32, key0, b);
+        }
+        mbar_wait(&v_empty[st], ph ^ 1);
+        mbar_expect_tx(&v_full[st], kStageBytes);
+        uint8_t* dv = sV + st * kStageBytes;
+#pragma unroll
+        for (int c = 0; c < kDH / 32; ++c) {
+          tma_load_3d(dv + c * 4096, &map_hi, &v_full[st], col_v + c * 32, key0, b);
+          if (NPASS == 3) tma_load_3d(dv + kTileBytes + c * 4096, &map_lo, &v_full[st], col_v + c * 32, key0, b);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0 && ntiles > 0) {
+      constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, kAQ, kAK, 0, 0);  // A: TMEM, B: K tile, K-major
+      constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, kAQ, kDH, 0, 1);  // A: TMEM, B: V tile, MN-major
+      const uint32_t tq = tmem_base + kColQ, to = tmem_base + kColO;
+
+      auto issue_qk = [&](int j) {
+        const int st = j % kKVStages;
+        mbar_wait(&k_full[st], (j / kKVStages) & 1);
+        tc_fence_after();
+        const uint32_t ts = tmem_base + kColS + (j & 1) * kAK;
+        const uint32_t kh = smem_u32(sK + st * kStageBytes), kl = kh + kTileBytes;
+#pragma unroll
+        for (int i = 0; i < kDH / 16; ++i) {
+          const uint32_t off = (i >> 1) * 4096 + (i & 1) * 32;
+          const uint64_t dkh = make_smem_desc(kh + off, 16, 512, kSwizzle64);
+          umma_f16_ts(ts, tq + i * 8, dkh, idesc_qk, i ? 1u : 0u);
+          if (NPASS == 3) {
+            const uint64_t dkl = make_smem_desc(kl + off, 16, 512, kSwizzle64);
+            umma_f16_ts(ts, tq + 64 + i * 8, dkh, idesc_qk, 1u);
+            umma_f16_ts(ts, tq + i * 8, dkl, idesc_qk, 1u);
+          }
+        }
+        umma_commit(&k_empty[st]);
+        umma_commit(&s_full[j & 1]);
+      };
+
+      mbar_wait(&q_full, 0);
+      tc_fence_after();
+      issue_qk(0);
+      if (ntiles > 1) issue_qk(1);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % kKVStages;
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        mbar_wait(&v_full[st], (j / kKVStages) & 1);
+        tc_fence_after();
+        const uint32_t tp = tmem_base + kColS + (j & 1) * kAK;  // P hi: 32 cols, P lo: next 32
+        const uint32_t vh = smem_u32(sV + st * kStageBytes), vl = vh + kTileBytes;
+#pragma unroll
+        for (int i = 0; i < kAK / 16; ++i) {
+          const uint64_t dvh = make_smem_desc(vh + i * 1024, 4096, 512, kSwizzle64);
+          umma_f16_ts(to, tp + i * 8, dvh, idesc_pv, (j | i) ? 1u : 0u);
+          if (NPASS == 3) {
+            const uint64_t dvl = make_smem_desc(vl + i * 1024, 4096, 512, kSwizzle64);
+            umma_f16_ts(to, tp + 32 + i * 8, dvh, idesc_pv, 1u);
+            umma_f16_ts(to, tp + i * 8, dvl, idesc_pv, 1u);
+          }
+        }
+        umma_commit(&v_empty[st]);
+        umma_commit(&pv_done);
+        if (j + 2 < ntiles) issue_qk(j + 2);
+      }
+      umma_commit(&o_final);  // every product of this CTA has landed
+    }
+  } else {
+    // ===================== softmax warps: thread = query row =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int tq_row = q0 + r;
+    const bool row_ok = tq_row < p.t;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+
+    // ---- Q row -> TMEM (bf16 pairs; hi plane cols 0..63, lo plane cols 64..127) ----
+    {
+      uint32_t w[32];
+#pragma unroll
+      for (int pl = 0; pl < 2; ++pl) {
+        const __nv_bfloat16* src = (pl == 0 ? p.qkv_hi : p.qkv_lo) + ((size_t)b * p.t + tq_row) * 3 * p.d + col_q;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (row_ok && (pl == 0 || NPASS == 3)) {
+            const uint4* s4 = reinterpret_cast<const uint4*>(src) + half * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint4 v = __ldg(s4 + i);
+              w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) w[i] = 0u;
+          }
+          tmem_st32_u(tmem_base + kColQ + pl * 64 + half * 32 + lane_off, w);
+        }
+      }
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&q_full);
+    }
+
+    float m_run = -INFINITY;  // running max of the raw logits of this row
+    float l_run = 0.f;
+    const float c = p.scale_log2e;
+    const uint8_t* mrow = p.kpm ? p.kpm + (size_t)b * p.t : nullptr;
+
+    for (int j = 0; j < ntiles; ++j) {
+      const int key0 = j * kAK;
+      // 64-bit "key is masked" set of this tile (PAD keys and keys beyond T), warp-uniform
+      uint32_t mlo, mhi;
+      {
+        int k1 = key0 + lane, k2 = key0 + 32 + lane;
+        bool b1 = (k1 >= p.t) || (mrow && mrow[k1]);
+        bool b2 = (k2 >= p.t) || (mrow && mrow[k2]);
+        mlo = __ballot_sync(0xffffffffu, b1);
+        mhi = __ballot_sync(0xffffffffu, b2);
+      }
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t ts = tmem_base + kColS + (j & 1) * kAK + lane_off;
+      float s[64];
+      tmem_ld32_nowait(ts, s);
+      tmem_ld32_nowait(ts + 32, s + 32);
+      tmem_wait_ld();
+      if (mlo | mhi) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          if ((mlo >> i) & 1u) s[i] = -INFINITY;
+          if ((mhi >> i) & 1u) s[32 + i] = -INFINITY;
+        }
+      }
+      float tmax = s[0];
+#pragma unroll
+      for (int i = 1; i < 64; ++i) tmax = fmaxf(tmax, s[i]);
+      const float m_new = fmaxf(m_run, tmax);
+      const bool grew = m_new > m_run && j > 0;
+      // O rescale (warp-collective TMEM access): only when some row of this warp moved its max
+      if (__any_sync(0xffffffffu, grew)) {
+        mbar_wait(&pv_done, (j - 1) & 1);  // all PV products up to tile j-1 have landed in O
+        tc_fence_after();
+        const float alpha = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * c);
+        l_run *= alpha;
+        float o[32];
+#pragma unroll 1
+        for (int cc = 0; cc < kDH / 32; ++cc) {
+          tmem_ld32(tmem_base + kColO + cc * 32 + lane_off, o);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[i] *= alpha;
+          tmem_st32(tmem_base + kColO + cc * 32 + lane_off, o);
+        }
+        tmem_wait_st();
+      }
+      m_run = m_new;
+      const float mc = (m_new == -INFINITY) ? 0.f : m_new * c;
+      uint32_t ph[32], pl[32];
+      float lsum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        float p0 = exp2f(fmaf(s[2 * i], c, -mc));
+        float p1 = exp2f(fmaf(s[2 * i + 1], c, -mc));
+        lsum += p0 + p1;
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(p0, h0, l0);
+        split_bf16(p1, h1, l1);
+        ph[i] = pack_bf16(h0, h1);
+        pl[i] = pack_bf16(l0, l1);
+      }
+      l_run += lsum;
+      tmem_st32_u(ts, ph);
+      if (NPASS == 3) tmem_st32_u(ts + 32, pl);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+    }
+
+    // ---- epilogue: O / l -> ctx planes ----
+    const size_t orow = ((size_t)b * p.t + tq_row) * p.d + col_q;
+    if (ntiles > 0) {
+      mbar_wait(&o_final, 0);
+      tc_fence_after();
+    }
+    const float inv_l = 1.f / l_run;  // l == 0 (no unmasked key) -> inf -> NaN rows, like the reference
+    float o[32];
+#pragma unroll 1
+    for (int cc = 0; cc < kDH / 32; ++cc) {
+      if (ntiles > 0) {
+        tmem_ld32(tmem_base + kColO + cc * 32 + lane_off, o);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] *= inv_l;
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[i] = __int_as_float(0x7fc00000);
+      }
+      if (row_ok) {
+        if (p.ctx_f32) {
+          float4* of = reinterpret_cast<float4*>(p.ctx_f32 + orow + cc * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) of[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        }
+        if (p.ctx_hi) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(o[2 * i], h0, l0);
+            split_bf16(o[2 * i + 1], h1, l1);
+            hi[i] = pack_bf16(h0, h1);
+            lo[i] = pack_bf16(l0, l1);
+          }
+          uint4* oh = reinterpret_cast<uint4*>(p.ctx_hi + orow + cc * 32);
+          uint4* ol = reinterpret_cast<uint4*>(p.ctx_lo + orow + cc * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int NPASS>
+static int launch_attention_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& p, int batch,
+                               int nhead, cudaStream_t s) {
+  constexpr int kSmem = 2 * kKVStages * (NPASS == 3 ? 2 : 1) * kTileBytes + 1024;
+  auto kern = attention_tc_kernel<NPASS>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) {
+      set_error("attention_tc: cannot reserve %d bytes of shared memory", kSmem);
+      return LFS2_ERR_CUDA;
+    }
+    configured = true;
+  }
+  dim3 grid((p.t + kAQ - 1) / kAQ, nhead, batch);
+  kern<<<grid, kAttnTcThreads, kSmem, s>>>(mh, ml, p);
+  LFS2_CHECK_LAUNCH("attention_tc");
+  return LFS2_OK;
+}
+
+}  // namespace tc
+}  // namespace lfs2
+
+using namespace lfs2;
+using namespace lfs2::tc;
+
+extern "C" {
+
+int lfs2_attention_tc_workspace_bytes(int batch) { return batch > 0 ? batch * (int)sizeof(int) : 0; }
+
+int lfs2_attention_tc(const void* qkv_hi, const void* qkv_lo, const uint8_t* key_padding_mask, void* ctx_hi,
+                      void* ctx_lo, float* ctx_f32, void* workspace, int batch, int t, int d, int nhead, int npass,
+                      void* stream) {
+  LFS2_REQUIRE(qkv_hi && workspace, LFS2_ERR_INVALID_ARG, "attention_tc: null pointer");
+  LFS2_REQUIRE(npass == 1 || npass == 3, LFS2_ERR_INVALID_ARG, "attention_tc: npass must be 1 or 3");
+  LFS2_REQUIRE(npass == 1 || qkv_lo, LFS2_ERR_INVALID_ARG, "attention_tc: npass=3 needs the lo plane");
+  LFS2_REQUIRE((ctx_hi && ctx_lo) || ctx_f32, LFS2_ERR_INVALID_ARG, "attention_tc: no output");
+  LFS2_REQUIRE(!ctx_hi == !ctx_lo, LFS2_ERR_INVALID_ARG, "attention_tc: ctx_hi and ctx_lo go together");
+  if (batch == 0 || t == 0) return LFS2_OK;
+  LFS2_REQUIRE(batch > 0 && t > 0 && d > 0 && nhead > 0 && d % nhead == 0, LFS2_ERR_INVALID_ARG,
+               "attention_tc: bad shape");
+  LFS2_REQUIRE(d / nhead == kDH, LFS2_ERR_UNSUPPORTED, "attention_tc: head_dim %d (only %d is implemented)",
+               d / nhead, kDH);
+  LFS2_REQUIRE(batch <= 65535 && nhead <= 65535, LFS2_ERR_UNSUPPORTED, "attention_tc: batch/heads exceed grid limits");
+  LFS2_REQUIRE(aligned16(qkv_hi) && (!qkv_lo || aligned16(qkv_lo)) && (!ctx_hi || (aligned16(ctx_hi) && aligned16(ctx_lo))) &&
+                   (!ctx_f32 || aligned16(ctx_f32)),
+               LFS2_ERR_INVALID_ARG, "attention_tc: pointers must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  int* kend = reinterpret_cast<int*>(workspace);
+  attn_kend_kernel<<<ceil_div((long long)batch * 32, 128), 128, 0, s>>>(key_padding_mask, kend, batch, t);
+  LFS2_CHECK_LAUNCH("attn_kend");
+
+  CUtensorMap mh, ml;
+  bool ok = make_tmap_3d(&mh, qkv_hi, 3ull * d, t, batch, 32, kAK, 64);
+  if (npass == 3) ok = ok && make_tmap_3d(&ml, qkv_lo, 3ull * d, t, batch, 32, kAK, 64);
+  else ml = mh;
+  LFS2_REQUIRE(ok, LFS2_ERR_CUDA, "attention_tc: cuTensorMapEncodeTiled failed");
+
+  AttnTcParams p;
+  p.qkv_hi = (const __nv_bfloat16*)qkv_hi;
+  p.qkv_lo = (const __nv_bfloat16*)qkv_lo;
+  p.kpm = key_padding_mask;
+  p.kend = kend;
+  p.ctx_hi = (__nv_bfloat16*)ctx_hi;
+  p.ctx_lo = (__nv_bfloat16*)ctx_lo;
+  p.ctx_f32 = ctx_f32;
+  p.t = t;
+  p.d = d;
+  p.scale_log2e = (float)(1.4426950408889634 / sqrt((double)kDH));
+  return npass == 3 ? launch_attention_tc<3>(mh, ml, p, batch, nhead, s)
+                    : launch_attention_tc<1>(mh, ml, p, batch, nhead, s);
+}
+
+}  // extern "C"

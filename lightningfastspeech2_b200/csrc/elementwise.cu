@@ -6,6 +6,8 @@
 #include <math.h>
 #include <stdarg.h>
 
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace lfs2 {
@@ -140,8 +142,8 @@ __global__ void add_layernorm_kernel(const float4* __restrict__ x, const float4*
 // thread = 4 channels x kDwT consecutive frames (sliding window held in registers)
 constexpr int kDwT = 8;
 __global__ void dwconv1d_kernel(const float4* __restrict__ x, const float4* __restrict__ wt,
-                                const float4* __restrict__ bias, float4* __restrict__ out, int batch, int t,
-                                int d4, int ksize, int nchunk) {
+                                const float4* __restrict__ bias, float4* __restrict__ out, uint2* __restrict__ out_hi,
+                                uint2* __restrict__ out_lo, int batch, int t, int d4, int ksize, int nchunk) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t total = (size_t)batch * nchunk * d4;
   if (i >= total) return;
@@ -172,10 +174,26 @@ __global__ void dwconv1d_kernel(const float4* __restrict__ x, const float4* __re
       }
     }
   }
-  float4* ob = out + (size_t)b * t * d4 + c;
+  const size_t obase = (size_t)b * t * d4 + c;
 #pragma unroll
   for (int o = 0; o < kDwT; ++o)
-    if (t0 + o < t) ob[(size_t)(t0 + o) * d4] = acc[o];
+    if (t0 + o < t) {
+      const size_t oi = obase + (size_t)(t0 + o) * d4;
+      if (out) out[oi] = acc[o];
+      if (out_hi) {  // bf16 hi/lo planes (x = hi + lo), the operand format of the tcgen05 GEMMs
+        __nv_bfloat16 h[4], l[4];
+        const float v[4] = {acc[o].x, acc[o].y, acc[o].z, acc[o].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          h[q] = __float2bfloat16_rn(v[q]);
+          l[q] = __float2bfloat16_rn(v[q] - __bfloat162float(h[q]));
+        }
+        out_hi[oi] = make_uint2((uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16),
+                                (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16));
+        out_lo[oi] = make_uint2((uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16),
+                                (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16));
+      }
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -356,17 +374,25 @@ int lfs2_add_layernorm(const float* x, const float* y, const float* gamma, const
 
 int lfs2_dwconv1d(const float* x, const float* wt, const float* bias, float* out, int batch, int t, int d,
                   int ksize, void* stream) {
-  LFS2_REQUIRE(x && wt && bias && out, LFS2_ERR_INVALID_ARG, "dwconv1d: null pointer");
+  return lfs2_dwconv1d_planes(x, wt, bias, out, nullptr, nullptr, batch, t, d, ksize, stream);
+}
+
+int lfs2_dwconv1d_planes(const float* x, const float* wt, const float* bias, float* out, void* out_hi, void* out_lo,
+                         int batch, int t, int d, int ksize, void* stream) {
+  LFS2_REQUIRE(x && wt && bias && (out || out_hi), LFS2_ERR_INVALID_ARG, "dwconv1d: null pointer");
+  LFS2_REQUIRE(!out_hi == !out_lo, LFS2_ERR_INVALID_ARG, "dwconv1d: out_hi and out_lo go together");
   if (batch == 0 || t == 0) return LFS2_OK;
   LFS2_REQUIRE(d > 0 && d % 4 == 0, LFS2_ERR_UNSUPPORTED, "dwconv1d: d=%d must be a multiple of 4", d);
   LFS2_REQUIRE(ksize > 0 && ksize % 2 == 1, LFS2_ERR_UNSUPPORTED,
                "dwconv1d: kernel size %d must be odd ('same' padding is asymmetric otherwise)", ksize);
-  LFS2_REQUIRE(aligned16(x) && aligned16(wt) && aligned16(bias) && aligned16(out), LFS2_ERR_INVALID_ARG,
-               "dwconv1d: pointers must be 16-byte aligned");
+  LFS2_REQUIRE(aligned16(x) && aligned16(wt) && aligned16(bias) && (!out || aligned16(out)) &&
+                   (!out_hi || (aligned16(out_hi) && aligned16(out_lo))),
+               LFS2_ERR_INVALID_ARG, "dwconv1d: pointers must be 16-byte aligned");
   int nchunk = ceil_div(t, kDwT);
   size_t total = (size_t)batch * nchunk * (d / 4);
   dwconv1d_kernel<<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(
-      (const float4*)x, (const float4*)wt, (const float4*)bias, (float4*)out, batch, t, d / 4, ksize, nchunk);
+      (const float4*)x, (const float4*)wt, (const float4*)bias, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, batch, t,
+      d / 4, ksize, nchunk);
   LFS2_CHECK_LAUNCH("dwconv1d");
   return LFS2_OK;
 }

@@ -20,7 +20,8 @@ from torch import nn
 
 from .. import ops
 from .loss import FastSpeech2Loss
-from .model import ConformerEncoderLayer, PositionalEncoding, SpeakerEmbedding, VarianceAdaptor
+from .model import (COMPUTE_MODES, ConformerEncoderLayer, PositionalEncoding, SpeakerEmbedding, VarianceAdaptor,
+                    _PackCache)
 from .noam import NoamLR
 
 try:  # the real Lightning base class when it is installed (it is not in this image)
@@ -238,6 +239,7 @@ class FastSpeech2(_Base):
         self.decoder = stack(hp.decoder_hidden, hp.decoder_head, hp.decoder_layers, hp.decoder_kernel_sizes,
                              hp.decoder_conv_filter_size, hp.decoder_dropout, hp.decoder_depthwise_conv)
         self.linear = nn.Linear(hp.decoder_hidden, hp.n_mels)
+        self._mel_pack = _PackCache()
         if fastdiff_head:  # same shape as the reference's head (:393-402); feeds only result["fastdiff_var"]
             self.fastdiff_linear = nn.Sequential(nn.Linear(hp.decoder_hidden, hp.decoder_hidden),
                                                  nn.Linear(hp.decoder_hidden, hp.n_mels))
@@ -252,6 +254,19 @@ class FastSpeech2(_Base):
                                     loss_weights)
 
     # ------------------------------------------------------------------------------------
+    compute_mode = "fp32"
+
+    def set_compute_mode(self, mode):
+        """"fp32": tcgen05 GEMM/attention on bf16 hi/lo split operands, 3 passes (fp32 parity, mel within 1e-3);
+        "bf16": single-pass bf16 operands, fp32 accumulate/residual/LayerNorm/softmax (mel within 1e-2);
+        "simt": the exact-fp32 CUDA-core kernels (ground truth on device, any shape)."""
+        if mode not in COMPUTE_MODES:
+            raise ValueError(f"compute_mode must be one of {COMPUTE_MODES}")
+        for m in self.modules():
+            if hasattr(type(m), "compute_mode"):
+                m.compute_mode = mode
+        return self
+
     def _max_frames(self):
         hp = self.hparams
         return hp.max_length * hp.sampling_rate / hp.hop_length  # float, 2756.25 by default
@@ -325,7 +340,12 @@ class FastSpeech2(_Base):
         output = ops.add_pe_spk_(variance_output["x"], pe, spk)
         tgt_mask = variance_output["tgt_mask"]
         output = self.decoder(output, src_key_padding_mask=tgt_mask)
-        mel = ops.linear(output, self.linear.weight, self.linear.bias, tag="mel_linear")
+        if self.compute_mode != "simt" and hp.decoder_hidden % 32 == 0 and hp.n_mels % 16 == 0:
+            wmel = self._mel_pack.get([self.linear.weight], lambda: ops.split_bf16(self.linear.weight.detach().contiguous()))
+            mel, _ = ops.gemm_tc(ops.planes_of(output), wmel, self.linear.bias,
+                                 npass=3 if self.compute_mode == "fp32" else 1, tag="mel_linear")
+        else:
+            mel = ops.linear(output, self.linear.weight, self.linear.bias, tag="mel_linear")
 
         result = {
             "mel": mel,

@@ -41,6 +41,21 @@ class _PackCache:
         return self._val
 
 
+COMPUTE_MODES = ("fp32", "bf16", "simt")
+
+
+def _npass(mode):
+    """fp32 = bf16 hi/lo split, 3 tensor-core passes per product (fp32 parity, <=1e-3 on mel);
+    bf16 = single pass on the hi planes (<=1e-2); simt = exact-fp32 CUDA-core kernels."""
+    if mode not in COMPUTE_MODES:
+        raise ValueError(f"compute_mode must be one of {COMPUTE_MODES}, got {mode!r}")
+    return 3 if mode == "fp32" else 1
+
+
+def _tc_ok(*dims):
+    return all(v % 32 == 0 for v in dims)
+
+
 def _require_inference(module, p, what):
     if module.training and p > 0:
         raise NotImplementedError(
@@ -109,8 +124,30 @@ class ConformerEncoderLayer(nn.Module):
             self.conv1 = nn.Conv1d(conv_in, fsz, kernel_size=k1, padding="same")
             self.conv2 = nn.Conv1d(fsz, conv_in, kernel_size=k2, padding="same")
         self._pack = _PackCache()
+        self._pack_tc = _PackCache()
+
+    compute_mode = "fp32"
 
     # -- weight repacks -------------------------------------------------------------------
+    def _build_pack_tc(self):
+        """bf16 hi/lo planes of every GEMM weight (operands of lfs2_gemm_tc)."""
+        p = self._packed()
+        sa = self.self_attn
+        w = {"in_proj": ops.split_bf16(sa.in_proj_weight.detach().contiguous()),
+             "out_proj": ops.split_bf16(sa.out_proj.weight.detach().contiguous())}
+        if self.depthwise:
+            w["pw1"] = ops.split_bf16(p["pw1_w"])
+            w["w_eff"] = ops.split_bf16(p["w_eff"])
+        else:
+            w["c1"] = ops.split_bf16(p["c1_wp"])
+            w["c2"] = ops.split_bf16(p["c2_wp"])
+        return w
+
+    def _packed_tc(self):
+        sa = self.self_attn
+        params = [sa.in_proj_weight, sa.out_proj.weight] + list(self.conv1.parameters()) + list(self.conv2.parameters())
+        return self._pack_tc.get(params, self._build_pack_tc)
+
     def _build_pack(self):
         p = {}
         if self.depthwise:
@@ -145,11 +182,55 @@ class ConformerEncoderLayer(nn.Module):
         _require_inference(self, self.p_drop, "ConformerEncoderLayer")
         x = src
         sa = self.self_attn
+        d = x.shape[-1]
+        fsz = self.conv1[1].weight.shape[0] if self.depthwise else self.conv1.weight.shape[0]
+        if self.compute_mode != "simt" and _tc_ok(d, fsz):
+            return self._forward_tc(x.contiguous(), src_key_padding_mask, _npass(self.compute_mode))
         qkv = ops.linear(x, sa.in_proj_weight, sa.in_proj_bias, tag="qkv_gemm")
         ctx = ops.attention(qkv, src_key_padding_mask, self.nhead)
         a = ops.linear(ctx, sa.out_proj.weight, sa.out_proj.bias, tag="out_proj_gemm")
         x1 = ops.add_layernorm(x, a, self.norm1.weight, self.norm1.bias, self.eps)
         y = self._ff_block(x1)
+        return ops.add_layernorm(x1, y, self.norm2.weight, self.norm2.bias, self.eps)
+
+    def _forward_tc(self, x, kpm, npass):
+        """tcgen05 path: every GEMM on bf16 hi/lo planes with fused bias/ReLU/residual+LayerNorm
+        epilogues; attention with Q/P in tensor memory; activations travel between kernels as
+        planes (GEMM operands) and fp32 (residual stream, depthwise conv input)."""
+        sa, w, p = self.self_attn, self._packed_tc(), self._packed()
+        d = x.shape[-1]
+        fuse_ln = d == 256  # the LayerNorm epilogue needs the whole row in one 256-column tile
+        xp = ops.planes_of(x)
+        if d // self.nhead == 128:
+            _, qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, want_f32=False, want_planes=True, npass=npass,
+                                 tag="qkv_gemm")
+            _, ctx = ops.attention_tc(qkv, kpm, self.nhead, npass=npass)
+        else:
+            qkv, _ = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, npass=npass, tag="qkv_gemm")
+            ctx = ops.split_bf16(ops.attention(qkv, kpm, self.nhead))
+        need_x1p = not self.depthwise
+        if fuse_ln:
+            x1, x1p = ops.gemm_tc(ctx, w["out_proj"], sa.out_proj.bias, residual=x, gamma=self.norm1.weight,
+                                  beta=self.norm1.bias, eps=self.eps, want_planes=need_x1p, npass=npass,
+                                  tag="out_proj_ln_gemm")
+        else:
+            a, _ = ops.gemm_tc(ctx, w["out_proj"], sa.out_proj.bias, npass=npass, tag="out_proj_gemm")
+            x1 = ops.add_layernorm(x, a, self.norm1.weight, self.norm1.bias, self.eps)
+            x1p = ops.split_bf16(x1) if need_x1p else None
+        if self.depthwise:
+            _, up = ops.dwconv1d_planes(x1, p["dw_wt"], self.conv1[0].bias)
+            _, vp = ops.gemm_tc(up, w["pw1"], self.conv1[1].bias, relu=True, want_f32=False, want_planes=True,
+                                npass=npass, tag="ffn1_gemm")
+            w2, b2, taps2 = w["w_eff"], p["b_eff"], 1
+        else:
+            _, vp = ops.gemm_tc(x1p, w["c1"], self.conv1.bias, taps=self.conv1.kernel_size[0], relu=True,
+                                want_f32=False, want_planes=True, npass=npass, tag="ffn1_gemm")
+            w2, b2, taps2 = w["c2"], self.conv2.bias, self.conv2.kernel_size[0]
+        if fuse_ln:
+            x2, x2p = ops.gemm_tc(vp, w2, b2, taps=taps2, residual=x1, gamma=self.norm2.weight, beta=self.norm2.bias,
+                                  eps=self.eps, want_planes=True, npass=npass, tag="ffn2_ln_gemm")
+            return ops.attach_planes(x2, x2p)
+        y, _ = ops.gemm_tc(vp, w2, b2, taps=taps2, npass=npass, tag="ffn2_gemm")
         return ops.add_layernorm(x1, y, self.norm2.weight, self.norm2.bias, self.eps)
 
     def _ff_block(self, x):
@@ -204,17 +285,37 @@ class VarianceConvolutionLayer(nn.Module):
         self.layers = nn.Sequential(Transpose(conv), nn.ReLU(), nn.LayerNorm(filter_size), nn.Dropout(dropout))
         self._pack = _PackCache()
 
+    compute_mode = "fp32"
+
     def _build_pack(self):
         conv = self.layers[0].module
         if self.depthwise:
-            return {"dw_wt": conv[0].weight[:, 0, :].t().contiguous(), "pw_w": conv[1].weight[:, :, 0].contiguous()}
+            p = {"dw_wt": conv[0].weight[:, 0, :].t().contiguous(), "pw_w": conv[1].weight[:, :, 0].contiguous()}
+            if conv[1].weight.is_cuda:
+                p["pw_planes"] = ops.split_bf16(p["pw_w"])
+            return p
         f, d, k = conv.weight.shape
-        return {"wp": conv.weight.permute(0, 2, 1).reshape(f, k * d).contiguous()}
+        p = {"wp": conv.weight.permute(0, 2, 1).reshape(f, k * d).contiguous()}
+        if conv.weight.is_cuda:
+            p["wp_planes"] = ops.split_bf16(p["wp"])
+        return p
 
     def forward(self, x):
         _require_inference(self, self.layers[3].p, "VarianceConvolutionLayer")
         conv, ln = self.layers[0].module, self.layers[2]
         p = self._pack.get(list(conv.parameters()), self._build_pack)
+        fsz = ln.weight.shape[0]
+        if self.compute_mode != "simt" and _tc_ok(x.shape[-1], fsz):
+            npass = _npass(self.compute_mode)
+            fuse = dict(gamma=ln.weight, beta=ln.bias, eps=ln.eps) if fsz == 256 else {}
+            if self.depthwise:
+                _, up = ops.dwconv1d_planes(x.contiguous(), p["dw_wt"], conv[0].bias)
+                h, _ = ops.gemm_tc(up, p["pw_planes"], conv[1].bias, relu=True, npass=npass,
+                                   tag="predictor_pw_ln_gemm", **fuse)
+            else:
+                h, _ = ops.gemm_tc(ops.planes_of(x), p["wp_planes"], conv.bias, taps=self.kernel_size, relu=True,
+                                   npass=npass, tag="predictor_conv_ln_gemm", **fuse)
+            return h if fuse else ops.add_layernorm(h, None, ln.weight, ln.bias, ln.eps)
         if self.depthwise:
             u = ops.dwconv1d(x, p["dw_wt"], conv[0].bias)
             h = ops.linear(u, p["pw_w"], conv[1].bias, relu=True, tag="predictor_pw_gemm")

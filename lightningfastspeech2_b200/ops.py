@@ -92,6 +92,7 @@ def add_pe_spk_(x, pe, spk):
     if t > pe.shape[-2]:
         raise ValueError(f"sequence length {t} exceeds the positional table ({pe.shape[-2]})")
     _launch("lfs2_add_pe_spk", _p(x), _p(pe), _p(spk), b, t, d, _s(), nbytes=2 * x.numel() * 4)
+    drop_planes(x)
     return x
 
 
@@ -183,6 +184,7 @@ def bucket_embed_add_(x, val, std, mean, bins, emb, idx_forced=None, acc=None, a
     _launch("lfs2_bucket_embed_add", _p(x), _p(val), float(std), float(mean), _p(bins),
                                                 emb.shape[0], _p(emb), _p(idx_forced), _p(idx_out), _p(acc), mode,
                                                 b * t, d, _s(), nbytes=4.0 * b * t * d * (2 + (acc is not None)))
+    drop_planes(x)
     return idx_out
 
 
@@ -237,6 +239,37 @@ class Planes:
         return self.hi.float() + self.lo.float()
 
 
+def attach_planes(x, planes):
+    """Remember the hi/lo planes a kernel already produced for the fp32 tensor x, so the next
+    tensor-core GEMM does not have to split it again (module APIs stay tensor -> tensor)."""
+    if planes is not None:
+        x._lfs2_planes = planes
+    return x
+
+
+def drop_planes(x):
+    if getattr(x, "_lfs2_planes", None) is not None:
+        x._lfs2_planes = None
+
+
+def planes_of(x):
+    p = getattr(x, "_lfs2_planes", None)
+    return p if p is not None else split_bf16(x.contiguous())
+
+
+def dwconv1d_planes(x, wt, bias, want_f32=False):
+    """depthwise conv writing bf16 hi/lo planes (and optionally fp32): x (B,T,d), wt (ksize,d)"""
+    _chk(x, torch.float32, "dwconv input", 3); _chk(wt, torch.float32, "dwconv weight", 2)
+    b, t, d = x.shape
+    out = torch.empty_like(x) if want_f32 else None
+    po = Planes(torch.empty(x.shape, device=x.device, dtype=torch.bfloat16),
+                torch.empty(x.shape, device=x.device, dtype=torch.bfloat16))
+    _launch("lfs2_dwconv1d_planes", _p(x), _p(wt), _p(bias), _p(out), _p(po.hi), _p(po.lo), b, t, d, wt.shape[0],
+            _s(), tag="lfs2_dwconv1d", flops=2.0 * b * t * d * wt.shape[0],
+            nbytes=(8.0 + 4.0 * int(want_f32)) * b * t * d)
+    return out, po
+
+
 def split_bf16(x):
     _chk(x, torch.float32, "split_bf16 input")
     hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
@@ -278,3 +311,27 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
             nbytes=4.0 * m * d + 4.0 * n * taps * d + 4.0 * m * n * (int(want_f32) + int(want_planes))
             + (4.0 * m * n if residual is not None else 0.0))
     return out, po
+
+
+def attention_tc(qkv, kpm, nhead, npass=3, want_f32=False, want_planes=True):
+    """qkv: Planes (B,T,3d) packed [q|k|v]; kpm (B,T) bool True=PAD -> (ctx f32 or None, ctx Planes or None)"""
+    if not isinstance(qkv, Planes):
+        raise TypeError("attention_tc: qkv must be Planes")
+    _chk(qkv.hi, torch.bfloat16, "qkv.hi", 3); _chk(qkv.lo, torch.bfloat16, "qkv.lo", 3)
+    b, t, d3 = qkv.shape
+    d = d3 // 3
+    if kpm is not None:
+        _chk(kpm, torch.bool, "key_padding_mask", 2)
+    dev = qkv.hi.device
+    ctx = torch.empty(b, t, d, device=dev, dtype=torch.float32) if want_f32 else None
+    po = Planes(torch.empty(b, t, d, device=dev, dtype=torch.bfloat16),
+                torch.empty(b, t, d, device=dev, dtype=torch.bfloat16)) if want_planes else None
+    ws = torch.empty(max(1, _lib.lib().lfs2_attention_tc_workspace_bytes(b)), device=dev, dtype=torch.uint8)
+    fl = 0.0
+    if PROFILE is not None:  # algorithmic flops: every query row x the utterance's VALID keys
+        nkeys = (~kpm).sum(1).double() if kpm is not None else torch.full((b,), float(t))
+        fl = float(4.0 * d * t * nkeys.sum())
+    _launch("lfs2_attention_tc", _p(qkv.hi), _p(qkv.lo), _p(kpm), _p(po.hi if po else None),
+            _p(po.lo if po else None), _p(ctx), _p(ws), b, t, d, nhead, npass, _s(), flops=fl,
+            nbytes=4.0 * qkv.hi.numel() + 4.0 * b * t * d * (int(want_f32) + int(want_planes)))
+    return ctx, po

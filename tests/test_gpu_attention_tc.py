@@ -1,0 +1,88 @@
+"""tcgen05 attention (lfs2_attention_tc) against an fp64 torch restatement of
+nn.MultiheadAttention's core (reference model.py:111-114 -> torch _sa_block): q scaled by
+head_dim^-1/2, -inf on PAD keys, softmax over keys, P.V.  npass=3 is the fp32-parity mode
+(tolerance 1e-4 abs on O(1) outputs), npass=1 the bf16 mode (3e-2)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from lightningfastspeech2_b200 import ops
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def ref_attention(qkv, kpm, nhead):
+    b, t, d3 = qkv.shape
+    d = d3 // 3
+    dh = d // nhead
+    q, k, v = qkv.double().split(d, dim=-1)
+    q = q.view(b, t, nhead, dh).transpose(1, 2) / math.sqrt(dh)
+    k = k.view(b, t, nhead, dh).transpose(1, 2)
+    v = v.view(b, t, nhead, dh).transpose(1, 2)
+    s = q @ k.transpose(-1, -2)
+    if kpm is not None:
+        s = s.masked_fill(kpm[:, None, None, :], float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return (p @ v).transpose(1, 2).reshape(b, t, d)
+
+
+def make(b, t, d, seed, lens=None, scale=1.0):
+    g = np.random.default_rng(seed)
+    qkv = torch.from_numpy((g.standard_normal((b, t, 3 * d)) * scale).astype(np.float32))
+    kpm = None
+    if lens is not None:
+        kpm = torch.arange(t)[None, :] >= torch.tensor(lens)[:, None]
+    return qkv, kpm
+
+
+@pytest.mark.parametrize("b,t,lens", [(2, 200, [200, 77]), (1, 64, None), (3, 1, None), (2, 130, [1, 129]),
+                                      (2, 700, [700, 333]), (1, 128, [64]), (4, 257, [257, 256, 65, 3])])
+@pytest.mark.parametrize("npass", [3, 1])
+def test_matches_fp64(b, t, lens, npass):
+    d, nhead = 256, 2
+    qkv, kpm = make(b, t, d, seed=t + b, lens=lens)
+    ref = ref_attention(qkv, kpm, nhead)
+    planes = ops.split_bf16(qkv.to(DEV))
+    ctx, cp = ops.attention_tc(planes, None if kpm is None else kpm.to(DEV), nhead, npass=npass, want_f32=True)
+    tol = 1e-4 if npass == 3 else 3e-2
+    err = (ctx.cpu() - ref).abs().max()
+    assert err < tol, float(err)
+    assert (cp.float().cpu() - ctx.cpu()).abs().max() < 1e-4
+
+
+def test_large_logits_and_growing_max():
+    """logit scale 6 => row maxima keep growing across key tiles: exercises the O rescale path"""
+    qkv, kpm = make(2, 500, 256, seed=5, lens=[500, 410], scale=2.5)
+    ref = ref_attention(qkv, kpm, 2)
+    ctx, _ = ops.attention_tc(ops.split_bf16(qkv.to(DEV)), kpm.to(DEV), 2, want_f32=True)
+    # |v| up to ~10 and logits of std 6: the split-bf16 products carry ~2^-16 relative error
+    assert (ctx.cpu() - ref).abs().max() < 1e-3
+
+
+def test_non_suffix_mask_and_fully_masked_utterance():
+    qkv, _ = make(3, 150, 256, seed=6)
+    g = torch.Generator().manual_seed(0)
+    kpm = torch.rand(3, 150, generator=g) < 0.4
+    kpm[1, :70] = True        # a whole leading key tile masked
+    kpm[2, :] = True          # no valid key at all -> NaN like torch
+    ref = ref_attention(qkv, kpm, 2)
+    ctx, _ = ops.attention_tc(ops.split_bf16(qkv.to(DEV)), kpm.to(DEV), 2, want_f32=True)
+    ctx = ctx.cpu()
+    assert torch.isnan(ref[2]).all() and torch.isnan(ctx[2]).all()
+    assert (ctx[:2] - ref[:2]).abs().max() < 1e-4
+
+
+def test_agrees_with_fp32_simt_attention():
+    qkv, kpm = make(2, 300, 256, seed=7, lens=[300, 190])
+    a = ops.attention(qkv.to(DEV), kpm.to(DEV), 2)
+    ctx, _ = ops.attention_tc(ops.split_bf16(qkv.to(DEV)), kpm.to(DEV), 2, want_f32=True)
+    assert (ctx - a).abs().max() < 1e-4
+
+
+def test_unsupported_head_dim_raises():
+    qkv, _ = make(1, 32, 192, seed=8)
+    with pytest.raises(NotImplementedError):
+        ops.attention_tc(ops.split_bf16(qkv.to(DEV)), None, 2)
