@@ -81,10 +81,12 @@ LFS2_API int lfs2_conv1d_dense(const float* x, const float* wp, const float* bia
  * of the reference's (d,1,ksize) weight.  replaces model.py:75-81 and model.py:545-551. */
 LFS2_API int lfs2_dwconv1d(const float* x, const float* wt, const float* bias, float* out,
                   int batch, int t, int d, int ksize, void* stream);
-/* same, writing the result as fp32 (out, may be NULL) and/or as bf16 hi/lo planes (the A
- * operand of the following pointwise lfs2_gemm_tc) */
-LFS2_API int lfs2_dwconv1d_planes(const float* x, const float* wt, const float* bias, float* out, void* out_hi,
-                                  void* out_lo, int batch, int t, int d, int ksize, void* stream);
+/* same, reading the input as fp32 (x) OR as bf16 hi/lo planes (x_hi, x_lo; x = NULL), and writing
+ * the result as fp32 (out, may be NULL) and/or as hi/lo planes (the A operand of the following
+ * pointwise lfs2_gemm_tc) */
+LFS2_API int lfs2_dwconv1d_planes(const float* x, const void* x_hi, const void* x_lo, const float* wt,
+                                  const float* bias, float* out, void* out_hi, void* out_lo, int batch, int t,
+                                  int d, int ksize, void* stream);
 
 /* Multi-head self attention core on a packed qkv (B,T,3d) tensor [q | k | v], heads =
  * contiguous d/nhead column blocks, q scaled by (d/nhead)^-1/2, PAD keys get -inf,
@@ -137,15 +139,18 @@ LFS2_API int lfs2_length_regulate_scatter(const void* x, const int64_t* cum, con
  *   w_hi/w_lo : (n, taps*d)        row-major bf16   (weights, tap-major for taps > 1)
  * acc[b,tt,:] = sum_j a[b, tt + j - (taps-1)/2, :] . w[:, j*d:(j+1)*d]^T   (rows outside [0,t) are zero)
  * npass = 3: hi.hi + lo.hi + hi.lo (fp32-parity, ~2^-16 relative); npass = 1: hi.hi only.
- * Epilogue, in fp32:  v = acc + bias ; relu ? max(v,0) ; if gamma: v = LayerNorm(v + residual)
- * (LayerNorm needs n == 256); written to out_f32 (batch*t, n) and/or as hi/lo planes.
+ * Residual: if res_hi/res_lo (batch, t, n) are given (with ident_hi = bf16 identity (n, n)), the
+ * tensor core also accumulates res_hi.I + res_lo.I, i.e. acc += residual, before the epilogue.
+ * Epilogue, in fp32:  v = acc + bias ; relu ? max(v,0) ; if gamma: v = LayerNorm(v) (needs n == 256);
+ * written EITHER to out_f32 (batch*t, n) OR as hi/lo planes (out_hi, out_lo), by coalesced TMA stores.
  * taps = 1 replaces the Linear / pointwise Conv1d GEMMs (model.py:82,92,111-114,552;
  * fastspeech2.py:723); taps = k replaces the dense Conv1d(d, n, k) (model.py:95-106,529-536);
- * the LayerNorm epilogue replaces norm1/norm2 + residual (model.py:114-115) and the predictor
+ * residual + LayerNorm replaces norm1/norm2 (model.py:114-115); ReLU + LayerNorm the predictor
  * ReLU -> LayerNorm (model.py:537-538,555-556). */
 LFS2_API int lfs2_gemm_tc(const void* a_hi, const void* a_lo, int batch, int t, int d, int taps,
                           const void* w_hi, const void* w_lo, int n, const float* bias, int relu,
-                          const float* residual, const float* gamma, const float* beta, float eps,
+                          const void* res_hi, const void* res_lo, const void* ident_hi,
+                          const float* gamma, const float* beta, float eps,
                           float* out_f32, void* out_hi, void* out_lo, int npass, void* stream);
 
 /* tensor-core multi-head self attention (head_dim 128) on the bf16 hi/lo planes of the packed
@@ -160,6 +165,9 @@ LFS2_API int lfs2_attention_tc_workspace_bytes(int batch);
 LFS2_API int lfs2_attention_tc(const void* qkv_hi, const void* qkv_lo, const uint8_t* key_padding_mask,
                                void* ctx_hi, void* ctx_lo, float* ctx_f32, void* workspace, int batch, int t,
                                int d, int nhead, int npass, void* stream);
+
+/* out = hi + lo (fp32) for n values (n % 4 == 0): the inverse of lfs2_split_bf16 up to 2^-17 relative */
+LFS2_API int lfs2_merge_planes(const void* hi, const void* lo, float* out, long long n, void* stream);
 
 /* hi = bf16(x), lo = bf16(x - hi) for n fp32 values (n % 4 == 0) */
 LFS2_API int lfs2_split_bf16(const float* x, void* hi, void* lo, long long n, void* stream);

@@ -22,7 +22,8 @@ SIGNATURES = {
     "lfs2_linear": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "lfs2_conv1d_dense": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp],
     "lfs2_dwconv1d": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "lfs2_dwconv1d_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "lfs2_dwconv1d_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "lfs2_merge_planes": [_vp, _vp, _vp, ctypes.c_longlong, _vp],
     "lfs2_attention": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "lfs2_add_layernorm": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
     "lfs2_rowdot_mask": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
@@ -30,7 +31,8 @@ SIGNATURES = {
     "lfs2_duration_round_guard": [_vp, _vp, _vp, _i, _i, _vp],
     "lfs2_length_regulate_scan": [_vp, _i, _vp, _vp, _vp, _i, _i, _vp],
     "lfs2_length_regulate_scatter": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
-    "lfs2_gemm_tc": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i, _vp],
+    "lfs2_gemm_tc": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i,
+                     _vp],
     "lfs2_attention_tc_workspace_bytes": [_i],
     "lfs2_attention_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "lfs2_split_bf16": [_vp, _vp, _vp, ctypes.c_longlong, _vp],

@@ -14,8 +14,8 @@
 //   warps: 0 = TMA producer (K and V rings, 3 stages each), 1 = MMA issuer (one thread),
 //   2..5 = softmax (thread = query row; TMEM lane quadrant = warp & 3).
 //   tensor-pipe order:  QK_0 QK_1 | PV_0 QK_2 | PV_1 QK_3 | ...   so softmax_{j+1} overlaps
-//   PV_j + QK_{j+2}.  The running maximum only moves upwards (exact online softmax); the O
-//   accumulator is rescaled in TMEM by the softmax warps only when some row's maximum grew.
+//   PV_j + QK_{j+2}.  Online softmax with a lazily updated exponent reference: the O
+//   accumulator is rescaled in TMEM only when a row's logits outgrow the reference by 2^8.
 //
 //   NPASS = 3: hi.hi + lo.hi + hi.lo for both products (fp32-parity mode); NPASS = 1: hi.hi.
 //   The softmax itself (max, exp2, sum, 1/l) is fp32.  PAD keys (key_padding_mask) and keys
@@ -294,10 +294,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       float tmax = s[0];
 #pragma unroll
       for (int i = 1; i < 64; ++i) tmax = fmaxf(tmax, s[i]);
-      const float m_new = fmaxf(m_run, tmax);
-      const bool grew = m_new > m_run && j > 0;
-      // O rescale (warp-collective TMEM access): only when some row of this warp moved its max
-      if (__any_sync(0xffffffffu, grew)) {
+      // Lazy rescale: m_run is the exponent reference, not necessarily the true running maximum.
+      // It is only moved (and O, l rescaled) when some row's logits exceed it by more than 2^8
+      // in the exp2 domain, so p <= 256 always and the O accumulator is almost never touched;
+      // softmax is shift-invariant, so the result is exact either way.
+      const bool grow = (j > 0) && ((tmax - m_run) * c > 8.f);  // (x - -inf) = inf: first finite tile moves it
+      if (j == 0) {
+        m_run = tmax;
+      } else if (__any_sync(0xffffffffu, grow)) {
+        const float m_new = fmaxf(m_run, tmax);
         mbar_wait(&pv_done, (j - 1) & 1);  // all PV products up to tile j-1 have landed in O
         tc_fence_after();
         const float alpha = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * c);
@@ -311,9 +316,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
           tmem_st32(tmem_base + kColO + cc * 32 + lane_off, o);
         }
         tmem_wait_st();
+        m_run = m_new;
       }
-      m_run = m_new;
-      const float mc = (m_new == -INFINITY) ? 0.f : m_new * c;
+      const float mc = (m_run == -INFINITY) ? 0.f : m_run * c;
       uint32_t ph[32], pl[32];
       float lsum = 0.f;
 #pragma unroll

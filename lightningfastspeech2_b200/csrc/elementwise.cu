@@ -141,7 +141,18 @@ __global__ void add_layernorm_kernel(const float4* __restrict__ x, const float4*
 // depthwise conv, channels-last: out[b,t,c] = bias[c] + sum_j wt[j,c] * x[b,t+j-h,c]
 // thread = 4 channels x kDwT consecutive frames (sliding window held in registers)
 constexpr int kDwT = 8;
-__global__ void dwconv1d_kernel(const float4* __restrict__ x, const float4* __restrict__ wt,
+__device__ __forceinline__ float4 planes_to_f4(uint2 h, uint2 l) {
+  float4 r;
+  r.x = __uint_as_float(h.x << 16) + __uint_as_float(l.x << 16);
+  r.y = __uint_as_float(h.x & 0xffff0000u) + __uint_as_float(l.x & 0xffff0000u);
+  r.z = __uint_as_float(h.y << 16) + __uint_as_float(l.y << 16);
+  r.w = __uint_as_float(h.y & 0xffff0000u) + __uint_as_float(l.y & 0xffff0000u);
+  return r;
+}
+
+template <bool IN_PLANES>
+__global__ void dwconv1d_kernel(const float4* __restrict__ x, const uint2* __restrict__ x_hi,
+                                const uint2* __restrict__ x_lo, const float4* __restrict__ wt,
                                 const float4* __restrict__ bias, float4* __restrict__ out, uint2* __restrict__ out_hi,
                                 uint2* __restrict__ out_lo, int batch, int t, int d4, int ksize, int nchunk) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,7 +163,7 @@ __global__ void dwconv1d_kernel(const float4* __restrict__ x, const float4* __re
   int b = (int)(i / ((size_t)d4 * nchunk));
   int t0 = chunk * kDwT;
   int h = (ksize - 1) / 2;
-  const float4* xb = x + (size_t)b * t * d4 + c;
+  const size_t xoff = (size_t)b * t * d4 + c;
   float4 acc[kDwT];
   float4 bz = bias[c];
 #pragma unroll
@@ -161,7 +172,9 @@ __global__ void dwconv1d_kernel(const float4* __restrict__ x, const float4* __re
   for (int j = 0; j < kDwT + ksize - 1; ++j) {
     int ti = t0 - h + j;
     if (ti < 0 || ti >= t) continue;
-    float4 xv = xb[(size_t)ti * d4];
+    float4 xv;
+    if (IN_PLANES) xv = planes_to_f4(x_hi[xoff + (size_t)ti * d4], x_lo[xoff + (size_t)ti * d4]);
+    else xv = x[xoff + (size_t)ti * d4];
 #pragma unroll
     for (int o = 0; o < kDwT; ++o) {
       int tap = j - o;
@@ -301,11 +314,31 @@ __global__ void bucket_embed_add_kernel(float4* __restrict__ x, const float* __r
   }
 }
 
+// x = hi + lo (fp32) from bf16 planes; one thread per 4 elements
+__global__ void merge_planes_kernel(const uint2* __restrict__ hi, const uint2* __restrict__ lo, float4* __restrict__ out,
+                                    size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n4) out[i] = planes_to_f4(hi[i], lo[i]);
+}
+
 }  // namespace lfs2
 
 using namespace lfs2;
 
 extern "C" {
+
+int lfs2_merge_planes(const void* hi, const void* lo, float* out, long long n, void* stream) {
+  LFS2_REQUIRE(hi && lo && out, LFS2_ERR_INVALID_ARG, "merge_planes: null pointer");
+  if (n == 0) return LFS2_OK;
+  LFS2_REQUIRE(n > 0 && n % 4 == 0, LFS2_ERR_UNSUPPORTED, "merge_planes: n must be a positive multiple of 4");
+  LFS2_REQUIRE(aligned16(hi) && aligned16(lo) && aligned16(out), LFS2_ERR_INVALID_ARG,
+               "merge_planes: pointers must be 16-byte aligned");
+  size_t n4 = (size_t)n / 4;
+  merge_planes_kernel<<<ceil_div(n4, 256), 256, 0, (cudaStream_t)stream>>>((const uint2*)hi, (const uint2*)lo,
+                                                                          (float4*)out, n4);
+  LFS2_CHECK_LAUNCH("merge_planes");
+  return LFS2_OK;
+}
 
 int lfs2_version(void) { return 100; }
 const char* lfs2_last_error(void) { return lfs2::g_err; }
@@ -374,25 +407,32 @@ int lfs2_add_layernorm(const float* x, const float* y, const float* gamma, const
 
 int lfs2_dwconv1d(const float* x, const float* wt, const float* bias, float* out, int batch, int t, int d,
                   int ksize, void* stream) {
-  return lfs2_dwconv1d_planes(x, wt, bias, out, nullptr, nullptr, batch, t, d, ksize, stream);
+  return lfs2_dwconv1d_planes(x, nullptr, nullptr, wt, bias, out, nullptr, nullptr, batch, t, d, ksize, stream);
 }
 
-int lfs2_dwconv1d_planes(const float* x, const float* wt, const float* bias, float* out, void* out_hi, void* out_lo,
-                         int batch, int t, int d, int ksize, void* stream) {
-  LFS2_REQUIRE(x && wt && bias && (out || out_hi), LFS2_ERR_INVALID_ARG, "dwconv1d: null pointer");
+int lfs2_dwconv1d_planes(const float* x, const void* x_hi, const void* x_lo, const float* wt, const float* bias,
+                         float* out, void* out_hi, void* out_lo, int batch, int t, int d, int ksize, void* stream) {
+  LFS2_REQUIRE((x || (x_hi && x_lo)) && wt && bias && (out || out_hi), LFS2_ERR_INVALID_ARG, "dwconv1d: null pointer");
+  LFS2_REQUIRE(!x || !x_hi, LFS2_ERR_INVALID_ARG, "dwconv1d: give the input as fp32 OR as planes");
   LFS2_REQUIRE(!out_hi == !out_lo, LFS2_ERR_INVALID_ARG, "dwconv1d: out_hi and out_lo go together");
   if (batch == 0 || t == 0) return LFS2_OK;
   LFS2_REQUIRE(d > 0 && d % 4 == 0, LFS2_ERR_UNSUPPORTED, "dwconv1d: d=%d must be a multiple of 4", d);
   LFS2_REQUIRE(ksize > 0 && ksize % 2 == 1, LFS2_ERR_UNSUPPORTED,
                "dwconv1d: kernel size %d must be odd ('same' padding is asymmetric otherwise)", ksize);
-  LFS2_REQUIRE(aligned16(x) && aligned16(wt) && aligned16(bias) && (!out || aligned16(out)) &&
+  LFS2_REQUIRE((!x || aligned16(x)) && (!x_hi || (aligned16(x_hi) && aligned16(x_lo))) && aligned16(wt) &&
+                   aligned16(bias) && (!out || aligned16(out)) &&
                    (!out_hi || (aligned16(out_hi) && aligned16(out_lo))),
                LFS2_ERR_INVALID_ARG, "dwconv1d: pointers must be 16-byte aligned");
   int nchunk = ceil_div(t, kDwT);
   size_t total = (size_t)batch * nchunk * (d / 4);
-  dwconv1d_kernel<<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(
-      (const float4*)x, (const float4*)wt, (const float4*)bias, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, batch, t,
-      d / 4, ksize, nchunk);
+  if (x)
+    dwconv1d_kernel<false><<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(
+        (const float4*)x, nullptr, nullptr, (const float4*)wt, (const float4*)bias, (float4*)out, (uint2*)out_hi,
+        (uint2*)out_lo, batch, t, d / 4, ksize, nchunk);
+  else
+    dwconv1d_kernel<true><<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(
+        nullptr, (const uint2*)x_hi, (const uint2*)x_lo, (const float4*)wt, (const float4*)bias, (float4*)out,
+        (uint2*)out_hi, (uint2*)out_lo, batch, t, d / 4, ksize, nchunk);
   LFS2_CHECK_LAUNCH("dwconv1d");
   return LFS2_OK;
 }

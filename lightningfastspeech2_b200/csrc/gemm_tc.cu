@@ -1,6 +1,7 @@
 // tcgen05 GEMM / implicit-GEMM Conv1d of the FFTBlock and predictor stacks:
 //
 //     acc[128 x N_TILE] (TMEM, fp32) = sum over (tap, k-slab)  A[rows + tap - half, slab] . W[n-tile, tap*d + slab]^T
+//                                      (+ residual[rows, n-tile] . I   -- the residual add rides the tensor pipe)
 //
 // * operands are bf16 "hi/lo" planes (x = hi + lo): NPASS = 3 issues hi.hi + lo.hi + hi.lo
 //   per k-step, which reproduces an fp32 product to ~2^-16 (fp32-parity mode); NPASS = 1
@@ -9,13 +10,17 @@
 //   64-byte swizzle); rows outside [0, T) of an utterance are zero-filled by TMA, which is
 //   exactly Conv1d's zero "same" padding, so Conv1d(d -> n, k) is k shifted GEMMs into one
 //   accumulator with no im2col.  W is an (n, taps*d) row-major tensor.
+// * the residual of the post-norm FFTBlock (x + f(x)) is added by the tensor core: its hi/lo
+//   planes are streamed as extra k-slabs against an identity weight (hi.I + lo.I, exact in the
+//   fp32 accumulator), so the epilogue never issues a strided global load.
 // * persistent CTAs (one per SM), warp-specialised: warp 0 = TMA producer, warp 1 = MMA
 //   issuer (one elected thread) + TMEM allocator, warps 2..5 = epilogue (thread = output row).
-//   4-stage smem ring (full/empty mbarriers), double-buffered TMEM accumulator so the
-//   epilogue of tile i overlaps the MMAs of tile i+1.
-// * epilogues (fused, thread-per-row, fp32): + bias, ReLU, + residual, LayerNorm over the
-//   full row (two-pass, statistics in fp32, staged through TMEM), outputs as fp32 and/or
-//   as bf16 hi/lo planes for the next GEMM.
+//   smem ring (full/empty mbarriers), double-buffered TMEM accumulator so the epilogue of
+//   tile i overlaps the MMAs of tile i+1.
+// * epilogue (fp32, thread-per-row): + bias, ReLU, LayerNorm over the full row (statistics in
+//   one TMEM pass, normalisation in a second), then 32-column chunks are written to a
+//   swizzled shared-memory staging buffer and leave as coalesced TMA tensor stores -- either
+//   fp32 or bf16 hi/lo planes for the next GEMM.  TMA clips rows/columns outside the tensor.
 #include "tc_common.cuh"
 
 namespace lfs2 {
@@ -23,41 +28,61 @@ namespace tc {
 
 constexpr int kBM = 128;     // rows per tile (UMMA M)
 constexpr int kBK = 32;      // k-slab: 32 bf16 = 64 bytes = one SWIZZLE_64B row
-constexpr int kStages = 4;
 constexpr int kGemmTcThreads = 192;
+constexpr int kStageChunk = kBM * 32 * 4;  // one 128 x 32 staging chunk: 16 KB (fp32) or 2 x 8 KB (hi | lo)
 
 struct GemmTcParams {
   int batch, t, d, taps, half;  // A is (batch, t, d); K = taps * d
   int n;                        // output columns
   int m_tiles_per_batch, n_tiles, total_tiles;
+  int has_residual;             // residual planes (batch, t, n) ride as extra k-slabs against I (n x n)
   const float* bias;            // (n) or null
   int relu;
-  const float* residual;        // (batch*t, n) or null   [LN mode]
-  const float* gamma;           // non-null => LayerNorm epilogue (requires n == N_TILE)
+  const float* gamma;           // LN only (n == N_TILE)
   const float* beta;
   float eps;
-  float* out_f32;               // (batch*t, n) or null
-  __nv_bfloat16* out_hi;        // (batch*t, n) or null
-  __nv_bfloat16* out_lo;
-};
-
-template <int N_TILE, int NPASS>
-struct SmemLayout {
-  static constexpr int kAPlane = kBM * kBK * 2;        // 8 KB
-  static constexpr int kWPlane = N_TILE * kBK * 2;
-  static constexpr int kStage = (NPASS == 3 ? 2 : 1) * (kAPlane + kWPlane);
-  static constexpr int kTotal = kStages * kStage + 1024;  // + alignment slack
 };
 
 template <int N_TILE, int NPASS, bool LN>
+struct SmemLayout {
+  static constexpr bool kHasLo = NPASS == 3 || LN;  // LN variants stream residual lo planes even in bf16 mode
+  static constexpr int kAPlane = kBM * kBK * 2;     // 8 KB
+  static constexpr int kWPlane = N_TILE * kBK * 2;
+  static constexpr int kStage = (kHasLo ? 2 : 1) * kAPlane + (NPASS == 3 ? 2 : 1) * kWPlane;
+  static constexpr int kOffWHi = kAPlane;
+  static constexpr int kOffALo = kAPlane + kWPlane;
+  static constexpr int kOffWLo = 2 * kAPlane + kWPlane;
+  static constexpr int kStages = (170 * 1024 - 2 * kStageChunk) / kStage > 6 ? 6 : (170 * 1024 - 2 * kStageChunk) / kStage;
+  static constexpr int kOffStaging = kStages * kStage;                 // 2 chunks, 1024-aligned (kStage % 1024 == 0)
+  static constexpr int kOffVec = kOffStaging + 2 * kStageChunk;        // bias | gamma | beta for LN: 3 * N_TILE floats
+  static constexpr int kTotal = kOffVec + (LN ? 3 * N_TILE * 4 : 0) + 1024;  // + alignment slack
+  static_assert(kStages >= 2, "not enough shared memory for a pipeline");
+  static_assert(kStage % 1024 == 0, "stage must keep 1024-byte alignment");
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+template <int N_TILE, int NPASS, bool LN, bool OUT_F32>
 __global__ void __launch_bounds__(kGemmTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
-               const GemmTcParams p) {
-  using L = SmemLayout<N_TILE, NPASS>;
+               const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
+               const __grid_constant__ CUtensorMap map_ident, const __grid_constant__ CUtensorMap map_o0,
+               const __grid_constant__ CUtensorMap map_o1, const GemmTcParams p) {
+  using L = SmemLayout<N_TILE, NPASS, LN>;
+  constexpr int kStages = L::kStages;
   constexpr int kAccCols = (N_TILE <= 32) ? 32 : (N_TILE <= 64) ? 64 : (N_TILE <= 128) ? 128 : 256;
   constexpr uint32_t kTmemCols = 2 * kAccCols;
-  constexpr int kChunks = (N_TILE + 31) / 32;
+  constexpr int kChunks = N_TILE / 32;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -65,15 +90,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int k_slabs = p.taps * (p.d / kBK);
+  const int a_slabs = p.taps * (p.d / kBK);
+  const int r_slabs = p.has_residual ? N_TILE / kBK : 0;
+  const int k_slabs = a_slabs + r_slabs;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_a_hi);
     prefetch_tmap(&map_w_hi);
-    if (NPASS == 3) {
-      prefetch_tmap(&map_a_lo);
-      prefetch_tmap(&map_w_lo);
-    }
+    prefetch_tmap(&map_o0);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -85,6 +109,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
+  if (LN && warp >= 2) {  // bias | gamma | beta -> shared (broadcast reads in the epilogue)
+    float* vec = reinterpret_cast<float*>(smem + L::kOffVec);
+    for (int i = threadIdx.x - 64; i < N_TILE; i += 128) {
+      vec[i] = p.bias ? p.bias[i] : 0.f;
+      vec[N_TILE + i] = p.gamma[i];
+      vec[2 * N_TILE + i] = p.beta[i];
+    }
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -100,15 +132,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         int b = m_tile / p.m_tiles_per_batch, t0 = (m_tile % p.m_tiles_per_batch) * kBM;
         int n0 = n_tile * N_TILE;
         for (int ks = 0; ks < k_slabs; ++ks) {
-          int tap = ks / (p.d / kBK), c0 = (ks % (p.d / kBK)) * kBK;
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * L::kStage;
-          mbar_expect_tx(&full_bar[stage], L::kStage);
-          tma_load_3d(st, &map_a_hi, &full_bar[stage], c0, t0 + tap - p.half, b);
-          tma_load_3d(st + L::kAPlane, &map_w_hi, &full_bar[stage], tap * p.d + c0, n0, 0);
-          if (NPASS == 3) {
-            tma_load_3d(st + L::kAPlane + L::kWPlane, &map_a_lo, &full_bar[stage], c0, t0 + tap - p.half, b);
-            tma_load_3d(st + 2 * L::kAPlane + L::kWPlane, &map_w_lo, &full_bar[stage], tap * p.d + c0, n0, 0);
+          if (ks < a_slabs) {
+            int tap = ks / (p.d / kBK), c0 = (ks % (p.d / kBK)) * kBK;
+            mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 2 : 1) * (L::kAPlane + L::kWPlane));
+            tma_load_3d(st, &map_a_hi, &full_bar[stage], c0, t0 + tap - p.half, b);
+            tma_load_3d(st + L::kOffWHi, &map_w_hi, &full_bar[stage], tap * p.d + c0, n0, 0);
+            if (NPASS == 3) {
+              tma_load_3d(st + L::kOffALo, &map_a_lo, &full_bar[stage], c0, t0 + tap - p.half, b);
+              tma_load_3d(st + L::kOffWLo, &map_w_lo, &full_bar[stage], tap * p.d + c0, n0, 0);
+            }
+          } else if (L::kHasLo) {  // residual slab: R_hi, R_lo against the identity block
+            int c0 = n0 + (ks - a_slabs) * kBK;
+            mbar_expect_tx(&full_bar[stage], 2 * L::kAPlane + L::kWPlane);
+            tma_load_3d(st, &map_r_hi, &full_bar[stage], c0, t0, b);
+            tma_load_3d(st + L::kOffALo, &map_r_lo, &full_bar[stage], c0, t0, b);
+            tma_load_3d(st + L::kOffWHi, &map_ident, &full_bar[stage], c0, n0, 0);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -134,19 +174,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           uint32_t sa_hi = smem_u32(smem + stage * L::kStage);
-          uint32_t sw_hi = sa_hi + L::kAPlane;
-          uint32_t sa_lo = sw_hi + L::kWPlane;
-          uint32_t sw_lo = sa_lo + L::kAPlane;
+          uint32_t sw_hi = sa_hi + L::kOffWHi;
+          uint32_t sa_lo = sa_hi + L::kOffALo;
+          uint32_t sw_lo = sa_hi + L::kOffWLo;
+          const bool res = ks >= a_slabs;
 #pragma unroll
           for (int k16 = 0; k16 < kBK / 16; ++k16) {
             uint32_t off = k16 * 32;  // 16 bf16 = 32 bytes along K inside the 64-byte swizzled row
             uint64_t a_hi = make_smem_desc(sa_hi + off, 16, 512, kSwizzle64);
             uint64_t w_hi = make_smem_desc(sw_hi + off, 16, 512, kSwizzle64);
             umma_f16(d_tmem, a_hi, w_hi, idesc, (ks | k16) ? 1u : 0u);
-            if (NPASS == 3) {
+            if (L::kHasLo && (NPASS == 3 || res)) {
               uint64_t a_lo = make_smem_desc(sa_lo + off, 16, 512, kSwizzle64);
-              uint64_t w_lo = make_smem_desc(sw_lo + off, 16, 512, kSwizzle64);
               umma_f16(d_tmem, a_lo, w_hi, idesc, 1u);
+            }
+            if (NPASS == 3 && !res) {
+              uint64_t w_lo = make_smem_desc(sw_lo + off, 16, 512, kSwizzle64);
               umma_f16(d_tmem, a_hi, w_lo, idesc, 1u);
             }
           }
@@ -162,17 +205,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   } else {
     // ===================== epilogue: warps 2..5, thread = one output row =====================
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    const int row_in_tile = quad * 32 + lane;
+    const int r = quad * 32 + lane;
+    const bool issuer = threadIdx.x == 64;  // issues / retires the TMA stores
+    const float* vec = reinterpret_cast<const float*>(smem + L::kOffVec);
+    uint8_t* staging = smem + L::kOffStaging;
     int it = 0;
+    uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       int acc = it & 1;
       uint32_t acc_phase = (it >> 1) & 1;
       int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
       int b = m_tile / p.m_tiles_per_batch, t0 = (m_tile % p.m_tiles_per_batch) * kBM;
       int n0 = n_tile * N_TILE;
-      int tt = t0 + row_in_tile;
-      bool row_ok = tt < p.t;
-      size_t row = (size_t)b * p.t + tt;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       uint32_t taddr = tmem_base + acc * kAccCols + ((uint32_t)(quad * 32) << 16);
@@ -180,53 +224,34 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
       float mean = 0.f, rstd = 1.f;
       if (LN) {
-        // pass 1: v = acc + bias (relu) + residual, written back to TMEM; row sum
-        float s = 0.f;
+        float s = 0.f, q = 0.f;
 #pragma unroll 1
         for (int c = 0; c < kChunks; ++c) {
           tmem_ld32(taddr + c * 32, v);
-          int col0 = n0 + c * 32;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = v[j] + (p.bias ? __ldg(p.bias + col0 + j) : 0.f);
+            float x = v[j] + vec[c * 32 + j];
             if (p.relu) x = fmaxf(x, 0.f);
-            v[j] = x;
+            s += x;
+            q = fmaf(x, x, q);
           }
-          if (p.residual && row_ok) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.residual + row * p.n + col0);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 r = r4[j];
-              v[4 * j] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-            }
-          }
-#pragma unroll
-          for (int j = 0; j < 32; ++j) s += v[j];
-          tmem_st32(taddr + c * 32, v);
         }
-        tmem_wait_st();
         mean = s * (1.f / N_TILE);
-        float q = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < kChunks; ++c) {
-          tmem_ld32(taddr + c * 32, v);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float dlt = v[j] - mean;
-            q = fmaf(dlt, dlt, q);
-          }
-        }
-        rstd = rsqrtf(q * (1.f / N_TILE) + p.eps);
+        rstd = rsqrtf(fmaxf(q * (1.f / N_TILE) - mean * mean, 0.f) + p.eps);
       }
 
 #pragma unroll 1
       for (int c = 0; c < kChunks; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.n) break;  // chunk entirely outside the tensor (n not a multiple of N_TILE)
         tmem_ld32(taddr + c * 32, v);
-        int col0 = n0 + c * 32;
         if (LN) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = (v[j] - mean) * rstd * __ldg(p.gamma + col0 + j) + __ldg(p.beta + col0 + j);
+          for (int j = 0; j < 32; ++j) {
+            float x = v[j] + vec[c * 32 + j];
+            if (p.relu) x = fmaxf(x, 0.f);
+            v[j] = (x - mean) * rstd * vec[N_TILE + c * 32 + j] + vec[2 * N_TILE + c * 32 + j];
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -236,42 +261,49 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             v[j] = x;
           }
         }
-        if (row_ok) {
-          // n is a multiple of 16: a 32-column chunk is either fully or half inside
-          int ncols = min(32, p.n - col0);
-          if (ncols > 0) {
-            if (p.out_f32) {
-              float4* o = reinterpret_cast<float4*>(p.out_f32 + row * p.n + col0);
+        uint8_t* sb = staging + (chunk_ctr & 1) * kStageChunk;
+        ++chunk_ctr;
+        if (OUT_F32) {  // 128 rows x 128 B, SWIZZLE_128B: 16-byte unit i of row r lives at unit i ^ (r & 7)
+          uint8_t* row = sb + r * 128;
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                if (4 * j < ncols) o[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-            }
-            if (p.out_hi) {
-              uint32_t hi[16], lo[16];
+          for (int i = 0; i < 8; ++i)
+            *reinterpret_cast<float4*>(row + ((i ^ (r & 7)) << 4)) =
+                make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {        // two 128 rows x 64 B planes, SWIZZLE_64B: unit i of row r at i ^ ((r >> 1) & 3)
+          uint32_t hi[16], lo[16];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                __nv_bfloat16 h0, l0, h1, l1;
-                split_bf16(v[2 * j], h0, l0);
-                split_bf16(v[2 * j + 1], h1, l1);
-                hi[j] = pack_bf16(h0, h1);
-                lo[j] = pack_bf16(l0, l1);
-              }
-              uint4* oh = reinterpret_cast<uint4*>(p.out_hi + row * p.n + col0);
-              uint4* ol = reinterpret_cast<uint4*>(p.out_lo + row * p.n + col0);
-#pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (8 * j < ncols) {
-                  oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-                  ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-                }
-            }
+          for (int j = 0; j < 16; ++j) {
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(v[2 * j], h0, l0);
+            split_bf16(v[2 * j + 1], h1, l1);
+            hi[j] = pack_bf16(h0, h1);
+            lo[j] = pack_bf16(l0, l1);
           }
+          uint8_t* rh = sb + r * 64;
+          uint8_t* rl = rh + kStageChunk / 2;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int u = (i ^ ((r >> 1) & 3)) << 4;
+            *reinterpret_cast<uint4*>(rh + u) = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+            *reinterpret_cast<uint4*>(rl + u) = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        // the store of the previous chunk (other buffer) must have finished READING before the
+        // threads that pass this barrier start overwriting that buffer for the next chunk
+        if (issuer) tma_store_wait_read0();
+        epi_bar_sync();
+        if (issuer) {
+          tma_store_3d(&map_o0, sb, col0, t0, b);
+          if (!OUT_F32) tma_store_3d(&map_o1, sb + kStageChunk / 2, col0, t0, b);
+          tma_store_commit();
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
     }
+    if (issuer) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -295,28 +327,36 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
-bool make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0,
-                  uint32_t box1, int swizzle_bytes) {
+bool make_tmap_3d_ex(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
+                     uint32_t box0, uint32_t box1, int swizzle_bytes) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t dims[3] = {d0, d1, d2};
-  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint64_t strides[2] = {d0 * elem_bytes, d0 * d1 * elem_bytes};
   cuuint32_t box[3] = {box0, box1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
+                   const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 
-template <int N_TILE, int NPASS, bool LN>
-static int launch_gemm_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
-                          const GemmTcParams& p, cudaStream_t s) {
-  using L = SmemLayout<N_TILE, NPASS>;
-  auto kern = gemm_tc_kernel<N_TILE, NPASS, LN>;
+bool make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0,
+                  uint32_t box1, int swizzle_bytes) {
+  return make_tmap_3d_ex(out, base, 2, d0, d1, d2, box0, box1, swizzle_bytes);
+}
+
+struct GemmTcMaps {
+  CUtensorMap ah, al, wh, wl, rh, rl, ident, o0, o1;
+};
+
+template <int N_TILE, int NPASS, bool LN, bool OUT_F32>
+static int launch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, cudaStream_t s) {
+  using L = SmemLayout<N_TILE, NPASS, LN>;
+  auto kern = gemm_tc_kernel<N_TILE, NPASS, LN, OUT_F32>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
@@ -326,9 +366,16 @@ static int launch_gemm_tc(const CUtensorMap& ah, const CUtensorMap& al, const CU
     configured = true;
   }
   int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  kern<<<grid, kGemmTcThreads, L::kTotal, s>>>(ah, al, wh, wl, p);
+  kern<<<grid, kGemmTcThreads, L::kTotal, s>>>(m.ah, m.al, m.wh, m.wl, m.rh, m.rl, m.ident, m.o0, m.o1, p);
   LFS2_CHECK_LAUNCH("gemm_tc");
   return LFS2_OK;
+}
+
+template <int N_TILE, bool LN>
+static int dispatch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, int npass, bool out_f32, cudaStream_t s) {
+  if (npass == 3)
+    return out_f32 ? launch_gemm_tc<N_TILE, 3, LN, true>(m, p, s) : launch_gemm_tc<N_TILE, 3, LN, false>(m, p, s);
+  return out_f32 ? launch_gemm_tc<N_TILE, 1, LN, true>(m, p, s) : launch_gemm_tc<N_TILE, 1, LN, false>(m, p, s);
 }
 
 }  // namespace tc
@@ -340,8 +387,9 @@ using namespace lfs2::tc;
 extern "C" {
 
 int lfs2_gemm_tc(const void* a_hi, const void* a_lo, int batch, int t, int d, int taps, const void* w_hi,
-                 const void* w_lo, int n, const float* bias, int relu, const float* residual, const float* gamma,
-                 const float* beta, float eps, float* out_f32, void* out_hi, void* out_lo, int npass, void* stream) {
+                 const void* w_lo, int n, const float* bias, int relu, const void* res_hi, const void* res_lo,
+                 const void* ident_hi, const float* gamma, const float* beta, float eps, float* out_f32,
+                 void* out_hi, void* out_lo, int npass, void* stream) {
   LFS2_REQUIRE(a_hi && w_hi, LFS2_ERR_INVALID_ARG, "gemm_tc: null operand");
   LFS2_REQUIRE(npass == 1 || npass == 3, LFS2_ERR_INVALID_ARG, "gemm_tc: npass must be 1 or 3");
   LFS2_REQUIRE(npass == 1 || (a_lo && w_lo), LFS2_ERR_INVALID_ARG, "gemm_tc: npass=3 needs the lo planes");
@@ -350,27 +398,43 @@ int lfs2_gemm_tc(const void* a_hi, const void* a_lo, int batch, int t, int d, in
   LFS2_REQUIRE(taps % 2 == 1, LFS2_ERR_UNSUPPORTED, "gemm_tc: kernel size %d must be odd", taps);
   LFS2_REQUIRE(d % kBK == 0, LFS2_ERR_UNSUPPORTED, "gemm_tc: d=%d must be a multiple of %d", d, kBK);
   LFS2_REQUIRE(n % 16 == 0, LFS2_ERR_UNSUPPORTED, "gemm_tc: n=%d must be a multiple of 16", n);
-  LFS2_REQUIRE(out_f32 || out_hi, LFS2_ERR_INVALID_ARG, "gemm_tc: no output");
+  LFS2_REQUIRE((out_f32 != nullptr) != (out_hi != nullptr), LFS2_ERR_INVALID_ARG,
+               "gemm_tc: exactly one of out_f32 / out_hi+out_lo");
   LFS2_REQUIRE(!out_hi || out_lo, LFS2_ERR_INVALID_ARG, "gemm_tc: out_hi without out_lo");
   LFS2_REQUIRE(aligned16(a_hi) && aligned16(w_hi) && (!a_lo || aligned16(a_lo)) && (!w_lo || aligned16(w_lo)) &&
                    (!out_f32 || aligned16(out_f32)) && (!out_hi || (aligned16(out_hi) && aligned16(out_lo))) &&
-                   (!residual || aligned16(residual)),
+                   (!res_hi || (aligned16(res_hi) && aligned16(res_lo))),
                LFS2_ERR_INVALID_ARG, "gemm_tc: pointers must be 16-byte aligned");
   const bool ln = gamma != nullptr;
   LFS2_REQUIRE(!ln || beta, LFS2_ERR_INVALID_ARG, "gemm_tc: gamma without beta");
-  LFS2_REQUIRE(ln || !residual, LFS2_ERR_UNSUPPORTED, "gemm_tc: residual is only fused with LayerNorm");
-  int n_tile = ln ? n : (n % 256 == 0 ? 256 : (n % 128 == 0 ? 128 : (n <= 128 ? 128 : 0)));
+  LFS2_REQUIRE(!res_hi || (ln && res_lo && ident_hi), LFS2_ERR_UNSUPPORTED,
+               "gemm_tc: the residual (hi, lo planes + identity) is only fused with LayerNorm");
+  LFS2_REQUIRE(!res_hi || !relu, LFS2_ERR_UNSUPPORTED, "gemm_tc: relu with a residual is not a reference pattern");
+  int n_tile = ln ? n : (n % 256 == 0 ? 256 : 128);
   if (ln) LFS2_REQUIRE(n == 256, LFS2_ERR_UNSUPPORTED, "gemm_tc: LayerNorm epilogue needs n == 256 (got %d)", n);
-  LFS2_REQUIRE(n_tile != 0, LFS2_ERR_UNSUPPORTED, "gemm_tc: n=%d not tileable", n);
 
-  CUtensorMap ah, al, wh, wl;
+  GemmTcMaps m;
   const uint64_t ktot = (uint64_t)taps * d;
-  bool ok = make_tmap_3d(&ah, a_hi, d, t, batch, kBK, kBM, 64) && make_tmap_3d(&wh, w_hi, ktot, n, 1, kBK, n_tile, 64);
+  bool ok = make_tmap_3d(&m.ah, a_hi, d, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.wh, w_hi, ktot, n, 1, kBK, n_tile, 64);
   if (npass == 3)
-    ok = ok && make_tmap_3d(&al, a_lo, d, t, batch, kBK, kBM, 64) && make_tmap_3d(&wl, w_lo, ktot, n, 1, kBK, n_tile, 64);
+    ok = ok && make_tmap_3d(&m.al, a_lo, d, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.wl, w_lo, ktot, n, 1, kBK, n_tile, 64);
   else {
-    al = ah;
-    wl = wh;
+    m.al = m.ah;
+    m.wl = m.wh;
+  }
+  if (res_hi)
+    ok = ok && make_tmap_3d(&m.rh, res_hi, n, t, batch, kBK, kBM, 64) &&
+         make_tmap_3d(&m.rl, res_lo, n, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.ident, ident_hi, n, n, 1, kBK, n_tile, 64);
+  else {
+    m.rh = m.ah;
+    m.rl = m.ah;
+    m.ident = m.wh;
+  }
+  if (out_f32) {
+    ok = ok && make_tmap_3d_ex(&m.o0, out_f32, 4, n, t, batch, 32, kBM, 128);
+    m.o1 = m.o0;
+  } else {
+    ok = ok && make_tmap_3d(&m.o0, out_hi, n, t, batch, 32, kBM, 64) && make_tmap_3d(&m.o1, out_lo, n, t, batch, 32, kBM, 64);
   }
   LFS2_REQUIRE(ok, LFS2_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed (driver entry point %s)",
                get_encode_tiled() ? "found" : "missing");
@@ -381,18 +445,12 @@ int lfs2_gemm_tc(const void* a_hi, const void* a_lo, int batch, int t, int d, in
   p.m_tiles_per_batch = (t + kBM - 1) / kBM;
   p.n_tiles = (n + n_tile - 1) / n_tile;
   p.total_tiles = batch * p.m_tiles_per_batch * p.n_tiles;
-  p.bias = bias; p.relu = relu; p.residual = residual; p.gamma = gamma; p.beta = beta; p.eps = eps;
-  p.out_f32 = out_f32; p.out_hi = (__nv_bfloat16*)out_hi; p.out_lo = (__nv_bfloat16*)out_lo;
+  p.has_residual = res_hi != nullptr;
+  p.bias = bias; p.relu = relu; p.gamma = gamma; p.beta = beta; p.eps = eps;
   cudaStream_t s = (cudaStream_t)stream;
-  if (ln) {
-    return npass == 3 ? launch_gemm_tc<256, 3, true>(ah, al, wh, wl, p, s)
-                      : launch_gemm_tc<256, 1, true>(ah, al, wh, wl, p, s);
-  }
-  if (n_tile == 256)
-    return npass == 3 ? launch_gemm_tc<256, 3, false>(ah, al, wh, wl, p, s)
-                      : launch_gemm_tc<256, 1, false>(ah, al, wh, wl, p, s);
-  return npass == 3 ? launch_gemm_tc<128, 3, false>(ah, al, wh, wl, p, s)
-                    : launch_gemm_tc<128, 1, false>(ah, al, wh, wl, p, s);
+  if (ln) return dispatch_gemm_tc<256, true>(m, p, npass, out_f32 != nullptr, s);
+  if (n_tile == 256) return dispatch_gemm_tc<256, false>(m, p, npass, out_f32 != nullptr, s);
+  return dispatch_gemm_tc<128, false>(m, p, npass, out_f32 != nullptr, s);
 }
 
 // x (n) fp32 -> hi/lo bf16 planes

@@ -78,11 +78,20 @@ class TransformerStack(nn.Module):
         super().__init__()
         self.layers = nn.ModuleList(layers)
 
-    def forward(self, src, mask=None, src_key_padding_mask=None):
+    def forward(self, src, mask=None, src_key_padding_mask=None, return_planes=False):
+        """return_planes=True (tensor-core path only) hands the result back as bf16 hi/lo planes,
+        the operand format of the next GEMM, instead of materialising an fp32 tensor."""
+        if mask is None and all(mod.tc_capable(src.shape[-1]) for mod in self.layers):
+            xp = ops.planes_of(src)
+            for mod in self.layers:
+                if mod.training and mod.p_drop > 0:
+                    raise NotImplementedError("dropout in training mode is not implemented by the CUDA path")
+                xp = mod.forward_planes(xp, src_key_padding_mask)
+            return xp if return_planes else ops.merge_planes(xp)
         out = src
         for mod in self.layers:
             out = mod(out, src_mask=mask, src_key_padding_mask=src_key_padding_mask)
-        return out
+        return ops.planes_of(out) if return_planes else out
 
 
 class FastSpeech2(_Base):
@@ -339,12 +348,13 @@ class FastSpeech2(_Base):
                                                 control=control)
         output = ops.add_pe_spk_(variance_output["x"], pe, spk)
         tgt_mask = variance_output["tgt_mask"]
-        output = self.decoder(output, src_key_padding_mask=tgt_mask)
         if self.compute_mode != "simt" and hp.decoder_hidden % 32 == 0 and hp.n_mels % 16 == 0:
+            output = self.decoder(output, src_key_padding_mask=tgt_mask, return_planes=True)
             wmel = self._mel_pack.get([self.linear.weight], lambda: ops.split_bf16(self.linear.weight.detach().contiguous()))
-            mel, _ = ops.gemm_tc(ops.planes_of(output), wmel, self.linear.bias,
-                                 npass=3 if self.compute_mode == "fp32" else 1, tag="mel_linear")
+            mel = ops.gemm_tc(output, wmel, self.linear.bias, npass=3 if self.compute_mode == "fp32" else 1,
+                              tag="mel_linear")
         else:
+            output = self.decoder(output, src_key_padding_mask=tgt_mask)
             mel = ops.linear(output, self.linear.weight, self.linear.bias, tag="mel_linear")
 
         result = {

@@ -182,10 +182,8 @@ class ConformerEncoderLayer(nn.Module):
         _require_inference(self, self.p_drop, "ConformerEncoderLayer")
         x = src
         sa = self.self_attn
-        d = x.shape[-1]
-        fsz = self.conv1[1].weight.shape[0] if self.depthwise else self.conv1.weight.shape[0]
-        if self.compute_mode != "simt" and _tc_ok(d, fsz):
-            return self._forward_tc(x.contiguous(), src_key_padding_mask, _npass(self.compute_mode))
+        if self.tc_capable(x.shape[-1]):
+            return ops.merge_planes(self.forward_planes(ops.planes_of(x), src_key_padding_mask))
         qkv = ops.linear(x, sa.in_proj_weight, sa.in_proj_bias, tag="qkv_gemm")
         ctx = ops.attention(qkv, src_key_padding_mask, self.nhead)
         a = ops.linear(ctx, sa.out_proj.weight, sa.out_proj.bias, tag="out_proj_gemm")
@@ -193,44 +191,54 @@ class ConformerEncoderLayer(nn.Module):
         y = self._ff_block(x1)
         return ops.add_layernorm(x1, y, self.norm2.weight, self.norm2.bias, self.eps)
 
-    def _forward_tc(self, x, kpm, npass):
-        """tcgen05 path: every GEMM on bf16 hi/lo planes with fused bias/ReLU/residual+LayerNorm
-        epilogues; attention with Q/P in tensor memory; activations travel between kernels as
-        planes (GEMM operands) and fp32 (residual stream, depthwise conv input)."""
+    def tc_capable(self, d):
+        fsz = self.conv1[1].weight.shape[0] if self.depthwise else self.conv1.weight.shape[0]
+        return self.compute_mode != "simt" and _tc_ok(d, fsz)
+
+    def forward_planes(self, xp, kpm):
+        """tcgen05 path, planes in -> planes out.  Activations travel between kernels only as bf16
+        hi/lo planes (x = hi + lo to 2^-17): every GEMM has fused bias/ReLU epilogues, the
+        residual add rides the tensor core (identity slabs) and LayerNorm is the epilogue of the
+        out-proj and FFN-2 GEMMs; attention keeps Q/P in tensor memory."""
+        npass = _npass(self.compute_mode)
         sa, w, p = self.self_attn, self._packed_tc(), self._packed()
-        d = x.shape[-1]
-        fuse_ln = d == 256  # the LayerNorm epilogue needs the whole row in one 256-column tile
-        xp = ops.planes_of(x)
+        d = xp.shape[-1]
+        if d != 256:
+            return ops.planes_of(self._forward_tc_unfused_ln(ops.merge_planes(xp), xp, kpm, npass))
         if d // self.nhead == 128:
-            _, qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, want_f32=False, want_planes=True, npass=npass,
-                                 tag="qkv_gemm")
+            qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="planes", npass=npass, tag="qkv_gemm")
             _, ctx = ops.attention_tc(qkv, kpm, self.nhead, npass=npass)
         else:
-            qkv, _ = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, npass=npass, tag="qkv_gemm")
+            qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, npass=npass, tag="qkv_gemm")
             ctx = ops.split_bf16(ops.attention(qkv, kpm, self.nhead))
-        need_x1p = not self.depthwise
-        if fuse_ln:
-            x1, x1p = ops.gemm_tc(ctx, w["out_proj"], sa.out_proj.bias, residual=x, gamma=self.norm1.weight,
-                                  beta=self.norm1.bias, eps=self.eps, want_planes=need_x1p, npass=npass,
-                                  tag="out_proj_ln_gemm")
-        else:
-            a, _ = ops.gemm_tc(ctx, w["out_proj"], sa.out_proj.bias, npass=npass, tag="out_proj_gemm")
-            x1 = ops.add_layernorm(x, a, self.norm1.weight, self.norm1.bias, self.eps)
-            x1p = ops.split_bf16(x1) if need_x1p else None
+        x1p = ops.gemm_tc(ctx, w["out_proj"], sa.out_proj.bias, residual=xp, gamma=self.norm1.weight,
+                          beta=self.norm1.bias, eps=self.eps, out="planes", npass=npass, tag="out_proj_ln_gemm")
         if self.depthwise:
-            _, up = ops.dwconv1d_planes(x1, p["dw_wt"], self.conv1[0].bias)
-            _, vp = ops.gemm_tc(up, w["pw1"], self.conv1[1].bias, relu=True, want_f32=False, want_planes=True,
-                                npass=npass, tag="ffn1_gemm")
+            up = ops.dwconv1d_planes(x1p, p["dw_wt"], self.conv1[0].bias)
+            vp = ops.gemm_tc(up, w["pw1"], self.conv1[1].bias, relu=True, out="planes", npass=npass, tag="ffn1_gemm")
             w2, b2, taps2 = w["w_eff"], p["b_eff"], 1
         else:
-            _, vp = ops.gemm_tc(x1p, w["c1"], self.conv1.bias, taps=self.conv1.kernel_size[0], relu=True,
-                                want_f32=False, want_planes=True, npass=npass, tag="ffn1_gemm")
+            vp = ops.gemm_tc(x1p, w["c1"], self.conv1.bias, taps=self.conv1.kernel_size[0], relu=True, out="planes",
+                             npass=npass, tag="ffn1_gemm")
             w2, b2, taps2 = w["c2"], self.conv2.bias, self.conv2.kernel_size[0]
-        if fuse_ln:
-            x2, x2p = ops.gemm_tc(vp, w2, b2, taps=taps2, residual=x1, gamma=self.norm2.weight, beta=self.norm2.bias,
-                                  eps=self.eps, want_planes=True, npass=npass, tag="ffn2_ln_gemm")
-            return ops.attach_planes(x2, x2p)
-        y, _ = ops.gemm_tc(vp, w2, b2, taps=taps2, npass=npass, tag="ffn2_gemm")
+        return ops.gemm_tc(vp, w2, b2, taps=taps2, residual=x1p, gamma=self.norm2.weight, beta=self.norm2.bias,
+                           eps=self.eps, out="planes", npass=npass, tag="ffn2_ln_gemm")
+
+    def _forward_tc_unfused_ln(self, x, xp, kpm, npass):
+        """d != 256 (e.g. the 76 M config, d = 768): tensor-core GEMMs, LayerNorm as its own kernel."""
+        sa, w, p = self.self_attn, self._packed_tc(), self._packed()
+        qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, npass=npass, tag="qkv_gemm")
+        ctx = ops.split_bf16(ops.attention(qkv, kpm, self.nhead))
+        a = ops.gemm_tc(ctx, w["out_proj"], sa.out_proj.bias, npass=npass, tag="out_proj_gemm")
+        x1 = ops.add_layernorm(x, a, self.norm1.weight, self.norm1.bias, self.eps)
+        if self.depthwise:
+            up = ops.dwconv1d_planes(x1, p["dw_wt"], self.conv1[0].bias)
+            vp = ops.gemm_tc(up, w["pw1"], self.conv1[1].bias, relu=True, out="planes", npass=npass, tag="ffn1_gemm")
+            y = ops.gemm_tc(vp, w["w_eff"], p["b_eff"], npass=npass, tag="ffn2_gemm")
+        else:
+            vp = ops.gemm_tc(ops.split_bf16(x1), w["c1"], self.conv1.bias, taps=self.conv1.kernel_size[0], relu=True,
+                             out="planes", npass=npass, tag="ffn1_gemm")
+            y = ops.gemm_tc(vp, w["c2"], self.conv2.bias, taps=self.conv2.kernel_size[0], npass=npass, tag="ffn2_gemm")
         return ops.add_layernorm(x1, y, self.norm2.weight, self.norm2.bias, self.eps)
 
     def _ff_block(self, x):
@@ -300,7 +308,9 @@ class VarianceConvolutionLayer(nn.Module):
             p["wp_planes"] = ops.split_bf16(p["wp"])
         return p
 
-    def forward(self, x):
+    def forward(self, x, out="f32"):
+        """x: fp32 (B,T,d) or Planes; out="planes" keeps the result as hi/lo planes for the next layer
+        (tensor-core path with the fused ReLU+LayerNorm epilogue only)."""
         _require_inference(self, self.layers[3].p, "VarianceConvolutionLayer")
         conv, ln = self.layers[0].module, self.layers[2]
         p = self._pack.get(list(conv.parameters()), self._build_pack)
@@ -308,14 +318,18 @@ class VarianceConvolutionLayer(nn.Module):
         if self.compute_mode != "simt" and _tc_ok(x.shape[-1], fsz):
             npass = _npass(self.compute_mode)
             fuse = dict(gamma=ln.weight, beta=ln.bias, eps=ln.eps) if fsz == 256 else {}
+            out = out if fuse else "f32"
             if self.depthwise:
-                _, up = ops.dwconv1d_planes(x.contiguous(), p["dw_wt"], conv[0].bias)
-                h, _ = ops.gemm_tc(up, p["pw_planes"], conv[1].bias, relu=True, npass=npass,
-                                   tag="predictor_pw_ln_gemm", **fuse)
+                up = ops.dwconv1d_planes(x if isinstance(x, ops.Planes) else x.contiguous(), p["dw_wt"], conv[0].bias)
+                h = ops.gemm_tc(up, p["pw_planes"], conv[1].bias, relu=True, npass=npass, out=out,
+                                tag="predictor_pw_ln_gemm", **fuse)
             else:
-                h, _ = ops.gemm_tc(ops.planes_of(x), p["wp_planes"], conv.bias, taps=self.kernel_size, relu=True,
-                                   npass=npass, tag="predictor_conv_ln_gemm", **fuse)
+                xp = x if isinstance(x, ops.Planes) else ops.planes_of(x)
+                h = ops.gemm_tc(xp, p["wp_planes"], conv.bias, taps=self.kernel_size, relu=True, npass=npass, out=out,
+                                tag="predictor_conv_ln_gemm", **fuse)
             return h if fuse else ops.add_layernorm(h, None, ln.weight, ln.bias, ln.eps)
+        if isinstance(x, ops.Planes):
+            x = ops.merge_planes(x)
         if self.depthwise:
             u = ops.dwconv1d(x, p["dw_wt"], conv[0].bias)
             h = ops.linear(u, p["pw_w"], conv[1].bias, relu=True, tag="predictor_pw_gemm")
@@ -339,8 +353,11 @@ class VariancePredictor(nn.Module):
 
     def forward(self, x, mask=None, return_conv=False):
         z = x
-        for layer in self.layers:
-            z = layer(z)
+        nl = len(self.layers)
+        for i, layer in enumerate(self.layers):
+            z = layer(z, out="planes" if i + 1 < nl else "f32")
+        if isinstance(z, ops.Planes):
+            z = ops.merge_planes(z)
         out = ops.rowdot_mask(z, self.linear.weight, self.linear.bias, mask)
         return (out, z) if return_conv else out
 

@@ -257,17 +257,31 @@ def planes_of(x):
     return p if p is not None else split_bf16(x.contiguous())
 
 
-def dwconv1d_planes(x, wt, bias, want_f32=False):
-    """depthwise conv writing bf16 hi/lo planes (and optionally fp32): x (B,T,d), wt (ksize,d)"""
-    _chk(x, torch.float32, "dwconv input", 3); _chk(wt, torch.float32, "dwconv weight", 2)
-    b, t, d = x.shape
-    out = torch.empty_like(x) if want_f32 else None
-    po = Planes(torch.empty(x.shape, device=x.device, dtype=torch.bfloat16),
-                torch.empty(x.shape, device=x.device, dtype=torch.bfloat16))
-    _launch("lfs2_dwconv1d_planes", _p(x), _p(wt), _p(bias), _p(out), _p(po.hi), _p(po.lo), b, t, d, wt.shape[0],
-            _s(), tag="lfs2_dwconv1d", flops=2.0 * b * t * d * wt.shape[0],
-            nbytes=(8.0 + 4.0 * int(want_f32)) * b * t * d)
-    return out, po
+def dwconv1d_planes(x, wt, bias, out="planes"):
+    """depthwise conv, x (B,T,d) fp32 tensor or Planes, wt (ksize,d) -> Planes (or fp32 if out == "f32")"""
+    _chk(wt, torch.float32, "dwconv weight", 2)
+    if isinstance(x, Planes):
+        _chk(x.hi, torch.bfloat16, "dwconv input", 3); _chk(x.lo, torch.bfloat16, "dwconv input", 3)
+        xf, xh, xl, shape, dev = None, x.hi, x.lo, x.hi.shape, x.hi.device
+    else:
+        _chk(x, torch.float32, "dwconv input", 3)
+        xf, xh, xl, shape, dev = x, None, None, x.shape, x.device
+    b, t, d = shape
+    of = torch.empty(shape, device=dev, dtype=torch.float32) if out == "f32" else None
+    po = Planes(torch.empty(shape, device=dev, dtype=torch.bfloat16),
+                torch.empty(shape, device=dev, dtype=torch.bfloat16)) if out == "planes" else None
+    _launch("lfs2_dwconv1d_planes", _p(xf), _p(xh), _p(xl), _p(wt), _p(bias), _p(of), _p(po.hi if po else None),
+            _p(po.lo if po else None), b, t, d, wt.shape[0], _s(), tag="lfs2_dwconv1d",
+            flops=2.0 * b * t * d * wt.shape[0], nbytes=8.0 * b * t * d)
+    return of if out == "f32" else po
+
+
+def merge_planes(p):
+    """Planes -> fp32 tensor (hi + lo)"""
+    _chk(p.hi, torch.bfloat16, "planes.hi"); _chk(p.lo, torch.bfloat16, "planes.lo")
+    out = torch.empty(p.hi.shape, device=p.hi.device, dtype=torch.float32)
+    _launch("lfs2_merge_planes", _p(p.hi), _p(p.lo), _p(out), p.hi.numel(), _s(), nbytes=8.0 * p.hi.numel())
+    return attach_planes(out, p)
 
 
 def split_bf16(x):
@@ -278,12 +292,26 @@ def split_bf16(x):
     return Planes(hi, lo)
 
 
-def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None, eps=LN_EPS, want_f32=True,
-            want_planes=False, npass=3, tag=None):
+_IDENT = {}
+
+
+def _identity_planes(n, device):
+    key = (n, str(device))
+    if key not in _IDENT:
+        _IDENT[key] = torch.eye(n, device=device, dtype=torch.bfloat16).contiguous()
+    return _IDENT[key]
+
+
+def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None, eps=LN_EPS, out="f32",
+            npass=3, tag=None):
     """a: Planes (B,T,d) [taps>1: Conv1d over T per utterance] or (...,d) for taps == 1;
-    w: Planes (n, taps*d).  Returns (out_f32 or None, Planes or None), shaped like a with last dim n."""
+    w: Planes (n, taps*d); residual: Planes shaped like the output (added on the tensor core,
+    LayerNorm epilogues only).  out = "f32" -> fp32 tensor, "planes" -> Planes; shaped like a
+    with last dim n."""
     if not isinstance(a, Planes) or not isinstance(w, Planes):
         raise TypeError("gemm_tc: operands must be Planes (see split_bf16)")
+    if out not in ("f32", "planes"):
+        raise ValueError("gemm_tc: out must be 'f32' or 'planes'")
     d = a.shape[-1]
     n = w.shape[0]
     if w.shape[1] != taps * d:
@@ -298,19 +326,23 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
         _chk(x_, torch.bfloat16, "gemm_tc operand plane")
     out_shape = tuple(a.shape[:-1]) + (n,)
     dev = a.hi.device
-    out = torch.empty(out_shape, device=dev, dtype=torch.float32) if want_f32 else None
+    of = torch.empty(out_shape, device=dev, dtype=torch.float32) if out == "f32" else None
     po = Planes(torch.empty(out_shape, device=dev, dtype=torch.bfloat16),
-                torch.empty(out_shape, device=dev, dtype=torch.bfloat16)) if want_planes else None
+                torch.empty(out_shape, device=dev, dtype=torch.bfloat16)) if out == "planes" else None
+    ident = None
     if residual is not None:
-        _chk(residual, torch.float32, "gemm_tc residual")
+        if not isinstance(residual, Planes) or tuple(residual.shape) != out_shape:
+            raise ValueError("gemm_tc: residual must be Planes shaped like the output")
+        _chk(residual.hi, torch.bfloat16, "gemm_tc residual"); _chk(residual.lo, torch.bfloat16, "gemm_tc residual")
+        ident = _identity_planes(n, dev)
     m = batch * t
     _launch("lfs2_gemm_tc", _p(a.hi), _p(a.lo), batch, t, d, taps, _p(w.hi), _p(w.lo), n, _p(bias), int(relu),
-            _p(residual), _p(gamma), _p(beta), float(eps), _p(out), _p(po.hi if po else None),
+            _p(residual.hi if residual is not None else None), _p(residual.lo if residual is not None else None),
+            _p(ident), _p(gamma), _p(beta), float(eps), _p(of), _p(po.hi if po else None),
             _p(po.lo if po else None), npass, _s(), tag=tag or f"gemm_tc_n{n}_k{taps * d}",
             flops=2.0 * m * n * taps * d,
-            nbytes=4.0 * m * d + 4.0 * n * taps * d + 4.0 * m * n * (int(want_f32) + int(want_planes))
-            + (4.0 * m * n if residual is not None else 0.0))
-    return out, po
+            nbytes=4.0 * m * d + 4.0 * n * taps * d + 4.0 * m * n + (4.0 * m * n if residual is not None else 0.0))
+    return of if out == "f32" else po
 
 
 def attention_tc(qkv, kpm, nhead, npass=3, want_f32=False, want_planes=True):

@@ -20,7 +20,7 @@ MEL_TOL = 1e-3
 # compute modes of the CUDA path: tcgen05 split-bf16 x3 ("fp32", the default), tcgen05 single-pass
 # bf16 ("bf16", tolerance 1e-2 per BASELINE.json) and the exact-fp32 CUDA-core kernels ("simt")
 TOL = {"fp32": 1e-3, "simt": 1e-3, "bf16": 1e-2}
-AUX_TOL = {"fp32": 1e-4, "simt": 1e-4, "bf16": 2e-2}
+AUX_TOL = {"fp32": 1e-4, "simt": 1e-4, "bf16": 5e-2}
 
 
 def build(preset, seed, stats=None, shapes=None, mode="fp32"):

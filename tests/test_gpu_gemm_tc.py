@@ -33,20 +33,20 @@ def test_split_bf16_reconstructs_to_2e_minus_16():
 def test_linear(m, n, k, npass):
     a, w, b = rnd(m, k, seed=1), rnd(n, k, seed=2, scale=k ** -0.5), rnd(n, seed=3, scale=0.1)
     ref = F.linear(a.double(), w.double(), b.double())
-    out, planes = ops.gemm_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV), npass=npass,
-                              want_planes=True)
+    ap, wp = ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV))
+    out = ops.gemm_tc(ap, wp, b.to(DEV), npass=npass)                       # fp32 out (TMA store, 128B swizzle)
+    planes = ops.gemm_tc(ap, wp, b.to(DEV), npass=npass, out="planes")      # hi/lo planes out (64B swizzle)
     tol = 2e-4 if npass == 3 else 3e-2
     err = (out.cpu() - ref).abs().max()
     assert err < tol, float(err)
     assert (planes.float().cpu() - out.cpu()).abs().max() < 1e-4
+    assert torch.equal(planes.hi, out.to(torch.bfloat16))
 
 
 def test_relu_and_planes_only():
     a, w, b = rnd(333, 256, seed=4), rnd(1024, 256, seed=5, scale=1 / 16), rnd(1024, seed=6, scale=0.1)
     ref = torch.relu(F.linear(a.double(), w.double(), b.double()))
-    out, planes = ops.gemm_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV), relu=True,
-                              want_f32=False, want_planes=True)
-    assert out is None
+    planes = ops.gemm_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV), relu=True, out="planes")
     assert (planes.float().cpu() - ref).abs().max() < 2e-4
 
 
@@ -56,7 +56,7 @@ def test_conv1d_taps(bsz, t, d, n, ks):
     x, w, b = rnd(bsz, t, d, seed=7), rnd(n, d, ks, seed=8, scale=(d * ks) ** -0.5), rnd(n, seed=9, scale=0.1)
     ref = F.conv1d(x.double().transpose(1, 2), w.double(), b.double(), padding=(ks - 1) // 2).transpose(1, 2)
     wp = w.permute(0, 2, 1).reshape(n, ks * d).contiguous()
-    out, _ = ops.gemm_tc(ops.split_bf16(x.to(DEV)), ops.split_bf16(wp.to(DEV)), b.to(DEV), taps=ks)
+    out = ops.gemm_tc(ops.split_bf16(x.to(DEV)), ops.split_bf16(wp.to(DEV)), b.to(DEV), taps=ks)
     err = (out.cpu() - ref).abs().max()
     assert err < 2e-4, float(err)
 
@@ -73,9 +73,10 @@ def test_layernorm_epilogue(m, k, relu, res):
     if res:
         v = v + r.double()
     ref = F.layer_norm(v, (n,), g.double(), bt.double(), 1e-5)
-    out, planes = ops.gemm_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV), relu=relu,
-                              residual=r.to(DEV) if res else None, gamma=g.to(DEV), beta=bt.to(DEV),
-                              want_planes=True)
+    kw = dict(relu=relu, residual=ops.split_bf16(r.to(DEV)) if res else None, gamma=g.to(DEV), beta=bt.to(DEV))
+    ap, wp = ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV))
+    out = ops.gemm_tc(ap, wp, b.to(DEV), **kw)
+    planes = ops.gemm_tc(ap, wp, b.to(DEV), out="planes", **kw)
     err = (out.cpu() - ref).abs().max()
     assert err < 3e-4, float(err)
     assert (planes.float().cpu() - out.cpu()).abs().max() < 1e-4
@@ -85,5 +86,29 @@ def test_matches_fp32_simt_gemm_closely():
     """same inputs through the exact-fp32 CUDA-core GEMM: the split path must agree to ~1e-5"""
     a, w, b = rnd(4096, 256, seed=16), rnd(768, 256, seed=17, scale=1 / 16), rnd(768, seed=18, scale=0.1)
     ref = ops.linear(a.to(DEV), w.to(DEV), b.to(DEV))
-    out, _ = ops.gemm_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV))
+    out = ops.gemm_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV))
     assert (out - ref).abs().max() < 1e-4
+
+
+def test_bf16_mode_keeps_the_residual_in_fp32_precision():
+    """npass=1 rounds the GEMM operands to bf16 but the residual still rides as hi+lo planes"""
+    m, k, n = 500, 256, 256
+    a, w, b = rnd(m, k, seed=20, scale=1e-3), rnd(n, k, seed=21, scale=k ** -0.5), rnd(n, seed=22, scale=1e-3)
+    r = rnd(m, n, seed=23)
+    g, bt = torch.ones(n), torch.zeros(n)
+    ref = F.layer_norm(F.linear(a.double(), w.double(), b.double()) + r.double(), (n,), g.double(), bt.double(), 1e-5)
+    out = ops.gemm_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV), residual=ops.split_bf16(r.to(DEV)),
+                      gamma=g.to(DEV), beta=bt.to(DEV), npass=1)
+    assert (out.cpu() - ref).abs().max() < 1e-4
+
+
+def test_merge_and_dwconv_on_planes():
+    x = rnd(3, 70, 256, seed=24).to(DEV)
+    xp = ops.split_bf16(x)
+    assert (ops.merge_planes(xp) - x).abs().max() < 2.0 ** -15 * x.abs().max()
+    wt, bias = rnd(9, 256, seed=25, scale=0.3).to(DEV), rnd(256, seed=26, scale=0.1).to(DEV)
+    ref = ops.dwconv1d(x, wt, bias)
+    got = ops.dwconv1d_planes(xp, wt, bias)              # planes in -> planes out
+    got32 = ops.dwconv1d_planes(x, wt, bias, out="f32")  # fp32 in -> fp32 out
+    assert torch.equal(got32, ref)
+    assert (got.float() - ref).abs().max() < 1e-4
