@@ -12,7 +12,9 @@
 //                        [256,384) O   fp32 accumulator (128 head-dim columns)
 //
 //   warps: 0 = TMA producer (K and V rings, 3 stages each), 1 = MMA issuer (one thread),
-//   2..5 = softmax (thread = query row; TMEM lane quadrant = warp & 3).
+//   2..9 = softmax (thread = query row; TMEM lane quadrant = warp & 3; the two warps of a
+//   quadrant split each tile's 64 keys and the 128 O columns, and agree on the row maximum
+//   through shared memory + one 64-thread named barrier per tile).
 //   tensor-pipe order:  QK_0 QK_1 | PV_0 QK_2 | PV_1 QK_3 | ...   so softmax_{j+1} overlaps
 //   PV_j + QK_{j+2}.  Online softmax with a lazily updated exponent reference: the O
 //   accumulator is rescaled in TMEM only when a row's logits outgrow the reference by 2^8.
@@ -31,19 +33,9 @@ constexpr int kAQ = 128;        // queries per CTA (UMMA M)
 constexpr int kAK = 64;         // keys per tile
 constexpr int kDH = 128;        // head dim
 constexpr int kKVStages = 3;
-constexpr int kAttnTcThreads = 192;
+constexpr int kAttnTcThreads = 320;  // TMA, MMA, 8 softmax warps (two per TMEM lane quadrant)
 constexpr int kTileBytes = kAK * kDH * 2;          // one plane of a K or V tile: 16 KB
 constexpr uint32_t kColQ = 0, kColS = 128, kColO = 256;
-
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
-                                            uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 
 // 32 lanes x 32 columns without the trailing wait (caller batches the wait)
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
@@ -71,6 +63,17 @@ __device__ __forceinline__ void tmem_st32_u(uint32_t taddr, const uint32_t* r) {
       "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
+}
+
+__device__ __forceinline__ void tmem_st16_u(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void pair_bar_sync(int quad) {
+  asm volatile("bar.sync %0, 64;" ::"r"(4 + quad) : "memory");
 }
 
 struct AttnTcParams {
@@ -114,6 +117,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   __shared__ __align__(8) uint64_t k_full[kKVStages], k_empty[kKVStages], v_full[kKVStages], v_empty[kKVStages];
   __shared__ __align__(8) uint64_t q_full, s_full[2], p_full[2], pv_done, o_final;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float xch[2][2][kAQ];  // [tile parity][half][row]: row maxima / partial sums between the warp pair
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kAQ, h = blockIdx.y, b = blockIdx.z;
@@ -130,10 +134,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
     }
-    mbar_init(&q_full, 4);
+    mbar_init(&q_full, 8);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1);
-      mbar_init(&p_full[i], 4);
+      mbar_init(&p_full[i], 8);
     }
     mbar_init(&pv_done, 1);
     mbar_init(&o_final, 1);
@@ -172,30 +176,37 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0 && ntiles > 0) {
+    // The whole warp runs the (warp-uniform) control flow so descriptors stay in uniform
+    // registers; one elected lane issues the tcgen05 instructions.  Per-instruction work is a
+    // 64-bit add on a precomputed descriptor.
+    if (ntiles > 0) {
       constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, kAQ, kAK, 0, 0);  // A: TMEM, B: K tile, K-major
       constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, kAQ, kDH, 0, 1);  // A: TMEM, B: V tile, MN-major
       const uint32_t tq = tmem_base + kColQ, to = tmem_base + kColO;
+      const uint64_t dk0 = make_smem_desc(smem_u32(sK), 16, 512, kSwizzle64);
+      const uint64_t dv0 = make_smem_desc(smem_u32(sV), 4096, 512, kSwizzle64);
 
       auto issue_qk = [&](int j) {
         const int st = j % kKVStages;
         mbar_wait(&k_full[st], (j / kKVStages) & 1);
         tc_fence_after();
-        const uint32_t ts = tmem_base + kColS + (j & 1) * kAK;
-        const uint32_t kh = smem_u32(sK + st * kStageBytes), kl = kh + kTileBytes;
+        if (elect_one()) {
+          const uint32_t ts = tmem_base + kColS + (j & 1) * kAK;
+          const uint64_t dkh = desc_advance(dk0, st * kStageBytes), dkl = desc_advance(dkh, kTileBytes);
 #pragma unroll
-        for (int i = 0; i < kDH / 16; ++i) {
-          const uint32_t off = (i >> 1) * 4096 + (i & 1) * 32;
-          const uint64_t dkh = make_smem_desc(kh + off, 16, 512, kSwizzle64);
-          umma_f16_ts(ts, tq + i * 8, dkh, idesc_qk, i ? 1u : 0u);
-          if (NPASS == 3) {
-            const uint64_t dkl = make_smem_desc(kl + off, 16, 512, kSwizzle64);
-            umma_f16_ts(ts, tq + 64 + i * 8, dkh, idesc_qk, 1u);
-            umma_f16_ts(ts, tq + i * 8, dkl, idesc_qk, 1u);
+          for (int i = 0; i < kDH / 16; ++i) {
+            const uint32_t off = (i >> 1) * 4096 + (i & 1) * 32;
+            if (i == 0) umma_f16_ts_c<false>(ts, tq, dkh, idesc_qk);
+            else umma_f16_ts_c<true>(ts, tq + i * 8, desc_advance(dkh, off), idesc_qk);
+            if (NPASS == 3) {
+              umma_f16_ts_c<true>(ts, tq + 64 + i * 8, desc_advance(dkh, off), idesc_qk);
+              umma_f16_ts_c<true>(ts, tq + i * 8, desc_advance(dkl, off), idesc_qk);
+            }
           }
+          umma_commit(&k_empty[st]);
+          umma_commit(&s_full[j & 1]);
         }
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[j & 1]);
+        __syncwarp();
       };
 
       mbar_wait(&q_full, 0);
@@ -207,53 +218,54 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         mbar_wait(&p_full[j & 1], (j >> 1) & 1);
         mbar_wait(&v_full[st], (j / kKVStages) & 1);
         tc_fence_after();
-        const uint32_t tp = tmem_base + kColS + (j & 1) * kAK;  // P hi: 32 cols, P lo: next 32
-        const uint32_t vh = smem_u32(sV + st * kStageBytes), vl = vh + kTileBytes;
+        if (elect_one()) {
+          const uint32_t tp = tmem_base + kColS + (j & 1) * kAK;  // P hi: 32 cols, P lo: next 32
+          const uint64_t dvh = desc_advance(dv0, st * kStageBytes), dvl = desc_advance(dvh, kTileBytes);
 #pragma unroll
-        for (int i = 0; i < kAK / 16; ++i) {
-          const uint64_t dvh = make_smem_desc(vh + i * 1024, 4096, 512, kSwizzle64);
-          umma_f16_ts(to, tp + i * 8, dvh, idesc_pv, (j | i) ? 1u : 0u);
-          if (NPASS == 3) {
-            const uint64_t dvl = make_smem_desc(vl + i * 1024, 4096, 512, kSwizzle64);
-            umma_f16_ts(to, tp + 32 + i * 8, dvh, idesc_pv, 1u);
-            umma_f16_ts(to, tp + i * 8, dvl, idesc_pv, 1u);
+          for (int i = 0; i < kAK / 16; ++i) {
+            if (i == 0) umma_f16_ts(to, tp, dvh, idesc_pv, j ? 1u : 0u);
+            else umma_f16_ts_c<true>(to, tp + i * 8, desc_advance(dvh, i * 1024), idesc_pv);
+            if (NPASS == 3) {
+              umma_f16_ts_c<true>(to, tp + 32 + i * 8, desc_advance(dvh, i * 1024), idesc_pv);
+              umma_f16_ts_c<true>(to, tp + i * 8, desc_advance(dvl, i * 1024), idesc_pv);
+            }
           }
+          umma_commit(&v_empty[st]);
+          umma_commit(&pv_done);
+          if (j + 1 == ntiles) umma_commit(&o_final);  // every product of this CTA has landed
         }
-        umma_commit(&v_empty[st]);
-        umma_commit(&pv_done);
+        __syncwarp();
         if (j + 2 < ntiles) issue_qk(j + 2);
       }
-      umma_commit(&o_final);  // every product of this CTA has landed
     }
   } else {
     // ===================== softmax warps: thread = query row =====================
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;  // which 32 of the tile's 64 keys / which 64 of the 128 O columns
     const int r = quad * 32 + lane;
     const int tq_row = q0 + r;
     const bool row_ok = tq_row < p.t;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
 
-    // ---- Q row -> TMEM (bf16 pairs; hi plane cols 0..63, lo plane cols 64..127) ----
+    // ---- Q row -> TMEM (bf16 pairs; half 0 loads the hi plane -> cols 0..63, half 1 the lo plane -> 64..127) ----
     {
       uint32_t w[32];
+      const __nv_bfloat16* src = (half == 0 ? p.qkv_hi : p.qkv_lo) + ((size_t)b * p.t + tq_row) * 3 * p.d + col_q;
+      const bool load = row_ok && (half == 0 || NPASS == 3);
 #pragma unroll
-      for (int pl = 0; pl < 2; ++pl) {
-        const __nv_bfloat16* src = (pl == 0 ? p.qkv_hi : p.qkv_lo) + ((size_t)b * p.t + tq_row) * 3 * p.d + col_q;
+      for (int hh = 0; hh < 2; ++hh) {
+        if (load) {
+          const uint4* s4 = reinterpret_cast<const uint4*>(src) + hh * 8;
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-          if (row_ok && (pl == 0 || NPASS == 3)) {
-            const uint4* s4 = reinterpret_cast<const uint4*>(src) + half * 8;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              uint4 v = __ldg(s4 + i);
-              w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) w[i] = 0u;
+          for (int i = 0; i < 8; ++i) {
+            uint4 v = __ldg(s4 + i);
+            w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
           }
-          tmem_st32_u(tmem_base + kColQ + pl * 64 + half * 32 + lane_off, w);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) w[i] = 0u;
         }
+        tmem_st32_u(tmem_base + kColQ + half * 64 + hh * 32 + lane_off, w);
       }
       tmem_wait_st();
       tc_fence_before();
@@ -261,43 +273,42 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       if (lane == 0) mbar_arrive(&q_full);
     }
 
-    float m_run = -INFINITY;  // running max of the raw logits of this row
-    float l_run = 0.f;
+    float m_run = -INFINITY;  // exponent reference of this row (shared by both halves)
+    float l_run = 0.f;        // partial row sum over this half's keys
     const float c = p.scale_log2e;
     const uint8_t* mrow = p.kpm ? p.kpm + (size_t)b * p.t : nullptr;
 
     for (int j = 0; j < ntiles; ++j) {
-      const int key0 = j * kAK;
-      // 64-bit "key is masked" set of this tile (PAD keys and keys beyond T), warp-uniform
-      uint32_t mlo, mhi;
+      const int key0 = j * kAK + half * 32;
+      // "key is masked" bits of this half's 32 keys (PAD keys and keys beyond T), warp-uniform
+      uint32_t mbits;
       {
-        int k1 = key0 + lane, k2 = key0 + 32 + lane;
+        int k1 = key0 + lane;
         bool b1 = (k1 >= p.t) || (mrow && mrow[k1]);
-        bool b2 = (k2 >= p.t) || (mrow && mrow[k2]);
-        mlo = __ballot_sync(0xffffffffu, b1);
-        mhi = __ballot_sync(0xffffffffu, b2);
+        mbits = __ballot_sync(0xffffffffu, b1);
       }
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t ts = tmem_base + kColS + (j & 1) * kAK + lane_off;
-      float s[64];
-      tmem_ld32_nowait(ts, s);
-      tmem_ld32_nowait(ts + 32, s + 32);
-      tmem_wait_ld();
-      if (mlo | mhi) {
+      float s[32];
+      tmem_ld32(ts + half * 32, s);
+      if (mbits) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if ((mlo >> i) & 1u) s[i] = -INFINITY;
-          if ((mhi >> i) & 1u) s[32 + i] = -INFINITY;
-        }
+        for (int i = 0; i < 32; ++i)
+          if ((mbits >> i) & 1u) s[i] = -INFINITY;
       }
       float tmax = s[0];
 #pragma unroll
-      for (int i = 1; i < 64; ++i) tmax = fmaxf(tmax, s[i]);
+      for (int i = 1; i < 32; ++i) tmax = fmaxf(tmax, s[i]);
+      // row maximum over all 64 keys: exchange with the partner warp (parity double buffer)
+      xch[j & 1][half][r] = tmax;
+      pair_bar_sync(quad);
+      tmax = fmaxf(tmax, xch[j & 1][half ^ 1][r]);
       // Lazy rescale: m_run is the exponent reference, not necessarily the true running maximum.
       // It is only moved (and O, l rescaled) when some row's logits exceed it by more than 2^8
       // in the exp2 domain, so p <= 256 always and the O accumulator is almost never touched;
-      // softmax is shift-invariant, so the result is exact either way.
+      // softmax is shift-invariant, so the result is exact either way.  Both halves see the same
+      // tmax and m_run, hence take the same (warp-uniform) branch.
       const bool grow = (j > 0) && ((tmax - m_run) * c > 8.f);  // (x - -inf) = inf: first finite tile moves it
       if (j == 0) {
         m_run = tmax;
@@ -305,11 +316,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         const float m_new = fmaxf(m_run, tmax);
         mbar_wait(&pv_done, (j - 1) & 1);  // all PV products up to tile j-1 have landed in O
         tc_fence_after();
-        const float alpha = (m_new == -INFINITY) ? 1.f : exp2f((m_run - m_new) * c);
+        const float alpha = (m_new == -INFINITY) ? 1.f : ex2_approx((m_run - m_new) * c);
         l_run *= alpha;
         float o[32];
 #pragma unroll 1
-        for (int cc = 0; cc < kDH / 32; ++cc) {
+        for (int cc = 2 * half; cc < 2 * half + 2; ++cc) {
           tmem_ld32(tmem_base + kColO + cc * 32 + lane_off, o);
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] *= alpha;
@@ -319,29 +330,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         m_run = m_new;
       }
       const float mc = (m_run == -INFINITY) ? 0.f : m_run * c;
-      uint32_t ph[32], pl[32];
+      uint32_t ph[16], pl[16];
       float lsum = 0.f;
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        float p0 = exp2f(fmaf(s[2 * i], c, -mc));
-        float p1 = exp2f(fmaf(s[2 * i + 1], c, -mc));
+      for (int i = 0; i < 16; ++i) {
+        float p0 = ex2_approx(fmaf(s[2 * i], c, -mc));
+        float p1 = ex2_approx(fmaf(s[2 * i + 1], c, -mc));
         lsum += p0 + p1;
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(p0, h0, l0);
-        split_bf16(p1, h1, l1);
-        ph[i] = pack_bf16(h0, h1);
-        pl[i] = pack_bf16(l0, l1);
+        split_pack2(p0, p1, ph[i], pl[i]);
       }
       l_run += lsum;
-      tmem_st32_u(ts, ph);
-      if (NPASS == 3) tmem_st32_u(ts + 32, pl);
+      tmem_st16_u(ts + half * 16, ph);                       // P hi: cols [0,32) of the S buffer
+      if (NPASS == 3) tmem_st16_u(ts + 32 + half * 16, pl);  // P lo: cols [32,64)
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[j & 1]);
     }
 
-    // ---- epilogue: O / l -> ctx planes ----
+    // ---- epilogue: O / l -> ctx planes (this half's 64 columns) ----
+    xch[ntiles & 1][half][r] = l_run;
+    pair_bar_sync(quad);
+    l_run += xch[ntiles & 1][half ^ 1][r];
     const size_t orow = ((size_t)b * p.t + tq_row) * p.d + col_q;
     if (ntiles > 0) {
       mbar_wait(&o_final, 0);
@@ -350,7 +360,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     const float inv_l = 1.f / l_run;  // l == 0 (no unmasked key) -> inf -> NaN rows, like the reference
     float o[32];
 #pragma unroll 1
-    for (int cc = 0; cc < kDH / 32; ++cc) {
+    for (int cc = 2 * half; cc < 2 * half + 2; ++cc) {
       if (ntiles > 0) {
         tmem_ld32(tmem_base + kColO + cc * 32 + lane_off, o);
 #pragma unroll
@@ -368,13 +378,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         if (p.ctx_hi) {
           uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(o[2 * i], h0, l0);
-            split_bf16(o[2 * i + 1], h1, l1);
-            hi[i] = pack_bf16(h0, h1);
-            lo[i] = pack_bf16(l0, l1);
-          }
+          for (int i = 0; i < 16; ++i) split_pack2(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
           uint4* oh = reinterpret_cast<uint4*>(p.ctx_hi + orow + cc * 32);
           uint4* ol = reinterpret_cast<uint4*>(p.ctx_lo + orow + cc * 32);
 #pragma unroll

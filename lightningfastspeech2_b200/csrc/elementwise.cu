@@ -314,6 +314,133 @@ __global__ void bucket_embed_add_kernel(float4* __restrict__ x, const float* __r
   }
 }
 
+// Depthwise conv specialised on the kernel size, shared-memory tiled: one CTA = 64 (K <= 9) or
+// 32 output frames x 256 channels of one utterance, two CTAs per SM so one CTA's load phase
+// overlaps the other's arithmetic.  The (tile + K - 1) input rows are staged once in
+// shared memory as fp32 (coalesced 8/16-byte loads, all independent -> deep memory-level
+// parallelism; rows outside [0, T) are zeros = Conv1d's "same" padding), then each thread
+// slides NT consecutive frames of its 4 channels through registers: the K tap weights live in
+// registers and the (input row, output row) -> tap mapping is resolved at compile time, so the
+// inner loop is LDS.128 + FFMA only.  Results leave as fp32 and/or bf16 hi/lo planes.
+__device__ __forceinline__ void split_pack2_ew(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - bh), "f"(a - ah));
+}
+
+constexpr int kDwCh4 = 64;    // float4 channel groups per CTA (256 channels)
+
+template <int K, int NT, int kDwTile, bool IN_PLANES>
+__global__ void __launch_bounds__(kDwCh4 * (kDwTile / NT), 2)
+dwconv1d_k_kernel(const float4* __restrict__ x, const uint2* __restrict__ x_hi, const uint2* __restrict__ x_lo,
+                  const float4* __restrict__ wt, const float4* __restrict__ bias, float4* __restrict__ out,
+                  uint2* __restrict__ out_hi, uint2* __restrict__ out_lo, int t, int d4) {
+  extern __shared__ float4 xs[];  // [kDwTile + K - 1][kDwCh4]
+  constexpr int H = (K - 1) / 2;
+  constexpr int kRows = kDwTile + K - 1;
+  constexpr int kThreads = kDwCh4 * (kDwTile / NT);
+  const int t0 = blockIdx.x * kDwTile;
+  const int cb = blockIdx.y * kDwCh4;  // first float4 channel group of this CTA
+  const int b = blockIdx.z;
+  const int nch = min(kDwCh4, d4 - cb);
+  const size_t base = (size_t)b * t * d4 + cb;
+
+  // stage the input rows: all global loads of a thread are issued before the first use
+  constexpr int kIters = (kRows * kDwCh4 + kThreads - 1) / kThreads;
+  {
+    const int c = threadIdx.x % kDwCh4;            // kThreads is a multiple of kDwCh4
+    const int row0 = threadIdx.x / kDwCh4;
+    constexpr int kRowStep = kThreads / kDwCh4;
+    uint2 rh[kIters], rl[kIters];
+    float4 rf[IN_PLANES ? 1 : kIters];
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int row = row0 + it * kRowStep;
+      const int ti = t0 - H + row;
+      const bool ok = row < kRows && ti >= 0 && ti < t && c < nch;
+      const size_t gi = base + (size_t)(ok ? ti : 0) * d4 + (ok ? c : 0);
+      if (IN_PLANES) {
+        rh[it] = ok ? x_hi[gi] : make_uint2(0u, 0u);
+        rl[it] = ok ? x_lo[gi] : make_uint2(0u, 0u);
+      } else {
+        rf[it] = ok ? x[gi] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kIters; ++it) {
+      const int row = row0 + it * kRowStep;
+      if (row < kRows) xs[row * kDwCh4 + c] = IN_PLANES ? planes_to_f4(rh[it], rl[it]) : rf[it];
+    }
+  }
+  __syncthreads();
+
+  const int c = threadIdx.x % kDwCh4, tg = threadIdx.x / kDwCh4;
+  if (c >= nch) return;
+  float4 w[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) w[j] = wt[(size_t)j * d4 + cb + c];
+  const float4 bz = bias[cb + c];
+  float4 acc[NT];
+#pragma unroll
+  for (int o = 0; o < NT; ++o) acc[o] = bz;
+  const float4* xr = xs + (size_t)(tg * NT) * kDwCh4 + c;
+#pragma unroll
+  for (int j = 0; j < NT + K - 1; ++j) {
+    const float4 xv = xr[j * kDwCh4];
+#pragma unroll
+    for (int o = 0; o < NT; ++o) {
+      const int tap = j - o;  // compile-time after unrolling
+      if (tap >= 0 && tap < K) {
+        acc[o].x = fmaf(w[tap].x, xv.x, acc[o].x);
+        acc[o].y = fmaf(w[tap].y, xv.y, acc[o].y);
+        acc[o].z = fmaf(w[tap].z, xv.z, acc[o].z);
+        acc[o].w = fmaf(w[tap].w, xv.w, acc[o].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < NT; ++o) {
+    const int to = t0 + tg * NT + o;
+    if (to < t) {
+      const size_t oi = base + (size_t)to * d4 + c;
+      if (out) out[oi] = acc[o];
+      if (out_hi) {
+        uint2 h, l;
+        split_pack2_ew(acc[o].x, acc[o].y, h.x, l.x);
+        split_pack2_ew(acc[o].z, acc[o].w, h.y, l.y);
+        out_hi[oi] = h;
+        out_lo[oi] = l;
+      }
+    }
+  }
+}
+
+template <int K, int NT, int kDwTile>
+static int launch_dwconv_k(const float* x, const void* x_hi, const void* x_lo, const float* wt, const float* bias,
+                           float* out, void* out_hi, void* out_lo, int batch, int t, int d, cudaStream_t s) {
+  constexpr int kThreads = kDwCh4 * (kDwTile / NT);
+  constexpr int kSmem = (kDwTile + K - 1) * kDwCh4 * 16;
+  dim3 grid(ceil_div(t, kDwTile), ceil_div(d / 4, kDwCh4), batch);
+  static bool configured = false;
+  auto kf = dwconv1d_k_kernel<K, NT, kDwTile, false>;
+  auto kp = dwconv1d_k_kernel<K, NT, kDwTile, true>;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess ||
+        cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) {
+      set_error("dwconv1d: cannot reserve %d bytes of shared memory", kSmem);
+      return LFS2_ERR_CUDA;
+    }
+    configured = true;
+  }
+  if (x)
+    kf<<<grid, kThreads, kSmem, s>>>((const float4*)x, nullptr, nullptr, (const float4*)wt, (const float4*)bias,
+                                     (float4*)out, (uint2*)out_hi, (uint2*)out_lo, t, d / 4);
+  else
+    kp<<<grid, kThreads, kSmem, s>>>(nullptr, (const uint2*)x_hi, (const uint2*)x_lo, (const float4*)wt,
+                                     (const float4*)bias, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, t, d / 4);
+  return LFS2_OK;
+}
+
 // x = hi + lo (fp32) from bf16 planes; one thread per 4 elements
 __global__ void merge_planes_kernel(const uint2* __restrict__ hi, const uint2* __restrict__ lo, float4* __restrict__ out,
                                     size_t n4) {
@@ -423,16 +550,31 @@ int lfs2_dwconv1d_planes(const float* x, const void* x_hi, const void* x_lo, con
                    aligned16(bias) && (!out || aligned16(out)) &&
                    (!out_hi || (aligned16(out_hi) && aligned16(out_lo))),
                LFS2_ERR_INVALID_ARG, "dwconv1d: pointers must be 16-byte aligned");
-  int nchunk = ceil_div(t, kDwT);
-  size_t total = (size_t)batch * nchunk * (d / 4);
-  if (x)
-    dwconv1d_kernel<false><<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(
-        (const float4*)x, nullptr, nullptr, (const float4*)wt, (const float4*)bias, (float4*)out, (uint2*)out_hi,
-        (uint2*)out_lo, batch, t, d / 4, ksize, nchunk);
-  else
-    dwconv1d_kernel<true><<<ceil_div(total, 128), 128, 0, (cudaStream_t)stream>>>(
-        nullptr, (const uint2*)x_hi, (const uint2*)x_lo, (const float4*)wt, (const float4*)bias, (float4*)out,
-        (uint2*)out_hi, (uint2*)out_lo, batch, t, d / 4, ksize, nchunk);
+  cudaStream_t s = (cudaStream_t)stream;
+  LFS2_REQUIRE(batch <= 65535, LFS2_ERR_UNSUPPORTED, "dwconv1d: batch exceeds the grid limit");
+#define LFS2_DW_CASE(K, TT)                                                                          \
+  case K: {                                                                                          \
+    int rc = launch_dwconv_k<K, TT, (K <= 9 ? 64 : 32)>(x, x_hi, x_lo, wt, bias, out, out_hi, out_lo, batch, t, d, s);   \
+    if (rc != LFS2_OK) return rc;                                                                    \
+  } break;
+  switch (ksize) {
+    LFS2_DW_CASE(1, 16) LFS2_DW_CASE(3, 16) LFS2_DW_CASE(5, 16) LFS2_DW_CASE(7, 16) LFS2_DW_CASE(9, 16)
+    LFS2_DW_CASE(11, 8) LFS2_DW_CASE(13, 8) LFS2_DW_CASE(15, 8) LFS2_DW_CASE(17, 8) LFS2_DW_CASE(19, 8)
+    LFS2_DW_CASE(21, 8) LFS2_DW_CASE(23, 8) LFS2_DW_CASE(25, 8)
+    default: {
+      int nchunk = ceil_div(t, kDwT);
+      size_t total = (size_t)batch * nchunk * (d / 4);
+      if (x)
+        dwconv1d_kernel<false><<<ceil_div(total, 128), 128, 0, s>>>(
+            (const float4*)x, nullptr, nullptr, (const float4*)wt, (const float4*)bias, (float4*)out, (uint2*)out_hi,
+            (uint2*)out_lo, batch, t, d / 4, ksize, nchunk);
+      else
+        dwconv1d_kernel<true><<<ceil_div(total, 128), 128, 0, s>>>(
+            nullptr, (const uint2*)x_hi, (const uint2*)x_lo, (const float4*)wt, (const float4*)bias, (float4*)out,
+            (uint2*)out_hi, (uint2*)out_lo, batch, t, d / 4, ksize, nchunk);
+    }
+  }
+#undef LFS2_DW_CASE
   LFS2_CHECK_LAUNCH("dwconv1d");
   return LFS2_OK;
 }

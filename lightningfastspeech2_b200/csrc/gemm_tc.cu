@@ -28,7 +28,7 @@ namespace tc {
 
 constexpr int kBM = 128;     // rows per tile (UMMA M)
 constexpr int kBK = 32;      // k-slab: 32 bf16 = 64 bytes = one SWIZZLE_64B row
-constexpr int kGemmTcThreads = 192;
+constexpr int kGemmTcThreads = 320;  // TMA + MMA warps, 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int kStageChunk = kBM * 32 * 4;  // one 128 x 32 staging chunk: 16 KB (fp32) or 2 x 8 KB (hi | lo)
 
 struct GemmTcParams {
@@ -52,10 +52,12 @@ struct SmemLayout {
   static constexpr int kOffWHi = kAPlane;
   static constexpr int kOffALo = kAPlane + kWPlane;
   static constexpr int kOffWLo = 2 * kAPlane + kWPlane;
-  static constexpr int kStages = (170 * 1024 - 2 * kStageChunk) / kStage > 6 ? 6 : (170 * 1024 - 2 * kStageChunk) / kStage;
-  static constexpr int kOffStaging = kStages * kStage;                 // 2 chunks, 1024-aligned (kStage % 1024 == 0)
-  static constexpr int kOffVec = kOffStaging + 2 * kStageChunk;        // bias | gamma | beta for LN: 3 * N_TILE floats
-  static constexpr int kTotal = kOffVec + (LN ? 3 * N_TILE * 4 : 0) + 1024;  // + alignment slack
+  static constexpr int kFixed = 4 * kStageChunk + (LN ? 3 * N_TILE * 4 + 2 * 2 * kBM * 8 : 0) + 1024;
+  static constexpr int kStages = (226 * 1024 - kFixed) / kStage > 6 ? 6 : (226 * 1024 - kFixed) / kStage;
+  static constexpr int kOffStaging = kStages * kStage;                 // 2 halves x 2 chunks, 1024-aligned
+  static constexpr int kOffVec = kOffStaging + 4 * kStageChunk;        // bias | gamma | beta for LN: 3 * N_TILE floats
+  static constexpr int kOffStats = kOffVec + 3 * N_TILE * 4;           // LN partial (sum, sumsq): [2 tiles][2 halves][128]
+  static constexpr int kTotal = kStages * kStage + kFixed;
   static_assert(kStages >= 2, "not enough shared memory for a pipeline");
   static_assert(kStage % 1024 == 0, "stage must keep 1024-byte alignment");
 };
@@ -69,7 +71,9 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* map, const void*
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
 template <int N_TILE, int NPASS, bool LN, bool OUT_F32>
 __global__ void __launch_bounds__(kGemmTcThreads, 1)
@@ -104,14 +108,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
   if (LN && warp >= 2) {  // bias | gamma | beta -> shared (broadcast reads in the epilogue)
     float* vec = reinterpret_cast<float*>(smem + L::kOffVec);
-    for (int i = threadIdx.x - 64; i < N_TILE; i += 128) {
+    for (int i = threadIdx.x - 64; i < N_TILE; i += 256) {
       vec[i] = p.bias ? p.bias[i] : 0.f;
       vec[N_TILE + i] = p.gamma[i];
       vec[2 * N_TILE + i] = p.beta[i];
@@ -159,56 +163,64 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(kFmtBF16, kBM, N_TILE, 0, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-        int acc = it & 1;
-        uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // whole warp runs the uniform control flow (descriptors stay in uniform registers), one
+    // elected lane issues; per instruction the descriptor is a 64-bit add on a precomputed base
+    constexpr uint32_t idesc = make_idesc(kFmtBF16, kBM, N_TILE, 0, 0);
+    const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 512, kSwizzle64);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      int acc = it & 1;
+      uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kAccCols;
+      for (int ks = 0; ks < k_slabs; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        uint32_t d_tmem = tmem_base + acc * kAccCols;
-        for (int ks = 0; ks < k_slabs; ++ks) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          uint32_t sa_hi = smem_u32(smem + stage * L::kStage);
-          uint32_t sw_hi = sa_hi + L::kOffWHi;
-          uint32_t sa_lo = sa_hi + L::kOffALo;
-          uint32_t sw_lo = sa_hi + L::kOffWLo;
+        if (elect_one()) {
+          const uint64_t a_hi = desc_advance(d0, stage * L::kStage);
+          const uint64_t w_hi = desc_advance(a_hi, L::kOffWHi);
+          const uint64_t a_lo = desc_advance(a_hi, L::kOffALo);
+          const uint64_t w_lo = desc_advance(a_hi, L::kOffWLo);
           const bool res = ks >= a_slabs;
-#pragma unroll
-          for (int k16 = 0; k16 < kBK / 16; ++k16) {
-            uint32_t off = k16 * 32;  // 16 bf16 = 32 bytes along K inside the 64-byte swizzled row
-            uint64_t a_hi = make_smem_desc(sa_hi + off, 16, 512, kSwizzle64);
-            uint64_t w_hi = make_smem_desc(sw_hi + off, 16, 512, kSwizzle64);
-            umma_f16(d_tmem, a_hi, w_hi, idesc, (ks | k16) ? 1u : 0u);
-            if (L::kHasLo && (NPASS == 3 || res)) {
-              uint64_t a_lo = make_smem_desc(sa_lo + off, 16, 512, kSwizzle64);
-              umma_f16(d_tmem, a_lo, w_hi, idesc, 1u);
-            }
-            if (NPASS == 3 && !res) {
-              uint64_t w_lo = make_smem_desc(sw_lo + off, 16, 512, kSwizzle64);
-              umma_f16(d_tmem, a_hi, w_lo, idesc, 1u);
-            }
+          // 16 bf16 = 32 bytes along K inside the 64-byte swizzled row per k16 step
+          if (ks == 0) umma_f16_c<false>(d_tmem, a_hi, w_hi, idesc);
+          else umma_f16_c<true>(d_tmem, a_hi, w_hi, idesc);
+          umma_f16_c<true>(d_tmem, desc_advance(a_hi, 32), desc_advance(w_hi, 32), idesc);
+          if (L::kHasLo && (NPASS == 3 || res)) {
+            umma_f16_c<true>(d_tmem, a_lo, w_hi, idesc);
+            umma_f16_c<true>(d_tmem, desc_advance(a_lo, 32), desc_advance(w_hi, 32), idesc);
           }
-          umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-          if (++stage == kStages) {
-            stage = 0;
-            phase ^= 1;
+          if (NPASS == 3 && !res) {
+            umma_f16_c<true>(d_tmem, a_hi, w_lo, idesc);
+            umma_f16_c<true>(d_tmem, desc_advance(a_hi, 32), desc_advance(w_lo, 32), idesc);
           }
+          umma_commit(&empty_bar[stage]);                        // smem slot reusable once these MMAs retire
+          if (ks + 1 == k_slabs) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        __syncwarp();
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else {
-    // ===================== epilogue: warps 2..5, thread = one output row =====================
-    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    // ===================== epilogue: warps 2..9 =====================
+    // thread = one output row (TMEM lane quadrant = warp & 3); the two warps of a quadrant split
+    // the tile's 32-column chunks between them (half 0: first chunks, half 1: the rest), each
+    // half with its own staging buffers, store-issuing thread and named barrier.
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
-    const bool issuer = threadIdx.x == 64;  // issues / retires the TMA stores
+    const bool issuer = (warp == 2 || warp == 6) && lane == 0;  // issues / retires this half's TMA stores
     const float* vec = reinterpret_cast<const float*>(smem + L::kOffVec);
-    uint8_t* staging = smem + L::kOffStaging;
+    float2* stats = reinterpret_cast<float2*>(smem + L::kOffStats);
+    uint8_t* staging = smem + L::kOffStaging + half * 2 * kStageChunk;
+    constexpr int kHalfChunks = kChunks / 2;
+    const int c_begin = half * kHalfChunks, c_end = c_begin + kHalfChunks;
     int it = 0;
     uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
@@ -226,7 +238,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       if (LN) {
         float s = 0.f, q = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < kChunks; ++c) {
+        for (int c = c_begin; c < c_end; ++c) {
           tmem_ld32(taddr + c * 32, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -236,12 +248,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             q = fmaf(x, x, q);
           }
         }
+        float2* st = stats + (it & 1) * 2 * kBM;
+        st[half * kBM + r] = make_float2(s, q);
+        named_bar_sync(3, 256);
+        const float2 o = st[(half ^ 1) * kBM + r];
+        s += o.x;
+        q += o.y;
         mean = s * (1.f / N_TILE);
         rstd = rsqrtf(fmaxf(q * (1.f / N_TILE) - mean * mean, 0.f) + p.eps);
       }
 
 #pragma unroll 1
-      for (int c = 0; c < kChunks; ++c) {
+      for (int c = c_begin; c < c_end; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.n) break;  // chunk entirely outside the tensor (n not a multiple of N_TILE)
         tmem_ld32(taddr + c * 32, v);
@@ -272,13 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         } else {        // two 128 rows x 64 B planes, SWIZZLE_64B: unit i of row r at i ^ ((r >> 1) & 3)
           uint32_t hi[16], lo[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(v[2 * j], h0, l0);
-            split_bf16(v[2 * j + 1], h1, l1);
-            hi[j] = pack_bf16(h0, h1);
-            lo[j] = pack_bf16(l0, l1);
-          }
+          for (int j = 0; j < 16; ++j) split_pack2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
           uint8_t* rh = sb + r * 64;
           uint8_t* rl = rh + kStageChunk / 2;
 #pragma unroll
@@ -292,7 +304,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // the store of the previous chunk (other buffer) must have finished READING before the
         // threads that pass this barrier start overwriting that buffer for the next chunk
         if (issuer) tma_store_wait_read0();
-        epi_bar_sync();
+        named_bar_sync(1 + half, 128);
         if (issuer) {
           tma_store_3d(&map_o0, sb, col0, t0, b);
           if (!OUT_F32) tma_store_3d(&map_o1, sb + kStageChunk / 2, col0, t0, b);
