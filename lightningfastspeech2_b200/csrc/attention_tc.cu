@@ -7,16 +7,19 @@
 //   no transposed copy of V exists anywhere).
 //
 //   TMEM columns (512):  [0,128)   Q   bf16 pairs: hi plane cols 0..63, lo plane cols 64..127
-//                        [128,256) S/P two 64-column buffers: S_j fp32 (64 keys) is
+//                        [128,320) S/P three 64-column buffers: S_j fp32 (64 keys) is
 //                                  overwritten in place by P_j (hi: 32 cols, lo: 32 cols)
-//                        [256,384) O   fp32 accumulator (128 head-dim columns)
+//                        [320,448) O   fp32 accumulator (128 head-dim columns)
 //
-//   warps: 0 = TMA producer (K and V rings, 3 stages each), 1 = MMA issuer (one thread),
+//   warps: 0 = TMA producer of the Q tile and the K ring, 10 = TMA producer of the V ring
+//   (3 stages each), 1 = MMA issuer (one elected thread),
 //   2..9 = softmax (thread = query row; TMEM lane quadrant = warp & 3; the two warps of a
 //   quadrant split each tile's 64 keys and the 128 O columns, and agree on the row maximum
 //   through shared memory + one 64-thread named barrier per tile).
-//   tensor-pipe order:  QK_0 QK_1 | PV_0 QK_2 | PV_1 QK_3 | ...   so softmax_{j+1} overlaps
-//   PV_j + QK_{j+2}.  Online softmax with a lazily updated exponent reference: the O
+//   tensor-pipe order:  QK_0 QK_1 QK_2 | PV_0 QK_3 | PV_1 QK_4 | ...   QK runs up to three tiles
+//   ahead, so the softmax warps always find S ready and only PV waits for them.  The Q tile is
+//   fetched by TMA into (still idle) V-ring memory and moved to TMEM by the softmax warps; the
+//   normalised O leaves through swizzled staging in the (idle) K ring and TMA tensor stores.  Online softmax with a lazily updated exponent reference: the O
 //   accumulator is rescaled in TMEM only when a row's logits outgrow the reference by 2^8.
 //
 //   NPASS = 3: hi.hi + lo.hi + hi.lo for both products (fp32-parity mode); NPASS = 1: hi.hi.
@@ -33,9 +36,10 @@ constexpr int kAQ = 128;        // queries per CTA (UMMA M)
 constexpr int kAK = 64;         // keys per tile
 constexpr int kDH = 128;        // head dim
 constexpr int kKVStages = 3;
-constexpr int kAttnTcThreads = 320;  // TMA, MMA, 8 softmax warps (two per TMEM lane quadrant)
+constexpr int kAttnTcThreads = 352;  // K-TMA, MMA, 8 softmax warps (two per TMEM lane quadrant), V-TMA
+constexpr int kSBufs = 3;           // S/P buffers in TMEM: QK products run up to 3 tiles ahead of PV
 constexpr int kTileBytes = kAK * kDH * 2;          // one plane of a K or V tile: 16 KB
-constexpr uint32_t kColQ = 0, kColS = 128, kColO = 256;
+constexpr uint32_t kColQ = 0, kColS = 128, kColO = 128 + kSBufs * kAK;
 
 // 32 lanes x 32 columns without the trailing wait (caller batches the wait)
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
@@ -104,18 +108,27 @@ __global__ void attn_kend_kernel(const uint8_t* __restrict__ kpm, int* __restric
   if (lane == 0) kend[b] = last;
 }
 
+__device__ __forceinline__ void tma_store_3d_a(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+
 template <int NPASS>
 __global__ void __launch_bounds__(kAttnTcThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
+                    const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
+                    const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
                     const AttnTcParams p) {
   constexpr int kPlanes = NPASS == 3 ? 2 : 1;
   constexpr int kStageBytes = kPlanes * kTileBytes;  // K (or V) tile, hi [+ lo]
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sK = smem;
-  uint8_t* sV = smem + kKVStages * kStageBytes;
+  uint8_t* sK = smem;                                // K ring; reused as the O staging buffer at the end
+  uint8_t* sV = smem + kKVStages * kStageBytes;      // V ring; holds the Q tile until it has moved to TMEM
   __shared__ __align__(8) uint64_t k_full[kKVStages], k_empty[kKVStages], v_full[kKVStages], v_empty[kKVStages];
-  __shared__ __align__(8) uint64_t q_full, s_full[2], p_full[2], pv_done, o_final;
+  __shared__ __align__(8) uint64_t q_smem_full, q_full, s_full[kSBufs], p_full[kSBufs], pv_done[kSBufs], o_final;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float xch[2][2][kAQ];  // [tile parity][half][row]: row maxima / partial sums between the warp pair
 
@@ -127,6 +140,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_hi);
+    prefetch_tmap(&map_q_hi);
     if (NPASS == 3) prefetch_tmap(&map_lo);
     for (int s = 0; s < kKVStages; ++s) {
       mbar_init(&k_full[s], 1);
@@ -134,12 +148,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
     }
+    mbar_init(&q_smem_full, 1);
     mbar_init(&q_full, 8);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kSBufs; ++i) {
       mbar_init(&s_full[i], 1);
       mbar_init(&p_full[i], 8);
+      mbar_init(&pv_done[i], 1);
     }
-    mbar_init(&pv_done, 1);
     mbar_init(&o_final, 1);
     fence_barrier_init();
   }
@@ -150,35 +165,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   const uint32_t tmem_base = tmem_base_smem;
 
   if (warp == 0) {
-    // ===================== TMA producer: K_j then V_j =====================
+    // ===================== TMA producer: Q tile, then the K ring =====================
     if (lane == 0) {
+      // Q (128 rows x 128 head-dim columns per plane) as two [64 cols x 128 rows] SWIZZLE_128B boxes
+      mbar_expect_tx(&q_smem_full, kPlanes * 2 * 16384);
+#pragma unroll
+      for (int bx = 0; bx < 2; ++bx) {
+        tma_load_3d(sV + bx * 16384, &map_q_hi, &q_smem_full, col_q + bx * 64, q0, b);
+        if (NPASS == 3) tma_load_3d(sV + 32768 + bx * 16384, &map_q_lo, &q_smem_full, col_q + bx * 64, q0, b);
+      }
       for (int j = 0; j < ntiles; ++j) {
         const int st = j % kKVStages;
-        const uint32_t ph = (j / kKVStages) & 1;
-        const int key0 = j * kAK;
-        mbar_wait(&k_empty[st], ph ^ 1);
+        mbar_wait(&k_empty[st], ((j / kKVStages) & 1) ^ 1);
         mbar_expect_tx(&k_full[st], kStageBytes);
         uint8_t* dk = sK + st * kStageBytes;
 #pragma unroll
         for (int c = 0; c < kDH / 32; ++c) {
-          tma_load_3d(dk + c * 4096, &map_hi, &k_full[st], col_k + c * 32, key0, b);
-          if (NPASS == 3) tma_load_3d(dk + kTileBytes + c * 4096, &map_lo, &k_full[st], col_k + c * 32, key0, b);
+          tma_load_3d(dk + c * 4096, &map_hi, &k_full[st], col_k + c * 32, j * kAK, b);
+          if (NPASS == 3) tma_load_3d(dk + kTileBytes + c * 4096, &map_lo, &k_full[st], col_k + c * 32, j * kAK, b);
         }
-        mbar_wait(&v_empty[st], ph ^ 1);
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== TMA producer: the V ring (after Q has left shared memory) =====================
+    if (lane == 0) {
+      mbar_wait(&q_full, 0);
+      for (int j = 0; j < ntiles; ++j) {
+        const int st = j % kKVStages;
+        mbar_wait(&v_empty[st], ((j / kKVStages) & 1) ^ 1);
         mbar_expect_tx(&v_full[st], kStageBytes);
         uint8_t* dv = sV + st * kStageBytes;
 #pragma unroll
         for (int c = 0; c < kDH / 32; ++c) {
-          tma_load_3d(dv + c * 4096, &map_hi, &v_full[st], col_v + c * 32, key0, b);
-          if (NPASS == 3) tma_load_3d(dv + kTileBytes + c * 4096, &map_lo, &v_full[st], col_v + c * 32, key0, b);
+          tma_load_3d(dv + c * 4096, &map_hi, &v_full[st], col_v + c * 32, j * kAK, b);
+          if (NPASS == 3) tma_load_3d(dv + kTileBytes + c * 4096, &map_lo, &v_full[st], col_v + c * 32, j * kAK, b);
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     // The whole warp runs the (warp-uniform) control flow so descriptors stay in uniform
-    // registers; one elected lane issues the tcgen05 instructions.  Per-instruction work is a
-    // 64-bit add on a precomputed descriptor.
+    // registers; one elected lane issues the tcgen05 instructions.  QK products run up to
+    // kSBufs tiles ahead of the PV products, so the softmax warps always find S ready.
     if (ntiles > 0) {
       constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, kAQ, kAK, 0, 0);  // A: TMEM, B: K tile, K-major
       constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, kAQ, kDH, 0, 1);  // A: TMEM, B: V tile, MN-major
@@ -187,11 +215,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       const uint64_t dv0 = make_smem_desc(smem_u32(sV), 4096, 512, kSwizzle64);
 
       auto issue_qk = [&](int j) {
-        const int st = j % kKVStages;
+        const int st = j % kKVStages, sb = j % kSBufs;
         mbar_wait(&k_full[st], (j / kKVStages) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t ts = tmem_base + kColS + (j & 1) * kAK;
+          const uint32_t ts = tmem_base + kColS + sb * kAK;
           const uint64_t dkh = desc_advance(dk0, st * kStageBytes), dkl = desc_advance(dkh, kTileBytes);
 #pragma unroll
           for (int i = 0; i < kDH / 16; ++i) {
@@ -204,22 +232,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             }
           }
           umma_commit(&k_empty[st]);
-          umma_commit(&s_full[j & 1]);
+          umma_commit(&s_full[sb]);
         }
         __syncwarp();
       };
 
       mbar_wait(&q_full, 0);
       tc_fence_after();
-      issue_qk(0);
-      if (ntiles > 1) issue_qk(1);
+      for (int j = 0; j < kSBufs && j < ntiles; ++j) issue_qk(j);
       for (int j = 0; j < ntiles; ++j) {
-        const int st = j % kKVStages;
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        const int st = j % kKVStages, sb = j % kSBufs;
+        mbar_wait(&p_full[sb], (j / kSBufs) & 1);
         mbar_wait(&v_full[st], (j / kKVStages) & 1);
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t tp = tmem_base + kColS + (j & 1) * kAK;  // P hi: 32 cols, P lo: next 32
+          const uint32_t tp = tmem_base + kColS + sb * kAK;  // P hi: 32 cols, P lo: next 32
           const uint64_t dvh = desc_advance(dv0, st * kStageBytes), dvl = desc_advance(dvh, kTileBytes);
 #pragma unroll
           for (int i = 0; i < kAK / 16; ++i) {
@@ -231,15 +258,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
             }
           }
           umma_commit(&v_empty[st]);
-          umma_commit(&pv_done);
+          umma_commit(&pv_done[sb]);
           if (j + 1 == ntiles) umma_commit(&o_final);  // every product of this CTA has landed
         }
         __syncwarp();
-        if (j + 2 < ntiles) issue_qk(j + 2);
+        if (j + kSBufs < ntiles) issue_qk(j + kSBufs);
       }
     }
   } else {
-    // ===================== softmax warps: thread = query row =====================
+    // ===================== softmax warps 2..9: thread = query row =====================
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;  // which 32 of the tile's 64 keys / which 64 of the 128 O columns
     const int r = quad * 32 + lane;
@@ -247,27 +274,24 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     const bool row_ok = tq_row < p.t;
     const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
 
-    // ---- Q row -> TMEM (bf16 pairs; half 0 loads the hi plane -> cols 0..63, half 1 the lo plane -> 64..127) ----
+    // ---- Q row: swizzled shared memory -> TMEM (bf16 pairs; half 0 moves the hi plane -> cols 0..63,
+    //      half 1 the lo plane -> cols 64..127) ----
     {
-      uint32_t w[32];
-      const __nv_bfloat16* src = (half == 0 ? p.qkv_hi : p.qkv_lo) + ((size_t)b * p.t + tq_row) * 3 * p.d + col_q;
-      const bool load = row_ok && (half == 0 || NPASS == 3);
+      mbar_wait(&q_smem_full, 0);
+      if (half == 0 || NPASS == 3) {
+        const uint8_t* qrow = sV + half * 32768 + r * 128;
+        uint32_t w[32];
 #pragma unroll
-      for (int hh = 0; hh < 2; ++hh) {
-        if (load) {
-          const uint4* s4 = reinterpret_cast<const uint4*>(src) + hh * 8;
+        for (int bx = 0; bx < 2; ++bx) {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            uint4 v = __ldg(s4 + i);
+            const uint4 v = *reinterpret_cast<const uint4*>(qrow + bx * 16384 + ((i ^ (r & 7)) << 4));
             w[4 * i] = v.x; w[4 * i + 1] = v.y; w[4 * i + 2] = v.z; w[4 * i + 3] = v.w;
           }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) w[i] = 0u;
+          tmem_st32_u(tmem_base + kColQ + half * 64 + bx * 32 + lane_off, w);
         }
-        tmem_st32_u(tmem_base + kColQ + half * 64 + hh * 32 + lane_off, w);
+        tmem_wait_st();
       }
-      tmem_wait_st();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&q_full);
@@ -277,19 +301,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     float l_run = 0.f;        // partial row sum over this half's keys
     const float c = p.scale_log2e;
     const uint8_t* mrow = p.kpm ? p.kpm + (size_t)b * p.t : nullptr;
+    // "key is masked" flag of this lane's key in the NEXT tile (prefetched one tile ahead)
+    auto key_masked = [&](int j) {
+      const int k1 = j * kAK + half * 32 + lane;
+      return (k1 >= p.t) || (mrow && mrow[k1]);
+    };
+    bool next_masked = ntiles > 0 ? key_masked(0) : true;
 
     for (int j = 0; j < ntiles; ++j) {
-      const int key0 = j * kAK + half * 32;
-      // "key is masked" bits of this half's 32 keys (PAD keys and keys beyond T), warp-uniform
-      uint32_t mbits;
-      {
-        int k1 = key0 + lane;
-        bool b1 = (k1 >= p.t) || (mrow && mrow[k1]);
-        mbits = __ballot_sync(0xffffffffu, b1);
-      }
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      const int sb = j % kSBufs;
+      const uint32_t mbits = __ballot_sync(0xffffffffu, next_masked);
+      if (j + 1 < ntiles) next_masked = key_masked(j + 1);
+      mbar_wait(&s_full[sb], (j / kSBufs) & 1);
       tc_fence_after();
-      const uint32_t ts = tmem_base + kColS + (j & 1) * kAK + lane_off;
+      const uint32_t ts = tmem_base + kColS + sb * kAK + lane_off;
       float s[32];
       tmem_ld32(ts + half * 32, s);
       if (mbits) {
@@ -300,7 +325,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       float tmax = s[0];
 #pragma unroll
       for (int i = 1; i < 32; ++i) tmax = fmaxf(tmax, s[i]);
-      // row maximum over all 64 keys: exchange with the partner warp (parity double buffer)
+      // row maximum over all 64 keys: exchange with the partner warp (parity double buffer); the
+      // barrier also orders "both halves have read S" before either overwrites it with P
       xch[j & 1][half][r] = tmax;
       pair_bar_sync(quad);
       tmax = fmaxf(tmax, xch[j & 1][half ^ 1][r]);
@@ -314,7 +340,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         m_run = tmax;
       } else if (__any_sync(0xffffffffu, grow)) {
         const float m_new = fmaxf(m_run, tmax);
-        mbar_wait(&pv_done, (j - 1) & 1);  // all PV products up to tile j-1 have landed in O
+        // every PV product up to tile j-1 must have landed in O (PV_j cannot start before our P_j)
+        mbar_wait(&pv_done[(j - 1) % kSBufs], ((j - 1) / kSBufs) & 1);
         tc_fence_after();
         const float alpha = (m_new == -INFINITY) ? 1.f : ex2_approx((m_run - m_new) * c);
         l_run *= alpha;
@@ -345,19 +372,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[j & 1]);
+      if (lane == 0) mbar_arrive(&p_full[sb]);
     }
 
-    // ---- epilogue: O / l -> ctx planes (this half's 64 columns) ----
+    // ---- epilogue: O / l (this half's 64 columns) -> ctx ----
     xch[ntiles & 1][half][r] = l_run;
     pair_bar_sync(quad);
     l_run += xch[ntiles & 1][half ^ 1][r];
-    const size_t orow = ((size_t)b * p.t + tq_row) * p.d + col_q;
     if (ntiles > 0) {
       mbar_wait(&o_final, 0);
       tc_fence_after();
     }
     const float inv_l = 1.f / l_run;  // l == 0 (no unmasked key) -> inf -> NaN rows, like the reference
+    const size_t orow = ((size_t)b * p.t + tq_row) * p.d + col_q;
     float o[32];
 #pragma unroll 1
     for (int cc = 2 * half; cc < 2 * half + 2; ++cc) {
@@ -369,24 +396,36 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] = __int_as_float(0x7fc00000);
       }
-      if (row_ok) {
-        if (p.ctx_f32) {
-          float4* of = reinterpret_cast<float4*>(p.ctx_f32 + orow + cc * 32);
+      if (p.ctx_f32 && row_ok) {  // fp32 copy (tests / callers that want the reference's dtype)
+        float4* of = reinterpret_cast<float4*>(p.ctx_f32 + orow + cc * 32);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) of[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+        for (int i = 0; i < 8; ++i) of[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+      }
+      if (p.ctx_hi) {  // planes: swizzled staging in the (now idle) K ring, then TMA tensor stores
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) split_pack2(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
+        uint8_t* rh = sK + cc * 16384 + r * 64;  // chunk cc: hi plane [128 rows x 64 B], lo plane 8 KB further
+        uint8_t* rl = rh + 8192;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int u = (i ^ ((r >> 1) & 3)) << 4;
+          *reinterpret_cast<uint4*>(rh + u) = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+          *reinterpret_cast<uint4*>(rl + u) = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
         }
-        if (p.ctx_hi) {
-          uint32_t hi[16], lo[16];
+      }
+    }
+    if (p.ctx_hi) {
+      fence_proxy_async_smem();
+      asm volatile("bar.sync 8, 256;" ::: "memory");  // all 8 softmax warps have staged their columns
+      if (warp == 2 && lane == 0) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) split_pack2(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
-          uint4* oh = reinterpret_cast<uint4*>(p.ctx_hi + orow + cc * 32);
-          uint4* ol = reinterpret_cast<uint4*>(p.ctx_lo + orow + cc * 32);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-            ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-          }
+        for (int cc = 0; cc < kDH / 32; ++cc) {
+          tma_store_3d_a(&map_o_hi, sK + cc * 16384, col_q + cc * 32, q0, b);
+          tma_store_3d_a(&map_o_lo, sK + cc * 16384 + 8192, col_q + cc * 32, q0, b);
         }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
       }
     }
   }
@@ -399,9 +438,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   }
 }
 
+struct AttnMaps {
+  CUtensorMap kv_hi, kv_lo, q_hi, q_lo, o_hi, o_lo;
+};
+
 template <int NPASS>
-static int launch_attention_tc(const CUtensorMap& mh, const CUtensorMap& ml, const AttnTcParams& p, int batch,
-                               int nhead, cudaStream_t s) {
+static int launch_attention_tc(const AttnMaps& m, const AttnTcParams& p, int batch, int nhead, cudaStream_t s) {
   constexpr int kSmem = 2 * kKVStages * (NPASS == 3 ? 2 : 1) * kTileBytes + 1024;
   auto kern = attention_tc_kernel<NPASS>;
   static bool configured = false;
@@ -413,7 +455,7 @@ static int launch_attention_tc(const CUtensorMap& mh, const CUtensorMap& ml, con
     configured = true;
   }
   dim3 grid((p.t + kAQ - 1) / kAQ, nhead, batch);
-  kern<<<grid, kAttnTcThreads, kSmem, s>>>(mh, ml, p);
+  kern<<<grid, kAttnTcThreads, kSmem, s>>>(m.kv_hi, m.kv_lo, m.q_hi, m.q_lo, m.o_hi, m.o_lo, p);
   LFS2_CHECK_LAUNCH("attention_tc");
   return LFS2_OK;
 }
@@ -450,10 +492,22 @@ int lfs2_attention_tc(const void* qkv_hi, const void* qkv_lo, const uint8_t* key
   attn_kend_kernel<<<ceil_div((long long)batch * 32, 128), 128, 0, s>>>(key_padding_mask, kend, batch, t);
   LFS2_CHECK_LAUNCH("attn_kend");
 
-  CUtensorMap mh, ml;
-  bool ok = make_tmap_3d(&mh, qkv_hi, 3ull * d, t, batch, 32, kAK, 64);
-  if (npass == 3) ok = ok && make_tmap_3d(&ml, qkv_lo, 3ull * d, t, batch, 32, kAK, 64);
-  else ml = mh;
+  AttnMaps m;
+  bool ok = make_tmap_3d(&m.kv_hi, qkv_hi, 3ull * d, t, batch, 32, kAK, 64) &&
+            make_tmap_3d(&m.q_hi, qkv_hi, 3ull * d, t, batch, 64, kAQ, 128);
+  if (npass == 3)
+    ok = ok && make_tmap_3d(&m.kv_lo, qkv_lo, 3ull * d, t, batch, 32, kAK, 64) &&
+         make_tmap_3d(&m.q_lo, qkv_lo, 3ull * d, t, batch, 64, kAQ, 128);
+  else {
+    m.kv_lo = m.kv_hi;
+    m.q_lo = m.q_hi;
+  }
+  if (ctx_hi)
+    ok = ok && make_tmap_3d(&m.o_hi, ctx_hi, d, t, batch, 32, kAQ, 64) && make_tmap_3d(&m.o_lo, ctx_lo, d, t, batch, 32, kAQ, 64);
+  else {
+    m.o_hi = m.kv_hi;
+    m.o_lo = m.kv_hi;
+  }
   LFS2_REQUIRE(ok, LFS2_ERR_CUDA, "attention_tc: cuTensorMapEncodeTiled failed");
 
   AttnTcParams p;
@@ -467,8 +521,7 @@ int lfs2_attention_tc(const void* qkv_hi, const void* qkv_lo, const uint8_t* key
   p.t = t;
   p.d = d;
   p.scale_log2e = (float)(1.4426950408889634 / sqrt((double)kDH));
-  return npass == 3 ? launch_attention_tc<3>(mh, ml, p, batch, nhead, s)
-                    : launch_attention_tc<1>(mh, ml, p, batch, nhead, s);
+  return npass == 3 ? launch_attention_tc<3>(m, p, batch, nhead, s) : launch_attention_tc<1>(m, p, batch, nhead, s);
 }
 
 }  // extern "C"
