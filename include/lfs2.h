@@ -172,6 +172,112 @@ LFS2_API int lfs2_merge_planes(const void* hi, const void* lo, float* out, long 
 /* hi = bf16(x), lo = bf16(x - hi) for n fp32 values (n % 4 == 0) */
 LFS2_API int lfs2_split_bf16(const float* x, void* hi, void* lo, long long n, void* stream);
 
+/* ================= train-step config: backward kernels, loss, optimizer ===================
+ * The reference obtains all of these from torch.autograd / torch.optim; the citations name the
+ * forward construct each gradient belongs to.  Parameter-gradient outputs ACCUMULATE (+=) into
+ * caller-owned buffers (zeroed once per step by lfs2_adamw_step) using fp32 atomics. */
+
+/* lfs2_add_layernorm that also saves the pre-norm sum z = x (+ y) (m,d) and the per-row
+ * (mean, rstd) pairs stats (m,2) needed by lfs2_layernorm_bwd; z_out / stats may be NULL. */
+LFS2_API int lfs2_add_layernorm_train(const float* x, const float* y, const float* gamma, const float* beta,
+                                      float* out, float* z_out, float* stats, int m, int d, float eps,
+                                      void* stream);
+/* backward of out = LayerNorm(z; gamma, beta) (model.py:114-115, 538, 556):
+ *   dz = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat)) (+ add if non-NULL)
+ *   dgamma += sum_m dy * xhat ; dbeta += sum_m dy */
+LFS2_API int lfs2_layernorm_bwd(const float* dy, const float* z, const float* stats, const float* gamma,
+                                const float* add, float* dz, float* dgamma, float* dbeta, int m, int d,
+                                void* stream);
+
+/* weight gradient of Linear / pointwise Conv1d / one tap of a dense Conv1d:
+ *   c[n,k] += sum_r a[r, n] * b[r + shift, k]      (r over m rows; a is dY, b is the layer input)
+ * t > 0: rows are frames of utterances of length t and b-rows shifted outside [0,t) count as zero
+ * (Conv1d "same" padding); t = 0 requires shift = 0.  lda/ldb/ldc = leading dimensions. */
+LFS2_API int lfs2_gemm_tn(const float* a, const float* b, float* c, int m, int n, int k, int lda, int ldb,
+                          int ldc, int t, int shift, void* stream);
+/* bias gradient: out[n] += sum_m a[m,n] */
+LFS2_API int lfs2_colsum(const float* a, float* out, int m, int n, void* stream);
+/* dx = y > 0 ? dy : 0 (y = the ReLU output; dx may alias dy) */
+LFS2_API int lfs2_relu_bwd(const float* dy, const float* y, float* dx, long long n, void* stream);
+/* dst += src */
+LFS2_API int lfs2_add_inplace(float* dst, const float* src, long long n, void* stream);
+/* out (cols, rows) = in (rows, cols)^T -- transposed weight copies for the input-gradient GEMMs */
+LFS2_API int lfs2_transpose(const float* in, float* out, int rows, int cols, void* stream);
+
+/* depthwise Conv1d weight/bias gradient (model.py:75-81, 545-551):
+ *   dwt[j,c] += sum_{b,t} dy[b,t,c] * x[b,t+j-(ksize-1)/2,c] ; dbias[c] += sum dy   (dbias may be NULL)
+ * the input gradient is lfs2_dwconv1d itself with the taps reversed and a zero bias. */
+LFS2_API int lfs2_dwconv1d_bwd_w(const float* dy, const float* x, float* dwt, float* dbias, int batch, int t,
+                                 int d, int ksize, void* stream);
+
+/* lfs2_attention that also writes lse (B, nhead, T) = log-sum-exp of the scaled, masked logits */
+LFS2_API int lfs2_attention_lse(const float* qkv, const uint8_t* key_padding_mask, float* ctx, float* lse,
+                                int batch, int t, int d, int nhead, void* stream);
+/* backward of the attention core: dqkv (B,T,3d) = [dq | dk | dv] from qkv, ctx = forward output,
+ * dctx and the saved lse; probabilities are recomputed tile by tile.  workspace:
+ * lfs2_attention_bwd_workspace_bytes(batch, t, nhead) bytes. */
+LFS2_API long long lfs2_attention_bwd_workspace_bytes(int batch, int t, int nhead);
+LFS2_API int lfs2_attention_bwd(const float* qkv, const float* ctx, const float* dctx, const float* lse,
+                                const uint8_t* key_padding_mask, float* dqkv, void* workspace, int batch,
+                                int t, int d, int nhead, void* stream);
+
+/* LengthRegulator backward (model.py:349-370): dx[b,p,:] = sum of dout[b,f,:] over the frames
+ * f in [cum[b,p-1], min(cum[b,p], l)) phone p was repeated into (cum from lfs2_length_regulate_scan). */
+LFS2_API int lfs2_length_regulate_bwd(const float* dout, const int64_t* cum, float* dx, int batch, int tp,
+                                      int l, int d, void* stream);
+
+/* nn.Embedding weight gradient (fastspeech2.py:653; model.py:401,422): demb[idx[m],:] += dx[m,:];
+ * rows with idx == skip_idx get none (padding_idx; pass -1 for no padding row). */
+LFS2_API int lfs2_embedding_bwd(const float* dx, const int64_t* idx, float* demb, int m, int d, int nrows_emb,
+                                long long skip_idx, void* stream);
+/* out-of-place lfs2_bucket_embed_add: x[m,:] = x_in[m,:] + emb[idx,:] (the input stays intact for
+ * the predictor's backward pass) */
+LFS2_API int lfs2_bucket_embed_add_oop(const float* x_in, float* x, const float* val, float std, float mean,
+                                       const float* bins, int nbins, const float* emb,
+                                       const int64_t* idx_forced, int64_t* idx_out, float* acc, int acc_mode,
+                                       int m, int d, void* stream);
+
+/* backward of lfs2_rowdot_mask (model.py:512-518): g = mask[m] ? 0 : dout[m];
+ *   dz[m,:] = g * w ; dw += sum_m g * z[m,:] ; db += sum_m g */
+LFS2_API int lfs2_rowdot_mask_bwd(const float* dout, const float* z, const float* w, const uint8_t* mask,
+                                  float* dz, float* dw, float* db, int m, int f, void* stream);
+
+/* gradient of the broadcast speaker term (model.py:137-143 used at fastspeech2.py:658,707):
+ *   out[b,:] += sum_t dx[b,t,:] */
+LFS2_API int lfs2_sum_over_time(const float* dx, float* out, int batch, int t, int d, void* stream);
+
+/* conv2 of the depthwise FFTBlock (model.py:85-93): grouped 1x1 conv2.0 (weight w20 (F, g, 1),
+ * groups = d, g = F/d) followed by pointwise conv2.1 (weight w21 (d_out, F, 1)) folded into
+ *   w_eff (d_out, F) = w21 . blockdiag(w20) ; b_eff = b21 + w21 . b20
+ * and the chain rule back to the four reference parameters. */
+LFS2_API int lfs2_fold_pw_fwd(const float* w21, const float* w20, const float* b20, const float* b21,
+                              float* w_eff, float* b_eff, int d_out, int groups, int g, void* stream);
+LFS2_API int lfs2_fold_pw_bwd(const float* dw_eff, const float* db_eff, const float* w21, const float* w20,
+                              const float* b20, float* dw21, float* dw20, float* db20, float* db21, int d_out,
+                              int groups, int g, void* stream);
+
+/* ---- A9: FastSpeech2Loss default branches (loss.py:156-187) ---------------------------
+ * loss = mean over rows with pad_mask == 0 (and all `inner` columns) of |pred - tgt| (kind 0)
+ * or (pred - tgt)^2 (kind 1); tgt = target, or log(target_i64 + 1) for the duration loss.
+ * *loss_out = loss ; if total_out: *total_out += weight * loss (loss.py:204-211) ;
+ * if dpred: dpred = d(weight * loss)/d pred (zero on PAD rows).  workspace: 2 floats. */
+LFS2_API int lfs2_masked_loss(const float* pred, const float* target, const int64_t* target_i64,
+                              const uint8_t* pad_mask, int rows, int inner, int kind, float weight,
+                              float* loss_out, float* total_out, float* dpred, float* workspace, void* stream);
+
+/* x[i] *= *scalar (device scalar): applies an upstream d(total)/d(total) factor to the stored loss gradients */
+LFS2_API int lfs2_scale_by(float* x, const float* scalar, long long n, void* stream);
+
+/* ---- A10: AdamW + Noam (fastspeech2.py:1166-1182, noam.py:20-25) -----------------------
+ * out[0] += sum x^2 (global gradient norm for clipping) */
+LFS2_API int lfs2_sumsq(const float* x, float* out, long long n, void* stream);
+/* one AdamW step over flat buffers, torch.optim.AdamW operation order; the caller passes the
+ * Noam-scheduled lr.  g is scaled by grad_scale (1/world_size) and, if max_norm > 0, by
+ * min(1, max_norm / (sqrt(*gnorm_sq) * grad_scale + 1e-6)); zero_grad != 0 clears g afterwards. */
+LFS2_API int lfs2_adamw_step(float* p, float* g, float* m, float* v, long long n, float lr, float beta1,
+                             float beta2, float eps, float weight_decay, int step, float grad_scale,
+                             float max_norm, const float* gnorm_sq, int zero_grad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "liblfs2.so")
 
-_vp, _i, _f = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+_vp, _i, _f, _ll = ctypes.c_void_p, ctypes.c_int, ctypes.c_float, ctypes.c_longlong
 
 # name -> argtypes; every function returns int except lfs2_last_error
 SIGNATURES = {
@@ -36,7 +36,31 @@ SIGNATURES = {
     "lfs2_attention_tc_workspace_bytes": [_i],
     "lfs2_attention_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "lfs2_split_bf16": [_vp, _vp, _vp, ctypes.c_longlong, _vp],
+    # train-step config
+    "lfs2_add_layernorm_train": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
+    "lfs2_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "lfs2_gemm_tn": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "lfs2_colsum": [_vp, _vp, _i, _i, _vp],
+    "lfs2_relu_bwd": [_vp, _vp, _vp, _ll, _vp],
+    "lfs2_add_inplace": [_vp, _vp, _ll, _vp],
+    "lfs2_transpose": [_vp, _vp, _i, _i, _vp],
+    "lfs2_dwconv1d_bwd_w": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "lfs2_attention_lse": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "lfs2_attention_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "lfs2_length_regulate_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "lfs2_embedding_bwd": [_vp, _vp, _vp, _i, _i, _i, _ll, _vp],
+    "lfs2_bucket_embed_add_oop": [_vp, _vp, _vp, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "lfs2_rowdot_mask_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "lfs2_sum_over_time": [_vp, _vp, _i, _i, _i, _vp],
+    "lfs2_fold_pw_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "lfs2_fold_pw_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "lfs2_masked_loss": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp],
+    "lfs2_sumsq": [_vp, _vp, _ll, _vp],
+    "lfs2_scale_by": [_vp, _vp, _ll, _vp],
+    "lfs2_adamw_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _f, _vp, _i, _vp],
 }
+# functions whose return type is not int
+RESTYPES = {"lfs2_attention_bwd_workspace_bytes": (ctypes.c_longlong, [_i, _i, _i])}
 
 _lib = None
 CALLS = 0  # C-ABI launches issued by this process (bench.py reports the per-step count)
@@ -60,6 +84,10 @@ def lib():
         fn = getattr(h, name)  # AttributeError if the .so does not export a declared symbol
         fn.argtypes = argtypes
         fn.restype = ctypes.c_int
+    for name, (restype, argtypes) in RESTYPES.items():
+        fn = getattr(h, name)
+        fn.argtypes = argtypes
+        fn.restype = restype
     h.lfs2_last_error.argtypes = []
     h.lfs2_last_error.restype = ctypes.c_char_p
     _lib = h

@@ -131,7 +131,31 @@ TINY_DENSE = dict(
     duration_depthwise_conv=False,
 )
 
-PRESETS = {"C1": C1, "C2": C2, "C3": C3, "TINY_DW": TINY_DW, "TINY_DENSE": TINY_DENSE}
+# small trainable shapes the CUDA kernels cover (head_dim 64, d % 32 == 0), every dropout off:
+# the train-step parity config (SURVEY 8c iv: gradient parity is only checkable with p = 0)
+NO_DROPOUT = dict(encoder_dropout=0.0, decoder_dropout=0.0, duration_dropout=0.0)
+SMALL_TRAIN = dict(
+    {**_TWO_VARS, **NO_DROPOUT},
+    variance_dropout=[0.0, 0.0],
+    encoder_hidden=128,
+    decoder_hidden=128,
+    variance_filter_size=128,
+    duration_filter_size=128,
+    encoder_conv_filter_size=256,
+    decoder_conv_filter_size=256,
+    encoder_layers=2,
+    decoder_layers=2,
+    encoder_kernel_sizes=[5, 9],
+    decoder_kernel_sizes=[17, 3],
+    variance_nlayers=[2, 2],
+    variance_nbins=32,
+)
+# C4: train step on the "76 M" model, dropout off in both arms (stated in bench.py's config)
+C4 = dict(C3, **NO_DROPOUT, variance_dropout=[0.0, 0.0, 0.0])
+# C2-size train step (7.4 M params)
+C2_TRAIN = dict(C2, **NO_DROPOUT, variance_dropout=[0.0, 0.0])
+
+PRESETS = {"SMALL_TRAIN": SMALL_TRAIN, "C4": C4, "C2_TRAIN": C2_TRAIN, "C1": C1, "C2": C2, "C3": C3, "TINY_DW": TINY_DW, "TINY_DENSE": TINY_DENSE}
 
 
 def resolve(kwargs):

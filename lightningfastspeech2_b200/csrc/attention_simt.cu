@@ -17,8 +17,8 @@ constexpr int kAttnThreads = 256;
 
 template <int DH>
 __global__ void __launch_bounds__(kAttnThreads)
-attention_f32_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ kpm, float* __restrict__ ctx, int t,
-                     int d, float scale) {
+attention_f32_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ kpm, float* __restrict__ ctx,
+                     float* __restrict__ lse, int t, int d, float scale) {
   extern __shared__ __align__(16) float smem[];
   constexpr int LD = DH + APAD;
   constexpr int NG = DH / 64;  // float4 column groups per thread in the PV product
@@ -151,6 +151,8 @@ attention_f32_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ 
     int q = q0 + ty + 16 * i;
     if (q >= t) continue;
     float inv = 1.f / l_i[i];  // 0/0 -> NaN for fully masked rows, like the reference
+    // log-sum-exp of the scaled logits, saved for the backward pass: P = exp(S - lse)
+    if (lse && tx == 0) lse[((size_t)b * gridDim.y + h) * t + q] = m_i[i] + logf(l_i[i]);
     float* orow = ctx + ((size_t)b * t + q) * d + (size_t)h * DH;
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
@@ -162,8 +164,8 @@ attention_f32_kernel(const float* __restrict__ qkv, const uint8_t* __restrict__ 
 }
 
 template <int DH>
-static int launch_attention(const float* qkv, const uint8_t* kpm, float* ctx, int batch, int t, int d, int nhead,
-                            cudaStream_t s) {
+static int launch_attention(const float* qkv, const uint8_t* kpm, float* ctx, float* lse, int batch, int t, int d,
+                            int nhead, cudaStream_t s) {
   size_t smem = sizeof(float) * (AQ * (DH + APAD) + AK * (DH + APAD) + AQ * (AK + APAD)) + sizeof(int) * AK;
   static bool configured = false;
   if (!configured) {
@@ -176,7 +178,7 @@ static int launch_attention(const float* qkv, const uint8_t* kpm, float* ctx, in
   }
   dim3 grid(ceil_div(t, AQ), nhead, batch);
   float scale = 1.0f / sqrtf((float)DH);
-  attention_f32_kernel<DH><<<grid, kAttnThreads, smem, s>>>(qkv, kpm, ctx, t, d, scale);
+  attention_f32_kernel<DH><<<grid, kAttnThreads, smem, s>>>(qkv, kpm, ctx, lse, t, d, scale);
   LFS2_CHECK_LAUNCH("attention");
   return LFS2_OK;
 }
@@ -187,6 +189,11 @@ using namespace lfs2;
 
 extern "C" int lfs2_attention(const float* qkv, const uint8_t* key_padding_mask, float* ctx, int batch, int t, int d,
                               int nhead, void* stream) {
+  return lfs2_attention_lse(qkv, key_padding_mask, ctx, nullptr, batch, t, d, nhead, stream);
+}
+
+extern "C" int lfs2_attention_lse(const float* qkv, const uint8_t* key_padding_mask, float* ctx, float* lse, int batch,
+                                  int t, int d, int nhead, void* stream) {
   LFS2_REQUIRE(qkv && ctx, LFS2_ERR_INVALID_ARG, "attention: null pointer");
   if (batch == 0 || t == 0) return LFS2_OK;
   LFS2_REQUIRE(batch > 0 && t > 0 && d > 0 && nhead > 0 && d % nhead == 0, LFS2_ERR_INVALID_ARG, "attention: bad shape");
@@ -195,9 +202,9 @@ extern "C" int lfs2_attention(const float* qkv, const uint8_t* key_padding_mask,
   cudaStream_t s = (cudaStream_t)stream;
   int dh = d / nhead;
   switch (dh) {
-    case 64: return launch_attention<64>(qkv, key_padding_mask, ctx, batch, t, d, nhead, s);
-    case 128: return launch_attention<128>(qkv, key_padding_mask, ctx, batch, t, d, nhead, s);
-    case 384: return launch_attention<384>(qkv, key_padding_mask, ctx, batch, t, d, nhead, s);
+    case 64: return launch_attention<64>(qkv, key_padding_mask, ctx, lse, batch, t, d, nhead, s);
+    case 128: return launch_attention<128>(qkv, key_padding_mask, ctx, lse, batch, t, d, nhead, s);
+    case 384: return launch_attention<384>(qkv, key_padding_mask, ctx, lse, batch, t, d, nhead, s);
     default:
       set_error("attention: head_dim %d not supported (64, 128, 384)", dh);
       return LFS2_ERR_UNSUPPORTED;

@@ -89,7 +89,8 @@ __global__ void add_pe_spk_kernel(float4* __restrict__ x, const float4* __restri
 constexpr int kLnMaxVec = 8;  // float4 per lane -> d <= 1024
 __global__ void add_layernorm_kernel(const float4* __restrict__ x, const float4* __restrict__ y,
                                      const float4* __restrict__ gamma, const float4* __restrict__ beta,
-                                     float4* __restrict__ out, int m, int d4, float eps) {
+                                     float4* __restrict__ out, float4* __restrict__ z_out,
+                                     float2* __restrict__ stats, int m, int d4, float eps) {
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (row >= m) return;
@@ -107,6 +108,7 @@ __global__ void add_layernorm_kernel(const float4* __restrict__ x, const float4*
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
       }
       v[i] = a;
+      if (z_out) z_out[(size_t)row * d4 + c] = a;  // pre-norm sum, saved for the backward pass
       s += (a.x + a.y) + (a.z + a.w);
     }
   }
@@ -122,6 +124,7 @@ __global__ void add_layernorm_kernel(const float4* __restrict__ x, const float4*
     }
   }
   float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+  if (stats && lane == 0) stats[row] = make_float2(mean, rstd);
   float4* orow = out + (size_t)row * d4;
 #pragma unroll
   for (int i = 0; i < kLnMaxVec; ++i) {
@@ -274,7 +277,7 @@ __global__ void duration_round_guard_kernel(const float* __restrict__ log_dur, c
 
 // ---------------------------------------------------------------------------------------
 // bucketize (right=False, torch's lower-bound loop incl. its NaN behaviour) + embedding add
-__global__ void bucket_embed_add_kernel(float4* __restrict__ x, const float* __restrict__ val, float stdv,
+__global__ void bucket_embed_add_kernel(const float4* x_in, float4* x, const float* __restrict__ val, float stdv,
                                         float meanv, const float* __restrict__ bins, int nb,
                                         const float4* __restrict__ emb, const int64_t* __restrict__ idx_forced,
                                         int64_t* __restrict__ idx_out, float4* __restrict__ acc, int acc_mode,
@@ -299,9 +302,10 @@ __global__ void bucket_embed_add_kernel(float4* __restrict__ x, const float* __r
   if (lane == 0 && idx_out) idx_out[row] = idx;
   const float4* e = emb + (size_t)idx * d4;
   float4* xr = x + (size_t)row * d4;
+  const float4* xi = x_in + (size_t)row * d4;  // == xr for the in-place form
   float4* ar = acc ? acc + (size_t)row * d4 : nullptr;
   for (int c = lane; c < d4; c += 32) {
-    float4 ev = e[c], xv = xr[c];
+    float4 ev = e[c], xv = xi[c];
     xv.x += ev.x; xv.y += ev.y; xv.z += ev.z; xv.w += ev.w;
     xr[c] = xv;
     if (acc_mode == 1) {
@@ -519,7 +523,14 @@ int lfs2_add_pe_spk(float* x, const float* pe, const float* spk, int batch, int 
 
 int lfs2_add_layernorm(const float* x, const float* y, const float* gamma, const float* beta, float* out, int m,
                        int d, float eps, void* stream) {
+  return lfs2_add_layernorm_train(x, y, gamma, beta, out, nullptr, nullptr, m, d, eps, stream);
+}
+
+int lfs2_add_layernorm_train(const float* x, const float* y, const float* gamma, const float* beta, float* out,
+                             float* z_out, float* stats, int m, int d, float eps, void* stream) {
   LFS2_REQUIRE(x && gamma && beta && out, LFS2_ERR_INVALID_ARG, "add_layernorm: null pointer");
+  LFS2_REQUIRE((!z_out || aligned16(z_out)) && (reinterpret_cast<uintptr_t>(stats) & 7u) == 0, LFS2_ERR_INVALID_ARG,
+               "add_layernorm: z_out / stats misaligned");
   if (m == 0) return LFS2_OK;
   LFS2_REQUIRE(d > 0 && d % 4 == 0 && d <= 128 * kLnMaxVec, LFS2_ERR_UNSUPPORTED,
                "add_layernorm: d=%d must be a multiple of 4 and <= %d", d, 128 * kLnMaxVec);
@@ -527,7 +538,8 @@ int lfs2_add_layernorm(const float* x, const float* y, const float* gamma, const
                LFS2_ERR_INVALID_ARG, "add_layernorm: pointers must be 16-byte aligned");
   int threads = 256;
   add_layernorm_kernel<<<ceil_div((long long)m * 32, threads), threads, 0, (cudaStream_t)stream>>>(
-      (const float4*)x, (const float4*)y, (const float4*)gamma, (const float4*)beta, (float4*)out, m, d / 4, eps);
+      (const float4*)x, (const float4*)y, (const float4*)gamma, (const float4*)beta, (float4*)out, (float4*)z_out,
+      (float2*)stats, m, d / 4, eps);
   LFS2_CHECK_LAUNCH("add_layernorm");
   return LFS2_OK;
 }
@@ -604,7 +616,16 @@ int lfs2_duration_round_guard(const float* log_dur, const uint8_t* src_mask, int
 int lfs2_bucket_embed_add(float* x, const float* val, float stdv, float meanv, const float* bins, int nbins,
                           const float* emb, const int64_t* idx_forced, int64_t* idx_out, float* acc, int acc_mode,
                           int m, int d, void* stream) {
-  LFS2_REQUIRE(x && emb && (idx_forced || (val && bins)), LFS2_ERR_INVALID_ARG, "bucket_embed_add: null pointer");
+  return lfs2_bucket_embed_add_oop(x, x, val, stdv, meanv, bins, nbins, emb, idx_forced, idx_out, acc, acc_mode, m, d,
+                                   stream);
+}
+
+int lfs2_bucket_embed_add_oop(const float* x_in, float* x, const float* val, float stdv, float meanv,
+                              const float* bins, int nbins, const float* emb, const int64_t* idx_forced,
+                              int64_t* idx_out, float* acc, int acc_mode, int m, int d, void* stream) {
+  LFS2_REQUIRE(x_in && x && emb && (idx_forced || (val && bins)), LFS2_ERR_INVALID_ARG,
+               "bucket_embed_add: null pointer");
+  LFS2_REQUIRE(aligned16(x_in), LFS2_ERR_INVALID_ARG, "bucket_embed_add: x_in must be 16-byte aligned");
   if (m == 0) return LFS2_OK;
   LFS2_REQUIRE(d > 0 && d % 4 == 0 && nbins >= 1, LFS2_ERR_UNSUPPORTED, "bucket_embed_add: bad d/nbins");
   LFS2_REQUIRE(acc_mode == 0 || acc, LFS2_ERR_INVALID_ARG, "bucket_embed_add: acc_mode without acc");
@@ -612,7 +633,8 @@ int lfs2_bucket_embed_add(float* x, const float* val, float stdv, float meanv, c
                "bucket_embed_add: pointers must be 16-byte aligned");
   int threads = 256;
   bucket_embed_add_kernel<<<ceil_div((long long)m * 32, threads), threads, 0, (cudaStream_t)stream>>>(
-      (float4*)x, val, stdv, meanv, bins, nbins - 1, (const float4*)emb, idx_forced, idx_out, (float4*)acc,
+      (const float4*)x_in, (float4*)x, val, stdv, meanv, bins, nbins - 1, (const float4*)emb, idx_forced, idx_out,
+      (float4*)acc,
       acc ? acc_mode : 0, m, d / 4);
   LFS2_CHECK_LAUNCH("bucket_embed_add");
   return LFS2_OK;

@@ -19,6 +19,7 @@ import torch
 from torch import nn
 
 from .. import ops
+from . import training
 from .loss import FastSpeech2Loss
 from .model import (COMPUTE_MODES, ConformerEncoderLayer, PositionalEncoding, SpeakerEmbedding, VarianceAdaptor,
                     _PackCache)
@@ -334,6 +335,8 @@ class FastSpeech2(_Base):
         if dev.type != "cuda":
             raise ops._lib.Lfs2Error("FastSpeech2.forward needs the model on a CUDA device: there is no CPU path")
         hp = self.hparams
+        if not inference and self.training and torch.is_grad_enabled() and not force and not control:
+            return self._forward_train(targets)
         phones = targets["phones"].to(dev, non_blocking=True).contiguous()
         speakers = targets["speaker"].to(dev, dtype=torch.float32, non_blocking=True).contiguous()
 
@@ -376,12 +379,65 @@ class FastSpeech2(_Base):
                 result[f"_bucket_{var}"] = variance_output[f"_bucket_{var}"]
         return result
 
+    # -- train step: forward with saved activations + hand-written backward (training.py) -----
+    def _forward_train(self, targets):
+        """Teacher-forced forward (reference :636-784 with inference=False) whose outputs are connected
+        to autograd through ONE Function; its backward runs the liblfs2.so gradient kernels and
+        accumulates into p.grad (see training.py)."""
+        if not hasattr(self, "_grad_anchor") or self._grad_anchor.device != self.device:
+            self._grad_anchor = torch.zeros((), device=self.device, requires_grad=True)
+        keys = ["mel", "duration_prediction"] + [f"variances_{v}" for v in self.hparams.variances]
+        outs = training.ForwardTrainFn.apply(self._grad_anchor, self, targets, keys)
+        result = dict(self._last_train_result)
+        self._last_train_result = None
+        result.update(zip(keys, outs))
+        return result
+
+    def flatten_parameters(self):
+        """Re-home every trainable parameter (and its gradient) as a view of ONE flat fp32 buffer
+        (each tensor 128-byte aligned): the fused AdamW kernel and the single NCCL all-reduce of the
+        gradient path work on these buffers.  Call after .to(device); idempotent."""
+        params = [p for p in self.parameters() if p.requires_grad]
+        if getattr(self, "_flat_ids", None) == [id(p) for p in params] and self._flat_param.device == self.device:
+            return self._flat_param, self._flat_grad
+        offs, n = [], 0
+        for p in params:
+            offs.append(n)
+            n += (p.numel() + 31) // 32 * 32
+        dev = self.device
+        flat_p = torch.zeros(n, device=dev, dtype=torch.float32)
+        flat_g = torch.zeros(n, device=dev, dtype=torch.float32)
+        with torch.no_grad():
+            for p, o in zip(params, offs):
+                v = flat_p[o:o + p.numel()].view(p.shape)
+                v.copy_(p.data)
+                p.data = v
+                p.grad = flat_g[o:o + p.numel()].view(p.shape)
+        self._flat_param, self._flat_grad = flat_p, flat_g
+        self._flat_ids = [id(p) for p in params]
+        ops.WEIGHTS_EPOCH += 1
+        return flat_p, flat_g
+
+    def allreduce_gradients(self, group=None):
+        """Data-parallel gradient exchange: ONE NCCL all-reduce (sum) over the flat gradient buffer
+        (SURVEY 8e); the 1/world_size average is folded into FusedAdamW.  Returns the world size."""
+        import torch.distributed as dist
+
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+            return 1
+        _, flat_g = self.flatten_parameters()
+        dist.all_reduce(flat_g, op=dist.ReduceOp.SUM, group=group)
+        return dist.get_world_size(group)
+
     # -- train / validation steps (reference :786-807) ---------------------------------------
     def training_step(self, batch, batch_idx, optimizer_idx=0):
         result = self(batch, optimizer_idx)
         losses = self.loss(result, batch)
-        self.log_dict({f"train/{k}_loss": v.item() for k, v in losses.items()}, batch_size=self.batch_size,
-                      sync_dist=True)
+        if getattr(self, "log_losses", True):  # one D2H copy for all values (the reference does one .item() each)
+            vals = self.loss.last_buffer.tolist()
+            names = list(self.hparams.variances) + ["mel", "duration", "total"]
+            self.log_dict({f"train/{k}_loss": v for k, v in zip(names, vals)}, batch_size=self.batch_size,
+                          sync_dist=True)
         return losses["total"]
 
     def validation_step(self, batch, batch_idx):
@@ -392,7 +448,53 @@ class FastSpeech2(_Base):
         return self(batch, inference=True)
 
     def configure_optimizers(self):
-        self.optimizer = torch.optim.AdamW(self.parameters(), lr=self.hparams.lr, betas=[0.9, 0.98], eps=1e-8,
-                                           weight_decay=0.01)
+        """AdamW(lr, betas (0.9, 0.98), eps 1e-8, wd 0.01) + NoamLR stepped every batch (reference
+        :1166-1182).  On CUDA the optimizer is the fused flat-buffer AdamW kernel (same update rule,
+        same param_groups / scheduler interface); on CPU (construction-time checks) torch's own."""
+        if self.device.type == "cuda":
+            self.optimizer = FusedAdamW(self, lr=self.hparams.lr, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.01)
+        else:
+            self.optimizer = torch.optim.AdamW(self.parameters(), lr=self.hparams.lr, betas=[0.9, 0.98], eps=1e-8,
+                                               weight_decay=0.01)
         self.scheduler = NoamLR(self.optimizer, self.hparams.warmup_steps)
         return [self.optimizer], [{"scheduler": self.scheduler, "interval": "step"}]
+
+
+class FusedAdamW(torch.optim.Optimizer):
+    """torch.optim.AdamW semantics (decoupled weight decay, bias correction, same operation order) as
+    ONE kernel over the model's flat parameter / gradient / moment buffers (28 bytes per parameter).
+    ``grad_scale`` (1/world_size after the sum all-reduce) and optional global-norm clipping
+    (Trainer(gradient_clip_val=...) in the reference's scripts/train.sh) are folded into the same pass,
+    which also zeroes the gradient buffer for the next step.  The learning rate is read from
+    ``param_groups[0]["lr"]``, so NoamLR drives it exactly like torch's optimizer."""
+
+    def __init__(self, model, lr=1e-4, betas=(0.9, 0.98), eps=1e-8, weight_decay=0.01, max_grad_norm=0.0):
+        self.model = model
+        self.flat_p, self.flat_g = model.flatten_parameters()
+        params = [p for p in model.parameters() if p.requires_grad]
+        super().__init__(params, dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay))
+        self.exp_avg = torch.zeros_like(self.flat_p)
+        self.exp_avg_sq = torch.zeros_like(self.flat_p)
+        self.step_count = 0
+        self.grad_scale = 1.0
+        self.max_grad_norm = max_grad_norm
+        self._gnorm = torch.zeros(1, device=self.flat_p.device, dtype=torch.float32)
+
+    def zero_grad(self, set_to_none=False):
+        self.flat_g.zero_()
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        g = self.param_groups[0]
+        self.step_count += 1
+        gn = None
+        if self.max_grad_norm > 0:
+            self._gnorm.zero_()
+            ops.sumsq_(self._gnorm, self.flat_g)
+            gn = self._gnorm
+        ops.adamw_step_(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, g["lr"], g["betas"][0], g["betas"][1],
+                        g["eps"], g["weight_decay"], self.step_count, grad_scale=self.grad_scale,
+                        max_norm=self.max_grad_norm, gnorm_sq=gn, zero_grad=True)
+        ops.WEIGHTS_EPOCH += 1  # the kernel wrote through raw pointers: invalidate packed-weight caches
+        return loss

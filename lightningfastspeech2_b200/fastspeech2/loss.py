@@ -1,10 +1,32 @@
 """FastSpeech2Loss default branches (reference litfass/fastspeech2/loss.py:57-81, 83-213):
 masked MSE per variance, masked L1 on mel, masked MSE on log-duration, weighted total.
 
+On CUDA results every loss is one fused kernel (lfs2_masked_loss: value + d(weight*loss)/d pred
+in a single pass, no boolean-index gathers, no host sync); the values live in one small device
+buffer and ``losses["total"]`` is connected to autograd so ``training_step`` keeps the reference's
+contract (return the total, the trainer calls ``.backward()``).
+
 Soft-DTW, CWT and FastDiff/speaker losses are optional branches off the default path and
 raise NotImplementedError."""
 import torch
 from torch import nn
+
+from .. import ops
+
+
+class _LossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, total, grads, *preds):
+        ctx.grads = grads
+        return total.clone()
+
+    @staticmethod
+    def backward(ctx, gtotal):
+        out = []
+        for g in ctx.grads:
+            out.append(None if g is None else ops.scale_by_(g, gtotal.contiguous()))
+        ctx.grads = None
+        return (None, None, *out)
 
 
 class FastSpeech2Loss(nn.Module):
@@ -27,35 +49,46 @@ class FastSpeech2Loss(nn.Module):
         self.max_length = max_length
         self.loss_alphas = dict(loss_alphas or {})
 
-    @staticmethod
-    def _masked(pred, truth, kind, mask):
-        diff = pred[mask] - truth[mask]
-        return diff.abs().mean() if kind == "l1" else (diff * diff).mean()
-
     def forward(self, result, target, frozen_components=()):
-        dev, dt = result["mel"].device, result["mel"].dtype
-        valid_src = ~result["src_mask"]
-        valid_tgt = ~result["tgt_mask"]
+        mel = result["mel"]
+        if not mel.is_cuda:
+            raise ops._lib.Lfs2Error("FastSpeech2Loss needs CUDA results: there is no CPU path")
+        dev = mel.device
+        src_mask, tgt_mask = result["src_mask"], result["tgt_mask"]
         assert target["mel"].shape[1] <= self.max_length
-        losses = {}
-        for var, level, transform, kind in zip(self.variances, self.variance_levels, self.variance_transforms,
-                                               self.variance_losses):
+        want_grad = torch.is_grad_enabled() and mel.requires_grad
+        names = list(self.variances) + ["mel", "duration"]
+        buf = torch.zeros(len(names) + 1, device=dev, dtype=torch.float32)  # [losses..., total]
+        total = buf[len(names):]
+        preds, grads = [], []
+
+        def one(i, name, pred, kind, mask, tgt=None, tgt_i64=None):
+            frozen = any(f in name for f in frozen_components)
+            w = 0.0 if frozen else float(self.loss_alphas[name])
+            g = ops.masked_loss(pred.detach().contiguous(), tgt, mask, kind, w, buf[i:i + 1], None if frozen else total,
+                                want_grad=want_grad and not frozen, target_i64=tgt_i64)
+            preds.append(pred)
+            grads.append(g)
+
+        for i, (var, level, transform, kind) in enumerate(zip(self.variances, self.variance_levels,
+                                                              self.variance_transforms, self.variance_losses)):
             if transform == "cwt":
                 raise NotImplementedError("cwt loss")
-            truth = target[f"variances_{var}"].to(dev, dt)
+            pred = result[f"variances_{var}"]
+            truth = target[f"variances_{var}"].to(dev, torch.float32)
             if level == "frame":
                 truth = truth[:, : int(self.max_length)]
-                mask = valid_tgt
+                mask = tgt_mask
             elif level == "phone":
-                mask = valid_src
+                mask = src_mask
             else:
                 raise ValueError(f"Unknown variance level: {level}")
-            losses[var] = self._masked(result[f"variances_{var}"], truth, kind, mask)
-        m = valid_tgt.unsqueeze(-1).expand_as(result["mel"])
-        losses["mel"] = self._masked(result["mel"], target["mel"].to(dev, dt), self.mel_loss, m)
-        losses["duration"] = self._masked(result["duration_prediction"],
-                                          torch.log(target["duration"].to(dev) + 1).to(dt), self.duration_loss,
-                                          valid_src)
-        losses["total"] = sum(v * self.loss_alphas[k] for k, v in losses.items()
-                              if not any(f in k for f in frozen_components))
+            one(i, var, pred, kind, mask, tgt=truth[:, : pred.shape[1]].contiguous())
+        nv = len(self.variances)
+        one(nv, "mel", mel, self.mel_loss, tgt_mask, tgt=target["mel"].to(dev, torch.float32).contiguous())
+        one(nv + 1, "duration", result["duration_prediction"], self.duration_loss, src_mask,
+            tgt_i64=target["duration"].to(dev, torch.int64).contiguous())
+        losses = {name: buf[i] for i, name in enumerate(names)}
+        losses["total"] = _LossFn.apply(total, grads, *preds).reshape(()) if want_grad else total.reshape(())
+        self.last_buffer = buf  # one D2H copy of this gives every value (training_step logging)
         return losses

@@ -21,7 +21,7 @@ from .. import ops
 
 
 def _version_key(*tensors):
-    return tuple((t.data_ptr(), t._version, t.device) for t in tensors)
+    return (ops.WEIGHTS_EPOCH,) + tuple((t.data_ptr(), t._version, t.device) for t in tensors)
 
 
 class _PackCache:

@@ -1,0 +1,284 @@
+"""Train-step graph of the mel-generation path: forward that saves what the backward needs,
+and the hand-written backward, both as sequences of liblfs2.so kernels (SURVEY.md 8a
+"Backward notes").  The reference gets all of this from torch.autograd over its nn.Modules
+(litfass/fastspeech2/fastspeech2.py:786-797 -> forward :636-784); here the graph is fixed and
+known, so the backward is written out explicitly: no autograd tape of ATen kernels, every
+gradient accumulation is a kernel of this library, parameter gradients accumulate (+=) straight
+into ``p.grad`` (views of one flat buffer when ``FastSpeech2.flatten_parameters()`` was called,
+which is what the fused AdamW and the single NCCL all-reduce consume).
+
+Dropout: the parity protocol of the train step runs with every ``*_dropout = 0``; a
+model constructed with dropout > 0 raises in train mode instead of silently skipping it.
+Dense-conv (non-depthwise) stacks are inference-only.
+"""
+import numpy as np
+import torch
+
+from .. import ops
+
+
+def grad_of(p):
+    """The gradient buffer of parameter p (allocated zeroed on first use; kernels accumulate into it)."""
+    if p.grad is None:
+        p.grad = torch.zeros_like(p, memory_format=torch.contiguous_format)
+    return p.grad
+
+
+class Engine:
+    """GEMM dispatch of one train step: exact-fp32 CUDA-core kernels ("simt") or the tcgen05 kernels
+    on bf16 hi/lo split operands ("fp32": 3 passes, "bf16": 1 pass; fp32 accumulation either way)."""
+
+    def __init__(self, mode):
+        self.mode = mode
+        self.tc = mode != "simt"
+        self.npass = 3 if mode == "fp32" else 1
+        self._wt = {}
+
+    def _planes(self, x):
+        return ops.planes_of(x)
+
+    def linear(self, x, w, b, relu=False, tag=None):
+        """x (..., k) . w (n, k)^T + b"""
+        n, k = w.shape
+        if self.tc and k % 32 == 0 and n % 16 == 0:
+            return ops.gemm_tc(self._planes(x), self._planes(w), b, relu=relu, npass=self.npass, tag=tag)
+        return ops.linear(x, w, b, relu=relu, tag=tag)
+
+    def dgrad(self, dy, w, tag=None):
+        """dy (..., n) . w (n, k) -> (..., k): the layer-input gradient of y = x . w^T"""
+        return self.linear(dy, ops.transpose(w), None, tag=tag)
+
+    def wgrad_(self, dw, db, dy, x, tag=None):
+        """dw (n, k) += dy^T . x ; db (n) += column sums of dy"""
+        n, k = dw.shape
+        if self.tc and ops.wgrad_tc_ok(n, k):
+            ops.gemm_wgrad_tc_(dw, db, self._planes(dy), self._planes(x), npass=self.npass, tag=tag)
+            return
+        ops.gemm_tn_(dw, dy, x)
+        if db is not None:
+            ops.colsum_(db, dy)
+
+
+def _check_trainable(p_drop, what):
+    if p_drop > 0:
+        raise NotImplementedError(
+            f"{what}: dropout p={p_drop} in training mode is not implemented by the CUDA path; construct the model "
+            "with all *_dropout = 0 (the train-step parity protocol, SURVEY 8d)")
+
+
+def _mat(w):
+    """(n, k, 1) pointwise-conv weight or its gradient as an (n, k) matrix view"""
+    return w.view(w.shape[0], w.shape[1])
+
+
+def _dwmat(w):
+    """(d, 1, k) depthwise-conv weight or its gradient as a (d, k) matrix view"""
+    return w.view(w.shape[0], w.shape[2])
+
+
+# ------------------------------------------------------------------------------------------
+# FFTBlock (reference model.py:108-122)
+def fft_fwd(L, E, x, kpm):
+    if not L.depthwise:
+        raise NotImplementedError("training the dense-conv FFTBlock (only the depthwise variant has a backward)")
+    _check_trainable(L.p_drop, "ConformerEncoderLayer")
+    sa = L.self_attn
+    dwc, pw, gc, pw2 = L.conv1[0], L.conv1[1], L.conv2[0], L.conv2[1]
+    if gc.kernel_size[0] != 1:
+        raise NotImplementedError("grouped conv2.0 with kernel > 1")
+    s = {"x": x, "kpm": kpm}
+    s["qkv"] = E.linear(x, sa.in_proj_weight, sa.in_proj_bias, tag="qkv_gemm")
+    s["ctx"], s["lse"] = ops.attention_lse(s["qkv"], kpm, L.nhead)
+    a = E.linear(s["ctx"], sa.out_proj.weight, sa.out_proj.bias, tag="out_proj_gemm")
+    x1, s["z1"], s["st1"] = ops.add_layernorm_train(x, a, L.norm1.weight, L.norm1.bias, L.eps)
+    s["x1"] = x1
+    s["dw_wt"] = ops.transpose(_dwmat(dwc.weight))                        # (k, d)
+    s["u"] = ops.dwconv1d(x1, s["dw_wt"], dwc.bias)
+    s["v"] = E.linear(s["u"], _mat(pw.weight), pw.bias, relu=True, tag="ffn1_gemm")
+    s["w_eff"], b_eff = ops.fold_pw(_mat(pw2.weight), _mat(gc.weight), gc.bias, pw2.bias)
+    y = E.linear(s["v"], s["w_eff"], b_eff, tag="ffn2_gemm")
+    x2, s["z2"], s["st2"] = ops.add_layernorm_train(x1, y, L.norm2.weight, L.norm2.bias, L.eps)
+    return x2, s
+
+
+def fft_bwd(L, E, s, dx2):
+    sa = L.self_attn
+    dwc, pw, gc, pw2 = L.conv1[0], L.conv1[1], L.conv2[0], L.conv2[1]
+    dev = dx2.device
+    dz2 = ops.layernorm_bwd(dx2, s["z2"], s["st2"], L.norm2.weight, grad_of(L.norm2.weight), grad_of(L.norm2.bias))
+    # conv2 (folded): y = v . w_eff^T + b_eff
+    dv = E.dgrad(dz2, s["w_eff"], tag="ffn2_dgrad")
+    dw_eff = torch.zeros_like(s["w_eff"])
+    db_eff = torch.zeros(s["w_eff"].shape[0], device=dev, dtype=torch.float32)
+    E.wgrad_(dw_eff, db_eff, dz2, s["v"], tag="ffn2_wgrad")
+    ops.fold_pw_bwd_(dw_eff, db_eff, _mat(pw2.weight), _mat(gc.weight), gc.bias, _mat(grad_of(pw2.weight)),
+                     _mat(grad_of(gc.weight)), grad_of(gc.bias), grad_of(pw2.bias))
+    ops.relu_bwd_(dv, s["v"])
+    du = E.dgrad(dv, _mat(pw.weight), tag="ffn1_dgrad")
+    E.wgrad_(_mat(grad_of(pw.weight)), grad_of(pw.bias), dv, s["u"], tag="ffn1_wgrad")
+    dx1 = _dwconv_bwd(dwc, s["dw_wt"], du, s["x1"])
+    ops.add_(dx1, dz2)                                                   # residual around the FFN
+    dz1 = ops.layernorm_bwd(dx1, s["z1"], s["st1"], L.norm1.weight, grad_of(L.norm1.weight), grad_of(L.norm1.bias))
+    dctx = E.dgrad(dz1, sa.out_proj.weight, tag="out_proj_dgrad")
+    E.wgrad_(grad_of(sa.out_proj.weight), grad_of(sa.out_proj.bias), dz1, s["ctx"], tag="out_proj_wgrad")
+    dqkv = ops.attention_bwd(s["qkv"], s["ctx"], dctx, s["lse"], s["kpm"], L.nhead)
+    dx = E.dgrad(dqkv, sa.in_proj_weight, tag="qkv_dgrad")
+    E.wgrad_(grad_of(sa.in_proj_weight), grad_of(sa.in_proj_bias), dqkv, s["x"], tag="qkv_wgrad")
+    ops.add_(dx, dz1)                                                    # residual around the attention
+    return dx
+
+
+def _dwconv_bwd(conv, dw_wt, du, x_in):
+    """depthwise Conv1d backward: returns d(input); accumulates weight (d,1,k) and bias gradients"""
+    k, d = dw_wt.shape
+    zero_b = torch.zeros(d, device=du.device, dtype=torch.float32)
+    dx = ops.dwconv1d(du, dw_wt.flip(0).contiguous(), zero_b)            # correlation with the reversed taps
+    dwt = torch.zeros_like(dw_wt)
+    ops.dwconv1d_bwd_w_(dwt, grad_of(conv.bias), du, x_in)
+    ops.add_(_dwmat(grad_of(conv.weight)), ops.transpose(dwt))
+    return dx
+
+
+# ------------------------------------------------------------------------------------------
+# VariancePredictor (reference model.py:482-561)
+def vp_fwd(P, E, x, mask):
+    layers = []
+    z = x
+    for layer in P.layers:
+        if not layer.depthwise:
+            raise NotImplementedError("training dense-conv variance predictors")
+        _check_trainable(layer.layers[3].p, "VarianceConvolutionLayer")
+        conv, ln = layer.layers[0].module, layer.layers[2]
+        dw_wt = ops.transpose(_dwmat(conv[0].weight))
+        u = ops.dwconv1d(z, dw_wt, conv[0].bias)
+        h = E.linear(u, _mat(conv[1].weight), conv[1].bias, relu=True, tag="predictor_pw_gemm")
+        zo, _, st = ops.add_layernorm_train(h, None, ln.weight, ln.bias, ln.eps)
+        layers.append({"x": z, "u": u, "h": h, "st": st, "dw_wt": dw_wt})
+        z = zo
+    out = ops.rowdot_mask(z, P.linear.weight, P.linear.bias, mask)
+    return out, {"layers": layers, "z": z, "mask": mask}
+
+
+def vp_bwd(P, E, s, dout):
+    dz = ops.rowdot_mask_bwd(dout.contiguous(), s["z"], P.linear.weight, s["mask"], grad_of(P.linear.weight),
+                             grad_of(P.linear.bias))
+    for layer, sl in zip(reversed(list(P.layers)), reversed(s["layers"])):
+        conv, ln = layer.layers[0].module, layer.layers[2]
+        dh = ops.layernorm_bwd(dz, sl["h"], sl["st"], ln.weight, grad_of(ln.weight), grad_of(ln.bias))
+        ops.relu_bwd_(dh, sl["h"])
+        du = E.dgrad(dh, _mat(conv[1].weight), tag="predictor_dgrad")
+        E.wgrad_(_mat(grad_of(conv[1].weight)), grad_of(conv[1].bias), dh, sl["u"], tag="predictor_wgrad")
+        dz = _dwconv_bwd(conv[0], sl["dw_wt"], du, sl["x"])
+    return dz
+
+
+# ------------------------------------------------------------------------------------------
+# whole model (reference fastspeech2.py:636-784, teacher-forced branch)
+def forward_train(M, targets):
+    """-> (result dict with the reference's keys, saved state for backward_train)"""
+    hp = M.hparams
+    dev = M.device
+    E = Engine(M.compute_mode)
+    va = M.variance_adaptor
+    if any(level == "phone" for level in va.variance_levels):
+        raise NotImplementedError("phone-level variances")
+    _check_trainable(hp.encoder_dropout, "encoder")
+    _check_trainable(hp.decoder_dropout, "decoder")
+    phones = targets["phones"].to(dev, non_blocking=True).contiguous()
+    dvec = targets["speaker"].to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+    pe = M.positional_encoding.pe
+    S = {"E": E, "phones": phones, "dvec": dvec}
+
+    spk = ops.speaker_proj(dvec, M.speaker_embedding.projection.weight, M.speaker_embedding.projection.bias)
+    S["spk"] = spk
+    x, src_mask = ops.embed_pe_spk(phones, M.phone_embedding.weight, pe, spk)
+    S["enc"] = []
+    for L in M.encoder.layers:
+        x, s = fft_fwd(L, E, x, src_mask)
+        S["enc"].append(s)
+
+    dur_pred, S["dp"] = vp_fwd(va.duration_predictor, E, x, src_mask)
+    np.random.uniform(0, 1)  # the reference draws the teacher-forcing coin here (model.py:272); tf_ratio = 1
+    duration = targets["duration"].to(dev)
+    x, tgt_mask, S["cum"] = ops.length_regulate_train(x, duration, va.max_length)
+    S["vars"] = []
+    result = {}
+    for var in va.variances:
+        enc = va.encoders[var]
+        pred, s_vp = vp_fwd(enc.predictor, E, x, tgt_mask)
+        tgt = targets[f"variances_{var}"].to(dev, dtype=torch.float32)[:, : x.shape[1]].contiguous()
+        x, idx = ops.bucket_embed_add_oop(x, tgt, enc.std, enc.mean, enc.bins, enc.embedding.weight)
+        S["vars"].append((var, s_vp, idx))
+        result[f"variances_{var}"] = pred
+
+    x = ops.add_pe_spk_(x, pe, spk)
+    S["dec"] = []
+    for L in M.decoder.layers:
+        x, s = fft_fwd(L, E, x, tgt_mask)
+        S["dec"].append(s)
+    S["dec_out"] = x
+    result["mel"] = E.linear(x, M.linear.weight, M.linear.bias, tag="mel_linear")
+    result["duration_prediction"] = dur_pred
+    result["duration_rounded"] = duration
+    result["src_mask"] = src_mask
+    result["tgt_mask"] = tgt_mask
+    return result, S
+
+
+def backward_train(M, S, dmel, ddur, dvars):
+    """dmel (B,Tm,80), ddur (B,Tp), dvars {var: (B,Tm)} (any may be None) -> accumulates every parameter gradient"""
+    E = S["E"]
+    va = M.variance_adaptor
+    dev = M.device
+    bsz = S["phones"].shape[0]
+    d = M.hparams.encoder_hidden
+    dspk = torch.zeros(bsz, d, device=dev, dtype=torch.float32)
+
+    if dmel is not None:
+        dmel = dmel.contiguous()
+        dx = E.dgrad(dmel, M.linear.weight, tag="mel_dgrad")
+        E.wgrad_(grad_of(M.linear.weight), grad_of(M.linear.bias), dmel, S["dec_out"], tag="mel_wgrad")
+        for L, s in zip(reversed(list(M.decoder.layers)), reversed(S["dec"])):
+            dx = fft_bwd(L, E, s, dx)
+        ops.sum_over_time_(dspk, dx)                                     # "+ spk" at Tm (fastspeech2.py:707)
+    else:
+        dx = torch.zeros_like(S["dec_out"])
+    for var, s_vp, idx in reversed(S["vars"]):
+        enc = va.encoders[var]
+        ops.embedding_bwd_(grad_of(enc.embedding.weight), dx, idx)
+        g = dvars.get(var)
+        if g is not None:
+            ops.add_(dx, vp_bwd(enc.predictor, E, s_vp, g))
+    dx = ops.length_regulate_bwd(dx, S["cum"])
+    if ddur is not None:
+        ops.add_(dx, vp_bwd(va.duration_predictor, E, S["dp"], ddur))
+    for L, s in zip(reversed(list(M.encoder.layers)), reversed(S["enc"])):
+        dx = fft_bwd(L, E, s, dx)
+    ops.sum_over_time_(dspk, dx)                                         # "+ spk" at Tp (fastspeech2.py:658)
+    ops.embedding_bwd_(grad_of(M.phone_embedding.weight), dx, S["phones"], skip_idx=0)
+    # speaker term: spk = relu(W . dvec + b)   (model.py:137-143)
+    proj = M.speaker_embedding.projection
+    ops.relu_bwd_(dspk, S["spk"])
+    ops.gemm_tn_(grad_of(proj.weight), dspk, S["dvec"])
+    ops.colsum_(grad_of(proj.bias), dspk)
+
+
+class ForwardTrainFn(torch.autograd.Function):
+    """autograd boundary of the train step: tensors out, gradients in; everything between is kernels
+    of liblfs2.so.  ``anchor`` is a dummy scalar that requires grad so that autograd calls backward;
+    parameter gradients are accumulated into p.grad directly (torch's own semantics for leaves)."""
+
+    @staticmethod
+    def forward(ctx, anchor, model, targets, keys):
+        result, saved = forward_train(model, targets)
+        ctx.model, ctx.saved, ctx.keys = model, saved, keys
+        model._last_train_result = result
+        return tuple(result[k] for k in keys)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        g = dict(zip(ctx.keys, grads))
+        dvars = {k[len("variances_"):]: v for k, v in g.items() if k.startswith("variances_")}
+        backward_train(ctx.model, ctx.saved, g.get("mel"), g.get("duration_prediction"), dvars)
+        ctx.saved = None
+        return None, None, None, None

@@ -12,6 +12,10 @@ from . import _lib
 
 LN_EPS = 1e-5
 
+# bumped whenever a kernel rewrites parameters through raw pointers (fused optimizer, re-homed flat
+# buffers): tensor._version cannot see those writes, so weight-pack caches key on this as well
+WEIGHTS_EPOCH = 0
+
 # When bench.py sets PROFILE = {} every launch is bracketed by CUDA events on the launching
 # stream and tagged with its algorithmic flops / HBM bytes (SURVEY 8d definitions).
 PROFILE = None
@@ -367,3 +371,211 @@ def attention_tc(qkv, kpm, nhead, npass=3, want_f32=False, want_planes=True):
             _p(po.lo if po else None), _p(ctx), _p(ws), b, t, d, nhead, npass, _s(), flops=fl,
             nbytes=4.0 * qkv.hi.numel() + 4.0 * b * t * d * (int(want_f32) + int(want_planes)))
     return ctx, po
+
+
+# ---------------------------------------------------------------------------------------------
+# train-step config: forward variants that save what the backward needs, backward kernels, loss,
+# optimizer.  Parameter gradients accumulate (+=) into the tensors passed as d<param>.
+def add_layernorm_train(x, y, gamma, beta, eps=LN_EPS):
+    """-> (out, z = x (+ y), stats (m,2) = per-row (mean, rstd))"""
+    _chk(x, torch.float32, "layernorm input")
+    d = x.shape[-1]
+    m = x.numel() // d
+    out = torch.empty_like(x)
+    z = torch.empty_like(x) if y is not None else x
+    stats = torch.empty(m, 2, device=x.device, dtype=torch.float32)
+    _launch("lfs2_add_layernorm_train", _p(x), _p(y), _p(gamma), _p(beta), _p(out), _p(z if y is not None else None),
+            _p(stats), m, d, eps, _s(), tag="lfs2_add_layernorm", nbytes=4.0 * m * d * (4 if y is not None else 2))
+    return out, z, stats
+
+
+def layernorm_bwd(dy, z, stats, gamma, dgamma, dbeta, add=None):
+    _chk(dy, torch.float32, "layernorm_bwd dy"); _chk(z, torch.float32, "layernorm_bwd z")
+    d = z.shape[-1]
+    m = z.numel() // d
+    dz = torch.empty_like(z)
+    _launch("lfs2_layernorm_bwd", _p(dy), _p(z), _p(stats), _p(gamma), _p(add), _p(dz), _p(dgamma), _p(dbeta), m, d,
+            _s(), nbytes=4.0 * m * d * (3 + (add is not None)))
+    return dz
+
+
+def gemm_tn_(dw, dy, x, t=0, shift=0, col_offset=0):
+    """dw[:, col_offset:col_offset+k] += dy (m,n)^T . x (m,k)   (x rows shifted by `shift` inside utterances of t)"""
+    n, k = dy.shape[-1], x.shape[-1]
+    m = dy.numel() // n
+    _launch("lfs2_gemm_tn", _p(dy), _p(x), ctypes.c_void_p(dw.data_ptr() + 4 * col_offset), m, n, k, n, k,
+            dw.shape[-1], t, shift, _s(), tag=f"wgrad_n{n}_k{k}", flops=2.0 * m * n * k, nbytes=4.0 * m * (n + k))
+
+
+def colsum_(out, a):
+    n = a.shape[-1]
+    _launch("lfs2_colsum", _p(a), _p(out), a.numel() // n, n, _s(), nbytes=4.0 * a.numel())
+
+
+def relu_bwd_(dy, y):
+    _launch("lfs2_relu_bwd", _p(dy), _p(y), _p(dy), dy.numel(), _s(), nbytes=12.0 * dy.numel())
+    return dy
+
+
+def add_(dst, src):
+    _launch("lfs2_add_inplace", _p(dst), _p(src), dst.numel(), _s(), nbytes=12.0 * dst.numel())
+    return dst
+
+
+def transpose(w):
+    """(rows, cols) fp32 -> (cols, rows)"""
+    _chk(w, torch.float32, "transpose input", 2)
+    out = torch.empty(w.shape[1], w.shape[0], device=w.device, dtype=torch.float32)
+    _launch("lfs2_transpose", _p(w), _p(out), w.shape[0], w.shape[1], _s())
+    return out
+
+
+def dwconv1d_bwd_w_(dwt, dbias, dy, x):
+    b, t, d = x.shape
+    _launch("lfs2_dwconv1d_bwd_w", _p(dy), _p(x), _p(dwt), _p(dbias), b, t, d, dwt.shape[0], _s(),
+            flops=2.0 * b * t * d * dwt.shape[0], nbytes=8.0 * b * t * d)
+
+
+def attention_lse(qkv, kpm, nhead):
+    """-> (ctx (B,T,d), lse (B,nhead,T))"""
+    _chk(qkv, torch.float32, "qkv", 3)
+    b, t, d3 = qkv.shape
+    d = d3 // 3
+    ctx = torch.empty(b, t, d, device=qkv.device, dtype=torch.float32)
+    lse = torch.empty(b, nhead, t, device=qkv.device, dtype=torch.float32)
+    _launch("lfs2_attention_lse", _p(qkv), _p(kpm), _p(ctx), _p(lse), b, t, d, nhead, _s(), tag="lfs2_attention",
+            flops=4.0 * d * t * t * b, nbytes=4.0 * (qkv.numel() + ctx.numel()))
+    return ctx, lse
+
+
+def attention_bwd(qkv, ctx, dctx, lse, kpm, nhead):
+    b, t, d3 = qkv.shape
+    d = d3 // 3
+    dqkv = torch.empty_like(qkv)
+    ws = torch.empty(max(4, _lib.lib().lfs2_attention_bwd_workspace_bytes(b, t, nhead)), device=qkv.device,
+                     dtype=torch.uint8)
+    _launch("lfs2_attention_bwd", _p(qkv), _p(ctx), _p(dctx), _p(lse), _p(kpm), _p(dqkv), _p(ws), b, t, d, nhead, _s(),
+            flops=14.0 * d * t * t * b, nbytes=4.0 * (2 * qkv.numel() + 2 * ctx.numel()))
+    return dqkv
+
+
+def length_regulate_train(x, durations, max_length):
+    """length_regulate that also returns the prefix sums its backward needs"""
+    durations = durations.contiguous()
+    b, tp, d = x.shape
+    dev = x.device
+    cum = torch.empty(b, tp, device=dev, dtype=torch.int64)
+    lengths = torch.empty(b, device=dev, dtype=torch.int64)
+    mx = torch.empty(1, device=dev, dtype=torch.int64)
+    _launch("lfs2_length_regulate_scan", _p(durations), int(durations.dtype == torch.int64), _p(cum), _p(lengths),
+            _p(mx), b, tp, _s())
+    longest = int(mx.item())
+    l = min(longest, int(max_length)) if max_length is not None else longest
+    out = torch.empty(b, l, d, device=dev, dtype=x.dtype)
+    mask = torch.empty(b, l, device=dev, dtype=torch.bool)
+    _launch("lfs2_length_regulate_scatter", _p(x), _p(cum), _p(lengths), _p(out), _p(mask), b, tp, l,
+            d * x.element_size(), _s())
+    return out, mask, cum
+
+
+def length_regulate_bwd(dout, cum):
+    b, l, d = dout.shape
+    tp = cum.shape[1]
+    dx = torch.empty(b, tp, d, device=dout.device, dtype=torch.float32)
+    _launch("lfs2_length_regulate_bwd", _p(dout), _p(cum), _p(dx), b, tp, l, d, _s(),
+            nbytes=4.0 * d * (b * l + b * tp))
+    return dx
+
+
+def embedding_bwd_(demb, dx, idx, skip_idx=-1):
+    _chk(idx, torch.int64, "embedding indices")
+    d = dx.shape[-1]
+    _launch("lfs2_embedding_bwd", _p(dx), _p(idx), _p(demb), dx.numel() // d, d, demb.shape[0], skip_idx, _s(),
+            nbytes=4.0 * dx.numel())
+
+
+def bucket_embed_add_oop(x_in, val, std, mean, bins, emb, idx_forced=None):
+    """-> (x_in + emb[idx], idx)"""
+    _chk(x_in, torch.float32, "x", 3)
+    b, t, d = x_in.shape
+    out = torch.empty_like(x_in)
+    idx_out = torch.empty(b, t, device=x_in.device, dtype=torch.int64)
+    _launch("lfs2_bucket_embed_add_oop", _p(x_in), _p(out), _p(val), float(std), float(mean), _p(bins), emb.shape[0],
+            _p(emb), _p(idx_forced), _p(idx_out), _p(None), 0, b * t, d, _s(), tag="lfs2_bucket_embed_add",
+            nbytes=8.0 * b * t * d)
+    return out, idx_out
+
+
+def rowdot_mask_bwd(dout, z, w, mask, dw, db):
+    f = z.shape[-1]
+    dz = torch.empty_like(z)
+    _launch("lfs2_rowdot_mask_bwd", _p(dout), _p(z), _p(w), _p(mask), _p(dz), _p(dw), _p(db), z.numel() // f, f, _s(),
+            nbytes=8.0 * z.numel())
+    return dz
+
+
+def sum_over_time_(out, dx):
+    b, t, d = dx.shape
+    _launch("lfs2_sum_over_time", _p(dx), _p(out), b, t, d, _s(), nbytes=4.0 * dx.numel())
+
+
+def fold_pw(w21, w20, b20, b21):
+    """-> (w_eff (d_out, F), b_eff (d_out)) of conv2.1 . conv2.0 (grouped 1x1)"""
+    d_out, f = w21.shape[0], w21.shape[1]
+    g = w20.shape[1]
+    w_eff = torch.empty(d_out, f, device=w21.device, dtype=torch.float32)
+    b_eff = torch.empty(d_out, device=w21.device, dtype=torch.float32)
+    _launch("lfs2_fold_pw_fwd", _p(w21), _p(w20), _p(b20), _p(b21), _p(w_eff), _p(b_eff), d_out, f // g, g, _s())
+    return w_eff, b_eff
+
+
+def fold_pw_bwd_(dw_eff, db_eff, w21, w20, b20, dw21, dw20, db20, db21):
+    d_out, f = w21.shape[0], w21.shape[1]
+    g = w20.shape[1]
+    _launch("lfs2_fold_pw_bwd", _p(dw_eff), _p(db_eff), _p(w21), _p(w20), _p(b20), _p(dw21), _p(dw20), _p(db20),
+            _p(db21), d_out, f // g, g, _s())
+
+
+def masked_loss(pred, target, pad_mask, kind, weight, loss_out, total_out, want_grad=True, target_i64=None):
+    """loss_out / total_out: 1-element fp32 device tensors (views).  -> d(weight*loss)/d pred or None"""
+    _chk(pred, torch.float32, "loss prediction")
+    rows = pad_mask.numel()
+    inner = pred.numel() // rows
+    if target_i64 is not None:
+        _chk(target_i64, torch.int64, "integer loss target")
+        if target_i64.numel() != pred.numel():
+            raise ValueError("masked_loss: target shape mismatch")
+    else:
+        _chk(target, torch.float32, "loss target")
+        if target.numel() != pred.numel():
+            raise ValueError(f"masked_loss: target {tuple(target.shape)} vs prediction {tuple(pred.shape)}")
+    dpred = torch.empty_like(pred) if want_grad else None
+    ws = torch.empty(2, device=pred.device, dtype=torch.float32)
+    _launch("lfs2_masked_loss", _p(pred), _p(target), _p(target_i64), _p(pad_mask), rows, inner,
+            {"l1": 0, "mse": 1}[kind], float(weight), _p(loss_out), _p(total_out), _p(dpred), _p(ws), _s(),
+            nbytes=4.0 * pred.numel() * (3 if want_grad else 2))
+    return dpred
+
+
+def sumsq_(out, x):
+    _launch("lfs2_sumsq", _p(x), _p(out), x.numel(), _s(), nbytes=4.0 * x.numel())
+
+
+def adamw_step_(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, grad_scale=1.0, max_norm=0.0, gnorm_sq=None,
+                zero_grad=True):
+    for t_ in (p, g, m, v):
+        _chk(t_, torch.float32, "adamw flat buffer", 1)
+    _launch("lfs2_adamw_step", _p(p), _p(g), _p(m), _p(v), p.numel(), float(lr), float(beta1), float(beta2), float(eps),
+            float(weight_decay), int(step), float(grad_scale), float(max_norm), _p(gnorm_sq), int(zero_grad), _s(),
+            nbytes=28.0 * p.numel())
+
+
+def scale_by_(x, scalar):
+    """x *= scalar (a 0-dim / 1-element fp32 device tensor), no host sync"""
+    _launch("lfs2_scale_by", _p(x), _p(scalar), x.numel(), _s(), nbytes=8.0 * x.numel())
+    return x
+
+
+def wgrad_tc_ok(n, k):
+    """shapes the tcgen05 weight-gradient kernel covers (else the CUDA-core gemm_tn runs)"""
+    return False

@@ -297,3 +297,41 @@ def noam_scale(step, warmup):
     """NoamLR.get_lr scale factor (noam.py:20-25)."""
     s = max(1, step)
     return warmup ** 0.5 * min(s ** -0.5, s * warmup ** -1.5)
+
+
+def gradients(sd, hp, batch, dtype=torch.float32):
+    """Loss values and d(total)/d(parameter) of the teacher-forced train step (dropout off), by
+    torch.autograd over this restatement -- what the reference's training_step + backward()
+    computes (fastspeech2.py:786-797).  Returns ({loss name: float}, {param name: grad tensor})."""
+    leaves = {}
+    for k, v in sd.items():
+        if k.endswith(".bins") or k.endswith("positional_encoding.pe") or not v.is_floating_point():
+            leaves[k] = v
+        else:
+            leaves[k] = v.detach().to(dtype).clone().requires_grad_(True)
+    b = {k: (v.to(dtype) if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in batch.items()}
+    r = forward(leaves, hp, b, inference=False, dtype=dtype)
+    ls = loss(hp, r, b)
+    ls["total"].backward()
+    grads = {k: v.grad for k, v in leaves.items() if torch.is_tensor(v) and v.requires_grad and v.grad is not None}
+    if "phone_embedding.weight" in grads:
+        grads["phone_embedding.weight"][0] = 0  # nn.Embedding(padding_idx=0): no gradient for the PAD row
+    return {k: float(v.detach()) for k, v in ls.items()}, grads
+
+
+def adamw_noam_step(param, grad, exp_avg, exp_avg_sq, step, base_lr, warmup, betas=(0.9, 0.98), eps=1e-8,
+                    weight_decay=0.01):
+    """One AdamW update with the Noam-scheduled learning rate, as configure_optimizers sets it up
+    (fastspeech2.py:1166-1182; noam.py:20-25): the scheduler has been stepped `step - 1` times when
+    optimizer step number `step` (1-based) runs.  Plain tensor arithmetic, torch.optim.AdamW's order.
+    Returns (new_param, new_exp_avg, new_exp_avg_sq, lr)."""
+    lr = base_lr * noam_scale(step - 1, warmup)
+    b1, b2 = betas
+    p = param * (1 - lr * weight_decay)
+    m = exp_avg + (grad - exp_avg) * (1 - b1)
+    v = exp_avg_sq * b2 + (1 - b2) * grad * grad
+    bc1 = 1 - b1 ** step
+    bc2 = 1 - b2 ** step
+    denom = v.sqrt() / math.sqrt(bc2) + eps
+    p = p - (lr / bc1) * (m / denom)
+    return p, m, v, lr

@@ -67,6 +67,14 @@ def _run(model, batch, inference):
     return r32, r64
 
 
+def grad_probe(name, n):
+    """seeded +-1 probe vector for gradient fingerprints (rebuilt identically by the tests)"""
+    import zlib
+
+    r = np.random.default_rng([97, zlib.crc32(name.encode())])
+    return torch.from_numpy(r.integers(0, 2, size=n).astype(np.float64) * 2 - 1)
+
+
 def forward_golden(name, preset, seed, batch, inference, stats=None, train_targets=False):
     model, hp = _ref_model(configs.PRESETS[preset], seed, stats)
     if train_targets:
@@ -99,6 +107,21 @@ def forward_golden(name, preset, seed, batch, inference, stats=None, train_targe
         ls["total"].backward()
         g["loss_train_mode"] = {k: float(v) for k, v in ls.items()}
         g["grad_norms"] = {k: float(p.grad.norm()) for k, p in model.named_parameters() if p.grad is not None}
+        # gradient fingerprints: the dot product with a seeded probe vector pins direction as well as
+        # magnitude without committing megabytes; small tensors are stored whole
+        g["grad_dots"] = {k: float((p.grad.double().flatten() * grad_probe(k, p.numel())).sum())
+                          for k, p in model.named_parameters() if p.grad is not None}
+        g["grad_small"] = {k: p.grad.clone() for k, p in model.named_parameters()
+                           if p.grad is not None and p.numel() <= 512}
+        # one optimizer step exactly as the reference configures it (fastspeech2.py:1166-1182)
+        before = {k: p.detach().clone() for k, p in model.named_parameters()}
+        (opt,), (sch,) = model.configure_optimizers()
+        opt.step()
+        sch["scheduler"].step()
+        g["lr_first_step"] = float(opt.param_groups[0]["lr"])
+        g["step_delta_norms"] = {k: float((p.detach() - before[k]).norm()) for k, p in model.named_parameters()}
+        g["step_delta_dots"] = {k: float(((p.detach() - before[k]).double().flatten() * grad_probe(k, p.numel())).sum())
+                                for k, p in model.named_parameters()}
     torch.save(g, os.path.join(OUT, name + ".pt"))
     valid = int((~r32["tgt_mask"]).sum())
     print(f"{name}: mel {tuple(r32['mel'].shape)} valid_frames {valid}")
@@ -168,6 +191,8 @@ def main():
     forward_golden("tiny_dw_infer", "TINY_DW", 1, tiny, True, stats=STATS)
     forward_golden("tiny_dense_infer", "TINY_DENSE", 2, tiny, True, stats=STATS)
     forward_golden("tiny_dw_train", "TINY_DW", 3, tiny, False, stats=STATS, train_targets=True)
+    forward_golden("small_train", "SMALL_TRAIN", 4, synthetic.make_batch(3, 9, 40, seed=4), False, stats=STATS,
+                   train_targets=True)
     forward_golden("c1_infer", "C1", 1234, synthetic.make_batch(1, 128, 128, seed=1234), True)
     forward_golden("c2_small_infer", "C2", 2, synthetic.make_batch(4, 20, 96, seed=2), True)
 

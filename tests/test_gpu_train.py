@@ -1,0 +1,321 @@
+"""Train-step config on the GPU: every backward kernel against torch.autograd of the same op on the
+CPU, then the whole step (forward, FastSpeech2Loss, hand-written backward, fused AdamW + Noam)
+against (a) the reference's own backward()/optimizer step (tests/golden/small_train.pt fingerprints)
+and (b) the oracle's autograd gradients element by element.
+
+Tolerances (SURVEY 8c iv): loss values 1e-4 relative, gradients 1e-3 relative (dropout off)."""
+import os
+import zlib
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from lightningfastspeech2_b200 import configs, ops, synthetic
+from lightningfastspeech2_b200.fastspeech2.fastspeech2 import FastSpeech2, FusedAdamW
+from oracle import fs2_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(*shape, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randn(*shape, generator=g) * scale
+
+
+def close(a, b, rel=1e-4, name=""):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    err = (a - b).abs().max().item()
+    ref = max(b.abs().max().item(), 1e-12)
+    assert err <= rel * ref, f"{name}: max err {err:.3e} vs scale {ref:.3e}"
+
+
+# ---------------------------------------------------------------------------------- kernels
+@pytest.mark.parametrize("m,n,k", [(300, 64, 96), (1000, 128, 256), (77, 80, 128), (5000, 256, 1024)])
+def test_gemm_tn_and_colsum(m, n, k):
+    dy, x = rnd(m, n, seed=1), rnd(m, k, seed=2)
+    dw = torch.zeros(n, k, device=DEV)
+    db = torch.zeros(n, device=DEV)
+    ops.gemm_tn_(dw, dy.to(DEV), x.to(DEV))
+    ops.colsum_(db, dy.to(DEV))
+    close(dw, dy.double().t() @ x.double(), 1e-5, "gemm_tn")
+    close(db, dy.double().sum(0), 1e-5, "colsum")
+    ops.gemm_tn_(dw, dy.to(DEV), x.to(DEV))  # accumulates
+    close(dw, 2 * (dy.double().t() @ x.double()), 1e-5, "gemm_tn accumulate")
+
+
+def test_gemm_tn_conv_taps():
+    b, t, d, n, ks = 3, 37, 32, 64, 5
+    x, dy = rnd(b, t, d, seed=3), rnd(b, t, n, seed=4)
+    w = rnd(n, d, ks, seed=5).requires_grad_(True)
+    y = F.conv1d(x.transpose(1, 2), w, padding=ks // 2).transpose(1, 2)
+    y.backward(dy)
+    dwp = torch.zeros(n, ks * d, device=DEV)
+    for j in range(ks):
+        ops.gemm_tn_(dwp, dy.to(DEV), x.to(DEV), t=t, shift=j - ks // 2, col_offset=j * d)
+    close(dwp.view(n, ks, d).permute(0, 2, 1), w.grad, 1e-5, "conv wgrad")
+
+
+@pytest.mark.parametrize("d", [128, 256, 768])
+def test_layernorm_train_and_bwd(d):
+    m = 517
+    x, y, dy = rnd(m, d, seed=1), rnd(m, d, seed=2), rnd(m, d, seed=3)
+    gam = (1 + 0.1 * rnd(d, seed=4)).requires_grad_(True)
+    bet = (0.1 * rnd(d, seed=5)).requires_grad_(True)
+    z = (x + y).requires_grad_(True)
+    out = F.layer_norm(z, (d,), gam, bet, 1e-5)
+    out.backward(dy)
+    o, zs, st = ops.add_layernorm_train(x.to(DEV), y.to(DEV), gam.detach().to(DEV), bet.detach().to(DEV))
+    close(o, out, 1e-5, "ln fwd")
+    close(zs, z, 1e-6, "ln z")
+    dg, dbt = torch.zeros(d, device=DEV), torch.zeros(d, device=DEV)
+    add = rnd(m, d, seed=6)
+    dz = ops.layernorm_bwd(dy.to(DEV), zs, st, gam.detach().to(DEV), dg, dbt, add=add.to(DEV))
+    close(dz, z.grad + add, 1e-4, "ln dz")
+    close(dg, gam.grad, 1e-4, "ln dgamma")
+    close(dbt, bet.grad, 1e-4, "ln dbeta")
+
+
+@pytest.mark.parametrize("ks", [3, 9, 17, 25])
+def test_dwconv_backward(ks):
+    b, t, d = 3, 150, 128
+    x = rnd(b, t, d, seed=1).requires_grad_(True)
+    w = rnd(d, 1, ks, seed=2).requires_grad_(True)
+    bias = rnd(d, seed=3).requires_grad_(True)
+    dy = rnd(b, t, d, seed=4)
+    y = F.conv1d(x.transpose(1, 2), w, bias, padding=ks // 2, groups=d).transpose(1, 2)
+    y.backward(dy)
+    wt = w.detach()[:, 0, :].t().contiguous().to(DEV)
+    dx = ops.dwconv1d(dy.to(DEV), wt.flip(0).contiguous(), torch.zeros(d, device=DEV))
+    close(dx, x.grad, 1e-5, "dwconv dx")
+    dwt, dbias = torch.zeros(ks, d, device=DEV), torch.zeros(d, device=DEV)
+    ops.dwconv1d_bwd_w_(dwt, dbias, dy.to(DEV), x.detach().to(DEV))
+    close(dwt.t(), w.grad[:, 0, :], 1e-4, "dwconv dw")
+    close(dbias, bias.grad, 1e-4, "dwconv db")
+
+
+@pytest.mark.parametrize("d,nhead,t", [(128, 2, 70), (256, 2, 200), (768, 2, 90)])
+def test_attention_backward(d, nhead, t):
+    b = 3
+    qkv = rnd(b, t, 3 * d, seed=1, scale=0.7).requires_grad_(True)
+    dctx = rnd(b, t, d, seed=2)
+    kpm = torch.zeros(b, t, dtype=torch.bool)
+    kpm[1, t - 17:] = True
+    kpm[2, t // 2:] = True
+    dh = d // nhead
+    q, k, v = qkv.split(d, dim=-1)
+    hd = lambda z: z.reshape(b, t, nhead, dh).permute(0, 2, 1, 3)
+    s = (hd(q) * dh ** -0.5) @ hd(k).transpose(-1, -2)
+    s = s.masked_fill(kpm[:, None, None, :], float("-inf"))
+    ctx = (torch.softmax(s, -1) @ hd(v)).permute(0, 2, 1, 3).reshape(b, t, d)
+    ctx.backward(dctx)
+    c, lse = ops.attention_lse(qkv.detach().to(DEV), kpm.to(DEV), nhead)
+    close(c, ctx, 1e-5, "attention fwd")
+    close(lse, torch.logsumexp(s, -1), 1e-5, "lse")
+    dqkv = ops.attention_bwd(qkv.detach().to(DEV), c, dctx.to(DEV), lse, kpm.to(DEV), nhead)
+    close(dqkv, qkv.grad, 2e-4, "attention bwd")
+
+
+def test_length_regulator_backward():
+    b, tp, d = 4, 23, 64
+    x = rnd(b, tp, d, seed=1).requires_grad_(True)
+    g = torch.Generator().manual_seed(2)
+    dur = torch.randint(0, 6, (b, tp), generator=g)
+    dur[0, 3] = 40
+    out, mask = O.length_regulator(x, dur, 60.5)
+    dout = rnd(*out.shape, seed=3)
+    out.backward(dout)
+    o, mk, cum = ops.length_regulate_train(x.detach().to(DEV), dur.to(DEV), 60.5)
+    assert torch.equal(o.cpu(), out.detach()) and torch.equal(mk.cpu(), mask)
+    dx = ops.length_regulate_bwd(dout.to(DEV), cum)
+    close(dx, x.grad, 1e-5, "lr bwd")
+
+
+def test_embedding_rowdot_sum_fold():
+    m, d, nb = 700, 128, 16
+    dx = rnd(m, d, seed=1)
+    g = torch.Generator().manual_seed(2)
+    idx = torch.randint(0, nb, (m,), generator=g)
+    idx[300:] = 5  # a long run of equal indices, like PAD frames
+    emb = torch.zeros(nb, d, requires_grad=True)
+    (F.embedding(idx, emb, padding_idx=0) * dx).sum().backward()
+    demb = torch.zeros(nb, d, device=DEV)
+    ops.embedding_bwd_(demb, dx.to(DEV), idx.to(DEV), skip_idx=0)
+    close(demb, emb.grad, 1e-4, "embedding bwd")
+
+    z = rnd(m, d, seed=3).requires_grad_(True)
+    w = rnd(1, d, seed=4).requires_grad_(True)
+    bb = rnd(1, seed=5).requires_grad_(True)
+    mask = torch.zeros(m, dtype=torch.bool)
+    mask[500:] = True
+    dout = rnd(m, seed=6)
+    out = F.linear(z, w, bb).squeeze(-1).masked_fill(mask, 0)
+    out.backward(dout)
+    dw, db = torch.zeros(1, d, device=DEV), torch.zeros(1, device=DEV)
+    dz = ops.rowdot_mask_bwd(dout.to(DEV), z.detach().to(DEV).view(1, m, d), w.detach().to(DEV), mask.to(DEV), dw, db)
+    close(dz.view(m, d), z.grad, 1e-5, "rowdot dz")
+    close(dw, w.grad, 1e-4, "rowdot dw")
+    close(db, bb.grad, 1e-4, "rowdot db")
+
+    x3 = rnd(3, 50, d, seed=7)
+    acc = torch.zeros(3, d, device=DEV)
+    ops.sum_over_time_(acc, x3.to(DEV))
+    close(acc, x3.sum(1), 1e-5, "sum_over_time")
+
+    # conv2.0 (grouped 1x1) . conv2.1 fold and its chain rule
+    dd, gsz = 32, 4
+    f = dd * gsz
+    w21 = rnd(dd, f, seed=8).requires_grad_(True)
+    w20 = rnd(f, gsz, seed=9).requires_grad_(True)
+    b20 = rnd(f, seed=10).requires_grad_(True)
+    b21 = rnd(dd, seed=11).requires_grad_(True)
+    v = rnd(40, f, seed=12)
+    wv = F.conv1d(v.t()[None], w20[:, :, None], b20, groups=dd)
+    y = F.conv1d(wv, w21[:, :, None], b21)[0].t()
+    dyy = rnd(40, dd, seed=13)
+    y.backward(dyy)
+    dv = lambda t_: t_.detach().to(DEV)
+    w_eff, b_eff = ops.fold_pw(dv(w21), dv(w20), dv(b20), dv(b21))
+    close(v.to(DEV) @ w_eff.t() + b_eff, y, 1e-5, "fold fwd")
+    dw_eff = (dyy.t() @ v).to(DEV).contiguous()
+    db_eff = dyy.sum(0).to(DEV)
+    g21, g20, gb20, gb21 = (torch.zeros_like(dv(t_)) for t_ in (w21, w20, b20, b21))
+    ops.fold_pw_bwd_(dw_eff, db_eff, dv(w21), dv(w20), dv(b20), g21, g20, gb20, gb21)
+    close(g21, w21.grad, 1e-4, "fold dw21")
+    close(g20, w20.grad, 1e-4, "fold dw20")
+    close(gb20, b20.grad, 1e-4, "fold db20")
+    close(gb21, b21.grad, 1e-4, "fold db21")
+
+
+@pytest.mark.parametrize("kind", ["l1", "mse"])
+def test_masked_loss(kind):
+    b, t, inner = 4, 33, 80
+    pred = rnd(b, t, inner, seed=1).requires_grad_(True)
+    tgt = rnd(b, t, inner, seed=2)
+    mask = torch.zeros(b, t, dtype=torch.bool)
+    mask[1, 20:] = True
+    mask[3, 5:] = True
+    sel = (~mask)[:, :, None].expand_as(pred)
+    ref = F.l1_loss(pred[sel], tgt[sel]) if kind == "l1" else F.mse_loss(pred[sel], tgt[sel])
+    (0.7 * ref).backward()
+    buf = torch.zeros(2, device=DEV)
+    g = ops.masked_loss(pred.detach().to(DEV), tgt.to(DEV), mask.to(DEV), kind, 0.7, buf[0:1], buf[1:2])
+    assert abs(buf[0].item() - ref.item()) <= 1e-5 * abs(ref.item())
+    assert abs(buf[1].item() - 0.7 * ref.item()) <= 1e-5 * abs(ref.item())
+    close(g, pred.grad, 1e-5, "loss grad")
+    dur = torch.randint(0, 9, (b, t))
+    p2 = rnd(b, t, seed=3)
+    ref2 = F.mse_loss(p2[~mask], torch.log(dur + 1)[~mask])
+    ops.masked_loss(p2.to(DEV), None, mask.to(DEV), "mse", 1.0, buf[0:1], None, target_i64=dur.to(DEV))
+    assert abs(buf[0].item() - ref2.item()) <= 1e-5 * abs(ref2.item())
+
+
+def test_fused_adamw_matches_oracle_update():
+    n = 4096 + 64
+    p0, g0 = rnd(n, seed=1), rnd(n, seed=2, scale=0.01)
+    p, g = p0.clone().to(DEV), g0.clone().to(DEV)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    rp, rm, rv = p0.double(), torch.zeros(n, dtype=torch.float64), torch.zeros(n, dtype=torch.float64)
+    for step in (1, 2, 3):
+        lr = 1e-4 * O.noam_scale(step - 1, 4000)
+        ops.adamw_step_(p, g, m, v, lr, 0.9, 0.98, 1e-8, 0.01, step, zero_grad=False)
+        rp, rm, rv, lr_o = O.adamw_noam_step(rp, g0.double(), rm, rv, step, 1e-4, 4000)
+        assert abs(lr - lr_o) < 1e-18
+    close(p - p0.to(DEV), rp - p0.double(), 1e-3, "adamw delta")
+    # clipping + world-size averaging + zeroing
+    gn = torch.zeros(1, device=DEV)
+    ops.sumsq_(gn, g)
+    assert abs(gn.item() - float((g0.double() ** 2).sum())) < 1e-4 * gn.item()
+    ops.adamw_step_(p, g, m, v, 1e-4, 0.9, 0.98, 1e-8, 0.01, 4, grad_scale=0.5, max_norm=0.1, gnorm_sq=gn)
+    assert float(g.abs().max()) == 0.0
+
+
+# ---------------------------------------------------------------------------- whole train step
+def _probe(name, n):
+    r = np.random.default_rng([97, zlib.crc32(name.encode())])
+    return torch.from_numpy(r.integers(0, 2, size=n).astype(np.float64) * 2 - 1)
+
+
+def _build(g, mode):
+    kw = configs.PRESETS[g["preset"]]
+    hp = configs.resolve(kw)
+    st = {v: dict(g["stats"]) for v in hp["variances"]}
+    model = FastSpeech2(stats=st, phone2id={f"p{i}": i for i in range(80)}, num_workers=0, **kw)
+    shapes = {k: v for k, v in g["shapes"].items() if not k.startswith("fastdiff_linear")}
+    sd = synthetic.fill_state_dict(shapes, seed=g["seed"], stats=g["stats"])
+    model.load_state_dict(sd, strict=True)
+    hp["stats"] = st
+    model = model.to(DEV).train().set_compute_mode(mode)
+    return model, sd, hp
+
+
+@pytest.mark.parametrize("mode,rel", [("simt", 1e-3), ("fp32", 2e-3)])
+def test_train_step_against_reference_and_oracle(golden_dir, mode, rel):
+    g = torch.load(os.path.join(golden_dir, "small_train.pt"), weights_only=False)
+    model, sd, hp = _build(g, mode)
+    batch = g["batch"]
+    model.log_losses = False
+    total = model.training_step(batch, 0)
+    vals = dict(zip(list(hp["variances"]) + ["mel", "duration", "total"], model.loss.last_buffer.tolist()))
+    for k, v in g["loss_train_mode"].items():
+        assert abs(vals[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, vals[k], v)
+    total.backward()
+    torch.cuda.synchronize()
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    # (a) the reference's own backward(): norms + probe dot products + small tensors
+    scale = max(g["grad_norms"].values())
+    for k, ref in g["grad_norms"].items():
+        if k.startswith("fastdiff_linear"):
+            continue
+        gk = grads[k].cpu()
+        assert abs(float(gk.norm()) - ref) <= rel * max(ref, 1e-3 * scale), (k, float(gk.norm()), ref)
+        dot = float((gk.double().flatten() * _probe(k, gk.numel())).sum())
+        assert abs(dot - g["grad_dots"][k]) <= rel * max(ref * gk.numel() ** 0.5, 1e-3 * scale), k
+    # (b) the oracle's autograd gradients, element by element
+    _, ograds = O.gradients(sd, hp, batch)
+    worst = 0.0
+    for k, og in ograds.items():
+        err = (grads[k].cpu() - og).abs().max().item()
+        ref = max(og.abs().max().item(), 1e-3 * scale)
+        worst = max(worst, err / ref)
+        assert err <= rel * ref, (k, err, ref)
+    print(f"train step [{mode}]: worst relative gradient error {worst:.2e}")
+
+
+def test_train_step_optimizer_and_flat_buffers(golden_dir):
+    g = torch.load(os.path.join(golden_dir, "small_train.pt"), weights_only=False)
+    model, sd, hp = _build(g, "simt")
+    model.log_losses = False
+    (opt,), (sch,) = model.configure_optimizers()
+    assert isinstance(opt, FusedAdamW)
+    flat_p, flat_g = model.flatten_parameters()
+    before = {k: p.detach().clone() for k, p in model.named_parameters()}
+    loss = model.training_step(g["batch"], 0)
+    loss.backward()
+    assert float(flat_g.abs().sum()) > 0  # gradients landed in the flat buffer
+    opt.step()
+    sch["scheduler"].step()
+    assert float(flat_g.abs().max()) == 0.0  # and were zeroed by the fused step
+    assert abs(opt.param_groups[0]["lr"] - g["lr_first_step"]) < 1e-15
+    for k, p in model.named_parameters():
+        if k not in g["step_delta_norms"] or not p.requires_grad:
+            continue
+        delta = (p.detach() - before[k]).cpu()
+        ref = g["step_delta_norms"][k]
+        assert abs(float(delta.norm()) - ref) <= 5e-3 * max(ref, 1e-12), (k, float(delta.norm()), ref)
+    # inference after the step sees the updated weights (pack caches invalidated)
+    model.eval()
+    with torch.no_grad():
+        r = model({k: v for k, v in g["batch"].items()}, inference=True)
+    assert torch.isfinite(r["mel"]).all()
+
+
+def test_train_mode_rejects_dropout():
+    kw = dict(configs.PRESETS["SMALL_TRAIN"], encoder_dropout=0.1)
+    st = {v: {"min": -3.0, "max": 3.0, "mean": 0.0, "std": 1.0} for v in kw["variances"]}
+    model = FastSpeech2(stats=st, phone2id={f"p{i}": i for i in range(80)}, num_workers=0, **kw).to(DEV).train()
+    batch = synthetic.add_train_targets(synthetic.make_batch(2, 8, 16, seed=1), kw["variances"], seed=1)
+    with pytest.raises(NotImplementedError):
+        model(batch)

@@ -103,3 +103,46 @@ def test_noam_matches_formula():
     assert abs(O.noam_scale(0, 4000) - O.noam_scale(1, 4000)) == 0
     assert abs(O.noam_scale(4000, 4000) - 1.0) < 1e-12
     assert O.noam_scale(16000, 4000) == pytest.approx(0.5)
+
+
+def _probe(name, n):
+    import zlib
+
+    import numpy as np
+
+    r = np.random.default_rng([97, zlib.crc32(name.encode())])
+    return torch.from_numpy(r.integers(0, 2, size=n).astype(np.float64) * 2 - 1)
+
+
+@pytest.mark.parametrize("name", ["tiny_dw_train", "small_train"])
+def test_train_step_gradients_and_adamw(golden_dir, name):
+    """Oracle autograd vs the reference's own backward() + AdamW/Noam step: loss values, per-parameter
+    gradient norms, probe-vector dot products (direction), small tensors whole, and the first
+    optimizer step's parameter deltas."""
+    g = _load(golden_dir, name)
+    hp, sd = _setup(g)
+    losses, grads = O.gradients(sd, hp, g["batch"])
+    for k, v in g["loss_train_mode"].items():
+        assert abs(losses[k] - v) <= 1e-5 * max(1.0, abs(v)), k
+    assert set(g["grad_norms"]) - {k for k in g["grad_norms"] if k.startswith("fastdiff_linear")} <= set(grads)
+    scale = max(g["grad_norms"].values())
+    for k, ref in g["grad_norms"].items():
+        if k.startswith("fastdiff_linear"):
+            continue
+        gk = grads[k]
+        assert abs(float(gk.norm()) - ref) <= 2e-4 * max(ref, 1e-3 * scale), k
+        dot = float((gk.double().flatten() * _probe(k, gk.numel())).sum())
+        assert abs(dot - g["grad_dots"][k]) <= 2e-4 * max(ref * gk.numel() ** 0.5, 1e-3 * scale), k
+    for k, ref in g["grad_small"].items():
+        if k in grads:
+            assert (grads[k] - ref).abs().max() <= 1e-4 * max(float(ref.abs().max()), 1e-3 * scale), k
+    # first AdamW step with the Noam lr (scheduler not yet stepped)
+    for k, ref in g["step_delta_norms"].items():
+        if k not in grads:
+            continue
+        p0 = sd[k]
+        p1, _, _, lr = O.adamw_noam_step(p0, grads[k], torch.zeros_like(p0), torch.zeros_like(p0), 1, hp["lr"],
+                                         hp["warmup_steps"])
+        delta = p1 - p0
+        assert abs(float(delta.norm()) - ref) <= 2e-3 * max(ref, 1e-12), k
+    assert abs(O.noam_scale(1, hp["warmup_steps"]) * hp["lr"] - g["lr_first_step"]) < 1e-15
