@@ -144,6 +144,137 @@ def cpu_port_throughput(sd, hp, batch, nutt, repeats=1):
     return frames / best, best, frames
 
 
+# ---------------------------------------------------------------------------------------------
+# train step (BASELINE.json configs[3], "C4"): forward + FastSpeech2Loss + backward + gradient
+# all-reduce + AdamW/Noam on the 76 M model, global batch 64 split across the ranks (strong scaling)
+TRAIN_PRESET = "C4"
+TRAIN_BATCH, TRAIN_MIN_LEN, TRAIN_MAX_LEN = 64, 32, 256
+TRAIN_WORKLOAD = (f"C4 train step (forward + loss + backward + grad all-reduce + AdamW/Noam), 76M-parameter "
+                  f"depthwise FastSpeech2 (d=768, 4 enc + 5 dec FFTBlocks, 3 variances), global batch={TRAIN_BATCH} "
+                  f"utterances, phoneme len U[{TRAIN_MIN_LEN},{TRAIN_MAX_LEN}], durations U[1,9], dropout 0 in both arms")
+
+
+def train_batch(hp, rank, world):
+    """The rank's shard of the global train batch: utterances sorted by length and dealt in snake
+    order, each rank padded to its own maximum length."""
+    full = synthetic.make_batch(TRAIN_BATCH, TRAIN_MIN_LEN, TRAIN_MAX_LEN, seed=4)
+    order = torch.argsort(full["phones_lengths"], descending=True).tolist()
+    mine = [u for i, u in enumerate(order) if (i % (2 * world) == rank or i % (2 * world) == 2 * world - 1 - rank)]
+    sub = {k: v[mine].contiguous() for k, v in full.items()}
+    keep = int(sub["phones_lengths"].max())
+    sub["phones"] = sub["phones"][:, :keep].contiguous()
+    return synthetic.add_train_targets(sub, hp["variances"], seed=4 + rank)
+
+
+def build_train_model(device, preset=TRAIN_PRESET):
+    from lightningfastspeech2_b200.fastspeech2.fastspeech2 import FastSpeech2
+
+    kw = configs.PRESETS[preset]
+    hp = configs.resolve(kw)
+    stats = {v: {"min": -3.0, "max": 3.0, "mean": 0.0, "std": 1.0} for v in hp["variances"]}
+    model = FastSpeech2(stats=stats, phone2id={f"p{i}": i for i in range(80)}, num_workers=0, **kw)
+    sd = synthetic.fill_state_dict(model.state_dict(), seed=0)
+    model.load_state_dict(sd)
+    hp["stats"] = stats
+    if device is not None:
+        model = model.to(device).train()
+    return model, sd, hp
+
+
+def cpu_port_train_step(sd, hp, batch, nutt):
+    """Oracle port of one train step (forward + loss + autograd backward + AdamW/Noam update of every
+    parameter) on the first `nutt` utterances, all host threads.  Returns seconds."""
+    from oracle import fs2_oracle as O
+
+    torch.set_num_threads(os.cpu_count())
+    sub = {k: (v[:nutt].contiguous() if torch.is_tensor(v) else v) for k, v in batch.items()}
+    keep = int((sub["phones"] != 0).sum(1).max())
+    tm = int(sub["duration"][:, :keep].sum(1).max())
+    sub["phones"], sub["duration"] = sub["phones"][:, :keep].contiguous(), sub["duration"][:, :keep].contiguous()
+    sub["mel"] = sub["mel"][:, :tm].contiguous()
+    for v in hp["variances"]:
+        sub[f"variances_{v}"] = sub[f"variances_{v}"][:, :tm].contiguous()
+    t0 = time.perf_counter()
+    _, grads = O.gradients(sd, hp, sub)
+    for k, g in grads.items():
+        O.adamw_noam_step(sd[k], g, torch.zeros_like(g), torch.zeros_like(g), 1, hp["lr"], hp["warmup_steps"])
+    return time.perf_counter() - t0, int(sub["duration"].sum())
+
+
+def run_train_steps(model, batch, opt, sch, steps, world):
+    for _ in range(steps):
+        loss = model.training_step(batch, 0)
+        loss.backward()
+        opt.grad_scale = 1.0 / model.allreduce_gradients()
+        opt.step()
+        sch.step()
+
+
+def measure_train(args, dev, rank, world, barrier):
+    """-> dict for the "train" key of the JSON line (rank 0) / None"""
+    import torch.distributed as dist
+
+    from lightningfastspeech2_b200 import _lib, ops
+
+    model, sd, hp = build_train_model(dev)
+    model.set_compute_mode(args.train_mode)
+    model.log_losses = False
+    batch = train_batch(hp, rank, world)
+    dbatch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    (opt,), (schd,) = model.configure_optimizers()
+    sch = schd["scheduler"]
+    run_train_steps(model, dbatch, opt, sch, 3, world)
+    barrier()
+    calls0 = _lib.CALLS
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run_train_steps(model, dbatch, opt, sch, args.train_steps, world)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / args.train_steps
+    launches = (_lib.CALLS - calls0) // args.train_steps
+    ops.PROFILE = {}
+    run_train_steps(model, dbatch, opt, sch, 1, world)
+    prof = ops.collect_profile()
+    ops.PROFILE = None
+    loss_vals = model.loss.last_buffer.tolist()
+    frames = int(batch["duration"].sum())
+    nparams = sum(p.numel() for p in model.parameters() if p.requires_grad)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
+        c = torch.tensor([frames], device=dev, dtype=torch.int64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        frames = int(c[0])
+    del model, opt
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    total_ms = sum(v["ms"] for v in prof.values()) or 1.0
+    out = {"metric": "ms/step (train)", "ms_per_step": ms, "steps": args.train_steps, "warmup": 3,
+           "scaling": "strong", "n_gpus": world, "dtype": {"simt": "f32", "fp32": "f32", "bf16": "bf16"}[args.train_mode],
+           "compute_mode": args.train_mode, "valid_frames_per_step": frames, "frames_per_s": frames / (ms * 1e-3),
+           "parameters": nparams, "gpu_launches_per_step": launches,
+           "allreduce_bytes_per_step": 0 if world == 1 else 4 * model_flat_numel(nparams),
+           "final_losses": {"total": loss_vals[-1]},
+           "config": {"workload": TRAIN_WORKLOAD, "preset": TRAIN_PRESET, "utterances_rank0": int(batch["phones"].shape[0]),
+                      "padded_phones_rank0": int(batch["phones"].shape[1]), "mel_frames_rank0": int(batch["mel"].shape[1]),
+                      "parallelism": f"data-parallel x{world}, one NCCL all-reduce of the flat fp32 gradient buffer"},
+           "kernel_shares": {k: round(v["ms"] / total_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]}}
+    if world == 1 and args.train_cpu_utts > 0:
+        secs, cfr = cpu_port_train_step(sd, hp, batch, args.train_cpu_utts)
+        out["cpu_baseline"] = {"value": secs * 1e3 * frames / max(cfr, 1), "unit": "ms/step (extrapolated by frames)",
+                               "cores": os.cpu_count(), "kind": "port",
+                               "sample": f"first {args.train_cpu_utts} utterances of the batch ({cfr} frames), one "
+                                         f"oracle train step of {secs:.1f} s, scaled to {frames} frames"}
+    return out
+
+
+def model_flat_numel(nparams):
+    return nparams
+
+
 def run_reference(args):
     rank, world, local = dist_env()
     if rank != 0:
@@ -273,6 +404,12 @@ def run_lfs2(args):
     else:
         frames_all, e2e_all = frames, e2e_frames
 
+    train = None
+    if args.train_steps > 0:
+        del model
+        torch.cuda.empty_cache()
+        train = measure_train(args, dev, rank, world, barrier)
+
     if rank == 0:
         pk = peaks()
         total_ms = sum(v["ms"] for v in prof.values())
@@ -313,6 +450,8 @@ def run_lfs2(args):
             "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                              "sample": sample},
         }
+        if train is not None:
+            line["train"] = train
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -325,6 +464,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lfs2", choices=["lfs2", "reference"])
     ap.add_argument("--ref-utts", type=int, default=4, help="utterances in the bounded CPU sample")
+    ap.add_argument("--train-steps", type=int, default=5, help="timed C4 train steps reported under 'train' (0 = skip)")
+    ap.add_argument("--train-mode", default="fp32", choices=["simt", "fp32", "bf16"])
+    ap.add_argument("--train-cpu-utts", type=int, default=2, help="utterances in the CPU train-step sample (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

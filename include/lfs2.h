@@ -172,6 +172,41 @@ LFS2_API int lfs2_merge_planes(const void* hi, const void* lo, float* out, long 
 /* hi = bf16(x), lo = bf16(x - hi) for n fp32 values (n % 4 == 0) */
 LFS2_API int lfs2_split_bf16(const float* x, void* hi, void* lo, long long n, void* stream);
 
+/* ---- general batched tcgen05 GEMM with per-operand majorness (weight gradients, attention products) ----
+ * An operand is a window of a dense row-major bf16 tensor (d2, d1, d0) (d0 innermost, d0 % 8 == 0), given
+ * as hi/lo planes.  mn_major = 0 ("K-major"): tensor rows = the operand's m (n) index, columns = the
+ * contraction index k.  mn_major = 1 ("MN-major"): tensor ROWS = the contraction index, columns = the
+ * m (n) index, i.e. the operand is used transposed without a transposed copy.  For batch element
+ * z = b * nhead + h the window starts at column col0 + h * hstride of tensor slice (per_z ? z : b). */
+typedef struct lfs2_operand {
+  int mn_major;
+  int d0, d1, d2;
+  int col0, hstride, per_z;
+} lfs2_operand;
+/*   C[z] (m x n, fp32, row pitch ldc, at c + b*c_bstride + h*c_hstride)  (+)=  A[z] (m x k) . B[z] (n x k)^T
+ * npass = 3: hi.hi + lo.hi + hi.lo; npass = 1: hi.hi.  accumulate != 0 adds into C with fp32 atomics and
+ * lets the kernel split the contraction across CTAs (C must be initialised); 0 overwrites C.
+ * replaces (as gradients) the Linear / Conv1d(.,.,1) weight gradients torch.autograd computes for
+ * model.py:82,92,111-114,552 and fastspeech2.py:723, and the bmm's of torch MHA (model.py:111-114). */
+LFS2_API int lfs2_gemm_tc2(const void* a_hi, const void* a_lo, const lfs2_operand* a, const void* b_hi,
+                           const void* b_lo, const lfs2_operand* b, float* c, int ldc, long long c_bstride,
+                           long long c_hstride, int m, int n, int k, int nbatch, int nhead, int npass,
+                           int accumulate, void* stream);
+
+/* GEMM-decomposed attention, row-wise pieces (see csrc/attention_mat.cu).  Z = batch*nhead, tp = t rounded
+ * up to a multiple of 8.
+ * softmax: s (Z,t,tp) raw Q.K^T logits -> P = softmax(s*scale with PAD keys masked) as bf16 hi/lo planes
+ *          (Z,t,tp) (p_lo may be NULL), lse (Z,t) of the scaled logits; pad columns / PAD keys get 0. */
+LFS2_API int lfs2_attn_softmax_planes(const float* s, const uint8_t* key_padding_mask, void* p_hi, void* p_lo,
+                                      float* lse, int batch, int nhead, int t, int tp, float scale, void* stream);
+/* delta (Z,t) = rowsum(dctx o ctx) per head */
+LFS2_API int lfs2_attn_delta(const float* dctx, const float* ctx, float* delta, int batch, int t, int d, int nhead,
+                             void* stream);
+/* dS = scale * P o (dP - delta) as hi/lo planes (Z,t,tp) (lo pointers may be NULL) */
+LFS2_API int lfs2_attn_ds_planes(const void* p_hi, const void* p_lo, const float* dp, const float* delta,
+                                 void* ds_hi, void* ds_lo, int batch, int nhead, int t, int tp, float scale,
+                                 void* stream);
+
 /* ================= train-step config: backward kernels, loss, optimizer ===================
  * The reference obtains all of these from torch.autograd / torch.optim; the citations name the
  * forward construct each gradient belongs to.  Parameter-gradient outputs ACCUMULATE (+=) into

@@ -36,6 +36,10 @@ SIGNATURES = {
     "lfs2_attention_tc_workspace_bytes": [_i],
     "lfs2_attention_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "lfs2_split_bf16": [_vp, _vp, _vp, ctypes.c_longlong, _vp],
+    "lfs2_gemm_tc2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
+    "lfs2_attn_softmax_planes": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
+    "lfs2_attn_delta": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "lfs2_attn_ds_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     # train-step config
     "lfs2_add_layernorm_train": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
     "lfs2_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
@@ -61,6 +65,11 @@ SIGNATURES = {
 }
 # functions whose return type is not int
 RESTYPES = {"lfs2_attention_bwd_workspace_bytes": (ctypes.c_longlong, [_i, _i, _i])}
+
+class Operand(ctypes.Structure):
+    """lfs2_operand of include/lfs2.h"""
+    _fields_ = [("mn_major", _i), ("d0", _i), ("d1", _i), ("d2", _i), ("col0", _i), ("hstride", _i), ("per_z", _i)]
+
 
 _lib = None
 CALLS = 0  # C-ABI launches issued by this process (bench.py reports the per-step count)

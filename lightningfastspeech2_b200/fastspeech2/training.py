@@ -35,7 +35,28 @@ class Engine:
         self._wt = {}
 
     def _planes(self, x):
-        return ops.planes_of(x)
+        """hi/lo planes of an fp32 tensor, split once and remembered on the tensor (activations are used by
+        the forward GEMM and again by the weight-gradient GEMM)"""
+        p = getattr(x, "_lfs2_planes", None)
+        if p is None:
+            p = ops.split_bf16(x.contiguous())
+            if not isinstance(x, torch.nn.Parameter):
+                ops.attach_planes(x, p)
+        return p
+
+    def attention_fwd(self, qkv, kpm, nhead):
+        """-> (ctx, saved)"""
+        d = qkv.shape[-1] // 3
+        if self.tc and (d // nhead) % 32 == 0:
+            ctx, p, lse = ops.attention_mat_fwd(self._planes(qkv), kpm, nhead, npass=self.npass)
+            return ctx, {"p": p}
+        ctx, lse = ops.attention_lse(qkv, kpm, nhead)
+        return ctx, {"lse": lse}
+
+    def attention_bwd(self, qkv, ctx, dctx, saved, kpm, nhead):
+        if "p" in saved:
+            return ops.attention_mat_bwd(self._planes(qkv), saved["p"], ctx, dctx, nhead, npass=self.npass)
+        return ops.attention_bwd(qkv, ctx, dctx, saved["lse"], kpm, nhead)
 
     def linear(self, x, w, b, relu=False, tag=None):
         """x (..., k) . w (n, k)^T + b"""
@@ -52,9 +73,9 @@ class Engine:
         """dw (n, k) += dy^T . x ; db (n) += column sums of dy"""
         n, k = dw.shape
         if self.tc and ops.wgrad_tc_ok(n, k):
-            ops.gemm_wgrad_tc_(dw, db, self._planes(dy), self._planes(x), npass=self.npass, tag=tag)
-            return
-        ops.gemm_tn_(dw, dy, x)
+            ops.gemm_wgrad_tc_(dw, self._planes(dy), self._planes(x), npass=self.npass, tag=tag)
+        else:
+            ops.gemm_tn_(dw, dy, x)
         if db is not None:
             ops.colsum_(db, dy)
 
@@ -88,7 +109,7 @@ def fft_fwd(L, E, x, kpm):
         raise NotImplementedError("grouped conv2.0 with kernel > 1")
     s = {"x": x, "kpm": kpm}
     s["qkv"] = E.linear(x, sa.in_proj_weight, sa.in_proj_bias, tag="qkv_gemm")
-    s["ctx"], s["lse"] = ops.attention_lse(s["qkv"], kpm, L.nhead)
+    s["ctx"], s["att"] = E.attention_fwd(s["qkv"], kpm, L.nhead)
     a = E.linear(s["ctx"], sa.out_proj.weight, sa.out_proj.bias, tag="out_proj_gemm")
     x1, s["z1"], s["st1"] = ops.add_layernorm_train(x, a, L.norm1.weight, L.norm1.bias, L.eps)
     s["x1"] = x1
@@ -121,7 +142,7 @@ def fft_bwd(L, E, s, dx2):
     dz1 = ops.layernorm_bwd(dx1, s["z1"], s["st1"], L.norm1.weight, grad_of(L.norm1.weight), grad_of(L.norm1.bias))
     dctx = E.dgrad(dz1, sa.out_proj.weight, tag="out_proj_dgrad")
     E.wgrad_(grad_of(sa.out_proj.weight), grad_of(sa.out_proj.bias), dz1, s["ctx"], tag="out_proj_wgrad")
-    dqkv = ops.attention_bwd(s["qkv"], s["ctx"], dctx, s["lse"], s["kpm"], L.nhead)
+    dqkv = E.attention_bwd(s["qkv"], s["ctx"], dctx, s["att"], s["kpm"], L.nhead)
     dx = E.dgrad(dqkv, sa.in_proj_weight, tag="qkv_dgrad")
     E.wgrad_(grad_of(sa.in_proj_weight), grad_of(sa.in_proj_bias), dqkv, s["x"], tag="qkv_wgrad")
     ops.add_(dx, dz1)                                                    # residual around the attention

@@ -414,11 +414,13 @@ def colsum_(out, a):
 
 def relu_bwd_(dy, y):
     _launch("lfs2_relu_bwd", _p(dy), _p(y), _p(dy), dy.numel(), _s(), nbytes=12.0 * dy.numel())
+    drop_planes(dy)
     return dy
 
 
 def add_(dst, src):
     _launch("lfs2_add_inplace", _p(dst), _p(src), dst.numel(), _s(), nbytes=12.0 * dst.numel())
+    drop_planes(dst)
     return dst
 
 
@@ -576,6 +578,97 @@ def scale_by_(x, scalar):
     return x
 
 
+def _operand(t, mn_major, col0=0, hstride=0, per_z=False):
+    """lfs2_operand for a contiguous bf16 tensor viewed as (d2, d1, d0)"""
+    if t.dim() == 2:
+        d2, d1, d0 = 1, t.shape[0], t.shape[1]
+    else:
+        d2, d1, d0 = t.shape[0], t.shape[1], t.shape[2]
+    return _lib.Operand(int(mn_major), d0, d1, d2, col0, hstride, int(per_z))
+
+
+def gemm_tc2(a, a_op, b, b_op, c, ldc, m, n, k, nbatch=1, nhead=1, c_bstride=0, c_hstride=0, c_offset=0, npass=3,
+             accumulate=False, tag=None):
+    """C[z] (+)= A[z] . B[z]^T on tcgen05 with per-operand majorness (see lfs2_gemm_tc2)."""
+    for x_ in (a.hi, b.hi):
+        _chk(x_, torch.bfloat16, "gemm_tc2 operand plane")
+    _launch("lfs2_gemm_tc2", _p(a.hi), _p(a.lo if npass == 3 else None), ctypes.byref(a_op), _p(b.hi),
+            _p(b.lo if npass == 3 else None), ctypes.byref(b_op), ctypes.c_void_p(c.data_ptr() + 4 * c_offset), ldc,
+            c_bstride, c_hstride, m, n, k, nbatch, nhead, npass, int(accumulate), _s(), tag=tag or "gemm_tc2",
+            flops=2.0 * m * n * k * nbatch * nhead, nbytes=4.0 * nbatch * nhead * (m * k + n * k + m * n))
+
+
 def wgrad_tc_ok(n, k):
     """shapes the tcgen05 weight-gradient kernel covers (else the CUDA-core gemm_tn runs)"""
-    return False
+    return n % 8 == 0 and k % 8 == 0 and n >= 32 and k >= 32
+
+
+def gemm_wgrad_tc_(dw, dy, x, npass=3, tag=None):
+    """dw (n, k) += dy (m, n)^T . x (m, k) on the tensor cores (both operands MN-major: the contraction runs
+    over the rows of dy and x, no transposed copies)."""
+    n, k = dw.shape
+    m = dy.hi.numel() // n
+    dy2 = Planes(dy.hi.view(m, n), dy.lo.view(m, n) if dy.lo is not None else None)
+    x2 = Planes(x.hi.view(m, k), x.lo.view(m, k) if x.lo is not None else None)
+    gemm_tc2(dy2, _operand(dy2.hi, True), x2, _operand(x2.hi, True), dw, k, n, k, m, npass=npass, accumulate=True,
+             tag=tag or f"wgrad_tc_n{n}_k{k}")
+
+
+def attention_mat_fwd(qkv, kpm, nhead, npass=3):
+    """GEMM-decomposed attention forward on qkv Planes (B,T,3d): -> (ctx fp32 (B,T,d), P Planes (Z,T,Tp), lse (Z,T))"""
+    b, t, d3 = qkv.shape
+    d = d3 // 3
+    dh = d // nhead
+    z = b * nhead
+    tp = (t + 7) // 8 * 8
+    dev = qkv.hi.device
+    s = torch.empty(z, t, tp, device=dev, dtype=torch.float32)
+    q_op = _operand(qkv.hi, False, col0=0, hstride=dh)
+    k_op = _operand(qkv.hi, False, col0=d, hstride=dh)
+    gemm_tc2(qkv, q_op, qkv, k_op, s, tp, t, t, dh, nbatch=b, nhead=nhead, c_bstride=nhead * t * tp, c_hstride=t * tp,
+             npass=npass, tag="attn_qk_gemm")
+    p = Planes(torch.empty(z, t, tp, device=dev, dtype=torch.bfloat16),
+               torch.empty(z, t, tp, device=dev, dtype=torch.bfloat16) if npass == 3 else None)
+    lse = torch.empty(z, t, device=dev, dtype=torch.float32)
+    _launch("lfs2_attn_softmax_planes", _p(s), _p(kpm), _p(p.hi), _p(p.lo), _p(lse), b, nhead, t, tp,
+            float(dh) ** -0.5, _s(), nbytes=(8.0 if npass == 3 else 6.0) * z * t * tp)
+    del s
+    ctx = torch.empty(b, t, d, device=dev, dtype=torch.float32)
+    p_op = _operand(p.hi, False, per_z=True)
+    v_op = _operand(qkv.hi, True, col0=2 * d, hstride=dh)
+    gemm_tc2(p, p_op, qkv, v_op, ctx, d, t, dh, t, nbatch=b, nhead=nhead, c_bstride=t * d, c_hstride=dh, npass=npass,
+             tag="attn_pv_gemm")
+    return ctx, p, lse
+
+
+def attention_mat_bwd(qkv, p, ctx, dctx, nhead, npass=3):
+    """backward of attention_mat_fwd: -> dqkv fp32 (B,T,3d) = [dq | dk | dv]"""
+    b, t, d3 = qkv.shape
+    d = d3 // 3
+    dh = d // nhead
+    z = b * nhead
+    tp = p.hi.shape[-1]
+    dev = qkv.hi.device
+    do = split_bf16(dctx)
+    delta = torch.empty(z, t, device=dev, dtype=torch.float32)
+    _launch("lfs2_attn_delta", _p(dctx), _p(ctx), _p(delta), b, t, d, nhead, _s(), nbytes=8.0 * dctx.numel())
+    dp = torch.empty(z, t, tp, device=dev, dtype=torch.float32)
+    do_k = _operand(do.hi, False, col0=0, hstride=dh)
+    v_k = _operand(qkv.hi, False, col0=2 * d, hstride=dh)
+    gemm_tc2(do, do_k, qkv, v_k, dp, tp, t, t, dh, nbatch=b, nhead=nhead, c_bstride=nhead * t * tp, c_hstride=t * tp,
+             npass=npass, tag="attn_dp_gemm")
+    ds = Planes(torch.empty(z, t, tp, device=dev, dtype=torch.bfloat16),
+                torch.empty(z, t, tp, device=dev, dtype=torch.bfloat16) if npass == 3 else None)
+    _launch("lfs2_attn_ds_planes", _p(p.hi), _p(p.lo), _p(dp), _p(delta), _p(ds.hi), _p(ds.lo), b, nhead, t, tp,
+            float(dh) ** -0.5, _s(), nbytes=(12.0 if npass == 3 else 8.0) * z * t * tp)
+    del dp
+    dqkv = torch.empty(b, t, d3, device=dev, dtype=torch.float32)
+    common = dict(nbatch=b, nhead=nhead, c_bstride=t * d3, c_hstride=dh, npass=npass)
+    # dV = P^T . dO ; dK = dS^T . (scale folded into dS) Q ; dQ = dS . K
+    gemm_tc2(p, _operand(p.hi, True, per_z=True), do, _operand(do.hi, True, col0=0, hstride=dh), dqkv, d3, t, dh, t,
+             c_offset=2 * d, tag="attn_dv_gemm", **common)
+    gemm_tc2(ds, _operand(ds.hi, True, per_z=True), qkv, _operand(qkv.hi, True, col0=0, hstride=dh), dqkv, d3, t, dh, t,
+             c_offset=d, tag="attn_dk_gemm", **common)
+    gemm_tc2(ds, _operand(ds.hi, False, per_z=True), qkv, _operand(qkv.hi, True, col0=d, hstride=dh), dqkv, d3, t, dh,
+             t, c_offset=0, tag="attn_dq_gemm", **common)
+    return dqkv

@@ -320,3 +320,63 @@ def test_train_mode_rejects_dropout():
     batch = synthetic.add_train_targets(synthetic.make_batch(2, 8, 16, seed=1), kw["variances"], seed=1)
     with pytest.raises(NotImplementedError):
         model(batch)
+
+
+# ------------------------------------------------------------- tcgen05 general GEMM (gemm_tc2)
+@pytest.mark.parametrize("npass,rel", [(3, 3e-5), (1, 2e-2)])
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (304, 200, 1000), (80, 768, 5000), (768, 3072, 777)])
+def test_wgrad_tc(m, n, k, npass, rel):
+    """dw (m x n) += dy^T . x with both operands MN-major (contraction over tensor rows), split-K + atomics"""
+    rows = k
+    dy, x = rnd(rows, m, seed=1), rnd(rows, n, seed=2)
+    dw = torch.ones(m, n, device=DEV)
+    ops.gemm_wgrad_tc_(dw, ops.split_bf16(dy.to(DEV)), ops.split_bf16(x.to(DEV)), npass=npass)
+    ref = 1.0 + dy.double().t() @ x.double()
+    err = (dw.cpu().double() - ref).abs().max().item()
+    assert err <= rel * ref.abs().max().item(), (err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+def test_gemm_tc2_batched_head_windows(a_mn, b_mn):
+    """operands as column windows of packed (B, T, 3d)-style tensors, z = b*nhead + h"""
+    B, H, m, n, k = 2, 2, 150, 96, 64
+    # A source tensor: K-major -> (B, m, H*k) ; MN-major -> (B, k, H*m')  with m' = m rounded to 8
+    mp, np_ = (m + 7) // 8 * 8, (n + 7) // 8 * 8
+    a_src = rnd(B, k if a_mn else m, H * (mp if a_mn else k), seed=1)
+    b_src = rnd(B, k if b_mn else n, H * (np_ if b_mn else k), seed=2)
+    A = torch.stack([torch.stack([
+        (a_src[b, :, h * mp:h * mp + m].t() if a_mn else a_src[b, :, h * k:(h + 1) * k]) for h in range(H)]) for b in range(B)])
+    Bm = torch.stack([torch.stack([
+        (b_src[b, :, h * np_:h * np_ + n].t() if b_mn else b_src[b, :, h * k:(h + 1) * k]) for h in range(H)]) for b in range(B)])
+    ref = A.double() @ Bm.double().transpose(-1, -2)           # (B, H, m, n)
+    ap, bp = ops.split_bf16(a_src.to(DEV)), ops.split_bf16(b_src.to(DEV))
+    a_op = ops._operand(ap.hi, a_mn, col0=0, hstride=mp if a_mn else k)
+    b_op = ops._operand(bp.hi, b_mn, col0=0, hstride=np_ if b_mn else k)
+    c = torch.full((B, H, m, n), 7.0, device=DEV)
+    ops.gemm_tc2(ap, a_op, bp, b_op, c, n, m, n, k, nbatch=B, nhead=H, c_bstride=H * m * n, c_hstride=m * n, npass=3)
+    err = (c.cpu().double() - ref).abs().max().item()
+    assert err <= 3e-5 * ref.abs().max().item(), err
+
+
+@pytest.mark.parametrize("mode,rel", [(3, 2e-4), (1, 3e-2)])
+@pytest.mark.parametrize("d,nhead,t", [(128, 2, 70), (256, 2, 203), (768, 2, 90)])
+def test_attention_mat_forward_backward(d, nhead, t, mode, rel):
+    b = 3
+    qkv = rnd(b, t, 3 * d, seed=1, scale=0.7).requires_grad_(True)
+    dctx = rnd(b, t, d, seed=2)
+    kpm = torch.zeros(b, t, dtype=torch.bool)
+    kpm[1, t - 17:] = True
+    kpm[2, t // 2:] = True
+    dh = d // nhead
+    q, k, v = qkv.split(d, dim=-1)
+    hd = lambda z: z.reshape(b, t, nhead, dh).permute(0, 2, 1, 3)
+    s = (hd(q) * dh ** -0.5) @ hd(k).transpose(-1, -2)
+    s = s.masked_fill(kpm[:, None, None, :], float("-inf"))
+    ctx = (torch.softmax(s, -1) @ hd(v)).permute(0, 2, 1, 3).reshape(b, t, d)
+    ctx.backward(dctx)
+    qp = ops.split_bf16(qkv.detach().to(DEV))
+    c, p, lse = ops.attention_mat_fwd(qp, kpm.to(DEV), nhead, npass=mode)
+    close(c, ctx, rel, "attention_mat fwd")
+    close(lse.view(b, nhead, t), torch.logsumexp(s, -1), rel, "attention_mat lse")
+    dqkv = ops.attention_mat_bwd(qp, p, c, dctx.to(DEV), nhead, npass=mode)
+    close(dqkv, qkv.grad, 3 * rel, "attention_mat bwd")
