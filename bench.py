@@ -49,6 +49,16 @@ def peaks():
     return {"hbm": 6650.0, "tensor": 1590.0, "tensor_sustained": 1400.0, "src": "fallback"}
 
 
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed
+    `ncu --set full` capture of this workload (profiles/ncu_traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return json.load(open(p)).get(kernel, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
 class ClockSampler:
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -424,13 +434,19 @@ def run_lfs2(args):
             peak, unit = pk["hbm"], "GB/s"
         roofline = {"kernel": top_name, "bound": "hbm" if top["bound"] == "hbm" else "tensor",
                     "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
-                    "traffic": None, "peak_source": pk["src"], "us_per_launch": per_launch_s * 1e6,
+                    "traffic": ncu_traffic(top_name), "peak_source": pk["src"], "us_per_launch": per_launch_s * 1e6,
                     "share_of_step": top["ms"] / total_ms,
                     "kernel_shares": {k: round(v["ms"] / total_ms, 4) for k, v in sorted(
                         prof.items(), key=lambda kv: -kv[1]["ms"])}}
-        cpu_fps, cpu_s, cpu_frames = cpu_port_throughput(sd, hp, host_batch, args.ref_utts)
-        sample = (f"first {args.ref_utts} of the {BATCH} utterances of the same batch, 1 run of {cpu_s:.1f} s "
-                  f"({cpu_frames} valid frames)")
+        # bounded CPU sample of the same workload: grow the sub-batch until one run takes >= ~10 s of CPU work
+        nutt = max(1, args.ref_utts)
+        while True:
+            cpu_fps, cpu_s, cpu_frames = cpu_port_throughput(sd, hp, host_batch, nutt)
+            if cpu_s >= 10.0 or nutt >= min(BATCH, args.ref_utts_max):
+                break
+            nutt = min(BATCH, args.ref_utts_max, nutt * (4 if cpu_s < 1.5 else 2))
+        sample = (f"first {nutt} of the {BATCH} utterances of the same batch (padded to their own max length), "
+                  f"1 run of {cpu_s:.1f} s ({cpu_frames} valid frames), torch CPU ops on {os.cpu_count()} threads")
         value = frames_all * args.steps / (ms * 1e-3)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -463,7 +479,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lfs2", choices=["lfs2", "reference"])
-    ap.add_argument("--ref-utts", type=int, default=4, help="utterances in the bounded CPU sample")
+    ap.add_argument("--ref-utts", type=int, default=8, help="utterances in the bounded CPU sample (first try)")
+    ap.add_argument("--ref-utts-max", type=int, default=32, help="upper bound of the adaptive CPU sample")
     ap.add_argument("--train-steps", type=int, default=5, help="timed C4 train steps reported under 'train' (0 = skip)")
     ap.add_argument("--train-mode", default="fp32", choices=["simt", "fp32", "bf16"])
     ap.add_argument("--train-cpu-utts", type=int, default=2, help="utterances in the CPU train-step sample (0 = skip)")

@@ -209,8 +209,7 @@ class ConformerEncoderLayer(nn.Module):
             qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="planes", npass=npass, tag="qkv_gemm")
             _, ctx = ops.attention_tc(qkv, kpm, self.nhead, npass=npass)
         else:
-            qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, npass=npass, tag="qkv_gemm")
-            ctx = ops.split_bf16(ops.attention(qkv, kpm, self.nhead))
+            ctx = self._attention_any_head_dim(xp, kpm, npass)
         x1p = ops.gemm_tc(ctx, w["out_proj"], sa.out_proj.bias, residual=xp, gamma=self.norm1.weight,
                           beta=self.norm1.bias, eps=self.eps, out="planes", npass=npass, tag="out_proj_ln_gemm")
         if self.depthwise:
@@ -224,11 +223,23 @@ class ConformerEncoderLayer(nn.Module):
         return ops.gemm_tc(vp, w2, b2, taps=taps2, residual=x1p, gamma=self.norm2.weight, beta=self.norm2.bias,
                            eps=self.eps, out="planes", npass=npass, tag="ffn2_ln_gemm")
 
+    def _attention_any_head_dim(self, xp, kpm, npass):
+        """head_dim != 128 (e.g. 384 of the 76 M config): attention as tcgen05 GEMMs (Q.K^T, P.V through
+        lfs2_gemm_tc2) around a row-softmax kernel; head_dim not a multiple of 32: CUDA-core flash kernel.
+        Returns ctx as Planes."""
+        sa, w = self.self_attn, self._packed_tc()
+        d = xp.shape[-1]
+        if (d // self.nhead) % 32 == 0:
+            qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="planes", npass=npass, tag="qkv_gemm")
+            ctx, _, _ = ops.attention_mat_fwd(qkv, kpm, self.nhead, npass=npass)
+            return ops.split_bf16(ctx)
+        qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, npass=npass, tag="qkv_gemm")
+        return ops.split_bf16(ops.attention(qkv, kpm, self.nhead))
+
     def _forward_tc_unfused_ln(self, x, xp, kpm, npass):
         """d != 256 (e.g. the 76 M config, d = 768): tensor-core GEMMs, LayerNorm as its own kernel."""
         sa, w, p = self.self_attn, self._packed_tc(), self._packed()
-        qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, npass=npass, tag="qkv_gemm")
-        ctx = ops.split_bf16(ops.attention(qkv, kpm, self.nhead))
+        ctx = self._attention_any_head_dim(xp, kpm, npass)
         a = ops.gemm_tc(ctx, w["out_proj"], sa.out_proj.bias, npass=npass, tag="out_proj_gemm")
         x1 = ops.add_layernorm(x, a, self.norm1.weight, self.norm1.bias, self.eps)
         if self.depthwise:
