@@ -167,13 +167,10 @@ TRAIN_WORKLOAD = (f"C4 train step (forward + loss + backward + grad all-reduce +
 def train_batch(hp, rank, world):
     """The rank's shard of the global train batch: utterances sorted by length and dealt in snake
     order, each rank padded to its own maximum length."""
+    from lightningfastspeech2_b200.sharding import shard_batch
+
     full = synthetic.make_batch(TRAIN_BATCH, TRAIN_MIN_LEN, TRAIN_MAX_LEN, seed=4)
-    order = torch.argsort(full["phones_lengths"], descending=True).tolist()
-    mine = [u for i, u in enumerate(order) if (i % (2 * world) == rank or i % (2 * world) == 2 * world - 1 - rank)]
-    sub = {k: v[mine].contiguous() for k, v in full.items()}
-    keep = int(sub["phones_lengths"].max())
-    sub["phones"] = sub["phones"][:, :keep].contiguous()
-    return synthetic.add_train_targets(sub, hp["variances"], seed=4 + rank)
+    return synthetic.add_train_targets(shard_batch(full, rank, world), hp["variances"], seed=4 + rank)
 
 
 def build_train_model(device, preset=TRAIN_PRESET):

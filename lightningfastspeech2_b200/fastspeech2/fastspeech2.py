@@ -421,13 +421,10 @@ class FastSpeech2(_Base):
     def allreduce_gradients(self, group=None):
         """Data-parallel gradient exchange: ONE NCCL all-reduce (sum) over the flat gradient buffer
         (SURVEY 8e); the 1/world_size average is folded into FusedAdamW.  Returns the world size."""
-        import torch.distributed as dist
+        from ..sharding import allreduce_sum_
 
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-            return 1
         _, flat_g = self.flatten_parameters()
-        dist.all_reduce(flat_g, op=dist.ReduceOp.SUM, group=group)
-        return dist.get_world_size(group)
+        return allreduce_sum_(flat_g, group)
 
     # -- train / validation steps (reference :786-807) ---------------------------------------
     def training_step(self, batch, batch_idx, optimizer_idx=0):
