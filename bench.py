@@ -477,7 +477,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lfs2", choices=["lfs2", "reference"])
     ap.add_argument("--ref-utts", type=int, default=8, help="utterances in the bounded CPU sample (first try)")
-    ap.add_argument("--ref-utts-max", type=int, default=32, help="upper bound of the adaptive CPU sample")
+    ap.add_argument("--ref-utts-max", type=int, default=64, help="upper bound of the adaptive CPU sample")
     ap.add_argument("--train-steps", type=int, default=5, help="timed C4 train steps reported under 'train' (0 = skip)")
     ap.add_argument("--train-mode", default="fp32", choices=["simt", "fp32", "bf16"])
     ap.add_argument("--train-cpu-utts", type=int, default=2, help="utterances in the CPU train-step sample (0 = skip)")
