@@ -161,7 +161,8 @@ TRAIN_PRESET = "C4"
 TRAIN_BATCH, TRAIN_MIN_LEN, TRAIN_MAX_LEN = 64, 32, 256
 TRAIN_WORKLOAD = (f"C4 train step (forward + loss + backward + grad all-reduce + AdamW/Noam), 76M-parameter "
                   f"depthwise FastSpeech2 (d=768, 4 enc + 5 dec FFTBlocks, 3 variances), global batch={TRAIN_BATCH} "
-                  f"utterances, phoneme len U[{TRAIN_MIN_LEN},{TRAIN_MAX_LEN}], durations U[1,9], dropout 0 in both arms")
+                  f"utterances, phoneme len U[{TRAIN_MIN_LEN},{TRAIN_MAX_LEN}], durations U[1,9], reference-default dropout "
+                  f"(0.1 / 0.5) in the CUDA arm, none in the CPU port")
 
 
 def train_batch(hp, rank, world):

@@ -291,6 +291,15 @@ LFS2_API int lfs2_fold_pw_bwd(const float* dw_eff, const float* db_eff, const fl
                               const float* b20, float* dw21, float* dw20, float* db20, float* db21, int d_out,
                               int groups, int g, void* stream);
 
+/* dropout (nn.Dropout at model.py:42,55,111-122,539,557): y = x * keep / (1 - p), keep(i) a pure function
+ * of (seed, site, i) via Philox4x32-10 -- calling it again on a gradient with the same (seed, site)
+ * IS the backward pass (no stored mask).  y may alias x.  The stream differs from PyTorch's generator. */
+LFS2_API int lfs2_dropout(const float* x, float* y, long long n, float p, unsigned long long seed,
+                          unsigned int site, void* stream);
+/* same on bf16 hi/lo planes (attention probabilities); lo pointers may be NULL */
+LFS2_API int lfs2_dropout_planes(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, long long n,
+                                 float p, unsigned long long seed, unsigned int site, void* stream);
+
 /* ---- A9: FastSpeech2Loss default branches (loss.py:156-187) ---------------------------
  * loss = mean over rows with pad_mask == 0 (and all `inner` columns) of |pred - tgt| (kind 0)
  * or (pred - tgt)^2 (kind 1); tgt = target, or log(target_i64 + 1) for the duration loss.

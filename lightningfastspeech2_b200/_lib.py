@@ -58,6 +58,8 @@ SIGNATURES = {
     "lfs2_sum_over_time": [_vp, _vp, _i, _i, _i, _vp],
     "lfs2_fold_pw_fwd": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "lfs2_fold_pw_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "lfs2_dropout": [_vp, _vp, _ll, _f, ctypes.c_ulonglong, ctypes.c_uint, _vp],
+    "lfs2_dropout_planes": [_vp, _vp, _vp, _vp, _ll, _f, ctypes.c_ulonglong, ctypes.c_uint, _vp],
     "lfs2_masked_loss": [_vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _vp, _vp, _vp, _vp],
     "lfs2_sumsq": [_vp, _vp, _ll, _vp],
     "lfs2_scale_by": [_vp, _vp, _ll, _vp],

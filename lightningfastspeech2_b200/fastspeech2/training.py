@@ -7,9 +7,12 @@ gradient accumulation is a kernel of this library, parameter gradients accumulat
 into ``p.grad`` (views of one flat buffer when ``FastSpeech2.flatten_parameters()`` was called,
 which is what the fused AdamW and the single NCCL all-reduce consume).
 
-Dropout: the parity protocol of the train step runs with every ``*_dropout = 0``; a
-model constructed with dropout > 0 raises in train mode instead of silently skipping it.
-Dense-conv (non-depthwise) stacks are inference-only.
+Dropout: all seven sites of the reference (PE dropout x2, attention probabilities, dropout1/2 and the
+post-ReLU dropout of the FFTBlock, predictor layers) are implemented with a counter-based Philox mask
+that the backward regenerates from (seed, site); the random stream necessarily differs from PyTorch's,
+so gradient PARITY is checked with every ``*_dropout = 0`` and dropout itself by its
+statistics and by directional derivatives.  Attention-probability dropout needs the tensor-core
+attention path.  Dense-conv (non-depthwise) stacks are inference-only.
 """
 import numpy as np
 import torch
@@ -32,7 +35,26 @@ class Engine:
         self.mode = mode
         self.tc = mode != "simt"
         self.npass = 3 if mode == "fp32" else 1
-        self._wt = {}
+        # dropout: one 64-bit seed per forward pass from torch's CPU generator (torch.manual_seed makes runs
+        # reproducible), one site number per dropout call; the backward replays (seed, site)
+        self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        self.site = 0
+
+    def dropout_(self, x, p):
+        """in-place dropout; returns the replay token for the backward pass (None if p == 0)"""
+        if p <= 0:
+            return None
+        self.site += 1
+        tok = (p, self.seed, self.site)
+        ops.dropout_(x, *tok)
+        return tok
+
+    @staticmethod
+    def dropout_bwd(dy, tok, inplace=True):
+        """gradient through a dropout site: same mask, same 1/(1-p) scale"""
+        if tok is None:
+            return dy
+        return ops.dropout_(dy, *tok, out=None if inplace else torch.empty_like(dy))
 
     def _planes(self, x):
         """hi/lo planes of an fp32 tensor, split once and remembered on the tensor (activations are used by
@@ -44,18 +66,27 @@ class Engine:
                 ops.attach_planes(x, p)
         return p
 
-    def attention_fwd(self, qkv, kpm, nhead):
+    def attention_fwd(self, qkv, kpm, nhead, p_drop=0.0):
         """-> (ctx, saved)"""
         d = qkv.shape[-1] // 3
         if self.tc and (d // nhead) % 32 == 0:
-            ctx, p, lse = ops.attention_mat_fwd(self._planes(qkv), kpm, nhead, npass=self.npass)
-            return ctx, {"p": p}
+            drop = None
+            if p_drop > 0:
+                self.site += 1
+                drop = (p_drop, self.seed, self.site)
+            ctx, p, lse = ops.attention_mat_fwd(self._planes(qkv), kpm, nhead, npass=self.npass, drop=drop)
+            return ctx, {"p": p, "drop": drop}
+        if p_drop > 0:
+            raise NotImplementedError(
+                "attention-probability dropout needs the tensor-core attention (compute_mode 'fp32' or 'bf16' and "
+                "head_dim % 32 == 0); the CUDA-core kernel implements p = 0 only")
         ctx, lse = ops.attention_lse(qkv, kpm, nhead)
         return ctx, {"lse": lse}
 
     def attention_bwd(self, qkv, ctx, dctx, saved, kpm, nhead):
         if "p" in saved:
-            return ops.attention_mat_bwd(self._planes(qkv), saved["p"], ctx, dctx, nhead, npass=self.npass)
+            return ops.attention_mat_bwd(self._planes(qkv), saved["p"], ctx, dctx, nhead, npass=self.npass,
+                                         drop=saved["drop"])
         return ops.attention_bwd(qkv, ctx, dctx, saved["lse"], kpm, nhead)
 
     def linear(self, x, w, b, relu=False, tag=None):
@@ -80,13 +111,6 @@ class Engine:
             ops.colsum_(db, dy)
 
 
-def _check_trainable(p_drop, what):
-    if p_drop > 0:
-        raise NotImplementedError(
-            f"{what}: dropout p={p_drop} in training mode is not implemented by the CUDA path; construct the model "
-            "with all *_dropout = 0 (the train-step parity protocol, SURVEY 8d)")
-
-
 def _mat(w):
     """(n, k, 1) pointwise-conv weight or its gradient as an (n, k) matrix view"""
     return w.view(w.shape[0], w.shape[1])
@@ -102,22 +126,25 @@ def _dwmat(w):
 def fft_fwd(L, E, x, kpm):
     if not L.depthwise:
         raise NotImplementedError("training the dense-conv FFTBlock (only the depthwise variant has a backward)")
-    _check_trainable(L.p_drop, "ConformerEncoderLayer")
+    p = L.p_drop
     sa = L.self_attn
     dwc, pw, gc, pw2 = L.conv1[0], L.conv1[1], L.conv2[0], L.conv2[1]
     if gc.kernel_size[0] != 1:
         raise NotImplementedError("grouped conv2.0 with kernel > 1")
     s = {"x": x, "kpm": kpm}
     s["qkv"] = E.linear(x, sa.in_proj_weight, sa.in_proj_bias, tag="qkv_gemm")
-    s["ctx"], s["att"] = E.attention_fwd(s["qkv"], kpm, L.nhead)
+    s["ctx"], s["att"] = E.attention_fwd(s["qkv"], kpm, L.nhead, p)
     a = E.linear(s["ctx"], sa.out_proj.weight, sa.out_proj.bias, tag="out_proj_gemm")
+    s["drop1"] = E.dropout_(a, p)                                         # dropout1 (model.py:114)
     x1, s["z1"], s["st1"] = ops.add_layernorm_train(x, a, L.norm1.weight, L.norm1.bias, L.eps)
     s["x1"] = x1
     s["dw_wt"] = ops.transpose(_dwmat(dwc.weight))                        # (k, d)
     s["u"] = ops.dwconv1d(x1, s["dw_wt"], dwc.bias)
     s["v"] = E.linear(s["u"], _mat(pw.weight), pw.bias, relu=True, tag="ffn1_gemm")
+    s["dropv"] = E.dropout_(s["v"], p)                                    # dropout after ReLU (model.py:120)
     s["w_eff"], b_eff = ops.fold_pw(_mat(pw2.weight), _mat(gc.weight), gc.bias, pw2.bias)
     y = E.linear(s["v"], s["w_eff"], b_eff, tag="ffn2_gemm")
+    s["drop2"] = E.dropout_(y, p)                                         # dropout2 (model.py:115)
     x2, s["z2"], s["st2"] = ops.add_layernorm_train(x1, y, L.norm2.weight, L.norm2.bias, L.eps)
     return x2, s
 
@@ -128,10 +155,12 @@ def fft_bwd(L, E, s, dx2):
     dev = dx2.device
     dz2 = ops.layernorm_bwd(dx2, s["z2"], s["st2"], L.norm2.weight, grad_of(L.norm2.weight), grad_of(L.norm2.bias))
     # conv2 (folded): y = v . w_eff^T + b_eff
-    dv = E.dgrad(dz2, s["w_eff"], tag="ffn2_dgrad")
+    dy = E.dropout_bwd(dz2, s["drop2"], inplace=False)
+    dv = E.dgrad(dy, s["w_eff"], tag="ffn2_dgrad")
     dw_eff = torch.zeros_like(s["w_eff"])
     db_eff = torch.zeros(s["w_eff"].shape[0], device=dev, dtype=torch.float32)
-    E.wgrad_(dw_eff, db_eff, dz2, s["v"], tag="ffn2_wgrad")
+    E.wgrad_(dw_eff, db_eff, dy, s["v"], tag="ffn2_wgrad")
+    E.dropout_bwd(dv, s["dropv"])
     ops.fold_pw_bwd_(dw_eff, db_eff, _mat(pw2.weight), _mat(gc.weight), gc.bias, _mat(grad_of(pw2.weight)),
                      _mat(grad_of(gc.weight)), grad_of(gc.bias), grad_of(pw2.bias))
     ops.relu_bwd_(dv, s["v"])
@@ -140,8 +169,9 @@ def fft_bwd(L, E, s, dx2):
     dx1 = _dwconv_bwd(dwc, s["dw_wt"], du, s["x1"])
     ops.add_(dx1, dz2)                                                   # residual around the FFN
     dz1 = ops.layernorm_bwd(dx1, s["z1"], s["st1"], L.norm1.weight, grad_of(L.norm1.weight), grad_of(L.norm1.bias))
-    dctx = E.dgrad(dz1, sa.out_proj.weight, tag="out_proj_dgrad")
-    E.wgrad_(grad_of(sa.out_proj.weight), grad_of(sa.out_proj.bias), dz1, s["ctx"], tag="out_proj_wgrad")
+    da = E.dropout_bwd(dz1, s["drop1"], inplace=False)
+    dctx = E.dgrad(da, sa.out_proj.weight, tag="out_proj_dgrad")
+    E.wgrad_(grad_of(sa.out_proj.weight), grad_of(sa.out_proj.bias), da, s["ctx"], tag="out_proj_wgrad")
     dqkv = E.attention_bwd(s["qkv"], s["ctx"], dctx, s["att"], s["kpm"], L.nhead)
     dx = E.dgrad(dqkv, sa.in_proj_weight, tag="qkv_dgrad")
     E.wgrad_(grad_of(sa.in_proj_weight), grad_of(sa.in_proj_bias), dqkv, s["x"], tag="qkv_wgrad")
@@ -168,13 +198,12 @@ def vp_fwd(P, E, x, mask):
     for layer in P.layers:
         if not layer.depthwise:
             raise NotImplementedError("training dense-conv variance predictors")
-        _check_trainable(layer.layers[3].p, "VarianceConvolutionLayer")
         conv, ln = layer.layers[0].module, layer.layers[2]
         dw_wt = ops.transpose(_dwmat(conv[0].weight))
         u = ops.dwconv1d(z, dw_wt, conv[0].bias)
         h = E.linear(u, _mat(conv[1].weight), conv[1].bias, relu=True, tag="predictor_pw_gemm")
         zo, _, st = ops.add_layernorm_train(h, None, ln.weight, ln.bias, ln.eps)
-        layers.append({"x": z, "u": u, "h": h, "st": st, "dw_wt": dw_wt})
+        layers.append({"x": z, "u": u, "h": h, "st": st, "dw_wt": dw_wt, "drop": E.dropout_(zo, layer.layers[3].p)})
         z = zo
     out = ops.rowdot_mask(z, P.linear.weight, P.linear.bias, mask)
     return out, {"layers": layers, "z": z, "mask": mask}
@@ -185,6 +214,7 @@ def vp_bwd(P, E, s, dout):
                              grad_of(P.linear.bias))
     for layer, sl in zip(reversed(list(P.layers)), reversed(s["layers"])):
         conv, ln = layer.layers[0].module, layer.layers[2]
+        E.dropout_bwd(dz, sl["drop"])
         dh = ops.layernorm_bwd(dz, sl["h"], sl["st"], ln.weight, grad_of(ln.weight), grad_of(ln.bias))
         ops.relu_bwd_(dh, sl["h"])
         du = E.dgrad(dh, _mat(conv[1].weight), tag="predictor_dgrad")
@@ -203,8 +233,6 @@ def forward_train(M, targets):
     va = M.variance_adaptor
     if any(level == "phone" for level in va.variance_levels):
         raise NotImplementedError("phone-level variances")
-    _check_trainable(hp.encoder_dropout, "encoder")
-    _check_trainable(hp.decoder_dropout, "decoder")
     phones = targets["phones"].to(dev, non_blocking=True).contiguous()
     dvec = targets["speaker"].to(dev, dtype=torch.float32, non_blocking=True).contiguous()
     pe = M.positional_encoding.pe
@@ -212,7 +240,16 @@ def forward_train(M, targets):
 
     spk = ops.speaker_proj(dvec, M.speaker_embedding.projection.weight, M.speaker_embedding.projection.bias)
     S["spk"] = spk
-    x, src_mask = ops.embed_pe_spk(phones, M.phone_embedding.weight, pe, spk)
+    p_pe = M.positional_encoding.dropout.p
+    if p_pe > 0:  # dropout sits between "+ PE" and "+ spk" (fastspeech2.py:653-660): split the fused front end
+        zero_spk = torch.zeros_like(spk)
+        zero_pe = torch.zeros(1, max(phones.shape[1], 1), pe.shape[-1], device=dev, dtype=torch.float32)
+        x, src_mask = ops.embed_pe_spk(phones, M.phone_embedding.weight, pe, zero_spk)
+        S["drop_enc"] = E.dropout_(x, p_pe)
+        ops.add_pe_spk_(x, zero_pe, spk)
+    else:
+        S["drop_enc"] = None
+        x, src_mask = ops.embed_pe_spk(phones, M.phone_embedding.weight, pe, spk)
     S["enc"] = []
     for L in M.encoder.layers:
         x, s = fft_fwd(L, E, x, src_mask)
@@ -232,7 +269,14 @@ def forward_train(M, targets):
         S["vars"].append((var, s_vp, idx))
         result[f"variances_{var}"] = pred
 
-    x = ops.add_pe_spk_(x, pe, spk)
+    if p_pe > 0:  # fastspeech2.py:703-707
+        zero_pe = torch.zeros(1, max(x.shape[1], 1), pe.shape[-1], device=dev, dtype=torch.float32)
+        ops.add_pe_spk_(x, pe, torch.zeros_like(spk))
+        S["drop_dec"] = E.dropout_(x, p_pe)
+        ops.add_pe_spk_(x, zero_pe, spk)
+    else:
+        S["drop_dec"] = None
+        x = ops.add_pe_spk_(x, pe, spk)
     S["dec"] = []
     for L in M.decoder.layers:
         x, s = fft_fwd(L, E, x, tgt_mask)
@@ -262,6 +306,7 @@ def backward_train(M, S, dmel, ddur, dvars):
         for L, s in zip(reversed(list(M.decoder.layers)), reversed(S["dec"])):
             dx = fft_bwd(L, E, s, dx)
         ops.sum_over_time_(dspk, dx)                                     # "+ spk" at Tm (fastspeech2.py:707)
+        E.dropout_bwd(dx, S["drop_dec"])
     else:
         dx = torch.zeros_like(S["dec_out"])
     for var, s_vp, idx in reversed(S["vars"]):
@@ -276,6 +321,7 @@ def backward_train(M, S, dmel, ddur, dvars):
     for L, s in zip(reversed(list(M.encoder.layers)), reversed(S["enc"])):
         dx = fft_bwd(L, E, s, dx)
     ops.sum_over_time_(dspk, dx)                                         # "+ spk" at Tp (fastspeech2.py:658)
+    E.dropout_bwd(dx, S["drop_enc"])
     ops.embedding_bwd_(grad_of(M.phone_embedding.weight), dx, S["phones"], skip_idx=0)
     # speaker term: spk = relu(W . dvec + b)   (model.py:137-143)
     proj = M.speaker_embedding.projection

@@ -614,8 +614,26 @@ def gemm_wgrad_tc_(dw, dy, x, npass=3, tag=None):
              tag=tag or f"wgrad_tc_n{n}_k{k}")
 
 
-def attention_mat_fwd(qkv, kpm, nhead, npass=3):
-    """GEMM-decomposed attention forward on qkv Planes (B,T,3d): -> (ctx fp32 (B,T,d), P Planes (Z,T,Tp), lse (Z,T))"""
+def dropout_(x, p, seed, site, out=None):
+    """x * keep / (1 - p) with keep = Philox(seed, site, element index); in place unless `out` is given.
+    Calling it on a gradient with the same (seed, site) is the backward pass."""
+    _chk(x, torch.float32, "dropout input")
+    y = x if out is None else out
+    _launch("lfs2_dropout", _p(x), _p(y), x.numel(), float(p), int(seed), int(site), _s(), nbytes=8.0 * x.numel())
+    drop_planes(y)
+    return y
+
+
+def dropout_planes(pl, p, seed, site):
+    out = Planes(torch.empty_like(pl.hi), torch.empty_like(pl.lo) if pl.lo is not None else None)
+    _launch("lfs2_dropout_planes", _p(pl.hi), _p(pl.lo), _p(out.hi), _p(out.lo), pl.hi.numel(), float(p), int(seed),
+            int(site), _s(), tag="lfs2_dropout", nbytes=(8.0 if pl.lo is not None else 4.0) * pl.hi.numel())
+    return out
+
+
+def attention_mat_fwd(qkv, kpm, nhead, npass=3, drop=None):
+    """GEMM-decomposed attention forward on qkv Planes (B,T,3d): -> (ctx fp32 (B,T,d), P Planes (Z,T,Tp), lse (Z,T));
+    drop = (p, seed, site): attention-probability dropout, then the 2nd result is (P, P o mask/(1-p))."""
     b, t, d3 = qkv.shape
     d = d3 // 3
     dh = d // nhead
@@ -633,16 +651,20 @@ def attention_mat_fwd(qkv, kpm, nhead, npass=3):
     _launch("lfs2_attn_softmax_planes", _p(s), _p(kpm), _p(p.hi), _p(p.lo), _p(lse), b, nhead, t, tp,
             float(dh) ** -0.5, _s(), nbytes=(8.0 if npass == 3 else 6.0) * z * t * tp)
     del s
+    pm = dropout_planes(p, *drop) if drop is not None else p
     ctx = torch.empty(b, t, d, device=dev, dtype=torch.float32)
-    p_op = _operand(p.hi, False, per_z=True)
+    p_op = _operand(pm.hi, False, per_z=True)
     v_op = _operand(qkv.hi, True, col0=2 * d, hstride=dh)
-    gemm_tc2(p, p_op, qkv, v_op, ctx, d, t, dh, t, nbatch=b, nhead=nhead, c_bstride=t * d, c_hstride=dh, npass=npass,
+    gemm_tc2(pm, p_op, qkv, v_op, ctx, d, t, dh, t, nbatch=b, nhead=nhead, c_bstride=t * d, c_hstride=dh, npass=npass,
              tag="attn_pv_gemm")
-    return ctx, p, lse
+    return ctx, (p if drop is None else (p, pm)), lse
 
 
-def attention_mat_bwd(qkv, p, ctx, dctx, nhead, npass=3):
+def attention_mat_bwd(qkv, p, ctx, dctx, nhead, npass=3, drop=None):
     """backward of attention_mat_fwd: -> dqkv fp32 (B,T,3d) = [dq | dk | dv]"""
+    pm = p
+    if drop is not None:
+        p, pm = p
     b, t, d3 = qkv.shape
     d = d3 // 3
     dh = d // nhead
@@ -657,6 +679,8 @@ def attention_mat_bwd(qkv, p, ctx, dctx, nhead, npass=3):
     v_k = _operand(qkv.hi, False, col0=2 * d, hstride=dh)
     gemm_tc2(do, do_k, qkv, v_k, dp, tp, t, t, dh, nbatch=b, nhead=nhead, c_bstride=nhead * t * tp, c_hstride=t * tp,
              npass=npass, tag="attn_dp_gemm")
+    if drop is not None:  # O = (P o M).V  =>  dP_eff = M o (dO.V^T); delta = rowsum(dO o O) still holds
+        dropout_(dp, *drop)
     ds = Planes(torch.empty(z, t, tp, device=dev, dtype=torch.bfloat16),
                 torch.empty(z, t, tp, device=dev, dtype=torch.bfloat16) if npass == 3 else None)
     _launch("lfs2_attn_ds_planes", _p(p.hi), _p(p.lo), _p(dp), _p(delta), _p(ds.hi), _p(ds.lo), b, nhead, t, tp,
@@ -665,7 +689,7 @@ def attention_mat_bwd(qkv, p, ctx, dctx, nhead, npass=3):
     dqkv = torch.empty(b, t, d3, device=dev, dtype=torch.float32)
     common = dict(nbatch=b, nhead=nhead, c_bstride=t * d3, c_hstride=dh, npass=npass)
     # dV = P^T . dO ; dK = dS^T . (scale folded into dS) Q ; dQ = dS . K
-    gemm_tc2(p, _operand(p.hi, True, per_z=True), do, _operand(do.hi, True, col0=0, hstride=dh), dqkv, d3, t, dh, t,
+    gemm_tc2(pm, _operand(pm.hi, True, per_z=True), do, _operand(do.hi, True, col0=0, hstride=dh), dqkv, d3, t, dh, t,
              c_offset=2 * d, tag="attn_dv_gemm", **common)
     gemm_tc2(ds, _operand(ds.hi, True, per_z=True), qkv, _operand(qkv.hi, True, col0=0, hstride=dh), dqkv, d3, t, dh, t,
              c_offset=d, tag="attn_dk_gemm", **common)

@@ -313,13 +313,104 @@ def test_train_step_optimizer_and_flat_buffers(golden_dir):
     assert torch.isfinite(r["mel"]).all()
 
 
-def test_train_mode_rejects_dropout():
-    kw = dict(configs.PRESETS["SMALL_TRAIN"], encoder_dropout=0.1)
+def _dropout_model(mode, seed=7):
+    kw = dict(configs.PRESETS["SMALL_TRAIN"], encoder_dropout=0.1, decoder_dropout=0.1, duration_dropout=0.5,
+              variance_dropout=[0.5, 0.5])
     st = {v: {"min": -3.0, "max": 3.0, "mean": 0.0, "std": 1.0} for v in kw["variances"]}
-    model = FastSpeech2(stats=st, phone2id={f"p{i}": i for i in range(80)}, num_workers=0, **kw).to(DEV).train()
-    batch = synthetic.add_train_targets(synthetic.make_batch(2, 8, 16, seed=1), kw["variances"], seed=1)
+    model = FastSpeech2(stats=st, phone2id={f"p{i}": i for i in range(80)}, num_workers=0, **kw)
+    model.load_state_dict(synthetic.fill_state_dict(model.state_dict(), seed=seed))
+    model = model.to(DEV).train().set_compute_mode(mode)
+    model.log_losses = False
+    batch = synthetic.add_train_targets(synthetic.make_batch(3, 9, 40, seed=seed), kw["variances"], seed=seed)
+    return model, batch
+
+
+def test_cuda_core_attention_rejects_dropout():
+    model, batch = _dropout_model("simt")
     with pytest.raises(NotImplementedError):
         model(batch)
+
+
+def test_dropout_kernel_statistics_and_replay():
+    n = 1 << 20
+    x = torch.ones(n, device=DEV)
+    for p in (0.1, 0.5):
+        y = ops.dropout_(x.clone(), p, seed=1234, site=3)
+        keep = (y != 0).float().mean().item()
+        assert abs(keep - (1 - p)) < 4 * (p * (1 - p) / n) ** 0.5 + 1e-4, (p, keep)
+        assert torch.allclose(y[y != 0], torch.full((1,), 1 / (1 - p), device=DEV))
+        again = ops.dropout_(x.clone(), p, seed=1234, site=3)       # replay = backward mask
+        assert torch.equal(y, again)
+        other = ops.dropout_(x.clone(), p, seed=1234, site=4)
+        assert (other != y).float().mean().item() > 0.05
+        oop = torch.empty_like(x)
+        ops.dropout_(x, p, seed=1234, site=3, out=oop)
+        assert torch.equal(oop, y) and float(x.min()) == 1.0
+    assert torch.equal(ops.dropout_(x.clone(), 0.0, 1, 1), x)
+
+
+@pytest.mark.parametrize("d,nhead,t", [(128, 2, 70), (768, 2, 90)])
+def test_attention_mat_dropout_matches_masked_reference(d, nhead, t):
+    """attention-probability dropout: the kernel's Philox mask is extracted (dropout of a ones tensor with the
+    same seed/site) and fed to a plain torch restatement, whose autograd gradients the backward must match"""
+    b, p_drop, tok = 2, 0.3, (0.3, 99, 5)
+    tp = (t + 7) // 8 * 8
+    qkv = rnd(b, t, 3 * d, seed=1, scale=0.7).requires_grad_(True)
+    dctx = rnd(b, t, d, seed=2)
+    kpm = torch.zeros(b, t, dtype=torch.bool)
+    kpm[1, t - 11:] = True
+    mask = ops.dropout_(torch.ones(b * nhead, t, tp, device=DEV), *tok).cpu()[:, :, :t].reshape(b, nhead, t, t)
+    dh = d // nhead
+    q, k, v = qkv.split(d, dim=-1)
+    hd = lambda z: z.reshape(b, t, nhead, dh).permute(0, 2, 1, 3)
+    s = ((hd(q) * dh ** -0.5) @ hd(k).transpose(-1, -2)).masked_fill(kpm[:, None, None, :], float("-inf"))
+    ctx = ((torch.softmax(s, -1) * mask) @ hd(v)).permute(0, 2, 1, 3).reshape(b, t, d)
+    ctx.backward(dctx)
+    qp = ops.split_bf16(qkv.detach().to(DEV))
+    c, saved, _ = ops.attention_mat_fwd(qp, kpm.to(DEV), nhead, npass=3, drop=tok)
+    close(c, ctx, 2e-4, "dropout attention fwd")
+    dqkv = ops.attention_mat_bwd(qp, saved, c, dctx.to(DEV), nhead, npass=3, drop=tok)
+    close(dqkv, qkv.grad, 6e-4, "dropout attention bwd")
+
+
+def test_train_step_with_dropout_directional_derivative():
+    """all seven dropout sites on (p = 0.1 / 0.5): with the RNG seed fixed the loss is a deterministic function
+    of the weights, so <grad, delta> must equal the central finite difference along delta"""
+    model, batch = _dropout_model("fp32")
+    params = [p for p in model.parameters() if p.requires_grad]
+
+    def loss_at():
+        torch.manual_seed(1234)
+        res = model(batch)
+        return model.loss(res, batch)["total"]
+
+    l0 = loss_at()
+    l0.backward()
+    g = [p.grad.detach().clone() for p in params]
+    gn2 = sum(float((x.double() ** 2).sum()) for x in g)
+    assert gn2 > 0 and all(torch.isfinite(x).all() for x in g)
+    eta = 2e-2 / gn2                      # predicted loss change 2e-2 along +-eta * g
+    vals = []
+    with torch.no_grad():
+        for sign in (1.0, -2.0):
+            for p, gi in zip(params, g):
+                p.add_(gi, alpha=sign * eta)
+            ops.WEIGHTS_EPOCH += 1
+            with torch.enable_grad():
+                vals.append(float(loss_at().detach()))
+        for p, gi in zip(params, g):
+            p.add_(gi, alpha=eta)
+    fd = (vals[0] - vals[1]) / (2 * eta)
+    print(f"dropout train step: <g,g> = {gn2:.5e}, finite difference = {fd:.5e}, loss = {float(l0):.4f}")
+    assert abs(fd - gn2) <= 0.05 * gn2, (fd, gn2)
+    # dropout is active: two different seeds give different losses, the same seed the same loss
+    torch.manual_seed(1)
+    a = float(model.loss(model(batch), batch)["total"].detach())
+    torch.manual_seed(2)
+    b2 = float(model.loss(model(batch), batch)["total"].detach())
+    torch.manual_seed(1)
+    a2 = float(model.loss(model(batch), batch)["total"].detach())
+    assert a == a2 and a != b2
 
 
 # ------------------------------------------------------------- tcgen05 general GEMM (gemm_tc2)
