@@ -133,6 +133,13 @@ LFS2_API int lfs2_length_regulate_scatter(const void* x, const int64_t* cum, con
                                  void* out, uint8_t* mask, int batch, int tp, int l, int row_bytes,
                                  void* stream);
 
+/* same with l output frames of which only those below cap (<= l) can be valid: frames in [cap, l) are PAD
+ * (+0, mask = 1) for every utterance.  Used by the length-bucketed synthesis, which appends the decoder's
+ * conv halo as explicit PAD frames to each bucket (cap = the reference's L). */
+LFS2_API int lfs2_length_regulate_scatter_ex(const void* x, const int64_t* cum, const int64_t* lengths,
+                                    void* out, uint8_t* mask, int batch, int tp, int l, int cap,
+                                    int row_bytes, void* stream);
+
 /* ---- tensor-core (tcgen05) GEMM / Conv1d with fused epilogues ---------------------------
  * Operands are bf16 "hi/lo" planes of fp32 values (x = hi + lo, see lfs2_split_bf16):
  *   a_hi/a_lo : (batch, t, d)      row-major bf16   (activations)

@@ -31,6 +31,7 @@ SIGNATURES = {
     "lfs2_duration_round_guard": [_vp, _vp, _vp, _i, _i, _vp],
     "lfs2_length_regulate_scan": [_vp, _i, _vp, _vp, _vp, _i, _i, _vp],
     "lfs2_length_regulate_scatter": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "lfs2_length_regulate_scatter_ex": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "lfs2_gemm_tc": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i,
                      _vp],
     "lfs2_attention_tc_workspace_bytes": [_i],

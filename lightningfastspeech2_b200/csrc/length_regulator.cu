@@ -58,7 +58,8 @@ constexpr int kLrUnroll = 4;
 
 __global__ void __launch_bounds__(kLrThreads)
 lr_scatter_kernel(const int4* __restrict__ x, const int64_t* __restrict__ cum, const int64_t* __restrict__ lengths,
-                  int4* __restrict__ out, uint8_t* __restrict__ mask, int tp, int l, int cpr /*16B chunks per row*/) {
+                  int4* __restrict__ out, uint8_t* __restrict__ mask, int tp, int l, int cap,
+                  int cpr /*16B chunks per row*/) {
   int b = blockIdx.y;
   int t0 = blockIdx.x * kLrFrames;
   __shared__ int s_idx[kLrFrames];
@@ -66,7 +67,7 @@ lr_scatter_kernel(const int4* __restrict__ x, const int64_t* __restrict__ cum, c
   if (threadIdx.x < kLrFrames) {
     int t = t0 + threadIdx.x;
     int idx = -1;
-    if (t < l && (long long)t < len) {
+    if (t < l && t < cap && (long long)t < len) {  // frames at or beyond the reference's cut (cap) are PAD
       const int64_t* c = cum + (size_t)b * tp;
       int lo = 0, hi = tp;  // first p with cum[p] > t  == number of p with cum[p] <= t
       while (lo < hi) {
@@ -129,6 +130,11 @@ int lfs2_length_regulate_scan(const void* dur, int dur_is_i64, int64_t* cum, int
 
 int lfs2_length_regulate_scatter(const void* x, const int64_t* cum, const int64_t* lengths, void* out,
                                  uint8_t* mask, int batch, int tp, int l, int row_bytes, void* stream) {
+  return lfs2_length_regulate_scatter_ex(x, cum, lengths, out, mask, batch, tp, l, l, row_bytes, stream);
+}
+
+int lfs2_length_regulate_scatter_ex(const void* x, const int64_t* cum, const int64_t* lengths, void* out,
+                                    uint8_t* mask, int batch, int tp, int l, int cap, int row_bytes, void* stream) {
   LFS2_REQUIRE(cum && lengths, LFS2_ERR_INVALID_ARG, "length_regulate_scatter: null pointer");
   LFS2_REQUIRE(batch > 0 && tp > 0 && l >= 0, LFS2_ERR_INVALID_ARG, "length_regulate_scatter: bad shape");
   if (l == 0) return LFS2_OK;
@@ -140,7 +146,7 @@ int lfs2_length_regulate_scatter(const void* x, const int64_t* cum, const int64_
   LFS2_REQUIRE(batch <= 65535, LFS2_ERR_UNSUPPORTED, "length_regulate_scatter: batch > 65535");
   dim3 grid(ceil_div(l, kLrFrames), batch);
   lr_scatter_kernel<<<grid, kLrThreads, 0, (cudaStream_t)stream>>>((const int4*)x, cum, lengths, (int4*)out, mask,
-                                                                  tp, l, row_bytes / 16);
+                                                                  tp, l, cap, row_bytes / 16);
   LFS2_CHECK_LAUNCH("length_regulate_scatter");
   return LFS2_OK;
 }

@@ -337,18 +337,33 @@ class FastSpeech2(_Base):
         hp = self.hparams
         if not inference and self.training and torch.is_grad_enabled() and not force and not control:
             return self._forward_train(targets)
+        if inference and self.length_buckets > 1 and targets["phones"].shape[0] > 1:
+            return self._forward_bucketed(targets, control, force)
+        st = self._encode_stage(targets, inference, force)
+        return self._decode_stage(st, targets, inference, force, control)
+
+    def _encode_stage(self, targets, inference, force):
+        """front end, encoder, duration predictor and the durations used (reference :639-686 + model.py:249-309)"""
+        dev, hp = self.device, self.hparams
         phones = targets["phones"].to(dev, non_blocking=True).contiguous()
         speakers = targets["speaker"].to(dev, dtype=torch.float32, non_blocking=True).contiguous()
-
         spk = self.speaker_embedding.project(speakers)                       # (B, d)
         pe = self.positional_encoding.pe
         if self.training and hp.encoder_dropout > 0:
-            raise NotImplementedError("dropout in training mode")
+            raise NotImplementedError("dropout in training mode outside the train step (use model.train() with grad "
+                                      "enabled for the train path, or .eval())")
         output, src_mask = ops.embed_pe_spk(phones, self.phone_embedding.weight, pe, spk)
         output = self.encoder(output, src_key_padding_mask=src_mask)
+        st = self.variance_adaptor.durations(output, src_mask, targets, inference=inference, force=force)
+        st.update(enc=output, src_mask=src_mask, spk=spk)
+        return st
 
-        variance_output = self.variance_adaptor(output, src_mask, targets, inference=inference, force=force,
-                                                control=control)
+    def _decode_stage(self, st, targets, inference, force, control, scan=None, frames=None):
+        """LengthRegulator, variance encoders, decoder, mel Linear, result dict (reference model.py:311-341, :703-784)"""
+        dev, hp = self.device, self.hparams
+        pe, spk, src_mask = self.positional_encoding.pe, st["spk"], st["src_mask"]
+        variance_output = self.variance_adaptor.expand(st["enc"], st, targets, inference=inference, force=force,
+                                                       control=control, scan=scan, frames=frames)
         output = ops.add_pe_spk_(variance_output["x"], pe, spk)
         tgt_mask = variance_output["tgt_mask"]
         if self.compute_mode != "simt" and hp.decoder_hidden % 32 == 0 and hp.n_mels % 16 == 0:
@@ -378,6 +393,88 @@ class FastSpeech2(_Base):
             if f"_bucket_{var}" in variance_output:
                 result[f"_bucket_{var}"] = variance_output[f"_bucket_{var}"]
         return result
+
+    # -- length-bucketed synthesis ---------------------------------------------------
+    length_buckets = 1
+
+    def _halos(self):
+        """(encoder side, decoder side): rows beyond an utterance's end that can still influence its valid
+        rows -- the summed conv half-widths of everything downstream (attention never reads PAD keys)."""
+        va = self.variance_adaptor
+        h_enc = sum(layer.halo() for layer in self.encoder.layers) + va.duration_predictor.halo()
+        h_dec = max([sum(layer.halo() for layer in self.decoder.layers)] +
+                    [va.encoders[v].predictor.halo() for v in va.variances])
+        return h_enc, h_dec
+
+    def _forward_bucketed(self, targets, control, force=None):
+        """Synthesis of a ragged batch as `length_buckets` length-sorted sub-batches, each padded only to ITS
+        longest utterance plus the conv halo.  Exactness: PAD rows are never attention keys, so they reach
+        valid rows only through the FFN / predictor convolutions; every row within the summed half-widths
+        (`_halos`) of an utterance's end is kept (and holds exactly the value the reference computes there:
+        PE[t] + speaker term, ...), rows farther out are provably unobservable on valid rows.  Valid
+        positions therefore equal the un-bucketed result; positions the reference's consumers mask with
+        tgt_mask (generator.py:164) are returned as zeros instead of the reference's PAD-row values."""
+        dev, hp = self.device, self.hparams
+        phones_all = targets["phones"]
+        speaker_all = targets["speaker"]
+        bsz, tp = phones_all.shape
+        nz = (phones_all != 0)
+        lengths = (nz * torch.arange(1, tp + 1, device=phones_all.device)).amax(1).tolist()  # last valid phone + 1
+        order = sorted(range(bsz), key=lambda i: -lengths[i])
+        ngroups = min(self.length_buckets, bsz)
+        per = (bsz + ngroups - 1) // ngroups
+        h_enc, h_dec = self._halos()
+        cap = int(self.variance_adaptor.max_length)
+        # phase 1, per bucket: encoder + durations (the encoder side may be cut at the bucket's longest utterance
+        # + halo because the full tensor's end, where the reference zero-pads, is known: tp)
+        stages = []
+        for g0 in range(0, bsz, per):
+            idx = order[g0:g0 + per]
+            tp_g = min(tp, max(lengths[i] for i in idx) + h_enc)
+            it = torch.tensor(idx, device=phones_all.device)
+            sub = {"phones": phones_all[it][:, :tp_g].contiguous(), "speaker": speaker_all[it].contiguous()}
+            f = None
+            if force:  # parity runs: the reference's discrete decisions, sliced to this bucket
+                f = {"want_idx": force.get("want_idx", False)}
+                if "duration_rounded" in force:
+                    f["duration_rounded"] = force["duration_rounded"][it.to(force["duration_rounded"].device)][:, :tp_g]
+                if "bucket_idx" in force:
+                    f["bucket_idx"] = {v: t[it.to(t.device)] for v, t in force["bucket_idx"].items()}
+            st = self._encode_stage(sub, True, f)
+            scan = ops.length_regulate_scan(st["duration_rounded"], st["enc"].shape[:2])
+            stages.append((idx, tp_g, f, st, scan))
+        # the decoder side needs the global frame count first (where the reference's tensor ends): ONE read-back
+        longest = torch.cat([sc[2] for *_, sc in stages]).tolist()
+        l_glob = min(max(longest), cap)
+        parts = []
+        for (idx, tp_g, f, st, scan), lg in zip(stages, longest):
+            cap_g = min(lg, cap)
+            frames = (min(cap_g + h_dec, l_glob), cap_g)
+            parts.append((idx, tp_g, self._decode_stage(st, None, True, f, control, scan=scan, frames=frames)))
+        n_mels = hp.n_mels
+        out = {
+            "mel": torch.zeros(bsz, l_glob, n_mels, device=dev),
+            "duration_prediction": torch.zeros(bsz, tp, device=dev),
+            "duration_rounded": torch.zeros(bsz, tp, device=dev, dtype=torch.int32),
+            "src_mask": phones_all.to(dev) == 0,
+            "tgt_mask": torch.ones(bsz, l_glob, device=dev, dtype=torch.bool),
+        }
+        for v in hp.variances:
+            out[f"variances_{v}"] = torch.zeros(bsz, l_glob, device=dev)
+            if any(f"_bucket_{v}" in r for _, _, r in parts):
+                out[f"_bucket_{v}"] = torch.zeros(bsz, l_glob, device=dev, dtype=torch.int64)
+        if any("fastdiff_var" in r for _, _, r in parts):
+            out["fastdiff_var"] = torch.zeros(bsz, l_glob, n_mels, device=dev)
+        for idx, tp_g, r in parts:
+            it = torch.tensor(idx, device=dev)
+            w = min(r["mel"].shape[1], l_glob)
+            for key in ("mel", "tgt_mask", "fastdiff_var", *[f"variances_{v}" for v in hp.variances],
+                        *[f"_bucket_{v}" for v in hp.variances]):
+                if key in r and key in out:
+                    out[key][it, :w] = r[key][:, :w]
+            out["duration_prediction"][it, :tp_g] = r["duration_prediction"]
+            out["duration_rounded"][it, :tp_g] = r["duration_rounded"].to(torch.int32)
+        return out
 
     # -- train step: forward with saved activations + hand-written backward (training.py) -----
     def _forward_train(self, targets):

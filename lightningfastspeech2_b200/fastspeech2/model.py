@@ -191,6 +191,12 @@ class ConformerEncoderLayer(nn.Module):
         y = self._ff_block(x1)
         return ops.add_layernorm(x1, y, self.norm2.weight, self.norm2.bias, self.eps)
 
+    def halo(self):
+        """frames of context on each side that the FFN convolutions of this block reach"""
+        if self.depthwise:
+            return (self.conv1[0].kernel_size[0] - 1) // 2 + (self.conv2[0].kernel_size[0] - 1) // 2
+        return (self.conv1.kernel_size[0] - 1) // 2 + (self.conv2.kernel_size[0] - 1) // 2
+
     def tc_capable(self, d):
         fsz = self.conv1[1].weight.shape[0] if self.depthwise else self.conv1.weight.shape[0]
         return self.compute_mode != "simt" and _tc_ok(d, fsz)
@@ -352,6 +358,10 @@ class VarianceConvolutionLayer(nn.Module):
 class VariancePredictor(nn.Module):
     """reference model.py:482-522."""
 
+    def halo(self):
+        """rows of context on each side that one output row depends on"""
+        return sum((layer.kernel_size - 1) // 2 for layer in self.layers)
+
     def __init__(self, nlayers, in_channels, filter_size, kernel_size, dropout, depthwise=False, cwt=False):
         super().__init__()
         if cwt:
@@ -420,8 +430,8 @@ class LengthRegulator(nn.Module):
             raise NotImplementedError("pad_to_multiple_of (only the FastDiff adaptor uses it)")
         self.pad_to_multiple_of = pad_to_multiple_of
 
-    def forward(self, x, durations, max_length=None):
-        return ops.length_regulate(x.contiguous(), durations.to(x.device), max_length)
+    def forward(self, x, durations, max_length=None, scan=None, frames=None):
+        return ops.length_regulate(x.contiguous(), durations.to(x.device), max_length, scan=scan, frames=frames)
 
 
 class VarianceAdaptor(nn.Module):
@@ -452,6 +462,16 @@ class VarianceAdaptor(nn.Module):
         self.encoders = nn.ModuleDict(encoders)
         self.frozen_components = []
 
+    @staticmethod
+    def _fit_forced(idx, width, enc):
+        """forced bucket indices cut / extended to `width` frames; frames past the given ones are PAD frames,
+        whose prediction is masked to 0, i.e. bucket(mean) (parity harness only)"""
+        if idx.shape[1] >= width:
+            return idx[:, :width].contiguous()
+        pad = int(torch.bucketize(torch.tensor(0.0 * enc.std + enc.mean), enc.bins.detach().cpu()))
+        ext = torch.full((idx.shape[0], width - idx.shape[1]), pad, device=idx.device, dtype=idx.dtype)
+        return torch.cat([idx, ext], 1).contiguous()
+
     def freeze(self, component):
         mod = self.duration_predictor if component == "duration" else self.encoders[component]
         for param in mod.parameters():
@@ -459,12 +479,15 @@ class VarianceAdaptor(nn.Module):
         self.frozen_components.append(component)
 
     def forward(self, x, src_mask, targets, inference=False, tf_ratio=1.0, oracles=[], force=None, control=None):
+        st = self.durations(x, src_mask, targets, inference=inference, tf_ratio=tf_ratio, force=force)
+        return self.expand(x, st, targets, inference=inference, oracles=oracles, force=force, control=control)
+
+    def durations(self, x, src_mask, targets, inference=False, tf_ratio=1.0, force=None):
+        """first half of the reference forward (model.py:249-309): duration prediction and the durations used"""
         force = force or {}
-        control = control or {}
         if any(level == "phone" for level in self.variance_levels):
             raise NotImplementedError("phone-level variances")
         duration_pred = self.duration_predictor(x, src_mask)
-        result = {}
         tf_val = np.random.uniform(0, 1) <= tf_ratio  # reference model.py:272
         if "duration_rounded" in force:
             duration_rounded = force["duration_rounded"].to(x.device)
@@ -472,17 +495,26 @@ class VarianceAdaptor(nn.Module):
             duration_rounded = targets["duration"].to(x.device)
         else:
             duration_rounded = ops.duration_round_guard(duration_pred, src_mask)
+        return {"duration_prediction": duration_pred, "duration_rounded": duration_rounded, "tf_val": tf_val}
 
-        x, tgt_mask = self.length_regulator(x, duration_rounded, self.max_length)
+    def expand(self, x, st, targets, inference=False, oracles=[], force=None, control=None, scan=None, frames=None):
+        """second half (model.py:311-341): LengthRegulator, then the frame-level variance encoders in sequence"""
+        force = force or {}
+        control = control or {}
+        result = {}
+        duration_pred, duration_rounded, tf_val = st["duration_prediction"], st["duration_rounded"], st["tf_val"]
+        x, tgt_mask = self.length_regulator(x, duration_rounded, self.max_length, scan=scan, frames=frames)
 
         out_val = torch.empty_like(x) if len(self.variances) else None
         for i, var in enumerate(self.variances):
             teacher = (not inference and tf_val) or var in oracles
             tgt = targets[f"variances_{var}"] if teacher else None
             forced = force.get("bucket_idx", {}).get(var)
+            if forced is not None:
+                forced = self._fit_forced(forced.to(x.device), x.shape[1], self.encoders[var])
             pred, idx = self.encoders[var].encode_(
                 x, tgt, tgt_mask, control.get(var, 1.0), acc=out_val, acc_init=(i == 0),
-                forced_idx=None if forced is None else forced.to(x.device),
+                forced_idx=forced,
                 want_idx=force.get("want_idx", False))
             result[f"variances_{var}"] = pred
             if idx is not None:

@@ -200,29 +200,46 @@ def duration_round_guard(log_dur, src_mask):
     return dur
 
 
-def length_regulate(x, durations, max_length):
-    """LengthRegulator.forward: x (B,Tp,d) any dtype, durations (B,Tp) int32/int64 ->
-    (out (B,L,d), mask (B,L) bool).  One host read-back (the maximum length)."""
-    if not (x.is_cuda and x.is_contiguous() and x.dim() == 3):
-        raise _lib.Lfs2Error("length_regulate: x must be a contiguous CUDA (B,Tp,d) tensor")
+def length_regulate_scan(durations, batch_first_shape):
+    """prefix sums of the durations: -> (cum (B,Tp) int64, lengths (B) int64, max_len (1) int64, all on the device)"""
     if durations.dtype not in (torch.int32, torch.int64):
         raise TypeError("length_regulate: durations must be int32 or int64")
     durations = durations.contiguous()
-    b, tp, d = x.shape
-    dev = x.device
+    b, tp = batch_first_shape
+    dev = durations.device
     cum = torch.empty(b, tp, device=dev, dtype=torch.int64)
     lengths = torch.empty(b, device=dev, dtype=torch.int64)
     mx = torch.empty(1, device=dev, dtype=torch.int64)
-    _launch("lfs2_length_regulate_scan", _p(durations), int(durations.dtype == torch.int64), _p(cum),
-                                                    _p(lengths), _p(mx), b, tp, _s())
-    longest = int(mx.item())  # the single device->host sync of the path
-    l = min(longest, int(max_length)) if max_length is not None else longest
-    out = torch.empty(b, l, d, device=dev, dtype=x.dtype)
-    mask = torch.empty(b, l, device=dev, dtype=torch.bool)
-    _launch("lfs2_length_regulate_scatter", _p(x), _p(cum), _p(lengths), _p(out), _p(mask), b, tp, l,
-                                                       d * x.element_size(), _s(),
+    _launch("lfs2_length_regulate_scan", _p(durations), int(durations.dtype == torch.int64), _p(cum), _p(lengths),
+            _p(mx), b, tp, _s())
+    return cum, lengths, mx
+
+
+def length_regulate_scatter(x, cum, lengths, l, cap):
+    """out (B,l,d), mask (B,l): frames below min(lengths[b], cap) copy their phone's row, the rest are PAD (+0)"""
+    b, tp, d = x.shape
+    out = torch.empty(b, l, d, device=x.device, dtype=x.dtype)
+    mask = torch.empty(b, l, device=x.device, dtype=torch.bool)
+    _launch("lfs2_length_regulate_scatter_ex", _p(x), _p(cum), _p(lengths), _p(out), _p(mask), b, tp, l, cap,
+            d * x.element_size(), _s(), tag="lfs2_length_regulate_scatter",
             nbytes=float(b * tp * (d * x.element_size() + 8) + b * l * (d * x.element_size() + 1)))
     return out, mask
+
+
+def length_regulate(x, durations, max_length, scan=None, frames=None):
+    """LengthRegulator.forward: x (B,Tp,d) any dtype, durations (B,Tp) int32/int64 ->
+    (out (B,L,d), mask (B,L) bool), L = min(longest, int(max_length)).  One host read-back (the maximum length).
+    scan = a precomputed length_regulate_scan result; frames = (l, cap) overrides the output length
+    (length-bucketed synthesis: l >= cap, frames in [cap, l) are PAD) and needs no read-back."""
+    if not (x.is_cuda and x.is_contiguous() and x.dim() == 3):
+        raise _lib.Lfs2Error("length_regulate: x must be a contiguous CUDA (B,Tp,d) tensor")
+    cum, lengths, mx = scan if scan is not None else length_regulate_scan(durations, x.shape[:2])
+    if frames is None:
+        longest = int(mx.item())  # the single device->host sync of the path
+        l = cap = min(longest, int(max_length)) if max_length is not None else longest
+    else:
+        l, cap = frames
+    return length_regulate_scatter(x, cum, lengths, l, cap)
 
 
 # ---------------------------------------------------------------------------------------------

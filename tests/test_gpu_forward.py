@@ -112,3 +112,61 @@ def test_deterministic_and_forward_teacher_forced():
     lo = O.loss(hp, ref, batch)
     for k in lo:
         assert abs(float(ls[k]) - float(lo[k])) < 1e-4 * max(1.0, abs(float(lo[k]))), k
+
+
+@pytest.mark.parametrize("preset,bsz,lo,hi,buckets", [("C2", 12, 20, 200, 3), ("C2", 9, 8, 120, 4), ("C1", 6, 20, 90, 2)])
+def test_length_bucketed_synthesis_matches_full_batch(preset, bsz, lo, hi, buckets):
+    """length-bucketed synthesis (sub-batches padded to their own longest utterance + the conv halo) must agree
+    with the full padded batch -- and with the oracle -- on every valid position; only positions masked by
+    tgt_mask (PAD frames) may differ (they come back as zeros)."""
+    model, sd, hp = build(preset, 11)
+    batch = synthetic.make_batch(bsz, lo, hi, seed=11)
+    with torch.no_grad():
+        full = model(batch, inference=True, force={"want_idx": True})
+        model.length_buckets = buckets
+        free = model(batch, inference=True, force={"want_idx": True})
+        # a ~1e-6 difference in a prediction can move it across one of the 255 bucket boundaries (SURVEY 0.6):
+        # count such flips on the free run, compare values with the full batch's decisions forced
+        flips = sum(int((free[f"_bucket_{v}"] != full[f"_bucket_{v}"])[~full["tgt_mask"]].sum()) for v in hp["variances"])
+        flips += int((free["duration_rounded"] != full["duration_rounded"]).sum())
+        total = sum(int((~full["tgt_mask"]).sum()) for _ in hp["variances"])
+        assert flips <= max(3, total // 200), (flips, total)  # same ~1e-3 rate as against the reference itself
+        force = {"duration_rounded": full["duration_rounded"],
+                 "bucket_idx": {v: full[f"_bucket_{v}"] for v in hp["variances"]}}
+        part = model(batch, inference=True, force=force)
+        model.length_buckets = 1
+    assert torch.equal(full["duration_rounded"], part["duration_rounded"])
+    assert torch.equal(full["tgt_mask"], part["tgt_mask"]) and torch.equal(full["src_mask"], part["src_mask"])
+    assert full["mel"].shape == part["mel"].shape
+    valid = ~full["tgt_mask"]
+    err = (full["mel"] - part["mel"])[valid].abs().max().item()
+    print(f"{preset} bucketed x{buckets}: max |mel diff| on valid frames = {err:.3e}, decision flips (free run) = {flips}")
+    assert err < 1e-4, err
+    for v in hp["variances"]:
+        assert (full[f"variances_{v}"] - part[f"variances_{v}"]).abs().max() < 1e-4
+    assert (full["duration_prediction"] - part["duration_prediction"]).abs().max() < 1e-4
+    # and against the oracle, with the oracle's discrete decisions forced (as in compare())
+    ref = O.forward(sd, hp, batch, inference=True)
+    force = {"duration_rounded": ref["duration_rounded"], "bucket_idx": {v: ref[f"_bucket_{v}"] for v in hp["variances"]}}
+    model.length_buckets = buckets
+    with torch.no_grad():
+        pr = model(batch, inference=True, force=force)
+    model.length_buckets = 1
+    assert torch.equal(pr["tgt_mask"].cpu(), ref["tgt_mask"])
+    vr = ~ref["tgt_mask"]
+    assert (pr["mel"].cpu() - ref["mel"])[vr].abs().max() < MEL_TOL
+
+
+def test_length_regulator_extra_frames_respect_the_cut():
+    """extra PAD frames are appended after the reference's L, also when an utterance is truncated at max_length"""
+    x = torch.randn(2, 4, 8)
+    dur = torch.tensor([[3, 9, 2, 1], [1, 1, 0, 0]], dtype=torch.int32)
+    from lightningfastspeech2_b200 import ops
+    for cap in (2756.25, 10.5):
+        ro, rm = O.length_regulator(x, dur, cap)
+        l = ro.shape[1]
+        scan = ops.length_regulate_scan(dur.to(DEV), x.shape[:2])
+        out, mask = ops.length_regulate(x.to(DEV), dur.to(DEV), cap, scan=scan, frames=(l + 5, l))
+        assert out.shape[1] == l + 5
+        assert torch.equal(out[:, :l].cpu(), ro) and torch.equal(mask[:, :l].cpu(), rm)
+        assert bool(mask[:, l:].all()) and float(out[:, l:].abs().max()) == 0.0
