@@ -412,6 +412,43 @@ def run_lfs2(args):
     else:
         frames_all, e2e_all = frames, e2e_frames
 
+    # ---- length-bucketed synthesis of the SAME batch (valid frames bit-identical, PAD frames zero) ----------
+    bucketed = []
+    for nb in args.buckets:
+        model.length_buckets = nb
+        for _ in range(3):
+            step_resident()
+        barrier()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        calls_b = _lib.CALLS
+        b0.record()
+        for _ in range(args.steps):
+            step_resident()
+        b1.record()
+        barrier()
+        ms_b = b0.elapsed_time(b1)
+        launches_b = _lib.CALLS - calls_b
+        step_e2e()
+        barrier()
+        b2, b3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b2.record()
+        fr_b = 0
+        for _ in range(args.steps):
+            fr_b += step_e2e()
+        b3.record()
+        barrier()
+        ms_be = b2.elapsed_time(b3)
+        if world > 1:
+            t = torch.tensor([ms_b, ms_be], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_b, ms_be = float(t[0]), float(t[1])
+            c = torch.tensor([fr_b], device=dev, dtype=torch.int64)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            fr_b = int(c[0])
+        bucketed.append({"length_buckets": nb, "ms_per_step": ms_b / args.steps, "gpu_launches": launches_b,
+                         "frames_all_ranks_e2e": fr_b, "ms_per_step_e2e": ms_be / args.steps})
+    model.length_buckets = 1
+
     train = None
     if args.train_steps > 0:
         del model
@@ -464,6 +501,15 @@ def run_lfs2(args):
             "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                              "sample": sample},
         }
+        if bucketed:
+            line["bucketed"] = {
+                "what": "same batch, same API call with model.length_buckets = n: length-sorted sub-batches padded to "
+                        "their own longest utterance + the conv halo; valid frames are bit-identical to the full padded "
+                        "batch (tests/test_gpu_forward.py), frames masked by tgt_mask come back as zeros",
+                "runs": [{"length_buckets": b["length_buckets"], "ms_per_step": b["ms_per_step"],
+                          "value": frames_all * args.steps / (b["ms_per_step"] * args.steps * 1e-3),
+                          "e2e_value": b["frames_all_ranks_e2e"] / (b["ms_per_step_e2e"] * args.steps * 1e-3),
+                          "gpu_launches": b["gpu_launches"], "unit": UNIT} for b in bucketed]}
         if train is not None:
             line["train"] = train
         print(json.dumps(line))
@@ -479,6 +525,7 @@ def main():
     ap.add_argument("--impl", default="lfs2", choices=["lfs2", "reference"])
     ap.add_argument("--ref-utts", type=int, default=8, help="utterances in the bounded CPU sample (first try)")
     ap.add_argument("--ref-utts-max", type=int, default=64, help="upper bound of the adaptive CPU sample")
+    ap.add_argument("--buckets", type=int, nargs="*", default=[2, 4], help="length_buckets values of the 'bucketed' runs")
     ap.add_argument("--train-steps", type=int, default=5, help="timed C4 train steps reported under 'train' (0 = skip)")
     ap.add_argument("--train-mode", default="fp32", choices=["simt", "fp32", "bf16"])
     ap.add_argument("--train-cpu-utts", type=int, default=2, help="utterances in the CPU train-step sample (0 = skip)")

@@ -1,6 +1,6 @@
 // Backward kernels of the mel-generation path (train-step config, SURVEY 8a "Backward notes"),
 // exact fp32 on CUDA cores.  They are the gradient ground truth on the device (the tensor-core
-// weight-gradient kernel in gemm_wgrad_tc.cu is checked against gemm_tn here) and serve every
+// weight-gradient GEMM in gemm_tc2.cu is checked against gemm_tn here) and serve every
 // shape.  Parameter gradients ACCUMULATE (+=) into caller-owned buffers -- the caller zeroes
 // them once per step (the fused AdamW kernel does) -- so a parameter used twice (speaker
 // projection at Tp and Tm) needs no extra pass; reductions over rows use fp32 atomics.
@@ -175,6 +175,7 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 //   xhat = (z - mean) * rstd ; g = dy * gamma ; dz = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ add)
 //   dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy     (register partials, one atomic per lane at the end)
 constexpr int kLnbMaxVec = 8;
+template <int NV>  // float4 column groups per lane: d <= 128 * NV
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ z, const float2* __restrict__ stats,
                      const float4* __restrict__ gamma, const float4* __restrict__ add, float4* __restrict__ dz,
@@ -182,32 +183,30 @@ layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ z
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  float4 gacc[kLnbMaxVec], bacc[kLnbMaxVec], gm[kLnbMaxVec];
+  float4 gacc[NV], bacc[NV];
 #pragma unroll
-  for (int i = 0; i < kLnbMaxVec; ++i) {
+  for (int i = 0; i < NV; ++i) {
     gacc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     bacc[i] = gacc[i];
-    int c = lane + 32 * i;
-    gm[i] = c < d4 ? gamma[c] : gacc[i];
   }
   const float inv_d = 1.f / (float)(d4 * 4);
   for (int row = warp; row < m; row += nwarps) {
     const float2 st = stats[row];
     const float mean = st.x, rstd = st.y;
-    float4 g[kLnbMaxVec], xh[kLnbMaxVec];
+    float4 g[NV], xh[NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnbMaxVec; ++i) {
-      int c = lane + 32 * i;
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
       if (c < d4) {
-        float4 dv = dy[(size_t)row * d4 + c], zv = z[(size_t)row * d4 + c];
+        const float4 dv = dy[(size_t)row * d4 + c], zv = z[(size_t)row * d4 + c], gm = __ldg(gamma + c);
         float4 x;
         x.x = (zv.x - mean) * rstd; x.y = (zv.y - mean) * rstd; x.z = (zv.z - mean) * rstd; x.w = (zv.w - mean) * rstd;
         gacc[i].x = fmaf(dv.x, x.x, gacc[i].x); gacc[i].y = fmaf(dv.y, x.y, gacc[i].y);
         gacc[i].z = fmaf(dv.z, x.z, gacc[i].z); gacc[i].w = fmaf(dv.w, x.w, gacc[i].w);
         bacc[i].x += dv.x; bacc[i].y += dv.y; bacc[i].z += dv.z; bacc[i].w += dv.w;
         float4 gg;
-        gg.x = dv.x * gm[i].x; gg.y = dv.y * gm[i].y; gg.z = dv.z * gm[i].z; gg.w = dv.w * gm[i].w;
+        gg.x = dv.x * gm.x; gg.y = dv.y * gm.y; gg.z = dv.z * gm.z; gg.w = dv.w * gm.w;
         s1 += (gg.x + gg.y) + (gg.z + gg.w);
         s2 += (gg.x * x.x + gg.y * x.y) + (gg.z * x.z + gg.w * x.w);
         g[i] = gg;
@@ -216,8 +215,8 @@ layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ z
     }
     const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
 #pragma unroll
-    for (int i = 0; i < kLnbMaxVec; ++i) {
-      int c = lane + 32 * i;
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
       if (c < d4) {
         float4 o;
         o.x = rstd * (g[i].x - c1 - xh[i].x * c2);
@@ -225,7 +224,7 @@ layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ z
         o.z = rstd * (g[i].z - c1 - xh[i].z * c2);
         o.w = rstd * (g[i].w - c1 - xh[i].w * c2);
         if (add) {
-          float4 e = add[(size_t)row * d4 + c];
+          const float4 e = add[(size_t)row * d4 + c];
           o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
         }
         dz[(size_t)row * d4 + c] = o;
@@ -238,7 +237,7 @@ layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ z
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
 #pragma unroll
-    for (int i = 0; i < kLnbMaxVec; ++i) {
+    for (int i = 0; i < NV; ++i) {
       if (32 * i < d4) {  // CTA-uniform
         const int c = lane + 32 * i;
         red[w][lane] = pass == 0 ? gacc[i] : bacc[i];
@@ -566,11 +565,19 @@ int lfs2_layernorm_bwd(const float* dy, const float* z, const float* stats, cons
                    ((reinterpret_cast<uintptr_t>(stats) & 7u) == 0),
                LFS2_ERR_INVALID_ARG, "layernorm_bwd: pointers must be 16-byte aligned");
   int blocks = ceil_div(m, 8 * 8);  // >= 8 rows per warp
-  if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
   if (blocks < 1) blocks = 1;
-  layernorm_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)dy, (const float4*)z,
-                                                               (const float2*)stats, (const float4*)gamma,
-                                                               (const float4*)add, (float4*)dz, dgamma, dbeta, m, d / 4);
+  const int nv = ceil_div(d / 4, 32);
+#define LFS2_LNB(NV)                                                                                            \
+  layernorm_bwd_kernel<NV><<<blocks, 256, 0, (cudaStream_t)stream>>>(                                           \
+      (const float4*)dy, (const float4*)z, (const float2*)stats, (const float4*)gamma, (const float4*)add,      \
+      (float4*)dz, dgamma, dbeta, m, d / 4)
+  if (nv <= 1) LFS2_LNB(1);
+  else if (nv <= 2) LFS2_LNB(2);
+  else if (nv <= 4) LFS2_LNB(4);
+  else if (nv <= 6) LFS2_LNB(6);
+  else LFS2_LNB(8);
+#undef LFS2_LNB
   LFS2_CHECK_LAUNCH("layernorm_bwd");
   return LFS2_OK;
 }

@@ -143,10 +143,16 @@ class ConformerEncoderLayer(nn.Module):
             w["c2"] = ops.split_bf16(p["c2_wp"])
         return w
 
+    def _conv_params(self):
+        cp = self.__dict__.get("_conv_param_list")
+        if cp is None:  # plain attribute (not a registered parameter list): the module tree is walked once
+            cp = list(self.conv1.parameters()) + list(self.conv2.parameters())
+            self.__dict__["_conv_param_list"] = cp
+        return cp
+
     def _packed_tc(self):
         sa = self.self_attn
-        params = [sa.in_proj_weight, sa.out_proj.weight] + list(self.conv1.parameters()) + list(self.conv2.parameters())
-        return self._pack_tc.get(params, self._build_pack_tc)
+        return self._pack_tc.get([sa.in_proj_weight, sa.out_proj.weight] + self._conv_params(), self._build_pack_tc)
 
     def _build_pack(self):
         p = {}
@@ -173,8 +179,7 @@ class ConformerEncoderLayer(nn.Module):
         return p
 
     def _packed(self):
-        params = [q for q in self.conv1.parameters()] + [q for q in self.conv2.parameters()]
-        return self._pack.get(params, self._build_pack)
+        return self._pack.get(self._conv_params(), self._build_pack)
 
     def forward(self, src, src_mask=None, src_key_padding_mask=None):
         if src_mask is not None:
@@ -330,7 +335,11 @@ class VarianceConvolutionLayer(nn.Module):
         (tensor-core path with the fused ReLU+LayerNorm epilogue only)."""
         _require_inference(self, self.layers[3].p, "VarianceConvolutionLayer")
         conv, ln = self.layers[0].module, self.layers[2]
-        p = self._pack.get(list(conv.parameters()), self._build_pack)
+        cp = self.__dict__.get("_conv_param_list")
+        if cp is None:
+            cp = list(conv.parameters())
+            self.__dict__["_conv_param_list"] = cp
+        p = self._pack.get(cp, self._build_pack)
         fsz = ln.weight.shape[0]
         if self.compute_mode != "simt" and _tc_ok(x.shape[-1], fsz):
             npass = _npass(self.compute_mode)

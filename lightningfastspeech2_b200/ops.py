@@ -54,7 +54,9 @@ def _p(t):
 
 
 def _s():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # raw handle of torch's current stream on the current device (the public torch.cuda.current_stream() builds
+    # a Stream object per call: ~5 us of host time on every launch)
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 def _chk(t, dtype, name, ndim=None):
@@ -260,6 +262,12 @@ class Planes:
         return self.hi.float() + self.lo.float()
 
 
+def _empty_planes(shape, dev):
+    """hi and lo planes carved out of ONE allocation (one caching-allocator call per launch instead of two)"""
+    buf = torch.empty((2,) + tuple(shape), device=dev, dtype=torch.bfloat16)
+    return Planes(buf[0], buf[1])
+
+
 def attach_planes(x, planes):
     """Remember the hi/lo planes a kernel already produced for the fp32 tensor x, so the next
     tensor-core GEMM does not have to split it again (module APIs stay tensor -> tensor)."""
@@ -289,8 +297,7 @@ def dwconv1d_planes(x, wt, bias, out="planes"):
         xf, xh, xl, shape, dev = x, None, None, x.shape, x.device
     b, t, d = shape
     of = torch.empty(shape, device=dev, dtype=torch.float32) if out == "f32" else None
-    po = Planes(torch.empty(shape, device=dev, dtype=torch.bfloat16),
-                torch.empty(shape, device=dev, dtype=torch.bfloat16)) if out == "planes" else None
+    po = _empty_planes(shape, dev) if out == "planes" else None
     _launch("lfs2_dwconv1d_planes", _p(xf), _p(xh), _p(xl), _p(wt), _p(bias), _p(of), _p(po.hi if po else None),
             _p(po.lo if po else None), b, t, d, wt.shape[0], _s(), tag="lfs2_dwconv1d",
             flops=2.0 * b * t * d * wt.shape[0], nbytes=8.0 * b * t * d)
@@ -307,10 +314,9 @@ def merge_planes(p):
 
 def split_bf16(x):
     _chk(x, torch.float32, "split_bf16 input")
-    hi = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    lo = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
-    _launch("lfs2_split_bf16", _p(x), _p(hi), _p(lo), x.numel(), _s(), nbytes=8.0 * x.numel())
-    return Planes(hi, lo)
+    pl = _empty_planes(x.shape, x.device)
+    _launch("lfs2_split_bf16", _p(x), _p(pl.hi), _p(pl.lo), x.numel(), _s(), nbytes=8.0 * x.numel())
+    return pl
 
 
 _IDENT = {}
@@ -348,8 +354,7 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
     out_shape = tuple(a.shape[:-1]) + (n,)
     dev = a.hi.device
     of = torch.empty(out_shape, device=dev, dtype=torch.float32) if out == "f32" else None
-    po = Planes(torch.empty(out_shape, device=dev, dtype=torch.bfloat16),
-                torch.empty(out_shape, device=dev, dtype=torch.bfloat16)) if out == "planes" else None
+    po = _empty_planes(out_shape, dev) if out == "planes" else None
     ident = None
     if residual is not None:
         if not isinstance(residual, Planes) or tuple(residual.shape) != out_shape:
@@ -377,8 +382,7 @@ def attention_tc(qkv, kpm, nhead, npass=3, want_f32=False, want_planes=True):
         _chk(kpm, torch.bool, "key_padding_mask", 2)
     dev = qkv.hi.device
     ctx = torch.empty(b, t, d, device=dev, dtype=torch.float32) if want_f32 else None
-    po = Planes(torch.empty(b, t, d, device=dev, dtype=torch.bfloat16),
-                torch.empty(b, t, d, device=dev, dtype=torch.bfloat16)) if want_planes else None
+    po = _empty_planes((b, t, d), dev) if want_planes else None
     ws = torch.empty(max(1, _lib.lib().lfs2_attention_tc_workspace_bytes(b)), device=dev, dtype=torch.uint8)
     fl = 0.0
     if PROFILE is not None:  # algorithmic flops: every query row x the utterance's VALID keys
