@@ -170,3 +170,67 @@ def test_length_regulator_extra_frames_respect_the_cut():
         assert out.shape[1] == l + 5
         assert torch.equal(out[:, :l].cpu(), ro) and torch.equal(mask[:, :l].cpu(), rm)
         assert bool(mask[:, l:].all()) and float(out[:, l:].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------- edge cases
+def _edge_model(mode="fp32", **over):
+    kw = dict(configs.PRESETS["C2"], **over)
+    hp = configs.resolve(kw)
+    st = {v: {"min": -3.0, "max": 3.0, "mean": 0.0, "std": 1.0} for v in hp["variances"]}
+    model = FastSpeech2(stats=st, phone2id={f"p{i}": i for i in range(80)}, num_workers=0, **kw)
+    sd = synthetic.fill_state_dict(model.state_dict(), seed=21)
+    model.load_state_dict(sd)
+    hp["stats"] = st
+    return model.eval().to(DEV).set_compute_mode(mode), sd, hp
+
+
+def _check_vs_oracle(model, sd, hp, batch, tol=MEL_TOL):
+    ref = O.forward(sd, hp, batch, inference=True)
+    r, fd, fb = compare(model, ref, batch, hp)
+    assert torch.equal(r["tgt_mask"].cpu(), ref["tgt_mask"]) and torch.equal(r["src_mask"].cpu(), ref["src_mask"])
+    assert r["mel"].shape == ref["mel"].shape
+    if ref["mel"].numel():
+        assert (r["mel"].cpu() - ref["mel"]).abs().max() < tol
+    return r, ref
+
+
+@pytest.mark.parametrize("mode", ["fp32", "simt"])
+def test_single_phone_and_tiny_batches(mode):
+    """B = 1, Tp = 1 .. 3 and a ragged 2-utterance batch with a 1-phone utterance"""
+    model, sd, hp = _edge_model(mode)
+    for bsz, lo, hi, seed in [(1, 1, 1, 1), (1, 3, 3, 2), (2, 1, 9, 3)]:
+        batch = synthetic.make_batch(bsz, lo, hi, seed=seed)
+        r, ref = _check_vs_oracle(model, sd, hp, batch)
+        assert r["mel"].shape[1] == int(ref["duration_rounded"].sum(1).max())
+
+
+def test_truncation_at_max_length():
+    """max_length caps the LengthRegulator output (model.py:355): frames beyond int(max_length*sr/hop) are cut and the
+    truncated utterance has an all-False mask row, exactly like the reference"""
+    model, sd, hp = _edge_model("fp32", max_length=0.5)  # cap = int(0.5 * 22050 / 256) = 43 frames
+    batch = synthetic.make_batch(3, 6, 30, seed=5)
+    r, ref = _check_vs_oracle(model, sd, hp, batch)
+    assert r["mel"].shape[1] == 43
+    assert int((~r["tgt_mask"]).sum(1).max()) == 43
+    # bucketed synthesis keeps the same cut
+    model.length_buckets = 2
+    with torch.no_grad():
+        rb = model(batch, inference=True, force={"duration_rounded": ref["duration_rounded"],
+                                                "bucket_idx": {v: ref[f"_bucket_{v}"] for v in hp["variances"]}})
+    model.length_buckets = 1
+    assert torch.equal(rb["tgt_mask"].cpu(), ref["tgt_mask"])
+    assert (rb["mel"].cpu() - ref["mel"])[~ref["tgt_mask"]].abs().max() < MEL_TOL
+
+
+def test_zero_duration_guard_end_to_end():
+    """a duration head that predicts ~0 frames everywhere triggers the reference's guard (model.py:306-309): every valid
+    phone gets duration 1"""
+    model, sd, hp = _edge_model("fp32")
+    k = "variance_adaptor.duration_predictor.linear.bias"
+    sd[k] = torch.full_like(sd[k], -3.0)
+    model.load_state_dict(sd)
+    batch = synthetic.make_batch(3, 4, 12, seed=8)
+    r, ref = _check_vs_oracle(model, sd, hp, batch)
+    valid = batch["phones"] != 0
+    assert torch.equal(r["duration_rounded"].cpu()[valid], torch.ones(int(valid.sum()), dtype=torch.int32))
+    assert r["mel"].shape[1] == int(valid.sum(1).max())
