@@ -301,16 +301,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     float l_run = 0.f;        // partial row sum over this half's keys
     const float c = p.scale_log2e;
     const uint8_t* mrow = p.kpm ? p.kpm + (size_t)b * p.t : nullptr;
-    // "key is masked" flag of this lane's key in the NEXT tile (prefetched one tile ahead)
-    auto key_masked = [&](int j) {
+    // "key is masked" byte of this lane's key in the NEXT tile, prefetched one tile ahead and only TESTED at
+    // the top of the next iteration, so the load's latency hides behind a whole tile of work
+    auto key_masked = [&](int j) -> uint32_t {
       const int k1 = j * kAK + half * 32 + lane;
-      return (k1 >= p.t) || (mrow && mrow[k1]);
+      uint32_t v = 1u;
+      if (k1 < p.t) v = mrow ? (uint32_t)mrow[k1] : 0u;
+      return v;
     };
-    bool next_masked = ntiles > 0 ? key_masked(0) : true;
+    uint32_t next_masked = ntiles > 0 ? key_masked(0) : 1u;
 
     for (int j = 0; j < ntiles; ++j) {
       const int sb = j % kSBufs;
-      const uint32_t mbits = __ballot_sync(0xffffffffu, next_masked);
+      const uint32_t mbits = __ballot_sync(0xffffffffu, next_masked != 0u);
       if (j + 1 < ntiles) next_masked = key_masked(j + 1);
       mbar_wait(&s_full[sb], (j / kSBufs) & 1);
       tc_fence_after();
@@ -425,7 +428,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
           tma_store_3d_a(&map_o_lo, sK + cc * 16384 + 8192, col_q + cc * 32, q0, b);
         }
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // smem may be released once it has been read
       }
     }
   }

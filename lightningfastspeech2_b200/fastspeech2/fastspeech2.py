@@ -396,6 +396,44 @@ class FastSpeech2(_Base):
 
     # -- length-bucketed synthesis ---------------------------------------------------
     length_buckets = 1
+    bucket_graphs = True   # replay each bucket's kernel sequence as a CUDA graph once its shape has been seen twice
+    max_graphs = 32
+
+    def _graphs_validate(self):
+        """graphs bake in the addresses of the packed weights: drop them when any parameter changed"""
+        sig = (ops.WEIGHTS_EPOCH, self.compute_mode, sum(p._version for p in self.parameters()),
+               sum(p.data_ptr() for p in self.parameters()) & 0xFFFFFFFFFFFF)
+        if getattr(self, "_graph_sig", None) != sig:
+            self._graphs = {}
+            self._graph_sig = sig
+
+    def _graphed(self, key, fn, inputs):
+        """Run fn(*inputs) eagerly the first time `key` is seen (this also builds the weight packs), capture it
+        into a CUDA graph the second time, replay afterwards: a bucket is ~90 short launches and the host
+        (Python + ctypes, ~30 us per launch) is otherwise the bottleneck.  Returns (outputs, replayed);
+        replayed outputs live in the graph's private pool and are overwritten by the next replay."""
+        cache = self.__dict__.setdefault("_graphs", {})
+        entry = cache.get(key)
+        if entry is None:
+            if len(cache) >= self.max_graphs:
+                cache.pop(next(iter(cache)))
+            cache[key] = {"seen": 1}
+            return fn(*inputs), False
+        if "graph" not in entry:
+            static_in = [torch.empty_like(x, device=self.device) for x in inputs]
+            for sbuf, x in zip(static_in, inputs):
+                sbuf.copy_(x, non_blocking=True)
+            calls0 = ops._lib.CALLS
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = fn(*static_in)
+            entry.update(graph=graph, static_in=static_in, out=out, launches=ops._lib.CALLS - calls0)
+            ops._lib.CALLS = calls0
+        for sbuf, x in zip(entry["static_in"], inputs):
+            sbuf.copy_(x, non_blocking=True)
+        entry["graph"].replay()
+        ops._lib.CALLS += entry["launches"]
+        return entry["out"], True
 
     def _halos(self):
         """(encoder side, decoder side): rows beyond an utterance's end that can still influence its valid
@@ -427,6 +465,9 @@ class FastSpeech2(_Base):
         cap = int(self.variance_adaptor.max_length)
         # phase 1, per bucket: encoder + durations (the encoder side may be cut at the bucket's longest utterance
         # + halo because the full tensor's end, where the reference zero-pads, is known: tp)
+        use_graphs = self.bucket_graphs and not force and not control and ops.PROFILE is None
+        if use_graphs:
+            self._graphs_validate()
         stages = []
         for g0 in range(0, bsz, per):
             idx = order[g0:g0 + per]
@@ -440,17 +481,36 @@ class FastSpeech2(_Base):
                     f["duration_rounded"] = force["duration_rounded"][it.to(force["duration_rounded"].device)][:, :tp_g]
                 if "bucket_idx" in force:
                     f["bucket_idx"] = {v: t[it.to(t.device)] for v, t in force["bucket_idx"].items()}
-            st = self._encode_stage(sub, True, f)
-            scan = ops.length_regulate_scan(st["duration_rounded"], st["enc"].shape[:2])
-            stages.append((idx, tp_g, f, st, scan))
+
+            def enc_fn(phones, speaker, f=f):
+                st = self._encode_stage({"phones": phones, "speaker": speaker}, True, f)
+                st["scan"] = ops.length_regulate_scan(st["duration_rounded"], st["enc"].shape[:2])
+                return st
+
+            # one graph per bucket ORDINAL: two buckets of equal shape must not share static output buffers, since
+            # every encoder stage of the batch runs before the first decoder stage
+            key = ("E", g0, len(idx), tp_g, self.compute_mode)
+            if use_graphs:
+                st, replayed = self._graphed(key, enc_fn, [sub["phones"], sub["speaker"]])
+            else:
+                st, replayed = enc_fn(sub["phones"], sub["speaker"]), False
+            stages.append((idx, tp_g, f, st, key if replayed else None))
         # the decoder side needs the global frame count first (where the reference's tensor ends): ONE read-back
-        longest = torch.cat([sc[2] for *_, sc in stages]).tolist()
+        longest = torch.cat([st["scan"][2] for _, _, _, st, _ in stages]).tolist()
         l_glob = min(max(longest), cap)
         parts = []
-        for (idx, tp_g, f, st, scan), lg in zip(stages, longest):
+        for (idx, tp_g, f, st, ekey), lg in zip(stages, longest):
             cap_g = min(lg, cap)
             frames = (min(cap_g + h_dec, l_glob), cap_g)
-            parts.append((idx, tp_g, self._decode_stage(st, None, True, f, control, scan=scan, frames=frames)))
+
+            def dec_fn(st=st, f=f, frames=frames):
+                return self._decode_stage(st, None, True, f, control, scan=st["scan"], frames=frames)
+
+            if ekey is not None:  # the encoder stage was a graph replay: its outputs live at fixed addresses
+                r, _ = self._graphed(("D", ekey, frames), dec_fn, [])
+            else:
+                r = dec_fn()
+            parts.append((idx, tp_g, r))
         n_mels = hp.n_mels
         out = {
             "mel": torch.zeros(bsz, l_glob, n_mels, device=dev),

@@ -234,3 +234,36 @@ def test_zero_duration_guard_end_to_end():
     valid = batch["phones"] != 0
     assert torch.equal(r["duration_rounded"].cpu()[valid], torch.ones(int(valid.sum()), dtype=torch.int32))
     assert r["mel"].shape[1] == int(valid.sum(1).max())
+
+
+def test_bucketed_cuda_graph_replay_is_identical_and_tracks_weight_updates():
+    """bucket kernel sequences are replayed as CUDA graphs from the 3rd call with the same shapes on; results must be
+    identical to the eager bucketed run, and a parameter update must invalidate the captured graphs"""
+    model, sd, hp = build("C2", 13)
+    batch = {k: v.to(DEV) for k, v in synthetic.make_batch(10, 16, 120, seed=13).items() if k in ("phones", "speaker")}
+    model.length_buckets = 3
+    with torch.no_grad():
+        model.bucket_graphs = False
+        eager = model(batch, inference=True)
+        model.bucket_graphs = True
+        outs = [model(batch, inference=True) for _ in range(4)]   # eager, capture+replay, replay, replay
+        assert any("graph" in e for e in model._graphs.values())
+        for o in outs:
+            assert torch.equal(o["mel"], eager["mel"]) and torch.equal(o["tgt_mask"], eager["tgt_mask"])
+            assert torch.equal(o["duration_rounded"], eager["duration_rounded"])
+        # another batch with the same shapes but different content goes through the same graphs
+        other = dict(batch)
+        other["speaker"] = batch["speaker"].flip(0).contiguous()
+        model.bucket_graphs = False
+        e2 = model(other, inference=True)
+        model.bucket_graphs = True
+        o2 = model(other, inference=True)
+        assert torch.equal(o2["duration_rounded"], e2["duration_rounded"])
+        if o2["mel"].shape == e2["mel"].shape:
+            assert torch.equal(o2["mel"], e2["mel"])
+        # weight update -> graphs dropped, new result follows the new weights
+        model.linear.bias.add_(1.0)
+        o3 = model(batch, inference=True)
+        valid = ~eager["tgt_mask"]
+        assert torch.allclose(o3["mel"][valid], eager["mel"][valid] + 1.0, atol=1e-5)
+    model.length_buckets = 1
