@@ -120,10 +120,10 @@ def dist_env():
     return rank, world, local
 
 
-def build_model(device):
+def build_model(device, preset=PRESET):
     from lightningfastspeech2_b200.fastspeech2.fastspeech2 import FastSpeech2
 
-    kw = configs.PRESETS[PRESET]
+    kw = configs.PRESETS[preset]
     hp = configs.resolve(kw)
     stats = {v: {"min": -3.0, "max": 3.0, "mean": 0.0, "std": 1.0} for v in hp["variances"]}
     model = FastSpeech2(stats=stats, phone2id={f"p{i}": i for i in range(80)}, num_workers=0, **kw)
@@ -307,6 +307,17 @@ def run_reference(args):
     value = frames * len(times) / total
     sample = (f"first {nutt} of the {BATCH} utterances of the C2 batch (seed 2) per step, padded to their own max "
               f"length; oracle/fs2_oracle.py (torch CPU conv1d/linear/softmax/layer_norm), no_grad")
+    train = None
+    if args.train_cpu_utts > 0:  # the train-step leg of the metric on the CPU port, same global batch, bounded sample
+        _, sd4, hp4 = build_train_model(None)
+        tb = train_batch(hp4, 0, 1)
+        secs, cfr = cpu_port_train_step(sd4, hp4, tb, args.train_cpu_utts)
+        frames4 = int(tb["duration"].sum())
+        train = {"metric": "ms/step (train)", "ms_per_step": secs * 1e3 * frames4 / max(cfr, 1), "impl": "reference",
+                 "cores": os.cpu_count(), "kind": "port", "valid_frames_per_step": frames4,
+                 "sample": f"first {args.train_cpu_utts} utterances of the C4 batch ({cfr} frames): one oracle train step "
+                           f"(forward + loss + autograd backward + AdamW/Noam) of {secs:.1f} s, scaled to {frames4} frames",
+                 "config": {"workload": TRAIN_WORKLOAD}}
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
@@ -316,6 +327,8 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if train is not None:
+        line["train"] = train
     print(json.dumps(line))
 
 
@@ -476,9 +489,45 @@ def run_lfs2(args):
                          "frames_all_ranks_e2e": fr_b, "ms_per_step_e2e": ms_be / args.steps})
     model.length_buckets = 1
 
+    # ---- BASELINE.json configs[2] ("C3"): 76 M-parameter model, bf16 synthesis, 32 utterances per GPU ----------
+    c3 = None
+    if args.c3_steps > 0:
+        del model
+        torch.cuda.empty_cache()
+        m3, _, _ = build_model(dev, preset="C3")
+        m3.set_compute_mode("bf16")
+        b3 = {k: v.to(dev) for k, v in synthetic.make_batch(32, MIN_LEN, MAX_LEN, seed=200 + rank).items()
+              if k in ("phones", "speaker")}
+        with torch.no_grad():
+            for _ in range(3):
+                r3 = m3(b3, inference=True)
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record()
+            for _ in range(args.c3_steps):
+                r3 = m3(b3, inference=True)
+            c1.record()
+            barrier()
+        ms3 = c0.elapsed_time(c1) / args.c3_steps
+        fr3 = int((~r3["tgt_mask"]).sum())
+        if world > 1:
+            t = torch.tensor([ms3], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms3 = float(t[0])
+            c = torch.tensor([fr3], device=dev, dtype=torch.int64)
+            dist.all_reduce(c, op=dist.ReduceOp.SUM)
+            fr3 = int(c[0])
+        c3 = {"workload": "C3: 76M-parameter model (d=768, head_dim 384, 4 enc + 5 dec FFTBlocks, 3 variances), bf16 mode, "
+                          "32 utterances per GPU, phoneme len U[32,512] (BASELINE.json configs[2]: 256 utterances over 8 GPUs)",
+              "value": fr3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3, "valid_frames_per_step": fr3,
+              "mel_shape_rank0": list(r3["mel"].shape), "steps": args.c3_steps}
+        del m3, r3
+        torch.cuda.empty_cache()
+        model = None
+
     train = None
     if args.train_steps > 0:
-        del model
+        model = None
         torch.cuda.empty_cache()
         train = measure_train(args, dev, rank, world, barrier)
 
@@ -547,6 +596,8 @@ def run_lfs2(args):
                           "value": frames_all * args.steps / (b["ms_per_step"] * args.steps * 1e-3),
                           "e2e_value": b["frames_all_ranks_e2e"] / (b["ms_per_step_e2e"] * args.steps * 1e-3),
                           "gpu_launches": b["gpu_launches"], "unit": UNIT} for b in bucketed]}
+        if c3 is not None:
+            line["c3_bf16"] = c3
         if train is not None:
             line["train"] = train
         print(json.dumps(line))
@@ -560,9 +611,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lfs2", choices=["lfs2", "reference"])
-    ap.add_argument("--ref-utts", type=int, default=8, help="utterances in the bounded CPU sample (first try)")
+    ap.add_argument("--ref-utts", type=int, default=16, help="utterances in the bounded CPU sample (first try)")
     ap.add_argument("--ref-utts-max", type=int, default=64, help="upper bound of the adaptive CPU sample")
     ap.add_argument("--buckets", type=int, nargs="*", default=[2, 4], help="length_buckets values of the 'bucketed' runs")
+    ap.add_argument("--c3-steps", type=int, default=3, help="timed C3 (76M, bf16) synthesis steps under 'c3_bf16' (0 = skip)")
     ap.add_argument("--train-steps", type=int, default=5, help="timed C4 train steps reported under 'train' (0 = skip)")
     ap.add_argument("--train-mode", default="fp32", choices=["simt", "fp32", "bf16"])
     ap.add_argument("--train-cpu-utts", type=int, default=2, help="utterances in the CPU train-step sample (0 = skip)")
