@@ -59,6 +59,8 @@ class Engine:
     def _planes(self, x):
         """hi/lo planes of an fp32 tensor, split once and remembered on the tensor (activations are used by
         the forward GEMM and again by the weight-gradient GEMM)"""
+        if isinstance(x, ops.Planes):
+            return x
         p = getattr(x, "_lfs2_planes", None)
         if p is None:
             p = ops.split_bf16(x.contiguous())
@@ -69,7 +71,7 @@ class Engine:
     def attention_fwd(self, qkv, kpm, nhead, p_drop=0.0):
         """-> (ctx, saved)"""
         d = qkv.shape[-1] // 3
-        if self.tc and (d // nhead) % 32 == 0:
+        if isinstance(qkv, ops.Planes) or (self.tc and (d // nhead) % 32 == 0):
             drop = None
             if p_drop > 0:
                 self.site += 1
@@ -89,12 +91,20 @@ class Engine:
                                          drop=saved["drop"])
         return ops.attention_bwd(qkv, ctx, dctx, saved["lse"], kpm, nhead)
 
-    def linear(self, x, w, b, relu=False, tag=None):
-        """x (..., k) . w (n, k)^T + b"""
+    def linear(self, x, w, b, relu=False, tag=None, planes_out=False):
+        """x (..., k) . w (n, k)^T + b.  planes_out: on the tensor-core path return bf16 hi/lo Planes instead of an
+        fp32 tensor (for results that only feed further tensor-core kernels: no fp32 copy, no split pass)."""
         n, k = w.shape
         if self.tc and k % 32 == 0 and n % 16 == 0:
-            return ops.gemm_tc(self._planes(x), self._planes(w), b, relu=relu, npass=self.npass, tag=tag)
-        return ops.linear(x, w, b, relu=relu, tag=tag)
+            return ops.gemm_tc(self._planes(x), self._planes(w), b, relu=relu, npass=self.npass, tag=tag,
+                               out="planes" if planes_out else "f32")
+        return ops.linear(x if not isinstance(x, ops.Planes) else ops.merge_planes(x), w, b, relu=relu, tag=tag)
+
+    def dwconv(self, x, wt, bias):
+        """depthwise conv whose result only feeds GEMMs: Planes on the tensor-core path, fp32 otherwise"""
+        if self.tc and x.shape[-1] % 32 == 0:
+            return ops.dwconv1d_planes(x, wt, bias, out="planes")
+        return ops.dwconv1d(x, wt, bias)
 
     def dgrad(self, dy, w, tag=None):
         """dy (..., n) . w (n, k) -> (..., k): the layer-input gradient of y = x . w^T"""
@@ -106,7 +116,7 @@ class Engine:
         if self.tc and ops.wgrad_tc_ok(n, k):
             ops.gemm_wgrad_tc_(dw, self._planes(dy), self._planes(x), npass=self.npass, tag=tag)
         else:
-            ops.gemm_tn_(dw, dy, x)
+            ops.gemm_tn_(dw, dy, ops.merge_planes(x) if isinstance(x, ops.Planes) else x)
         if db is not None:
             ops.colsum_(db, dy)
 
@@ -132,14 +142,16 @@ def fft_fwd(L, E, x, kpm):
     if gc.kernel_size[0] != 1:
         raise NotImplementedError("grouped conv2.0 with kernel > 1")
     s = {"x": x, "kpm": kpm}
-    s["qkv"] = E.linear(x, sa.in_proj_weight, sa.in_proj_bias, tag="qkv_gemm")
+    d_model = x.shape[-1]
+    qkv_planes = E.tc and (d_model // L.nhead) % 32 == 0   # consumed only by the attention GEMMs and the wgrad
+    s["qkv"] = E.linear(x, sa.in_proj_weight, sa.in_proj_bias, tag="qkv_gemm", planes_out=qkv_planes)
     s["ctx"], s["att"] = E.attention_fwd(s["qkv"], kpm, L.nhead, p)
     a = E.linear(s["ctx"], sa.out_proj.weight, sa.out_proj.bias, tag="out_proj_gemm")
     s["drop1"] = E.dropout_(a, p)                                         # dropout1 (model.py:114)
     x1, s["z1"], s["st1"] = ops.add_layernorm_train(x, a, L.norm1.weight, L.norm1.bias, L.eps)
     s["x1"] = x1
     s["dw_wt"] = ops.transpose(_dwmat(dwc.weight))                        # (k, d)
-    s["u"] = ops.dwconv1d(x1, s["dw_wt"], dwc.bias)
+    s["u"] = E.dwconv(x1, s["dw_wt"], dwc.bias)
     s["v"] = E.linear(s["u"], _mat(pw.weight), pw.bias, relu=True, tag="ffn1_gemm")
     s["dropv"] = E.dropout_(s["v"], p)                                    # dropout after ReLU (model.py:120)
     s["w_eff"], b_eff = ops.fold_pw(_mat(pw2.weight), _mat(gc.weight), gc.bias, pw2.bias)
@@ -200,7 +212,7 @@ def vp_fwd(P, E, x, mask):
             raise NotImplementedError("training dense-conv variance predictors")
         conv, ln = layer.layers[0].module, layer.layers[2]
         dw_wt = ops.transpose(_dwmat(conv[0].weight))
-        u = ops.dwconv1d(z, dw_wt, conv[0].bias)
+        u = E.dwconv(z, dw_wt, conv[0].bias)
         h = E.linear(u, _mat(conv[1].weight), conv[1].bias, relu=True, tag="predictor_pw_gemm")
         zo, _, st = ops.add_layernorm_train(h, None, ln.weight, ln.bias, ln.eps)
         layers.append({"x": z, "u": u, "h": h, "st": st, "dw_wt": dw_wt, "drop": E.dropout_(zo, layer.layers[3].p)})

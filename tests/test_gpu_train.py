@@ -401,7 +401,7 @@ def test_train_step_with_dropout_directional_derivative():
         for p, gi in zip(params, g):
             p.add_(gi, alpha=eta)
     fd = (vals[0] - vals[1]) / (2 * eta)
-    print(f"dropout train step: <g,g> = {gn2:.5e}, finite difference = {fd:.5e}, loss = {float(l0):.4f}")
+    print(f"dropout train step: <g,g> = {gn2:.5e}, finite difference = {fd:.5e}, loss = {float(l0.detach()):.4f}")
     assert abs(fd - gn2) <= 0.05 * gn2, (fd, gn2)
     # dropout is active: two different seeds give different losses, the same seed the same loss
     torch.manual_seed(1)
@@ -410,7 +410,8 @@ def test_train_step_with_dropout_directional_derivative():
     b2 = float(model.loss(model(batch), batch)["total"].detach())
     torch.manual_seed(1)
     a2 = float(model.loss(model(batch), batch)["total"].detach())
-    assert a == a2 and a != b2
+    # (loss reductions use fp32 atomics: equal up to summation order)
+    assert abs(a - a2) < 1e-5 and abs(a - b2) > 1e-4, (a, a2, b2)
 
 
 # ------------------------------------------------------------- tcgen05 general GEMM (gemm_tc2)
