@@ -271,11 +271,17 @@ def measure_train(args, dev, rank, world, barrier):
                       "parallelism": f"data-parallel x{world}, one NCCL all-reduce of the flat fp32 gradient buffer"},
            "kernel_shares": {k: round(v["ms"] / total_ms, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]}}
     if world == 1 and args.train_cpu_utts > 0:
-        secs, cfr = cpu_port_train_step(sd, hp, batch, args.train_cpu_utts)
+        nutt = args.train_cpu_utts  # grow the sample until one oracle train step takes ~8 s of CPU work
+        while True:
+            secs, cfr = cpu_port_train_step(sd, hp, batch, nutt)
+            if secs >= 8.0 or nutt >= 32:
+                break
+            nutt = min(32, nutt * (4 if secs < 1.5 else 2))
         out["cpu_baseline"] = {"value": secs * 1e3 * frames / max(cfr, 1), "unit": "ms/step (extrapolated by frames)",
                                "cores": os.cpu_count(), "kind": "port",
-                               "sample": f"first {args.train_cpu_utts} utterances of the batch ({cfr} frames), one "
-                                         f"oracle train step of {secs:.1f} s, scaled to {frames} frames"}
+                               "sample": f"first {nutt} utterances of the batch ({cfr} frames), one oracle train step "
+                                         f"(forward + loss + autograd backward + AdamW/Noam) of {secs:.1f} s, scaled to "
+                                         f"{frames} frames"}
     return out
 
 
@@ -545,6 +551,10 @@ def run_lfs2(args):
             peak, unit = pk["hbm"], "GB/s"
         roofline = {"kernel": top_name, "bound": "hbm" if top["bound"] == "hbm" else "tensor",
                     "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
+                    # fp32-parity mode issues 3 bf16 MMA passes (hi.hi + lo.hi + hi.lo) per algorithmic product:
+                    # `achieved`/`frac` count each product ONCE; the tensor pipe executes 3x that
+                    "mma_passes": 3 if top["bound"] == "tensor" else None,
+                    "issued_frac": (3 * achieved / peak) if top["bound"] == "tensor" else None,
                     "traffic": ncu_traffic(top_name), "peak_source": pk["src"], "us_per_launch": per_launch_s * 1e6,
                     "share_of_step": top["ms"] / total_ms,
                     "kernel_shares": {k: round(v["ms"] / total_ms, 4) for k, v in sorted(
