@@ -558,7 +558,16 @@ def run_lfs2(args):
                     "traffic": ncu_traffic(top_name), "peak_source": pk["src"], "us_per_launch": per_launch_s * 1e6,
                     "share_of_step": top["ms"] / total_ms,
                     "kernel_shares": {k: round(v["ms"] / total_ms, 4) for k, v in sorted(
-                        prof.items(), key=lambda kv: -kv[1]["ms"])}}
+                        prof.items(), key=lambda kv: -kv[1]["ms"])},
+                    # every kernel of the step against ITS roofline (algorithmic bytes / flops of SURVEY 8d, CUDA
+                    # events on the launching stream): frac = max(bytes/t / HBM peak, flops/t / tensor peak)
+                    "per_kernel": {k: {"launches": v["launches"], "ms": round(v["ms"], 4), "bound": v["bound"],
+                                       "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else 0.0,
+                                       "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["ms"] > 0 else 0.0,
+                                       "frac": round(max(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm"],
+                                                         v["flops"] / (v["ms"] * 1e-3) / 1e12 / pk["tensor"]), 3)
+                                       if v["ms"] > 0 else 0.0}
+                                   for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]}}
         # bounded CPU sample of the same workload: grow the sub-batch until one run takes >= ~10 s of CPU work
         nutt = max(1, args.ref_utts)
         while True:
