@@ -484,21 +484,9 @@ def attention_bwd(qkv, ctx, dctx, lse, kpm, nhead):
 
 def length_regulate_train(x, durations, max_length):
     """length_regulate that also returns the prefix sums its backward needs"""
-    durations = durations.contiguous()
-    b, tp, d = x.shape
-    dev = x.device
-    cum = torch.empty(b, tp, device=dev, dtype=torch.int64)
-    lengths = torch.empty(b, device=dev, dtype=torch.int64)
-    mx = torch.empty(1, device=dev, dtype=torch.int64)
-    _launch("lfs2_length_regulate_scan", _p(durations), int(durations.dtype == torch.int64), _p(cum), _p(lengths),
-            _p(mx), b, tp, _s())
-    longest = int(mx.item())
-    l = min(longest, int(max_length)) if max_length is not None else longest
-    out = torch.empty(b, l, d, device=dev, dtype=x.dtype)
-    mask = torch.empty(b, l, device=dev, dtype=torch.bool)
-    _launch("lfs2_length_regulate_scatter", _p(x), _p(cum), _p(lengths), _p(out), _p(mask), b, tp, l,
-            d * x.element_size(), _s())
-    return out, mask, cum
+    scan = length_regulate_scan(durations, x.shape[:2])
+    out, mask = length_regulate(x, durations, max_length, scan=scan)
+    return out, mask, scan[0]
 
 
 def length_regulate_bwd(dout, cum):
