@@ -339,10 +339,10 @@ class FastSpeech2(_Base):
             return self._forward_train(targets)
         if inference and self.length_buckets > 1 and targets["phones"].shape[0] > 1:
             return self._forward_bucketed(targets, control, force)
-        st = self._encode_stage(targets, inference, force)
+        st = self._encode_stage(targets, inference, force, control)
         return self._decode_stage(st, targets, inference, force, control)
 
-    def _encode_stage(self, targets, inference, force):
+    def _encode_stage(self, targets, inference, force, control=None):
         """front end, encoder, duration predictor and the durations used (reference :639-686 + model.py:249-309)"""
         dev, hp = self.device, self.hparams
         phones = targets["phones"].to(dev, non_blocking=True).contiguous()
@@ -354,8 +354,9 @@ class FastSpeech2(_Base):
                                       "enabled for the train path, or .eval())")
         output, src_mask = ops.embed_pe_spk(phones, self.phone_embedding.weight, pe, spk)
         output = self.encoder(output, src_key_padding_mask=src_mask)
-        st = self.variance_adaptor.durations(output, src_mask, targets, inference=inference, force=force)
-        st.update(enc=output, src_mask=src_mask, spk=spk)
+        st = self.variance_adaptor.durations(output, src_mask, targets, inference=inference, force=force,
+                                             control=control)
+        st.update(enc=st["x_phone"], src_mask=src_mask, spk=spk)
         return st
 
     def _decode_stage(self, st, targets, inference, force, control, scan=None, frames=None):
@@ -483,7 +484,7 @@ class FastSpeech2(_Base):
                     f["bucket_idx"] = {v: t[it.to(t.device)] for v, t in force["bucket_idx"].items()}
 
             def enc_fn(phones, speaker, f=f):
-                st = self._encode_stage({"phones": phones, "speaker": speaker}, True, f)
+                st = self._encode_stage({"phones": phones, "speaker": speaker}, True, f, control)
                 st["scan"] = ops.length_regulate_scan(st["duration_rounded"], st["enc"].shape[:2])
                 return st
 

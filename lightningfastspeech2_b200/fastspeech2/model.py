@@ -488,43 +488,75 @@ class VarianceAdaptor(nn.Module):
         self.frozen_components.append(component)
 
     def forward(self, x, src_mask, targets, inference=False, tf_ratio=1.0, oracles=[], force=None, control=None):
-        st = self.durations(x, src_mask, targets, inference=inference, tf_ratio=tf_ratio, force=force)
-        return self.expand(x, st, targets, inference=inference, oracles=oracles, force=force, control=control)
+        st = self.durations(x, src_mask, targets, inference=inference, tf_ratio=tf_ratio, force=force, control=control,
+                            oracles=oracles)
+        return self.expand(st["x_phone"], st, targets, inference=inference, oracles=oracles, force=force,
+                           control=control)
 
-    def durations(self, x, src_mask, targets, inference=False, tf_ratio=1.0, force=None):
+    def durations(self, x, src_mask, targets, inference=False, tf_ratio=1.0, force=None, control=None, oracles=[]):
         """first half of the reference forward (model.py:249-309): duration prediction and the durations used"""
         force = force or {}
-        if any(level == "phone" for level in self.variance_levels):
-            raise NotImplementedError("phone-level variances")
+        control = control or {}
         duration_pred = self.duration_predictor(x, src_mask)
         tf_val = np.random.uniform(0, 1) <= tf_ratio  # reference model.py:272
+        # phone-level variances act on the encoder output before the LengthRegulator (model.py:277-294)
+        result, out_val = {}, None
+        phone_vars = [(i, v) for i, v in enumerate(self.variances) if self.variance_levels[i] == "phone"]
+        if phone_vars:
+            x = x.clone() if not isinstance(x, ops.Planes) else ops.merge_planes(x)  # duration_pred read the original
+            out_val = torch.empty_like(x)
+            for n, (i, var) in enumerate(phone_vars):
+                teacher = (not inference and tf_val) or var in oracles
+                forced = force.get("bucket_idx", {}).get(var)
+                pred, idx = self.encoders[var].encode_(
+                    x, targets[f"variances_{var}"] if teacher else None, src_mask, control.get(var, 1.0), acc=out_val,
+                    acc_init=(n == 0), forced_idx=None if forced is None else forced.to(x.device).contiguous(),
+                    want_idx=force.get("want_idx", False))
+                result[f"variances_{var}"] = pred
+                if idx is not None:
+                    result[f"_bucket_{var}"] = idx
         if "duration_rounded" in force:
             duration_rounded = force["duration_rounded"].to(x.device)
         elif not inference:
             duration_rounded = targets["duration"].to(x.device)
         else:
             duration_rounded = ops.duration_round_guard(duration_pred, src_mask)
-        return {"duration_prediction": duration_pred, "duration_rounded": duration_rounded, "tf_val": tf_val}
+        return {"duration_prediction": duration_pred, "duration_rounded": duration_rounded, "tf_val": tf_val,
+                "x_phone": x, "out_phone": out_val, "phone_result": result}
 
     def expand(self, x, st, targets, inference=False, oracles=[], force=None, control=None, scan=None, frames=None):
         """second half (model.py:311-341): LengthRegulator, then the frame-level variance encoders in sequence"""
         force = force or {}
         control = control or {}
-        result = {}
+        result = dict(st.get("phone_result") or {})
         duration_pred, duration_rounded, tf_val = st["duration_prediction"], st["duration_rounded"], st["tf_val"]
-        x, tgt_mask = self.length_regulator(x, duration_rounded, self.max_length, scan=scan, frames=frames)
-
-        out_val = torch.empty_like(x) if len(self.variances) else None
+        if scan is None:
+            scan = ops.length_regulate_scan(duration_rounded.to(x.device), x.shape[:2])
+        if frames is None:
+            longest = int(scan[2].item())  # the single device->host sync of the path
+            l = min(longest, int(self.max_length)) if self.max_length is not None else longest
+            frames = (l, l)
+        x_in = x
+        x, tgt_mask = self.length_regulator(x_in, duration_rounded, self.max_length, scan=scan, frames=frames)
+        have_acc = st.get("out_phone") is not None
+        if have_acc:  # the summed phone-level embeddings are length-regulated too (model.py:312-313)
+            out_val, _ = self.length_regulator(st["out_phone"], duration_rounded, self.max_length, scan=scan, frames=frames)
+        else:
+            out_val = torch.empty_like(x) if len(self.variances) else None
+        nframe = 0
         for i, var in enumerate(self.variances):
+            if self.variance_levels[i] != "frame":
+                continue
             teacher = (not inference and tf_val) or var in oracles
             tgt = targets[f"variances_{var}"] if teacher else None
             forced = force.get("bucket_idx", {}).get(var)
             if forced is not None:
                 forced = self._fit_forced(forced.to(x.device), x.shape[1], self.encoders[var])
             pred, idx = self.encoders[var].encode_(
-                x, tgt, tgt_mask, control.get(var, 1.0), acc=out_val, acc_init=(i == 0),
+                x, tgt, tgt_mask, control.get(var, 1.0), acc=out_val, acc_init=(nframe == 0 and not have_acc),
                 forced_idx=forced,
                 want_idx=force.get("want_idx", False))
+            nframe += 1
             result[f"variances_{var}"] = pred
             if idx is not None:
                 result[f"_bucket_{var}"] = idx

@@ -243,8 +243,6 @@ def forward_train(M, targets):
     dev = M.device
     E = Engine(M.compute_mode)
     va = M.variance_adaptor
-    if any(level == "phone" for level in va.variance_levels):
-        raise NotImplementedError("phone-level variances")
     phones = targets["phones"].to(dev, non_blocking=True).contiguous()
     dvec = targets["speaker"].to(dev, dtype=torch.float32, non_blocking=True).contiguous()
     pe = M.positional_encoding.pe
@@ -269,11 +267,23 @@ def forward_train(M, targets):
 
     dur_pred, S["dp"] = vp_fwd(va.duration_predictor, E, x, src_mask)
     np.random.uniform(0, 1)  # the reference draws the teacher-forcing coin here (model.py:272); tf_ratio = 1
+    result = {}
+    S["phone_vars"] = []
+    for i, var in enumerate(va.variances):  # phone-level variances act on the encoder output (model.py:277-294)
+        if va.variance_levels[i] != "phone":
+            continue
+        enc = va.encoders[var]
+        pred, s_vp = vp_fwd(enc.predictor, E, x, src_mask)
+        tgt = targets[f"variances_{var}"].to(dev, dtype=torch.float32)[:, : x.shape[1]].contiguous()
+        x, idx = ops.bucket_embed_add_oop(x, tgt, enc.std, enc.mean, enc.bins, enc.embedding.weight)
+        S["phone_vars"].append((var, s_vp, idx))
+        result[f"variances_{var}"] = pred
     duration = targets["duration"].to(dev)
     x, tgt_mask, S["cum"] = ops.length_regulate_train(x, duration, va.max_length)
     S["vars"] = []
-    result = {}
-    for var in va.variances:
+    for i, var in enumerate(va.variances):
+        if va.variance_levels[i] != "frame":
+            continue
         enc = va.encoders[var]
         pred, s_vp = vp_fwd(enc.predictor, E, x, tgt_mask)
         tgt = targets[f"variances_{var}"].to(dev, dtype=torch.float32)[:, : x.shape[1]].contiguous()
@@ -328,6 +338,12 @@ def backward_train(M, S, dmel, ddur, dvars):
         if g is not None:
             ops.add_(dx, vp_bwd(enc.predictor, E, s_vp, g))
     dx = ops.length_regulate_bwd(dx, S["cum"])
+    for var, s_vp, idx in reversed(S["phone_vars"]):
+        enc = va.encoders[var]
+        ops.embedding_bwd_(grad_of(enc.embedding.weight), dx, idx)
+        g = dvars.get(var)
+        if g is not None:
+            ops.add_(dx, vp_bwd(enc.predictor, E, s_vp, g))
     if ddur is not None:
         ops.add_(dx, vp_bwd(va.duration_predictor, E, S["dp"], ddur))
     for L, s in zip(reversed(list(M.encoder.layers)), reversed(S["enc"])):

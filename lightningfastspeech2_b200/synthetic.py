@@ -99,7 +99,7 @@ def make_batch(batch_size, min_len, max_len, seed=0, vocab=80, pad_to=None):
     }
 
 
-def add_train_targets(batch, variances, seed=0, n_mels=80, dur_lo=1, dur_hi=9):
+def add_train_targets(batch, variances, seed=0, n_mels=80, dur_lo=1, dur_hi=9, levels=None):
     """Teacher-forcing targets for the train-step config:
     duration ~ U{dur_lo..dur_hi} on valid phones, Tm = max sum(duration) exactly
     (HEAD quirk 6), mel ~ N(0,1), variances_* ~ N(0,1)."""
@@ -112,6 +112,8 @@ def add_train_targets(batch, variances, seed=0, n_mels=80, dur_lo=1, dur_hi=9):
     out = dict(batch)
     out["duration"] = torch.from_numpy(dur.astype(np.int64))
     out["mel"] = torch.from_numpy(g.standard_normal((b, tm, n_mels)).astype(np.float32))
-    for v in variances:
-        out[f"variances_{v}"] = torch.from_numpy(g.standard_normal((b, tm)).astype(np.float32))
+    for i, v in enumerate(variances):
+        frame = levels is None or levels[i] == "frame"
+        shape = (b, tm) if frame else phones.shape  # phone-level targets are per phoneme (datasets.py:592-601)
+        out[f"variances_{v}"] = torch.from_numpy(g.standard_normal(shape).astype(np.float32))
     return out

@@ -215,25 +215,10 @@ def forward(sd, hp, batch, inference=False, dtype=torch.float32, force=None, con
     va = "variance_adaptor."
     log_dur = variance_predictor(x, src_mask, sd, va + "duration_predictor.", hp["duration_nlayers"],
                                  hp["duration_depthwise_conv"], dtype)
-    if "phone" in hp["variance_levels"]:
-        raise NotImplementedError("phone-level variances")
-    if "duration_rounded" in force:
-        dur = force["duration_rounded"]
-    elif not inference:
-        dur = batch["duration"]
-    else:
-        dur = round_durations(log_dur, src_mask)
-
-    from_cfg = hp["max_length"] * hp["sampling_rate"] / hp["hop_length"]
-    x, tgt_mask = length_regulator(x, dur, from_cfg)
-    res["_lr"] = x
-
-    out_val = None
-    for i, var in enumerate(hp["variances"]):
-        if hp["variance_transforms"][i] == "cwt":
-            raise NotImplementedError("cwt")
+    def encode(i, var, x, mask, out_val):
+        """VarianceEncoder.forward + the `x = x + out` of the adaptor (model.py:409-441, 284-294 / 315-333)"""
         pre = va + f"encoders.{var}."
-        pred = variance_predictor(x, tgt_mask, sd, pre + "predictor.", hp["variance_nlayers"][i],
+        pred = variance_predictor(x, mask, sd, pre + "predictor.", hp["variance_nlayers"][i],
                                   hp["variance_depthwise_conv"], dtype)
         bins = sd[pre + "bins"].to(dtype)
         stats = hp.get("stats", {}).get(var, {"mean": 0.0, "std": 1.0})
@@ -246,10 +231,32 @@ def forward(sd, hp, batch, inference=False, dtype=torch.float32, force=None, con
         if inference:
             pred = pred * control.get(var, 1.0)
         emb = sd[pre + "embedding.weight"].to(dtype)[idx]
-        out_val = emb if out_val is None else out_val + emb
-        x = x + emb
         res[f"variances_{var}"] = pred
         res[f"_bucket_{var}"] = idx
+        return x + emb, (emb if out_val is None else out_val + emb)
+
+    out_val = None
+    for i, var in enumerate(hp["variances"]):  # phone-level variances act on the encoder output (model.py:277-294)
+        if hp["variance_transforms"][i] == "cwt":
+            raise NotImplementedError("cwt")
+        if hp["variance_levels"][i] == "phone":
+            x, out_val = encode(i, var, x, src_mask, out_val)
+    if "duration_rounded" in force:
+        dur = force["duration_rounded"]
+    elif not inference:
+        dur = batch["duration"]
+    else:
+        dur = round_durations(log_dur, src_mask)
+
+    from_cfg = hp["max_length"] * hp["sampling_rate"] / hp["hop_length"]
+    x, tgt_mask = length_regulator(x, dur, from_cfg)
+    if out_val is not None:
+        out_val, _ = length_regulator(out_val, dur, from_cfg)
+    res["_lr"] = x
+
+    for i, var in enumerate(hp["variances"]):
+        if hp["variance_levels"][i] == "frame":
+            x, out_val = encode(i, var, x, tgt_mask, out_val)
     res["_va"] = x
 
     x = x + positional_table(sd, dtype)[:, : x.shape[1], :]
@@ -280,8 +287,12 @@ def loss(hp, result, batch):
     cap = int(hp["max_length"] * hp["sampling_rate"] / hp["hop_length"])
     out = {}
     for i, var in enumerate(hp["variances"]):
-        tgt = batch[f"variances_{var}"][:, :cap].to(dt)
-        out[var] = F.mse_loss(result[f"variances_{var}"][valid_tgt], tgt[valid_tgt])
+        if hp["variance_levels"][i] == "phone":  # loss.py:129-130: phone-level variances use the source mask
+            tgt = batch[f"variances_{var}"].to(dt)
+            out[var] = F.mse_loss(result[f"variances_{var}"][valid_src], tgt[valid_src])
+        else:
+            tgt = batch[f"variances_{var}"][:, :cap].to(dt)
+            out[var] = F.mse_loss(result[f"variances_{var}"][valid_tgt], tgt[valid_tgt])
     m = valid_tgt[:, :, None].expand_as(result["mel"])
     out["mel"] = F.l1_loss(result["mel"][m], batch["mel"].to(dt)[m])
     out["duration"] = F.mse_loss(result["duration_prediction"][valid_src],

@@ -78,7 +78,7 @@ def grad_probe(name, n):
 def forward_golden(name, preset, seed, batch, inference, stats=None, train_targets=False):
     model, hp = _ref_model(configs.PRESETS[preset], seed, stats)
     if train_targets:
-        batch = synthetic.add_train_targets(batch, hp["variances"], seed=seed)
+        batch = synthetic.add_train_targets(batch, hp["variances"], seed=seed, levels=hp["variance_levels"])
     r32, r64 = _run(model, batch, inference)
     g = {
         "preset": preset, "seed": seed, "inference": inference, "stats": stats,
@@ -193,6 +193,9 @@ def main():
     forward_golden("tiny_dw_train", "TINY_DW", 3, tiny, False, stats=STATS, train_targets=True)
     forward_golden("small_train", "SMALL_TRAIN", 4, synthetic.make_batch(3, 9, 40, seed=4), False, stats=STATS,
                    train_targets=True)
+    forward_golden("small_train_phone", "SMALL_TRAIN_PHONE", 6, synthetic.make_batch(3, 9, 40, seed=6), False, stats=STATS,
+                   train_targets=True)
+    forward_golden("small_phone_infer", "SMALL_TRAIN_PHONE", 7, synthetic.make_batch(3, 9, 40, seed=7), True, stats=STATS)
     forward_golden("c1_infer", "C1", 1234, synthetic.make_batch(1, 128, 128, seed=1234), True)
     forward_golden("c2_small_infer", "C2", 2, synthetic.make_batch(4, 20, 96, seed=2), True)
 

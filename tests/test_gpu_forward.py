@@ -51,7 +51,7 @@ def compare(model, ref, batch, hp):
 
 
 @pytest.mark.parametrize("mode", ["fp32", "simt", "bf16"])
-@pytest.mark.parametrize("name", ["c1_infer", "c2_small_infer"])
+@pytest.mark.parametrize("name", ["c1_infer", "c2_small_infer", "small_phone_infer"])
 def test_against_reference_goldens(golden_dir, name, mode):
     g = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
     model, sd, hp = build(g["preset"], g["seed"], g["stats"], g["shapes"], mode=mode)

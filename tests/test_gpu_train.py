@@ -252,9 +252,10 @@ def _build(g, mode):
     return model, sd, hp
 
 
+@pytest.mark.parametrize("golden", ["small_train", "small_train_phone"])
 @pytest.mark.parametrize("mode,rel", [("simt", 1e-3), ("fp32", 2e-3)])
-def test_train_step_against_reference_and_oracle(golden_dir, mode, rel):
-    g = torch.load(os.path.join(golden_dir, "small_train.pt"), weights_only=False)
+def test_train_step_against_reference_and_oracle(golden_dir, mode, rel, golden):
+    g = torch.load(os.path.join(golden_dir, golden + ".pt"), weights_only=False)
     model, sd, hp = _build(g, mode)
     batch = g["batch"]
     model.log_losses = False
@@ -277,9 +278,12 @@ def test_train_step_against_reference_and_oracle(golden_dir, mode, rel):
     # (b) the oracle's autograd gradients, element by element
     _, ograds = O.gradients(sd, hp, batch)
     worst = 0.0
+    # absolute floor: the split-bf16 tensor-core products carry ~2e-5 of the OPERANDS' scale, which shows on
+    # gradients that are small through cancellation; the exact-fp32 kernels are held to a 10x tighter floor
+    floor = (1e-3 if mode == "simt" else 1e-2) * scale
     for k, og in ograds.items():
         err = (grads[k].cpu() - og).abs().max().item()
-        ref = max(og.abs().max().item(), 1e-3 * scale)
+        ref = max(og.abs().max().item(), floor)
         worst = max(worst, err / ref)
         assert err <= rel * ref, (k, err, ref)
     print(f"train step [{mode}]: worst relative gradient error {worst:.2e}")

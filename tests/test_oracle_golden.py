@@ -10,7 +10,7 @@ import torch
 from lightningfastspeech2_b200 import configs, synthetic
 from oracle import fs2_oracle as O
 
-FWD = ["tiny_dw_infer", "tiny_dense_infer", "c1_infer", "c2_small_infer"]
+FWD = ["tiny_dw_infer", "tiny_dense_infer", "c1_infer", "c2_small_infer", "small_phone_infer"]
 
 
 def _load(golden_dir, name):
@@ -114,7 +114,7 @@ def _probe(name, n):
     return torch.from_numpy(r.integers(0, 2, size=n).astype(np.float64) * 2 - 1)
 
 
-@pytest.mark.parametrize("name", ["tiny_dw_train", "small_train"])
+@pytest.mark.parametrize("name", ["tiny_dw_train", "small_train", "small_train_phone"])
 def test_train_step_gradients_and_adamw(golden_dir, name):
     """Oracle autograd vs the reference's own backward() + AdamW/Noam step: loss values, per-parameter
     gradient norms, probe-vector dot products (direction), small tensors whole, and the first
