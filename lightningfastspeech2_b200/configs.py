@@ -152,6 +152,9 @@ SMALL_TRAIN = dict(
 )
 # the same with the first variance at phone level (model.py:277-294) / with dense (non-depthwise) convolutions
 SMALL_TRAIN_PHONE = dict(SMALL_TRAIN, variance_levels=["phone", "frame"])
+SMALL_TRAIN_DENSE = dict(SMALL_TRAIN, encoder_depthwise_conv=False, decoder_depthwise_conv=False,
+                         variance_depthwise_conv=False, duration_depthwise_conv=False,
+                         encoder_kernel_sizes=[5, 9], decoder_kernel_sizes=[9, 3])
 # C4: train step on the "76 M" model with the reference's default dropouts (0.1 FFTBlock / PE, 0.5 predictors),
 # C4_P0: the same with every dropout off (gradient-parity runs)
 C4 = dict(C3)
@@ -159,7 +162,7 @@ C4_P0 = dict(C3, **NO_DROPOUT, variance_dropout=[0.0, 0.0, 0.0])
 # C2-size train step (7.4 M params)
 C2_TRAIN = dict(C2, **NO_DROPOUT, variance_dropout=[0.0, 0.0])
 
-PRESETS = {"SMALL_TRAIN": SMALL_TRAIN, "SMALL_TRAIN_PHONE": SMALL_TRAIN_PHONE, "C4": C4, "C4_P0": C4_P0, "C2_TRAIN": C2_TRAIN, "C1": C1, "C2": C2, "C3": C3, "TINY_DW": TINY_DW, "TINY_DENSE": TINY_DENSE}
+PRESETS = {"SMALL_TRAIN": SMALL_TRAIN, "SMALL_TRAIN_PHONE": SMALL_TRAIN_PHONE, "SMALL_TRAIN_DENSE": SMALL_TRAIN_DENSE, "C4": C4, "C4_P0": C4_P0, "C2_TRAIN": C2_TRAIN, "C1": C1, "C2": C2, "C3": C3, "TINY_DW": TINY_DW, "TINY_DENSE": TINY_DENSE}
 
 
 def resolve(kwargs):

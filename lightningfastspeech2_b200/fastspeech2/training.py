@@ -12,7 +12,8 @@ post-ReLU dropout of the FFTBlock, predictor layers) are implemented with a coun
 that the backward regenerates from (seed, site); the random stream necessarily differs from PyTorch's,
 so gradient PARITY is checked with every ``*_dropout = 0`` and dropout itself by its
 statistics and by directional derivatives.  Attention-probability dropout needs the tensor-core
-attention path.  Dense-conv (non-depthwise) stacks are inference-only.
+attention path.  Dense-conv (non-depthwise) stacks train too (forward / input gradients on the tensor
+cores as k shifted GEMMs, per-tap weight gradients on the exact-fp32 CUDA-core kernel).
 """
 import numpy as np
 import torch
@@ -110,6 +111,36 @@ class Engine:
         """dy (..., n) . w (n, k) -> (..., k): the layer-input gradient of y = x . w^T"""
         return self.linear(dy, ops.transpose(w), None, tag=tag)
 
+    # -- dense Conv1d(c -> n, k, "same") over (B, T, c), weight in the reference layout (n, c, k) -------------
+    def conv(self, x, w, b, relu=False, tag=None):
+        n, c, k = w.shape
+        wp = w.permute(0, 2, 1).reshape(n, k * c).contiguous()           # tap-major repack (weights only)
+        if self.tc and c % 32 == 0 and n % 16 == 0:
+            return ops.gemm_tc(self._planes(x), ops.split_bf16(wp), b, taps=k, relu=relu, npass=self.npass, tag=tag)
+        return ops.conv1d_dense(x, wp, b, k, relu=relu, tag=tag)
+
+    def conv_dgrad(self, dy, w, tag=None):
+        """input gradient = the same convolution with reversed taps and transposed channels"""
+        n, c, k = w.shape
+        wt = w.flip(2).permute(1, 2, 0).reshape(c, k * n).contiguous()
+        if self.tc and n % 32 == 0 and c % 16 == 0:
+            return ops.gemm_tc(self._planes(dy), ops.split_bf16(wt), None, taps=k, npass=self.npass, tag=tag)
+        return ops.conv1d_dense(dy, wt, None, k, tag=tag)
+
+    def conv_wgrad_(self, dw, db, dy, x, tag=None):
+        """dw (n, c, k) += per-tap dy^T . shift(x); db += column sums of dy"""
+        n, c, k = dw.shape
+        if k == 1:
+            self.wgrad_(dw.view(n, c), db, dy, x, tag=tag)
+            return
+        t = x.shape[1]
+        dwp = torch.zeros(n, k * c, device=dy.device, dtype=torch.float32)
+        for j in range(k):  # exact-fp32 CUDA-core kernel: rows of x shifted by the tap offset inside each utterance
+            ops.gemm_tn_(dwp, dy, x, t=t, shift=j - (k - 1) // 2, col_offset=j * c)
+        ops.add_(dw, dwp.view(n, k, c).permute(0, 2, 1).contiguous())
+        if db is not None:
+            ops.colsum_(db, dy)
+
     def wgrad_(self, dw, db, dy, x, tag=None):
         """dw (n, k) += dy^T . x ; db (n) += column sums of dy"""
         n, k = dw.shape
@@ -134,13 +165,12 @@ def _dwmat(w):
 # ------------------------------------------------------------------------------------------
 # FFTBlock (reference model.py:108-122)
 def fft_fwd(L, E, x, kpm):
-    if not L.depthwise:
-        raise NotImplementedError("training the dense-conv FFTBlock (only the depthwise variant has a backward)")
     p = L.p_drop
     sa = L.self_attn
-    dwc, pw, gc, pw2 = L.conv1[0], L.conv1[1], L.conv2[0], L.conv2[1]
-    if gc.kernel_size[0] != 1:
-        raise NotImplementedError("grouped conv2.0 with kernel > 1")
+    if L.depthwise:
+        dwc, pw, gc, pw2 = L.conv1[0], L.conv1[1], L.conv2[0], L.conv2[1]
+        if gc.kernel_size[0] != 1:
+            raise NotImplementedError("grouped conv2.0 with kernel > 1")
     s = {"x": x, "kpm": kpm}
     d_model = x.shape[-1]
     qkv_planes = E.tc and (d_model // L.nhead) % 32 == 0   # consumed only by the attention GEMMs and the wgrad
@@ -150,24 +180,42 @@ def fft_fwd(L, E, x, kpm):
     s["drop1"] = E.dropout_(a, p)                                         # dropout1 (model.py:114)
     x1, s["z1"], s["st1"] = ops.add_layernorm_train(x, a, L.norm1.weight, L.norm1.bias, L.eps)
     s["x1"] = x1
-    s["dw_wt"] = ops.transpose(_dwmat(dwc.weight))                        # (k, d)
-    s["u"] = E.dwconv(x1, s["dw_wt"], dwc.bias)
-    s["v"] = E.linear(s["u"], _mat(pw.weight), pw.bias, relu=True, tag="ffn1_gemm")
-    s["dropv"] = E.dropout_(s["v"], p)                                    # dropout after ReLU (model.py:120)
-    s["w_eff"], b_eff = ops.fold_pw(_mat(pw2.weight), _mat(gc.weight), gc.bias, pw2.bias)
-    y = E.linear(s["v"], s["w_eff"], b_eff, tag="ffn2_gemm")
+    if L.depthwise:
+        s["dw_wt"] = ops.transpose(_dwmat(dwc.weight))                    # (k, d)
+        s["u"] = E.dwconv(x1, s["dw_wt"], dwc.bias)
+        s["v"] = E.linear(s["u"], _mat(pw.weight), pw.bias, relu=True, tag="ffn1_gemm")
+        s["dropv"] = E.dropout_(s["v"], p)                                # dropout after ReLU (model.py:120)
+        s["w_eff"], b_eff = ops.fold_pw(_mat(pw2.weight), _mat(gc.weight), gc.bias, pw2.bias)
+        y = E.linear(s["v"], s["w_eff"], b_eff, tag="ffn2_gemm")
+    else:                                                                  # dense convolutions (model.py:95-106)
+        s["v"] = E.conv(x1, L.conv1.weight, L.conv1.bias, relu=True, tag="ffn1_gemm")
+        s["dropv"] = E.dropout_(s["v"], p)
+        y = E.conv(s["v"], L.conv2.weight, L.conv2.bias, tag="ffn2_gemm")
     s["drop2"] = E.dropout_(y, p)                                         # dropout2 (model.py:115)
     x2, s["z2"], s["st2"] = ops.add_layernorm_train(x1, y, L.norm2.weight, L.norm2.bias, L.eps)
     return x2, s
 
 
 def fft_bwd(L, E, s, dx2):
-    sa = L.self_attn
-    dwc, pw, gc, pw2 = L.conv1[0], L.conv1[1], L.conv2[0], L.conv2[1]
     dev = dx2.device
     dz2 = ops.layernorm_bwd(dx2, s["z2"], s["st2"], L.norm2.weight, grad_of(L.norm2.weight), grad_of(L.norm2.bias))
-    # conv2 (folded): y = v . w_eff^T + b_eff
     dy = E.dropout_bwd(dz2, s["drop2"], inplace=False)
+    if L.depthwise:
+        dx1 = _ffn_bwd_depthwise(L, E, s, dy, dev)
+    else:
+        dv = E.conv_dgrad(dy, L.conv2.weight, tag="ffn2_dgrad")
+        E.conv_wgrad_(grad_of(L.conv2.weight), grad_of(L.conv2.bias), dy, s["v"], tag="ffn2_wgrad")
+        E.dropout_bwd(dv, s["dropv"])
+        ops.relu_bwd_(dv, s["v"])
+        dx1 = E.conv_dgrad(dv, L.conv1.weight, tag="ffn1_dgrad")
+        E.conv_wgrad_(grad_of(L.conv1.weight), grad_of(L.conv1.bias), dv, s["x1"], tag="ffn1_wgrad")
+    ops.add_(dx1, dz2)                                                   # residual around the FFN
+    return _attn_bwd(L, E, s, dx1)
+
+
+def _ffn_bwd_depthwise(L, E, s, dy, dev):
+    """conv1 = depthwise(k1) + pointwise, conv2 = grouped 1x1 + pointwise (folded): returns d(x1) without the residual"""
+    dwc, pw, gc, pw2 = L.conv1[0], L.conv1[1], L.conv2[0], L.conv2[1]
     dv = E.dgrad(dy, s["w_eff"], tag="ffn2_dgrad")
     dw_eff = torch.zeros_like(s["w_eff"])
     db_eff = torch.zeros(s["w_eff"].shape[0], device=dev, dtype=torch.float32)
@@ -178,8 +226,11 @@ def fft_bwd(L, E, s, dx2):
     ops.relu_bwd_(dv, s["v"])
     du = E.dgrad(dv, _mat(pw.weight), tag="ffn1_dgrad")
     E.wgrad_(_mat(grad_of(pw.weight)), grad_of(pw.bias), dv, s["u"], tag="ffn1_wgrad")
-    dx1 = _dwconv_bwd(dwc, s["dw_wt"], du, s["x1"])
-    ops.add_(dx1, dz2)                                                   # residual around the FFN
+    return _dwconv_bwd(dwc, s["dw_wt"], du, s["x1"])
+
+
+def _attn_bwd(L, E, s, dx1):
+    sa = L.self_attn
     dz1 = ops.layernorm_bwd(dx1, s["z1"], s["st1"], L.norm1.weight, grad_of(L.norm1.weight), grad_of(L.norm1.bias))
     da = E.dropout_bwd(dz1, s["drop1"], inplace=False)
     dctx = E.dgrad(da, sa.out_proj.weight, tag="out_proj_dgrad")
@@ -208,12 +259,14 @@ def vp_fwd(P, E, x, mask):
     layers = []
     z = x
     for layer in P.layers:
-        if not layer.depthwise:
-            raise NotImplementedError("training dense-conv variance predictors")
         conv, ln = layer.layers[0].module, layer.layers[2]
-        dw_wt = ops.transpose(_dwmat(conv[0].weight))
-        u = E.dwconv(z, dw_wt, conv[0].bias)
-        h = E.linear(u, _mat(conv[1].weight), conv[1].bias, relu=True, tag="predictor_pw_gemm")
+        if layer.depthwise:
+            dw_wt = ops.transpose(_dwmat(conv[0].weight))
+            u = E.dwconv(z, dw_wt, conv[0].bias)
+            h = E.linear(u, _mat(conv[1].weight), conv[1].bias, relu=True, tag="predictor_pw_gemm")
+        else:
+            dw_wt, u = None, None
+            h = E.conv(z, conv.weight, conv.bias, relu=True, tag="predictor_conv_gemm")
         zo, _, st = ops.add_layernorm_train(h, None, ln.weight, ln.bias, ln.eps)
         layers.append({"x": z, "u": u, "h": h, "st": st, "dw_wt": dw_wt, "drop": E.dropout_(zo, layer.layers[3].p)})
         z = zo
@@ -229,9 +282,13 @@ def vp_bwd(P, E, s, dout):
         E.dropout_bwd(dz, sl["drop"])
         dh = ops.layernorm_bwd(dz, sl["h"], sl["st"], ln.weight, grad_of(ln.weight), grad_of(ln.bias))
         ops.relu_bwd_(dh, sl["h"])
-        du = E.dgrad(dh, _mat(conv[1].weight), tag="predictor_dgrad")
-        E.wgrad_(_mat(grad_of(conv[1].weight)), grad_of(conv[1].bias), dh, sl["u"], tag="predictor_wgrad")
-        dz = _dwconv_bwd(conv[0], sl["dw_wt"], du, sl["x"])
+        if layer.depthwise:
+            du = E.dgrad(dh, _mat(conv[1].weight), tag="predictor_dgrad")
+            E.wgrad_(_mat(grad_of(conv[1].weight)), grad_of(conv[1].bias), dh, sl["u"], tag="predictor_wgrad")
+            dz = _dwconv_bwd(conv[0], sl["dw_wt"], du, sl["x"])
+        else:
+            dz = E.conv_dgrad(dh, conv.weight, tag="predictor_dgrad")
+            E.conv_wgrad_(grad_of(conv.weight), grad_of(conv.bias), dh, sl["x"], tag="predictor_wgrad")
     return dz
 
 

@@ -195,6 +195,8 @@ def main():
                    train_targets=True)
     forward_golden("small_train_phone", "SMALL_TRAIN_PHONE", 6, synthetic.make_batch(3, 9, 40, seed=6), False, stats=STATS,
                    train_targets=True)
+    forward_golden("small_train_dense", "SMALL_TRAIN_DENSE", 8, synthetic.make_batch(3, 9, 40, seed=8), False, stats=STATS,
+                   train_targets=True)
     forward_golden("small_phone_infer", "SMALL_TRAIN_PHONE", 7, synthetic.make_batch(3, 9, 40, seed=7), True, stats=STATS)
     forward_golden("c1_infer", "C1", 1234, synthetic.make_batch(1, 128, 128, seed=1234), True)
     forward_golden("c2_small_infer", "C2", 2, synthetic.make_batch(4, 20, 96, seed=2), True)

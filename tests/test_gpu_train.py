@@ -252,7 +252,7 @@ def _build(g, mode):
     return model, sd, hp
 
 
-@pytest.mark.parametrize("golden", ["small_train", "small_train_phone"])
+@pytest.mark.parametrize("golden", ["small_train", "small_train_phone", "small_train_dense"])
 @pytest.mark.parametrize("mode,rel", [("simt", 1e-3), ("fp32", 2e-3)])
 def test_train_step_against_reference_and_oracle(golden_dir, mode, rel, golden):
     g = torch.load(os.path.join(golden_dir, golden + ".pt"), weights_only=False)
