@@ -114,6 +114,12 @@ LFS2_API int lfs2_bucket_embed_add(float* x, const float* val, float std, float 
                           int nbins, const float* emb, const int64_t* idx_forced, int64_t* idx_out,
                           float* acc, int acc_mode, int m, int d, void* stream);
 
+/* PriorEmbedding.forward (model.py:146-164, used at fastspeech2.py:687-692): per-utterance scalar prior ->
+ * out[b,:] = relu(emb[bucketize(prior[b], bins[nbins-1], right=False), :]) (B,d); idx_out (B) optional.
+ * The broadcast add over time is lfs2_add_pe_spk with a zero positional table. */
+LFS2_API int lfs2_prior_embed(const float* prior, const float* bins, int nbins, const float* emb, float* out,
+                              int64_t* idx_out, int batch, int d, void* stream);
+
 /* ---- A5: inference durations ----------------------------------------------------------
  * dur = int32(clamp(round_half_even(exp(log_dur) - 1), 0)); per utterance, if
  * sum(dur[valid]) <= n_valid/2 then dur[valid] = 1.   replaces model.py:300-309. */

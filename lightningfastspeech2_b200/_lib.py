@@ -28,6 +28,7 @@ SIGNATURES = {
     "lfs2_add_layernorm": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
     "lfs2_rowdot_mask": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "lfs2_bucket_embed_add": [_vp, _vp, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "lfs2_prior_embed": [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp],
     "lfs2_duration_round_guard": [_vp, _vp, _vp, _i, _i, _vp],
     "lfs2_length_regulate_scan": [_vp, _i, _vp, _vp, _vp, _i, _i, _vp],
     "lfs2_length_regulate_scatter": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],

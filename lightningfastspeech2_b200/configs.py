@@ -152,6 +152,7 @@ SMALL_TRAIN = dict(
 )
 # the same with the first variance at phone level (model.py:277-294) / with dense (non-depthwise) convolutions
 SMALL_TRAIN_PHONE = dict(SMALL_TRAIN, variance_levels=["phone", "frame"])
+SMALL_TRAIN_PRIOR = dict(SMALL_TRAIN, priors=["pitch", "duration"])
 SMALL_TRAIN_DENSE = dict(SMALL_TRAIN, encoder_depthwise_conv=False, decoder_depthwise_conv=False,
                          variance_depthwise_conv=False, duration_depthwise_conv=False,
                          encoder_kernel_sizes=[5, 9], decoder_kernel_sizes=[9, 3])
@@ -162,7 +163,7 @@ C4_P0 = dict(C3, **NO_DROPOUT, variance_dropout=[0.0, 0.0, 0.0])
 # C2-size train step (7.4 M params)
 C2_TRAIN = dict(C2, **NO_DROPOUT, variance_dropout=[0.0, 0.0])
 
-PRESETS = {"SMALL_TRAIN": SMALL_TRAIN, "SMALL_TRAIN_PHONE": SMALL_TRAIN_PHONE, "SMALL_TRAIN_DENSE": SMALL_TRAIN_DENSE, "C4": C4, "C4_P0": C4_P0, "C2_TRAIN": C2_TRAIN, "C1": C1, "C2": C2, "C3": C3, "TINY_DW": TINY_DW, "TINY_DENSE": TINY_DENSE}
+PRESETS = {"SMALL_TRAIN": SMALL_TRAIN, "SMALL_TRAIN_PHONE": SMALL_TRAIN_PHONE, "SMALL_TRAIN_DENSE": SMALL_TRAIN_DENSE, "SMALL_TRAIN_PRIOR": SMALL_TRAIN_PRIOR, "C4": C4, "C4_P0": C4_P0, "C2_TRAIN": C2_TRAIN, "C1": C1, "C2": C2, "C3": C3, "TINY_DW": TINY_DW, "TINY_DENSE": TINY_DENSE}
 
 
 def resolve(kwargs):

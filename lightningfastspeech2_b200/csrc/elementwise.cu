@@ -318,6 +318,27 @@ __global__ void bucket_embed_add_kernel(const float4* x_in, float4* x, const flo
   }
 }
 
+// PriorEmbedding (reference model.py:146-164): out[b,:] = relu(emb[bucketize(prior[b], bins), :]); one warp per utterance
+__global__ void prior_embed_kernel(const float* __restrict__ prior, const float* __restrict__ bins, int nb,
+                                   const float4* __restrict__ emb, float4* __restrict__ out, int64_t* __restrict__ idx_out,
+                                   int batch, int d4) {
+  int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (b >= batch) return;
+  const float v = prior[b];
+  int lo = 0, hi = nb;
+  while (lo < hi) {
+    int mid = lo + ((hi - lo) >> 1);
+    if (!(bins[mid] >= v)) lo = mid + 1;
+    else hi = mid;
+  }
+  if (lane == 0 && idx_out) idx_out[b] = lo;
+  for (int c = lane; c < d4; c += 32) {
+    float4 e = emb[(size_t)lo * d4 + c];
+    e.x = fmaxf(e.x, 0.f); e.y = fmaxf(e.y, 0.f); e.z = fmaxf(e.z, 0.f); e.w = fmaxf(e.w, 0.f);
+    out[(size_t)b * d4 + c] = e;
+  }
+}
+
 // Depthwise conv specialised on the kernel size, shared-memory tiled: one CTA = 64 (K <= 9) or
 // 32 output frames x 256 channels of one utterance, two CTAs per SM so one CTA's load phase
 // overlaps the other's arithmetic.  The (tile + K - 1) input rows are staged once in
@@ -610,6 +631,18 @@ int lfs2_duration_round_guard(const float* log_dur, const uint8_t* src_mask, int
   if (batch == 0 || tp == 0) return LFS2_OK;
   duration_round_guard_kernel<<<batch, 256, 0, (cudaStream_t)stream>>>(log_dur, src_mask, dur, tp);
   LFS2_CHECK_LAUNCH("duration_round_guard");
+  return LFS2_OK;
+}
+
+int lfs2_prior_embed(const float* prior, const float* bins, int nbins, const float* emb, float* out, int64_t* idx_out,
+                     int batch, int d, void* stream) {
+  LFS2_REQUIRE(prior && bins && emb && out, LFS2_ERR_INVALID_ARG, "prior_embed: null pointer");
+  if (batch == 0) return LFS2_OK;
+  LFS2_REQUIRE(batch > 0 && d > 0 && d % 4 == 0 && nbins >= 1, LFS2_ERR_UNSUPPORTED, "prior_embed: bad shape");
+  LFS2_REQUIRE(aligned16(emb) && aligned16(out), LFS2_ERR_INVALID_ARG, "prior_embed: pointers must be 16-byte aligned");
+  prior_embed_kernel<<<ceil_div((long long)batch * 32, 128), 128, 0, (cudaStream_t)stream>>>(
+      prior, bins, nbins - 1, (const float4*)emb, (float4*)out, idx_out, batch, d / 4);
+  LFS2_CHECK_LAUNCH("prior_embed");
   return LFS2_OK;
 }
 

@@ -21,8 +21,8 @@ from torch import nn
 from .. import ops
 from . import training
 from .loss import FastSpeech2Loss
-from .model import (COMPUTE_MODES, ConformerEncoderLayer, PositionalEncoding, SpeakerEmbedding, VarianceAdaptor,
-                    _PackCache)
+from .model import (COMPUTE_MODES, ConformerEncoderLayer, PositionalEncoding, PriorEmbedding, SpeakerEmbedding,
+                    VarianceAdaptor, _PackCache)
 from .noam import NoamLR
 
 try:  # the real Lightning base class when it is installed (it is not in this image)
@@ -208,8 +208,6 @@ class FastSpeech2(_Base):
             raise NotImplementedError("only d-vector speakers work at the reference HEAD (SURVEY 8, quirk 2)")
         if speaker_embedding_every_layer or prior_embedding_every_layer:
             raise NotImplementedError("*_embedding_every_layer (TypeError in the reference, quirk 4)")
-        if len(priors) > 0:
-            raise NotImplementedError("prior embeddings (SURVEY 8f N3)")
         if not (encoder_conformer and decoder_conformer):
             raise NotImplementedError("plain TransformerEncoderLayer stacks")
         if encoder_hidden != decoder_hidden:
@@ -253,6 +251,10 @@ class FastSpeech2(_Base):
         if fastdiff_head:  # same shape as the reference's head (:393-402); feeds only result["fastdiff_var"]
             self.fastdiff_linear = nn.Sequential(nn.Linear(hp.decoder_hidden, hp.decoder_hidden),
                                                  nn.Linear(hp.decoder_hidden, hp.n_mels))
+        if hasattr(self, "stats"):  # reference :416-424
+            self.prior_embeddings = nn.ModuleDict({
+                prior: PriorEmbedding(hp.encoder_hidden, hp.variance_nbins, self.stats[f"{prior}_prior"])
+                for prior in hp.priors})
         self.speaker_embedding = SpeakerEmbedding(hp.encoder_hidden, hp.speaker_type)
 
         loss_weights = {"mel": hp.mel_loss_weight, "duration": hp.duration_loss_weight,
@@ -354,6 +356,11 @@ class FastSpeech2(_Base):
                                       "enabled for the train path, or .eval())")
         output, src_mask = ops.embed_pe_spk(phones, self.phone_embedding.weight, pe, spk)
         output = self.encoder(output, src_key_padding_mask=src_mask)
+        if len(hp.priors):  # per-utterance prior embeddings, broadcast over the phones (reference :687-692)
+            zero_pe = torch.zeros(1, max(output.shape[1], 1), output.shape[2], device=dev)
+            for prior in hp.priors:
+                term, _ = self.prior_embeddings[prior].term(targets[f"priors_{prior}"])
+                ops.add_pe_spk_(output, zero_pe, term)
         st = self.variance_adaptor.durations(output, src_mask, targets, inference=inference, force=force,
                                              control=control)
         st.update(enc=st["x_phone"], src_mask=src_mask, spk=spk)

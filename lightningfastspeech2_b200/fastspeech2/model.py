@@ -299,6 +299,26 @@ class SpeakerEmbedding(nn.Module):
         return out.reshape(-1, 1, output_shape).expand(-1, input_length, -1)
 
 
+class PriorEmbedding(nn.Module):
+    """reference model.py:146-164: per-utterance scalar prior -> bucketize -> embedding -> relu, broadcast over time."""
+
+    def __init__(self, embedding_dim, nbins, stats):
+        super().__init__()
+        self.embedding_dim = embedding_dim
+        self.bins = nn.Parameter(torch.linspace(stats["min"], stats["max"], nbins - 1), requires_grad=False)
+        self.embedding = nn.Embedding(nbins, embedding_dim)
+        self.relu = nn.ReLU()
+
+    def term(self, x):
+        """(B) prior values -> ((B, d) term, (B) bucket indices)"""
+        x = torch.as_tensor(x, dtype=torch.float32).to(self.bins.device).contiguous()
+        return ops.prior_embed(x, self.bins, self.embedding.weight)
+
+    def forward(self, x, input_length):
+        out, _ = self.term(x)
+        return out.reshape(-1, 1, self.embedding_dim).expand(-1, input_length, -1)
+
+
 class VarianceConvolutionLayer(nn.Module):
     """reference model.py:524-561: Transpose(conv) -> ReLU -> LayerNorm(filter) -> Dropout."""
 

@@ -322,6 +322,13 @@ def forward_train(M, targets):
         x, s = fft_fwd(L, E, x, src_mask)
         S["enc"].append(s)
 
+    S["priors"] = []
+    if len(hp.priors):  # per-utterance prior embeddings added to the encoder output (fastspeech2.py:687-692)
+        zero_pe = torch.zeros(1, max(x.shape[1], 1), x.shape[2], device=dev)
+        for prior in hp.priors:
+            term, idx = M.prior_embeddings[prior].term(targets[f"priors_{prior}"])
+            ops.add_pe_spk_(x, zero_pe, term)
+            S["priors"].append((prior, term, idx))
     dur_pred, S["dp"] = vp_fwd(va.duration_predictor, E, x, src_mask)
     np.random.uniform(0, 1)  # the reference draws the teacher-forcing coin here (model.py:272); tf_ratio = 1
     result = {}
@@ -403,6 +410,11 @@ def backward_train(M, S, dmel, ddur, dvars):
             ops.add_(dx, vp_bwd(enc.predictor, E, s_vp, g))
     if ddur is not None:
         ops.add_(dx, vp_bwd(va.duration_predictor, E, S["dp"], ddur))
+    for prior, term, idx in S["priors"]:  # relu(emb[bucket]) broadcast over time: sum the gradient over t, mask, scatter
+        g = torch.zeros(bsz, d, device=dev, dtype=torch.float32)
+        ops.sum_over_time_(g, dx)
+        ops.relu_bwd_(g, term)
+        ops.embedding_bwd_(grad_of(M.prior_embeddings[prior].embedding.weight), g, idx)
     for L, s in zip(reversed(list(M.encoder.layers)), reversed(S["enc"])):
         dx = fft_bwd(L, E, s, dx)
     ops.sum_over_time_(dspk, dx)                                         # "+ spk" at Tp (fastspeech2.py:658)

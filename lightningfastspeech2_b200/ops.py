@@ -194,6 +194,16 @@ def bucket_embed_add_(x, val, std, mean, bins, emb, idx_forced=None, acc=None, a
     return idx_out
 
 
+def prior_embed(prior, bins, emb):
+    """PriorEmbedding: prior (B) fp32 -> (relu(emb[bucketize(prior)]) (B,d), bucket indices (B) int64)"""
+    _chk(prior, torch.float32, "prior values", 1)
+    b, d = prior.shape[0], emb.shape[1]
+    out = torch.empty(b, d, device=prior.device, dtype=torch.float32)
+    idx = torch.empty(b, device=prior.device, dtype=torch.int64)
+    _launch("lfs2_prior_embed", _p(prior), _p(bins), emb.shape[0], _p(emb), _p(out), _p(idx), b, d, _s())
+    return out, idx
+
+
 def duration_round_guard(log_dur, src_mask):
     _chk(log_dur, torch.float32, "duration_prediction", 2); _chk(src_mask, torch.bool, "src_mask", 2)
     dur = torch.empty(log_dur.shape, device=log_dur.device, dtype=torch.int32)

@@ -210,6 +210,11 @@ def forward(sd, hp, batch, inference=False, dtype=torch.float32, force=None, con
     for i in range(hp["encoder_layers"]):
         x = fft_block(x, src_mask, sd, f"encoder.layers.{i}.", hp["encoder_head"],
                       hp["encoder_depthwise_conv"], dtype)
+    for prior in hp.get("priors", []):  # PriorEmbedding (model.py:146-164) added after the encoder (fastspeech2.py:687-692)
+        pre = f"prior_embeddings.{prior}."
+        vals = torch.as_tensor(batch[f"priors_{prior}"]).to(dtype)
+        idx = torch.bucketize(vals, sd[pre + "bins"].to(dtype))
+        x = x + torch.relu(sd[pre + "embedding.weight"].to(dtype)[idx])[:, None, :]
     res["_enc"] = x
 
     va = "variance_adaptor."

@@ -36,6 +36,8 @@ def _ref_model(kwargs, seed, stats=None):
             super().__init__(ds, **kw)
             if stats is not None:
                 self.stats = {v: dict(stats) for v in hp["variances"]}
+            for p in hp["priors"]:
+                self.stats[f"{p}_prior"] = dict(stats or {"min": -3.0, "max": 3.0})
 
     dsmod.TTSDataset = DS
     f.TTSDataset = DS
@@ -79,6 +81,11 @@ def forward_golden(name, preset, seed, batch, inference, stats=None, train_targe
     model, hp = _ref_model(configs.PRESETS[preset], seed, stats)
     if train_targets:
         batch = synthetic.add_train_targets(batch, hp["variances"], seed=seed, levels=hp["variance_levels"])
+    if hp["priors"]:  # per-utterance scalar priors (the dataset emits python lists; tensors work the same way)
+        batch = dict(batch)
+        g = np.random.default_rng(seed + 1000)
+        for p in hp["priors"]:
+            batch[f"priors_{p}"] = torch.from_numpy(g.uniform(-2.0, 3.0, size=batch["phones"].shape[0]).astype(np.float32))
     r32, r64 = _run(model, batch, inference)
     g = {
         "preset": preset, "seed": seed, "inference": inference, "stats": stats,
@@ -196,6 +203,8 @@ def main():
     forward_golden("small_train_phone", "SMALL_TRAIN_PHONE", 6, synthetic.make_batch(3, 9, 40, seed=6), False, stats=STATS,
                    train_targets=True)
     forward_golden("small_train_dense", "SMALL_TRAIN_DENSE", 8, synthetic.make_batch(3, 9, 40, seed=8), False, stats=STATS,
+                   train_targets=True)
+    forward_golden("small_train_prior", "SMALL_TRAIN_PRIOR", 9, synthetic.make_batch(3, 9, 40, seed=9), False, stats=STATS,
                    train_targets=True)
     forward_golden("small_phone_infer", "SMALL_TRAIN_PHONE", 7, synthetic.make_batch(3, 9, 40, seed=7), True, stats=STATS)
     forward_golden("c1_infer", "C1", 1234, synthetic.make_batch(1, 128, 128, seed=1234), True)

@@ -114,7 +114,7 @@ def _probe(name, n):
     return torch.from_numpy(r.integers(0, 2, size=n).astype(np.float64) * 2 - 1)
 
 
-@pytest.mark.parametrize("name", ["tiny_dw_train", "small_train", "small_train_phone", "small_train_dense"])
+@pytest.mark.parametrize("name", ["tiny_dw_train", "small_train", "small_train_phone", "small_train_dense", "small_train_prior"])
 def test_train_step_gradients_and_adamw(golden_dir, name):
     """Oracle autograd vs the reference's own backward() + AdamW/Noam step: loss values, per-parameter
     gradient norms, probe-vector dot products (direction), small tensors whole, and the first
