@@ -410,6 +410,28 @@ def run_lfs2(args):
     f1.record()
     barrier()
     ms_e2e = f0.elapsed_time(f1)
+
+    # ---- e2e, pipelined: the same per-step work (pinned H2D of the inputs, D2H of mel + mask into pinned memory,
+    #      host reads the mask), with the read-back of step i on a second stream overlapping step i+1's kernels
+    #      (lightningfastspeech2_b200.pipeline.SynthesisStream, depth 2) ----------------------------------------
+    from lightningfastspeech2_b200.pipeline import SynthesisStream
+
+    pipe = SynthesisStream(model, depth=2)
+    for _ in range(4):  # warm-up: both slots allocate their pinned buffers, the allocator reaches its steady state
+        pipe.collect(pipe.submit(pinned))
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    piped_frames, prev = 0, None
+    for _ in range(args.steps):
+        tk = pipe.submit(pinned)
+        if prev is not None:
+            piped_frames += int((~pipe.collect(prev)["tgt_mask"]).sum())
+        prev = tk
+    piped_frames += int((~pipe.collect(prev)["tgt_mask"]).sum())
+    p1.record()
+    barrier()
+    ms_piped = p0.elapsed_time(p1)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel CUDA-event pass (same inputs, after the timed region) -----------------
@@ -422,14 +444,14 @@ def run_lfs2(args):
 
     # ---- reduce over ranks ------------------------------------------------------------------
     if world > 1:
-        t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_piped], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
-        c = torch.tensor([frames, e2e_frames], device=dev, dtype=torch.int64)
+        ms, ms_e2e, ms_piped = float(t[0]), float(t[1]), float(t[2])
+        c = torch.tensor([frames, e2e_frames, piped_frames], device=dev, dtype=torch.int64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        frames_all, e2e_all = int(c[0]), int(c[1])
+        frames_all, e2e_all, piped_all = int(c[0]), int(c[1]), int(c[2])
     else:
-        frames_all, e2e_all = frames, e2e_frames
+        frames_all, e2e_all, piped_all = frames, e2e_frames, piped_frames
 
     # ---- bf16 mode (single-pass bf16 MMA operands, fp32 accumulate / residual / LayerNorm / softmax; tolerance
     #      1e-2 per BASELINE.json) on the same batch: secondary number, same timing protocol -------------------
@@ -590,7 +612,10 @@ def run_lfs2(args):
             "e2e": {"value": e2e_all / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pinned.values()) * world,
                     "d2h_bytes_per_step": (mel_host.numel() * 4 + mask_host.numel() + 8) * world,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / args.steps,
+                    "pipelined": {"value": piped_all / (ms_piped * 1e-3), "ms_per_step": ms_piped / args.steps,
+                                  "what": "same copies every step; D2H of step i on a second stream overlaps step "
+                                          "i+1 (pipeline.SynthesisStream, depth 2)"}},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",

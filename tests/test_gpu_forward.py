@@ -267,3 +267,23 @@ def test_bucketed_cuda_graph_replay_is_identical_and_tracks_weight_updates():
         valid = ~eager["tgt_mask"]
         assert torch.allclose(o3["mel"][valid], eager["mel"][valid] + 1.0, atol=1e-5)
     model.length_buckets = 1
+
+
+def test_synthesis_stream_pipelining_returns_the_same_results():
+    from lightningfastspeech2_b200.pipeline import SynthesisStream
+
+    model, sd, hp = build("C2", 17)
+    batches = [{k: v.pin_memory() for k, v in synthetic.make_batch(4, 10, 40, seed=30 + i).items() if k in ("phones", "speaker")}
+               for i in range(5)]
+    with torch.no_grad():
+        ref = [model(b, inference=True) for b in batches]
+    pipe = SynthesisStream(model, depth=2)
+    got, prev = [], None
+    for b in batches:
+        tk = pipe.submit(b)
+        if prev is not None:
+            got.append({k: v.clone() for k, v in pipe.collect(prev).items()})
+        prev = tk
+    got.append({k: v.clone() for k, v in pipe.collect(prev).items()})
+    for r, g in zip(ref, got):
+        assert torch.equal(r["mel"].cpu(), g["mel"]) and torch.equal(r["tgt_mask"].cpu(), g["tgt_mask"])
