@@ -166,6 +166,16 @@ LFS2_API int lfs2_gemm_tc(const void* a_hi, const void* a_lo, int batch, int t, 
                           const float* gamma, const float* beta, float eps,
                           float* out_f32, void* out_hi, void* out_lo, int npass, void* stream);
 
+/* Fused position-wise FFN tail of the depthwise FFTBlock (model.py:118-122 after the depthwise conv; model width 256):
+ *   out = LayerNorm( res + relu(u . w1^T + b1) . w2^T + b2 ; gamma, beta, eps )
+ * u, res, out: (m, 256) bf16 hi/lo planes; w1 (f, 256), w2 (256, f) hi/lo planes (w2 = the folded
+ * conv2.1 . blockdiag(conv2.0) matrix, b2 its folded bias); ident_hi = bf16 identity (256, 256).  The f-wide
+ * intermediate stays in tensor memory (f % 256 == 0, f <= 2048).  npass as in lfs2_gemm_tc. */
+LFS2_API int lfs2_ffn_fused_tc(const void* u_hi, const void* u_lo, int m, const void* w1_hi, const void* w1_lo, int f,
+                               const float* b1, const void* w2_hi, const void* w2_lo, const float* b2,
+                               const void* res_hi, const void* res_lo, const void* ident_hi, const float* gamma,
+                               const float* beta, float eps, void* out_hi, void* out_lo, int npass, void* stream);
+
 /* tensor-core multi-head self attention (head_dim 128) on the bf16 hi/lo planes of the packed
  * qkv (B,T,3d) tensor [q | k | v] written by lfs2_gemm_tc: flash-style streaming softmax,
  * S = Q.K^T and O = P.V on tcgen05 with Q/P read from tensor memory, K/V tiles by TMA.

@@ -1,0 +1,430 @@
+// Fused position-wise FFN of the depthwise FFTBlock (reference model.py:118-122 after the depthwise conv):
+//
+//     out = LayerNorm( x1 + relu(u . W11^T + b11) . W_eff^T + b_eff )          u = dwconv(x1), d = 256
+//
+// in ONE kernel: the F-wide intermediate v = relu(.) never leaves the SM.  Per 128-row tile and per
+// 256-column chunk c of F:
+//     G1  acc1 (TMEM, fp32 128 x 256)  = u . W11[c]^T                 SS form: u and W11 slabs by TMA
+//     E1  8 epilogue warps: acc1 + b11, ReLU, split into bf16 hi/lo pairs, written back IN PLACE into the same
+//         tensor-memory columns (per 32-column block: 16 packed hi columns, 16 packed lo columns)
+//     G2  acc2 (TMEM, fp32 128 x 256) += v[c] . W_eff[:, c]^T        TS form: A = v read from tensor memory
+// then the residual x1 rides the tensor core (hi.I + lo.I, as in gemm_tc.cu), and the epilogue does
+// + b_eff, LayerNorm over the 256 columns and leaves as bf16 hi/lo planes through swizzled staging + TMA stores.
+// HBM traffic per row: read u (1 KB) + x1 (1 KB), write out (1 KB) -- the unfused pair moves 11 KB.
+// tcgen05.mma executes in issue order, so G1 of chunk c+1 may be issued right behind G2 of chunk c although it
+// overwrites the columns G2 reads (same pattern as S/P in attention_tc.cu).
+// NPASS = 3: hi.hi + lo.hi + hi.lo for every product (fp32-parity mode); NPASS = 1: hi.hi only.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue (thread = row, two warps per quadrant).
+#include "tc_common.cuh"
+
+namespace lfs2 {
+namespace tc {
+
+constexpr int kFM = 128;      // rows per tile
+constexpr int kFK = 32;       // k-slab
+constexpr int kFD = 256;      // model width = K of G1 = N of G2 = LayerNorm width
+constexpr int kFC = 256;      // F chunk = N of G1 = K of G2
+constexpr int kFThreads = 320;
+constexpr int kFStageChunk = kFM * 32 * 4;  // 16 KB staging chunk (hi | lo planes of 128 x 32)
+
+struct FfnParams {
+  int m;            // rows
+  int f;            // hidden width (multiple of 256)
+  int total_tiles;
+  const float* b1;  // (f)
+  const float* b2;  // (256) folded bias
+  const float* gamma;
+  const float* beta;
+  float eps;
+};
+
+template <int NPASS>
+struct FfnSmem {
+  static constexpr int kAPlane = kFM * kFK * 2;   // 8 KB
+  static constexpr int kWPlane = kFC * kFK * 2;   // 16 KB
+  static constexpr int kStage = 2 * kAPlane + (NPASS == 3 ? 2 : 1) * kWPlane;  // residual slabs always carry R_lo
+  static constexpr int kOffWHi = kAPlane;
+  static constexpr int kOffALo = kAPlane + kWPlane;
+  static constexpr int kOffWLo = 2 * kAPlane + kWPlane;
+  static constexpr int kMaxF = 2048;
+  static constexpr int kFixed = 4 * kFStageChunk + kMaxF * 4 + 3 * kFD * 4 + 2 * 2 * kFM * 8 + 1024;
+  static constexpr int kStages = (226 * 1024 - kFixed) / kStage > 6 ? 6 : (226 * 1024 - kFixed) / kStage;
+  static constexpr int kOffStaging = kStages * kStage;
+  static constexpr int kOffB1 = kOffStaging + 4 * kFStageChunk;   // b1: kMaxF floats
+  static constexpr int kOffVec = kOffB1 + kMaxF * 4;              // b2 | gamma | beta
+  static constexpr int kOffStats = kOffVec + 3 * kFD * 4;
+  static constexpr int kTotal = kStages * kStage + kFixed;
+  static_assert(kStages >= 2, "not enough shared memory for a pipeline");
+  static_assert(kStage % 1024 == 0, "stage must keep 1024-byte alignment");
+};
+
+__device__ __forceinline__ void f_tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void f_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void f_tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+template <int NPASS>
+__global__ void __launch_bounds__(kFThreads, 1)
+ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_constant__ CUtensorMap map_u_lo,
+                    const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
+                    const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
+                    const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
+                    const __grid_constant__ CUtensorMap map_ident, const __grid_constant__ CUtensorMap map_o_hi,
+                    const __grid_constant__ CUtensorMap map_o_lo, const FfnParams p) {
+  using L = FfnSmem<NPASS>;
+  constexpr int kStages = L::kStages;
+  constexpr int kSlabs = kFD / kFK;  // 8 k-slabs per product (K = 256 everywhere)
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc1_full, v_ready, acc2_full, acc2_empty;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunks = p.f / kFC;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&map_u_hi);
+    prefetch_tmap(&map_w1_hi);
+    prefetch_tmap(&map_w2_hi);
+    prefetch_tmap(&map_o_hi);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&acc1_full, 1);
+    mbar_init(&v_ready, 8);
+    mbar_init(&acc2_full, 1);
+    mbar_init(&acc2_empty, 8);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
+  if (warp >= 2) {
+    float* b1s = reinterpret_cast<float*>(smem + L::kOffB1);
+    float* vec = reinterpret_cast<float*>(smem + L::kOffVec);
+    for (int i = threadIdx.x - 64; i < p.f; i += 256) b1s[i] = p.b1 ? p.b1[i] : 0.f;
+    for (int i = threadIdx.x - 64; i < kFD; i += 256) {
+      vec[i] = p.b2 ? p.b2[i] : 0.f;
+      vec[kFD + i] = p.gamma[i];
+      vec[2 * kFD + i] = p.beta[i];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  const uint32_t t_acc1 = tmem_base, t_acc2 = tmem_base + 256;
+
+  if (warp == 0) {
+    // ===================== TMA producer: slabs in exactly the order the MMA warp consumes them =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      auto next = [&]() {
+        if (++stage == kStages) {
+          stage = 0;
+          phase ^= 1;
+        }
+      };
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const int r0 = tile * kFM;
+        for (int c = 0; c < nchunks; ++c) {
+          for (int ks = 0; ks < kSlabs; ++ks) {  // G1: u slab + W11 slab
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * L::kStage;
+            mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 2 : 1) * (L::kAPlane + L::kWPlane));
+            tma_load_3d(st, &map_u_hi, &full_bar[stage], ks * kFK, r0, 0);
+            tma_load_3d(st + L::kOffWHi, &map_w1_hi, &full_bar[stage], ks * kFK, c * kFC, 0);
+            if (NPASS == 3) {
+              tma_load_3d(st + L::kOffALo, &map_u_lo, &full_bar[stage], ks * kFK, r0, 0);
+              tma_load_3d(st + L::kOffWLo, &map_w1_lo, &full_bar[stage], ks * kFK, c * kFC, 0);
+            }
+            next();
+          }
+          for (int ks = 0; ks < kSlabs; ++ks) {  // G2: W_eff slab only (A = v lives in tensor memory)
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * L::kStage;
+            mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 2 : 1) * L::kWPlane);
+            tma_load_3d(st + L::kOffWHi, &map_w2_hi, &full_bar[stage], c * kFC + ks * kFK, 0, 0);
+            if (NPASS == 3) tma_load_3d(st + L::kOffWLo, &map_w2_lo, &full_bar[stage], c * kFC + ks * kFK, 0, 0);
+            next();
+          }
+        }
+        for (int ks = 0; ks < kSlabs; ++ks) {  // residual: R_hi, R_lo against the identity block
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * L::kStage;
+          mbar_expect_tx(&full_bar[stage], 2 * L::kAPlane + L::kWPlane);
+          tma_load_3d(st, &map_r_hi, &full_bar[stage], ks * kFK, r0, 0);
+          tma_load_3d(st + L::kOffALo, &map_r_lo, &full_bar[stage], ks * kFK, r0, 0);
+          tma_load_3d(st + L::kOffWHi, &map_ident, &full_bar[stage], ks * kFK, 0, 0);
+          next();
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc = make_idesc(kFmtBF16, kFM, kFC, 0, 0);  // M128 x N256, K-major operands
+    const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 512, kSwizzle64);
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t chunk_ctr = 0;
+    int it = 0;
+    auto next = [&]() {
+      if (++stage == kStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    };
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
+        // ---- G1: acc1 = u . W11[c]^T ----
+        for (int ks = 0; ks < kSlabs; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t a_hi = desc_advance(d0, stage * L::kStage);
+            const uint64_t w_hi = desc_advance(a_hi, L::kOffWHi);
+            const uint64_t a_lo = desc_advance(a_hi, L::kOffALo);
+            const uint64_t w_lo = desc_advance(a_hi, L::kOffWLo);
+            if (ks == 0) umma_f16_c<false>(t_acc1, a_hi, w_hi, idesc);
+            else umma_f16_c<true>(t_acc1, a_hi, w_hi, idesc);
+            umma_f16_c<true>(t_acc1, desc_advance(a_hi, 32), desc_advance(w_hi, 32), idesc);
+            if (NPASS == 3) {
+              umma_f16_c<true>(t_acc1, a_lo, w_hi, idesc);
+              umma_f16_c<true>(t_acc1, desc_advance(a_lo, 32), desc_advance(w_hi, 32), idesc);
+              umma_f16_c<true>(t_acc1, a_hi, w_lo, idesc);
+              umma_f16_c<true>(t_acc1, desc_advance(a_hi, 32), desc_advance(w_lo, 32), idesc);
+            }
+            umma_commit(&empty_bar[stage]);
+            if (ks + 1 == kSlabs) umma_commit(&acc1_full);
+          }
+          __syncwarp();
+          next();
+        }
+        // ---- G2: acc2 += v[c] . W_eff[:, c]^T, A = v from tensor memory (written in place over acc1) ----
+        mbar_wait(&v_ready, chunk_ctr & 1);
+        // the first G2 of a tile overwrites acc2: the previous tile's LayerNorm epilogue must have drained it
+        // (G1 of this tile was already issued and ran under that epilogue)
+        if (c == 0) mbar_wait(&acc2_empty, (it & 1) ^ 1);
+        tc_fence_after();
+        for (int ks = 0; ks < kSlabs; ++ks) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t w_hi = desc_advance(d0, stage * L::kStage + L::kOffWHi);
+            const uint64_t w_lo = desc_advance(d0, stage * L::kStage + L::kOffWLo);
+            const uint32_t v_hi = t_acc1 + 32 * ks, v_lo = v_hi + 16;  // packed pairs: 8 columns per k16
+            if (c == 0 && ks == 0) umma_f16_ts_c<false>(t_acc2, v_hi, w_hi, idesc);
+            else umma_f16_ts_c<true>(t_acc2, v_hi, w_hi, idesc);
+            umma_f16_ts_c<true>(t_acc2, v_hi + 8, desc_advance(w_hi, 32), idesc);
+            if (NPASS == 3) {
+              umma_f16_ts_c<true>(t_acc2, v_lo, w_hi, idesc);
+              umma_f16_ts_c<true>(t_acc2, v_lo + 8, desc_advance(w_hi, 32), idesc);
+              umma_f16_ts_c<true>(t_acc2, v_hi, w_lo, idesc);
+              umma_f16_ts_c<true>(t_acc2, v_hi + 8, desc_advance(w_lo, 32), idesc);
+            }
+            umma_commit(&empty_bar[stage]);
+          }
+          __syncwarp();
+          next();
+        }
+      }
+      // ---- residual x1 on the tensor core: acc2 += R_hi . I + R_lo . I ----
+      for (int ks = 0; ks < kSlabs; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a_hi = desc_advance(d0, stage * L::kStage);
+          const uint64_t w_hi = desc_advance(a_hi, L::kOffWHi);
+          const uint64_t a_lo = desc_advance(a_hi, L::kOffALo);
+          umma_f16_c<true>(t_acc2, a_hi, w_hi, idesc);
+          umma_f16_c<true>(t_acc2, desc_advance(a_hi, 32), desc_advance(w_hi, 32), idesc);
+          umma_f16_c<true>(t_acc2, a_lo, w_hi, idesc);
+          umma_f16_c<true>(t_acc2, desc_advance(a_lo, 32), desc_advance(w_hi, 32), idesc);
+          umma_commit(&empty_bar[stage]);
+          if (ks + 1 == kSlabs) umma_commit(&acc2_full);
+        }
+        __syncwarp();
+        next();
+      }
+    }
+  } else {
+    // ===================== epilogue warps 2..9 =====================
+    const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quad * 32) << 16;
+    const bool issuer = (warp == 2 || warp == 6) && lane == 0;
+    const float* b1s = reinterpret_cast<const float*>(smem + L::kOffB1);
+    const float* vec = reinterpret_cast<const float*>(smem + L::kOffVec);
+    float2* stats = reinterpret_cast<float2*>(smem + L::kOffStats);
+    uint8_t* staging = smem + L::kOffStaging + half * 2 * kFStageChunk;
+    uint32_t chunk_ctr = 0, st_ctr = 0;
+    int it = 0;
+    float v[32];
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int r0 = tile * kFM;
+      // ---- E1 per F chunk: acc1 -> relu(acc1 + b1) as bf16 hi/lo pairs, in place ----
+      for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
+        mbar_wait(&acc1_full, chunk_ctr & 1);
+        tc_fence_after();
+#pragma unroll 1
+        for (int j = 4 * half; j < 4 * half + 4; ++j) {
+          const uint32_t ta = t_acc1 + lane_off + 32 * j;
+          tmem_ld32(ta, v);
+          uint32_t hi[16], lo[16];
+          const float* bb = b1s + c * kFC + 32 * j;
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            const float x0 = fmaxf(v[2 * e] + bb[2 * e], 0.f), x1 = fmaxf(v[2 * e + 1] + bb[2 * e + 1], 0.f);
+            split_pack2(x0, x1, hi[e], lo[e]);
+          }
+          f_tmem_st16(ta, hi);
+          if (NPASS == 3) f_tmem_st16(ta + 16, lo);
+        }
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&v_ready);
+      }
+      // ---- final epilogue: acc2 + b2 -> LayerNorm -> hi/lo planes ----
+      mbar_wait(&acc2_full, it & 1);
+      tc_fence_after();
+      const uint32_t ta2 = t_acc2 + lane_off;
+      float s = 0.f, q = 0.f;
+#pragma unroll 1
+      for (int j = 4 * half; j < 4 * half + 4; ++j) {
+        tmem_ld32(ta2 + 32 * j, v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float x = v[e] + vec[32 * j + e];
+          s += x;
+          q = fmaf(x, x, q);
+        }
+      }
+      float2* stt = stats + (it & 1) * 2 * kFM;
+      stt[half * kFM + r] = make_float2(s, q);
+      f_bar_sync(3, 256);
+      const float2 o = stt[(half ^ 1) * kFM + r];
+      s += o.x;
+      q += o.y;
+      const float mean = s * (1.f / kFD);
+      const float rstd = rsqrtf(fmaxf(q * (1.f / kFD) - mean * mean, 0.f) + p.eps);
+#pragma unroll 1
+      for (int j = 4 * half; j < 4 * half + 4; ++j) {
+        tmem_ld32(ta2 + 32 * j, v);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) {
+          const float x = v[e] + vec[32 * j + e];
+          v[e] = (x - mean) * rstd * vec[kFD + 32 * j + e] + vec[2 * kFD + 32 * j + e];
+        }
+        uint8_t* sb = staging + (st_ctr & 1) * kFStageChunk;
+        ++st_ctr;
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) split_pack2(v[2 * e], v[2 * e + 1], hi[e], lo[e]);
+        uint8_t* rh = sb + r * 64;
+        uint8_t* rl = rh + kFStageChunk / 2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int u = (i ^ ((r >> 1) & 3)) << 4;
+          *reinterpret_cast<uint4*>(rh + u) = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+          *reinterpret_cast<uint4*>(rl + u) = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+        }
+        fence_proxy_async_smem();
+        if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        f_bar_sync(1 + half, 128);
+        if (issuer) {
+          f_tma_store_3d(&map_o_hi, sb, 32 * j, r0, 0);
+          f_tma_store_3d(&map_o_lo, sb + kFStageChunk / 2, 32 * j, r0, 0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc2_empty);
+    }
+    if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int NPASS>
+static int launch_ffn(const CUtensorMap* m, const FfnParams& p, cudaStream_t s) {
+  using L = FfnSmem<NPASS>;
+  auto kern = ffn_fused_tc_kernel<NPASS>;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
+      set_error("ffn_fused_tc: cannot reserve %d bytes of shared memory", L::kTotal);
+      return LFS2_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+  kern<<<grid, kFThreads, L::kTotal, s>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], p);
+  LFS2_CHECK_LAUNCH("ffn_fused_tc");
+  return LFS2_OK;
+}
+
+}  // namespace tc
+}  // namespace lfs2
+
+using namespace lfs2;
+using namespace lfs2::tc;
+
+extern "C" int lfs2_ffn_fused_tc(const void* u_hi, const void* u_lo, int m, const void* w1_hi, const void* w1_lo, int f,
+                                 const float* b1, const void* w2_hi, const void* w2_lo, const float* b2,
+                                 const void* res_hi, const void* res_lo, const void* ident_hi, const float* gamma,
+                                 const float* beta, float eps, void* out_hi, void* out_lo, int npass, void* stream) {
+  LFS2_REQUIRE(u_hi && w1_hi && w2_hi && res_hi && res_lo && ident_hi && gamma && beta && out_hi && out_lo,
+               LFS2_ERR_INVALID_ARG, "ffn_fused_tc: null pointer");
+  LFS2_REQUIRE(npass == 1 || npass == 3, LFS2_ERR_INVALID_ARG, "ffn_fused_tc: npass must be 1 or 3");
+  LFS2_REQUIRE(npass == 1 || (u_lo && w1_lo && w2_lo), LFS2_ERR_INVALID_ARG, "ffn_fused_tc: npass=3 needs the lo planes");
+  if (m == 0) return LFS2_OK;
+  LFS2_REQUIRE(m > 0 && f > 0, LFS2_ERR_INVALID_ARG, "ffn_fused_tc: bad shape");
+  LFS2_REQUIRE(f % kFC == 0 && f <= FfnSmem<3>::kMaxF, LFS2_ERR_UNSUPPORTED,
+               "ffn_fused_tc: hidden width %d must be a multiple of %d and <= %d (model width is fixed at %d)", f, kFC,
+               FfnSmem<3>::kMaxF, kFD);
+  LFS2_REQUIRE(aligned16(u_hi) && aligned16(w1_hi) && aligned16(w2_hi) && aligned16(res_hi) && aligned16(res_lo) &&
+                   aligned16(out_hi) && aligned16(out_lo) && (!u_lo || aligned16(u_lo)),
+               LFS2_ERR_INVALID_ARG, "ffn_fused_tc: pointers must be 16-byte aligned");
+  CUtensorMap maps[11];
+  bool ok = make_tmap_3d(&maps[0], u_hi, kFD, m, 1, kFK, kFM, 64) && make_tmap_3d(&maps[2], w1_hi, kFD, f, 1, kFK, kFC, 64) &&
+            make_tmap_3d(&maps[4], w2_hi, f, kFD, 1, kFK, kFD, 64) && make_tmap_3d(&maps[6], res_hi, kFD, m, 1, kFK, kFM, 64) &&
+            make_tmap_3d(&maps[7], res_lo, kFD, m, 1, kFK, kFM, 64) &&
+            make_tmap_3d(&maps[8], ident_hi, kFD, kFD, 1, kFK, kFD, 64) &&
+            make_tmap_3d(&maps[9], out_hi, kFD, m, 1, 32, kFM, 64) && make_tmap_3d(&maps[10], out_lo, kFD, m, 1, 32, kFM, 64);
+  if (npass == 3)
+    ok = ok && make_tmap_3d(&maps[1], u_lo, kFD, m, 1, kFK, kFM, 64) && make_tmap_3d(&maps[3], w1_lo, kFD, f, 1, kFK, kFC, 64) &&
+         make_tmap_3d(&maps[5], w2_lo, f, kFD, 1, kFK, kFD, 64);
+  else {
+    maps[1] = maps[0];
+    maps[3] = maps[2];
+    maps[5] = maps[4];
+  }
+  LFS2_REQUIRE(ok, LFS2_ERR_CUDA, "ffn_fused_tc: cuTensorMapEncodeTiled failed");
+  FfnParams p;
+  p.m = m; p.f = f; p.total_tiles = ceil_div(m, kFM);
+  p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta; p.eps = eps;
+  cudaStream_t s = (cudaStream_t)stream;
+  return npass == 3 ? launch_ffn<3>(maps, p, s) : launch_ffn<1>(maps, p, s);
+}

@@ -127,6 +127,7 @@ class ConformerEncoderLayer(nn.Module):
         self._pack_tc = _PackCache()
 
     compute_mode = "fp32"
+    fused_ffn = True
 
     # -- weight repacks -------------------------------------------------------------------
     def _build_pack_tc(self):
@@ -225,6 +226,11 @@ class ConformerEncoderLayer(nn.Module):
                           beta=self.norm1.bias, eps=self.eps, out="planes", npass=npass, tag="out_proj_ln_gemm")
         if self.depthwise:
             up = ops.dwconv1d_planes(x1p, p["dw_wt"], self.conv1[0].bias)
+            fsz = w["pw1"].shape[0]
+            if self.fused_ffn and fsz % 256 == 0 and fsz <= 2048:
+                # FFN-1 -> ReLU -> FFN-2 -> + x1 -> LayerNorm in one kernel, the F-wide intermediate in tensor memory
+                return ops.ffn_fused_tc(up, w["pw1"], self.conv1[1].bias, w["w_eff"], p["b_eff"], x1p,
+                                        self.norm2.weight, self.norm2.bias, self.eps, npass=npass)
             vp = ops.gemm_tc(up, w["pw1"], self.conv1[1].bias, relu=True, out="planes", npass=npass, tag="ffn1_gemm")
             w2, b2, taps2 = w["w_eff"], p["b_eff"], 1
         else:

@@ -381,6 +381,24 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
     return of if out == "f32" else po
 
 
+def ffn_fused_tc(u, w1, b1, w2, b2, residual, gamma, beta, eps=LN_EPS, npass=3):
+    """LayerNorm(residual + relu(u . w1^T + b1) . w2^T + b2) in one kernel, the F-wide intermediate on chip.
+    u, residual: Planes (..., 256); w1 Planes (F, 256); w2 Planes (256, F) -> Planes (..., 256)"""
+    d = u.shape[-1]
+    f = w1.shape[0]
+    if d != 256 or tuple(w1.shape) != (f, 256) or tuple(w2.shape) != (256, f) or tuple(residual.shape) != tuple(u.shape):
+        raise ValueError("ffn_fused_tc: shapes must be u/residual (..., 256), w1 (F, 256), w2 (256, F)")
+    for x_ in (u.hi, u.lo, w1.hi, w1.lo, w2.hi, w2.lo, residual.hi, residual.lo):
+        _chk(x_, torch.bfloat16, "ffn_fused_tc operand plane")
+    m = u.hi.numel() // d
+    out = _empty_planes(tuple(u.shape), u.hi.device)
+    ident = _identity_planes(d, u.hi.device)
+    _launch("lfs2_ffn_fused_tc", _p(u.hi), _p(u.lo), m, _p(w1.hi), _p(w1.lo), f, _p(b1), _p(w2.hi), _p(w2.lo), _p(b2),
+            _p(residual.hi), _p(residual.lo), _p(ident), _p(gamma), _p(beta), float(eps), _p(out.hi), _p(out.lo), npass,
+            _s(), tag="ffn_fused", flops=4.0 * m * d * f, nbytes=4.0 * m * d * 3 + 8.0 * d * f)
+    return out
+
+
 def attention_tc(qkv, kpm, nhead, npass=3, want_f32=False, want_planes=True):
     """qkv: Planes (B,T,3d) packed [q|k|v]; kpm (B,T) bool True=PAD -> (ctx f32 or None, ctx Planes or None)"""
     if not isinstance(qkv, Planes):

@@ -112,3 +112,29 @@ def test_merge_and_dwconv_on_planes():
     got32 = ops.dwconv1d_planes(x, wt, bias, out="f32")  # fp32 in -> fp32 out
     assert torch.equal(got32, ref)
     assert (got.float() - ref).abs().max() < 1e-4
+
+
+@pytest.mark.parametrize("npass,tol", [(3, 5e-5), (1, 3e-2)])
+@pytest.mark.parametrize("m,f", [(128, 256), (1000, 1024), (40000, 1024), (333, 2048)])
+def test_ffn_fused_tc(m, f, npass, tol):
+    """LayerNorm(res + relu(u.W1^T + b1).W2^T + b2) in one kernel vs an fp64 restatement"""
+    import torch.nn.functional as F
+
+    from lightningfastspeech2_b200 import ops
+
+    g = torch.Generator().manual_seed(m + f)
+    d = 256
+    u = torch.randn(m, d, generator=g)
+    res = torch.randn(m, d, generator=g)
+    w1 = torch.randn(f, d, generator=g) / d ** 0.5
+    w2 = torch.randn(d, f, generator=g) / f ** 0.5
+    b1, b2 = torch.randn(f, generator=g) * 0.1, torch.randn(d, generator=g) * 0.1
+    gam, bet = 1 + 0.1 * torch.randn(d, generator=g), 0.1 * torch.randn(d, generator=g)
+    ref = F.layer_norm(res.double() + torch.relu(u.double() @ w1.double().t() + b1.double()) @ w2.double().t() + b2.double(),
+                       (d,), gam.double(), bet.double(), 1e-5)
+    dev = "cuda"
+    sp = lambda t: ops.split_bf16(t.to(dev).contiguous())
+    out = ops.ffn_fused_tc(sp(u), sp(w1), b1.to(dev), sp(w2), b2.to(dev), sp(res), gam.to(dev), bet.to(dev), 1e-5, npass=npass)
+    err = (out.float().cpu().double() - ref).abs().max().item()
+    print(f"ffn_fused m={m} f={f} npass={npass}: max err {err:.3e}")
+    assert err < tol, err
