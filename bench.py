@@ -609,13 +609,17 @@ def run_lfs2(args):
                        "l2": "no flush: every activation tensor of a step (>=168 MB) exceeds the 126 MB L2",
                        "parallelism": f"utterance-sharded x{world}, no collective"},
             "clocks": clocks,
-            "e2e": {"value": e2e_all / (ms_e2e * 1e-3), "unit": UNIT,
+            # end to end through the public API with HOST buffers: every step copies its inputs from pinned host memory
+            # and its mel + mask back to pinned host memory, and the host reads the mask.  `value` = the generation-loop
+            # API (pipeline.SynthesisStream, depth 2: step i's read-back overlaps step i+1's kernels);
+            # `sequential` = the same work with a blocking read-back after every model(batch) call.
+            "e2e": {"value": piped_all / (ms_piped * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pinned.values()) * world,
                     "d2h_bytes_per_step": (mel_host.numel() * 4 + mask_host.numel() + 8) * world,
-                    "ms_per_step": ms_e2e / args.steps,
-                    "pipelined": {"value": piped_all / (ms_piped * 1e-3), "ms_per_step": ms_piped / args.steps,
-                                  "what": "same copies every step; D2H of step i on a second stream overlaps step "
-                                          "i+1 (pipeline.SynthesisStream, depth 2)"}},
+                    "ms_per_step": ms_piped / args.steps,
+                    "api": "lightningfastspeech2_b200.pipeline.SynthesisStream(model).submit / collect",
+                    "sequential": {"value": e2e_all / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / args.steps,
+                                   "api": "model(batch, inference=True); mel.cpu()"}},
             "gpu_launches": launches,
             "roofline": roofline,
             "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
