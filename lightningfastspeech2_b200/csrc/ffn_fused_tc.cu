@@ -3,11 +3,12 @@
 //     out = LayerNorm( x1 + relu(u . W11^T + b11) . W_eff^T + b_eff )          u = dwconv(x1), d = 256
 //
 // in ONE kernel: the F-wide intermediate v = relu(.) never leaves the SM.  Per 128-row tile and per
-// 256-column chunk c of F:
-//     G1  acc1 (TMEM, fp32 128 x 256)  = u . W11[c]^T                 SS form: u and W11 slabs by TMA
+// 128-column chunk c of F (two acc1 buffers, so the conversion of chunk c runs under the MMAs of chunk c+1):
+//     G1  acc1[c&1] (TMEM, fp32 128 x 128)  = u . W11[c]^T            SS form: u and W11 slabs by TMA
 //     E1  8 epilogue warps: acc1 + b11, ReLU, split into bf16 hi/lo pairs, written back IN PLACE into the same
 //         tensor-memory columns (per 32-column block: 16 packed hi columns, 16 packed lo columns)
 //     G2  acc2 (TMEM, fp32 128 x 256) += v[c] . W_eff[:, c]^T        TS form: A = v read from tensor memory
+// tensor-pipe order: G1(0) | G1(1) G2(0) | G1(2) G2(1) | ...
 // then the residual x1 rides the tensor core (hi.I + lo.I, as in gemm_tc.cu), and the epilogue does
 // + b_eff, LayerNorm over the 256 columns and leaves as bf16 hi/lo planes through swizzled staging + TMA stores.
 // HBM traffic per row: read u (1 KB) + x1 (1 KB), write out (1 KB) -- the unfused pair moves 11 KB.
@@ -23,7 +24,7 @@ namespace tc {
 constexpr int kFM = 128;      // rows per tile
 constexpr int kFK = 32;       // k-slab
 constexpr int kFD = 256;      // model width = K of G1 = N of G2 = LayerNorm width
-constexpr int kFC = 256;      // F chunk = N of G1 = K of G2
+constexpr int kFC = 128;      // F chunk = N of G1 = K of G2
 constexpr int kFThreads = 320;
 constexpr int kFStageChunk = kFM * 32 * 4;  // 16 KB staging chunk (hi | lo planes of 128 x 32)
 
@@ -40,12 +41,16 @@ struct FfnParams {
 
 template <int NPASS>
 struct FfnSmem {
+  // one 32 KB stage, three uses:
+  //   G1       : u_hi 8K | W11_hi 8K | u_lo 8K | W11_lo 8K          (slab = 128 rows x 32 k per operand)
+  //   G2       : W_eff_hi 16K | W_eff_lo 16K                        (slab = 256 n-rows x 32 k)
+  //   residual : R_hi 8K | R_lo 8K | I_hi 16K
   static constexpr int kAPlane = kFM * kFK * 2;   // 8 KB
-  static constexpr int kWPlane = kFC * kFK * 2;   // 16 KB
-  static constexpr int kStage = 2 * kAPlane + (NPASS == 3 ? 2 : 1) * kWPlane;  // residual slabs always carry R_lo
-  static constexpr int kOffWHi = kAPlane;
-  static constexpr int kOffALo = kAPlane + kWPlane;
-  static constexpr int kOffWLo = 2 * kAPlane + kWPlane;
+  static constexpr int kW2Plane = kFD * kFK * 2;  // 16 KB
+  static constexpr int kStage = 32 * 1024;
+  static constexpr int kG1W1Hi = kAPlane, kG1ALo = 2 * kAPlane, kG1W1Lo = 3 * kAPlane;
+  static constexpr int kG2Lo = kW2Plane;
+  static constexpr int kResLo = kAPlane, kResI = 2 * kAPlane;
   static constexpr int kMaxF = 2048;
   static constexpr int kFixed = 4 * kFStageChunk + kMaxF * 4 + 3 * kFD * 4 + 2 * 2 * kFM * 8 + 1024;
   static constexpr int kStages = (226 * 1024 - kFixed) / kStage > 6 ? 6 : (226 * 1024 - kFixed) / kStage;
@@ -55,7 +60,6 @@ struct FfnSmem {
   static constexpr int kOffStats = kOffVec + 3 * kFD * 4;
   static constexpr int kTotal = kStages * kStage + kFixed;
   static_assert(kStages >= 2, "not enough shared memory for a pipeline");
-  static_assert(kStage % 1024 == 0, "stage must keep 1024-byte alignment");
 };
 
 __device__ __forceinline__ void f_tma_store_3d(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
@@ -89,7 +93,7 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc1_full, v_ready, acc2_full, acc2_empty;
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc1_full[2], v_ready[2], acc2_full, acc2_empty;
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -104,8 +108,10 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(&acc1_full, 1);
-    mbar_init(&v_ready, 8);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&acc1_full[i], 1);
+      mbar_init(&v_ready[i], 8);
+    }
     mbar_init(&acc2_full, 1);
     mbar_init(&acc2_empty, 8);
     fence_barrier_init();
@@ -125,7 +131,7 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  const uint32_t t_acc1 = tmem_base, t_acc2 = tmem_base + 256;
+  const uint32_t t_acc1 = tmem_base, t_acc2 = tmem_base + 256;  // acc1 buffer b: columns [128 b, 128 b + 128)
 
   if (warp == 0) {
     // ===================== TMA producer: slabs in exactly the order the MMA warp consumes them =====================
@@ -138,48 +144,56 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
           phase ^= 1;
         }
       };
+      auto load_g1 = [&](int r0, int c) {  // u slab + W11 slab, 8 slabs
+        for (int ks = 0; ks < kSlabs; ++ks) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * L::kStage;
+          mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 4 : 2) * L::kAPlane);
+          tma_load_3d(st, &map_u_hi, &full_bar[stage], ks * kFK, r0, 0);
+          tma_load_3d(st + L::kG1W1Hi, &map_w1_hi, &full_bar[stage], ks * kFK, c * kFC, 0);
+          if (NPASS == 3) {
+            tma_load_3d(st + L::kG1ALo, &map_u_lo, &full_bar[stage], ks * kFK, r0, 0);
+            tma_load_3d(st + L::kG1W1Lo, &map_w1_lo, &full_bar[stage], ks * kFK, c * kFC, 0);
+          }
+          next();
+        }
+      };
+      auto load_g2 = [&](int c) {  // W_eff slab only (A = v lives in tensor memory), 4 slabs
+        for (int ks = 0; ks < kFC / kFK; ++ks) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* st = smem + stage * L::kStage;
+          mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 2 : 1) * L::kW2Plane);
+          tma_load_3d(st, &map_w2_hi, &full_bar[stage], c * kFC + ks * kFK, 0, 0);
+          if (NPASS == 3) tma_load_3d(st + L::kG2Lo, &map_w2_lo, &full_bar[stage], c * kFC + ks * kFK, 0, 0);
+          next();
+        }
+      };
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const int r0 = tile * kFM;
-        for (int c = 0; c < nchunks; ++c) {
-          for (int ks = 0; ks < kSlabs; ++ks) {  // G1: u slab + W11 slab
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = smem + stage * L::kStage;
-            mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 2 : 1) * (L::kAPlane + L::kWPlane));
-            tma_load_3d(st, &map_u_hi, &full_bar[stage], ks * kFK, r0, 0);
-            tma_load_3d(st + L::kOffWHi, &map_w1_hi, &full_bar[stage], ks * kFK, c * kFC, 0);
-            if (NPASS == 3) {
-              tma_load_3d(st + L::kOffALo, &map_u_lo, &full_bar[stage], ks * kFK, r0, 0);
-              tma_load_3d(st + L::kOffWLo, &map_w1_lo, &full_bar[stage], ks * kFK, c * kFC, 0);
-            }
-            next();
-          }
-          for (int ks = 0; ks < kSlabs; ++ks) {  // G2: W_eff slab only (A = v lives in tensor memory)
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* st = smem + stage * L::kStage;
-            mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 2 : 1) * L::kWPlane);
-            tma_load_3d(st + L::kOffWHi, &map_w2_hi, &full_bar[stage], c * kFC + ks * kFK, 0, 0);
-            if (NPASS == 3) tma_load_3d(st + L::kOffWLo, &map_w2_lo, &full_bar[stage], c * kFC + ks * kFK, 0, 0);
-            next();
-          }
+        load_g1(r0, 0);
+        for (int c = 0; c < nchunks; ++c) {  // same order as the MMA warp: G1(c+1) is issued before G2(c)
+          if (c + 1 < nchunks) load_g1(r0, c + 1);
+          load_g2(c);
         }
         for (int ks = 0; ks < kSlabs; ++ks) {  // residual: R_hi, R_lo against the identity block
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * L::kStage;
-          mbar_expect_tx(&full_bar[stage], 2 * L::kAPlane + L::kWPlane);
+          mbar_expect_tx(&full_bar[stage], 2 * L::kAPlane + L::kW2Plane);
           tma_load_3d(st, &map_r_hi, &full_bar[stage], ks * kFK, r0, 0);
-          tma_load_3d(st + L::kOffALo, &map_r_lo, &full_bar[stage], ks * kFK, r0, 0);
-          tma_load_3d(st + L::kOffWHi, &map_ident, &full_bar[stage], ks * kFK, 0, 0);
+          tma_load_3d(st + L::kResLo, &map_r_lo, &full_bar[stage], ks * kFK, r0, 0);
+          tma_load_3d(st + L::kResI, &map_ident, &full_bar[stage], ks * kFK, 0, 0);
           next();
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc = make_idesc(kFmtBF16, kFM, kFC, 0, 0);  // M128 x N256, K-major operands
+    constexpr uint32_t idesc1 = make_idesc(kFmtBF16, kFM, kFC, 0, 0);  // G1: M128 x N128
+    constexpr uint32_t idesc2 = make_idesc(kFmtBF16, kFM, kFD, 0, 0);  // G2 / residual: M128 x N256
     const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 512, kSwizzle64);
     int stage = 0;
     uint32_t phase = 0;
-    uint32_t chunk_ctr = 0;
+    uint32_t chunk_ctr = 0;  // chunks since kernel start: buffer = ctr & 1, barrier parity = (ctr >> 1) & 1
     int it = 0;
     auto next = [&]() {
       if (++stage == kStages) {
@@ -187,53 +201,59 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
         phase ^= 1;
       }
     };
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
-        // ---- G1: acc1 = u . W11[c]^T ----
-        for (int ks = 0; ks < kSlabs; ++ks) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          if (elect_one()) {
-            const uint64_t a_hi = desc_advance(d0, stage * L::kStage);
-            const uint64_t w_hi = desc_advance(a_hi, L::kOffWHi);
-            const uint64_t a_lo = desc_advance(a_hi, L::kOffALo);
-            const uint64_t w_lo = desc_advance(a_hi, L::kOffWLo);
-            if (ks == 0) umma_f16_c<false>(t_acc1, a_hi, w_hi, idesc);
-            else umma_f16_c<true>(t_acc1, a_hi, w_hi, idesc);
-            umma_f16_c<true>(t_acc1, desc_advance(a_hi, 32), desc_advance(w_hi, 32), idesc);
-            if (NPASS == 3) {
-              umma_f16_c<true>(t_acc1, a_lo, w_hi, idesc);
-              umma_f16_c<true>(t_acc1, desc_advance(a_lo, 32), desc_advance(w_hi, 32), idesc);
-              umma_f16_c<true>(t_acc1, a_hi, w_lo, idesc);
-              umma_f16_c<true>(t_acc1, desc_advance(a_hi, 32), desc_advance(w_lo, 32), idesc);
-            }
-            umma_commit(&empty_bar[stage]);
-            if (ks + 1 == kSlabs) umma_commit(&acc1_full);
+    auto issue_g1 = [&](uint32_t ctr) {  // acc1[ctr & 1] = u . W11[chunk]^T
+      const uint32_t acc = t_acc1 + 128 * (ctr & 1);
+      for (int ks = 0; ks < kSlabs; ++ks) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t a_hi = desc_advance(d0, stage * L::kStage);
+          const uint64_t w_hi = desc_advance(a_hi, L::kG1W1Hi);
+          const uint64_t a_lo = desc_advance(a_hi, L::kG1ALo);
+          const uint64_t w_lo = desc_advance(a_hi, L::kG1W1Lo);
+          if (ks == 0) umma_f16_c<false>(acc, a_hi, w_hi, idesc1);
+          else umma_f16_c<true>(acc, a_hi, w_hi, idesc1);
+          umma_f16_c<true>(acc, desc_advance(a_hi, 32), desc_advance(w_hi, 32), idesc1);
+          if (NPASS == 3) {
+            umma_f16_c<true>(acc, a_lo, w_hi, idesc1);
+            umma_f16_c<true>(acc, desc_advance(a_lo, 32), desc_advance(w_hi, 32), idesc1);
+            umma_f16_c<true>(acc, a_hi, w_lo, idesc1);
+            umma_f16_c<true>(acc, desc_advance(a_hi, 32), desc_advance(w_lo, 32), idesc1);
           }
-          __syncwarp();
-          next();
+          umma_commit(&empty_bar[stage]);
+          if (ks + 1 == kSlabs) umma_commit(&acc1_full[ctr & 1]);
         }
+        __syncwarp();
+        next();
+      }
+    };
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      issue_g1(chunk_ctr);
+      for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
+        // G1 of the next chunk goes first: it runs on the tensor pipe while the epilogue warps convert chunk c.
+        // (its accumulator buffer was last read by G2(c-1), issued earlier: tcgen05.mma executes in issue order)
+        if (c + 1 < nchunks) issue_g1(chunk_ctr + 1);
         // ---- G2: acc2 += v[c] . W_eff[:, c]^T, A = v from tensor memory (written in place over acc1) ----
-        mbar_wait(&v_ready, chunk_ctr & 1);
+        mbar_wait(&v_ready[chunk_ctr & 1], (chunk_ctr >> 1) & 1);
         // the first G2 of a tile overwrites acc2: the previous tile's LayerNorm epilogue must have drained it
-        // (G1 of this tile was already issued and ran under that epilogue)
         if (c == 0) mbar_wait(&acc2_empty, (it & 1) ^ 1);
         tc_fence_after();
-        for (int ks = 0; ks < kSlabs; ++ks) {
+        const uint32_t vbase = t_acc1 + 128 * (chunk_ctr & 1);
+        for (int ks = 0; ks < kFC / kFK; ++ks) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           if (elect_one()) {
-            const uint64_t w_hi = desc_advance(d0, stage * L::kStage + L::kOffWHi);
-            const uint64_t w_lo = desc_advance(d0, stage * L::kStage + L::kOffWLo);
-            const uint32_t v_hi = t_acc1 + 32 * ks, v_lo = v_hi + 16;  // packed pairs: 8 columns per k16
-            if (c == 0 && ks == 0) umma_f16_ts_c<false>(t_acc2, v_hi, w_hi, idesc);
-            else umma_f16_ts_c<true>(t_acc2, v_hi, w_hi, idesc);
-            umma_f16_ts_c<true>(t_acc2, v_hi + 8, desc_advance(w_hi, 32), idesc);
+            const uint64_t w_hi = desc_advance(d0, stage * L::kStage);
+            const uint64_t w_lo = desc_advance(w_hi, L::kG2Lo);
+            const uint32_t v_hi = vbase + 32 * ks, v_lo = v_hi + 16;  // packed pairs: 8 columns per k16
+            if (c == 0 && ks == 0) umma_f16_ts_c<false>(t_acc2, v_hi, w_hi, idesc2);
+            else umma_f16_ts_c<true>(t_acc2, v_hi, w_hi, idesc2);
+            umma_f16_ts_c<true>(t_acc2, v_hi + 8, desc_advance(w_hi, 32), idesc2);
             if (NPASS == 3) {
-              umma_f16_ts_c<true>(t_acc2, v_lo, w_hi, idesc);
-              umma_f16_ts_c<true>(t_acc2, v_lo + 8, desc_advance(w_hi, 32), idesc);
-              umma_f16_ts_c<true>(t_acc2, v_hi, w_lo, idesc);
-              umma_f16_ts_c<true>(t_acc2, v_hi + 8, desc_advance(w_lo, 32), idesc);
+              umma_f16_ts_c<true>(t_acc2, v_lo, w_hi, idesc2);
+              umma_f16_ts_c<true>(t_acc2, v_lo + 8, desc_advance(w_hi, 32), idesc2);
+              umma_f16_ts_c<true>(t_acc2, v_hi, w_lo, idesc2);
+              umma_f16_ts_c<true>(t_acc2, v_hi + 8, desc_advance(w_lo, 32), idesc2);
             }
             umma_commit(&empty_bar[stage]);
           }
@@ -247,12 +267,12 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
         tc_fence_after();
         if (elect_one()) {
           const uint64_t a_hi = desc_advance(d0, stage * L::kStage);
-          const uint64_t w_hi = desc_advance(a_hi, L::kOffWHi);
-          const uint64_t a_lo = desc_advance(a_hi, L::kOffALo);
-          umma_f16_c<true>(t_acc2, a_hi, w_hi, idesc);
-          umma_f16_c<true>(t_acc2, desc_advance(a_hi, 32), desc_advance(w_hi, 32), idesc);
-          umma_f16_c<true>(t_acc2, a_lo, w_hi, idesc);
-          umma_f16_c<true>(t_acc2, desc_advance(a_lo, 32), desc_advance(w_hi, 32), idesc);
+          const uint64_t a_lo = desc_advance(a_hi, L::kResLo);
+          const uint64_t w_hi = desc_advance(a_hi, L::kResI);
+          umma_f16_c<true>(t_acc2, a_hi, w_hi, idesc2);
+          umma_f16_c<true>(t_acc2, desc_advance(a_hi, 32), desc_advance(w_hi, 32), idesc2);
+          umma_f16_c<true>(t_acc2, a_lo, w_hi, idesc2);
+          umma_f16_c<true>(t_acc2, desc_advance(a_lo, 32), desc_advance(w_hi, 32), idesc2);
           umma_commit(&empty_bar[stage]);
           if (ks + 1 == kSlabs) umma_commit(&acc2_full);
         }
@@ -278,11 +298,11 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
       const int r0 = tile * kFM;
       // ---- E1 per F chunk: acc1 -> relu(acc1 + b1) as bf16 hi/lo pairs, in place ----
       for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
-        mbar_wait(&acc1_full, chunk_ctr & 1);
+        mbar_wait(&acc1_full[chunk_ctr & 1], (chunk_ctr >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int j = 4 * half; j < 4 * half + 4; ++j) {
-          const uint32_t ta = t_acc1 + lane_off + 32 * j;
+        for (int j = 2 * half; j < 2 * half + 2; ++j) {  // 4 blocks of 32 columns per chunk, 2 per warp of the pair
+          const uint32_t ta = t_acc1 + 128 * (chunk_ctr & 1) + lane_off + 32 * j;
           tmem_ld32(ta, v);
           uint32_t hi[16], lo[16];
           const float* bb = b1s + c * kFC + 32 * j;
@@ -297,7 +317,7 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&v_ready);
+        if (lane == 0) mbar_arrive(&v_ready[chunk_ctr & 1]);
       }
       // ---- final epilogue: acc2 + b2 -> LayerNorm -> hi/lo planes ----
       mbar_wait(&acc2_full, it & 1);
