@@ -166,6 +166,23 @@ LFS2_API int lfs2_gemm_tc(const void* a_hi, const void* a_lo, int batch, int t, 
                           const float* gamma, const float* beta, float eps,
                           float* out_f32, void* out_hi, void* out_lo, int npass, void* stream);
 
+/* lfs2_gemm_tc / lfs2_dwconv1d_planes restricted to the rows a caller needs: for utterance b every 128-row tile
+ * that starts at or after row_limit[b] + limit_extra is skipped and its output rows are left untouched (A is
+ * tiled per utterance: batch x t).  Used by the variance predictors, whose outputs on PAD rows are masked to 0 by
+ * construction (model.py:518), so skipping rows farther than the conv halo beyond an utterance's end changes no
+ * result bit.  row_limit = lfs2_mask_lengths of the padding mask. */
+LFS2_API int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch, int t, int d, int taps,
+                                  const void* w_hi, const void* w_lo, int n, const float* bias, int relu,
+                                  const void* res_hi, const void* res_lo, const void* ident_hi,
+                                  const float* gamma, const float* beta, float eps, float* out_f32, void* out_hi,
+                                  void* out_lo, int npass, const int* row_limit, int limit_extra, void* stream);
+LFS2_API int lfs2_dwconv1d_planes_limited(const float* x, const void* x_hi, const void* x_lo, const float* wt,
+                                          const float* bias, float* out, void* out_hi, void* out_lo, int batch,
+                                          int t, int d, int ksize, const int* row_limit, int limit_extra,
+                                          void* stream);
+/* lengths[b] = 1 + index of the last row with pad_mask[b, .] == 0 (0 if all PAD); pad_mask NULL -> t */
+LFS2_API int lfs2_mask_lengths(const uint8_t* pad_mask, int* lengths, int batch, int t, void* stream);
+
 /* Fused position-wise FFN tail of the depthwise FFTBlock (model.py:118-122 after the depthwise conv; model width 256):
  *   out = LayerNorm( res + relu(u . w1^T + b1) . w2^T + b2 ; gamma, beta, eps )
  * u, res, out: (m, 256) bf16 hi/lo planes; w1 (f, 256), w2 (256, f) hi/lo planes (w2 = the folded

@@ -35,6 +35,10 @@ SIGNATURES = {
     "lfs2_length_regulate_scatter_ex": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "lfs2_gemm_tc": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i,
                      _vp],
+    "lfs2_gemm_tc_limited": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp,
+                             _i, _vp, _i, _vp],
+    "lfs2_dwconv1d_planes_limited": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "lfs2_mask_lengths": [_vp, _vp, _i, _i, _vp],
     "lfs2_ffn_fused_tc": [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp],
     "lfs2_attention_tc_workspace_bytes": [_i],
     "lfs2_attention_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],

@@ -473,6 +473,15 @@ extern "C" {
 
 int lfs2_attention_tc_workspace_bytes(int batch) { return batch > 0 ? batch * (int)sizeof(int) : 0; }
 
+int lfs2_mask_lengths(const uint8_t* pad_mask, int* lengths, int batch, int t, void* stream) {
+  LFS2_REQUIRE(lengths, LFS2_ERR_INVALID_ARG, "mask_lengths: null pointer");
+  if (batch == 0) return LFS2_OK;
+  LFS2_REQUIRE(batch > 0 && t >= 0, LFS2_ERR_INVALID_ARG, "mask_lengths: bad shape");
+  attn_kend_kernel<<<ceil_div((long long)batch * 32, 128), 128, 0, (cudaStream_t)stream>>>(pad_mask, lengths, batch, t);
+  LFS2_CHECK_LAUNCH("mask_lengths");
+  return LFS2_OK;
+}
+
 int lfs2_attention_tc(const void* qkv_hi, const void* qkv_lo, const uint8_t* key_padding_mask, void* ctx_hi,
                       void* ctx_lo, float* ctx_f32, void* workspace, int batch, int t, int d, int nhead, int npass,
                       void* stream) {

@@ -359,7 +359,8 @@ template <int K, int NT, int kDwTile, bool IN_PLANES>
 __global__ void __launch_bounds__(kDwCh4 * (kDwTile / NT), 2)
 dwconv1d_k_kernel(const float4* __restrict__ x, const uint2* __restrict__ x_hi, const uint2* __restrict__ x_lo,
                   const float4* __restrict__ wt, const float4* __restrict__ bias, float4* __restrict__ out,
-                  uint2* __restrict__ out_hi, uint2* __restrict__ out_lo, int t, int d4) {
+                  uint2* __restrict__ out_hi, uint2* __restrict__ out_lo, int t, int d4,
+                  const int* __restrict__ row_limit, int limit_extra) {
   extern __shared__ float4 xs[];  // [kDwTile + K - 1][kDwCh4]
   constexpr int H = (K - 1) / 2;
   constexpr int kRows = kDwTile + K - 1;
@@ -367,6 +368,8 @@ dwconv1d_k_kernel(const float4* __restrict__ x, const uint2* __restrict__ x_hi, 
   const int t0 = blockIdx.x * kDwTile;
   const int cb = blockIdx.y * kDwCh4;  // first float4 channel group of this CTA
   const int b = blockIdx.z;
+  // rows the caller does not need (same 128-row granularity as the tensor-core GEMM that consumes the result)
+  if (row_limit && (t0 & ~127) >= __ldg(row_limit + b) + limit_extra) return;
   const int nch = min(kDwCh4, d4 - cb);
   const size_t base = (size_t)b * t * d4 + cb;
 
@@ -442,7 +445,8 @@ dwconv1d_k_kernel(const float4* __restrict__ x, const uint2* __restrict__ x_hi, 
 
 template <int K, int NT, int kDwTile>
 static int launch_dwconv_k(const float* x, const void* x_hi, const void* x_lo, const float* wt, const float* bias,
-                           float* out, void* out_hi, void* out_lo, int batch, int t, int d, cudaStream_t s) {
+                           float* out, void* out_hi, void* out_lo, int batch, int t, int d, const int* row_limit,
+                           int limit_extra, cudaStream_t s) {
   constexpr int kThreads = kDwCh4 * (kDwTile / NT);
   constexpr int kSmem = (kDwTile + K - 1) * kDwCh4 * 16;
   dim3 grid(ceil_div(t, kDwTile), ceil_div(d / 4, kDwCh4), batch);
@@ -459,10 +463,11 @@ static int launch_dwconv_k(const float* x, const void* x_hi, const void* x_lo, c
   }
   if (x)
     kf<<<grid, kThreads, kSmem, s>>>((const float4*)x, nullptr, nullptr, (const float4*)wt, (const float4*)bias,
-                                     (float4*)out, (uint2*)out_hi, (uint2*)out_lo, t, d / 4);
+                                     (float4*)out, (uint2*)out_hi, (uint2*)out_lo, t, d / 4, row_limit, limit_extra);
   else
     kp<<<grid, kThreads, kSmem, s>>>(nullptr, (const uint2*)x_hi, (const uint2*)x_lo, (const float4*)wt,
-                                     (const float4*)bias, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, t, d / 4);
+                                     (const float4*)bias, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, t, d / 4,
+                                     row_limit, limit_extra);
   return LFS2_OK;
 }
 
@@ -572,6 +577,12 @@ int lfs2_dwconv1d(const float* x, const float* wt, const float* bias, float* out
 
 int lfs2_dwconv1d_planes(const float* x, const void* x_hi, const void* x_lo, const float* wt, const float* bias,
                          float* out, void* out_hi, void* out_lo, int batch, int t, int d, int ksize, void* stream) {
+  return lfs2_dwconv1d_planes_limited(x, x_hi, x_lo, wt, bias, out, out_hi, out_lo, batch, t, d, ksize, nullptr, 0, stream);
+}
+
+int lfs2_dwconv1d_planes_limited(const float* x, const void* x_hi, const void* x_lo, const float* wt, const float* bias,
+                                 float* out, void* out_hi, void* out_lo, int batch, int t, int d, int ksize,
+                                 const int* row_limit, int limit_extra, void* stream) {
   LFS2_REQUIRE((x || (x_hi && x_lo)) && wt && bias && (out || out_hi), LFS2_ERR_INVALID_ARG, "dwconv1d: null pointer");
   LFS2_REQUIRE(!x || !x_hi, LFS2_ERR_INVALID_ARG, "dwconv1d: give the input as fp32 OR as planes");
   LFS2_REQUIRE(!out_hi == !out_lo, LFS2_ERR_INVALID_ARG, "dwconv1d: out_hi and out_lo go together");
@@ -587,7 +598,8 @@ int lfs2_dwconv1d_planes(const float* x, const void* x_hi, const void* x_lo, con
   LFS2_REQUIRE(batch <= 65535, LFS2_ERR_UNSUPPORTED, "dwconv1d: batch exceeds the grid limit");
 #define LFS2_DW_CASE(K, TT)                                                                          \
   case K: {                                                                                          \
-    int rc = launch_dwconv_k<K, TT, (K <= 9 ? 64 : 32)>(x, x_hi, x_lo, wt, bias, out, out_hi, out_lo, batch, t, d, s);   \
+    int rc = launch_dwconv_k<K, TT, (K <= 9 ? 64 : 32)>(x, x_hi, x_lo, wt, bias, out, out_hi, out_lo, batch, t, d,       \
+                                                        row_limit, limit_extra, s);                                   \
     if (rc != LFS2_OK) return rc;                                                                    \
   } break;
   switch (ksize) {
@@ -595,6 +607,7 @@ int lfs2_dwconv1d_planes(const float* x, const void* x_hi, const void* x_lo, con
     LFS2_DW_CASE(11, 8) LFS2_DW_CASE(13, 8) LFS2_DW_CASE(15, 8) LFS2_DW_CASE(17, 8) LFS2_DW_CASE(19, 8)
     LFS2_DW_CASE(21, 8) LFS2_DW_CASE(23, 8) LFS2_DW_CASE(25, 8)
     default: {
+      LFS2_REQUIRE(!row_limit, LFS2_ERR_UNSUPPORTED, "dwconv1d: row limits need an odd kernel size <= 25");
       int nchunk = ceil_div(t, kDwT);
       size_t total = (size_t)batch * nchunk * (d / 4);
       if (x)

@@ -41,7 +41,14 @@ struct GemmTcParams {
   const float* gamma;           // LN only (n == N_TILE)
   const float* beta;
   float eps;
+  const int* row_limit;         // (batch) or null: tiles of utterance b that start at or after row_limit[b] + limit_extra
+  int limit_extra;              //   are skipped entirely (their output rows are left untouched)
 };
+
+// rows of utterance b at or beyond this are not needed by the caller (see lfs2_gemm_tc_limited)
+__device__ __forceinline__ bool tile_skipped(const GemmTcParams& p, int b, int t0) {
+  return p.row_limit != nullptr && t0 >= __ldg(p.row_limit + b) + p.limit_extra;
+}
 
 template <int N_TILE, int NPASS, bool LN>
 struct SmemLayout {
@@ -135,6 +142,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
         int b = m_tile / p.m_tiles_per_batch, t0 = (m_tile % p.m_tiles_per_batch) * kBM;
         int n0 = n_tile * N_TILE;
+        if (tile_skipped(p, b, t0)) continue;
         for (int ks = 0; ks < k_slabs; ++ks) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * L::kStage;
@@ -169,8 +177,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 512, kSwizzle64);
     int stage = 0;
     uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    int it = -1;  // counts the tiles this CTA actually processes (skipped tiles use no accumulator)
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      {
+        const int m_tile = tile / p.n_tiles;
+        if (tile_skipped(p, m_tile / p.m_tiles_per_batch, (m_tile % p.m_tiles_per_batch) * kBM)) continue;
+      }
+      ++it;
       int acc = it & 1;
       uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -221,14 +234,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     uint8_t* staging = smem + L::kOffStaging + half * 2 * kStageChunk;
     constexpr int kHalfChunks = kChunks / 2;
     const int c_begin = half * kHalfChunks, c_end = c_begin + kHalfChunks;
-    int it = 0;
+    int it = -1;
     uint32_t chunk_ctr = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      int acc = it & 1;
-      uint32_t acc_phase = (it >> 1) & 1;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
       int b = m_tile / p.m_tiles_per_batch, t0 = (m_tile % p.m_tiles_per_batch) * kBM;
       int n0 = n_tile * N_TILE;
+      if (tile_skipped(p, b, t0)) continue;
+      ++it;
+      int acc = it & 1;
+      uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       uint32_t taddr = tmem_base + acc * kAccCols + ((uint32_t)(quad * 32) << 16);
@@ -402,6 +417,14 @@ int lfs2_gemm_tc(const void* a_hi, const void* a_lo, int batch, int t, int d, in
                  const void* w_lo, int n, const float* bias, int relu, const void* res_hi, const void* res_lo,
                  const void* ident_hi, const float* gamma, const float* beta, float eps, float* out_f32,
                  void* out_hi, void* out_lo, int npass, void* stream) {
+  return lfs2_gemm_tc_limited(a_hi, a_lo, batch, t, d, taps, w_hi, w_lo, n, bias, relu, res_hi, res_lo, ident_hi, gamma,
+                              beta, eps, out_f32, out_hi, out_lo, npass, nullptr, 0, stream);
+}
+
+int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch, int t, int d, int taps, const void* w_hi,
+                         const void* w_lo, int n, const float* bias, int relu, const void* res_hi, const void* res_lo,
+                         const void* ident_hi, const float* gamma, const float* beta, float eps, float* out_f32,
+                         void* out_hi, void* out_lo, int npass, const int* row_limit, int limit_extra, void* stream) {
   LFS2_REQUIRE(a_hi && w_hi, LFS2_ERR_INVALID_ARG, "gemm_tc: null operand");
   LFS2_REQUIRE(npass == 1 || npass == 3, LFS2_ERR_INVALID_ARG, "gemm_tc: npass must be 1 or 3");
   LFS2_REQUIRE(npass == 1 || (a_lo && w_lo), LFS2_ERR_INVALID_ARG, "gemm_tc: npass=3 needs the lo planes");
@@ -459,6 +482,7 @@ int lfs2_gemm_tc(const void* a_hi, const void* a_lo, int batch, int t, int d, in
   p.total_tiles = batch * p.m_tiles_per_batch * p.n_tiles;
   p.has_residual = res_hi != nullptr;
   p.bias = bias; p.relu = relu; p.gamma = gamma; p.beta = beta; p.eps = eps;
+  p.row_limit = row_limit; p.limit_extra = limit_extra;
   cudaStream_t s = (cudaStream_t)stream;
   if (ln) return dispatch_gemm_tc<256, true>(m, p, npass, out_f32 != nullptr, s);
   if (n_tile == 256) return dispatch_gemm_tc<256, false>(m, p, npass, out_f32 != nullptr, s);

@@ -356,9 +356,9 @@ class VarianceConvolutionLayer(nn.Module):
             p["wp_planes"] = ops.split_bf16(p["wp"])
         return p
 
-    def forward(self, x, out="f32"):
+    def forward(self, x, out="f32", row_limit=None):
         """x: fp32 (B,T,d) or Planes; out="planes" keeps the result as hi/lo planes for the next layer
-        (tensor-core path with the fused ReLU+LayerNorm epilogue only)."""
+        (tensor-core path with the fused ReLU+LayerNorm epilogue only).  row_limit: see VariancePredictor."""
         _require_inference(self, self.layers[3].p, "VarianceConvolutionLayer")
         conv, ln = self.layers[0].module, self.layers[2]
         cp = self.__dict__.get("_conv_param_list")
@@ -372,9 +372,11 @@ class VarianceConvolutionLayer(nn.Module):
             fuse = dict(gamma=ln.weight, beta=ln.bias, eps=ln.eps) if fsz == 256 else {}
             out = out if fuse else "f32"
             if self.depthwise:
-                up = ops.dwconv1d_planes(x if isinstance(x, ops.Planes) else x.contiguous(), p["dw_wt"], conv[0].bias)
+                lim = row_limit if fuse else None  # (the unfused LayerNorm kernel has no row limit)
+                up = ops.dwconv1d_planes(x if isinstance(x, ops.Planes) else x.contiguous(), p["dw_wt"], conv[0].bias,
+                                         row_limit=lim)
                 h = ops.gemm_tc(up, p["pw_planes"], conv[1].bias, relu=True, npass=npass, out=out,
-                                tag="predictor_pw_ln_gemm", **fuse)
+                                tag="predictor_pw_ln_gemm", row_limit=lim, **fuse)
             else:
                 xp = x if isinstance(x, ops.Planes) else ops.planes_of(x)
                 h = ops.gemm_tc(xp, p["wp_planes"], conv.bias, taps=self.kernel_size, relu=True, npass=npass, out=out,
@@ -407,11 +409,20 @@ class VariancePredictor(nn.Module):
         self.cwt = cwt
         self.linear = nn.Linear(filter_size, 1)
 
+    skip_pad_tiles = True
+
     def forward(self, x, mask=None, return_conv=False):
+        """The head masks every PAD position to 0 (model.py:518), so only rows within the conv halo of an utterance's
+        last valid position can influence the result: 128-row tiles beyond that are skipped in the depthwise /
+        tensor-core path (bit-identical output; the hidden state `z` of skipped rows is undefined)."""
         z = x
         nl = len(self.layers)
+        lim = None
+        if (self.skip_pad_tiles and mask is not None and not return_conv and not isinstance(x, ops.Planes)
+                and x.dim() == 3 and all(l.depthwise and l.compute_mode != "simt" for l in self.layers)):
+            lim = (ops.mask_lengths(mask), self.halo())
         for i, layer in enumerate(self.layers):
-            z = layer(z, out="planes" if i + 1 < nl else "f32")
+            z = layer(z, out="planes" if i + 1 < nl else "f32", row_limit=lim)
         if isinstance(z, ops.Planes):
             z = ops.merge_planes(z)
         out = ops.rowdot_mask(z, self.linear.weight, self.linear.bias, mask)

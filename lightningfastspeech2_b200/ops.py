@@ -296,8 +296,26 @@ def planes_of(x):
     return p if p is not None else split_bf16(x.contiguous())
 
 
-def dwconv1d_planes(x, wt, bias, out="planes"):
-    """depthwise conv, x (B,T,d) fp32 tensor or Planes, wt (ksize,d) -> Planes (or fp32 if out == "f32")"""
+def _limited_fraction(row_limit, t):
+    """fraction of the (B, t) rows a row-limited launch really processes (profiling only: reads the lengths back)"""
+    if row_limit is None or PROFILE is None:
+        return 1.0
+    lim, extra = row_limit
+    rows = torch.clamp((lim.long() + extra + 127) // 128 * 128, max=t).clamp(min=0).sum().item()
+    return rows / float(lim.numel() * t)
+
+
+def mask_lengths(mask):
+    """(B,T) bool padding mask (True = PAD) -> int32 (B): 1 + index of the last non-PAD position"""
+    _chk(mask, torch.bool, "padding mask", 2)
+    out = torch.empty(mask.shape[0], device=mask.device, dtype=torch.int32)
+    _launch("lfs2_mask_lengths", _p(mask), _p(out), mask.shape[0], mask.shape[1], _s())
+    return out
+
+
+def dwconv1d_planes(x, wt, bias, out="planes", row_limit=None):
+    """depthwise conv, x (B,T,d) fp32 tensor or Planes, wt (ksize,d) -> Planes (or fp32 if out == "f32").
+    row_limit = (lengths int32 (B), extra): 128-row groups starting at or after lengths[b] + extra are skipped."""
     _chk(wt, torch.float32, "dwconv weight", 2)
     if isinstance(x, Planes):
         _chk(x.hi, torch.bfloat16, "dwconv input", 3); _chk(x.lo, torch.bfloat16, "dwconv input", 3)
@@ -308,9 +326,11 @@ def dwconv1d_planes(x, wt, bias, out="planes"):
     b, t, d = shape
     of = torch.empty(shape, device=dev, dtype=torch.float32) if out == "f32" else None
     po = _empty_planes(shape, dev) if out == "planes" else None
-    _launch("lfs2_dwconv1d_planes", _p(xf), _p(xh), _p(xl), _p(wt), _p(bias), _p(of), _p(po.hi if po else None),
-            _p(po.lo if po else None), b, t, d, wt.shape[0], _s(), tag="lfs2_dwconv1d",
-            flops=2.0 * b * t * d * wt.shape[0], nbytes=8.0 * b * t * d)
+    lim, extra = row_limit if row_limit is not None else (None, 0)
+    frac = _limited_fraction(row_limit, t)
+    _launch("lfs2_dwconv1d_planes_limited", _p(xf), _p(xh), _p(xl), _p(wt), _p(bias), _p(of), _p(po.hi if po else None),
+            _p(po.lo if po else None), b, t, d, wt.shape[0], _p(lim), int(extra), _s(), tag="lfs2_dwconv1d",
+            flops=2.0 * b * t * d * wt.shape[0] * frac, nbytes=8.0 * b * t * d * frac)
     return of if out == "f32" else po
 
 
@@ -340,7 +360,7 @@ def _identity_planes(n, device):
 
 
 def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None, eps=LN_EPS, out="f32",
-            npass=3, tag=None):
+            npass=3, tag=None, row_limit=None):
     """a: Planes (B,T,d) [taps>1: Conv1d over T per utterance] or (...,d) for taps == 1;
     w: Planes (n, taps*d); residual: Planes shaped like the output (added on the tensor core,
     LayerNorm epilogues only).  out = "f32" -> fp32 tensor, "planes" -> Planes; shaped like a
@@ -353,7 +373,7 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
     n = w.shape[0]
     if w.shape[1] != taps * d:
         raise ValueError(f"gemm_tc: weight {tuple(w.shape)} does not match taps*d = {taps * d}")
-    if taps == 1:
+    if taps == 1 and row_limit is None:
         batch, t = 1, a.hi.numel() // d
     else:
         if a.hi.dim() != 3:
@@ -372,10 +392,12 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
         _chk(residual.hi, torch.bfloat16, "gemm_tc residual"); _chk(residual.lo, torch.bfloat16, "gemm_tc residual")
         ident = _identity_planes(n, dev)
     m = batch * t
-    _launch("lfs2_gemm_tc", _p(a.hi), _p(a.lo), batch, t, d, taps, _p(w.hi), _p(w.lo), n, _p(bias), int(relu),
+    lim, extra = row_limit if row_limit is not None else (None, 0)
+    m = m * _limited_fraction(row_limit, t)  # rows really processed (for the flop / byte accounting below)
+    _launch("lfs2_gemm_tc_limited", _p(a.hi), _p(a.lo), batch, t, d, taps, _p(w.hi), _p(w.lo), n, _p(bias), int(relu),
             _p(residual.hi if residual is not None else None), _p(residual.lo if residual is not None else None),
             _p(ident), _p(gamma), _p(beta), float(eps), _p(of), _p(po.hi if po else None),
-            _p(po.lo if po else None), npass, _s(), tag=tag or f"gemm_tc_n{n}_k{taps * d}",
+            _p(po.lo if po else None), npass, _p(lim), int(extra), _s(), tag=tag or f"gemm_tc_n{n}_k{taps * d}",
             flops=2.0 * m * n * taps * d,
             nbytes=4.0 * m * d + 4.0 * n * taps * d + 4.0 * m * n + (4.0 * m * n if residual is not None else 0.0))
     return of if out == "f32" else po

@@ -287,3 +287,23 @@ def test_synthesis_stream_pipelining_returns_the_same_results():
     got.append({k: v.clone() for k, v in pipe.collect(prev).items()})
     for r, g in zip(ref, got):
         assert torch.equal(r["mel"].cpu(), g["mel"]) and torch.equal(r["tgt_mask"].cpu(), g["tgt_mask"])
+
+
+def test_predictor_pad_tile_skipping_is_bit_identical():
+    """the variance predictors skip 128-row tiles that lie beyond (last valid row + conv halo): their PAD outputs are
+    masked to 0 anyway, so every output bit -- predictions, bucket indices, mel on ALL positions -- must be unchanged"""
+    from lightningfastspeech2_b200.fastspeech2.model import VariancePredictor
+
+    model, sd, hp = build("C2", 19)
+    batch = synthetic.make_batch(6, 10, 160, seed=19)   # ragged: 50 .. 800 frames, several 128-row tiles of pure PAD
+    with torch.no_grad():
+        VariancePredictor.skip_pad_tiles = False
+        try:
+            full = model(batch, inference=True, force={"want_idx": True})
+        finally:
+            VariancePredictor.skip_pad_tiles = True
+        skip = model(batch, inference=True, force={"want_idx": True})
+    assert int(full["tgt_mask"].sum()) > 3 * 128 * 2  # there is PAD to skip
+    for k in ("mel", "duration_prediction", "duration_rounded", "tgt_mask", "variances_pitch", "variances_energy",
+              "_bucket_pitch", "_bucket_energy"):
+        assert torch.equal(full[k], skip[k]), k
