@@ -175,7 +175,10 @@ LFS2_API int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch,
                                   const void* w_hi, const void* w_lo, int n, const float* bias, int relu,
                                   const void* res_hi, const void* res_lo, const void* ident_hi,
                                   const float* gamma, const float* beta, float eps, float* out_f32, void* out_hi,
-                                  void* out_lo, int npass, const int* row_limit, int limit_extra, void* stream);
+                                  void* out_lo, int npass, const int* row_limit, int limit_extra,
+                                  void* workspace, void* stream);
+/* workspace of lfs2_gemm_tc_limited when row_limit != NULL: the compact list of active row tiles */
+LFS2_API long long lfs2_gemm_tc_limited_workspace_bytes(int batch, int t);
 LFS2_API int lfs2_dwconv1d_planes_limited(const float* x, const void* x_hi, const void* x_lo, const float* wt,
                                           const float* bias, float* out, void* out_hi, void* out_lo, int batch,
                                           int t, int d, int ksize, const int* row_limit, int limit_extra,

@@ -36,7 +36,7 @@ SIGNATURES = {
     "lfs2_gemm_tc": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp, _i,
                      _vp],
     "lfs2_gemm_tc_limited": [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp,
-                             _i, _vp, _i, _vp],
+                             _i, _vp, _i, _vp, _vp],
     "lfs2_dwconv1d_planes_limited": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "lfs2_mask_lengths": [_vp, _vp, _i, _i, _vp],
     "lfs2_ffn_fused_tc": [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp],
@@ -73,7 +73,8 @@ SIGNATURES = {
     "lfs2_adamw_step": [_vp, _vp, _vp, _vp, _ll, _f, _f, _f, _f, _f, _i, _f, _f, _vp, _i, _vp],
 }
 # functions whose return type is not int
-RESTYPES = {"lfs2_attention_bwd_workspace_bytes": (ctypes.c_longlong, [_i, _i, _i])}
+RESTYPES = {"lfs2_attention_bwd_workspace_bytes": (ctypes.c_longlong, [_i, _i, _i]),
+            "lfs2_gemm_tc_limited_workspace_bytes": (ctypes.c_longlong, [_i, _i])}
 
 class Operand(ctypes.Structure):
     """lfs2_operand of include/lfs2.h"""

@@ -41,13 +41,26 @@ struct GemmTcParams {
   const float* gamma;           // LN only (n == N_TILE)
   const float* beta;
   float eps;
-  const int* row_limit;         // (batch) or null: tiles of utterance b that start at or after row_limit[b] + limit_extra
-  int limit_extra;              //   are skipped entirely (their output rows are left untouched)
+  const int* tile_list;         // null, or [0] = number of active m-tiles, [1..] = their indices (b * m_tiles_per_batch + mt):
+                                //   only those row tiles are processed (lfs2_gemm_tc_limited), dealt round-robin to the CTAs
 };
 
-// rows of utterance b at or beyond this are not needed by the caller (see lfs2_gemm_tc_limited)
-__device__ __forceinline__ bool tile_skipped(const GemmTcParams& p, int b, int t0) {
-  return p.row_limit != nullptr && t0 >= __ldg(p.row_limit + b) + p.limit_extra;
+// work item i of this launch -> (m_tile, n_tile); the number of work items is tile_count(p)
+__device__ __forceinline__ int tile_count(const GemmTcParams& p) {
+  return p.tile_list ? __ldg(p.tile_list) * p.n_tiles : p.total_tiles;
+}
+__device__ __forceinline__ void tile_coords(const GemmTcParams& p, int i, int& m_tile, int& n_tile) {
+  n_tile = i % p.n_tiles;
+  m_tile = p.tile_list ? __ldg(p.tile_list + 1 + i / p.n_tiles) : i / p.n_tiles;
+}
+
+// active m-tiles of a row-limited launch: utterance b needs the tiles that start before row_limit[b] + extra
+__global__ void gemm_tile_list_kernel(const int* __restrict__ row_limit, int extra, int batch, int m_tiles_per_batch,
+                                      int* __restrict__ list) {
+  for (int i = threadIdx.x; i < batch * m_tiles_per_batch; i += blockDim.x) {
+    const int b = i / m_tiles_per_batch, mt = i % m_tiles_per_batch;
+    if (mt * kBM < row_limit[b] + extra) list[1 + atomicAdd(list, 1)] = i;
+  }
 }
 
 template <int N_TILE, int NPASS, bool LN>
@@ -138,11 +151,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+      const int ntiles = tile_count(p);
+      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        int n_tile, m_tile;
+        tile_coords(p, tile, m_tile, n_tile);
         int b = m_tile / p.m_tiles_per_batch, t0 = (m_tile % p.m_tiles_per_batch) * kBM;
         int n0 = n_tile * N_TILE;
-        if (tile_skipped(p, b, t0)) continue;
         for (int ks = 0; ks < k_slabs; ++ks) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * L::kStage;
@@ -177,13 +191,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 512, kSwizzle64);
     int stage = 0;
     uint32_t phase = 0;
-    int it = -1;  // counts the tiles this CTA actually processes (skipped tiles use no accumulator)
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      {
-        const int m_tile = tile / p.n_tiles;
-        if (tile_skipped(p, m_tile / p.m_tiles_per_batch, (m_tile % p.m_tiles_per_batch) * kBM)) continue;
-      }
-      ++it;
+    int it = 0;
+    const int ntiles = tile_count(p);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
       int acc = it & 1;
       uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -234,14 +244,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     uint8_t* staging = smem + L::kOffStaging + half * 2 * kStageChunk;
     constexpr int kHalfChunks = kChunks / 2;
     const int c_begin = half * kHalfChunks, c_end = c_begin + kHalfChunks;
-    int it = -1;
+    int it = 0;
     uint32_t chunk_ctr = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int n_tile = tile % p.n_tiles, m_tile = tile / p.n_tiles;
+    const int ntiles = tile_count(p);
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+      int n_tile, m_tile;
+      tile_coords(p, tile, m_tile, n_tile);
       int b = m_tile / p.m_tiles_per_batch, t0 = (m_tile % p.m_tiles_per_batch) * kBM;
       int n0 = n_tile * N_TILE;
-      if (tile_skipped(p, b, t0)) continue;
-      ++it;
       int acc = it & 1;
       uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -413,18 +423,23 @@ using namespace lfs2::tc;
 
 extern "C" {
 
+long long lfs2_gemm_tc_limited_workspace_bytes(int batch, int t) {
+  return batch > 0 && t > 0 ? (1 + (long long)batch * ((t + kBM - 1) / kBM)) * (long long)sizeof(int) : 0;
+}
+
 int lfs2_gemm_tc(const void* a_hi, const void* a_lo, int batch, int t, int d, int taps, const void* w_hi,
                  const void* w_lo, int n, const float* bias, int relu, const void* res_hi, const void* res_lo,
                  const void* ident_hi, const float* gamma, const float* beta, float eps, float* out_f32,
                  void* out_hi, void* out_lo, int npass, void* stream) {
   return lfs2_gemm_tc_limited(a_hi, a_lo, batch, t, d, taps, w_hi, w_lo, n, bias, relu, res_hi, res_lo, ident_hi, gamma,
-                              beta, eps, out_f32, out_hi, out_lo, npass, nullptr, 0, stream);
+                              beta, eps, out_f32, out_hi, out_lo, npass, nullptr, 0, nullptr, stream);
 }
 
 int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch, int t, int d, int taps, const void* w_hi,
                          const void* w_lo, int n, const float* bias, int relu, const void* res_hi, const void* res_lo,
                          const void* ident_hi, const float* gamma, const float* beta, float eps, float* out_f32,
-                         void* out_hi, void* out_lo, int npass, const int* row_limit, int limit_extra, void* stream) {
+                         void* out_hi, void* out_lo, int npass, const int* row_limit, int limit_extra,
+                         void* workspace, void* stream) {
   LFS2_REQUIRE(a_hi && w_hi, LFS2_ERR_INVALID_ARG, "gemm_tc: null operand");
   LFS2_REQUIRE(npass == 1 || npass == 3, LFS2_ERR_INVALID_ARG, "gemm_tc: npass must be 1 or 3");
   LFS2_REQUIRE(npass == 1 || (a_lo && w_lo), LFS2_ERR_INVALID_ARG, "gemm_tc: npass=3 needs the lo planes");
@@ -482,8 +497,19 @@ int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch, int t, i
   p.total_tiles = batch * p.m_tiles_per_batch * p.n_tiles;
   p.has_residual = res_hi != nullptr;
   p.bias = bias; p.relu = relu; p.gamma = gamma; p.beta = beta; p.eps = eps;
-  p.row_limit = row_limit; p.limit_extra = limit_extra;
   cudaStream_t s = (cudaStream_t)stream;
+  p.tile_list = nullptr;
+  if (row_limit) {  // compact list of the row tiles that are needed, built on the device (no host read-back)
+    LFS2_REQUIRE(workspace, LFS2_ERR_INVALID_ARG, "gemm_tc: a row limit needs the tile-list workspace");
+    int* list = reinterpret_cast<int*>(workspace);
+    if (cudaMemsetAsync(list, 0, sizeof(int), s) != cudaSuccess) {
+      set_error("gemm_tc: memset failed");
+      return LFS2_ERR_CUDA;
+    }
+    gemm_tile_list_kernel<<<1, 256, 0, s>>>(row_limit, limit_extra, batch, p.m_tiles_per_batch, list);
+    LFS2_CHECK_LAUNCH("gemm_tile_list");
+    p.tile_list = list;
+  }
   if (ln) return dispatch_gemm_tc<256, true>(m, p, npass, out_f32 != nullptr, s);
   if (n_tile == 256) return dispatch_gemm_tc<256, false>(m, p, npass, out_f32 != nullptr, s);
   return dispatch_gemm_tc<128, false>(m, p, npass, out_f32 != nullptr, s);

@@ -394,10 +394,13 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
     m = batch * t
     lim, extra = row_limit if row_limit is not None else (None, 0)
     m = m * _limited_fraction(row_limit, t)  # rows really processed (for the flop / byte accounting below)
+    ws = None
+    if lim is not None:
+        ws = torch.empty(_lib.lib().lfs2_gemm_tc_limited_workspace_bytes(batch, t) // 4, device=dev, dtype=torch.int32)
     _launch("lfs2_gemm_tc_limited", _p(a.hi), _p(a.lo), batch, t, d, taps, _p(w.hi), _p(w.lo), n, _p(bias), int(relu),
             _p(residual.hi if residual is not None else None), _p(residual.lo if residual is not None else None),
             _p(ident), _p(gamma), _p(beta), float(eps), _p(of), _p(po.hi if po else None),
-            _p(po.lo if po else None), npass, _p(lim), int(extra), _s(), tag=tag or f"gemm_tc_n{n}_k{taps * d}",
+            _p(po.lo if po else None), npass, _p(lim), int(extra), _p(ws), _s(), tag=tag or f"gemm_tc_n{n}_k{taps * d}",
             flops=2.0 * m * n * taps * d,
             nbytes=4.0 * m * d + 4.0 * n * taps * d + 4.0 * m * n + (4.0 * m * n if residual is not None else 0.0))
     return of if out == "f32" else po
