@@ -453,111 +453,125 @@ def run_lfs2(args):
     else:
         frames_all, e2e_all, piped_all = frames, e2e_frames, piped_frames
 
+    # The sections below are SECONDARY numbers.  Each runs under try/except with local synchronisation only, and its
+    # cross-rank reduction happens afterwards through reduce_section() on every rank, so that a failure in one of them
+    # can neither take the headline line down nor leave another rank waiting in a collective.
+    def local_sync():
+        torch.cuda.synchronize()
+
+    def reduce_section(ok, times, counts):
+        """-> (every rank succeeded, max over ranks of the times, sum over ranks of the counts)"""
+        if world == 1:
+            return ok, times, counts
+        tmax = torch.tensor(list(times) or [0.0], device=dev, dtype=torch.float64)
+        tsum = torch.tensor([1.0 if ok else 0.0] + list(counts), device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        return bool(tsum[0] == world), [float(x) for x in tmax[:len(times)]], [int(x) for x in tsum[1:]]
+
+    def timed(fn, steps):
+        """K calls of fn between two events on the current stream -> (ms, last result)"""
+        local_sync()
+        e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_a.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e_b.record()
+        local_sync()
+        return e_a.elapsed_time(e_b), out
+
+    errors = {}
+
     # ---- bf16 mode (single-pass bf16 MMA operands, fp32 accumulate / residual / LayerNorm / softmax; tolerance
     #      1e-2 per BASELINE.json) on the same batch: secondary number, same timing protocol -------------------
-    model.set_compute_mode("bf16")
-    for _ in range(3):
+    ok_bf16, ms_bf16, frames_bf16, prof_bf16 = True, 0.0, 0, {}
+    try:
+        model.set_compute_mode("bf16")
+        for _ in range(3):
+            step_resident()
+        ms_bf16, rb = timed(step_resident, args.steps)
+        frames_bf16 = int((~rb["tgt_mask"]).sum())
+        ops.PROFILE = {}
         step_resident()
-    barrier()
-    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    h0.record()
-    for _ in range(args.steps):
-        rb = step_resident()
-    h1.record()
-    barrier()
-    ms_bf16 = h0.elapsed_time(h1)
-    frames_bf16 = int((~rb["tgt_mask"]).sum())
-    ops.PROFILE = {}
-    step_resident()
-    prof_bf16 = ops.collect_profile()
-    ops.PROFILE = None
-    model.set_compute_mode("fp32")
-    if world > 1:
-        t = torch.tensor([ms_bf16], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_bf16 = float(t[0])
-        c = torch.tensor([frames_bf16], device=dev, dtype=torch.int64)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-        frames_bf16 = int(c[0])
+        prof_bf16 = ops.collect_profile()
+    except Exception as exc:  # noqa: BLE001
+        ok_bf16, errors["bf16_mode"] = False, repr(exc)[:300]
+    finally:
+        ops.PROFILE = None
+        model.set_compute_mode("fp32")
+    ok_bf16, (ms_bf16,), (frames_bf16,) = reduce_section(ok_bf16, [ms_bf16], [frames_bf16])
 
     # ---- length-bucketed synthesis of the SAME batch (valid frames bit-identical, PAD frames zero) ----------
     bucketed = []
     for nb in args.buckets:
-        model.length_buckets = nb
-        for _ in range(3):
-            step_resident()
-        barrier()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        calls_b = _lib.CALLS
-        b0.record()
-        for _ in range(args.steps):
-            step_resident()
-        b1.record()
-        barrier()
-        ms_b = b0.elapsed_time(b1)
-        launches_b = _lib.CALLS - calls_b
-        step_e2e()
-        barrier()
-        b2, b3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b2.record()
-        fr_b = 0
-        for _ in range(args.steps):
-            fr_b += step_e2e()
-        b3.record()
-        barrier()
-        ms_be = b2.elapsed_time(b3)
-        if world > 1:
-            t = torch.tensor([ms_b, ms_be], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_b, ms_be = float(t[0]), float(t[1])
-            c = torch.tensor([fr_b], device=dev, dtype=torch.int64)
-            dist.all_reduce(c, op=dist.ReduceOp.SUM)
-            fr_b = int(c[0])
-        bucketed.append({"length_buckets": nb, "ms_per_step": ms_b / args.steps, "gpu_launches": launches_b,
-                         "frames_all_ranks_e2e": fr_b, "ms_per_step_e2e": ms_be / args.steps})
-    model.length_buckets = 1
+        ok_b, ms_b, ms_be, fr_b, launches_b = True, 0.0, 0.0, 0, 0
+        try:
+            model.length_buckets = nb
+            for _ in range(3):
+                step_resident()
+            calls_b = _lib.CALLS
+            ms_b, _ = timed(step_resident, args.steps)
+            launches_b = _lib.CALLS - calls_b
+            step_e2e()
+            local_sync()
+            e_a, e_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e_a.record()
+            for _ in range(args.steps):
+                fr_b += step_e2e()
+            e_b.record()
+            local_sync()
+            ms_be = e_a.elapsed_time(e_b)
+        except Exception as exc:  # noqa: BLE001
+            ok_b, errors[f"bucketed_{nb}"] = False, repr(exc)[:300]
+        finally:
+            model.length_buckets = 1
+        ok_b, (ms_b, ms_be), (fr_b,) = reduce_section(ok_b, [ms_b, ms_be], [fr_b])
+        if ok_b:
+            bucketed.append({"length_buckets": nb, "ms_per_step": ms_b / args.steps, "gpu_launches": launches_b,
+                             "frames_all_ranks_e2e": fr_b, "ms_per_step_e2e": ms_be / args.steps})
 
     # ---- BASELINE.json configs[2] ("C3"): 76 M-parameter model, bf16 synthesis, 32 utterances per GPU ----------
     c3 = None
     if args.c3_steps > 0:
-        del model
-        torch.cuda.empty_cache()
-        m3, _, _ = build_model(dev, preset="C3")
-        m3.set_compute_mode("bf16")
-        b3 = {k: v.to(dev) for k, v in synthetic.make_batch(32, MIN_LEN, MAX_LEN, seed=200 + rank).items()
-              if k in ("phones", "speaker")}
-        with torch.no_grad():
-            for _ in range(3):
-                r3 = m3(b3, inference=True)
-            barrier()
-            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            c0.record()
-            for _ in range(args.c3_steps):
-                r3 = m3(b3, inference=True)
-            c1.record()
-            barrier()
-        ms3 = c0.elapsed_time(c1) / args.c3_steps
-        fr3 = int((~r3["tgt_mask"]).sum())
-        if world > 1:
-            t = torch.tensor([ms3], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms3 = float(t[0])
-            c = torch.tensor([fr3], device=dev, dtype=torch.int64)
-            dist.all_reduce(c, op=dist.ReduceOp.SUM)
-            fr3 = int(c[0])
-        c3 = {"workload": "C3: 76M-parameter model (d=768, head_dim 384, 4 enc + 5 dec FFTBlocks, 3 variances), bf16 mode, "
-                          "32 utterances per GPU, phoneme len U[32,512] (BASELINE.json configs[2]: 256 utterances over 8 GPUs)",
-              "value": fr3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3, "valid_frames_per_step": fr3,
-              "mel_shape_rank0": list(r3["mel"].shape), "steps": args.c3_steps}
-        del m3, r3
-        torch.cuda.empty_cache()
         model = None
+        torch.cuda.empty_cache()
+        ok3, ms3, fr3, shape3 = True, 0.0, 0, []
+        try:
+            m3, _, _ = build_model(dev, preset="C3")
+            m3.set_compute_mode("bf16")
+            b3 = {k: v.to(dev) for k, v in synthetic.make_batch(32, MIN_LEN, MAX_LEN, seed=200 + rank).items()
+                  if k in ("phones", "speaker")}
+
+            def step3():
+                with torch.no_grad():
+                    return m3(b3, inference=True)
+
+            for _ in range(3):
+                step3()
+            ms3, r3 = timed(step3, args.c3_steps)
+            ms3 /= args.c3_steps
+            fr3 = int((~r3["tgt_mask"]).sum())
+            shape3 = list(r3["mel"].shape)
+            del m3, r3
+        except Exception as exc:  # noqa: BLE001
+            ok3, errors["c3_bf16"] = False, repr(exc)[:300]
+        torch.cuda.empty_cache()
+        ok3, (ms3,), (fr3,) = reduce_section(ok3, [ms3], [fr3])
+        if ok3:
+            c3 = {"workload": "C3: 76M-parameter model (d=768, head_dim 384, 4 enc + 5 dec FFTBlocks, 3 variances), bf16 mode, "
+                              "32 utterances per GPU, phoneme len U[32,512] (BASELINE.json configs[2]: 256 utterances over 8 GPUs)",
+                  "value": fr3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3, "valid_frames_per_step": fr3,
+                  "mel_shape_rank0": shape3, "steps": args.c3_steps}
 
     train = None
     if args.train_steps > 0:
         model = None
         torch.cuda.empty_cache()
-        train = measure_train(args, dev, rank, world, barrier)
+        try:
+            train = measure_train(args, dev, rank, world, barrier)
+        except Exception as exc:  # noqa: BLE001
+            errors["train"] = repr(exc)[:300]
 
     if rank == 0:
         pk = peaks()
@@ -628,16 +642,21 @@ def run_lfs2(args):
             "cpu_baseline": {"value": cpu_fps, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                              "sample": sample},
         }
+        if errors:
+            line["errors"] = errors
         tot_b = sum(v["ms"] for v in prof_bf16.values()) or 1.0
-        top_b = max(prof_bf16, key=lambda k: prof_bf16[k]["ms"])
-        tb = prof_bf16[top_b]
-        line["bf16_mode"] = {
-            "what": "same batch and API call with model.set_compute_mode('bf16'): single-pass bf16 MMA operands, fp32 "
-                    "accumulation / residual / LayerNorm / softmax (mel within 1e-2 of the fp32 reference)",
-            "value": frames_bf16 * args.steps / (ms_bf16 * 1e-3), "unit": UNIT, "ms_per_step": ms_bf16 / args.steps,
-            "dominant_kernel": top_b, "share_of_step": tb["ms"] / tot_b,
-            "achieved_tflops": tb["flops"] / (tb["ms"] * 1e-3) / 1e12, "achieved_gbs": tb["bytes"] / (tb["ms"] * 1e-3) / 1e9,
-            "kernel_shares": {k: round(v["ms"] / tot_b, 4) for k, v in sorted(prof_bf16.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
+        top_b = max(prof_bf16, key=lambda k: prof_bf16[k]["ms"]) if prof_bf16 else None
+        tb = prof_bf16[top_b] if top_b else None
+        if ok_bf16 and tb:
+            line["bf16_mode"] = {
+                "what": "same batch and API call with model.set_compute_mode('bf16'): single-pass bf16 MMA operands, fp32 "
+                        "accumulation / residual / LayerNorm / softmax (mel within 1e-2 of the fp32 reference)",
+                "value": frames_bf16 * args.steps / (ms_bf16 * 1e-3), "unit": UNIT, "ms_per_step": ms_bf16 / args.steps,
+                "dominant_kernel": top_b, "share_of_step": tb["ms"] / tot_b,
+                "achieved_tflops": tb["flops"] / (tb["ms"] * 1e-3) / 1e12,
+                "achieved_gbs": tb["bytes"] / (tb["ms"] * 1e-3) / 1e9,
+                "kernel_shares": {k: round(v["ms"] / tot_b, 4)
+                                  for k, v in sorted(prof_bf16.items(), key=lambda kv: -kv[1]["ms"])[:8]}}
         if bucketed:
             line["bucketed"] = {
                 "what": "same batch, same API call with model.length_buckets = n: length-sorted sub-batches padded to "
