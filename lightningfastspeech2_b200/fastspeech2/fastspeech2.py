@@ -14,7 +14,6 @@ import argparse
 import inspect
 import multiprocessing
 
-import numpy as np
 import torch
 from torch import nn
 

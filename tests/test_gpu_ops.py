@@ -1,6 +1,5 @@
 """GPU parity of every C-ABI entry point against the oracle / fp64 torch on the same
 seeded inputs.  Tolerances are stated per test; integer/byte work is bit-exact."""
-import os
 
 import numpy as np
 import pytest

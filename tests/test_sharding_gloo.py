@@ -5,7 +5,6 @@ per-rank losses) -- checked against the oracle's autograd gradients of each shar
 import os
 import socket
 
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
