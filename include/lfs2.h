@@ -177,7 +177,8 @@ LFS2_API int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch,
                                   const float* gamma, const float* beta, float eps, float* out_f32, void* out_hi,
                                   void* out_lo, int npass, const int* row_limit, int limit_extra,
                                   void* workspace, void* stream);
-/* workspace of lfs2_gemm_tc_limited when row_limit != NULL: the compact list of active row tiles */
+/* workspace of lfs2_gemm_tc_limited when row_limit != NULL: the compact list of active row tiles.  A later call with
+ * row_limit == NULL and the same workspace reuses that list (same batch, t and limit: the layers of one predictor). */
 LFS2_API long long lfs2_gemm_tc_limited_workspace_bytes(int batch, int t);
 LFS2_API int lfs2_dwconv1d_planes_limited(const float* x, const void* x_hi, const void* x_lo, const float* wt,
                                           const float* bias, float* out, void* out_hi, void* out_lo, int batch,

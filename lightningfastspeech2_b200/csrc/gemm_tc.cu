@@ -499,7 +499,9 @@ int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch, int t, i
   p.bias = bias; p.relu = relu; p.gamma = gamma; p.beta = beta; p.eps = eps;
   cudaStream_t s = (cudaStream_t)stream;
   p.tile_list = nullptr;
-  if (row_limit) {  // compact list of the row tiles that are needed, built on the device (no host read-back)
+  if (!row_limit && workspace) {
+    p.tile_list = reinterpret_cast<const int*>(workspace);  // a list built earlier for the same (batch, t, limit): reuse
+  } else if (row_limit) {  // compact list of the row tiles that are needed, built on the device (no host read-back)
     LFS2_REQUIRE(workspace, LFS2_ERR_INVALID_ARG, "gemm_tc: a row limit needs the tile-list workspace");
     int* list = reinterpret_cast<int*>(workspace);
     if (cudaMemsetAsync(list, 0, sizeof(int), s) != cudaSuccess) {

@@ -420,7 +420,7 @@ class VariancePredictor(nn.Module):
         lim = None
         if (self.skip_pad_tiles and mask is not None and not return_conv and not isinstance(x, ops.Planes)
                 and x.dim() == 3 and all(l.depthwise and l.compute_mode != "simt" for l in self.layers)):
-            lim = (ops.mask_lengths(mask), self.halo())
+            lim = (ops.mask_lengths(mask), self.halo(), {})  # {} = tile list shared by the layers of this call
         for i, layer in enumerate(self.layers):
             z = layer(z, out="planes" if i + 1 < nl else "f32", row_limit=lim)
         if isinstance(z, ops.Planes):

@@ -300,7 +300,7 @@ def _limited_fraction(row_limit, t):
     """fraction of the (B, t) rows a row-limited launch really processes (profiling only: reads the lengths back)"""
     if row_limit is None or PROFILE is None:
         return 1.0
-    lim, extra = row_limit
+    lim, extra = row_limit[0], row_limit[1]
     rows = torch.clamp((lim.long() + extra + 127) // 128 * 128, max=t).clamp(min=0).sum().item()
     return rows / float(lim.numel() * t)
 
@@ -326,7 +326,7 @@ def dwconv1d_planes(x, wt, bias, out="planes", row_limit=None):
     b, t, d = shape
     of = torch.empty(shape, device=dev, dtype=torch.float32) if out == "f32" else None
     po = _empty_planes(shape, dev) if out == "planes" else None
-    lim, extra = row_limit if row_limit is not None else (None, 0)
+    lim, extra = (row_limit[0], row_limit[1]) if row_limit is not None else (None, 0)
     frac = _limited_fraction(row_limit, t)
     _launch("lfs2_dwconv1d_planes_limited", _p(xf), _p(xh), _p(xl), _p(wt), _p(bias), _p(of), _p(po.hi if po else None),
             _p(po.lo if po else None), b, t, d, wt.shape[0], _p(lim), int(extra), _s(), tag="lfs2_dwconv1d",
@@ -392,11 +392,19 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
         _chk(residual.hi, torch.bfloat16, "gemm_tc residual"); _chk(residual.lo, torch.bfloat16, "gemm_tc residual")
         ident = _identity_planes(n, dev)
     m = batch * t
-    lim, extra = row_limit if row_limit is not None else (None, 0)
+    lim, extra = (row_limit[0], row_limit[1]) if row_limit is not None else (None, 0)
     m = m * _limited_fraction(row_limit, t)  # rows really processed (for the flop / byte accounting below)
     ws = None
     if lim is not None:
-        ws = torch.empty(_lib.lib().lfs2_gemm_tc_limited_workspace_bytes(batch, t) // 4, device=dev, dtype=torch.int32)
+        # row_limit may carry a dict as third element: the tile list built by the first launch is reused by the next
+        cache = row_limit[2] if len(row_limit) > 2 else None
+        key = (batch, t)
+        if cache is not None and key in cache:
+            ws, lim = cache[key], None
+        else:
+            ws = torch.empty(_lib.lib().lfs2_gemm_tc_limited_workspace_bytes(batch, t) // 4, device=dev, dtype=torch.int32)
+            if cache is not None:
+                cache[key] = ws
     _launch("lfs2_gemm_tc_limited", _p(a.hi), _p(a.lo), batch, t, d, taps, _p(w.hi), _p(w.lo), n, _p(bias), int(relu),
             _p(residual.hi if residual is not None else None), _p(residual.lo if residual is not None else None),
             _p(ident), _p(gamma), _p(beta), float(eps), _p(of), _p(po.hi if po else None),
