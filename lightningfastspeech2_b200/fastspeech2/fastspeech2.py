@@ -369,6 +369,7 @@ class FastSpeech2(_Base):
         """LengthRegulator, variance encoders, decoder, mel Linear, result dict (reference model.py:311-341, :703-784)"""
         dev, hp = self.device, self.hparams
         pe, spk, src_mask = self.positional_encoding.pe, st["spk"], st["src_mask"]
+        self.variance_adaptor.need_out_val = hasattr(self, "fastdiff_linear")
         variance_output = self.variance_adaptor.expand(st["enc"], st, targets, inference=inference, force=force,
                                                        control=control, scan=scan, frames=frames)
         output = ops.add_pe_spk_(variance_output["x"], pe, spk)

@@ -518,6 +518,10 @@ class VarianceAdaptor(nn.Module):
         ext = torch.full((idx.shape[0], width - idx.shape[1]), pad, device=idx.device, dtype=idx.dtype)
         return torch.cat([idx, ext], 1).contiguous()
 
+    # result["out"] (sum of the variance embeddings) only feeds the optional fastdiff head (fastspeech2.py:733-736);
+    # FastSpeech2 clears this when the head does not exist
+    need_out_val = True
+
     def freeze(self, component):
         mod = self.duration_predictor if component == "duration" else self.encoders[component]
         for param in mod.parameters():
@@ -576,7 +580,9 @@ class VarianceAdaptor(nn.Module):
         x_in = x
         x, tgt_mask = self.length_regulator(x_in, duration_rounded, self.max_length, scan=scan, frames=frames)
         have_acc = st.get("out_phone") is not None
-        if have_acc:  # the summed phone-level embeddings are length-regulated too (model.py:312-313)
+        if not self.need_out_val:
+            have_acc, out_val = False, None  # nobody reads result["out"] (no fastdiff head): skip its HBM traffic
+        elif have_acc:  # the summed phone-level embeddings are length-regulated too (model.py:312-313)
             out_val, _ = self.length_regulator(st["out_phone"], duration_rounded, self.max_length, scan=scan, frames=frames)
         else:
             out_val = torch.empty_like(x) if len(self.variances) else None
