@@ -278,6 +278,9 @@ LFS2_API int lfs2_gemm_tn(const float* a, const float* b, float* c, int m, int n
 LFS2_API int lfs2_colsum(const float* a, float* out, int m, int n, void* stream);
 /* dx = y > 0 ? dy : 0 (y = the ReLU output; dx may alias dy) */
 LFS2_API int lfs2_relu_bwd(const float* dy, const float* y, float* dx, long long n, void* stream);
+/* dx = y > 0 ? dy * scale : 0: ReLU followed by dropout (model.py:120) in one pass -- y is the saved DROPPED
+ * activation, so y > 0 is relu-mask and keep-mask at once and scale = 1/(1-p) */
+LFS2_API int lfs2_relu_bwd_scaled(const float* dy, const float* y, float* dx, long long n, float scale, void* stream);
 /* dst += src */
 LFS2_API int lfs2_add_inplace(float* dst, const float* src, long long n, void* stream);
 /* out (cols, rows) = in (rows, cols)^T -- transposed weight copies for the input-gradient GEMMs */

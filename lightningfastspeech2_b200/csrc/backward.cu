@@ -138,15 +138,17 @@ __global__ void colsum_kernel(const float4* __restrict__ a, float* __restrict__ 
   }
 }
 
+// dx = y > 0 ? dy * scale : 0.  scale != 1 folds the backward of a dropout that followed the ReLU: the saved y is the
+// dropped activation (0 where dropped), so "y > 0" already is relu-mask AND keep-mask; only 1/(1-p) remains
 __global__ void relu_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ y, float4* __restrict__ dx,
-                                size_t n4) {
+                                size_t n4, float scale) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 g = dy[i], v = y[i];
-  g.x = v.x > 0.f ? g.x : 0.f;
-  g.y = v.y > 0.f ? g.y : 0.f;
-  g.z = v.z > 0.f ? g.z : 0.f;
-  g.w = v.w > 0.f ? g.w : 0.f;
+  g.x = v.x > 0.f ? g.x * scale : 0.f;
+  g.y = v.y > 0.f ? g.y * scale : 0.f;
+  g.z = v.z > 0.f ? g.z * scale : 0.f;
+  g.w = v.w > 0.f ? g.w * scale : 0.f;
   dx[i] = g;
 }
 
@@ -523,12 +525,17 @@ int lfs2_colsum(const float* a, float* out, int m, int n, void* stream) {
 }
 
 int lfs2_relu_bwd(const float* dy, const float* y, float* dx, long long n, void* stream) {
+  return lfs2_relu_bwd_scaled(dy, y, dx, n, 1.f, stream);
+}
+
+int lfs2_relu_bwd_scaled(const float* dy, const float* y, float* dx, long long n, float scale, void* stream) {
   LFS2_REQUIRE(dy && y && dx, LFS2_ERR_INVALID_ARG, "relu_bwd: null pointer");
   if (n == 0) return LFS2_OK;
   LFS2_REQUIRE(n > 0 && n % 4 == 0, LFS2_ERR_UNSUPPORTED, "relu_bwd: n must be a positive multiple of 4");
   LFS2_REQUIRE(aligned16(dy) && aligned16(y) && aligned16(dx), LFS2_ERR_INVALID_ARG, "relu_bwd: pointers must be 16-byte aligned");
   size_t n4 = (size_t)n / 4;
-  relu_bwd_kernel<<<ceil_div(n4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)dy, (const float4*)y, (float4*)dx, n4);
+  relu_bwd_kernel<<<ceil_div(n4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)dy, (const float4*)y, (float4*)dx, n4,
+                                                                       scale);
   LFS2_CHECK_LAUNCH("relu_bwd");
   return LFS2_OK;
 }

@@ -205,8 +205,7 @@ def fft_bwd(L, E, s, dx2):
     else:
         dv = E.conv_dgrad(dy, L.conv2.weight, tag="ffn2_dgrad")
         E.conv_wgrad_(grad_of(L.conv2.weight), grad_of(L.conv2.bias), dy, s["v"], tag="ffn2_wgrad")
-        E.dropout_bwd(dv, s["dropv"])
-        ops.relu_bwd_(dv, s["v"])
+        ops.relu_bwd_(dv, s["v"], scale=1.0 / (1.0 - s["dropv"][0]) if s["dropv"] else 1.0)
         dx1 = E.conv_dgrad(dv, L.conv1.weight, tag="ffn1_dgrad")
         E.conv_wgrad_(grad_of(L.conv1.weight), grad_of(L.conv1.bias), dv, s["x1"], tag="ffn1_wgrad")
     ops.add_(dx1, dz2)                                                   # residual around the FFN
@@ -220,10 +219,10 @@ def _ffn_bwd_depthwise(L, E, s, dy, dev):
     dw_eff = torch.zeros_like(s["w_eff"])
     db_eff = torch.zeros(s["w_eff"].shape[0], device=dev, dtype=torch.float32)
     E.wgrad_(dw_eff, db_eff, dy, s["v"], tag="ffn2_wgrad")
-    E.dropout_bwd(dv, s["dropv"])
     ops.fold_pw_bwd_(dw_eff, db_eff, _mat(pw2.weight), _mat(gc.weight), gc.bias, _mat(grad_of(pw2.weight)),
                      _mat(grad_of(gc.weight)), grad_of(gc.bias), grad_of(pw2.bias))
-    ops.relu_bwd_(dv, s["v"])
+    # ReLU + the dropout behind it in one pass: s["v"] is the dropped activation, so v > 0 is both masks
+    ops.relu_bwd_(dv, s["v"], scale=1.0 / (1.0 - s["dropv"][0]) if s["dropv"] else 1.0)
     du = E.dgrad(dv, _mat(pw.weight), tag="ffn1_dgrad")
     E.wgrad_(_mat(grad_of(pw.weight)), grad_of(pw.bias), dv, s["u"], tag="ffn1_wgrad")
     return _dwconv_bwd(dwc, s["dw_wt"], du, s["x1"])

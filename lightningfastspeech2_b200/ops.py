@@ -494,8 +494,10 @@ def colsum_(out, a):
     _launch("lfs2_colsum", _p(a), _p(out), a.numel() // n, n, _s(), nbytes=4.0 * a.numel())
 
 
-def relu_bwd_(dy, y):
-    _launch("lfs2_relu_bwd", _p(dy), _p(y), _p(dy), dy.numel(), _s(), nbytes=12.0 * dy.numel())
+def relu_bwd_(dy, y, scale=1.0):
+    """dy <- (y > 0 ? dy * scale : 0); scale = 1/(1-p) folds the backward of a dropout applied right after the ReLU"""
+    _launch("lfs2_relu_bwd_scaled", _p(dy), _p(y), _p(dy), dy.numel(), float(scale), _s(), tag="lfs2_relu_bwd",
+            nbytes=12.0 * dy.numel())
     drop_planes(dy)
     return dy
 
