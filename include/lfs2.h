@@ -243,6 +243,13 @@ LFS2_API int lfs2_gemm_tc2(const void* a_hi, const void* a_lo, const lfs2_operan
  *          (Z,t,tp) (p_lo may be NULL), lse (Z,t) of the scaled logits; pad columns / PAD keys get 0. */
 LFS2_API int lfs2_attn_softmax_planes(const float* s, const uint8_t* key_padding_mask, void* p_hi, void* p_lo,
                                       float* lse, int batch, int nhead, int t, int tp, float scale, void* stream);
+/* the same with attention-probability dropout (torch MHA dropout, model.py:111) fused: additionally writes
+ * PM = P o mask / (1 - p) (pm_hi / pm_lo, mask as lfs2_dropout_planes over the (Z,t,tp) index space): PM feeds P.V and
+ * P^T.dO, P stays for the softmax backward */
+LFS2_API int lfs2_attn_softmax_planes_drop(const float* s, const uint8_t* key_padding_mask, void* p_hi, void* p_lo,
+                                           void* pm_hi, void* pm_lo, float* lse, int batch, int nhead, int t, int tp,
+                                           float scale, float drop_p, unsigned long long drop_seed,
+                                           unsigned int drop_site, void* stream);
 /* delta (Z,t) = rowsum(dctx o ctx) per head */
 LFS2_API int lfs2_attn_delta(const float* dctx, const float* ctx, float* delta, int batch, int t, int d, int nhead,
                              void* stream);
@@ -250,6 +257,12 @@ LFS2_API int lfs2_attn_delta(const float* dctx, const float* ctx, float* delta, 
 LFS2_API int lfs2_attn_ds_planes(const void* p_hi, const void* p_lo, const float* dp, const float* delta,
                                  void* ds_hi, void* ds_lo, int batch, int nhead, int t, int tp, float scale,
                                  void* stream);
+
+/* the same with the dropout mask of the forward applied to dP first (dP_eff = mask/(1-p) o dP) */
+LFS2_API int lfs2_attn_ds_planes_drop(const void* p_hi, const void* p_lo, const float* dp, const float* delta,
+                                      void* ds_hi, void* ds_lo, int batch, int nhead, int t, int tp, float scale,
+                                      float drop_p, unsigned long long drop_seed, unsigned int drop_site,
+                                      void* stream);
 
 /* ================= train-step config: backward kernels, loss, optimizer ===================
  * The reference obtains all of these from torch.autograd / torch.optim; the citations name the
@@ -260,13 +273,22 @@ LFS2_API int lfs2_attn_ds_planes(const void* p_hi, const void* p_lo, const float
  * (mean, rstd) pairs stats (m,2) needed by lfs2_layernorm_bwd; z_out / stats may be NULL. */
 LFS2_API int lfs2_add_layernorm_train(const float* x, const float* y, const float* gamma, const float* beta,
                                       float* out, float* z_out, float* stats, int m, int d, float eps,
+                                      float drop_p, unsigned long long drop_seed, unsigned int drop_site,
                                       void* stream);
+/* (drop_p > 0 fuses dropout1 / dropout2 of the FFTBlock, model.py:114-115: z = x + dropout(y), mask as lfs2_dropout) */
 /* backward of out = LayerNorm(z; gamma, beta) (model.py:114-115, 538, 556):
  *   dz = rstd * (dy*gamma - mean(dy*gamma) - xhat * mean(dy*gamma*xhat)) (+ add if non-NULL)
  *   dgamma += sum_m dy * xhat ; dbeta += sum_m dy */
 LFS2_API int lfs2_layernorm_bwd(const float* dy, const float* z, const float* stats, const float* gamma,
                                 const float* add, float* dz, float* dgamma, float* dbeta, int m, int d,
                                 void* stream);
+
+/* same, plus dz_drop = dropout(dz) with the mask of (drop_p, drop_seed, drop_site): the gradient entering the branch
+ * whose output was dropped in the forward pass (dz itself continues along the residual) */
+LFS2_API int lfs2_layernorm_bwd_drop(const float* dy, const float* z, const float* stats, const float* gamma,
+                                     const float* add, float* dz, float* dz_drop, float* dgamma, float* dbeta,
+                                     int m, int d, float drop_p, unsigned long long drop_seed,
+                                     unsigned int drop_site, void* stream);
 
 /* weight gradient of Linear / pointwise Conv1d / one tap of a dense Conv1d:
  *   c[n,k] += sum_r a[r, n] * b[r + shift, k]      (r over m rows; a is dY, b is the layer input)

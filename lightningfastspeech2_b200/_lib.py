@@ -45,11 +45,17 @@ SIGNATURES = {
     "lfs2_split_bf16": [_vp, _vp, _vp, ctypes.c_longlong, _vp],
     "lfs2_gemm_tc2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
     "lfs2_attn_softmax_planes": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
+    "lfs2_attn_softmax_planes_drop": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, ctypes.c_ulonglong,
+                                      ctypes.c_uint, _vp],
+    "lfs2_attn_ds_planes_drop": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, ctypes.c_ulonglong, ctypes.c_uint,
+                                 _vp],
     "lfs2_attn_delta": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "lfs2_attn_ds_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     # train-step config
-    "lfs2_add_layernorm_train": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
+    "lfs2_add_layernorm_train": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, ctypes.c_ulonglong, ctypes.c_uint, _vp],
     "lfs2_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
+    "lfs2_layernorm_bwd_drop": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, ctypes.c_ulonglong, ctypes.c_uint,
+                                _vp],
     "lfs2_gemm_tn": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "lfs2_colsum": [_vp, _vp, _i, _i, _vp],
     "lfs2_relu_bwd": [_vp, _vp, _vp, _ll, _vp],

@@ -33,8 +33,9 @@ __device__ __forceinline__ float2 merge2(uint32_t hi, uint32_t lo) {
 // one warp per (z, query) row.  s: (Z, T, Tp) raw logits; kpm: (B, T) 1 = PAD key
 __global__ void __launch_bounds__(256)
 attn_softmax_planes_kernel(const float* __restrict__ s, const uint8_t* __restrict__ kpm, uint32_t* __restrict__ p_hi,
-                           uint32_t* __restrict__ p_lo, float* __restrict__ lse, long long rows, int t, int tp,
-                           int nhead, float scale) {
+                           uint32_t* __restrict__ p_lo, uint32_t* __restrict__ pm_hi, uint32_t* __restrict__ pm_lo,
+                           float* __restrict__ lse, long long rows, int t, int tp, int nhead, float scale,
+                           DropSite drop) {
   const long long row = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -63,6 +64,9 @@ attn_softmax_planes_kernel(const float* __restrict__ s, const uint8_t* __restric
   if (lane == 0) lse[row] = mx + logf(sum);
   uint2* ph = reinterpret_cast<uint2*>(p_hi + row * (tp / 2));
   uint2* pl = p_lo ? reinterpret_cast<uint2*>(p_lo + row * (tp / 2)) : nullptr;
+  // attention-probability dropout fused: P (kept for the backward) and P o mask / (1-p) (the operand of P.V)
+  uint2* mh = pm_hi ? reinterpret_cast<uint2*>(pm_hi + row * (tp / 2)) : nullptr;
+  uint2* ml = pm_lo ? reinterpret_cast<uint2*>(pm_lo + row * (tp / 2)) : nullptr;
   for (int c = lane * 4; c < tp; c += 128) {
     float pv[4] = {0.f, 0.f, 0.f, 0.f};
     if (c < t) {
@@ -77,6 +81,13 @@ attn_softmax_planes_kernel(const float* __restrict__ s, const uint8_t* __restric
     split2(pv[2], pv[3], h.y, l.y);
     ph[c / 4] = h;
     if (pl) pl[c / 4] = l;
+    if (mh) {
+      const float4 k = dropout_scale4((size_t)row * (tp / 4) + c / 4, drop.threshold, drop.inv_keep, drop.key, drop.site);
+      split2(pv[0] * k.x, pv[1] * k.y, h.x, l.x);
+      split2(pv[2] * k.z, pv[3] * k.w, h.y, l.y);
+      mh[c / 4] = h;
+      if (ml) ml[c / 4] = l;
+    }
   }
 }
 
@@ -101,14 +112,18 @@ __global__ void attn_delta_mat_kernel(const float4* __restrict__ dctx, const flo
 __global__ void __launch_bounds__(256)
 attn_ds_planes_kernel(const uint2* __restrict__ p_hi, const uint2* __restrict__ p_lo, const float4* __restrict__ dp,
                       const float* __restrict__ delta, uint2* __restrict__ ds_hi, uint2* __restrict__ ds_lo,
-                      long long rows, int tp4, float scale) {
+                      long long rows, int tp4, float scale, DropSite drop) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * tp4) return;
   const long long row = i / tp4;
   const uint2 h = p_hi[i];
   const uint2 l = p_lo ? p_lo[i] : make_uint2(0u, 0u);
   const float2 p01 = merge2(h.x, l.x), p23 = merge2(h.y, l.y);
-  const float4 g = dp[i];
+  float4 g = dp[i];
+  if (drop.threshold) {  // O = (P o M).V  =>  dP_eff = M o (dO.V^T): the forward's mask, regenerated
+    const float4 k = dropout_scale4((size_t)i, drop.threshold, drop.inv_keep, drop.key, drop.site);
+    g.x *= k.x; g.y *= k.y; g.z *= k.z; g.w *= k.w;
+  }
   const float dl = delta[row];
   // P = 0 on PAD keys / pad columns, where dP may hold anything finite
   const float d0 = p01.x != 0.f ? scale * p01.x * (g.x - dl) : 0.f;
@@ -130,6 +145,16 @@ extern "C" {
 
 int lfs2_attn_softmax_planes(const float* s, const uint8_t* key_padding_mask, void* p_hi, void* p_lo, float* lse,
                              int batch, int nhead, int t, int tp, float scale, void* stream) {
+  return lfs2_attn_softmax_planes_drop(s, key_padding_mask, p_hi, p_lo, nullptr, nullptr, lse, batch, nhead, t, tp, scale,
+                                       0.f, 0ull, 0u, stream);
+}
+
+int lfs2_attn_softmax_planes_drop(const float* s, const uint8_t* key_padding_mask, void* p_hi, void* p_lo, void* pm_hi,
+                                  void* pm_lo, float* lse, int batch, int nhead, int t, int tp, float scale,
+                                  float drop_p, unsigned long long drop_seed, unsigned int drop_site, void* stream) {
+  LFS2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, LFS2_ERR_INVALID_ARG, "attn_softmax_planes: dropout p must be in [0, 1)");
+  LFS2_REQUIRE((!pm_hi || aligned16(pm_hi)) && (!pm_lo || aligned16(pm_lo)), LFS2_ERR_INVALID_ARG,
+               "attn_softmax_planes: pointers must be 16-byte aligned");
   LFS2_REQUIRE(s && p_hi && lse, LFS2_ERR_INVALID_ARG, "attn_softmax_planes: null pointer");
   if (batch == 0 || t == 0) return LFS2_OK;
   LFS2_REQUIRE(batch > 0 && nhead > 0 && t > 0 && tp >= t && tp % 8 == 0, LFS2_ERR_INVALID_ARG,
@@ -138,7 +163,8 @@ int lfs2_attn_softmax_planes(const float* s, const uint8_t* key_padding_mask, vo
                "attn_softmax_planes: pointers must be 16-byte aligned");
   const long long rows = (long long)batch * nhead * t;
   attn_softmax_planes_kernel<<<ceil_div(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
-      s, key_padding_mask, (uint32_t*)p_hi, (uint32_t*)p_lo, lse, rows, t, tp, nhead, scale);
+      s, key_padding_mask, (uint32_t*)p_hi, (uint32_t*)p_lo, (uint32_t*)pm_hi, (uint32_t*)pm_lo, lse, rows, t, tp, nhead,
+      scale, make_drop_site(pm_hi ? drop_p : 0.f, drop_seed, drop_site));
   LFS2_CHECK_LAUNCH("attn_softmax_planes");
   return LFS2_OK;
 }
@@ -157,6 +183,13 @@ int lfs2_attn_delta(const float* dctx, const float* ctx, float* delta, int batch
 
 int lfs2_attn_ds_planes(const void* p_hi, const void* p_lo, const float* dp, const float* delta, void* ds_hi,
                         void* ds_lo, int batch, int nhead, int t, int tp, float scale, void* stream) {
+  return lfs2_attn_ds_planes_drop(p_hi, p_lo, dp, delta, ds_hi, ds_lo, batch, nhead, t, tp, scale, 0.f, 0ull, 0u, stream);
+}
+
+int lfs2_attn_ds_planes_drop(const void* p_hi, const void* p_lo, const float* dp, const float* delta, void* ds_hi,
+                             void* ds_lo, int batch, int nhead, int t, int tp, float scale, float drop_p,
+                             unsigned long long drop_seed, unsigned int drop_site, void* stream) {
+  LFS2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, LFS2_ERR_INVALID_ARG, "attn_ds_planes: dropout p must be in [0, 1)");
   LFS2_REQUIRE(p_hi && dp && delta && ds_hi, LFS2_ERR_INVALID_ARG, "attn_ds_planes: null pointer");
   if (batch == 0 || t == 0) return LFS2_OK;
   LFS2_REQUIRE(batch > 0 && nhead > 0 && t > 0 && tp >= t && tp % 8 == 0, LFS2_ERR_INVALID_ARG, "attn_ds_planes: bad shape");
@@ -167,7 +200,7 @@ int lfs2_attn_ds_planes(const void* p_hi, const void* p_lo, const float* dp, con
   const long long n = rows * (tp / 4);
   attn_ds_planes_kernel<<<ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(
       (const uint2*)p_hi, (const uint2*)p_lo, (const float4*)dp, delta, (uint2*)ds_hi, (uint2*)ds_lo, rows, tp / 4,
-      scale);
+      scale, make_drop_site(drop_p, drop_seed, drop_site));
   LFS2_CHECK_LAUNCH("attn_ds_planes");
   return LFS2_OK;
 }

@@ -181,7 +181,8 @@ template <int NV>  // float4 column groups per lane: d <= 128 * NV
 __global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ z, const float2* __restrict__ stats,
                      const float4* __restrict__ gamma, const float4* __restrict__ add, float4* __restrict__ dz,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int m, int d4) {
+                     float4* __restrict__ dz_drop, float* __restrict__ dgamma, float* __restrict__ dbeta, int m, int d4,
+                     DropSite drop) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -225,6 +226,10 @@ layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ z
         o.y = rstd * (g[i].y - c1 - xh[i].y * c2);
         o.z = rstd * (g[i].z - c1 - xh[i].z * c2);
         o.w = rstd * (g[i].w - c1 - xh[i].w * c2);
+        if (dz_drop) {  // gradient of the dropped branch: z = x + drop(y)  =>  dy = drop(dz) with the forward's mask
+          const float4 k = dropout_scale4((size_t)row * d4 + c, drop.threshold, drop.inv_keep, drop.key, drop.site);
+          dz_drop[(size_t)row * d4 + c] = make_float4(o.x * k.x, o.y * k.y, o.z * k.z, o.w * k.w);
+        }
         if (add) {
           const float4 e = add[(size_t)row * d4 + c];
           o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w;
@@ -564,7 +569,16 @@ int lfs2_transpose(const float* in, float* out, int rows, int cols, void* stream
 
 int lfs2_layernorm_bwd(const float* dy, const float* z, const float* stats, const float* gamma, const float* add,
                        float* dz, float* dgamma, float* dbeta, int m, int d, void* stream) {
+  return lfs2_layernorm_bwd_drop(dy, z, stats, gamma, add, dz, nullptr, dgamma, dbeta, m, d, 0.f, 0ull, 0u, stream);
+}
+
+int lfs2_layernorm_bwd_drop(const float* dy, const float* z, const float* stats, const float* gamma, const float* add,
+                            float* dz, float* dz_drop, float* dgamma, float* dbeta, int m, int d, float drop_p,
+                            unsigned long long drop_seed, unsigned int drop_site, void* stream) {
   LFS2_REQUIRE(dy && z && stats && gamma && dz && dgamma && dbeta, LFS2_ERR_INVALID_ARG, "layernorm_bwd: null pointer");
+  LFS2_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (!dz_drop || aligned16(dz_drop)), LFS2_ERR_INVALID_ARG,
+               "layernorm_bwd: bad dropout arguments");
+  const DropSite drop = make_drop_site(drop_p, drop_seed, drop_site);
   if (m == 0) return LFS2_OK;
   LFS2_REQUIRE(d > 0 && d % 4 == 0 && d <= 128 * kLnbMaxVec, LFS2_ERR_UNSUPPORTED,
                "layernorm_bwd: d=%d must be a multiple of 4 and <= %d", d, 128 * kLnbMaxVec);
@@ -578,7 +592,7 @@ int lfs2_layernorm_bwd(const float* dy, const float* z, const float* stats, cons
 #define LFS2_LNB(NV)                                                                                            \
   layernorm_bwd_kernel<NV><<<blocks, 256, 0, (cudaStream_t)stream>>>(                                           \
       (const float4*)dy, (const float4*)z, (const float2*)stats, (const float4*)gamma, (const float4*)add,      \
-      (float4*)dz, dgamma, dbeta, m, d / 4)
+      (float4*)dz, (float4*)dz_drop, dgamma, dbeta, m, d / 4, drop)
   if (nv <= 1) LFS2_LNB(1);
   else if (nv <= 2) LFS2_LNB(2);
   else if (nv <= 4) LFS2_LNB(4);

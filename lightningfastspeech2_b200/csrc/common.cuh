@@ -61,4 +61,42 @@ __device__ __forceinline__ void st_stream16(void* p, const int4& v) {
                : "memory");
 }
 
+// ---- counter-based dropout masks (dropout.cu and the kernels that fuse a dropout site) ----
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+
+// keep-scale factors of elements 4i .. 4i+3
+__device__ __forceinline__ float4 dropout_scale4(size_t i, uint32_t threshold, float inv_keep, uint2 key, uint32_t site) {
+  const uint4 r = philox4x32_10(make_uint4((uint32_t)i, (uint32_t)(i >> 32), site, 0u), key);
+  return make_float4(r.x >= threshold ? inv_keep : 0.f, r.y >= threshold ? inv_keep : 0.f,
+                     r.z >= threshold ? inv_keep : 0.f, r.w >= threshold ? inv_keep : 0.f);
+}
+
+// (p, seed, site) of one dropout site as kernel arguments; threshold == 0 and inv_keep == 1 mean "no dropout"
+struct DropSite {
+  uint32_t threshold;
+  float inv_keep;
+  uint2 key;
+  uint32_t site;
+};
+static inline DropSite make_drop_site(float p, unsigned long long seed, unsigned int site) {
+  DropSite d;
+  double t = (double)p * 4294967296.0;
+  d.threshold = p <= 0.f ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+  d.inv_keep = p <= 0.f ? 1.f : 1.f / (1.f - p);
+  d.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  d.site = site;
+  return d;
+}
+
 }  // namespace lfs2

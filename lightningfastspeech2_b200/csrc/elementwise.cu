@@ -90,7 +90,7 @@ constexpr int kLnMaxVec = 8;  // float4 per lane -> d <= 1024
 __global__ void add_layernorm_kernel(const float4* __restrict__ x, const float4* __restrict__ y,
                                      const float4* __restrict__ gamma, const float4* __restrict__ beta,
                                      float4* __restrict__ out, float4* __restrict__ z_out,
-                                     float2* __restrict__ stats, int m, int d4, float eps) {
+                                     float2* __restrict__ stats, int m, int d4, float eps, DropSite drop) {
   int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (row >= m) return;
@@ -105,6 +105,10 @@ __global__ void add_layernorm_kernel(const float4* __restrict__ x, const float4*
       float4 a = xr[c];
       if (yr) {
         float4 b = yr[c];
+        if (drop.threshold) {  // fused dropout of the branch (dropout1 / dropout2, model.py:114-115): z = x + drop(y)
+          const float4 k = dropout_scale4((size_t)row * d4 + c, drop.threshold, drop.inv_keep, drop.key, drop.site);
+          b.x *= k.x; b.y *= k.y; b.z *= k.z; b.w *= k.w;
+        }
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
       }
       v[i] = a;
@@ -549,11 +553,13 @@ int lfs2_add_pe_spk(float* x, const float* pe, const float* spk, int batch, int 
 
 int lfs2_add_layernorm(const float* x, const float* y, const float* gamma, const float* beta, float* out, int m,
                        int d, float eps, void* stream) {
-  return lfs2_add_layernorm_train(x, y, gamma, beta, out, nullptr, nullptr, m, d, eps, stream);
+  return lfs2_add_layernorm_train(x, y, gamma, beta, out, nullptr, nullptr, m, d, eps, 0.f, 0ull, 0u, stream);
 }
 
 int lfs2_add_layernorm_train(const float* x, const float* y, const float* gamma, const float* beta, float* out,
-                             float* z_out, float* stats, int m, int d, float eps, void* stream) {
+                             float* z_out, float* stats, int m, int d, float eps, float drop_p,
+                             unsigned long long drop_seed, unsigned int drop_site, void* stream) {
+  LFS2_REQUIRE(drop_p >= 0.f && drop_p < 1.f, LFS2_ERR_INVALID_ARG, "add_layernorm: dropout p must be in [0, 1)");
   LFS2_REQUIRE(x && gamma && beta && out, LFS2_ERR_INVALID_ARG, "add_layernorm: null pointer");
   LFS2_REQUIRE((!z_out || aligned16(z_out)) && (reinterpret_cast<uintptr_t>(stats) & 7u) == 0, LFS2_ERR_INVALID_ARG,
                "add_layernorm: z_out / stats misaligned");
@@ -565,7 +571,7 @@ int lfs2_add_layernorm_train(const float* x, const float* y, const float* gamma,
   int threads = 256;
   add_layernorm_kernel<<<ceil_div((long long)m * 32, threads), threads, 0, (cudaStream_t)stream>>>(
       (const float4*)x, (const float4*)y, (const float4*)gamma, (const float4*)beta, (float4*)out, (float4*)z_out,
-      (float2*)stats, m, d / 4, eps);
+      (float2*)stats, m, d / 4, eps, make_drop_site(y ? drop_p : 0.f, drop_seed, drop_site));
   LFS2_CHECK_LAUNCH("add_layernorm");
   return LFS2_OK;
 }

@@ -41,6 +41,13 @@ class Engine:
         self.seed = int(torch.randint(0, 2 ** 62, (1,)).item())
         self.site = 0
 
+    def site_token(self, p):
+        """replay token of a dropout site that a kernel applies itself (fused), None if p == 0"""
+        if p <= 0:
+            return None
+        self.site += 1
+        return (p, self.seed, self.site)
+
     def dropout_(self, x, p):
         """in-place dropout; returns the replay token for the backward pass (None if p == 0)"""
         if p <= 0:
@@ -177,8 +184,8 @@ def fft_fwd(L, E, x, kpm):
     s["qkv"] = E.linear(x, sa.in_proj_weight, sa.in_proj_bias, tag="qkv_gemm", planes_out=qkv_planes)
     s["ctx"], s["att"] = E.attention_fwd(s["qkv"], kpm, L.nhead, p)
     a = E.linear(s["ctx"], sa.out_proj.weight, sa.out_proj.bias, tag="out_proj_gemm")
-    s["drop1"] = E.dropout_(a, p)                                         # dropout1 (model.py:114)
-    x1, s["z1"], s["st1"] = ops.add_layernorm_train(x, a, L.norm1.weight, L.norm1.bias, L.eps)
+    s["drop1"] = E.site_token(p)                                          # dropout1 (model.py:114), fused into the LN kernel
+    x1, s["z1"], s["st1"] = ops.add_layernorm_train(x, a, L.norm1.weight, L.norm1.bias, L.eps, drop=s["drop1"])
     s["x1"] = x1
     if L.depthwise:
         s["dw_wt"] = ops.transpose(_dwmat(dwc.weight))                    # (k, d)
@@ -191,15 +198,16 @@ def fft_fwd(L, E, x, kpm):
         s["v"] = E.conv(x1, L.conv1.weight, L.conv1.bias, relu=True, tag="ffn1_gemm")
         s["dropv"] = E.dropout_(s["v"], p)
         y = E.conv(s["v"], L.conv2.weight, L.conv2.bias, tag="ffn2_gemm")
-    s["drop2"] = E.dropout_(y, p)                                         # dropout2 (model.py:115)
-    x2, s["z2"], s["st2"] = ops.add_layernorm_train(x1, y, L.norm2.weight, L.norm2.bias, L.eps)
+    s["drop2"] = E.site_token(p)                                          # dropout2 (model.py:115), fused into the LN kernel
+    x2, s["z2"], s["st2"] = ops.add_layernorm_train(x1, y, L.norm2.weight, L.norm2.bias, L.eps, drop=s["drop2"])
     return x2, s
 
 
 def fft_bwd(L, E, s, dx2):
     dev = dx2.device
-    dz2 = ops.layernorm_bwd(dx2, s["z2"], s["st2"], L.norm2.weight, grad_of(L.norm2.weight), grad_of(L.norm2.bias))
-    dy = E.dropout_bwd(dz2, s["drop2"], inplace=False)
+    dz2 = ops.layernorm_bwd(dx2, s["z2"], s["st2"], L.norm2.weight, grad_of(L.norm2.weight), grad_of(L.norm2.bias),
+                            drop=s["drop2"])
+    dz2, dy = dz2 if s["drop2"] else (dz2, dz2)                          # dy = dropout2's backward of dz2 (same kernel)
     if L.depthwise:
         dx1 = _ffn_bwd_depthwise(L, E, s, dy, dev)
     else:
@@ -230,8 +238,9 @@ def _ffn_bwd_depthwise(L, E, s, dy, dev):
 
 def _attn_bwd(L, E, s, dx1):
     sa = L.self_attn
-    dz1 = ops.layernorm_bwd(dx1, s["z1"], s["st1"], L.norm1.weight, grad_of(L.norm1.weight), grad_of(L.norm1.bias))
-    da = E.dropout_bwd(dz1, s["drop1"], inplace=False)
+    dz1 = ops.layernorm_bwd(dx1, s["z1"], s["st1"], L.norm1.weight, grad_of(L.norm1.weight), grad_of(L.norm1.bias),
+                            drop=s["drop1"])
+    dz1, da = dz1 if s["drop1"] else (dz1, dz1)
     dctx = E.dgrad(da, sa.out_proj.weight, tag="out_proj_dgrad")
     E.wgrad_(grad_of(sa.out_proj.weight), grad_of(sa.out_proj.bias), da, s["ctx"], tag="out_proj_wgrad")
     dqkv = E.attention_bwd(s["qkv"], s["ctx"], dctx, s["att"], s["kpm"], L.nhead)

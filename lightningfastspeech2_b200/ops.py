@@ -458,27 +458,33 @@ def attention_tc(qkv, kpm, nhead, npass=3, want_f32=False, want_planes=True):
 # ---------------------------------------------------------------------------------------------
 # train-step config: forward variants that save what the backward needs, backward kernels, loss,
 # optimizer.  Parameter gradients accumulate (+=) into the tensors passed as d<param>.
-def add_layernorm_train(x, y, gamma, beta, eps=LN_EPS):
-    """-> (out, z = x (+ y), stats (m,2) = per-row (mean, rstd))"""
+def add_layernorm_train(x, y, gamma, beta, eps=LN_EPS, drop=None):
+    """-> (out, z = x (+ y), stats (m,2) = per-row (mean, rstd)); drop = (p, seed, site): z = x + dropout(y), fused"""
     _chk(x, torch.float32, "layernorm input")
     d = x.shape[-1]
     m = x.numel() // d
     out = torch.empty_like(x)
     z = torch.empty_like(x) if y is not None else x
     stats = torch.empty(m, 2, device=x.device, dtype=torch.float32)
+    dp, dseed, dsite = drop if drop is not None else (0.0, 0, 0)
     _launch("lfs2_add_layernorm_train", _p(x), _p(y), _p(gamma), _p(beta), _p(out), _p(z if y is not None else None),
-            _p(stats), m, d, eps, _s(), tag="lfs2_add_layernorm", nbytes=4.0 * m * d * (4 if y is not None else 2))
+            _p(stats), m, d, eps, float(dp), int(dseed), int(dsite), _s(), tag="lfs2_add_layernorm",
+            nbytes=4.0 * m * d * (4 if y is not None else 2))
     return out, z, stats
 
 
-def layernorm_bwd(dy, z, stats, gamma, dgamma, dbeta, add=None):
+def layernorm_bwd(dy, z, stats, gamma, dgamma, dbeta, add=None, drop=None):
+    """-> dz, or (dz, dropout(dz)) when drop = (p, seed, site) of the branch dropout fused into the forward"""
     _chk(dy, torch.float32, "layernorm_bwd dy"); _chk(z, torch.float32, "layernorm_bwd z")
     d = z.shape[-1]
     m = z.numel() // d
     dz = torch.empty_like(z)
-    _launch("lfs2_layernorm_bwd", _p(dy), _p(z), _p(stats), _p(gamma), _p(add), _p(dz), _p(dgamma), _p(dbeta), m, d,
-            _s(), nbytes=4.0 * m * d * (3 + (add is not None)))
-    return dz
+    dzd = torch.empty_like(z) if drop is not None else None
+    dp, dseed, dsite = drop if drop is not None else (0.0, 0, 0)
+    _launch("lfs2_layernorm_bwd_drop", _p(dy), _p(z), _p(stats), _p(gamma), _p(add), _p(dz), _p(dzd), _p(dgamma),
+            _p(dbeta), m, d, float(dp), int(dseed), int(dsite), _s(), tag="lfs2_layernorm_bwd",
+            nbytes=4.0 * m * d * (3 + (add is not None) + (drop is not None)))
+    return dz if drop is None else (dz, dzd)
 
 
 def gemm_tn_(dw, dy, x, t=0, shift=0, col_offset=0):
@@ -720,10 +726,15 @@ def attention_mat_fwd(qkv, kpm, nhead, npass=3, drop=None):
     p = Planes(torch.empty(z, t, tp, device=dev, dtype=torch.bfloat16),
                torch.empty(z, t, tp, device=dev, dtype=torch.bfloat16) if npass == 3 else None)
     lse = torch.empty(z, t, device=dev, dtype=torch.float32)
-    _launch("lfs2_attn_softmax_planes", _p(s), _p(kpm), _p(p.hi), _p(p.lo), _p(lse), b, nhead, t, tp,
-            float(dh) ** -0.5, _s(), nbytes=(8.0 if npass == 3 else 6.0) * z * t * tp)
+    pm = p
+    if drop is not None:
+        pm = Planes(torch.empty_like(p.hi), torch.empty_like(p.lo) if p.lo is not None else None)
+    dp_, dseed, dsite = drop if drop is not None else (0.0, 0, 0)
+    _launch("lfs2_attn_softmax_planes_drop", _p(s), _p(kpm), _p(p.hi), _p(p.lo), _p(pm.hi if drop is not None else None),
+            _p(pm.lo if drop is not None else None), _p(lse), b, nhead, t, tp, float(dh) ** -0.5, float(dp_), int(dseed),
+            int(dsite), _s(), tag="lfs2_attn_softmax_planes",
+            nbytes=((8.0 if npass == 3 else 6.0) + (0.0 if drop is None else (4.0 if npass == 3 else 2.0))) * z * t * tp)
     del s
-    pm = dropout_planes(p, *drop) if drop is not None else p
     ctx = torch.empty(b, t, d, device=dev, dtype=torch.float32)
     p_op = _operand(pm.hi, False, per_z=True)
     v_op = _operand(qkv.hi, True, col0=2 * d, hstride=dh)
@@ -751,12 +762,13 @@ def attention_mat_bwd(qkv, p, ctx, dctx, nhead, npass=3, drop=None):
     v_k = _operand(qkv.hi, False, col0=2 * d, hstride=dh)
     gemm_tc2(do, do_k, qkv, v_k, dp, tp, t, t, dh, nbatch=b, nhead=nhead, c_bstride=nhead * t * tp, c_hstride=t * tp,
              npass=npass, tag="attn_dp_gemm")
-    if drop is not None:  # O = (P o M).V  =>  dP_eff = M o (dO.V^T); delta = rowsum(dO o O) still holds
-        dropout_(dp, *drop)
     ds = Planes(torch.empty(z, t, tp, device=dev, dtype=torch.bfloat16),
                 torch.empty(z, t, tp, device=dev, dtype=torch.bfloat16) if npass == 3 else None)
-    _launch("lfs2_attn_ds_planes", _p(p.hi), _p(p.lo), _p(dp), _p(delta), _p(ds.hi), _p(ds.lo), b, nhead, t, tp,
-            float(dh) ** -0.5, _s(), nbytes=(12.0 if npass == 3 else 8.0) * z * t * tp)
+    # O = (P o M).V  =>  dP_eff = M o (dO.V^T), applied inside the kernel; delta = rowsum(dO o O) still holds
+    dp_, dseed, dsite = drop if drop is not None else (0.0, 0, 0)
+    _launch("lfs2_attn_ds_planes_drop", _p(p.hi), _p(p.lo), _p(dp), _p(delta), _p(ds.hi), _p(ds.lo), b, nhead, t, tp,
+            float(dh) ** -0.5, float(dp_), int(dseed), int(dsite), _s(), tag="lfs2_attn_ds_planes",
+            nbytes=(12.0 if npass == 3 else 8.0) * z * t * tp)
     del dp
     dqkv = torch.empty(b, t, d3, device=dev, dtype=torch.float32)
     common = dict(nbatch=b, nhead=nhead, c_bstride=t * d3, c_hstride=dh, npass=npass)
