@@ -170,7 +170,9 @@ LFS2_API int lfs2_gemm_tc(const void* a_hi, const void* a_lo, int batch, int t, 
  * that starts at or after row_limit[b] + limit_extra is skipped and its output rows are left untouched (A is
  * tiled per utterance: batch x t).  Used by the variance predictors, whose outputs on PAD rows are masked to 0 by
  * construction (model.py:518), so skipping rows farther than the conv halo beyond an utterance's end changes no
- * result bit.  row_limit = lfs2_mask_lengths of the padding mask. */
+ * result bit.  row_limit = lfs2_mask_lengths of the padding mask.  The depthwise conv reads the input rows past the
+ * last kept tile (t_row >= roundup128(row_limit[b] + limit_extra)) as zeros instead of from memory, so a chain of
+ * row-limited kernels never consumes a row that none of them wrote. */
 LFS2_API int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch, int t, int d, int taps,
                                   const void* w_hi, const void* w_lo, int n, const float* bias, int relu,
                                   const void* res_hi, const void* res_lo, const void* ident_hi,
@@ -184,6 +186,9 @@ LFS2_API int lfs2_dwconv1d_planes_limited(const float* x, const void* x_hi, cons
                                           const float* bias, float* out, void* out_hi, void* out_lo, int batch,
                                           int t, int d, int ksize, const int* row_limit, int limit_extra,
                                           void* stream);
+/* x[r, :] = +0.0 for every row r with mask[r] != 0 (x: (rows, width) fp32, width % 4 == 0): the mel frames the
+ * reference's consumers drop with tgt_mask (generator.py:164) after a PAD-row skipping synthesis call. */
+LFS2_API int lfs2_zero_masked_rows(float* x, const uint8_t* mask, long long rows, int width, void* stream);
 /* lengths[b] = 1 + index of the last row with pad_mask[b, .] == 0 (0 if all PAD); pad_mask NULL -> t */
 LFS2_API int lfs2_mask_lengths(const uint8_t* pad_mask, int* lengths, int batch, int t, void* stream);
 
@@ -196,6 +201,17 @@ LFS2_API int lfs2_ffn_fused_tc(const void* u_hi, const void* u_lo, int m, const 
                                const float* b1, const void* w2_hi, const void* w2_lo, const float* b2,
                                const void* res_hi, const void* res_lo, const void* ident_hi, const float* gamma,
                                const float* beta, float eps, void* out_hi, void* out_lo, int npass, void* stream);
+/* Same over the (batch, t) rows of a padded batch, skipping the 128-row tiles no utterance needs: utterance b needs its
+ * rows t_row < roundup128(row_limit[b] + limit_extra) (the rule of lfs2_gemm_tc_limited); rows of skipped tiles are not
+ * written.  workspace: lfs2_ffn_fused_tc_limited_workspace_bytes(batch, t) bytes; row_limit NULL with a workspace
+ * filled by an earlier call = reuse that tile list; both NULL = every row.  Used by the PAD-row skipping synthesis
+ * path (PAD rows past an utterance's end + conv halo cannot reach its valid frames). */
+LFS2_API long long lfs2_ffn_fused_tc_limited_workspace_bytes(int batch, int t);
+LFS2_API int lfs2_ffn_fused_tc_limited(const void* u_hi, const void* u_lo, int batch, int t, const void* w1_hi,
+                                       const void* w1_lo, int f, const float* b1, const void* w2_hi, const void* w2_lo,
+                                       const float* b2, const void* res_hi, const void* res_lo, const void* ident_hi,
+                                       const float* gamma, const float* beta, float eps, void* out_hi, void* out_lo,
+                                       int npass, const int* row_limit, int limit_extra, void* workspace, void* stream);
 
 /* tensor-core multi-head self attention (head_dim 128) on the bf16 hi/lo planes of the packed
  * qkv (B,T,3d) tensor [q | k | v] written by lfs2_gemm_tc: flash-style streaming softmax,
@@ -209,6 +225,12 @@ LFS2_API int lfs2_attention_tc_workspace_bytes(int batch);
 LFS2_API int lfs2_attention_tc(const void* qkv_hi, const void* qkv_lo, const uint8_t* key_padding_mask,
                                void* ctx_hi, void* ctx_lo, float* ctx_f32, void* workspace, int batch, int t,
                                int d, int nhead, int npass, void* stream);
+/* Same, skipping the 128-row query tiles that start at or after row_limit[b] + limit_extra (their ctx rows are not
+ * written); row_limit NULL = every row.  Keys are unaffected (PAD keys are masked anyway). */
+LFS2_API int lfs2_attention_tc_limited(const void* qkv_hi, const void* qkv_lo, const uint8_t* key_padding_mask,
+                                       void* ctx_hi, void* ctx_lo, float* ctx_f32, void* workspace, int batch, int t,
+                                       int d, int nhead, int npass, const int* row_limit, int limit_extra,
+                                       void* stream);
 
 /* out = hi + lo (fp32) for n values (n % 4 == 0): the inverse of lfs2_split_bf16 up to 2^-17 relative */
 LFS2_API int lfs2_merge_planes(const void* hi, const void* lo, float* out, long long n, void* stream);

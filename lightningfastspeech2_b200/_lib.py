@@ -39,7 +39,11 @@ SIGNATURES = {
                              _i, _vp, _i, _vp, _vp],
     "lfs2_dwconv1d_planes_limited": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "lfs2_mask_lengths": [_vp, _vp, _i, _i, _vp],
+    "lfs2_zero_masked_rows": [_vp, _vp, _ll, _i, _vp],
     "lfs2_ffn_fused_tc": [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp],
+    "lfs2_ffn_fused_tc_limited": [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i,
+                                  _vp, _i, _vp, _vp],
+    "lfs2_attention_tc_limited": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "lfs2_attention_tc_workspace_bytes": [_i],
     "lfs2_attention_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "lfs2_split_bf16": [_vp, _vp, _vp, ctypes.c_longlong, _vp],
@@ -81,7 +85,8 @@ SIGNATURES = {
 }
 # functions whose return type is not int
 RESTYPES = {"lfs2_attention_bwd_workspace_bytes": (ctypes.c_longlong, [_i, _i, _i]),
-            "lfs2_gemm_tc_limited_workspace_bytes": (ctypes.c_longlong, [_i, _i])}
+            "lfs2_gemm_tc_limited_workspace_bytes": (ctypes.c_longlong, [_i, _i]),
+            "lfs2_ffn_fused_tc_limited_workspace_bytes": (ctypes.c_longlong, [_i, _i])}
 
 class Operand(ctypes.Structure):
     """lfs2_operand of include/lfs2.h"""

@@ -90,6 +90,8 @@ struct AttnTcParams {
   float* ctx_f32;               // (B, T, d) or null
   int t, d;
   float scale_log2e;            // head_dim^-1/2 * log2(e)
+  const int* row_limit;         // null, or (B): query tiles that start at or after row_limit[b] + limit_extra are skipped
+  int limit_extra;
 };
 
 // last valid key + 1 per utterance; one warp per utterance
@@ -134,6 +136,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kAQ, h = blockIdx.y, b = blockIdx.z;
+  // query rows the caller does not need (rows past an utterance's end + conv halo; same rule as the row-limited GEMM)
+  if (p.row_limit && q0 >= __ldg(p.row_limit + b) + p.limit_extra) return;
   const int kend = p.kend[b];
   const int ntiles = (kend + kAK - 1) / kAK;
   const int col_q = h * kDH, col_k = p.d + h * kDH, col_v = 2 * p.d + h * kDH;
@@ -485,6 +489,13 @@ int lfs2_mask_lengths(const uint8_t* pad_mask, int* lengths, int batch, int t, v
 int lfs2_attention_tc(const void* qkv_hi, const void* qkv_lo, const uint8_t* key_padding_mask, void* ctx_hi,
                       void* ctx_lo, float* ctx_f32, void* workspace, int batch, int t, int d, int nhead, int npass,
                       void* stream) {
+  return lfs2_attention_tc_limited(qkv_hi, qkv_lo, key_padding_mask, ctx_hi, ctx_lo, ctx_f32, workspace, batch, t, d,
+                                   nhead, npass, nullptr, 0, stream);
+}
+
+int lfs2_attention_tc_limited(const void* qkv_hi, const void* qkv_lo, const uint8_t* key_padding_mask, void* ctx_hi,
+                              void* ctx_lo, float* ctx_f32, void* workspace, int batch, int t, int d, int nhead,
+                              int npass, const int* row_limit, int limit_extra, void* stream) {
   LFS2_REQUIRE(qkv_hi && workspace, LFS2_ERR_INVALID_ARG, "attention_tc: null pointer");
   LFS2_REQUIRE(npass == 1 || npass == 3, LFS2_ERR_INVALID_ARG, "attention_tc: npass must be 1 or 3");
   LFS2_REQUIRE(npass == 1 || qkv_lo, LFS2_ERR_INVALID_ARG, "attention_tc: npass=3 needs the lo plane");
@@ -533,6 +544,8 @@ int lfs2_attention_tc(const void* qkv_hi, const void* qkv_lo, const uint8_t* key
   p.t = t;
   p.d = d;
   p.scale_log2e = (float)(1.4426950408889634 / sqrt((double)kDH));
+  p.row_limit = row_limit;
+  p.limit_extra = limit_extra;
   return npass == 3 ? launch_attention_tc<3>(m, p, batch, nhead, s) : launch_attention_tc<1>(m, p, batch, nhead, s);
 }
 

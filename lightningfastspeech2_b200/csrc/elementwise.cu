@@ -372,8 +372,14 @@ dwconv1d_k_kernel(const float4* __restrict__ x, const uint2* __restrict__ x_hi, 
   const int t0 = blockIdx.x * kDwTile;
   const int cb = blockIdx.y * kDwCh4;  // first float4 channel group of this CTA
   const int b = blockIdx.z;
-  // rows the caller does not need (same 128-row granularity as the tensor-core GEMM that consumes the result)
-  if (row_limit && (t0 & ~127) >= __ldg(row_limit + b) + limit_extra) return;
+  // rows the caller does not need (same 128-row granularity as the tensor-core GEMM that consumes the result);
+  // the rows past the last kept 128-row group are nobody's output, so they are read as zeros, not from memory
+  int t_in = t;
+  if (row_limit) {
+    const int lim = __ldg(row_limit + b) + limit_extra;
+    if ((t0 & ~127) >= lim) return;
+    t_in = min(t, (lim + 127) & ~127);
+  }
   const int nch = min(kDwCh4, d4 - cb);
   const size_t base = (size_t)b * t * d4 + cb;
 
@@ -389,7 +395,7 @@ dwconv1d_k_kernel(const float4* __restrict__ x, const uint2* __restrict__ x_hi, 
     for (int it = 0; it < kIters; ++it) {
       const int row = row0 + it * kRowStep;
       const int ti = t0 - H + row;
-      const bool ok = row < kRows && ti >= 0 && ti < t && c < nch;
+      const bool ok = row < kRows && ti >= 0 && ti < t_in && c < nch;
       const size_t gi = base + (size_t)(ok ? ti : 0) * d4 + (ok ? c : 0);
       if (IN_PLANES) {
         rh[it] = ok ? x_hi[gi] : make_uint2(0u, 0u);
@@ -482,11 +488,29 @@ __global__ void merge_planes_kernel(const uint2* __restrict__ hi, const uint2* _
   if (i < n4) out[i] = planes_to_f4(hi[i], lo[i]);
 }
 
+// x[r, :] = 0 where mask[r] != 0; one warp per row, float4 stores
+__global__ void zero_masked_rows_kernel(float4* __restrict__ x, const uint8_t* __restrict__ mask, long long rows, int w4) {
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (r >= rows || !mask[r]) return;
+  for (int c = threadIdx.x & 31; c < w4; c += 32) x[r * w4 + c] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
 }  // namespace lfs2
 
 using namespace lfs2;
 
 extern "C" {
+
+int lfs2_zero_masked_rows(float* x, const uint8_t* mask, long long rows, int width, void* stream) {
+  LFS2_REQUIRE(x && mask, LFS2_ERR_INVALID_ARG, "zero_masked_rows: null pointer");
+  if (rows == 0) return LFS2_OK;
+  LFS2_REQUIRE(rows > 0 && width > 0 && width % 4 == 0, LFS2_ERR_UNSUPPORTED,
+               "zero_masked_rows: width must be a positive multiple of 4");
+  LFS2_REQUIRE(aligned16(x), LFS2_ERR_INVALID_ARG, "zero_masked_rows: x must be 16-byte aligned");
+  zero_masked_rows_kernel<<<ceil_div(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>((float4*)x, mask, rows, width / 4);
+  LFS2_CHECK_LAUNCH("zero_masked_rows");
+  return LFS2_OK;
+}
 
 int lfs2_merge_planes(const void* hi, const void* lo, float* out, long long n, void* stream) {
   LFS2_REQUIRE(hi && lo && out, LFS2_ERR_INVALID_ARG, "merge_planes: null pointer");

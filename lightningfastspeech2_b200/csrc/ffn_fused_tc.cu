@@ -32,12 +32,33 @@ struct FfnParams {
   int m;            // rows
   int f;            // hidden width (multiple of 256)
   int total_tiles;
+  const int* tile_list;  // null, or [0] = number of active 128-row tiles, [1..] = their indices (row-limited launch)
   const float* b1;  // (f)
   const float* b2;  // (256) folded bias
   const float* gamma;
   const float* beta;
   float eps;
 };
+
+// work item i of this CTA's stride loop -> 128-row tile
+__device__ __forceinline__ int tile_count(const FfnParams& p) { return p.tile_list ? __ldg(p.tile_list) : p.total_tiles; }
+__device__ __forceinline__ int tile_at(const FfnParams& p, int i) { return p.tile_list ? __ldg(p.tile_list + 1 + i) : i; }
+
+// active tiles of a row-limited launch over (batch, t) rows flattened to (batch * t): a 128-row tile is needed when it
+// holds a row of some utterance b before that utterance's last kept 128-row group, i.e. t_row < roundup128(limit[b] + extra)
+__global__ void ffn_tile_list_kernel(const int* __restrict__ row_limit, int extra, int batch, int t, int total_tiles,
+                                     int* __restrict__ list) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total_tiles; i += gridDim.x * blockDim.x) {
+    const long long r0 = (long long)i * kFM, r1 = min(r0 + kFM, (long long)batch * t);
+    bool need = false;
+    for (int b = (int)(r0 / t); b < batch && (long long)b * t < r1 && !need; ++b) {
+      const int lim = min(t, (row_limit[b] + extra + 127) & ~127);
+      const long long first = max(r0, (long long)b * t);
+      need = first < (long long)b * t + lim;
+    }
+    if (need) list[1 + atomicAdd(list, 1)] = i;
+  }
+}
 
 template <int NPASS>
 struct FfnSmem {
@@ -98,6 +119,7 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = p.f / kFC;
+  const int ntiles = tile_count(p);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_u_hi);
@@ -168,8 +190,8 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
           next();
         }
       };
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int r0 = tile * kFM;
+      for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
+        const int r0 = tile_at(p, ti) * kFM;
         load_g1(r0, 0);
         for (int c = 0; c < nchunks; ++c) {  // same order as the MMA warp: G1(c+1) is issued before G2(c)
           if (c + 1 < nchunks) load_g1(r0, c + 1);
@@ -227,7 +249,7 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
         next();
       }
     };
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
       issue_g1(chunk_ctr);
       for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
         // G1 of the next chunk goes first: it runs on the tensor pipe while the epilogue warps convert chunk c.
@@ -294,8 +316,8 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
     uint32_t chunk_ctr = 0, st_ctr = 0;
     int it = 0;
     float v[32];
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
-      const int r0 = tile * kFM;
+    for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
+      const int r0 = tile_at(p, ti) * kFM;
       // ---- E1 per F chunk: acc1 -> relu(acc1 + b1) as bf16 hi/lo pairs, in place ----
       for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
         mbar_wait(&acc1_full[chunk_ctr & 1], (chunk_ctr >> 1) & 1);
@@ -415,6 +437,22 @@ extern "C" int lfs2_ffn_fused_tc(const void* u_hi, const void* u_lo, int m, cons
                                  const float* b1, const void* w2_hi, const void* w2_lo, const float* b2,
                                  const void* res_hi, const void* res_lo, const void* ident_hi, const float* gamma,
                                  const float* beta, float eps, void* out_hi, void* out_lo, int npass, void* stream) {
+  return lfs2_ffn_fused_tc_limited(u_hi, u_lo, 1, m, w1_hi, w1_lo, f, b1, w2_hi, w2_lo, b2, res_hi, res_lo, ident_hi, gamma,
+                                   beta, eps, out_hi, out_lo, npass, nullptr, 0, nullptr, stream);
+}
+
+extern "C" long long lfs2_ffn_fused_tc_limited_workspace_bytes(int batch, int t) {
+  return batch > 0 && t > 0 ? (1 + (long long)ceil_div((long long)batch * t, kFM)) * (long long)sizeof(int) : 0;
+}
+
+extern "C" int lfs2_ffn_fused_tc_limited(const void* u_hi, const void* u_lo, int batch, int t, const void* w1_hi,
+                                         const void* w1_lo, int f, const float* b1, const void* w2_hi, const void* w2_lo,
+                                         const float* b2, const void* res_hi, const void* res_lo, const void* ident_hi,
+                                         const float* gamma, const float* beta, float eps, void* out_hi, void* out_lo,
+                                         int npass, const int* row_limit, int limit_extra, void* workspace, void* stream) {
+  LFS2_REQUIRE(batch >= 0 && t >= 0 && (long long)batch * t <= 0x7fffffffLL, LFS2_ERR_INVALID_ARG, "ffn_fused_tc: bad shape");
+  LFS2_REQUIRE(!row_limit || workspace, LFS2_ERR_INVALID_ARG, "ffn_fused_tc: a row-limited launch needs its workspace");
+  const int m = batch * t;
   LFS2_REQUIRE(u_hi && w1_hi && w2_hi && res_hi && res_lo && ident_hi && gamma && beta && out_hi && out_lo,
                LFS2_ERR_INVALID_ARG, "ffn_fused_tc: null pointer");
   LFS2_REQUIRE(npass == 1 || npass == 3, LFS2_ERR_INVALID_ARG, "ffn_fused_tc: npass must be 1 or 3");
@@ -446,5 +484,18 @@ extern "C" int lfs2_ffn_fused_tc(const void* u_hi, const void* u_lo, int m, cons
   p.m = m; p.f = f; p.total_tiles = ceil_div(m, kFM);
   p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta; p.eps = eps;
   cudaStream_t s = (cudaStream_t)stream;
+  p.tile_list = nullptr;
+  if (!row_limit && workspace) {
+    p.tile_list = reinterpret_cast<const int*>(workspace);  // a list built earlier for the same (batch, t, limit): reuse
+  } else if (row_limit) {  // compact list of the needed row tiles, built on the device (no host read-back)
+    int* list = reinterpret_cast<int*>(workspace);
+    if (cudaMemsetAsync(list, 0, sizeof(int), s) != cudaSuccess) {
+      set_error("ffn_fused_tc: cudaMemsetAsync failed");
+      return LFS2_ERR_CUDA;
+    }
+    ffn_tile_list_kernel<<<ceil_div(p.total_tiles, 256), 256, 0, s>>>(row_limit, limit_extra, batch, t, p.total_tiles, list);
+    LFS2_CHECK_LAUNCH("ffn_tile_list");
+    p.tile_list = list;
+  }
   return npass == 3 ? launch_ffn<3>(maps, p, s) : launch_ffn<1>(maps, p, s);
 }

@@ -78,16 +78,25 @@ class TransformerStack(nn.Module):
         super().__init__()
         self.layers = nn.ModuleList(layers)
 
-    def forward(self, src, mask=None, src_key_padding_mask=None, return_planes=False):
+    def supports_row_limit(self, d):
+        return all(mod.supports_row_limit(d) for mod in self.layers)
+
+    def forward(self, src, mask=None, src_key_padding_mask=None, return_planes=False, row_limit=None):
         """return_planes=True (tensor-core path only) hands the result back as bf16 hi/lo planes,
-        the operand format of the next GEMM, instead of materialising an fp32 tensor."""
+        the operand format of the next GEMM, instead of materialising an fp32 tensor.
+        row_limit = (lengths, extra): rows at or after roundup128(lengths[b] + extra) are neither computed nor
+        written by any layer (FastSpeech2.skip_pad_rows)."""
         if mask is None and all(mod.tc_capable(src.shape[-1]) for mod in self.layers):
             xp = ops.planes_of(src)
+            if row_limit is not None:
+                row_limit = (row_limit[0], row_limit[1], {})  # one tile list per kernel family for the whole stack
             for mod in self.layers:
                 if mod.training and mod.p_drop > 0:
                     raise NotImplementedError("dropout in training mode is not implemented by the CUDA path")
-                xp = mod.forward_planes(xp, src_key_padding_mask)
+                xp = mod.forward_planes(xp, src_key_padding_mask, row_limit=row_limit)
             return xp if return_planes else ops.merge_planes(xp)
+        if row_limit is not None:
+            raise NotImplementedError("row limits need the tensor-core path")
         out = src
         for mod in self.layers:
             out = mod(out, src_mask=mask, src_key_padding_mask=src_key_padding_mask)
@@ -291,8 +300,15 @@ class FastSpeech2(_Base):
             hp.duration_dropout, hp.duration_filter_size, hp.duration_depthwise_conv, hp.encoder_hidden,
             self._max_frames()).to(self.device)
 
+    def _apply(self, fn, *args, **kwargs):
+        # .to() / .cuda() / .float(): parameters move, every captured graph and the cached parameter list is stale
+        self.__dict__.pop("_graph_params", None)
+        self.__dict__.pop("_graphs", None)
+        return super()._apply(fn, *args, **kwargs)
+
     # -- checkpoint hooks (reference :530-634) -----------------------------------------------
     def on_load_checkpoint(self, checkpoint):
+        self.__dict__.pop("_graph_params", None)
         self.stats = checkpoint["stats"]
         if not hasattr(self, "variance_adaptor"):
             self.variance_adaptor = self._make_variance_adaptor()
@@ -354,7 +370,10 @@ class FastSpeech2(_Base):
             raise NotImplementedError("dropout in training mode outside the train step (use model.train() with grad "
                                       "enabled for the train path, or .eval())")
         output, src_mask = ops.embed_pe_spk(phones, self.phone_embedding.weight, pe, spk)
-        output = self.encoder(output, src_key_padding_mask=src_mask)
+        limit = None
+        if self._skips_pad_rows(inference):
+            limit = (ops.mask_lengths(src_mask), self._halos()[0])
+        output = self.encoder(output, src_key_padding_mask=src_mask, row_limit=limit)
         if len(hp.priors):  # per-utterance prior embeddings, broadcast over the phones (reference :687-692)
             zero_pe = torch.zeros(1, max(output.shape[1], 1), output.shape[2], device=dev)
             for prior in hp.priors:
@@ -374,7 +393,16 @@ class FastSpeech2(_Base):
                                                        control=control, scan=scan, frames=frames)
         output = ops.add_pe_spk_(variance_output["x"], pe, spk)
         tgt_mask = variance_output["tgt_mask"]
-        if self.compute_mode != "simt" and hp.decoder_hidden % 32 == 0 and hp.n_mels % 16 == 0:
+        if self._skips_pad_rows(inference):
+            # PAD rows farther than the decoder's conv halo past an utterance's end: never computed, never written
+            lens = ops.mask_lengths(tgt_mask)
+            output = self.decoder(output, src_key_padding_mask=tgt_mask, return_planes=True,
+                                  row_limit=(lens, sum(layer.halo() for layer in self.decoder.layers)))
+            wmel = self._mel_pack.get([self.linear.weight], lambda: ops.split_bf16(self.linear.weight.detach().contiguous()))
+            mel = ops.gemm_tc(output, wmel, self.linear.bias, npass=3 if self.compute_mode == "fp32" else 1,
+                              tag="mel_linear", row_limit=(lens, 0))
+            ops.zero_masked_rows_(mel, tgt_mask)
+        elif self.compute_mode != "simt" and hp.decoder_hidden % 32 == 0 and hp.n_mels % 16 == 0:
             output = self.decoder(output, src_key_padding_mask=tgt_mask, return_planes=True)
             wmel = self._mel_pack.get([self.linear.weight], lambda: ops.split_bf16(self.linear.weight.detach().contiguous()))
             mel = ops.gemm_tc(output, wmel, self.linear.bias, npass=3 if self.compute_mode == "fp32" else 1,
@@ -402,6 +430,25 @@ class FastSpeech2(_Base):
                 result[f"_bucket_{var}"] = variance_output[f"_bucket_{var}"]
         return result
 
+    # -- PAD-row skipping synthesis ("drop PAD-row compute where provably unobservable") ----------
+    # Off by default: the default path computes every PAD row like the reference does.  When on, inference runs
+    # every encoder / decoder kernel only over the 128-row tiles that start before an utterance's end + the summed
+    # conv half-widths downstream (`_halos`): PAD rows are never attention keys, so rows farther out cannot reach a
+    # valid row, and the depthwise convs read the rows past the last kept tile as zeros.  Valid mel frames (and all
+    # predictions) are bit-identical to the default path; mel frames masked by tgt_mask come back as zeros.
+    skip_pad_rows = False
+
+    def _skips_pad_rows(self, inference):
+        if not (self.skip_pad_rows and inference) or self.length_buckets > 1:
+            return False
+        hp = self.hparams
+        if self.compute_mode == "simt" or hp.n_mels % 16 != 0 or any(lv != "frame" for lv in hp.variance_levels) \
+                or not self.encoder.supports_row_limit(hp.encoder_hidden) \
+                or not self.decoder.supports_row_limit(hp.decoder_hidden):
+            raise NotImplementedError("skip_pad_rows needs the fused tensor-core FFTBlocks (d = 256, head_dim 128, "
+                                      "depthwise FFN, frame-level variances, compute mode fp32 or bf16)")
+        return True
+
     # -- length-bucketed synthesis ---------------------------------------------------
     length_buckets = 1
     bucket_graphs = True   # replay each bucket's kernel sequence as a CUDA graph once its shape has been seen twice
@@ -409,8 +456,11 @@ class FastSpeech2(_Base):
 
     def _graphs_validate(self):
         """graphs bake in the addresses of the packed weights: drop them when any parameter changed"""
-        sig = (ops.WEIGHTS_EPOCH, self.compute_mode, sum(p._version for p in self.parameters()),
-               sum(p.data_ptr() for p in self.parameters()) & 0xFFFFFFFFFFFF)
+        plist = self.__dict__.get("_graph_params")
+        if plist is None:  # walking the module tree costs ~1 ms; the Parameter objects only change with the module set
+            plist = self.__dict__["_graph_params"] = list(self.parameters())
+        sig = (ops.WEIGHTS_EPOCH, self.compute_mode, sum(p._version for p in plist),
+               sum(p.data_ptr() for p in plist) & 0xFFFFFFFFFFFF)
         if getattr(self, "_graph_sig", None) != sig:
             self._graphs = {}
             self._graph_sig = sig

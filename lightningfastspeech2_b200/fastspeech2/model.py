@@ -207,30 +207,43 @@ class ConformerEncoderLayer(nn.Module):
         fsz = self.conv1[1].weight.shape[0] if self.depthwise else self.conv1.weight.shape[0]
         return self.compute_mode != "simt" and _tc_ok(d, fsz)
 
-    def forward_planes(self, xp, kpm):
+    def supports_row_limit(self, d):
+        """the PAD-row skipping path exists for the fully fused block: d = 256, head_dim 128, depthwise fused FFN"""
+        if not (self.depthwise and self.tc_capable(d) and d == 256 and d // self.nhead == 128 and self.fused_ffn):
+            return False
+        fsz = self.conv1[1].weight.shape[0]
+        return fsz % 256 == 0 and fsz <= 2048 and self.conv1[0].kernel_size[0] <= 25
+
+    def forward_planes(self, xp, kpm, row_limit=None):
         """tcgen05 path, planes in -> planes out.  Activations travel between kernels only as bf16
         hi/lo planes (x = hi + lo to 2^-17): every GEMM has fused bias/ReLU epilogues, the
         residual add rides the tensor core (identity slabs) and LayerNorm is the epilogue of the
-        out-proj and FFN-2 GEMMs; attention keeps Q/P in tensor memory."""
+        out-proj and FFN-2 GEMMs; attention keeps Q/P in tensor memory.
+        row_limit = (lengths int32 (B), extra, cache dict): every kernel of the block skips the 128-row tiles at or
+        after lengths[b] + extra of utterance b (see FastSpeech2.skip_pad_rows)."""
         npass = _npass(self.compute_mode)
         sa, w, p = self.self_attn, self._packed_tc(), self._packed()
         d = xp.shape[-1]
+        if row_limit is not None and not self.supports_row_limit(d):
+            raise NotImplementedError("row-limited FFTBlock needs d = 256, head_dim 128 and the fused depthwise FFN")
         if d != 256:
             return ops.planes_of(self._forward_tc_unfused_ln(ops.merge_planes(xp), xp, kpm, npass))
         if d // self.nhead == 128:
-            qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="planes", npass=npass, tag="qkv_gemm")
-            _, ctx = ops.attention_tc(qkv, kpm, self.nhead, npass=npass)
+            qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="planes", npass=npass, tag="qkv_gemm",
+                              row_limit=row_limit)
+            _, ctx = ops.attention_tc(qkv, kpm, self.nhead, npass=npass, row_limit=row_limit)
         else:
             ctx = self._attention_any_head_dim(xp, kpm, npass)
         x1p = ops.gemm_tc(ctx, w["out_proj"], sa.out_proj.bias, residual=xp, gamma=self.norm1.weight,
-                          beta=self.norm1.bias, eps=self.eps, out="planes", npass=npass, tag="out_proj_ln_gemm")
+                          beta=self.norm1.bias, eps=self.eps, out="planes", npass=npass, tag="out_proj_ln_gemm",
+                          row_limit=row_limit)
         if self.depthwise:
-            up = ops.dwconv1d_planes(x1p, p["dw_wt"], self.conv1[0].bias)
+            up = ops.dwconv1d_planes(x1p, p["dw_wt"], self.conv1[0].bias, row_limit=row_limit)
             fsz = w["pw1"].shape[0]
             if self.fused_ffn and fsz % 256 == 0 and fsz <= 2048:
                 # FFN-1 -> ReLU -> FFN-2 -> + x1 -> LayerNorm in one kernel, the F-wide intermediate in tensor memory
                 return ops.ffn_fused_tc(up, w["pw1"], self.conv1[1].bias, w["w_eff"], p["b_eff"], x1p,
-                                        self.norm2.weight, self.norm2.bias, self.eps, npass=npass)
+                                        self.norm2.weight, self.norm2.bias, self.eps, npass=npass, row_limit=row_limit)
             vp = ops.gemm_tc(up, w["pw1"], self.conv1[1].bias, relu=True, out="planes", npass=npass, tag="ffn1_gemm")
             w2, b2, taps2 = w["w_eff"], p["b_eff"], 1
         else:

@@ -313,6 +313,15 @@ def mask_lengths(mask):
     return out
 
 
+def zero_masked_rows_(x, mask):
+    """x (..., w) fp32, mask (...) bool: x[mask] = 0 in place"""
+    _chk(x, torch.float32, "zero_masked_rows input"); _chk(mask, torch.bool, "zero_masked_rows mask")
+    if tuple(x.shape[:-1]) != tuple(mask.shape):
+        raise ValueError("zero_masked_rows_: mask must be shaped like x without its last dim")
+    _launch("lfs2_zero_masked_rows", _p(x), _p(mask), mask.numel(), x.shape[-1], _s(), nbytes=2.0 * x.numel())
+    return x
+
+
 def dwconv1d_planes(x, wt, bias, out="planes", row_limit=None):
     """depthwise conv, x (B,T,d) fp32 tensor or Planes, wt (ksize,d) -> Planes (or fp32 if out == "f32").
     row_limit = (lengths int32 (B), extra): 128-row groups starting at or after lengths[b] + extra are skipped."""
@@ -383,7 +392,9 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
         _chk(x_, torch.bfloat16, "gemm_tc operand plane")
     out_shape = tuple(a.shape[:-1]) + (n,)
     dev = a.hi.device
-    of = torch.empty(out_shape, device=dev, dtype=torch.float32) if out == "f32" else None
+    # an fp32 result of a row-limited launch is a user-visible tensor: the rows of skipped tiles read as zeros
+    of = (torch.zeros if row_limit is not None else torch.empty)(out_shape, device=dev, dtype=torch.float32) \
+        if out == "f32" else None
     po = _empty_planes(out_shape, dev) if out == "planes" else None
     ident = None
     if residual is not None:
@@ -414,9 +425,11 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
     return of if out == "f32" else po
 
 
-def ffn_fused_tc(u, w1, b1, w2, b2, residual, gamma, beta, eps=LN_EPS, npass=3):
+def ffn_fused_tc(u, w1, b1, w2, b2, residual, gamma, beta, eps=LN_EPS, npass=3, row_limit=None):
     """LayerNorm(residual + relu(u . w1^T + b1) . w2^T + b2) in one kernel, the F-wide intermediate on chip.
-    u, residual: Planes (..., 256); w1 Planes (F, 256); w2 Planes (256, F) -> Planes (..., 256)"""
+    u, residual: Planes (..., 256); w1 Planes (F, 256); w2 Planes (256, F) -> Planes (..., 256).
+    row_limit = (lengths int32 (B), extra[, cache dict]) on (B,T,256) operands: 128-row tiles that hold no row
+    t < roundup128(lengths[b] + extra) of any utterance are skipped (their output rows stay unwritten)."""
     d = u.shape[-1]
     f = w1.shape[0]
     if d != 256 or tuple(w1.shape) != (f, 256) or tuple(w2.shape) != (256, f) or tuple(residual.shape) != tuple(u.shape):
@@ -426,14 +439,34 @@ def ffn_fused_tc(u, w1, b1, w2, b2, residual, gamma, beta, eps=LN_EPS, npass=3):
     m = u.hi.numel() // d
     out = _empty_planes(tuple(u.shape), u.hi.device)
     ident = _identity_planes(d, u.hi.device)
-    _launch("lfs2_ffn_fused_tc", _p(u.hi), _p(u.lo), m, _p(w1.hi), _p(w1.lo), f, _p(b1), _p(w2.hi), _p(w2.lo), _p(b2),
-            _p(residual.hi), _p(residual.lo), _p(ident), _p(gamma), _p(beta), float(eps), _p(out.hi), _p(out.lo), npass,
-            _s(), tag="ffn_fused", flops=4.0 * m * d * f, nbytes=4.0 * m * d * 3 + 8.0 * d * f)
+    if row_limit is None:
+        batch, t, lim, extra, ws = 1, m, None, 0, None
+    else:
+        if u.hi.dim() != 3:
+            raise ValueError("ffn_fused_tc: a row limit needs (B,T,256) operands")
+        batch, t = u.shape[0], u.shape[1]
+        lim, extra = row_limit[0], row_limit[1]
+        cache = row_limit[2] if len(row_limit) > 2 else None
+        key = ("ffn", batch, t)
+        if cache is not None and key in cache:
+            ws, lim = cache[key], None
+        else:
+            ws = torch.empty(_lib.lib().lfs2_ffn_fused_tc_limited_workspace_bytes(batch, t) // 4, device=u.hi.device,
+                             dtype=torch.int32)
+            if cache is not None:
+                cache[key] = ws
+        m = m * _limited_fraction(row_limit, t)
+    _launch("lfs2_ffn_fused_tc_limited", _p(u.hi), _p(u.lo), batch, t, _p(w1.hi), _p(w1.lo), f, _p(b1), _p(w2.hi),
+            _p(w2.lo), _p(b2), _p(residual.hi), _p(residual.lo), _p(ident), _p(gamma), _p(beta), float(eps), _p(out.hi),
+            _p(out.lo), npass, _p(lim), int(extra), _p(ws), _s(), tag="ffn_fused", flops=4.0 * m * d * f,
+            nbytes=4.0 * m * d * 3 + 8.0 * d * f)
     return out
 
 
-def attention_tc(qkv, kpm, nhead, npass=3, want_f32=False, want_planes=True):
-    """qkv: Planes (B,T,3d) packed [q|k|v]; kpm (B,T) bool True=PAD -> (ctx f32 or None, ctx Planes or None)"""
+def attention_tc(qkv, kpm, nhead, npass=3, want_f32=False, want_planes=True, row_limit=None):
+    """qkv: Planes (B,T,3d) packed [q|k|v]; kpm (B,T) bool True=PAD -> (ctx f32 or None, ctx Planes or None).
+    row_limit = (lengths int32 (B), extra, ...): 128-row query tiles starting at or after lengths[b] + extra are
+    skipped (their ctx rows stay unwritten)."""
     if not isinstance(qkv, Planes):
         raise TypeError("attention_tc: qkv must be Planes")
     _chk(qkv.hi, torch.bfloat16, "qkv.hi", 3); _chk(qkv.lo, torch.bfloat16, "qkv.lo", 3)
@@ -445,13 +478,19 @@ def attention_tc(qkv, kpm, nhead, npass=3, want_f32=False, want_planes=True):
     ctx = torch.empty(b, t, d, device=dev, dtype=torch.float32) if want_f32 else None
     po = _empty_planes((b, t, d), dev) if want_planes else None
     ws = torch.empty(max(1, _lib.lib().lfs2_attention_tc_workspace_bytes(b)), device=dev, dtype=torch.uint8)
-    fl = 0.0
-    if PROFILE is not None:  # algorithmic flops: every query row x the utterance's VALID keys
-        nkeys = (~kpm).sum(1).double() if kpm is not None else torch.full((b,), float(t))
-        fl = float(4.0 * d * t * nkeys.sum())
-    _launch("lfs2_attention_tc", _p(qkv.hi), _p(qkv.lo), _p(kpm), _p(po.hi if po else None),
-            _p(po.lo if po else None), _p(ctx), _p(ws), b, t, d, nhead, npass, _s(), flops=fl,
-            nbytes=4.0 * qkv.hi.numel() + 4.0 * b * t * d * (int(want_f32) + int(want_planes)))
+    lim, extra = (row_limit[0], row_limit[1]) if row_limit is not None else (None, 0)
+    fl, frac = 0.0, 1.0
+    if PROFILE is not None:  # algorithmic flops: every (computed) query row x the utterance's VALID keys
+        nkeys = (~kpm).sum(1).double() if kpm is not None else torch.full((b,), float(t), device=dev, dtype=torch.float64)
+        rows = torch.full((b,), float(t), device=dev, dtype=torch.float64)
+        if lim is not None:
+            rows = torch.clamp((lim.long() + extra + 127) // 128 * 128, min=0, max=t).double()
+            frac = float(rows.sum()) / float(b * t)
+        fl = float(4.0 * d * (rows * nkeys.to(dev)).sum())
+    _launch("lfs2_attention_tc_limited", _p(qkv.hi), _p(qkv.lo), _p(kpm), _p(po.hi if po else None),
+            _p(po.lo if po else None), _p(ctx), _p(ws), b, t, d, nhead, npass, _p(lim), int(extra), _s(),
+            tag="lfs2_attention_tc", flops=fl,
+            nbytes=(4.0 * qkv.hi.numel() + 4.0 * b * t * d * (int(want_f32) + int(want_planes))) * frac)
     return ctx, po
 
 

@@ -157,6 +157,52 @@ def test_length_bucketed_synthesis_matches_full_batch(preset, bsz, lo, hi, bucke
     assert (pr["mel"].cpu() - ref["mel"])[vr].abs().max() < MEL_TOL
 
 
+@pytest.mark.parametrize("bsz,lo,hi,mode", [(10, 8, 300, "fp32"), (7, 30, 420, "fp32"), (6, 8, 200, "bf16")])
+def test_skip_pad_rows_is_bit_identical_on_valid_frames(bsz, lo, hi, mode):
+    """model.skip_pad_rows: every encoder/decoder kernel skips the 128-row tiles past an utterance's end + conv halo.
+    Nothing a valid frame depends on may change: predictions, durations, masks and valid mel frames must be
+    bit-identical to the default path (which computes every PAD row like the reference); masked frames are zeros."""
+    model, sd, hp = build("C2", 5, mode=mode)
+    batch = synthetic.make_batch(bsz, lo, hi, seed=5)
+    with torch.no_grad():
+        full = model(batch, inference=True, force={"want_idx": True})
+        model.skip_pad_rows = True
+        part = model(batch, inference=True, force={"want_idx": True})
+        model.skip_pad_rows = False
+    assert torch.equal(full["duration_rounded"], part["duration_rounded"])
+    assert torch.equal(full["duration_prediction"], part["duration_prediction"])
+    assert torch.equal(full["tgt_mask"], part["tgt_mask"]) and torch.equal(full["src_mask"], part["src_mask"])
+    valid = ~full["tgt_mask"]
+    for v in hp["variances"]:
+        assert torch.equal(full[f"variances_{v}"], part[f"variances_{v}"]), v
+        assert torch.equal(full[f"_bucket_{v}"][valid], part[f"_bucket_{v}"][valid]), v
+    assert full["mel"].shape == part["mel"].shape
+    assert torch.equal(full["mel"][valid], part["mel"][valid])
+    assert float(part["mel"][full["tgt_mask"]].abs().max()) == 0.0 and bool(torch.isfinite(part["mel"]).all())
+    # the rows really were skipped: more than a third of this ragged batch's frame tiles lie past end + halo
+    lens = valid.sum(1)
+    kept = torch.clamp((lens + 28 + 127) // 128 * 128, max=valid.shape[1]).sum().item()
+    assert kept < 0.8 * valid.numel(), (kept, valid.numel())
+    if mode == "fp32":  # and against the oracle, its discrete decisions forced
+        ref = O.forward(sd, hp, batch, inference=True)
+        force = {"duration_rounded": ref["duration_rounded"], "bucket_idx": {v: ref[f"_bucket_{v}"] for v in hp["variances"]}}
+        model.skip_pad_rows = True
+        with torch.no_grad():
+            pr = model(batch, inference=True, force=force)
+        model.skip_pad_rows = False
+        assert torch.equal(pr["tgt_mask"].cpu(), ref["tgt_mask"])
+        vr = ~ref["tgt_mask"]
+        assert (pr["mel"].cpu() - ref["mel"])[vr].abs().max() < MEL_TOL
+
+
+def test_skip_pad_rows_unsupported_configs_raise():
+    model, sd, hp = build("C1", 3)  # dense FFN convolutions: no row-limited path
+    model.skip_pad_rows = True
+    with pytest.raises(NotImplementedError):
+        with torch.no_grad():
+            model(synthetic.make_batch(2, 8, 20, seed=1), inference=True)
+
+
 def test_length_regulator_extra_frames_respect_the_cut():
     """extra PAD frames are appended after the reference's L, also when an utterance is truncated at max_length"""
     x = torch.randn(2, 4, 8)
