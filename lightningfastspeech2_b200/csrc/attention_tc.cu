@@ -7,17 +7,18 @@
 //   no transposed copy of V exists anywhere).
 //
 //   TMEM columns (512):  [0,128)   Q   bf16 pairs: hi plane cols 0..63, lo plane cols 64..127
-//                        [128,320) S/P three 64-column buffers: S_j fp32 (64 keys) is
-//                                  overwritten in place by P_j (hi: 32 cols, lo: 32 cols)
-//                        [320,448) O   fp32 accumulator (128 head-dim columns)
+//                        [128,..)  S/P buffers: S_J fp32 (a group of kG 64-key tiles, see AttnCfg) is
+//                                  overwritten in place by P_J (hi: first half of the columns, lo: second half);
+//                                  two 128-column buffers (kG = 2)
+//                        then      O   fp32 accumulator (128 head-dim columns)
 //
 //   warps: 0 = TMA producer of the Q tile and the K ring, 10 = TMA producer of the V ring
 //   (3 stages each), 1 = MMA issuer (one elected thread),
 //   2..9 = softmax (thread = query row; TMEM lane quadrant = warp & 3; the two warps of a
-//   quadrant split each tile's 64 keys and the 128 O columns, and agree on the row maximum
-//   through shared memory + one 64-thread named barrier per tile).
-//   tensor-pipe order:  QK_0 QK_1 QK_2 | PV_0 QK_3 | PV_1 QK_4 | ...   QK runs up to three tiles
-//   ahead, so the softmax warps always find S ready and only PV waits for them.  The Q tile is
+//   quadrant split each group's keys and the 128 O columns, and agree on the row maximum through
+//   shared memory + one 64-thread named barrier per step).
+//   tensor-pipe order:  QK_0 .. QK_{n-1} | PV_0 QK_n | PV_1 QK_{n+1} | ...  (indices = tile groups, n = kSBufs)
+//   so the softmax warps always find S ready and only PV waits for them.  The Q tile is
 //   fetched by TMA into (still idle) V-ring memory and moved to TMEM by the softmax warps; the
 //   normalised O leaves through swizzled staging in the (idle) K ring and TMA tensor stores.  Online softmax with a lazily updated exponent reference: the O
 //   accumulator is rescaled in TMEM only when a row's logits outgrow the reference by 2^8.
@@ -37,9 +38,31 @@ constexpr int kAK = 64;         // keys per tile
 constexpr int kDH = 128;        // head dim
 constexpr int kKVStages = 3;
 constexpr int kAttnTcThreads = 352;  // K-TMA, MMA, 8 softmax warps (two per TMEM lane quadrant), V-TMA
-constexpr int kSBufs = 3;           // S/P buffers in TMEM: QK products run up to 3 tiles ahead of PV
 constexpr int kTileBytes = kAK * kDH * 2;          // one plane of a K or V tile: 16 KB
-constexpr uint32_t kColQ = 0, kColS = 128, kColO = 128 + kSBufs * kAK;
+// S/P buffers in TMEM.  A buffer holds a GROUP of kG consecutive key tiles (kG * 64 fp32 columns); the softmax
+// warps work through one group per step, so their per-step fixed latencies (TMEM load, maximum exchange, barrier,
+// TMEM store, mbarrier) are paid once per kG * 64 keys.  Measured on the C2 decoder shape (tools/attn_ab.py, one
+// launch): two 2-tile buffers vs three 1-tile buffers = 0.371 vs 0.458 ms in bf16 mode (bound by the softmax
+// warps), 0.595 vs 0.607 ms in fp32-parity mode (bound by the tensor pipe).
+#ifndef LFS2_ATTN_G1  // tuning knobs (tools/attn_ab.py builds the alternatives): tiles per buffer / buffers, per mode
+#define LFS2_ATTN_G1 2
+#define LFS2_ATTN_BUFS1 2
+#endif
+#ifndef LFS2_ATTN_G3
+#define LFS2_ATTN_G3 2
+#define LFS2_ATTN_BUFS3 2
+#endif
+template <int NPASS>
+struct AttnCfg {
+  static constexpr int kG = NPASS == 1 ? LFS2_ATTN_G1 : LFS2_ATTN_G3;              // key tiles per S/P buffer
+  static constexpr int kSBufs = NPASS == 1 ? LFS2_ATTN_BUFS1 : LFS2_ATTN_BUFS3;    // QK runs up to kSBufs groups ahead of PV
+  static constexpr int kSW = kG * kAK;              // keys (= fp32 columns) per buffer
+  static constexpr int kE = kSW / 2;                // keys per softmax thread and step
+  static constexpr uint32_t kColO = 128 + kSBufs * kSW;
+  static_assert(kColO + kDH <= 512, "tensor memory budget");
+};
+constexpr uint32_t kColQ = 0, kColS = 128;
+constexpr int kMaxSBufs = 3;
 
 // 32 lanes x 32 columns without the trailing wait (caller batches the wait)
 __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, float* v) {
@@ -123,6 +146,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
                     const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
                     const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
                     const AttnTcParams p) {
+  using Cfg = AttnCfg<NPASS>;
+  constexpr int kG = Cfg::kG, kSBufs = Cfg::kSBufs, kSW = Cfg::kSW, kE = Cfg::kE;
+  constexpr uint32_t kColO = Cfg::kColO;
   constexpr int kPlanes = NPASS == 3 ? 2 : 1;
   constexpr int kStageBytes = kPlanes * kTileBytes;  // K (or V) tile, hi [+ lo]
   extern __shared__ uint8_t smem_raw[];
@@ -130,7 +156,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   uint8_t* sK = smem;                                // K ring; reused as the O staging buffer at the end
   uint8_t* sV = smem + kKVStages * kStageBytes;      // V ring; holds the Q tile until it has moved to TMEM
   __shared__ __align__(8) uint64_t k_full[kKVStages], k_empty[kKVStages], v_full[kKVStages], v_empty[kKVStages];
-  __shared__ __align__(8) uint64_t q_smem_full, q_full, s_full[kSBufs], p_full[kSBufs], pv_done[kSBufs], o_final;
+  __shared__ __align__(8) uint64_t q_smem_full, q_full, s_full[kMaxSBufs], p_full[kMaxSBufs], pv_done[kMaxSBufs], o_final;
   __shared__ uint32_t tmem_base_smem;
   __shared__ float xch[2][2][kAQ];  // [tile parity][half][row]: row maxima / partial sums between the warp pair
 
@@ -218,61 +244,77 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       const uint64_t dk0 = make_smem_desc(smem_u32(sK), 16, 512, kSwizzle64);
       const uint64_t dv0 = make_smem_desc(smem_u32(sV), 4096, 512, kSwizzle64);
 
-      auto issue_qk = [&](int j) {
-        const int st = j % kKVStages, sb = j % kSBufs;
-        mbar_wait(&k_full[st], (j / kKVStages) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t ts = tmem_base + kColS + sb * kAK;
-          const uint64_t dkh = desc_advance(dk0, st * kStageBytes), dkl = desc_advance(dkh, kTileBytes);
+      const int npairs = (ntiles + kG - 1) / kG;
+      // S of tile group jp: tiles kG*jp .. kG*jp + kG-1 (those that exist) into the kG parts of S/P buffer jp % kSBufs
+      auto issue_qk = [&](int jp) {
+        const int sb = jp % kSBufs;
 #pragma unroll
-          for (int i = 0; i < kDH / 16; ++i) {
-            const uint32_t off = (i >> 1) * 4096 + (i & 1) * 32;
-            if (i == 0) umma_f16_ts_c<false>(ts, tq, dkh, idesc_qk);
-            else umma_f16_ts_c<true>(ts, tq + i * 8, desc_advance(dkh, off), idesc_qk);
-            if (NPASS == 3) {
-              umma_f16_ts_c<true>(ts, tq + 64 + i * 8, desc_advance(dkh, off), idesc_qk);
-              umma_f16_ts_c<true>(ts, tq + i * 8, desc_advance(dkl, off), idesc_qk);
+        for (int hh = 0; hh < kG; ++hh) {
+          const int j = kG * jp + hh;
+          if (j >= ntiles) break;
+          const int st = j % kKVStages;
+          mbar_wait(&k_full[st], (j / kKVStages) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t ts = tmem_base + kColS + sb * kSW + hh * kAK;
+            const uint64_t dkh = desc_advance(dk0, st * kStageBytes), dkl = desc_advance(dkh, kTileBytes);
+#pragma unroll
+            for (int i = 0; i < kDH / 16; ++i) {
+              const uint32_t off = (i >> 1) * 4096 + (i & 1) * 32;
+              if (i == 0) umma_f16_ts_c<false>(ts, tq, dkh, idesc_qk);
+              else umma_f16_ts_c<true>(ts, tq + i * 8, desc_advance(dkh, off), idesc_qk);
+              if (NPASS == 3) {
+                umma_f16_ts_c<true>(ts, tq + 64 + i * 8, desc_advance(dkh, off), idesc_qk);
+                umma_f16_ts_c<true>(ts, tq + i * 8, desc_advance(dkl, off), idesc_qk);
+              }
             }
+            umma_commit(&k_empty[st]);
+            if (hh == kG - 1 || j + 1 == ntiles) umma_commit(&s_full[sb]);  // the group's last existing tile
           }
-          umma_commit(&k_empty[st]);
-          umma_commit(&s_full[sb]);
+          __syncwarp();
         }
-        __syncwarp();
       };
 
       mbar_wait(&q_full, 0);
       tc_fence_after();
-      for (int j = 0; j < kSBufs && j < ntiles; ++j) issue_qk(j);
-      for (int j = 0; j < ntiles; ++j) {
-        const int st = j % kKVStages, sb = j % kSBufs;
-        mbar_wait(&p_full[sb], (j / kSBufs) & 1);
-        mbar_wait(&v_full[st], (j / kKVStages) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t tp = tmem_base + kColS + sb * kAK;  // P hi: 32 cols, P lo: next 32
-          const uint64_t dvh = desc_advance(dv0, st * kStageBytes), dvl = desc_advance(dvh, kTileBytes);
+      for (int jp = 0; jp < kSBufs && jp < npairs; ++jp) issue_qk(jp);
+      for (int jp = 0; jp < npairs; ++jp) {
+        const int sb = jp % kSBufs;
+        mbar_wait(&p_full[sb], (jp / kSBufs) & 1);
 #pragma unroll
-          for (int i = 0; i < kAK / 16; ++i) {
-            if (i == 0) umma_f16_ts(to, tp, dvh, idesc_pv, j ? 1u : 0u);
-            else umma_f16_ts_c<true>(to, tp + i * 8, desc_advance(dvh, i * 1024), idesc_pv);
-            if (NPASS == 3) {
-              umma_f16_ts_c<true>(to, tp + 32 + i * 8, desc_advance(dvh, i * 1024), idesc_pv);
-              umma_f16_ts_c<true>(to, tp + i * 8, desc_advance(dvl, i * 1024), idesc_pv);
+        for (int hh = 0; hh < kG; ++hh) {
+          const int j = kG * jp + hh;
+          if (j >= ntiles) break;
+          const int st = j % kKVStages;
+          mbar_wait(&v_full[st], (j / kKVStages) & 1);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t tp = tmem_base + kColS + sb * kSW + hh * 32;  // P hi: first kSW/2 cols of the buffer, P lo: the rest
+            const uint64_t dvh = desc_advance(dv0, st * kStageBytes), dvl = desc_advance(dvh, kTileBytes);
+#pragma unroll
+            for (int i = 0; i < kAK / 16; ++i) {
+              if (i == 0) umma_f16_ts(to, tp, dvh, idesc_pv, j ? 1u : 0u);
+              else umma_f16_ts_c<true>(to, tp + i * 8, desc_advance(dvh, i * 1024), idesc_pv);
+              if (NPASS == 3) {
+                umma_f16_ts_c<true>(to, tp + kSW / 2 + i * 8, desc_advance(dvh, i * 1024), idesc_pv);
+                umma_f16_ts_c<true>(to, tp + i * 8, desc_advance(dvl, i * 1024), idesc_pv);
+              }
+            }
+            umma_commit(&v_empty[st]);
+            if (hh == kG - 1 || j + 1 == ntiles) {
+              umma_commit(&pv_done[sb]);
+              if (j + 1 == ntiles) umma_commit(&o_final);  // every product of this CTA has landed
             }
           }
-          umma_commit(&v_empty[st]);
-          umma_commit(&pv_done[sb]);
-          if (j + 1 == ntiles) umma_commit(&o_final);  // every product of this CTA has landed
+          __syncwarp();
         }
-        __syncwarp();
-        if (j + kSBufs < ntiles) issue_qk(j + kSBufs);
+        if (jp + kSBufs < npairs) issue_qk(jp + kSBufs);
       }
     }
   } else {
     // ===================== softmax warps 2..9: thread = query row =====================
     const int quad = warp & 3;
-    const int half = (warp - 2) >> 2;  // which 32 of the tile's 64 keys / which 64 of the 128 O columns
+    const int half = (warp - 2) >> 2;  // which tile of the pair (64 of its 128 keys) / which 64 of the 128 O columns
     const int r = quad * 32 + lane;
     const int tq_row = q0 + r;
     const bool row_ok = tq_row < p.t;
@@ -305,50 +347,67 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     float l_run = 0.f;        // partial row sum over this half's keys
     const float c = p.scale_log2e;
     const uint8_t* mrow = p.kpm ? p.kpm + (size_t)b * p.t : nullptr;
-    // "key is masked" byte of this lane's key in the NEXT tile, prefetched one tile ahead and only TESTED at
-    // the top of the next iteration, so the load's latency hides behind a whole tile of work
-    auto key_masked = [&](int j) -> uint32_t {
-      const int k1 = j * kAK + half * 32 + lane;
+    // "key is masked" bytes of this lane's keys in the NEXT tile group, prefetched one step ahead and only
+    // TESTED at the top of the next iteration, so the loads' latency hides behind a whole step of work.
+    // This warp's keys of group jp: jp*kSW + half*kE + [0,kE); keys of a tile past the last one (bf16 mode, odd
+    // tile count) are all "masked": their S columns were never written and their P must be 0.
+    const int npairs = (ntiles + kG - 1) / kG;
+    auto key_masked = [&](int jp, int sub) -> uint32_t {
+      const int k0 = jp * kSW + half * kE;
+      const int k1 = k0 + sub * 32 + lane;
       uint32_t v = 1u;
-      if (k1 < p.t) v = mrow ? (uint32_t)mrow[k1] : 0u;
+      if (k1 < p.t && k0 / kAK < ntiles) v = mrow ? (uint32_t)mrow[k1] : 0u;
       return v;
     };
-    uint32_t next_masked = ntiles > 0 ? key_masked(0) : 1u;
+    uint32_t next_m0 = npairs > 0 ? key_masked(0, 0) : 1u;
+    uint32_t next_m1 = (kE > 32 && npairs > 0) ? key_masked(0, 1) : 0u;
 
-    for (int j = 0; j < ntiles; ++j) {
-      const int sb = j % kSBufs;
-      const uint32_t mbits = __ballot_sync(0xffffffffu, next_masked != 0u);
-      if (j + 1 < ntiles) next_masked = key_masked(j + 1);
-      mbar_wait(&s_full[sb], (j / kSBufs) & 1);
-      tc_fence_after();
-      const uint32_t ts = tmem_base + kColS + sb * kAK + lane_off;
-      float s[32];
-      tmem_ld32(ts + half * 32, s);
-      if (mbits) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          if ((mbits >> i) & 1u) s[i] = -INFINITY;
+    for (int jp = 0; jp < npairs; ++jp) {
+      const int sb = jp % kSBufs;
+      const uint32_t mbits0 = __ballot_sync(0xffffffffu, next_m0 != 0u);
+      const uint32_t mbits1 = kE > 32 ? __ballot_sync(0xffffffffu, next_m1 != 0u) : 0u;
+      if (jp + 1 < npairs) {
+        next_m0 = key_masked(jp + 1, 0);
+        if (kE > 32) next_m1 = key_masked(jp + 1, 1);
       }
-      float tmax = s[0];
+      mbar_wait(&s_full[sb], (jp / kSBufs) & 1);
+      tc_fence_after();
+      const uint32_t ts = tmem_base + kColS + sb * kSW + lane_off;
+      float s[kE];
+      tmem_ld32_nowait(ts + half * kE, s);
+      if (kE > 32) tmem_ld32_nowait(ts + half * kE + 32, s + (kE > 32 ? 32 : 0));
+      tmem_wait_ld();
+      if (mbits0 | mbits1) {
 #pragma unroll
-      for (int i = 1; i < 32; ++i) tmax = fmaxf(tmax, s[i]);
-      // row maximum over all 64 keys: exchange with the partner warp (parity double buffer); the
+        for (int i = 0; i < 32; ++i) {
+          if ((mbits0 >> i) & 1u) s[i] = -INFINITY;
+          if (kE > 32 && ((mbits1 >> i) & 1u)) s[(kE > 32 ? 32 : 0) + i] = -INFINITY;
+        }
+      }
+      float tmax0 = s[0], tmax1 = s[1];
+#pragma unroll
+      for (int i = 2; i < kE; i += 2) {
+        tmax0 = fmaxf(tmax0, s[i]);
+        tmax1 = fmaxf(tmax1, s[i + 1]);
+      }
+      float tmax = fmaxf(tmax0, tmax1);
+      // row maximum over all 128 keys: exchange with the partner warp (parity double buffer); the
       // barrier also orders "both halves have read S" before either overwrites it with P
-      xch[j & 1][half][r] = tmax;
+      xch[jp & 1][half][r] = tmax;
       pair_bar_sync(quad);
-      tmax = fmaxf(tmax, xch[j & 1][half ^ 1][r]);
+      tmax = fmaxf(tmax, xch[jp & 1][half ^ 1][r]);
       // Lazy rescale: m_run is the exponent reference, not necessarily the true running maximum.
       // It is only moved (and O, l rescaled) when some row's logits exceed it by more than 2^8
       // in the exp2 domain, so p <= 256 always and the O accumulator is almost never touched;
       // softmax is shift-invariant, so the result is exact either way.  Both halves see the same
       // tmax and m_run, hence take the same (warp-uniform) branch.
-      const bool grow = (j > 0) && ((tmax - m_run) * c > 8.f);  // (x - -inf) = inf: first finite tile moves it
-      if (j == 0) {
+      const bool grow = (jp > 0) && ((tmax - m_run) * c > 8.f);  // (x - -inf) = inf: first finite tile moves it
+      if (jp == 0) {
         m_run = tmax;
       } else if (__any_sync(0xffffffffu, grow)) {
         const float m_new = fmaxf(m_run, tmax);
-        // every PV product up to tile j-1 must have landed in O (PV_j cannot start before our P_j)
-        mbar_wait(&pv_done[(j - 1) % kSBufs], ((j - 1) / kSBufs) & 1);
+        // every PV product up to pair jp-1 must have landed in O (PV_jp cannot start before our P_jp)
+        mbar_wait(&pv_done[(jp - 1) % kSBufs], ((jp - 1) / kSBufs) & 1);
         tc_fence_after();
         const float alpha = (m_new == -INFINITY) ? 1.f : ex2_approx((m_run - m_new) * c);
         l_run *= alpha;
@@ -364,18 +423,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         m_run = m_new;
       }
       const float mc = (m_run == -INFINITY) ? 0.f : m_run * c;
-      uint32_t ph[16], pl[16];
-      float lsum = 0.f;
+      uint32_t ph[kE / 2], pl[kE / 2];
+      float lsum0 = 0.f, lsum1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
+      for (int i = 0; i < kE / 2; ++i) {
         float p0 = ex2_approx(fmaf(s[2 * i], c, -mc));
         float p1 = ex2_approx(fmaf(s[2 * i + 1], c, -mc));
-        lsum += p0 + p1;
+        lsum0 += p0;
+        lsum1 += p1;
         split_pack2(p0, p1, ph[i], pl[i]);
       }
-      l_run += lsum;
-      tmem_st16_u(ts + half * 16, ph);                       // P hi: cols [0,32) of the S buffer
-      if (NPASS == 3) tmem_st16_u(ts + 32 + half * 16, pl);  // P lo: cols [32,64)
+      l_run += lsum0 + lsum1;
+      // P hi: first kSW/2 columns of the S buffer (bf16 pairs in key order), P lo: the other kSW/2
+      if (kE > 32) {
+        tmem_st32_u(ts + half * (kE / 2), ph);
+        if (NPASS == 3) tmem_st32_u(ts + kSW / 2 + half * (kE / 2), pl);
+      } else {
+        tmem_st16_u(ts + half * (kE / 2), ph);
+        if (NPASS == 3) tmem_st16_u(ts + kSW / 2 + half * (kE / 2), pl);
+      }
       tmem_wait_st();
       tc_fence_before();
       __syncwarp();
@@ -383,9 +449,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     }
 
     // ---- epilogue: O / l (this half's 64 columns) -> ctx ----
-    xch[ntiles & 1][half][r] = l_run;
+    xch[npairs & 1][half][r] = l_run;
     pair_bar_sync(quad);
-    l_run += xch[ntiles & 1][half ^ 1][r];
+    l_run += xch[npairs & 1][half ^ 1][r];
     if (ntiles > 0) {
       mbar_wait(&o_final, 0);
       tc_fence_after();
