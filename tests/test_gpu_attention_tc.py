@@ -86,3 +86,20 @@ def test_unsupported_head_dim_raises():
     qkv, _ = make(1, 32, 192, seed=8)
     with pytest.raises(NotImplementedError):
         ops.attention_tc(ops.split_bf16(qkv.to(DEV)), None, 2)
+
+
+@pytest.mark.parametrize("npass", [3, 1])
+def test_query_row_limit_skips_tiles_and_keeps_the_rest(npass):
+    """lfs2_attention_tc_limited: query tiles starting at or after len + extra are not computed, all others are
+    bit-identical to the unlimited launch"""
+    b, t, d, nhead, extra = 3, 700, 256, 2, 28
+    lens = [700, 100, 333]
+    qkv, kpm = make(b, t, d, seed=11, lens=lens)
+    planes = ops.split_bf16(qkv.to(DEV))
+    full, _ = ops.attention_tc(planes, kpm.to(DEV), nhead, npass=npass, want_f32=True)
+    lim = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    part, pp = ops.attention_tc(planes, kpm.to(DEV), nhead, npass=npass, want_f32=True, row_limit=(lim, extra))
+    for i, n in enumerate(lens):
+        keep = min(t, (n + extra + 127) // 128 * 128)
+        assert torch.equal(part[i, :keep], full[i, :keep]), i
+        assert torch.equal(pp.hi[i, :keep], part[i, :keep].bfloat16())

@@ -138,3 +138,28 @@ def test_ffn_fused_tc(m, f, npass, tol):
     err = (out.float().cpu().double() - ref).abs().max().item()
     print(f"ffn_fused m={m} f={f} npass={npass}: max err {err:.3e}")
     assert err < tol, err
+
+
+@pytest.mark.parametrize("bsz,t,lens,extra", [(3, 300, [300, 1, 130], 0), (4, 257, [0, 128, 100, 257], 28), (2, 90, [40, 90], 5)])
+def test_ffn_fused_tc_row_limit_keeps_needed_tiles(bsz, t, lens, extra):
+    """row-limited launch: every row t_row < roundup128(len + extra) of every utterance must equal the full launch bit
+    for bit (tiles are 128 flattened rows, so a kept tile may also carry rows of the neighbours: those are unspecified)"""
+    from lightningfastspeech2_b200 import ops
+
+    g = torch.Generator().manual_seed(bsz * t)
+    d, f, dev = 256, 1024, "cuda"
+    sp = lambda x: ops.split_bf16(x.to(dev).contiguous())
+    u, res = sp(torch.randn(bsz, t, d, generator=g)), sp(torch.randn(bsz, t, d, generator=g))
+    w1, w2 = sp(torch.randn(f, d, generator=g) / 16), sp(torch.randn(d, f, generator=g) / 32)
+    b1, b2 = torch.randn(f, generator=g).to(dev) * 0.1, torch.randn(d, generator=g).to(dev) * 0.1
+    gam, bet = torch.ones(d, device=dev), torch.zeros(d, device=dev)
+    full = ops.ffn_fused_tc(u, w1, b1, w2, b2, res, gam, bet)
+    lim = torch.tensor(lens, dtype=torch.int32, device=dev)
+    cache = {}
+    part = ops.ffn_fused_tc(u, w1, b1, w2, b2, res, gam, bet, row_limit=(lim, extra, cache))
+    again = ops.ffn_fused_tc(u, w1, b1, w2, b2, res, gam, bet, row_limit=(lim, extra, cache))  # reuses the tile list
+    assert ("ffn", bsz, t) in cache
+    for b, n in enumerate(lens):
+        keep = min(t, (n + extra + 127) // 128 * 128)
+        for o in (part, again):
+            assert torch.equal(o.hi[b, :keep], full.hi[b, :keep]) and torch.equal(o.lo[b, :keep], full.lo[b, :keep]), b
