@@ -21,6 +21,8 @@
 //   one TMEM pass, normalisation in a second), then 32-column chunks are written to a
 //   swizzled shared-memory staging buffer and leave as coalesced TMA tensor stores -- either
 //   fp32 or bf16 hi/lo planes for the next GEMM.  TMA clips rows/columns outside the tensor.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace lfs2 {
@@ -44,15 +46,6 @@ struct GemmTcParams {
   const int* tile_list;         // null, or [0] = number of active m-tiles, [1..] = their indices (b * m_tiles_per_batch + mt):
                                 //   only those row tiles are processed (lfs2_gemm_tc_limited), dealt round-robin to the CTAs
 };
-
-// work item i of this launch -> (m_tile, n_tile); the number of work items is tile_count(p)
-__device__ __forceinline__ int tile_count(const GemmTcParams& p) {
-  return p.tile_list ? __ldg(p.tile_list) * p.n_tiles : p.total_tiles;
-}
-__device__ __forceinline__ void tile_coords(const GemmTcParams& p, int i, int& m_tile, int& n_tile) {
-  n_tile = i % p.n_tiles;
-  m_tile = p.tile_list ? __ldg(p.tile_list + 1 + i / p.n_tiles) : i / p.n_tiles;
-}
 
 // active m-tiles of a row-limited launch: utterance b needs the tiles that start before row_limit[b] + extra
 __global__ void gemm_tile_list_kernel(const int* __restrict__ row_limit, int extra, int batch, int m_tiles_per_batch,
@@ -95,7 +88,65 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int N_TILE, int NPASS, bool LN, bool OUT_F32>
+// ---- 2-CTA cluster variant (MC): the two CTAs of a cluster work on two row tiles of the SAME column tile, each
+// fetches half of every weight slab and multicasts it into both CTAs' shared memory.  A K = 256 GEMM re-reads its
+// whole weight tile for every 128-row tile (262 KB of the 521 KB a tile moves L2 -> SM in fp32 mode), which is what
+// bounds these kernels; sharing the slab halves that part.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
+// work items of one CTA: item i -> (utterance b, first row t0, first column n0)
+template <bool MC>
+struct TileWalk {
+  int first, stride, count, rank, m_count;
+  __device__ __forceinline__ explicit TileWalk(const GemmTcParams& p) {
+    rank = MC ? (int)cluster_ctarank() : 0;
+    m_count = p.tile_list ? __ldg(p.tile_list) : p.batch * p.m_tiles_per_batch;
+    if (MC) {  // a cluster takes a PAIR of row tiles of one column tile; an odd tail pairs with an out-of-range tile
+      first = blockIdx.x >> 1;
+      stride = gridDim.x >> 1;
+      count = ((m_count + 1) >> 1) * p.n_tiles;
+    } else {
+      first = blockIdx.x;
+      stride = gridDim.x;
+      count = m_count * p.n_tiles;
+    }
+  }
+  __device__ __forceinline__ void coords(const GemmTcParams& p, int i, int n_tile_cols, int& b, int& t0, int& n0) const {
+    n0 = (i % p.n_tiles) * n_tile_cols;
+    const int mi = MC ? 2 * (i / p.n_tiles) + rank : i / p.n_tiles;
+    if (mi < m_count) {
+      const int m_tile = p.tile_list ? __ldg(p.tile_list + 1 + mi) : mi;
+      b = m_tile / p.m_tiles_per_batch;
+      t0 = (m_tile % p.m_tiles_per_batch) * kBM;
+    } else {  // no such tile: TMA zero-fills loads and drops stores outside the tensor
+      b = p.batch;
+      t0 = 0;
+    }
+  }
+};
+
+template <int N_TILE, int NPASS, bool LN, bool OUT_F32, bool MC>
 __global__ void __launch_bounds__(kGemmTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -124,7 +175,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     prefetch_tmap(&map_o0);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC ? 2 : 1);  // MC: a slot is free when BOTH CTAs' MMAs have read it (the peer writes into it too)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
@@ -143,20 +194,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into this CTA
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  const TileWalk<MC> walk(p);
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const int ntiles = tile_count(p);
-      for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int n_tile, m_tile;
-        tile_coords(p, tile, m_tile, n_tile);
-        int b = m_tile / p.m_tiles_per_batch, t0 = (m_tile % p.m_tiles_per_batch) * kBM;
-        int n0 = n_tile * N_TILE;
+      // MC: the weight maps have half-height boxes; this CTA fetches rows [rank * N_TILE/2, +N_TILE/2) of a slab
+      // and multicasts them to the same place in both CTAs (each full barrier still sees a whole slab's bytes)
+      const int w_row = MC ? walk.rank * (N_TILE / 2) : 0;
+      const int w_off = MC ? walk.rank * (L::kWPlane / 2) : 0;
+      auto load_w = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+        if (MC) tma_load_3d_mc(dst + w_off, map, bar, c0, c1 + w_row, 0, (uint16_t)3);
+        else tma_load_3d(dst, map, bar, c0, c1, 0);
+      };
+      for (int tile = walk.first; tile < walk.count; tile += walk.stride) {
+        int b, t0, n0;
+        walk.coords(p, tile, N_TILE, b, t0, n0);
         for (int ks = 0; ks < k_slabs; ++ks) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * L::kStage;
@@ -164,17 +222,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             int tap = ks / (p.d / kBK), c0 = (ks % (p.d / kBK)) * kBK;
             mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 2 : 1) * (L::kAPlane + L::kWPlane));
             tma_load_3d(st, &map_a_hi, &full_bar[stage], c0, t0 + tap - p.half, b);
-            tma_load_3d(st + L::kOffWHi, &map_w_hi, &full_bar[stage], tap * p.d + c0, n0, 0);
+            load_w(st + L::kOffWHi, &map_w_hi, &full_bar[stage], tap * p.d + c0, n0);
             if (NPASS == 3) {
               tma_load_3d(st + L::kOffALo, &map_a_lo, &full_bar[stage], c0, t0 + tap - p.half, b);
-              tma_load_3d(st + L::kOffWLo, &map_w_lo, &full_bar[stage], tap * p.d + c0, n0, 0);
+              load_w(st + L::kOffWLo, &map_w_lo, &full_bar[stage], tap * p.d + c0, n0);
             }
           } else if (L::kHasLo) {  // residual slab: R_hi, R_lo against the identity block
             int c0 = n0 + (ks - a_slabs) * kBK;
             mbar_expect_tx(&full_bar[stage], 2 * L::kAPlane + L::kWPlane);
             tma_load_3d(st, &map_r_hi, &full_bar[stage], c0, t0, b);
             tma_load_3d(st + L::kOffALo, &map_r_lo, &full_bar[stage], c0, t0, b);
-            tma_load_3d(st + L::kOffWHi, &map_ident, &full_bar[stage], c0, n0, 0);
+            load_w(st + L::kOffWHi, &map_ident, &full_bar[stage], c0, n0);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -192,8 +250,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    const int ntiles = tile_count(p);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
+    for (int tile = walk.first; tile < walk.count; tile += walk.stride, ++it) {
       int acc = it & 1;
       uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
@@ -220,7 +277,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             umma_f16_c<true>(d_tmem, a_hi, w_lo, idesc);
             umma_f16_c<true>(d_tmem, desc_advance(a_hi, 32), desc_advance(w_lo, 32), idesc);
           }
-          umma_commit(&empty_bar[stage]);                        // smem slot reusable once these MMAs retire
+          if (MC) umma_commit_mc(&empty_bar[stage], (uint16_t)3);  // ... in both CTAs: either producer may refill it
+          else umma_commit(&empty_bar[stage]);                   // smem slot reusable once these MMAs retire
           if (ks + 1 == k_slabs) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
         }
         __syncwarp();
@@ -246,12 +304,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int c_begin = half * kHalfChunks, c_end = c_begin + kHalfChunks;
     int it = 0;
     uint32_t chunk_ctr = 0;
-    const int ntiles = tile_count(p);
-    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, ++it) {
-      int n_tile, m_tile;
-      tile_coords(p, tile, m_tile, n_tile);
-      int b = m_tile / p.m_tiles_per_batch, t0 = (m_tile % p.m_tiles_per_batch) * kBM;
-      int n0 = n_tile * N_TILE;
+    for (int tile = walk.first; tile < walk.count; tile += walk.stride, ++it) {
+      int b, t0, n0;
+      walk.coords(p, tile, N_TILE, b, t0, n0);
       int acc = it & 1;
       uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_phase);
@@ -345,6 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer may still arrive on this CTA's barriers until it has finished too
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -390,10 +446,10 @@ struct GemmTcMaps {
   CUtensorMap ah, al, wh, wl, rh, rl, ident, o0, o1;
 };
 
-template <int N_TILE, int NPASS, bool LN, bool OUT_F32>
+template <int N_TILE, int NPASS, bool LN, bool OUT_F32, bool MC>
 static int launch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, cudaStream_t s) {
   using L = SmemLayout<N_TILE, NPASS, LN>;
-  auto kern = gemm_tc_kernel<N_TILE, NPASS, LN, OUT_F32>;
+  auto kern = gemm_tc_kernel<N_TILE, NPASS, LN, OUT_F32, MC>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
@@ -403,16 +459,46 @@ static int launch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, cudaStream
     configured = true;
   }
   int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  kern<<<grid, kGemmTcThreads, L::kTotal, s>>>(m.ah, m.al, m.wh, m.wl, m.rh, m.rl, m.ident, m.o0, m.o1, p);
+  if (!MC) {
+    kern<<<grid, kGemmTcThreads, L::kTotal, s>>>(m.ah, m.al, m.wh, m.wl, m.rh, m.rl, m.ident, m.o0, m.o1, p);
+  } else {  // clusters of two CTAs (one per SM): pairs of row tiles share the multicast weight slabs
+    grid &= ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmTcThreads);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, m.ah, m.al, m.wh, m.wl, m.rh, m.rl, m.ident, m.o0, m.o1, p) != cudaSuccess) {
+      set_error("gemm_tc: cluster launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return LFS2_ERR_CUDA;
+    }
+  }
   LFS2_CHECK_LAUNCH("gemm_tc");
   return LFS2_OK;
 }
 
-template <int N_TILE, bool LN>
+template <int N_TILE, bool LN, bool MC>
 static int dispatch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, int npass, bool out_f32, cudaStream_t s) {
   if (npass == 3)
-    return out_f32 ? launch_gemm_tc<N_TILE, 3, LN, true>(m, p, s) : launch_gemm_tc<N_TILE, 3, LN, false>(m, p, s);
-  return out_f32 ? launch_gemm_tc<N_TILE, 1, LN, true>(m, p, s) : launch_gemm_tc<N_TILE, 1, LN, false>(m, p, s);
+    return out_f32 ? launch_gemm_tc<N_TILE, 3, LN, true, MC>(m, p, s) : launch_gemm_tc<N_TILE, 3, LN, false, MC>(m, p, s);
+  return out_f32 ? launch_gemm_tc<N_TILE, 1, LN, true, MC>(m, p, s) : launch_gemm_tc<N_TILE, 1, LN, false, MC>(m, p, s);
+}
+
+// LFS2_GEMM_MULTICAST=0 switches the 2-CTA weight multicast off (A/B measurements)
+static bool gemm_multicast_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("LFS2_GEMM_MULTICAST");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
 }
 
 }  // namespace tc
@@ -463,18 +549,23 @@ int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch, int t, i
   int n_tile = ln ? n : (n % 256 == 0 ? 256 : 128);
   if (ln) LFS2_REQUIRE(n == 256, LFS2_ERR_UNSUPPORTED, "gemm_tc: LayerNorm epilogue needs n == 256 (got %d)", n);
 
+  // 2-CTA multicast variant: full 256-column tiles, at least one pair of row tiles per cluster
+  const int m_tiles_all = batch * ((t + kBM - 1) / kBM);
+  const bool mc = n_tile == 256 && n % 256 == 0 && m_tiles_all >= 2 * kNumSMs && gemm_multicast_enabled();
+  const uint32_t w_box = mc ? n_tile / 2 : n_tile;  // MC: each CTA of a pair fetches half a weight slab
+
   GemmTcMaps m;
   const uint64_t ktot = (uint64_t)taps * d;
-  bool ok = make_tmap_3d(&m.ah, a_hi, d, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.wh, w_hi, ktot, n, 1, kBK, n_tile, 64);
+  bool ok = make_tmap_3d(&m.ah, a_hi, d, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.wh, w_hi, ktot, n, 1, kBK, w_box, 64);
   if (npass == 3)
-    ok = ok && make_tmap_3d(&m.al, a_lo, d, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.wl, w_lo, ktot, n, 1, kBK, n_tile, 64);
+    ok = ok && make_tmap_3d(&m.al, a_lo, d, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.wl, w_lo, ktot, n, 1, kBK, w_box, 64);
   else {
     m.al = m.ah;
     m.wl = m.wh;
   }
   if (res_hi)
     ok = ok && make_tmap_3d(&m.rh, res_hi, n, t, batch, kBK, kBM, 64) &&
-         make_tmap_3d(&m.rl, res_lo, n, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.ident, ident_hi, n, n, 1, kBK, n_tile, 64);
+         make_tmap_3d(&m.rl, res_lo, n, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.ident, ident_hi, n, n, 1, kBK, w_box, 64);
   else {
     m.rh = m.ah;
     m.rl = m.ah;
@@ -512,9 +603,13 @@ int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch, int t, i
     LFS2_CHECK_LAUNCH("gemm_tile_list");
     p.tile_list = list;
   }
-  if (ln) return dispatch_gemm_tc<256, true>(m, p, npass, out_f32 != nullptr, s);
-  if (n_tile == 256) return dispatch_gemm_tc<256, false>(m, p, npass, out_f32 != nullptr, s);
-  return dispatch_gemm_tc<128, false>(m, p, npass, out_f32 != nullptr, s);
+  if (mc) {
+    if (ln) return dispatch_gemm_tc<256, true, true>(m, p, npass, out_f32 != nullptr, s);
+    return dispatch_gemm_tc<256, false, true>(m, p, npass, out_f32 != nullptr, s);
+  }
+  if (ln) return dispatch_gemm_tc<256, true, false>(m, p, npass, out_f32 != nullptr, s);
+  if (n_tile == 256) return dispatch_gemm_tc<256, false, false>(m, p, npass, out_f32 != nullptr, s);
+  return dispatch_gemm_tc<128, false, false>(m, p, npass, out_f32 != nullptr, s);
 }
 
 // x (n) fp32 -> hi/lo bf16 planes

@@ -163,3 +163,33 @@ def test_ffn_fused_tc_row_limit_keeps_needed_tiles(bsz, t, lens, extra):
         keep = min(t, (n + extra + 127) // 128 * 128)
         for o in (part, again):
             assert torch.equal(o.hi[b, :keep], full.hi[b, :keep]) and torch.equal(o.lo[b, :keep], full.lo[b, :keep]), b
+
+
+@pytest.mark.parametrize("npass", [3, 1])
+def test_two_cta_multicast_path(npass):
+    """launches with >= 296 row tiles and 256-column tiles run as 2-CTA clusters that multicast the weight slabs:
+    odd tile counts (the tail pairs with an out-of-range tile), several column tiles, LayerNorm + residual, row limits"""
+    tol = 2e-4 if npass == 3 else 3e-2
+    m = 305 * 128 - 77  # 305 row tiles: odd
+    a, w, b = rnd(m, 256, seed=21), rnd(768, 256, seed=22, scale=1 / 16), rnd(768, seed=23, scale=0.1)
+    ap, wp = ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV))
+    out = ops.gemm_tc(ap, wp, b.to(DEV), npass=npass)
+    ref = F.linear(a.double(), w.double(), b.double())
+    assert (out.cpu() - ref).abs().max() < tol
+    # LayerNorm epilogue with the residual on the tensor core
+    n = 256
+    w2, b2, r = rnd(n, 256, seed=24, scale=1 / 16), rnd(n, seed=25, scale=0.1), rnd(m, n, seed=26)
+    g, bt = 1 + rnd(n, seed=27, scale=0.1), rnd(n, seed=28, scale=0.1)
+    ref = F.layer_norm(F.linear(a.double(), w2.double(), b2.double()) + r.double(), (n,), g.double(), bt.double(), 1e-5)
+    out = ops.gemm_tc(ap, ops.split_bf16(w2.to(DEV)), b2.to(DEV), residual=ops.split_bf16(r.to(DEV)), gamma=g.to(DEV),
+                      beta=bt.to(DEV), npass=npass, out="planes")
+    assert (out.float().cpu() - ref).abs().max() < (2e-4 if npass == 3 else 3e-2)
+    # row-limited launch over (B, T, d): kept rows equal the unlimited launch bit for bit
+    bsz, t = 64, 700
+    x = ops.split_bf16(rnd(bsz, t, 256, seed=29).to(DEV))
+    lens = torch.randint(1, t + 1, (bsz,), generator=torch.Generator().manual_seed(3)).to(torch.int32)
+    full = ops.gemm_tc(x, wp, b.to(DEV), npass=npass, out="planes")
+    part = ops.gemm_tc(x, wp, b.to(DEV), npass=npass, out="planes", row_limit=(lens.to(DEV), 28, {}))
+    for i, ln_ in enumerate(lens.tolist()):
+        keep = min(t, (ln_ + 28 + 127) // 128 * 128)
+        assert torch.equal(part.hi[i, :keep], full.hi[i, :keep]) and torch.equal(part.lo[i, :keep], full.lo[i, :keep]), i
