@@ -302,6 +302,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     uint8_t* staging = smem + L::kOffStaging + half * 2 * kStageChunk;
     constexpr int kHalfChunks = kChunks / 2;
     const int c_begin = half * kHalfChunks, c_end = c_begin + kHalfChunks;
+    const bool bias_vec = p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0;
     int it = 0;
     uint32_t chunk_ctr = 0;
     for (int tile = walk.first; tile < walk.count; tile += walk.stride, ++it) {
@@ -349,6 +350,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             float x = v[j] + vec[c * 32 + j];
             if (p.relu) x = fmaxf(x, 0.f);
             v[j] = (x - mean) * rstd * vec[N_TILE + c * 32 + j] + vec[2 * N_TILE + c * 32 + j];
+          }
+        } else if (bias_vec && col0 + 32 <= p.n) {
+          // the chunk's 32 bias values as 8 broadcast 16-byte loads (a per-element load + bounds test was 36 % of
+          // this kernel's instructions)
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = __ldg(b4 + j);
+            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
           }
         } else {
 #pragma unroll
