@@ -220,10 +220,18 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           uint8_t* st = smem + stage * L::kStage;
           if (ks < a_slabs) {
             int tap = ks / (p.d / kBK), c0 = (ks % (p.d / kBK)) * kBK;
+#ifdef LFS2_DIAG_NO_LO_LOADS  // timing diagnostics only (tools/gemm_ab.py): wrong results
+            mbar_expect_tx(&full_bar[stage], L::kAPlane + L::kWPlane);
+#else
             mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 2 : 1) * (L::kAPlane + L::kWPlane));
+#endif
             tma_load_3d(st, &map_a_hi, &full_bar[stage], c0, t0 + tap - p.half, b);
             load_w(st + L::kOffWHi, &map_w_hi, &full_bar[stage], tap * p.d + c0, n0);
+#ifdef LFS2_DIAG_NO_LO_LOADS
+            if (false) {
+#else
             if (NPASS == 3) {
+#endif
               tma_load_3d(st + L::kOffALo, &map_a_lo, &full_bar[stage], c0, t0 + tap - p.half, b);
               load_w(st + L::kOffWLo, &map_w_lo, &full_bar[stage], tap * p.d + c0, n0);
             }
@@ -269,11 +277,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           if (ks == 0) umma_f16_c<false>(d_tmem, a_hi, w_hi, idesc);
           else umma_f16_c<true>(d_tmem, a_hi, w_hi, idesc);
           umma_f16_c<true>(d_tmem, desc_advance(a_hi, 32), desc_advance(w_hi, 32), idesc);
+#ifdef LFS2_DIAG_NO_LO_MMAS
+          if (false) {
+#else
           if (L::kHasLo && (NPASS == 3 || res)) {
+#endif
             umma_f16_c<true>(d_tmem, a_lo, w_hi, idesc);
             umma_f16_c<true>(d_tmem, desc_advance(a_lo, 32), desc_advance(w_hi, 32), idesc);
           }
+#ifdef LFS2_DIAG_NO_LO_MMAS
+          if (false) {
+#else
           if (NPASS == 3 && !res) {
+#endif
             umma_f16_c<true>(d_tmem, a_hi, w_lo, idesc);
             umma_f16_c<true>(d_tmem, desc_advance(a_hi, 32), desc_advance(w_lo, 32), idesc);
           }
@@ -397,13 +413,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         fence_proxy_async_smem();
         // the store of the previous chunk (other buffer) must have finished READING before the
         // threads that pass this barrier start overwriting that buffer for the next chunk
+        // (letting it stay in flight one chunk longer -- wait_group.read 1 + a second barrier -- measured no gain)
         if (issuer) tma_store_wait_read0();
         named_bar_sync(1 + half, 128);
+#ifndef LFS2_DIAG_NO_STORES
         if (issuer) {
           tma_store_3d(&map_o0, sb, col0, t0, b);
           if (!OUT_F32) tma_store_3d(&map_o1, sb + kStageChunk / 2, col0, t0, b);
           tma_store_commit();
         }
+#endif
       }
       tc_fence_before();
       __syncwarp();
