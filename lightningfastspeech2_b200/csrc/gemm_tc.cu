@@ -580,6 +580,14 @@ int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch, int t, i
                "gemm_tc: the residual (hi, lo planes + identity) is only fused with LayerNorm");
   LFS2_REQUIRE(!res_hi || !relu, LFS2_ERR_UNSUPPORTED, "gemm_tc: relu with a residual is not a reference pattern");
   int n_tile = ln ? n : (n % 256 == 0 ? 256 : 128);
+  {  // LFS2_GEMM_NTILE=128: A/B knob (tools/gemm_ab.py) -- narrower column tiles for the plain epilogue
+    static int forced = -1;
+    if (forced < 0) {
+      const char* e = getenv("LFS2_GEMM_NTILE");
+      forced = e ? atoi(e) : 0;
+    }
+    if (!ln && forced == 128) n_tile = 128;
+  }
   if (ln) LFS2_REQUIRE(n == 256, LFS2_ERR_UNSUPPORTED, "gemm_tc: LayerNorm epilogue needs n == 256 (got %d)", n);
 
   // 2-CTA multicast variant: full 256-column tiles, at least one pair of row tiles per cluster

@@ -37,7 +37,8 @@ def one(name):
     sys.path.insert(0, ROOT)
     import torch
     from lightningfastspeech2_b200 import _lib
-    _lib.LIB_PATH = os.path.join(AB, f"liblfs2_{name}.so")
+    if name != "shipped":
+        _lib.LIB_PATH = os.path.join(AB, f"liblfs2_{name}.so")
     from lightningfastspeech2_b200 import ops
     g = torch.Generator().manual_seed(0)
     x = ops.split_bf16(torch.randn(64, 2635, 256, generator=g).cuda())
@@ -65,5 +66,10 @@ if __name__ == "__main__":
     elif sys.argv[1] == "run":
         for name in VARIANTS:
             subprocess.run([sys.executable, os.path.abspath(__file__), "one", name], check=True)
+    elif sys.argv[1] == "knobs":  # the shipped library under its environment knobs
+        for env in ({}, {"LFS2_GEMM_MULTICAST": "0"}, {"LFS2_GEMM_NTILE": "128"}):
+            print(env or "defaults", flush=True)
+            subprocess.run([sys.executable, os.path.abspath(__file__), "one", "shipped"], check=True,
+                           env=dict(os.environ, **env))
     else:
         one(sys.argv[2])
