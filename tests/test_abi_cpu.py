@@ -110,3 +110,43 @@ def test_noam_and_optimizer_recipe():
         from lightningfastspeech2_b200.fastspeech2.noam import noam_scale
 
         assert noam_scale(step, 4000) == pytest.approx(O.noam_scale(step, 4000))
+
+
+def test_pad_row_skipping_host_logic():
+    """model.skip_pad_rows: the halo the row limits are built from, and which configurations may use them"""
+    m = _mk("C2").eval()
+    # encoder FFN kernels 5,25,13,9 (+ duration predictor: 2 layers of k=3); decoder 17,21,9,13; predictors 5 x k=3
+    assert m._halos() == (2 + 12 + 6 + 4 + 2, 8 + 10 + 4 + 6)
+    assert m.encoder.supports_row_limit(256) and m.decoder.supports_row_limit(256)
+    assert m._skips_pad_rows(True) is False                      # off by default
+    m.skip_pad_rows = True
+    assert m._skips_pad_rows(True) is True
+    assert m._skips_pad_rows(False) is False                      # teacher-forced forward: every row, like the reference
+    m.length_buckets = 2
+    assert m._skips_pad_rows(True) is False                      # the bucketed path already cuts the rows
+    for preset in ("C1", "C3"):                                   # dense FFN / d = 768: no row-limited FFTBlock
+        other = _mk(preset).eval()
+        other.skip_pad_rows = True
+        assert not other.decoder.supports_row_limit(other.hparams.decoder_hidden)
+        with pytest.raises(NotImplementedError):
+            other._skips_pad_rows(True)
+    m.length_buckets, m.skip_pad_rows = 1, True
+    m.set_compute_mode("simt")
+    with pytest.raises(NotImplementedError):
+        m._skips_pad_rows(True)
+
+
+def test_graph_signature_tracks_parameter_changes():
+    """captured bucket graphs bake in weight addresses and packed copies: any parameter change must drop them"""
+    m = _mk("TINY_DW").eval()
+    m._graphs_validate()
+    m._graphs["sentinel"] = {"seen": 1}
+    m._graphs_validate()
+    assert "sentinel" in m._graphs
+    with torch.no_grad():
+        m.linear.bias.add_(1.0)
+    m._graphs_validate()
+    assert "sentinel" not in m._graphs
+    m._graphs["sentinel"] = {"seen": 1}
+    m.float()                                                     # _apply: parameters may move
+    assert "sentinel" not in m.__dict__.get("_graphs", {})
