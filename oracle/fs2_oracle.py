@@ -194,6 +194,24 @@ def bucket_indices(values, bins):
     return torch.bucketize(values, bins)
 
 
+def variance_encoder(x, tgt, mask, sd, pre, nlayers, depthwise, mean, std, dtype, control=1.0, forced_idx=None):
+    """VarianceEncoder.forward, non-CWT branch (model.py:409-441): prediction = predictor(x, mask); the embedding is
+    looked up at bucketize(tgt * std + mean) when a target is given (:417-422), else at bucketize(prediction * std +
+    mean) of the UNSCALED prediction, after which the returned prediction is multiplied by `control` (:434-438).
+    -> (prediction, embedding, bucket index)"""
+    pred = variance_predictor(x, mask, sd, pre + "predictor.", nlayers, depthwise, dtype)
+    bins = sd[pre + "bins"].to(dtype)
+    if forced_idx is not None:
+        idx = forced_idx
+    elif tgt is not None:
+        idx = bucket_indices(tgt.to(dtype) * std + mean, bins)
+    else:
+        idx = bucket_indices(pred * std + mean, bins)
+    if tgt is None:
+        pred = pred * control
+    return pred, sd[pre + "embedding.weight"].to(dtype)[idx], idx
+
+
 def forward(sd, hp, batch, inference=False, dtype=torch.float32, force=None, control=None):
     """FastSpeech2.forward (fastspeech2.py:636-736) -> dict with the reference's result keys
     plus '_'-prefixed intermediates used by per-stage parity tests.
@@ -223,19 +241,11 @@ def forward(sd, hp, batch, inference=False, dtype=torch.float32, force=None, con
     def encode(i, var, x, mask, out_val):
         """VarianceEncoder.forward + the `x = x + out` of the adaptor (model.py:409-441, 284-294 / 315-333)"""
         pre = va + f"encoders.{var}."
-        pred = variance_predictor(x, mask, sd, pre + "predictor.", hp["variance_nlayers"][i],
-                                  hp["variance_depthwise_conv"], dtype)
-        bins = sd[pre + "bins"].to(dtype)
         stats = hp.get("stats", {}).get(var, {"mean": 0.0, "std": 1.0})
-        if "bucket_idx" in force and var in force["bucket_idx"]:
-            idx = force["bucket_idx"][var]
-        elif not inference:
-            idx = bucket_indices(batch[f"variances_{var}"].to(dtype) * stats["std"] + stats["mean"], bins)
-        else:
-            idx = bucket_indices(pred * stats["std"] + stats["mean"], bins)
-        if inference:
-            pred = pred * control.get(var, 1.0)
-        emb = sd[pre + "embedding.weight"].to(dtype)[idx]
+        pred, emb, idx = variance_encoder(
+            x, None if inference else batch[f"variances_{var}"], mask, sd, pre, hp["variance_nlayers"][i],
+            hp["variance_depthwise_conv"], stats["mean"], stats["std"], dtype, control=control.get(var, 1.0),
+            forced_idx=force["bucket_idx"][var] if "bucket_idx" in force and var in force["bucket_idx"] else None)
         res[f"variances_{var}"] = pred
         res[f"_bucket_{var}"] = idx
         return x + emb, (emb if out_val is None else out_val + emb)

@@ -189,11 +189,39 @@ def block_golden():
     print("fft_block:", [o["tag"] for o in out])
 
 
+def variance_encoder_golden():
+    """The reference's VarianceEncoder called directly, with and without a target and with `control` != 1 (the
+    adaptor never passes it, model.py:284-288/323-327, so the whole-model goldens cannot pin that argument)."""
+    m = ref_shim.import_model()
+    g = np.random.default_rng(21)
+    out = []
+    for tag, d, nl, dw in [("dw_d32", 32, 2, True), ("dense_d32", 32, 2, False), ("dw_d256", 256, 5, True)]:
+        enc = m.VarianceEncoder(nl, d, d, 3, 0.1, dw, STATS["min"], STATS["max"], STATS["mean"], STATS["std"], 256,
+                                False).eval()
+        sd = synthetic.fill_state_dict(enc.state_dict(), seed=5)
+        enc.load_state_dict(sd)
+        b, t = 2, 37
+        x = torch.from_numpy(g.standard_normal((b, t, d)).astype(np.float32))
+        tgt = torch.from_numpy(g.standard_normal((b, t)).astype(np.float32))
+        mask = torch.zeros(b, t, dtype=torch.bool)
+        mask[1, 25:] = True
+        with torch.no_grad():
+            p_tf, e_tf = enc(x, tgt, mask)
+            p_free, e_free = enc(x, None, mask)
+            p_ctl, e_ctl = enc(x, None, mask, control=1.3)
+        out.append({"tag": tag, "d": d, "nlayers": nl, "depthwise": dw, "x": x, "tgt": tgt, "mask": mask,
+                    "mean": STATS["mean"], "std": STATS["std"], "shapes": {n: tuple(v.shape) for n, v in sd.items()},
+                    "teacher_forced": (p_tf, e_tf), "free": (p_free, e_free), "control_1.3": (p_ctl, e_ctl)})
+    torch.save(out, os.path.join(OUT, "variance_encoder.pt"))
+    print("variance_encoder:", [o["tag"] for o in out])
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
     length_regulator_golden()
     block_golden()
+    variance_encoder_golden()
     tiny = synthetic.make_batch(3, 5, 17, seed=5)
     forward_golden("tiny_dw_infer", "TINY_DW", 1, tiny, True, stats=STATS)
     forward_golden("tiny_dense_infer", "TINY_DENSE", 2, tiny, True, stats=STATS)

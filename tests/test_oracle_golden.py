@@ -88,6 +88,20 @@ def test_fft_block(golden_dir):
         assert (y64 - c["y64"]).abs().max() < 1e-12, c["tag"]
 
 
+def test_variance_encoder_with_control(golden_dir):
+    """VarianceEncoder called directly (model.py:409-441): teacher-forced, free-running and with control = 1.3 (the
+    embedding follows the UNSCALED prediction, only the returned prediction is scaled)"""
+    for c in _load(golden_dir, "variance_encoder"):
+        sd = synthetic.fill_state_dict(c["shapes"], seed=5)
+        for key, tgt, ctl in (("teacher_forced", c["tgt"], 1.0), ("free", None, 1.0), ("control_1.3", None, 1.3)):
+            pred, emb, _ = O.variance_encoder(c["x"], tgt, c["mask"], sd, "", c["nlayers"], c["depthwise"], c["mean"],
+                                              c["std"], torch.float32, control=ctl)
+            rp, re = c[key]
+            assert (pred - rp).abs().max() < 1e-5, (c["tag"], key)
+            assert torch.equal(emb, re), (c["tag"], key)
+        assert torch.equal(c["control_1.3"][1], c["free"][1])  # same buckets with and without control
+
+
 def test_length_regulator_bit_exact(golden_dir):
     for c in _load(golden_dir, "length_regulator"):
         out, mask = O.length_regulator(c["x"], c["dur"], c["max_length"])
