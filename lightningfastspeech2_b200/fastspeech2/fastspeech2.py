@@ -315,6 +315,11 @@ class FastSpeech2(_Base):
         self.phone2id = checkpoint["phone2id"]
         if not hasattr(self, "phone_embedding"):
             self.phone_embedding = nn.Embedding(len(self.phone2id), self.hparams.encoder_hidden, padding_idx=0)
+        if not hasattr(self, "prior_embeddings"):  # model built without stats (reference :555-563)
+            hp = self.hparams
+            self.prior_embeddings = nn.ModuleDict({
+                prior: PriorEmbedding(hp.encoder_hidden, hp.variance_nbins, self.stats[f"{prior}_prior"])
+                for prior in hp.priors}).to(self.device)
         for key in ("speaker2dvector", "speaker2priors", "speaker_gmms", "dvector_gmms"):
             if key in checkpoint:
                 setattr(self, key, checkpoint[key])
@@ -475,7 +480,10 @@ class FastSpeech2(_Base):
         if entry is None:
             if len(cache) >= self.max_graphs:
                 cache.pop(next(iter(cache)))
-            cache[key] = {"seen": 1}
+            # `gen` distinguishes this entry from an evicted one with the same key: graphs captured downstream of it
+            # (the decoder stage reads the encoder graph's static output buffers) carry it in THEIR key
+            self.__dict__["_graph_gen"] = self.__dict__.get("_graph_gen", 0) + 1
+            cache[key] = {"seen": 1, "gen": self.__dict__["_graph_gen"]}
             return fn(*inputs), False
         if "graph" not in entry:
             static_in = [torch.empty_like(x, device=self.device) for x in inputs]
@@ -550,9 +558,10 @@ class FastSpeech2(_Base):
             key = ("E", g0, len(idx), tp_g, self.compute_mode)
             if use_graphs:
                 st, replayed = self._graphed(key, enc_fn, [sub["phones"], sub["speaker"]])
+                ekey = (key, self._graphs[key]["gen"]) if replayed else None
             else:
-                st, replayed = enc_fn(sub["phones"], sub["speaker"]), False
-            stages.append((idx, tp_g, f, st, key if replayed else None))
+                st, ekey = enc_fn(sub["phones"], sub["speaker"]), None
+            stages.append((idx, tp_g, f, st, ekey))
         # the decoder side needs the global frame count first (where the reference's tensor ends): ONE read-back
         longest = torch.cat([st["scan"][2] for _, _, _, st, _ in stages]).tolist()
         l_glob = min(max(longest), cap)
@@ -630,8 +639,35 @@ class FastSpeech2(_Base):
                 p.grad = flat_g[o:o + p.numel()].view(p.shape)
         self._flat_param, self._flat_grad = flat_p, flat_g
         self._flat_ids = [id(p) for p in params]
+        self.__dict__["_flat_layout"] = (params, offs)
         ops.WEIGHTS_EPOCH += 1
         return flat_p, flat_g
+
+    def rehome_gradients(self):
+        """Make every p.grad a view of the flat gradient buffer again.  ``zero_grad(set_to_none=True)`` (torch's and
+        Lightning's default) drops the views; a gradient tensor that is not a view would never reach the fused AdamW
+        or the all-reduce.  A stray gradient that already holds values is added into its slot first."""
+        layout = self.__dict__.get("_flat_layout")
+        if layout is None:
+            return
+        flat_g = self._flat_grad
+        base = flat_g.data_ptr()
+        for p, o in zip(*layout):
+            g = p.grad
+            if g is not None and g.data_ptr() == base + 4 * o:
+                continue
+            view = flat_g[o:o + p.numel()].view(p.shape)
+            if g is not None:
+                with torch.no_grad():
+                    view.add_(g.to(view.dtype))
+            p.grad = view
+
+    def zero_grad(self, set_to_none=True):
+        """With flat buffers the gradients are zeroed in place and stay views (set_to_none would orphan them)."""
+        if self.__dict__.get("_flat_layout") is None:
+            return super().zero_grad(set_to_none=set_to_none)
+        self._flat_grad.zero_()
+        self.rehome_gradients()
 
     def allreduce_gradients(self, group=None):
         """Data-parallel gradient exchange: ONE NCCL all-reduce (sum) over the flat gradient buffer
@@ -694,11 +730,56 @@ class FusedAdamW(torch.optim.Optimizer):
 
     def zero_grad(self, set_to_none=False):
         self.flat_g.zero_()
+        self.model.rehome_gradients()
+
+    def _slots(self):
+        params, offs = self.model.__dict__["_flat_layout"]
+        return [(o, p.numel(), p.shape) for p, o in zip(params, offs)]
+
+    def state_dict(self):
+        """torch.optim.AdamW's layout ({"state": {i: {"step", "exp_avg", "exp_avg_sq"}}, "param_groups"}), so a
+        checkpoint written here resumes under torch's AdamW (the reference's optimizer) and vice versa."""
+        state = {}
+        if self.step_count > 0:
+            for i, (o, n, shape) in enumerate(self._slots()):
+                state[i] = {"step": torch.tensor(float(self.step_count)),
+                            "exp_avg": self.exp_avg[o:o + n].view(shape).clone(),
+                            "exp_avg_sq": self.exp_avg_sq[o:o + n].view(shape).clone()}
+        groups = [{k: v for k, v in g.items() if k != "params"} for g in self.param_groups]
+        groups[0]["params"] = list(range(len(self._slots())))
+        return {"state": state, "param_groups": groups, "lfs2_fused": {"step_count": self.step_count,
+                                                                        "max_grad_norm": self.max_grad_norm}}
+
+    def load_state_dict(self, sd):
+        slots = self._slots()
+        state = sd.get("state", {})
+        if state and len(state) != len(slots):
+            raise ValueError(f"optimizer state holds {len(state)} parameters, the model has {len(slots)} trainable ones")
+        steps = set()
+        with torch.no_grad():
+            self.exp_avg.zero_()
+            self.exp_avg_sq.zero_()
+            for i, (o, n, shape) in enumerate(slots):
+                st = state.get(i, state.get(str(i)))
+                if st is None:
+                    continue
+                if tuple(st["exp_avg"].shape) != tuple(shape):
+                    raise ValueError(f"optimizer state {i}: shape {tuple(st['exp_avg'].shape)} vs parameter {tuple(shape)}")
+                self.exp_avg[o:o + n].view(shape).copy_(st["exp_avg"])
+                self.exp_avg_sq[o:o + n].view(shape).copy_(st["exp_avg_sq"])
+                steps.add(int(float(st["step"])))
+        if len(steps) > 1:
+            raise ValueError(f"per-parameter step counts differ ({sorted(steps)}): the fused kernel keeps one")
+        self.step_count = steps.pop() if steps else int(sd.get("lfs2_fused", {}).get("step_count", 0))
+        for g, saved in zip(self.param_groups, sd.get("param_groups", [])):
+            g.update({k: v for k, v in saved.items() if k != "params"})
+            g["betas"] = tuple(g["betas"])
 
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
         g = self.param_groups[0]
+        self.model.rehome_gradients()
         self.step_count += 1
         gn = None
         if self.max_grad_norm > 0:

@@ -85,9 +85,12 @@ class FastSpeech2Loss(nn.Module):
                 raise ValueError(f"Unknown variance level: {level}")
             one(i, var, pred, kind, mask, tgt=truth[:, : pred.shape[1]].contiguous())
         nv = len(self.variances)
-        one(nv, "mel", mel, self.mel_loss, tgt_mask, tgt=target["mel"].to(dev, torch.float32).contiguous())
+        # a collated target can be longer than this batch's own longest utterance (sharded batches, padding to a
+        # multiple): frames past the prediction are PAD for every utterance here
+        one(nv, "mel", mel, self.mel_loss, tgt_mask,
+            tgt=target["mel"].to(dev, torch.float32)[:, : mel.shape[1]].contiguous())
         one(nv + 1, "duration", result["duration_prediction"], self.duration_loss, src_mask,
-            tgt_i64=target["duration"].to(dev, torch.int64).contiguous())
+            tgt_i64=target["duration"].to(dev, torch.int64)[:, : result["duration_prediction"].shape[1]].contiguous())
         losses = {name: buf[i] for i, name in enumerate(names)}
         losses["total"] = _LossFn.apply(total, grads, *preds).reshape(()) if want_grad else total.reshape(())
         self.last_buffer = buf  # one D2H copy of this gives every value (training_step logging)

@@ -389,6 +389,7 @@ def backward_train(M, S, dmel, ddur, dvars):
     E = S["E"]
     va = M.variance_adaptor
     dev = M.device
+    M.rehome_gradients()  # gradients dropped by zero_grad(set_to_none=True) become views of the flat buffer again
     bsz = S["phones"].shape[0]
     d = M.hparams.encoder_hidden
     dspk = torch.zeros(bsz, d, device=dev, dtype=torch.float32)

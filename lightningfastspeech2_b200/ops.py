@@ -35,9 +35,25 @@ def _launch(cname, *args, tag=None, flops=0.0, nbytes=0.0):
     _lib.check(rc, cname)
 
 
-def collect_profile(hbm_gbs=6548.2, tensor_tflops=1680.6):
+def measured_peaks():
+    """(HBM GB/s, dense bf16 TFLOP/s sustained) from MEASURED_PEAKS.json at the repo root (driver-written), else the
+    fallback figures of the profiling recipe"""
+    import json
+    import os
+
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    try:
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"]))
+    except Exception:  # noqa: BLE001
+        return 6650.0, 1400.0
+
+
+def collect_profile(hbm_gbs=None, tensor_tflops=None):
     """{tag: {ms, launches, flops, bytes, bound}} summed over the recorded launches; `bound` is
-    whichever of (bytes / HBM peak, flops / tensor peak) is the longer time."""
+    whichever of (bytes / HBM peak, flops / tensor peak) is the longer time (peaks: MEASURED_PEAKS.json)."""
+    if hbm_gbs is None or tensor_tflops is None:
+        hbm_gbs, tensor_tflops = measured_peaks()
     torch.cuda.synchronize()
     out = {}
     for tag, recs in (PROFILE or {}).items():
@@ -218,6 +234,8 @@ def length_regulate_scan(durations, batch_first_shape):
         raise TypeError("length_regulate: durations must be int32 or int64")
     durations = durations.contiguous()
     b, tp = batch_first_shape
+    if tuple(durations.shape) != (b, tp):
+        raise ValueError(f"length_regulate: durations {tuple(durations.shape)} do not match x[:2] = {(b, tp)}")
     dev = durations.device
     cum = torch.empty(b, tp, device=dev, dtype=torch.int64)
     lengths = torch.empty(b, device=dev, dtype=torch.int64)

@@ -23,21 +23,41 @@ def snake_shards(lengths, world):
     return shards
 
 
-def shard_batch(batch, rank, world, length_key="phones_lengths"):
+def phone_lengths(phones):
+    """(B,Tp) phoneme ids, 0 = PAD -> last valid position + 1 per utterance (not the count of non-PAD ids)"""
+    tp = phones.shape[1]
+    return ((phones != 0) * torch.arange(1, tp + 1, device=phones.device)).amax(1) if tp else phones.new_zeros(len(phones))
+
+
+def shard_batch(batch, rank, world, length_key="phones_lengths", max_frames=None):
     """The rank's slice of a collated batch dict (reference dataset/datasets.py:852-882 layout):
-    every tensor whose first dimension is the batch is indexed, phoneme-level tensors are cut
-    to the shard's own maximum length (each rank pads to ITS longest utterance)."""
-    lengths = batch[length_key].tolist() if length_key in batch else (batch["phones"] != 0).sum(1).tolist()
+    every tensor whose first dimension is the batch is indexed; phoneme-level tensors (`phones`, `duration`,
+    phone-level `variances_*`) are cut to the shard's own longest utterance and frame-level ones (`mel`, frame-level
+    `variances_*`) to the shard's own longest expanded length sum(duration), capped by `max_frames` (the
+    LengthRegulator's limit) -- each rank pads to ITS longest utterance, which is also the shape its model returns."""
+    lengths = batch[length_key].tolist() if length_key in batch else phone_lengths(batch["phones"]).tolist()
     mine = snake_shards(lengths, world)[rank]
     bsz = batch["phones"].shape[0]
     tp_full = batch["phones"].shape[1]
     keep = max(int(lengths[u]) for u in mine) if mine else 0
+    tm_full = batch["mel"].shape[1] if torch.is_tensor(batch.get("mel")) else None
+    tm_keep = None
+    if tm_full is not None and torch.is_tensor(batch.get("duration")) and mine:
+        tm_keep = int(batch["duration"][mine][:, :keep].sum(1).max())
+        if max_frames is not None:
+            tm_keep = min(tm_keep, int(max_frames))
     out = {}
     for k, v in batch.items():
         if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == bsz:
             v = v[mine]
-            if v.dim() >= 2 and v.shape[1] == tp_full and k in ("phones", "duration"):
+            phone_level = k in ("phones", "duration") or (k.startswith("variances_") and v.dim() == 2
+                                                          and v.shape[1] == tp_full and v.shape[1] != tm_full)
+            frame_level = tm_keep is not None and (k == "mel" or (k.startswith("variances_") and v.dim() == 2
+                                                                  and v.shape[1] == tm_full))
+            if v.dim() >= 2 and v.shape[1] == tp_full and phone_level:
                 v = v[:, :keep]
+            elif frame_level:
+                v = v[:, :tm_keep]
             out[k] = v.contiguous()
         else:
             out[k] = v

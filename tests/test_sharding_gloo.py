@@ -38,8 +38,29 @@ def test_shard_batch_pads_to_own_maximum():
         assert (sub["phones"] != 0).sum(1).tolist() == sub["phones_lengths"].tolist()
         assert sub["duration"].shape == sub["phones"].shape
         assert sub["mel"].shape[0] == 4 and sub["speaker"].shape == (4, 256)
+        # frame-level targets are cut to the shard's own longest expanded length: what the shard's model returns
+        tm = int(sub["duration"].sum(1).max())
+        assert sub["mel"].shape[1] == tm
+        assert all(sub[f"variances_{v}"].shape == (4, tm) for v in ("pitch", "energy"))
         seen += sub["phones_lengths"].tolist()
     assert sorted(seen) == sorted(batch["phones_lengths"].tolist())
+
+
+def test_shard_batch_cuts_phone_level_variances_and_caps_frames():
+    batch = synthetic.make_batch(6, 5, 30, seed=5)
+    batch = synthetic.add_train_targets(batch, ["pitch", "energy"], seed=5, levels=["phone", "frame"])
+    for rank in range(2):
+        sub = sharding.shard_batch(batch, rank, 2, max_frames=50)
+        tp = int(sub["phones_lengths"].max())
+        tm = min(int(sub["duration"].sum(1).max()), 50)
+        assert sub["variances_pitch"].shape == (3, tp)      # phone level: cut like `phones`
+        assert sub["variances_energy"].shape == (3, tm)     # frame level: cut like `mel`, capped
+        assert sub["mel"].shape[:2] == (3, tm)
+
+
+def test_phone_lengths_is_last_valid_plus_one():
+    phones = torch.tensor([[3, 0, 4, 0, 0], [1, 2, 3, 4, 5], [0, 0, 0, 0, 0]])
+    assert sharding.phone_lengths(phones).tolist() == [3, 5, 0]
 
 
 def _free_port():
@@ -60,12 +81,8 @@ def _worker(rank, world, port, out_dir):
     shapes = torch.load(os.path.join(os.path.dirname(__file__), "golden", "tiny_dw_train.pt"), weights_only=False)["shapes"]
     sd = synthetic.fill_state_dict({k: v for k, v in shapes.items() if not k.startswith("fastdiff")}, seed=9)
     full = synthetic.add_train_targets(synthetic.make_batch(6, 5, 17, seed=9), hp["variances"], seed=9)
-    # targets were generated for the full padded batch: cut the frame-level ones to the shard's own Tm
-    sub = sharding.shard_batch(full, rank, world)
-    tm = int(sub["duration"].sum(1).max())
-    sub["mel"] = sub["mel"][:, :tm].contiguous()
-    for v in hp["variances"]:
-        sub[f"variances_{v}"] = sub[f"variances_{v}"][:, :tm].contiguous()
+    # the collated FULL batch goes straight through shard_batch into model + loss (no re-slicing by hand)
+    sub = sharding.shard_batch(full, rank, world, max_frames=configs.max_frames(hp))
     losses, grads = O.gradients(sd, hp, sub)
     names = sorted(grads)
     flat = torch.cat([grads[k].flatten() for k in names])
