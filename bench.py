@@ -264,7 +264,7 @@ def measure_train(args, dev, rank, world, barrier):
            "scaling": "strong", "n_gpus": world, "dtype": {"simt": "f32", "fp32": "f32", "bf16": "bf16"}[args.train_mode],
            "compute_mode": args.train_mode, "valid_frames_per_step": frames, "frames_per_s": frames / (ms * 1e-3),
            "parameters": nparams, "gpu_launches_per_step": launches,
-           "allreduce_bytes_per_step": 0 if world == 1 else 4 * model_flat_numel(nparams),
+           "allreduce_bytes_per_step": 0 if world == 1 else 4 * nparams,
            "final_losses": {"total": loss_vals[-1]},
            "config": {"workload": TRAIN_WORKLOAD, "preset": TRAIN_PRESET, "utterances_rank0": int(batch["phones"].shape[0]),
                       "padded_phones_rank0": int(batch["phones"].shape[1]), "mel_frames_rank0": int(batch["mel"].shape[1]),
@@ -285,8 +285,149 @@ def measure_train(args, dev, rank, world, barrier):
     return out
 
 
-def model_flat_numel(nparams):
-    return nparams
+# ---------------------------------------------------------------------------------------------
+# secondary sections (rank 0 only, local synchronisation only)
+def parity_vs_oracle(model, sd, hp, host_batch, nutt, modes):
+    """max |mel_cuda - mel_oracle| on a slice of the TIMED batch: the first `nutt` utterances, padded to the full
+    batch's phoneme length exactly as in the timed tensors (padding leaks through the FFN convolutions, so the padded
+    length is part of the input), oracle (CPU port of the reference) vs this model in each compute mode.  The oracle's
+    discrete decisions (rounded durations, bucket indices) are forced on the CUDA run when any of them flipped
+    (SURVEY 0.6); flips are reported.  modes: {label: (compute_mode, skip_pad_rows)}."""
+    from oracle import fs2_oracle as O
+
+    sub = {"phones": host_batch["phones"][:nutt].contiguous(), "speaker": host_batch["speaker"][:nutt].contiguous()}
+    torch.set_num_threads(os.cpu_count())
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ref = O.forward(sd, hp, sub, inference=True)
+    out = {"utterances": nutt, "padded_phones": int(sub["phones"].shape[1]), "mel_shape": list(ref["mel"].shape),
+           "oracle_seconds": round(time.perf_counter() - t0, 2), "modes": {}}
+    valid = ~ref["tgt_mask"]
+    force = {"duration_rounded": ref["duration_rounded"], "bucket_idx": {v: ref[f"_bucket_{v}"] for v in hp["variances"]},
+             "want_idx": True}
+    old_mode, old_skip = model.compute_mode, model.skip_pad_rows
+    try:
+        for label, (mode, skip) in modes.items():
+            model.set_compute_mode(mode)
+            model.skip_pad_rows = skip
+            with torch.no_grad():
+                r = model(sub, inference=True, force={"want_idx": True})
+            flips = int((r["duration_rounded"].cpu() != ref["duration_rounded"]).sum())
+            if r["mel"].shape == ref["mel"].shape:
+                flips += sum(int((r[f"_bucket_{v}"].cpu() != ref[f"_bucket_{v}"]).sum()) for v in hp["variances"])
+            if flips or r["mel"].shape != ref["mel"].shape:
+                with torch.no_grad():
+                    r = model(sub, inference=True, force=force)
+            d = (r["mel"].cpu() - ref["mel"]).abs()
+            out["modes"][label] = {"max_abs_mel_err_valid_frames": float(d[valid].max()),
+                                   "max_abs_mel_err_all_positions": None if skip else float(d.max()),
+                                   "masks_equal": bool(torch.equal(r["tgt_mask"].cpu(), ref["tgt_mask"])),
+                                   "discrete_decision_flips_before_forcing": flips,
+                                   "tolerance": 1e-2 if mode == "bf16" else 1e-3}
+    finally:
+        model.set_compute_mode(old_mode)
+        model.skip_pad_rows = old_skip
+    return out
+
+
+def measure_c1(dev, steps=30):
+    """BASELINE.json configs[0] ("C1"): ming024-like dense-conv FastSpeech2 (k = 9, 24.5 M params), ONE 128-phoneme
+    utterance: latency of model(batch, inference=True) incl. the H2D of the inputs and a D2H of the mel, next to the
+    CPU port on the same input."""
+    from oracle import fs2_oracle as O
+
+    model, sd, hp = build_model(dev, preset="C1")
+    batch = synthetic.make_batch(1, 128, 128, seed=1234)
+    pinned = {k: v.pin_memory() for k, v in batch.items() if k in ("phones", "speaker")}
+
+    def once():
+        with torch.no_grad():
+            r = model(pinned, inference=True)
+        return r["mel"].cpu(), r
+
+    for _ in range(5):
+        once()
+    lat = []
+    for _ in range(steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mel, r = once()
+        lat.append((time.perf_counter() - t0) * 1e3)
+    frames = int((~r["tgt_mask"]).sum())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    resident = {k: v.to(dev) for k, v in pinned.items()}
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(steps):
+        with torch.no_grad():
+            model(resident, inference=True)
+    e1.record()
+    torch.cuda.synchronize()
+    dev_ms = e0.elapsed_time(e1) / steps
+    torch.set_num_threads(os.cpu_count())
+    cpu = []
+    for _ in range(4):
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            ref = O.forward(sd, hp, batch, inference=True)
+        cpu.append((time.perf_counter() - t0) * 1e3)
+    cpu_ms = statistics.median(cpu[1:])
+    err = None
+    if ref["mel"].shape == mel.shape:
+        err = float((mel - ref["mel"]).abs().max())
+    ms = statistics.median(lat)
+    return {"workload": "C1: dense-conv FastSpeech2 (k=9, d=256, 4+4 FFTBlocks, 24.5M params), 1 utterance x 128 phonemes, "
+                        "fp32-parity mode (BASELINE.json configs[0])",
+            "latency_ms_e2e_median": ms, "latency_ms_device": dev_ms, "valid_frames": frames,
+            "value": frames / (ms * 1e-3), "unit": UNIT, "steps": steps,
+            "cpu_baseline": {"latency_ms": cpu_ms, "value": int((~ref["tgt_mask"]).sum()) / (cpu_ms * 1e-3), "unit": UNIT,
+                             "cores": os.cpu_count(), "kind": "port", "sample": "the same utterance, median of 3 runs"},
+            "max_abs_mel_err_vs_oracle": err}
+
+
+def measure_c5(dev, hbm_peak, steps=20):
+    """BASELINE.json configs[4] ("C5"): LengthRegulator stress, B = 512, Tp = 400, d = 256 fp32, durations U{0..10}
+    (expanded length ~2000 frames): scan + scatter kernels against the HBM roofline, output bit-exact vs the oracle."""
+    from lightningfastspeech2_b200 import ops
+    from oracle import fs2_oracle as O
+
+    g = torch.Generator().manual_seed(5)
+    b, tp, d = 512, 400, 256
+    x = torch.randn(b, tp, d, generator=g)
+    dur = torch.randint(0, 11, (b, tp), generator=g, dtype=torch.int32)
+    cap = 2756.25
+    xd, dd = x.to(dev), dur.to(dev)
+    out, mask = ops.length_regulate(xd, dd, cap)
+    l = out.shape[1]
+    nref = 48  # bit-exactness against the oracle's torch restatement of model.py:349-370 on the first utterances
+    ro, rm = O.length_regulator(x[:nref], dur[:nref].long(), cap)
+    w = min(l, ro.shape[1])
+    exact = bool(torch.equal(out[:nref, :w].cpu(), ro[:, :w]) and torch.equal(mask[:nref, :w].cpu(), rm[:, :w])
+                 and (l >= ro.shape[1]))
+    scan = ops.length_regulate_scan(dd, (b, tp))
+    for _ in range(3):
+        ops.length_regulate_scatter(xd, scan[0], scan[1], l, l)
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    e[0].record()
+    for _ in range(steps):
+        scan = ops.length_regulate_scan(dd, (b, tp))
+    e[1].record()
+    for _ in range(steps):
+        ops.length_regulate_scatter(xd, scan[0], scan[1], l, l)
+    e[2].record()
+    torch.cuda.synchronize()
+    ms_scan, ms_scat = e[0].elapsed_time(e[1]) / steps, e[1].elapsed_time(e[2]) / steps
+    nbytes = b * tp * (d * 4 + 4) + b * l * (d * 4 + 1)      # SURVEY 8d: x + durations in, frames + mask out
+    gbs = nbytes / ((ms_scan + ms_scat) * 1e-3) / 1e9
+    return {"workload": f"C5: LengthRegulator B={b}, Tp={tp}, d={d} fp32, durations U{{0..10}} int32 -> {l} frames "
+                        "(BASELINE.json configs[4])",
+            "ms_scan": ms_scan, "ms_scatter": ms_scat, "algorithmic_bytes": nbytes, "achieved_gbs": gbs,
+            "peak_gbs": hbm_peak, "frac_of_hbm_roofline": gbs / hbm_peak,
+            "scatter_only_frac": (nbytes - b * tp * 4) / (ms_scat * 1e-3) / 1e9 / hbm_peak,
+            "bit_exact_vs_oracle": exact, "checked_utterances": nref,
+            "l2": "no flush: the 1.05 GB output exceeds the 126 MB L2"}
+
 
 
 def run_reference(args):
@@ -302,7 +443,8 @@ def run_reference(args):
     model = FastSpeech2(stats=stats, phone2id={f"p{i}": i for i in range(80)}, num_workers=0, **kw)
     sd = synthetic.fill_state_dict(model.state_dict(), seed=0)
     batch = synthetic.make_batch(BATCH, MIN_LEN, MAX_LEN, seed=2)
-    nutt = args.ref_utts
+    # the whole batch the GPU arm times at rank 0 (same config on both arms; ~5.5 s of CPU work per step)
+    nutt = BATCH if args.ref_utts is None else min(BATCH, args.ref_utts)
     for _ in range(args.warmup):
         cpu_port_throughput(sd, hp, batch, min(2, nutt))
     times, frames = [], 0
@@ -311,8 +453,9 @@ def run_reference(args):
         times.append(dt)
     total = sum(times)
     value = frames * len(times) / total
-    sample = (f"first {nutt} of the {BATCH} utterances of the C2 batch (seed 2) per step, padded to their own max "
-              f"length; oracle/fs2_oracle.py (torch CPU conv1d/linear/softmax/layer_norm), no_grad")
+    sample = (f"{'all' if nutt == BATCH else 'first ' + str(nutt) + ' of the'} {BATCH} utterances of the C2 batch (seed 2) "
+              f"per step = the GPU arm's rank-0 batch; warm-up steps run 2 utterances; oracle/fs2_oracle.py (torch CPU "
+              f"conv1d/linear/softmax/layer_norm on {os.cpu_count()} threads), no_grad")
     train = None
     if args.train_cpu_utts > 0:  # the train-step leg of the metric on the CPU port, same global batch, bounded sample
         _, sd4, hp4 = build_train_model(None)
@@ -328,7 +471,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample": sample},
+        "config": {"workload": WORKLOAD, "preset": PRESET, "utterances_per_gpu": BATCH, "sample": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -587,6 +730,16 @@ def run_lfs2(args):
         pad_skip = {"ms": ms_s, "ms_piped": ms_sp, "ms_bf16": ms_sb, "frames": fr_s, "frames_piped": fr_sp,
                     "launches": launches_s, "identical": n_same == world, "prof": prof_s, "rows": rows_s}
 
+    # ---- parity of the timed batch against the oracle (rank 0; the first utterances, padded like the timed tensors) ----
+    parity = {}
+    if rank == 0 and args.parity_utts > 0:
+        try:
+            parity["c2"] = parity_vs_oracle(model, sd, hp, host_batch, args.parity_utts,
+                                            {"fp32": ("fp32", False), "bf16": ("bf16", False),
+                                             "fp32_skip_pad_rows": ("fp32", True)})
+        except Exception as exc:  # noqa: BLE001
+            errors["parity_c2"] = repr(exc)[:300]
+
     # ---- BASELINE.json configs[2] ("C3"): 76 M-parameter model, bf16 synthesis, 32 utterances per GPU ----------
     c3 = None
     if args.c3_steps > 0:
@@ -594,10 +747,10 @@ def run_lfs2(args):
         torch.cuda.empty_cache()
         ok3, ms3, fr3, shape3 = True, 0.0, 0, []
         try:
-            m3, _, _ = build_model(dev, preset="C3")
+            m3, sd3, hp3 = build_model(dev, preset="C3")
             m3.set_compute_mode("bf16")
-            b3 = {k: v.to(dev) for k, v in synthetic.make_batch(32, MIN_LEN, MAX_LEN, seed=200 + rank).items()
-                  if k in ("phones", "speaker")}
+            hb3 = synthetic.make_batch(32, MIN_LEN, MAX_LEN, seed=200 + rank)
+            b3 = {k: v.to(dev) for k, v in hb3.items() if k in ("phones", "speaker")}
 
             def step3():
                 with torch.no_grad():
@@ -609,6 +762,12 @@ def run_lfs2(args):
             ms3 /= args.c3_steps
             fr3 = int((~r3["tgt_mask"]).sum())
             shape3 = list(r3["mel"].shape)
+            if rank == 0 and args.parity_utts > 0:
+                try:
+                    parity["c3"] = parity_vs_oracle(m3, sd3, hp3, hb3, max(1, args.parity_utts // 4),
+                                                    {"bf16": ("bf16", False), "fp32": ("fp32", False)})
+                except Exception as exc:  # noqa: BLE001
+                    errors["parity_c3"] = repr(exc)[:300]
             del m3, r3
         except Exception as exc:  # noqa: BLE001
             ok3, errors["c3_bf16"] = False, repr(exc)[:300]
@@ -628,6 +787,19 @@ def run_lfs2(args):
             train = measure_train(args, dev, rank, world, barrier)
         except Exception as exc:  # noqa: BLE001
             errors["train"] = repr(exc)[:300]
+
+    c1 = c5 = None
+    if rank == 0 and args.c1_steps > 0:
+        try:
+            c1 = measure_c1(dev, args.c1_steps)
+        except Exception as exc:  # noqa: BLE001
+            errors["c1"] = repr(exc)[:300]
+    if rank == 0 and args.c5_steps > 0:
+        try:
+            c5 = measure_c5(dev, peaks()["hbm"], args.c5_steps)
+        except Exception as exc:  # noqa: BLE001
+            errors["c5"] = repr(exc)[:300]
+        torch.cuda.empty_cache()
 
     if rank == 0:
         pk = peaks()
@@ -664,7 +836,7 @@ def run_lfs2(args):
                                        if v["ms"] > 0 else 0.0}
                                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]}}
         # bounded CPU sample of the same workload: grow the sub-batch until one run takes >= ~10 s of CPU work
-        nutt = max(1, args.ref_utts)
+        nutt = max(1, args.ref_utts or 16)
         while True:
             cpu_fps, cpu_s, cpu_frames = cpu_port_throughput(sd, hp, host_batch, nutt)
             if cpu_s >= 10.0 or nutt >= min(BATCH, args.ref_utts_max):
@@ -700,6 +872,17 @@ def run_lfs2(args):
         }
         if errors:
             line["errors"] = errors
+        # the short sections first: the driver keeps only the tail of a long line
+        if parity:
+            line["parity_check"] = parity
+        if c3 is not None:
+            line["c3_bf16"] = c3
+        if train is not None:
+            line["train"] = train
+        if c1 is not None:
+            line["c1"] = c1
+        if c5 is not None:
+            line["c5_length_regulator"] = c5
         tot_b = sum(v["ms"] for v in prof_bf16.values()) or 1.0
         top_b = max(prof_bf16, key=lambda k: prof_bf16[k]["ms"]) if prof_bf16 else None
         tb = prof_bf16[top_b] if top_b else None
@@ -740,10 +923,6 @@ def run_lfs2(args):
                 "kernel_ms": {k: round(v["ms"], 4) for k, v in sorted(ps["prof"].items(), key=lambda kv: -kv[1]["ms"])[:8]},
                 "kernel_shares": {k: round(v["ms"] / tot_s, 4)
                                   for k, v in sorted(ps["prof"].items(), key=lambda kv: -kv[1]["ms"])[:8]}}
-        if c3 is not None:
-            line["c3_bf16"] = c3
-        if train is not None:
-            line["train"] = train
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -755,10 +934,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="lfs2", choices=["lfs2", "reference"])
-    ap.add_argument("--ref-utts", type=int, default=16, help="utterances in the bounded CPU sample (first try)")
+    ap.add_argument("--ref-utts", type=int, default=None,
+                    help="utterances in the CPU sample: --impl reference times all 64 by default; the GPU arm's cpu_baseline "
+                         "starts at 16 and grows until one run takes ~10 s")
     ap.add_argument("--ref-utts-max", type=int, default=64, help="upper bound of the adaptive CPU sample")
     ap.add_argument("--buckets", type=int, nargs="*", default=[2, 4], help="length_buckets values of the 'bucketed' runs")
-    ap.add_argument("--c3-steps", type=int, default=3, help="timed C3 (76M, bf16) synthesis steps under 'c3_bf16' (0 = skip)")
+    ap.add_argument("--c3-steps", type=int, default=10, help="timed C3 (76M, bf16) synthesis steps under 'c3_bf16' (0 = skip)")
+    ap.add_argument("--parity-utts", type=int, default=16,
+                    help="utterances of the timed C2 batch compared with the oracle under 'parity_check' (C3: a quarter; 0 = skip)")
+    ap.add_argument("--c1-steps", type=int, default=30, help="timed C1 (1 x 128 phonemes, dense k=9) calls under 'c1' (0 = skip)")
+    ap.add_argument("--c5-steps", type=int, default=20, help="timed C5 LengthRegulator launches under 'c5_length_regulator' (0 = skip)")
     ap.add_argument("--train-steps", type=int, default=5, help="timed C4 train steps reported under 'train' (0 = skip)")
     ap.add_argument("--train-mode", default="fp32", choices=["simt", "fp32", "bf16"])
     ap.add_argument("--train-cpu-utts", type=int, default=2, help="utterances in the CPU train-step sample (0 = skip)")

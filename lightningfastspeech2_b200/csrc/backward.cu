@@ -448,16 +448,25 @@ __global__ void fold_pw_fwd_kernel(const float* __restrict__ w21, const float* _
   const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
   if (i0 >= d_out * groups) return;
   const int n = i0 / groups, G = i0 % groups, f = groups * g;
-  float bsum = 0.f;
   float o[kFoldMaxG];
   for (int i = 0; i < g; ++i) o[i] = 0.f;
   for (int oo = 0; oo < g; ++oo) {
     const float w = w21[(size_t)n * f + G * g + oo];
-    bsum = fmaf(w, b20[G * g + oo], bsum);
     for (int i = 0; i < g; ++i) o[i] = fmaf(w, w20[(size_t)(G * g + oo) * g + i], o[i]);
   }
   for (int i = 0; i < g; ++i) w_eff[(size_t)n * f + G * g + i] = o[i];
-  atomicAdd(b_eff + n, bsum + (G == 0 ? b21[n] : 0.f));
+}
+
+// b_eff[n] = W21[n, :] . b20 + b21[n]; one warp per output channel, fixed summation order (two model instances built
+// from the same weights must produce the same bits: checkpoints, multi-GPU replicas)
+__global__ void fold_pw_bias_kernel(const float* __restrict__ w21, const float* __restrict__ b20,
+                                    const float* __restrict__ b21, float* __restrict__ b_eff, int d_out, int f) {
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (n >= d_out) return;
+  float acc = 0.f;
+  for (int c = lane; c < f; c += 32) acc = fmaf(w21[(size_t)n * f + c], b20[c], acc);
+  acc = warp_sum(acc);
+  if (lane == 0) b_eff[n] = acc + b21[n];
 }
 
 // dW21[n, G*g+o] += sum_i dWe[n, G*g+i] * W20[G*g+o, i] + dbe[n] * b20[G*g+o]
@@ -689,13 +698,11 @@ int lfs2_fold_pw_fwd(const float* w21, const float* w20, const float* b20, const
   LFS2_REQUIRE(d_out > 0 && groups > 0 && g > 0 && g <= kFoldMaxG, LFS2_ERR_UNSUPPORTED,
                "fold_pw: group size %d not supported (1..%d)", g, kFoldMaxG);
   cudaStream_t s = (cudaStream_t)stream;
-  if (cudaMemsetAsync(b_eff, 0, sizeof(float) * d_out, s) != cudaSuccess) {
-    set_error("fold_pw_fwd: memset failed");
-    return LFS2_ERR_CUDA;
-  }
   fold_pw_fwd_kernel<<<ceil_div((long long)d_out * groups, 256), 256, 0, s>>>(w21, w20, b20, b21, w_eff, b_eff, d_out,
                                                                              groups, g);
   LFS2_CHECK_LAUNCH("fold_pw_fwd");
+  fold_pw_bias_kernel<<<ceil_div((long long)d_out * 32, 256), 256, 0, s>>>(w21, b20, b21, b_eff, d_out, groups * g);
+  LFS2_CHECK_LAUNCH("fold_pw_bias");
   return LFS2_OK;
 }
 

@@ -18,7 +18,7 @@ import torch
 from torch import nn
 
 from .. import ops
-from . import training
+from . import boundary, training
 from .loss import FastSpeech2Loss
 from .model import (COMPUTE_MODES, ConformerEncoderLayer, PositionalEncoding, PriorEmbedding, SpeakerEmbedding,
                     VarianceAdaptor, _PackCache)
@@ -223,13 +223,22 @@ class FastSpeech2(_Base):
         self.fastdiff_model = None
         self.fastdiff_speaker_generator = None
 
-        # -- dataset-derived metadata (reference :236-245); dataset building itself is out of scope
+        # -- datasets (reference :167-228: raw alignment datasets are wrapped in TTSDataset, behind the pickle cache;
+        #    built datasets pass through) and the metadata derived from them (:236-245)
+        train_ds, valid_ds = boundary.build_datasets(
+            train_ds, valid_ds, train_ds_kwargs, valid_ds_kwargs, cache_path,
+            dict(speaker_type=speaker_type, min_length=min_length, max_length=max_length,
+                 augment_duration=augment_duration, variances=variances, variance_levels=variance_levels,
+                 variance_transforms=variance_transforms, priors=priors, n_mels=n_mels, sampling_rate=sampling_rate,
+                 n_fft=n_fft, win_length=win_length, hop_length=hop_length))
         if train_ds is not None:
             self.train_ds = train_ds
             self.stats = train_ds.stats
             self.phone2id = train_ds.phone2id
             if "dvector" in getattr(train_ds, "speaker_type", speaker_type):
                 self.speaker2dvector = getattr(train_ds, "speaker2dvector", {})
+            if getattr(train_ds, "speaker_type", speaker_type) == "id":
+                self.speaker2id = getattr(train_ds, "speaker2id", {})
         if valid_ds is not None:
             self.valid_ds = valid_ds
         if stats is not None:
@@ -706,6 +715,23 @@ class FastSpeech2(_Base):
                                                weight_decay=0.01)
         self.scheduler = NoamLR(self.optimizer, self.hparams.warmup_steps)
         return [self.optimizer], [{"scheduler": self.scheduler, "interval": "step"}]
+
+    # -- argparse surface and dataloaders (reference :1184-1323; litfass/train.py:73-74, Trainer.fit) ----------
+    @staticmethod
+    def add_model_specific_args(parent_parser):
+        return boundary.add_model_specific_args(parent_parser)
+
+    @staticmethod
+    def add_dataset_specific_args(parent_parser):
+        return boundary.add_dataset_specific_args(parent_parser)
+
+    def train_dataloader(self):
+        if self.hparams.sort_data_by_length:
+            self.train_ds.sort_by_duration()
+        return boundary.dataloader(self.train_ds, self.batch_size, self.num_workers)
+
+    def val_dataloader(self):
+        return boundary.dataloader(self.valid_ds, self.batch_size, self.num_workers)
 
 
 class FusedAdamW(torch.optim.Optimizer):

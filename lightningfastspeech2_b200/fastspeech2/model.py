@@ -162,16 +162,13 @@ class ConformerEncoderLayer(nn.Module):
             gc, pw2 = self.conv2[0], self.conv2[1]
             if gc.kernel_size[0] != 1:
                 raise NotImplementedError("grouped conv2.0 with kernel > 1")
-            d, fsz = dw.weight.shape[0], pw.weight.shape[0]
-            g = fsz // d
             p["dw_wt"] = dw.weight[:, 0, :].t().contiguous()           # (k, d)
             p["pw1_w"] = pw.weight[:, :, 0].contiguous()               # (F, d)
             # conv2.0 (F->F, groups=d, 1x1) followed by conv2.1 (F->d, 1x1) with nothing in
             # between is one linear map: W_eff = W21 . blockdiag(W20), b_eff = W21.b20 + b21
-            w21 = pw2.weight[:, :, 0].double().reshape(d, d, g)        # (n, G, o)
-            w20 = gc.weight[:, :, 0].double().reshape(d, g, g)         # (G, o, i)
-            p["w_eff"] = torch.einsum("ngo,goi->ngi", w21, w20).reshape(d, fsz).float().contiguous()
-            p["b_eff"] = (pw2.weight[:, :, 0].double() @ gc.bias.double() + pw2.bias.double()).float().contiguous()
+            # (lfs2_fold_pw_fwd: the same kernel the train step uses; g = F/d terms per element)
+            p["w_eff"], p["b_eff"] = ops.fold_pw(pw2.weight[:, :, 0].contiguous(), gc.weight[:, :, 0].contiguous(),
+                                                 gc.bias, pw2.bias)
         else:
             fsz, d, k1 = self.conv1.weight.shape
             p["c1_wp"] = self.conv1.weight.permute(0, 2, 1).reshape(fsz, k1 * d).contiguous()

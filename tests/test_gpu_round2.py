@@ -1,0 +1,192 @@
+"""Model-level parity of the configurations bench.py times, and of the caller extras:
+
+* one C4_P0 train step (the 76 M model: d = 768, head_dim 384, F = 3072, 4 + 5 FFTBlocks, 3 variances; every dropout
+  off) against the oracle's autograd gradients -- element-wise in `simt`, per-tensor relative L2 in `fp32` mode;
+* `control=` scaling of the variance predictions (reference model.py:409, 434-438) against the oracle;
+* save -> `load_from_checkpoint` -> synthesise round trip with the reference's key names and hooks
+  (reference fastspeech2.py:530-634), model AND optimizer state (fused AdamW resumes where it stopped).
+"""
+import os
+
+import pytest
+import torch
+
+from lightningfastspeech2_b200 import configs, synthetic
+from lightningfastspeech2_b200.fastspeech2.fastspeech2 import FastSpeech2
+from oracle import fs2_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _build(preset, seed, mode, train=False, **over):
+    kw = dict(configs.PRESETS[preset], **over)
+    hp = configs.resolve(kw)
+    st = {v: {"min": -3.0, "max": 3.0, "mean": 0.0, "std": 1.0} for v in hp["variances"]}
+    st.update({f"{p}_prior": {"min": -3.0, "max": 3.0, "mean": 0.0, "std": 1.0} for p in hp["priors"]})
+    model = FastSpeech2(stats=st, phone2id={f"p{i}": i for i in range(80)}, num_workers=0, **kw)
+    sd = synthetic.fill_state_dict(model.state_dict(), seed=seed)
+    model.load_state_dict(sd, strict=True)
+    hp["stats"] = st
+    model = model.to(DEV)
+    model = model.train() if train else model.eval()
+    return model.set_compute_mode(mode), sd, hp
+
+
+@pytest.mark.parametrize("mode,rel", [("simt", 1e-3), ("fp32", 4e-3)])
+def test_c4_train_step_matches_oracle(mode, rel):
+    """the configuration bench.py's `train` section times (preset C4 with dropout off = C4_P0)"""
+    model, sd, hp = _build("C4_P0", 11, mode, train=True)
+    assert sum(p.numel() for p in model.parameters() if p.requires_grad) > 75_000_000
+    batch = synthetic.add_train_targets(synthetic.make_batch(4, 24, 64, seed=11), hp["variances"], seed=11)
+    model.log_losses = False
+    total = model.training_step(batch, 0)
+    total.backward()
+    torch.cuda.synchronize()
+    losses, ograds = O.gradients(sd, hp, batch)
+    vals = dict(zip(list(hp["variances"]) + ["mel", "duration", "total"], model.loss.last_buffer.tolist()))
+    for k, v in losses.items():
+        assert abs(vals[k] - float(v)) <= 1e-4 * max(1.0, abs(float(v))), (k, vals[k], float(v))
+    grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+    assert set(ograds) <= set(grads)
+    scale = max(float(g.abs().max()) for g in ograds.values())
+    floor = (1e-3 if mode == "simt" else 1e-2) * scale
+    worst = ("", 0.0)
+    for k, og in ograds.items():
+        diff = grads[k].cpu() - og
+        if mode == "simt":   # exact-fp32 kernels: element by element
+            e = float(diff.abs().max()) / max(float(og.abs().max()), floor)
+        else:                # split-bf16 tensor cores: per-tensor relative L2 (single ReLU-kink flips move single elements)
+            e = float(diff.norm()) / max(float(og.norm()), floor * og.numel() ** 0.5 * 0.1)
+        if e > worst[1]:
+            worst = (k, e)
+        assert e <= rel, (k, e)
+    print(f"C4_P0 train step [{mode}]: loss {vals['total']:.5f} (oracle {float(losses['total']):.5f}), "
+          f"worst gradient error {worst[1]:.2e} at {worst[0]}")
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-3), ("simt", 1e-3), ("bf16", 1e-2)])
+def test_control_scales_predictions_like_the_reference(mode, tol):
+    """control = {var: c}: the returned prediction is scaled, the embedding uses the UNSCALED one (model.py:434-438)"""
+    model, sd, hp = _build("C2", 21, mode)
+    batch = synthetic.make_batch(3, 12, 40, seed=21)
+    control = {"pitch": 1.5, "energy": 0.25}
+    ref = O.forward(sd, hp, batch, inference=True, control=control)
+    ref1 = O.forward(sd, hp, batch, inference=True)
+    force = {"duration_rounded": ref["duration_rounded"], "bucket_idx": {v: ref[f"_bucket_{v}"] for v in hp["variances"]}}
+    with torch.no_grad():
+        r = model(batch, inference=True, control=control, force=force)
+        r1 = model(batch, inference=True, force=force)
+    aux = 5e-2 if mode == "bf16" else 1e-4
+    for v, c in control.items():
+        assert (r[f"variances_{v}"].cpu() - ref[f"variances_{v}"]).abs().max() < aux
+        assert torch.allclose(r[f"variances_{v}"], r1[f"variances_{v}"] * c, rtol=1e-6, atol=1e-7)
+        assert (ref[f"variances_{v}"] - ref1[f"variances_{v}"] * c).abs().max() < 1e-6
+    # the mel does not depend on `control` (bucket indices come from the unscaled predictions)
+    assert torch.equal(r["mel"], r1["mel"])
+    assert (r["mel"].cpu() - ref["mel"]).abs().max() < tol
+
+
+def _save_checkpoint(model, path, optimizer=None, scheduler=None):
+    """what pl.Trainer.save_checkpoint writes: state_dict + hyper_parameters + the module's on_save_checkpoint extras"""
+    ckpt = {"state_dict": {k: v.detach().cpu() for k, v in model.state_dict().items()},
+            "hyper_parameters": dict(vars(model.hparams))}
+    if optimizer is not None:
+        ckpt["optimizer_states"] = [optimizer.state_dict()]
+        ckpt["lr_schedulers"] = [scheduler.state_dict()]
+    model.on_save_checkpoint(ckpt)
+    torch.save(ckpt, path)
+    return ckpt
+
+
+@pytest.mark.parametrize("preset", ["C2", "SMALL_TRAIN_PRIOR"])
+def test_checkpoint_round_trip_synthesises_identically(tmp_path, golden_dir, preset):
+    model, sd, hp = _build(preset, 31, "fp32")
+    model.speaker2dvector = {"spk0": [0.1] * 256}
+    batch = synthetic.make_batch(3, 10, 30, seed=31)
+    for p in hp["priors"]:
+        batch[f"priors_{p}"] = [0.3, -1.2, 2.0]
+    with torch.no_grad():
+        before = model(batch, inference=True)
+    path = os.path.join(tmp_path, "lit_model.ckpt")
+    ckpt = _save_checkpoint(model, path)
+    assert {"stats", "phone2id", "speaker2dvector"} <= set(ckpt)
+    # the keys are the reference's (golden `shapes` = state_dict of the reference module built with the same kwargs)
+    gname = {"C2": "c2_small_infer", "SMALL_TRAIN_PRIOR": "small_train_prior"}[preset]
+    ref_keys = {k for k in torch.load(os.path.join(golden_dir, gname + ".pt"), weights_only=False)["shapes"]
+                if not k.startswith("fastdiff_linear")}
+    assert set(ckpt["state_dict"]) == ref_keys, set(ckpt["state_dict"]) ^ ref_keys
+    # generate.py:106-112: no dataset, no stats -- everything comes out of the checkpoint
+    loaded = FastSpeech2.load_from_checkpoint(path, strict=False, num_workers=0)
+    assert loaded.stats == model.stats and loaded.phone2id == model.phone2id
+    assert loaded.speaker2dvector == {"spk0": [0.1] * 256}
+    loaded = loaded.eval().to(DEV)
+    with torch.no_grad():
+        after = loaded(batch, inference=True)
+    for k in ("mel", "duration_rounded", "tgt_mask", "duration_prediction"):
+        assert torch.equal(before[k], after[k]), k
+
+
+def test_checkpoint_with_mismatched_shapes_is_skipped_like_the_reference(tmp_path, capsys):
+    model, sd, hp = _build("C2", 32, "fp32")
+    path = os.path.join(tmp_path, "m.ckpt")
+    ckpt = _save_checkpoint(model, path)
+    ckpt["state_dict"]["linear.weight"] = torch.zeros(40, 256)      # wrong shape -> "Skip loading parameter"
+    ckpt["state_dict"]["not_a_parameter"] = torch.zeros(3)          # unknown key -> "Dropping parameter"
+    ckpt["optimizer_states"] = [{"state": {}}]
+    torch.save(ckpt, path)
+    loaded = FastSpeech2.load_from_checkpoint(path, strict=False, num_workers=0)
+    out = capsys.readouterr().out
+    assert "Skip loading parameter: linear.weight" in out and "Dropping parameter not_a_parameter" in out
+    assert loaded.linear.weight.shape == (80, 256)
+
+
+def test_fused_adamw_resumes_from_its_state_dict(tmp_path):
+    """3 steps straight == 2 steps, checkpoint (model + optimizer + scheduler), reload, 1 step"""
+    torch.manual_seed(5)
+
+    def steps(model, opt, sch, batch, n):
+        for _ in range(n):
+            loss = model.training_step(batch, 0)
+            loss.backward()
+            opt.step()
+            sch.step()
+
+    def make():
+        model, sd, hp = _build("SMALL_TRAIN", 41, "simt", train=True)
+        model.log_losses = False
+        (opt,), (s,) = model.configure_optimizers()
+        return model, opt, s["scheduler"], hp
+
+    a, opt_a, sch_a, hp = make()
+    batch = synthetic.add_train_targets(synthetic.make_batch(3, 8, 20, seed=41), hp["variances"], seed=41)
+    steps(a, opt_a, sch_a, batch, 3)
+    b, opt_b, sch_b, _ = make()
+    steps(b, opt_b, sch_b, batch, 2)
+    path = os.path.join(tmp_path, "resume.ckpt")
+    _save_checkpoint(b, path, opt_b, sch_b)
+    ck = torch.load(path, weights_only=False)
+    assert len(ck["optimizer_states"][0]["state"]) > 0 and float(ck["optimizer_states"][0]["state"][0]["step"]) == 2
+    # resume as litfass/train.py:241-250 does: the datasets (here: stats / phone2id) are passed again, so the modules
+    # -- and with them the optimizer's parameter indices -- are created in the constructor's order
+    c = FastSpeech2.load_from_checkpoint(path, num_workers=0, stats=b.stats, phone2id=b.phone2id)
+    c = c.to(DEV).train().set_compute_mode("simt")
+    c.log_losses = False
+    (opt_c,), (s,) = c.configure_optimizers()
+    opt_c.load_state_dict(ck["optimizer_states"][0])
+    s["scheduler"].load_state_dict(ck["lr_schedulers"][0])
+    assert opt_c.step_count == 2
+    c.zero_grad()  # torch's default set_to_none=True must not orphan the flat gradient views
+    steps(c, opt_c, s["scheduler"], batch, 1)
+    worst = 0.0
+    for (k, pa), (_, pc) in zip(a.named_parameters(), c.named_parameters()):
+        d = float((pa - pc).abs().max())
+        worst = max(worst, d / max(float(pa.abs().max()), 1e-6))
+    print(f"resume: worst relative parameter difference after the third step {worst:.2e}")
+    assert worst < 1e-5   # (fp32 atomics in the embedding / bias gradients are the only run-to-run noise)
+    # a resume WITHOUT the optimizer state would restart Adam's bias correction: the step would differ visibly
+    d, opt_d, sch_d, _ = make()
+    d.load_state_dict(b.state_dict())
+    steps(d, opt_d, sch_d, batch, 1)
+    diff = max(float((pa - pd).abs().max()) for pa, pd in zip(a.parameters(), d.parameters()))
+    assert diff > 1e-6
