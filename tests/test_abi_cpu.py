@@ -82,19 +82,23 @@ def test_unsupported_configs_raise():
         FastSpeech2(stats={}, phone2id={"a": 0}, num_workers=0, **dict(configs.C2, speaker_type="id"))
 
 
+@pytest.mark.gpu
 def test_conv2_fold_is_exact_linear_map():
-    """W_eff/b_eff (grouped 1x1 conv folded into the following pointwise conv) reproduce
-    conv2 of the reference layer on CPU."""
+    """W_eff/b_eff (grouped 1x1 conv folded into the following pointwise conv by lfs2_fold_pw_fwd) reproduce
+    conv2 of the reference layer, and two folds of the same weights give the same bits."""
     from lightningfastspeech2_b200.fastspeech2.model import ConformerEncoderLayer
 
     torch.manual_seed(0)
     layer = ConformerEncoderLayer(32, 2, conv_in=32, conv_filter_size=128, conv_kernel=(5, 1), batch_first=True,
                                   dropout=0.0, conv_depthwise=True)
-    p = layer._build_pack()
     v = torch.randn(3, 128, 11)
     ref = layer.conv2(v)
-    got = torch.einsum("nf,bft->bnt", p["w_eff"], v) + p["b_eff"][None, :, None]
+    layer = layer.cuda()
+    p = layer._build_pack()
+    got = torch.einsum("nf,bft->bnt", p["w_eff"].cpu(), v) + p["b_eff"].cpu()[None, :, None]
     assert (ref - got).abs().max() < 1e-5
+    q = layer._build_pack()
+    assert torch.equal(p["w_eff"], q["w_eff"]) and torch.equal(p["b_eff"], q["b_eff"])
 
 
 def test_noam_and_optimizer_recipe():
