@@ -179,6 +179,24 @@ LFS2_API int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch,
                                   const float* gamma, const float* beta, float eps, float* out_f32, void* out_hi,
                                   void* out_lo, int npass, const int* row_limit, int limit_extra,
                                   void* workspace, void* stream);
+/* General form of lfs2_gemm_tc(_limited):
+ *   dilation   tap spacing of the Conv1d (rows t + (j - (taps-1)/2) * dilation; HiFi-GAN's dilated ResBlock convs,
+ *              third_party/hifigan/models.py:24-57)
+ *   activation 0 none | 1 ReLU | 2 leaky ReLU with `slope` (models.py:86-93), applied after the bias
+ *   residual   res_hi/res_lo + ident_hi as in lfs2_gemm_tc; allowed without LayerNorm when npass = 3 (x = conv(.) + x)
+ *   out_kind   LFS2_OUT_PLANES: out0/out1 = bf16 hi/lo planes; LFS2_OUT_F32: out0 = fp32; LFS2_OUT_F16: out0 = ONE
+ *              fp16 plane (saturating conversion), the operand format of lfs2_attention_tc_ex(..., fp16)
+ *   row_mask   NULL or (batch, t) bytes: rows with a non-zero byte are written as zeros (PAD frames of a ragged batch)
+ *   column tiles of 256 / 128 / 64 outputs (n % 16 == 0). */
+#define LFS2_OUT_PLANES 0
+#define LFS2_OUT_F32 1
+#define LFS2_OUT_F16 2
+LFS2_API int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int t, int d, int taps, int dilation,
+                             const void* w_hi, const void* w_lo, int n, const float* bias, int activation, float slope,
+                             const void* res_hi, const void* res_lo, const void* ident_hi, const float* gamma,
+                             const float* beta, float eps, void* out0, void* out1, int out_kind, int npass,
+                             const int* row_limit, int limit_extra, void* workspace, const uint8_t* row_mask,
+                             void* stream);
 /* workspace of lfs2_gemm_tc_limited when row_limit != NULL: the compact list of active row tiles.  A later call with
  * row_limit == NULL and the same workspace reuses that list (same batch, t and limit: the layers of one predictor). */
 LFS2_API long long lfs2_gemm_tc_limited_workspace_bytes(int batch, int t);
@@ -231,6 +249,18 @@ LFS2_API int lfs2_attention_tc_limited(const void* qkv_hi, const void* qkv_lo, c
                                        void* ctx_hi, void* ctx_lo, float* ctx_f32, void* workspace, int batch, int t,
                                        int d, int nhead, int npass, const int* row_limit, int limit_extra,
                                        void* stream);
+/* Same with the operand format of qkv made explicit: LFS2_OPERAND_BF16 = bf16 hi (+ lo for npass = 3) planes;
+ * LFS2_OPERAND_F16 (npass = 1) = qkv_hi is ONE fp16 plane (written by lfs2_gemm_tc_ex(..., LFS2_OUT_F16)), Q.K^T and
+ * P.V run as single fp16 passes with P held as fp16: 11 significant bits on every operand.  Measured on the fp64
+ * goldens this keeps the mel within 1e-4 of the reference (budget 1e-3) at a third of the tensor work of npass = 3;
+ * it is what compute mode "fp32" uses by default (tools/precision_emulation.py).  ctx is written as bf16
+ * hi/lo planes and/or fp32 in every case. */
+#define LFS2_OPERAND_BF16 0
+#define LFS2_OPERAND_F16 1
+LFS2_API int lfs2_attention_tc_ex(const void* qkv_hi, const void* qkv_lo, int operand_format,
+                                  const uint8_t* key_padding_mask, void* ctx_hi, void* ctx_lo, float* ctx_f32,
+                                  void* workspace, int batch, int t, int d, int nhead, int npass, const int* row_limit,
+                                  int limit_extra, void* stream);
 
 /* out = hi + lo (fp32) for n values (n % 4 == 0): the inverse of lfs2_split_bf16 up to 2^-17 relative */
 LFS2_API int lfs2_merge_planes(const void* hi, const void* lo, float* out, long long n, void* stream);

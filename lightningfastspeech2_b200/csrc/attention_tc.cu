@@ -140,7 +140,16 @@ __device__ __forceinline__ void tma_store_3d_a(const CUtensorMap* map, const voi
                : "memory");
 }
 
-template <int NPASS>
+// two fp32 -> packed fp16 pair (element a in the low half)
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
+// FMT = operand format of Q, K, V and P: kFmtBF16 (hi [+ lo] planes) or kFmtF16 (NPASS = 1 only: ONE fp16 plane written
+// by lfs2_gemm_tc_ex(LFS2_OUT_F16); 11 significant bits instead of 8 -- see profiles/r2c_precision_emulation_*.txt)
+template <int NPASS, int FMT>
 __global__ void __launch_bounds__(kAttnTcThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                     const __grid_constant__ CUtensorMap map_q_hi, const __grid_constant__ CUtensorMap map_q_lo,
@@ -238,8 +247,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
     // registers; one elected lane issues the tcgen05 instructions.  QK products run up to
     // kSBufs tiles ahead of the PV products, so the softmax warps always find S ready.
     if (ntiles > 0) {
-      constexpr uint32_t idesc_qk = make_idesc(kFmtBF16, kAQ, kAK, 0, 0);  // A: TMEM, B: K tile, K-major
-      constexpr uint32_t idesc_pv = make_idesc(kFmtBF16, kAQ, kDH, 0, 1);  // A: TMEM, B: V tile, MN-major
+      constexpr uint32_t idesc_qk = make_idesc(FMT, kAQ, kAK, 0, 0);  // A: TMEM, B: K tile, K-major
+      constexpr uint32_t idesc_pv = make_idesc(FMT, kAQ, kDH, 0, 1);  // A: TMEM, B: V tile, MN-major
       const uint32_t tq = tmem_base + kColQ, to = tmem_base + kColO;
       const uint64_t dk0 = make_smem_desc(smem_u32(sK), 16, 512, kSwizzle64);
       const uint64_t dv0 = make_smem_desc(smem_u32(sV), 4096, 512, kSwizzle64);
@@ -431,7 +440,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         float p1 = ex2_approx(fmaf(s[2 * i + 1], c, -mc));
         lsum0 += p0;
         lsum1 += p1;
-        split_pack2(p0, p1, ph[i], pl[i]);
+        if (FMT == kFmtF16) ph[i] = pack_f16x2(p0, p1);
+        else split_pack2(p0, p1, ph[i], pl[i]);
       }
       l_run += lsum0 + lsum1;
       // P hi: first kSW/2 columns of the S buffer (bf16 pairs in key order), P lo: the other kSW/2
@@ -515,10 +525,11 @@ struct AttnMaps {
   CUtensorMap kv_hi, kv_lo, q_hi, q_lo, o_hi, o_lo;
 };
 
-template <int NPASS>
+template <int NPASS, int FMT>
 static int launch_attention_tc(const AttnMaps& m, const AttnTcParams& p, int batch, int nhead, cudaStream_t s) {
+  static_assert(FMT == kFmtBF16 || NPASS == 1, "fp16 operands are single-plane");
   constexpr int kSmem = 2 * kKVStages * (NPASS == 3 ? 2 : 1) * kTileBytes + 1024;
-  auto kern = attention_tc_kernel<NPASS>;
+  auto kern = attention_tc_kernel<NPASS, FMT>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) {
@@ -562,8 +573,17 @@ int lfs2_attention_tc(const void* qkv_hi, const void* qkv_lo, const uint8_t* key
 int lfs2_attention_tc_limited(const void* qkv_hi, const void* qkv_lo, const uint8_t* key_padding_mask, void* ctx_hi,
                               void* ctx_lo, float* ctx_f32, void* workspace, int batch, int t, int d, int nhead,
                               int npass, const int* row_limit, int limit_extra, void* stream) {
+  return lfs2_attention_tc_ex(qkv_hi, qkv_lo, LFS2_OPERAND_BF16, key_padding_mask, ctx_hi, ctx_lo, ctx_f32, workspace, batch,
+                              t, d, nhead, npass, row_limit, limit_extra, stream);
+}
+
+int lfs2_attention_tc_ex(const void* qkv_hi, const void* qkv_lo, int operand_format, const uint8_t* key_padding_mask,
+                         void* ctx_hi, void* ctx_lo, float* ctx_f32, void* workspace, int batch, int t, int d, int nhead,
+                         int npass, const int* row_limit, int limit_extra, void* stream) {
   LFS2_REQUIRE(qkv_hi && workspace, LFS2_ERR_INVALID_ARG, "attention_tc: null pointer");
   LFS2_REQUIRE(npass == 1 || npass == 3, LFS2_ERR_INVALID_ARG, "attention_tc: npass must be 1 or 3");
+  LFS2_REQUIRE(operand_format == LFS2_OPERAND_BF16 || (operand_format == LFS2_OPERAND_F16 && npass == 1),
+               LFS2_ERR_INVALID_ARG, "attention_tc: operand_format must be bf16, or fp16 with npass = 1");
   LFS2_REQUIRE(npass == 1 || qkv_lo, LFS2_ERR_INVALID_ARG, "attention_tc: npass=3 needs the lo plane");
   LFS2_REQUIRE((ctx_hi && ctx_lo) || ctx_f32, LFS2_ERR_INVALID_ARG, "attention_tc: no output");
   LFS2_REQUIRE(!ctx_hi == !ctx_lo, LFS2_ERR_INVALID_ARG, "attention_tc: ctx_hi and ctx_lo go together");
@@ -612,7 +632,9 @@ int lfs2_attention_tc_limited(const void* qkv_hi, const void* qkv_lo, const uint
   p.scale_log2e = (float)(1.4426950408889634 / sqrt((double)kDH));
   p.row_limit = row_limit;
   p.limit_extra = limit_extra;
-  return npass == 3 ? launch_attention_tc<3>(m, p, batch, nhead, s) : launch_attention_tc<1>(m, p, batch, nhead, s);
+  if (operand_format == LFS2_OPERAND_F16) return launch_attention_tc<1, kFmtF16>(m, p, batch, nhead, s);
+  return npass == 3 ? launch_attention_tc<3, kFmtBF16>(m, p, batch, nhead, s)
+                    : launch_attention_tc<1, kFmtBF16>(m, p, batch, nhead, s);
 }
 
 }  // extern "C"

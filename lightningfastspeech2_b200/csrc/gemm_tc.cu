@@ -22,6 +22,10 @@
 //   swizzled shared-memory staging buffer and leave as coalesced TMA tensor stores -- either
 //   fp32 or bf16 hi/lo planes for the next GEMM.  TMA clips rows/columns outside the tensor.
 #include <stdlib.h>
+#include <string.h>
+
+#include <mutex>
+#include <unordered_map>
 
 #include "tc_common.cuh"
 
@@ -33,13 +37,19 @@ constexpr int kBK = 32;      // k-slab: 32 bf16 = 64 bytes = one SWIZZLE_64B row
 constexpr int kGemmTcThreads = 320;  // TMA + MMA warps, 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int kStageChunk = kBM * 32 * 4;  // one 128 x 32 staging chunk: 16 KB (fp32) or 2 x 8 KB (hi | lo)
 
+enum { kOutPlanes = 0, kOutF32 = 1, kOutF16 = 2 };  // epilogue output: bf16 hi/lo planes | fp32 | ONE fp16 plane
+
 struct GemmTcParams {
   int batch, t, d, taps, half;  // A is (batch, t, d); K = taps * d
+  int dil;                      // tap spacing in rows (dilated Conv1d); 1 otherwise
   int n;                        // output columns
   int m_tiles_per_batch, n_tiles, total_tiles;
   int has_residual;             // residual planes (batch, t, n) ride as extra k-slabs against I (n x n)
   const float* bias;            // (n) or null
-  int relu;
+  int relu;                     // 0 none, 1 ReLU, 2 leaky ReLU with `slope`
+  float slope;
+  const uint8_t* row_mask;      // null, or (batch, t): rows with a non-zero byte are written as zeros (PAD frames of a
+                                //   ragged batch whose convolutions must see zeros there, like a per-utterance call would)
   const float* gamma;           // LN only (n == N_TILE)
   const float* beta;
   float eps;
@@ -146,7 +156,17 @@ struct TileWalk {
   }
 };
 
-template <int N_TILE, int NPASS, bool LN, bool OUT_F32, bool MC>
+__device__ __forceinline__ float activate(float x, int kind, float slope) {
+  return kind == 1 ? fmaxf(x, 0.f) : (kind == 2 ? (x > 0.f ? x : x * slope) : x);
+}
+// two fp32 -> packed fp16 pair (element a in the low half), saturating instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
+template <int N_TILE, int NPASS, bool LN, int OUT, bool MC>
 __global__ void __launch_bounds__(kGemmTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -225,14 +245,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #else
             mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 2 : 1) * (L::kAPlane + L::kWPlane));
 #endif
-            tma_load_3d(st, &map_a_hi, &full_bar[stage], c0, t0 + tap - p.half, b);
+            tma_load_3d(st, &map_a_hi, &full_bar[stage], c0, t0 + (tap - p.half) * p.dil, b);
             load_w(st + L::kOffWHi, &map_w_hi, &full_bar[stage], tap * p.d + c0, n0);
 #ifdef LFS2_DIAG_NO_LO_LOADS
             if (false) {
 #else
             if (NPASS == 3) {
 #endif
-              tma_load_3d(st + L::kOffALo, &map_a_lo, &full_bar[stage], c0, t0 + tap - p.half, b);
+              tma_load_3d(st + L::kOffALo, &map_a_lo, &full_bar[stage], c0, t0 + (tap - p.half) * p.dil, b);
               load_w(st + L::kOffWLo, &map_w_lo, &full_bar[stage], tap * p.d + c0, n0);
             }
           } else if (L::kHasLo) {  // residual slab: R_hi, R_lo against the identity block
@@ -330,6 +350,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       tc_fence_after();
       uint32_t taddr = tmem_base + acc * kAccCols + ((uint32_t)(quad * 32) << 16);
       float v[32];
+      const bool row_masked = p.row_mask && b < p.batch && t0 + r < p.t && p.row_mask[(size_t)b * p.t + t0 + r] != 0;
 
       float mean = 0.f, rstd = 1.f;
       if (LN) {
@@ -339,8 +360,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           tmem_ld32(taddr + c * 32, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = v[j] + vec[c * 32 + j];
-            if (p.relu) x = fmaxf(x, 0.f);
+            const float x = activate(v[j] + vec[c * 32 + j], p.relu, p.slope);
             s += x;
             q = fmaf(x, x, q);
           }
@@ -363,8 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (LN) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = v[j] + vec[c * 32 + j];
-            if (p.relu) x = fmaxf(x, 0.f);
+            const float x = activate(v[j] + vec[c * 32 + j], p.relu, p.slope);
             v[j] = (x - mean) * rstd * vec[N_TILE + c * 32 + j] + vec[2 * N_TILE + c * 32 + j];
           }
         } else if (bias_vec && col0 + 32 <= p.n) {
@@ -378,25 +397,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
           if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+            for (int j = 0; j < 32; ++j) v[j] = activate(v[j], p.relu, p.slope);
           }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             int col = col0 + j;
-            float x = v[j] + ((p.bias && col < p.n) ? __ldg(p.bias + col) : 0.f);
-            if (p.relu) x = fmaxf(x, 0.f);
-            v[j] = x;
+            v[j] = activate(v[j] + ((p.bias && col < p.n) ? __ldg(p.bias + col) : 0.f), p.relu, p.slope);
           }
+        }
+        if (row_masked) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
         uint8_t* sb = staging + (chunk_ctr & 1) * kStageChunk;
         ++chunk_ctr;
-        if (OUT_F32) {  // 128 rows x 128 B, SWIZZLE_128B: 16-byte unit i of row r lives at unit i ^ (r & 7)
+        if (OUT == kOutF32) {  // 128 rows x 128 B, SWIZZLE_128B: 16-byte unit i of row r lives at unit i ^ (r & 7)
           uint8_t* row = sb + r * 128;
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             *reinterpret_cast<float4*>(row + ((i ^ (r & 7)) << 4)) =
                 make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else if (OUT == kOutF16) {  // one 128 rows x 64 B fp16 plane, SWIZZLE_64B
+          uint32_t h[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) h[j] = pack_f16_sat(v[2 * j], v[2 * j + 1]);
+          uint8_t* rh = sb + r * 64;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            *reinterpret_cast<uint4*>(rh + ((i ^ ((r >> 1) & 3)) << 4)) = make_uint4(h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3]);
         } else {        // two 128 rows x 64 B planes, SWIZZLE_64B: unit i of row r at i ^ ((r >> 1) & 3)
           uint32_t hi[16], lo[16];
 #pragma unroll
@@ -419,7 +448,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #ifndef LFS2_DIAG_NO_STORES
         if (issuer) {
           tma_store_3d(&map_o0, sb, col0, t0, b);
-          if (!OUT_F32) tma_store_3d(&map_o1, sb + kStageChunk / 2, col0, t0, b);
+          if (OUT == kOutPlanes) tma_store_3d(&map_o1, sb + kStageChunk / 2, col0, t0, b);
           tma_store_commit();
         }
 #endif
@@ -453,8 +482,42 @@ EncodeTiledFn get_encode_tiled() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled costs ~1-2 us of host time and a launch needs up to eleven maps; a step re-issues the same
+// (pointer, shape, box) combinations over and over (weights are fixed, activations come back from the caching allocator
+// at the same addresses), so encoded maps are memoised.  A map is a pure function of its key: a stale entry cannot exist.
+struct TmapKey {
+  const void* base;
+  uint64_t d0, d1, d2;
+  uint32_t box0, box1;
+  int elem_bytes, swizzle_bytes;
+  bool operator==(const TmapKey& o) const { return memcmp(this, &o, sizeof(TmapKey)) == 0; }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    uint64_t h = 0x9E3779B97F4A7C15ull ^ reinterpret_cast<uintptr_t>(k.base);
+    const uint64_t v[5] = {k.d0, k.d1, k.d2, ((uint64_t)k.box0 << 32) | k.box1,
+                           ((uint64_t)(uint32_t)k.elem_bytes << 32) | (uint32_t)k.swizzle_bytes};
+    for (uint64_t x : v) h = (h ^ x) * 0xBF58476D1CE4E5B9ull + (h >> 29);
+    return (size_t)h;
+  }
+};
+
 bool make_tmap_3d_ex(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
                      uint32_t box0, uint32_t box1, int swizzle_bytes) {
+  static std::mutex mu;
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  TmapKey key;
+  memset(&key, 0, sizeof(key));  // padding bytes take part in the comparison
+  key.base = base; key.d0 = d0; key.d1 = d1; key.d2 = d2; key.box0 = box0; key.box1 = box1;
+  key.elem_bytes = elem_bytes; key.swizzle_bytes = swizzle_bytes;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return true;
+    }
+  }
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
   cuuint64_t dims[3] = {d0, d1, d2};
@@ -467,7 +530,11 @@ bool make_tmap_3d_ex(CUtensorMap* out, const void* base, int elem_bytes, uint64_
   CUresult r = enc(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
+  if (r != CUDA_SUCCESS) return false;
+  std::lock_guard<std::mutex> lock(mu);
+  if (cache.size() >= 16384) cache.clear();
+  cache.emplace(key, *out);
+  return true;
 }
 
 bool make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0,
@@ -479,10 +546,10 @@ struct GemmTcMaps {
   CUtensorMap ah, al, wh, wl, rh, rl, ident, o0, o1;
 };
 
-template <int N_TILE, int NPASS, bool LN, bool OUT_F32, bool MC>
+template <int N_TILE, int NPASS, bool LN, int OUT, bool MC>
 static int launch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, cudaStream_t s) {
   using L = SmemLayout<N_TILE, NPASS, LN>;
-  auto kern = gemm_tc_kernel<N_TILE, NPASS, LN, OUT_F32, MC>;
+  auto kern = gemm_tc_kernel<N_TILE, NPASS, LN, OUT, MC>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
@@ -518,10 +585,15 @@ static int launch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, cudaStream
 }
 
 template <int N_TILE, bool LN, bool MC>
-static int dispatch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, int npass, bool out_f32, cudaStream_t s) {
-  if (npass == 3)
-    return out_f32 ? launch_gemm_tc<N_TILE, 3, LN, true, MC>(m, p, s) : launch_gemm_tc<N_TILE, 3, LN, false, MC>(m, p, s);
-  return out_f32 ? launch_gemm_tc<N_TILE, 1, LN, true, MC>(m, p, s) : launch_gemm_tc<N_TILE, 1, LN, false, MC>(m, p, s);
+static int dispatch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, int npass, int out_kind, cudaStream_t s) {
+  if (npass == 3) {
+    if (out_kind == kOutF32) return launch_gemm_tc<N_TILE, 3, LN, kOutF32, MC>(m, p, s);
+    if (out_kind == kOutF16) return launch_gemm_tc<N_TILE, 3, LN, kOutF16, MC>(m, p, s);
+    return launch_gemm_tc<N_TILE, 3, LN, kOutPlanes, MC>(m, p, s);
+  }
+  if (out_kind == kOutF32) return launch_gemm_tc<N_TILE, 1, LN, kOutF32, MC>(m, p, s);
+  if (out_kind == kOutF16) return launch_gemm_tc<N_TILE, 1, LN, kOutF16, MC>(m, p, s);
+  return launch_gemm_tc<N_TILE, 1, LN, kOutPlanes, MC>(m, p, s);
 }
 
 // LFS2_GEMM_MULTICAST=0 switches the 2-CTA weight multicast off (A/B measurements)
@@ -559,34 +631,50 @@ int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch, int t, i
                          const void* ident_hi, const float* gamma, const float* beta, float eps, float* out_f32,
                          void* out_hi, void* out_lo, int npass, const int* row_limit, int limit_extra,
                          void* workspace, void* stream) {
-  LFS2_REQUIRE(a_hi && w_hi, LFS2_ERR_INVALID_ARG, "gemm_tc: null operand");
-  LFS2_REQUIRE(npass == 1 || npass == 3, LFS2_ERR_INVALID_ARG, "gemm_tc: npass must be 1 or 3");
-  LFS2_REQUIRE(npass == 1 || (a_lo && w_lo), LFS2_ERR_INVALID_ARG, "gemm_tc: npass=3 needs the lo planes");
-  if (batch == 0 || t == 0) return LFS2_OK;
-  LFS2_REQUIRE(batch > 0 && t > 0 && d > 0 && n > 0 && taps > 0, LFS2_ERR_INVALID_ARG, "gemm_tc: bad shape");
-  LFS2_REQUIRE(taps % 2 == 1, LFS2_ERR_UNSUPPORTED, "gemm_tc: kernel size %d must be odd", taps);
-  LFS2_REQUIRE(d % kBK == 0, LFS2_ERR_UNSUPPORTED, "gemm_tc: d=%d must be a multiple of %d", d, kBK);
-  LFS2_REQUIRE(n % 16 == 0, LFS2_ERR_UNSUPPORTED, "gemm_tc: n=%d must be a multiple of 16", n);
   LFS2_REQUIRE((out_f32 != nullptr) != (out_hi != nullptr), LFS2_ERR_INVALID_ARG,
                "gemm_tc: exactly one of out_f32 / out_hi+out_lo");
   LFS2_REQUIRE(!out_hi || out_lo, LFS2_ERR_INVALID_ARG, "gemm_tc: out_hi without out_lo");
+  return lfs2_gemm_tc_ex(a_hi, a_lo, batch, t, d, taps, 1, w_hi, w_lo, n, bias, relu ? 1 : 0, 0.f, res_hi, res_lo,
+                         ident_hi, gamma, beta, eps, out_f32 ? (void*)out_f32 : out_hi, out_lo,
+                         out_f32 ? LFS2_OUT_F32 : LFS2_OUT_PLANES, npass, row_limit, limit_extra, workspace, nullptr,
+                         stream);
+}
+
+int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int t, int d, int taps, int dilation,
+                    const void* w_hi, const void* w_lo, int n, const float* bias, int activation, float slope,
+                    const void* res_hi, const void* res_lo, const void* ident_hi, const float* gamma, const float* beta,
+                    float eps, void* out0, void* out1, int out_kind, int npass, const int* row_limit, int limit_extra,
+                    void* workspace, const uint8_t* row_mask, void* stream) {
+  LFS2_REQUIRE(a_hi && w_hi && out0, LFS2_ERR_INVALID_ARG, "gemm_tc: null operand");
+  LFS2_REQUIRE(npass == 1 || npass == 3, LFS2_ERR_INVALID_ARG, "gemm_tc: npass must be 1 or 3");
+  LFS2_REQUIRE(npass == 1 || (a_lo && w_lo), LFS2_ERR_INVALID_ARG, "gemm_tc: npass=3 needs the lo planes");
+  LFS2_REQUIRE(out_kind == LFS2_OUT_PLANES || out_kind == LFS2_OUT_F32 || out_kind == LFS2_OUT_F16, LFS2_ERR_INVALID_ARG,
+               "gemm_tc: out_kind must be LFS2_OUT_PLANES, LFS2_OUT_F32 or LFS2_OUT_F16");
+  LFS2_REQUIRE(out_kind != LFS2_OUT_PLANES || out1, LFS2_ERR_INVALID_ARG, "gemm_tc: plane output needs out1 (the lo plane)");
+  LFS2_REQUIRE(activation >= 0 && activation <= 2, LFS2_ERR_INVALID_ARG, "gemm_tc: activation must be 0, 1 or 2");
+  if (batch == 0 || t == 0) return LFS2_OK;
+  LFS2_REQUIRE(batch > 0 && t > 0 && d > 0 && n > 0 && taps > 0 && dilation > 0, LFS2_ERR_INVALID_ARG, "gemm_tc: bad shape");
+  LFS2_REQUIRE(taps % 2 == 1, LFS2_ERR_UNSUPPORTED, "gemm_tc: kernel size %d must be odd", taps);
+  LFS2_REQUIRE(d % kBK == 0, LFS2_ERR_UNSUPPORTED, "gemm_tc: d=%d must be a multiple of %d", d, kBK);
+  LFS2_REQUIRE(n % 16 == 0, LFS2_ERR_UNSUPPORTED, "gemm_tc: n=%d must be a multiple of 16", n);
   LFS2_REQUIRE(aligned16(a_hi) && aligned16(w_hi) && (!a_lo || aligned16(a_lo)) && (!w_lo || aligned16(w_lo)) &&
-                   (!out_f32 || aligned16(out_f32)) && (!out_hi || (aligned16(out_hi) && aligned16(out_lo))) &&
-                   (!res_hi || (aligned16(res_hi) && aligned16(res_lo))),
+                   aligned16(out0) && (!out1 || aligned16(out1)) && (!res_hi || (aligned16(res_hi) && aligned16(res_lo))),
                LFS2_ERR_INVALID_ARG, "gemm_tc: pointers must be 16-byte aligned");
   const bool ln = gamma != nullptr;
   LFS2_REQUIRE(!ln || beta, LFS2_ERR_INVALID_ARG, "gemm_tc: gamma without beta");
-  LFS2_REQUIRE(!res_hi || (ln && res_lo && ident_hi), LFS2_ERR_UNSUPPORTED,
-               "gemm_tc: the residual (hi, lo planes + identity) is only fused with LayerNorm");
-  LFS2_REQUIRE(!res_hi || !relu, LFS2_ERR_UNSUPPORTED, "gemm_tc: relu with a residual is not a reference pattern");
-  int n_tile = ln ? n : (n % 256 == 0 ? 256 : 128);
+  LFS2_REQUIRE(!res_hi || (res_lo && ident_hi), LFS2_ERR_INVALID_ARG, "gemm_tc: the residual needs hi, lo planes and the identity");
+  // (the residual slabs use the lo-plane slot of a pipeline stage, which exists in 3-pass and LayerNorm builds)
+  LFS2_REQUIRE(!res_hi || ln || npass == 3, LFS2_ERR_UNSUPPORTED,
+               "gemm_tc: a residual without LayerNorm needs npass = 3");
+  LFS2_REQUIRE(!res_hi || !activation, LFS2_ERR_UNSUPPORTED, "gemm_tc: an activation after the residual add is not a reference pattern");
+  int n_tile = ln ? n : (n % 256 == 0 ? 256 : (n > 64 ? 128 : 64));
   {  // LFS2_GEMM_NTILE=128: A/B knob (tools/gemm_ab.py) -- narrower column tiles for the plain epilogue
     static int forced = -1;
     if (forced < 0) {
       const char* e = getenv("LFS2_GEMM_NTILE");
       forced = e ? atoi(e) : 0;
     }
-    if (!ln && forced == 128) n_tile = 128;
+    if (!ln && forced == 128 && n_tile == 256) n_tile = 128;
   }
   if (ln) LFS2_REQUIRE(n == 256, LFS2_ERR_UNSUPPORTED, "gemm_tc: LayerNorm epilogue needs n == 256 (got %d)", n);
 
@@ -612,23 +700,26 @@ int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch, int t, i
     m.rl = m.ah;
     m.ident = m.wh;
   }
-  if (out_f32) {
-    ok = ok && make_tmap_3d_ex(&m.o0, out_f32, 4, n, t, batch, 32, kBM, 128);
+  if (out_kind == LFS2_OUT_F32) {
+    ok = ok && make_tmap_3d_ex(&m.o0, out0, 4, n, t, batch, 32, kBM, 128);
     m.o1 = m.o0;
-  } else {
-    ok = ok && make_tmap_3d(&m.o0, out_hi, n, t, batch, 32, kBM, 64) && make_tmap_3d(&m.o1, out_lo, n, t, batch, 32, kBM, 64);
+  } else {  // 16-bit planes (bf16 hi/lo, or one fp16 plane: the map only moves bytes)
+    ok = ok && make_tmap_3d(&m.o0, out0, n, t, batch, 32, kBM, 64);
+    if (out_kind == LFS2_OUT_PLANES) ok = ok && make_tmap_3d(&m.o1, out1, n, t, batch, 32, kBM, 64);
+    else m.o1 = m.o0;
   }
   LFS2_REQUIRE(ok, LFS2_ERR_CUDA, "gemm_tc: cuTensorMapEncodeTiled failed (driver entry point %s)",
                get_encode_tiled() ? "found" : "missing");
 
   GemmTcParams p;
-  p.batch = batch; p.t = t; p.d = d; p.taps = taps; p.half = (taps - 1) / 2;
+  p.batch = batch; p.t = t; p.d = d; p.taps = taps; p.half = (taps - 1) / 2; p.dil = dilation;
   p.n = n;
   p.m_tiles_per_batch = (t + kBM - 1) / kBM;
   p.n_tiles = (n + n_tile - 1) / n_tile;
   p.total_tiles = batch * p.m_tiles_per_batch * p.n_tiles;
   p.has_residual = res_hi != nullptr;
-  p.bias = bias; p.relu = relu; p.gamma = gamma; p.beta = beta; p.eps = eps;
+  p.bias = bias; p.relu = activation; p.slope = slope; p.row_mask = row_mask;
+  p.gamma = gamma; p.beta = beta; p.eps = eps;
   cudaStream_t s = (cudaStream_t)stream;
   p.tile_list = nullptr;
   if (!row_limit && workspace) {
@@ -645,12 +736,13 @@ int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch, int t, i
     p.tile_list = list;
   }
   if (mc) {
-    if (ln) return dispatch_gemm_tc<256, true, true>(m, p, npass, out_f32 != nullptr, s);
-    return dispatch_gemm_tc<256, false, true>(m, p, npass, out_f32 != nullptr, s);
+    if (ln) return dispatch_gemm_tc<256, true, true>(m, p, npass, out_kind, s);
+    return dispatch_gemm_tc<256, false, true>(m, p, npass, out_kind, s);
   }
-  if (ln) return dispatch_gemm_tc<256, true, false>(m, p, npass, out_f32 != nullptr, s);
-  if (n_tile == 256) return dispatch_gemm_tc<256, false, false>(m, p, npass, out_f32 != nullptr, s);
-  return dispatch_gemm_tc<128, false, false>(m, p, npass, out_f32 != nullptr, s);
+  if (ln) return dispatch_gemm_tc<256, true, false>(m, p, npass, out_kind, s);
+  if (n_tile == 256) return dispatch_gemm_tc<256, false, false>(m, p, npass, out_kind, s);
+  if (n_tile == 128) return dispatch_gemm_tc<128, false, false>(m, p, npass, out_kind, s);
+  return dispatch_gemm_tc<64, false, false>(m, p, npass, out_kind, s);
 }
 
 // x (n) fp32 -> hi/lo bf16 planes

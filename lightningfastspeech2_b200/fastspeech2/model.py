@@ -128,6 +128,11 @@ class ConformerEncoderLayer(nn.Module):
 
     compute_mode = "fp32"
     fused_ffn = True
+    # Attention operands in compute mode "fp32": "f16" = the QKV GEMM (3-pass split-bf16, fp32 accumulate) writes q, k, v
+    # as ONE fp16 plane and Q.K^T / P.V run as single fp16 tensor-core passes (11 significant bits per operand: mel error
+    # ~6e-5 against the 1e-3 budget, tools/precision_emulation.py; a third of the attention MMAs and half of the qkv
+    # traffic); "x3" = q, k, v and P as bf16 hi/lo planes, three passes per product (~1.4e-5).
+    attention_operands = "f16"
 
     # -- weight repacks -------------------------------------------------------------------
     def _build_pack_tc(self):
@@ -226,8 +231,9 @@ class ConformerEncoderLayer(nn.Module):
         if d != 256:
             return ops.planes_of(self._forward_tc_unfused_ln(ops.merge_planes(xp), xp, kpm, npass))
         if d // self.nhead == 128:
-            qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="planes", npass=npass, tag="qkv_gemm",
-                              row_limit=row_limit)
+            f16 = self.compute_mode == "fp32" and self.attention_operands == "f16"
+            qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="f16" if f16 else "planes", npass=npass,
+                              tag="qkv_gemm", row_limit=row_limit)
             _, ctx = ops.attention_tc(qkv, kpm, self.nhead, npass=npass, row_limit=row_limit)
         else:
             ctx = self._attention_any_head_dim(xp, kpm, npass)

@@ -386,21 +386,26 @@ def _identity_planes(n, device):
     return _IDENT[key]
 
 
+OUT_KINDS = {"planes": 0, "f32": 1, "f16": 2}
+
+
 def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None, eps=LN_EPS, out="f32",
-            npass=3, tag=None, row_limit=None):
+            npass=3, tag=None, row_limit=None, dilation=1, leaky_slope=None, row_mask=None):
     """a: Planes (B,T,d) [taps>1: Conv1d over T per utterance] or (...,d) for taps == 1;
-    w: Planes (n, taps*d); residual: Planes shaped like the output (added on the tensor core,
-    LayerNorm epilogues only).  out = "f32" -> fp32 tensor, "planes" -> Planes; shaped like a
-    with last dim n."""
+    w: Planes (n, taps*d); residual: Planes shaped like the output (added on the tensor core).
+    out = "f32" -> fp32 tensor, "planes" -> Planes (bf16 hi/lo), "f16" -> Planes(hi = ONE fp16 tensor, lo = None: the
+    operand of the single-pass fp16 attention); shaped like a with last dim n.
+    dilation: tap spacing (dilated Conv1d); leaky_slope: leaky ReLU instead of ReLU; row_mask (B,T) bool: rows written
+    as zeros (PAD frames of a ragged batch)."""
     if not isinstance(a, Planes) or not isinstance(w, Planes):
         raise TypeError("gemm_tc: operands must be Planes (see split_bf16)")
-    if out not in ("f32", "planes"):
-        raise ValueError("gemm_tc: out must be 'f32' or 'planes'")
+    if out not in OUT_KINDS:
+        raise ValueError("gemm_tc: out must be 'f32', 'planes' or 'f16'")
     d = a.shape[-1]
     n = w.shape[0]
     if w.shape[1] != taps * d:
         raise ValueError(f"gemm_tc: weight {tuple(w.shape)} does not match taps*d = {taps * d}")
-    if taps == 1 and row_limit is None:
+    if taps == 1 and row_limit is None and row_mask is None:
         batch, t = 1, a.hi.numel() // d
     else:
         if a.hi.dim() != 3:
@@ -414,12 +419,18 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
     of = (torch.zeros if row_limit is not None else torch.empty)(out_shape, device=dev, dtype=torch.float32) \
         if out == "f32" else None
     po = _empty_planes(out_shape, dev) if out == "planes" else None
+    if out == "f16":
+        po = Planes(torch.empty(out_shape, device=dev, dtype=torch.float16), None)
     ident = None
     if residual is not None:
         if not isinstance(residual, Planes) or tuple(residual.shape) != out_shape:
             raise ValueError("gemm_tc: residual must be Planes shaped like the output")
         _chk(residual.hi, torch.bfloat16, "gemm_tc residual"); _chk(residual.lo, torch.bfloat16, "gemm_tc residual")
         ident = _identity_planes(n, dev)
+    if row_mask is not None:
+        _chk(row_mask, torch.bool, "gemm_tc row mask", 2)
+        if tuple(row_mask.shape) != (batch, t):
+            raise ValueError("gemm_tc: row_mask must be (B, T)")
     m = batch * t
     lim, extra = (row_limit[0], row_limit[1]) if row_limit is not None else (None, 0)
     m = m * _limited_fraction(row_limit, t)  # rows really processed (for the flop / byte accounting below)
@@ -434,12 +445,15 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
             ws = torch.empty(_lib.lib().lfs2_gemm_tc_limited_workspace_bytes(batch, t) // 4, device=dev, dtype=torch.int32)
             if cache is not None:
                 cache[key] = ws
-    _launch("lfs2_gemm_tc_limited", _p(a.hi), _p(a.lo), batch, t, d, taps, _p(w.hi), _p(w.lo), n, _p(bias), int(relu),
-            _p(residual.hi if residual is not None else None), _p(residual.lo if residual is not None else None),
-            _p(ident), _p(gamma), _p(beta), float(eps), _p(of), _p(po.hi if po else None),
-            _p(po.lo if po else None), npass, _p(lim), int(extra), _p(ws), _s(), tag=tag or f"gemm_tc_n{n}_k{taps * d}",
+    act = 0 if not (relu or leaky_slope is not None) else (2 if leaky_slope is not None else 1)
+    out_bytes = {"f32": 4.0, "planes": 4.0, "f16": 2.0}[out]
+    _launch("lfs2_gemm_tc_ex", _p(a.hi), _p(a.lo), batch, t, d, taps, int(dilation), _p(w.hi), _p(w.lo), n, _p(bias), act,
+            float(leaky_slope or 0.0), _p(residual.hi if residual is not None else None),
+            _p(residual.lo if residual is not None else None), _p(ident), _p(gamma), _p(beta), float(eps),
+            _p(of if of is not None else po.hi), _p(po.lo if out == "planes" else None), OUT_KINDS[out], npass, _p(lim),
+            int(extra), _p(ws), _p(row_mask), _s(), tag=tag or f"gemm_tc_n{n}_k{taps * d}",
             flops=2.0 * m * n * taps * d,
-            nbytes=4.0 * m * d + 4.0 * n * taps * d + 4.0 * m * n + (4.0 * m * n if residual is not None else 0.0))
+            nbytes=4.0 * m * d + 4.0 * n * taps * d + out_bytes * m * n + (4.0 * m * n if residual is not None else 0.0))
     return of if out == "f32" else po
 
 
@@ -482,12 +496,19 @@ def ffn_fused_tc(u, w1, b1, w2, b2, residual, gamma, beta, eps=LN_EPS, npass=3, 
 
 
 def attention_tc(qkv, kpm, nhead, npass=3, want_f32=False, want_planes=True, row_limit=None):
-    """qkv: Planes (B,T,3d) packed [q|k|v]; kpm (B,T) bool True=PAD -> (ctx f32 or None, ctx Planes or None).
+    """qkv: Planes (B,T,3d) packed [q|k|v] -- bf16 hi/lo planes, or ONE fp16 plane (Planes(hi = fp16 tensor, lo = None)
+    from gemm_tc(out="f16"): single-pass fp16 products, npass is ignored); kpm (B,T) bool True=PAD ->
+    (ctx f32 or None, ctx Planes or None).
     row_limit = (lengths int32 (B), extra, ...): 128-row query tiles starting at or after lengths[b] + extra are
     skipped (their ctx rows stay unwritten)."""
     if not isinstance(qkv, Planes):
         raise TypeError("attention_tc: qkv must be Planes")
-    _chk(qkv.hi, torch.bfloat16, "qkv.hi", 3); _chk(qkv.lo, torch.bfloat16, "qkv.lo", 3)
+    f16 = qkv.hi.dtype == torch.float16
+    if f16:
+        _chk(qkv.hi, torch.float16, "qkv (fp16 plane)", 3)
+        npass = 1
+    else:
+        _chk(qkv.hi, torch.bfloat16, "qkv.hi", 3); _chk(qkv.lo, torch.bfloat16, "qkv.lo", 3)
     b, t, d3 = qkv.shape
     d = d3 // 3
     if kpm is not None:
@@ -505,10 +526,11 @@ def attention_tc(qkv, kpm, nhead, npass=3, want_f32=False, want_planes=True, row
             rows = torch.clamp((lim.long() + extra + 127) // 128 * 128, min=0, max=t).double()
             frac = float(rows.sum()) / float(b * t)
         fl = float(4.0 * d * (rows * nkeys.to(dev)).sum())
-    _launch("lfs2_attention_tc_limited", _p(qkv.hi), _p(qkv.lo), _p(kpm), _p(po.hi if po else None),
+    in_bytes = (2.0 if f16 else 4.0) * qkv.hi.numel()
+    _launch("lfs2_attention_tc_ex", _p(qkv.hi), _p(qkv.lo), 1 if f16 else 0, _p(kpm), _p(po.hi if po else None),
             _p(po.lo if po else None), _p(ctx), _p(ws), b, t, d, nhead, npass, _p(lim), int(extra), _s(),
             tag="lfs2_attention_tc", flops=fl,
-            nbytes=(4.0 * qkv.hi.numel() + 4.0 * b * t * d * (int(want_f32) + int(want_planes))) * frac)
+            nbytes=(in_bytes + 4.0 * b * t * d * (int(want_f32) + int(want_planes))) * frac)
     return ctx, po
 
 

@@ -103,3 +103,35 @@ def test_query_row_limit_skips_tiles_and_keeps_the_rest(npass):
         keep = min(t, (n + extra + 127) // 128 * 128)
         assert torch.equal(part[i, :keep], full[i, :keep]), i
         assert torch.equal(pp.hi[i, :keep], part[i, :keep].bfloat16())
+
+
+# ---- single-pass fp16 operands (compute mode "fp32" default: q, k, v as ONE fp16 plane, P as fp16)
+@pytest.mark.parametrize("b,t,lens", [(2, 200, [200, 77]), (3, 1, None), (2, 700, [700, 333]), (4, 257, [257, 256, 65, 3])])
+def test_fp16_operands_match_fp64(b, t, lens):
+    d, nhead = 256, 2
+    qkv, kpm = make(b, t, d, seed=t + b, lens=lens)
+    q16 = qkv.half()
+    ref = ref_attention(q16.float(), kpm, nhead)       # the fp16-rounded inputs are the kernel's inputs
+    ctx, cp = ops.attention_tc(ops.Planes(q16.to(DEV), None), None if kpm is None else kpm.to(DEV), nhead, want_f32=True)
+    err = (ctx.cpu() - ref).abs().max()
+    assert err < 2e-3, float(err)                     # P in fp16: 2^-12 relative per probability, O(1) values
+    assert (cp.float().cpu() - ctx.cpu()).abs().max() < 1e-4
+    # and against the UNROUNDED inputs the error stays an order of magnitude below the bf16 mode's
+    ref_full = ref_attention(qkv, kpm, nhead)
+    bf = ops.attention_tc(ops.split_bf16(qkv.to(DEV)), None if kpm is None else kpm.to(DEV), nhead, npass=1, want_f32=True)[0]
+    e16, ebf = (ctx.cpu() - ref_full).abs().max(), (bf.cpu() - ref_full).abs().max()
+    print(f"attention t={t}: max err fp16 operands {float(e16):.2e}, bf16 operands {float(ebf):.2e}")
+    assert e16 < 4e-3 and (t < 8 or e16 < 0.5 * ebf)
+
+
+def test_fp16_operands_row_limit_and_masks():
+    b, t, d, nhead = 3, 400, 256, 2
+    lens = [400, 100, 333]
+    qkv, kpm = make(b, t, d, seed=12, lens=lens)
+    planes = ops.Planes(qkv.half().to(DEV), None)
+    full, _ = ops.attention_tc(planes, kpm.to(DEV), nhead, want_f32=True)
+    lim = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    part, _ = ops.attention_tc(planes, kpm.to(DEV), nhead, want_f32=True, row_limit=(lim, 28))
+    for i, n in enumerate(lens):
+        keep = min(t, (n + 28 + 127) // 128 * 128)
+        assert torch.equal(part[i, :keep], full[i, :keep]), i

@@ -193,3 +193,52 @@ def test_two_cta_multicast_path(npass):
     for i, ln_ in enumerate(lens.tolist()):
         keep = min(t, (ln_ + 28 + 127) // 128 * 128)
         assert torch.equal(part.hi[i, :keep], full.hi[i, :keep]) and torch.equal(part.lo[i, :keep], full.lo[i, :keep]), i
+
+
+# ---- lfs2_gemm_tc_ex: fp16 output plane, dilation, leaky ReLU, residual without LayerNorm, row mask, 64-column tiles
+@pytest.mark.parametrize("m,n,k", [(300, 768, 256), (129, 80, 256), (4000, 768, 256)])
+def test_f16_output_plane(m, n, k):
+    a, w, b = rnd(m, k, seed=31), rnd(n, k, seed=32, scale=k ** -0.5), rnd(n, seed=33, scale=0.1)
+    ref = F.linear(a.double(), w.double(), b.double())
+    p = ops.gemm_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV), out="f16")
+    assert p.lo is None and p.hi.dtype == torch.float16 and tuple(p.hi.shape) == (m, n)
+    # the fp32 accumulator rounded once to fp16: half an ulp of 11 significant bits
+    assert ((p.hi.double().cpu() - ref).abs() <= 2.0 ** -11 * ref.abs() + 2e-4).all()
+    f32 = ops.gemm_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV))
+    assert torch.equal(p.hi, f32.half())
+
+
+def test_f16_output_saturates_instead_of_overflowing():
+    a, w = torch.full((128, 32), 300.0), torch.full((16, 32), 300.0)
+    p = ops.gemm_tc(ops.split_bf16(a.to(DEV)), ops.split_bf16(w.to(DEV)), None, out="f16")
+    assert torch.isfinite(p.hi).all() and float(p.hi.max()) == 65504.0
+
+
+@pytest.mark.parametrize("bsz,t,c,n,ks,dil", [(2, 300, 64, 64, 3, 5), (1, 513, 128, 128, 7, 3), (3, 200, 32, 32, 11, 5),
+                                              (2, 140, 256, 256, 3, 1), (1, 77, 512, 256, 7, 1)])
+def test_dilated_conv_leaky_relu_and_residual(bsz, t, c, n, ks, dil):
+    """HiFi-GAN ResBlock pieces (third_party/hifigan/models.py:86-93): dilated 'same' conv, leaky ReLU epilogue,
+    x + conv(.) with the residual on the tensor core, narrow channel counts (64-column tiles)"""
+    x, w, b = rnd(bsz, t, c, seed=41), rnd(n, c, ks, seed=42, scale=(c * ks) ** -0.5), rnd(n, seed=43, scale=0.1)
+    conv = F.conv1d(x.double().transpose(1, 2), w.double(), b.double(), padding=dil * (ks - 1) // 2,
+                    dilation=dil).transpose(1, 2)
+    wp = ops.split_bf16(w.permute(0, 2, 1).reshape(n, ks * c).contiguous().to(DEV))
+    xp = ops.split_bf16(x.to(DEV))
+    out = ops.gemm_tc(xp, wp, b.to(DEV), taps=ks, dilation=dil, leaky_slope=0.1)
+    assert (out.cpu() - F.leaky_relu(conv, 0.1)).abs().max() < 2e-4
+    if n == c:
+        res = ops.gemm_tc(xp, wp, b.to(DEV), taps=ks, dilation=dil, residual=xp, out="planes")
+        assert (res.float().cpu() - (conv + x.double())).abs().max() < 3e-4
+
+
+def test_row_mask_writes_zero_rows():
+    bsz, t, c, n = 3, 260, 64, 128
+    x, w, b = rnd(bsz, t, c, seed=44), rnd(n, c, seed=45, scale=c ** -0.5), rnd(n, seed=46)
+    lens = torch.tensor([260, 100, 1])
+    mask = (torch.arange(t)[None, :] >= lens[:, None]).to(DEV)
+    full = ops.gemm_tc(ops.split_bf16(x.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV), taps=1, row_mask=None)
+    out = ops.gemm_tc(ops.split_bf16(x.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV), taps=1, row_mask=mask)
+    pl = ops.gemm_tc(ops.split_bf16(x.to(DEV)), ops.split_bf16(w.to(DEV)), b.to(DEV), taps=1, row_mask=mask, out="planes")
+    full = full.view(bsz, t, n)
+    assert torch.equal(out[~mask], full[~mask]) and float(out[mask].abs().max()) == 0.0
+    assert float(pl.hi[mask].abs().max()) == 0.0 and float(pl.lo[mask].abs().max()) == 0.0

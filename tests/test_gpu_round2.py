@@ -44,6 +44,7 @@ def test_c4_train_step_matches_oracle(mode, rel):
     total.backward()
     torch.cuda.synchronize()
     losses, ograds = O.gradients(sd, hp, batch)
+    _, ograds64 = O.gradients(sd, hp, batch, dtype=torch.float64)   # yardstick: how far fp32 itself is from the truth
     vals = dict(zip(list(hp["variances"]) + ["mel", "duration", "total"], model.loss.last_buffer.tolist()))
     for k, v in losses.items():
         assert abs(vals[k] - float(v)) <= 1e-4 * max(1.0, abs(float(v))), (k, vals[k], float(v))
@@ -51,18 +52,26 @@ def test_c4_train_step_matches_oracle(mode, rel):
     assert set(ograds) <= set(grads)
     scale = max(float(g.abs().max()) for g in ograds.values())
     floor = (1e-3 if mode == "simt" else 1e-2) * scale
-    worst = ("", 0.0)
-    for k, og in ograds.items():
-        diff = grads[k].cpu() - og
+    worst, worst_ref = ("", 0.0), 0.0
+
+    def err(got, want):
+        diff = got.double() - want
         if mode == "simt":   # exact-fp32 kernels: element by element
-            e = float(diff.abs().max()) / max(float(og.abs().max()), floor)
-        else:                # split-bf16 tensor cores: per-tensor relative L2 (single ReLU-kink flips move single elements)
-            e = float(diff.norm()) / max(float(og.norm()), floor * og.numel() ** 0.5 * 0.1)
+            return float(diff.abs().max()) / max(float(want.abs().max()), floor)
+        # split-bf16 tensor cores: per-tensor relative L2 (single ReLU-kink flips move single elements)
+        return float(diff.norm()) / max(float(want.norm()), floor * want.numel() ** 0.5 * 0.1)
+
+    for k, og in ograds.items():
+        e = err(grads[k].cpu(), ograds64[k])          # this path vs the fp64 gradients
+        e_ref = err(og, ograds64[k])                   # the reference's own fp32 arithmetic (CPU) vs the same
+        worst_ref = max(worst_ref, e_ref)
         if e > worst[1]:
             worst = (k, e)
-        assert e <= rel, (k, e)
-    print(f"C4_P0 train step [{mode}]: loss {vals['total']:.5f} (oracle {float(losses['total']):.5f}), "
-          f"worst gradient error {worst[1]:.2e} at {worst[0]}")
+        # within `rel`, or -- where 13 layers of fp32 round-off already cost the reference more than that -- no worse
+        # than 3x the reference's own fp32 error on that tensor
+        assert e <= max(rel, 3.0 * e_ref), (k, e, e_ref)
+    print(f"C4_P0 train step [{mode}]: loss {vals['total']:.5f} (oracle {float(losses['total']):.5f}), worst gradient "
+          f"error vs fp64 {worst[1]:.2e} at {worst[0]} (the oracle's own fp32 run: worst {worst_ref:.2e})")
 
 
 @pytest.mark.parametrize("mode,tol", [("fp32", 1e-3), ("simt", 1e-3), ("bf16", 1e-2)])
@@ -190,3 +199,31 @@ def test_fused_adamw_resumes_from_its_state_dict(tmp_path):
     steps(d, opt_d, sch_d, batch, 1)
     diff = max(float((pa - pd).abs().max()) for pa, pd in zip(a.parameters(), d.parameters()))
     assert diff > 1e-6
+
+
+@pytest.mark.parametrize("name", ["c1_infer", "c2_small_infer"])
+def test_attention_operand_recipes_against_the_fp64_goldens(golden_dir, name):
+    """compute mode "fp32": q, k, v / P as ONE fp16 plane, single-pass products (default) vs bf16 hi/lo planes, three
+    passes ("x3").  Gate: max |mel - fp64 reference| <= 2e-4, i.e. >= 5x margin to the 1e-3
+    budget, on every position the reference defines."""
+    from lightningfastspeech2_b200.fastspeech2.model import ConformerEncoderLayer
+
+    g = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
+    kw = configs.PRESETS[g["preset"]]
+    hp = configs.resolve(kw)
+    st = {v: dict(g["stats"]) for v in hp["variances"]}
+    model = FastSpeech2(stats=st, phone2id={f"p{i}": i for i in range(80)}, fastdiff_head=True, num_workers=0, **kw)
+    model.load_state_dict(synthetic.fill_state_dict(g["shapes"], seed=g["seed"], stats=g["stats"]), strict=True)
+    model = model.eval().to(DEV)
+    force = {"duration_rounded": g["out"]["duration_rounded"], "bucket_idx": dict(g["bucket_idx"])}
+    errs = {}
+    try:
+        for recipe in ("f16", "x3"):
+            ConformerEncoderLayer.attention_operands = recipe
+            with torch.no_grad():
+                r = model(g["batch"], inference=True, force=force)
+            errs[recipe] = float((r["mel"].cpu().double() - g["out64_mel"]).abs().max())
+    finally:
+        ConformerEncoderLayer.attention_operands = "f16"
+    print(f"{name}: max |mel - fp64| with fp16 single-pass attention {errs['f16']:.2e}, 3-pass split-bf16 {errs['x3']:.2e}")
+    assert errs["x3"] < 1e-4 and errs["f16"] < 2e-4, errs
