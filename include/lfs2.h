@@ -443,6 +443,28 @@ LFS2_API int lfs2_adamw_step(float* p, float* g, float* m, float* v, long long n
                              float beta2, float eps, float weight_decay, int step, float grad_scale,
                              float max_norm, const float* gnorm_sq, int zero_grad, void* stream);
 
+/* ---- HiFi-GAN generator (reference litfass/third_party/hifigan/models.py:112-174) ----
+ * The convolutions run on lfs2_gemm_tc_ex (channels-last bf16 hi/lo planes; dilated taps; leaky-ReLU / residual
+ * epilogues; ConvTranspose1d(stride u, kernel 2u, padding u/2) as a 3-tap polyphase convolution onto u*C_out columns);
+ * these are the element-wise stages between them.  n = element count (multiple of 8). */
+/* y = leaky_relu(x, slope) on planes (models.py:87,89) */
+LFS2_API int lfs2_lrelu_planes(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, long long n,
+                               float slope, void* stream);
+/* y = leaky_relu(((a + b) + c) * scale, slope): the multi-receptive-field average of the three ResBlocks followed by
+ * the next stage's activation (models.py:157-166) */
+LFS2_API int lfs2_mean3_lrelu_planes(const void* a_hi, const void* a_lo, const void* b_hi, const void* b_lo,
+                                     const void* c_hi, const void* c_lo, void* out_hi, void* out_lo, long long n,
+                                     float scale, float slope, void* stream);
+/* mel (batch, c, t) fp32 channels-first (what Generator.forward takes, hifigan/__init__.py:37) -> (batch, t, c_padded)
+ * channels-last planes; channels >= c and frames t >= lengths[b] (lengths may be NULL) are zero */
+LFS2_API int lfs2_mel_to_planes(const float* mel, const int* lengths, void* out_hi, void* out_lo, int batch, int c,
+                                int t, int c_padded, void* stream);
+/* out[b, t] = tanh(Conv1d(c -> 1, ksize, "same")(leaky_relu(x, slope)))[b, t] (models.py:167-169); w is (ksize * c)
+ * tap-major; samples t >= lengths[b] are read as zero padding and written as 0 (lengths may be NULL) */
+LFS2_API int lfs2_conv_post_tanh(const void* x_hi, const void* x_lo, const float* w, const float* bias,
+                                 const int* lengths, float slope, float* out, int batch, int t, int c, int ksize,
+                                 void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,11 @@ SIGNATURES = {
                                  _vp],
     "lfs2_attn_delta": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "lfs2_attn_ds_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
+    # HiFi-GAN generator glue
+    "lfs2_lrelu_planes": [_vp, _vp, _vp, _vp, _ll, _f, _vp],
+    "lfs2_mean3_lrelu_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _vp],
+    "lfs2_mel_to_planes": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "lfs2_conv_post_tanh": [_vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp],
     # train-step config
     "lfs2_add_layernorm_train": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, ctypes.c_ulonglong, ctypes.c_uint, _vp],
     "lfs2_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],

@@ -535,6 +535,43 @@ def attention_tc(qkv, kpm, nhead, npass=3, want_f32=False, want_planes=True, row
 
 
 # ---------------------------------------------------------------------------------------------
+# HiFi-GAN generator glue (the convolutions are gemm_tc launches)
+def lrelu_planes(x, slope):
+    out = _empty_planes(tuple(x.shape), x.hi.device)
+    _launch("lfs2_lrelu_planes", _p(x.hi), _p(x.lo), _p(out.hi), _p(out.lo), x.hi.numel(), float(slope), _s(),
+            nbytes=8.0 * x.hi.numel())
+    return out
+
+
+def mean3_lrelu_planes(a, b, c, slope):
+    """leaky_relu((a + b + c) / 3, slope) on Planes"""
+    out = _empty_planes(tuple(a.shape), a.hi.device)
+    _launch("lfs2_mean3_lrelu_planes", _p(a.hi), _p(a.lo), _p(b.hi), _p(b.lo), _p(c.hi), _p(c.lo), _p(out.hi), _p(out.lo),
+            a.hi.numel(), 1.0 / 3.0, float(slope), _s(), nbytes=16.0 * a.hi.numel())
+    return out
+
+
+def mel_to_planes(mel, lengths, c_padded):
+    """mel (B, C, T) fp32 channels-first -> Planes (B, T, c_padded), zero beyond lengths (int32 (B) or None)"""
+    _chk(mel, torch.float32, "mel", 3)
+    b, c, t = mel.shape
+    out = _empty_planes((b, t, c_padded), mel.device)
+    _launch("lfs2_mel_to_planes", _p(mel), _p(lengths), _p(out.hi), _p(out.lo), b, c, t, c_padded, _s(),
+            nbytes=4.0 * mel.numel() + 4.0 * b * t * c_padded)
+    return out
+
+
+def conv_post_tanh(x, w, bias, lengths, slope):
+    """x Planes (B, T, C), w (k*C) tap-major fp32, bias (1) -> tanh(conv(leaky_relu(x))) (B, T) fp32"""
+    b, t, c = x.shape
+    k = w.numel() // c
+    out = torch.empty(b, t, device=x.hi.device, dtype=torch.float32)
+    _launch("lfs2_conv_post_tanh", _p(x.hi), _p(x.lo), _p(w), _p(bias), _p(lengths), float(slope), _p(out), b, t, c, k,
+            _s(), flops=2.0 * b * t * c * k, nbytes=4.0 * b * t * c + 4.0 * b * t)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # train-step config: forward variants that save what the backward needs, backward kernels, loss,
 # optimizer.  Parameter gradients accumulate (+=) into the tensors passed as d<param>.
 def add_layernorm_train(x, y, gamma, beta, eps=LN_EPS, drop=None):
