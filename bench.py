@@ -430,6 +430,65 @@ def measure_c5(dev, hbm_peak, steps=20):
 
 
 
+def measure_vocoder(dev, mel, tgt_mask, nutt, steps=3):
+    """the HiFi-GAN generator behind the path (reference synthesis/generator.py:160-170 vocodes every
+    utterance of the batch, one call each): the first `nutt` utterances of the timed batch's mel output, valid frames
+    only, as ONE ragged batch; seeded weights of the reference architecture (the bundled checkpoint cannot travel)."""
+    from lightningfastspeech2_b200 import hifigan
+    from oracle import hifigan_oracle as HO
+
+    cfg = dict(HO.CONFIG)
+    gen = hifigan.Generator(hifigan.AttrDict(cfg))
+    gen.remove_weight_norm()
+    sd = synthetic.hifigan_state_dict(cfg, seed=3)
+    gen.load_state_dict(sd)
+    gen = gen.eval().to(dev)
+    lens = (~tgt_mask[:nutt]).sum(1)
+    tmax = int(lens.max())
+    x = mel[:nutt, :tmax].transpose(1, 2).contiguous()          # (B, 80, T) as the reference feeds it
+    with torch.no_grad():
+        wav = gen(x, lens)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            wav = gen(x, lens)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    frames = int(lens.sum())
+    # CPU port on the shortest utterance (bounded), and parity on it
+    i = int(lens.argmin())
+    n = int(lens[i])
+    torch.set_num_threads(os.cpu_count())
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        ref = HO.generator(sd, x[i:i + 1, :, :n].cpu())
+    cpu_s = time.perf_counter() - t0
+    err = float((wav[i, 0, : n * 256].cpu() - ref[0, 0]).abs().max())
+    flops_per_frame = 0.0
+    ch = cfg["upsample_initial_channel"]
+    rate = 1
+    flops_per_frame += 2.0 * 80 * ch * 7
+    for si, (u, k) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
+        c_in, c_out = ch // 2 ** si, ch // 2 ** (si + 1)
+        flops_per_frame += 2.0 * c_in * c_out * k * rate          # ConvTranspose1d: k / u taps per output sample
+        rate *= u
+        flops_per_frame += rate * 2.0 * c_out * c_out * sum(cfg["resblock_kernel_sizes"]) * 6
+    flops_per_frame += rate * 2.0 * (ch // 2 ** len(cfg["upsample_rates"])) * 7
+    return {"what": "HiFi-GAN v1 generator (reference third_party/hifigan/models.py:112-174; 4 upsamplers x 3 ResBlocks, "
+                    "13.9M params, seeded weights) on the mel of the first utterances of the timed batch, ragged batch, "
+                    "fp32-parity mode (split-bf16 x3)",
+            "utterances": nutt, "mel_frames": frames, "padded_frames": tmax, "ms_per_batch": ms,
+            "value": frames / (ms * 1e-3), "unit": UNIT, "samples_per_s": frames * 256 / (ms * 1e-3),
+            "realtime_factor": frames * 256 / 22050.0 / (ms * 1e-3),
+            "algorithmic_gflop_per_frame": flops_per_frame / 1e9,
+            "achieved_tflops": flops_per_frame * frames / (ms * 1e-3) / 1e12,
+            "cpu_baseline": {"value": n / cpu_s, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                             "sample": f"the shortest of those utterances ({n} frames), one run of {cpu_s:.1f} s"},
+            "max_abs_wav_err_vs_oracle": err}
+
+
 def run_reference(args):
     rank, world, local = dist_env()
     if rank != 0:
@@ -740,6 +799,18 @@ def run_lfs2(args):
         except Exception as exc:  # noqa: BLE001
             errors["parity_c2"] = repr(exc)[:300]
 
+    # ---- N1: the vocoder behind the path, on this batch's mel (rank 0) ----
+    vocoder = None
+    if rank == 0 and args.vocoder_utts > 0:
+        try:
+            with torch.no_grad():
+                rv = model(resident, inference=True)
+            vocoder = measure_vocoder(dev, rv["mel"], rv["tgt_mask"], args.vocoder_utts)
+            del rv
+        except Exception as exc:  # noqa: BLE001
+            errors["vocoder"] = repr(exc)[:300]
+        torch.cuda.empty_cache()
+
     # ---- BASELINE.json configs[2] ("C3"): 76 M-parameter model, bf16 synthesis, 32 utterances per GPU ----------
     c3 = None
     if args.c3_steps > 0:
@@ -883,6 +954,8 @@ def run_lfs2(args):
             line["c1"] = c1
         if c5 is not None:
             line["c5_length_regulator"] = c5
+        if vocoder is not None:
+            line["vocoder_hifigan"] = vocoder
         tot_b = sum(v["ms"] for v in prof_bf16.values()) or 1.0
         top_b = max(prof_bf16, key=lambda k: prof_bf16[k]["ms"]) if prof_bf16 else None
         tb = prof_bf16[top_b] if top_b else None
@@ -944,6 +1017,8 @@ def main():
                     help="utterances of the timed C2 batch compared with the oracle under 'parity_check' (C3: a quarter; 0 = skip)")
     ap.add_argument("--c1-steps", type=int, default=30, help="timed C1 (1 x 128 phonemes, dense k=9) calls under 'c1' (0 = skip)")
     ap.add_argument("--c5-steps", type=int, default=20, help="timed C5 LengthRegulator launches under 'c5_length_regulator' (0 = skip)")
+    ap.add_argument("--vocoder-utts", type=int, default=8,
+                    help="utterances of the timed batch vocoded by the HiFi-GAN generator under 'vocoder_hifigan' (0 = skip)")
     ap.add_argument("--train-steps", type=int, default=5, help="timed C4 train steps reported under 'train' (0 = skip)")
     ap.add_argument("--train-mode", default="fp32", choices=["simt", "fp32", "bf16"])
     ap.add_argument("--train-cpu-utts", type=int, default=2, help="utterances in the CPU train-step sample (0 = skip)")

@@ -117,3 +117,31 @@ def add_train_targets(batch, variances, seed=0, n_mels=80, dur_lo=1, dur_hi=9, l
         shape = (b, tm) if frame else phones.shape  # phone-level targets are per phoneme (datasets.py:592-601)
         out[f"variances_{v}"] = torch.from_numpy(g.standard_normal(shape).astype(np.float32))
     return out
+
+
+def hifigan_state_dict(cfg, seed=0):
+    """Seeded weights of the HiFi-GAN generator (reference third_party/hifigan/models.py:112-148) with weight_norm
+    folded: {"conv_pre.weight", "ups.i.weight" (C_in, C_out, K), "resblocks.j.convs{1,2}.m.weight", "conv_post.weight",
+    + biases}.  Gains are chosen like the bundled universal checkpoint's (std * sqrt(fan_in) of
+    order 1) so that the signal survives the 4 x 9 residual convolutions and tanh is exercised but not saturated
+    (|wav| mean ~0.3, max ~0.9 on N(0,1) mels)."""
+    out = {}
+
+    def conv(name, shape, fan_in, gain):
+        g = _rng(seed, name)
+        out[name + ".weight"] = torch.from_numpy((g.standard_normal(shape) * gain / math.sqrt(fan_in)).astype(np.float32))
+        nb = shape[1] if name.startswith("ups.") else shape[0]
+        out[name + ".bias"] = torch.from_numpy((g.standard_normal(nb) * 0.05).astype(np.float32))
+
+    ch = cfg["upsample_initial_channel"]
+    conv("conv_pre", (ch, cfg["num_mels"], 7), cfg["num_mels"] * 7, 1.0)
+    nk = len(cfg["resblock_kernel_sizes"])
+    for i, (u, k) in enumerate(zip(cfg["upsample_rates"], cfg["upsample_kernel_sizes"])):
+        c_in, c_out = ch // (2 ** i), ch // (2 ** (i + 1))
+        conv(f"ups.{i}", (c_in, c_out, k), c_in * k // u, 1.2)
+        for j, (ks, ds) in enumerate(zip(cfg["resblock_kernel_sizes"], cfg["resblock_dilation_sizes"])):
+            for m in range(len(ds)):
+                conv(f"resblocks.{i * nk + j}.convs1.{m}", (c_out, c_out, ks), c_out * ks, 0.8)
+                conv(f"resblocks.{i * nk + j}.convs2.{m}", (c_out, c_out, ks), c_out * ks, 0.6)
+    conv("conv_post", (1, ch // (2 ** len(cfg["upsample_rates"])), 7), ch // (2 ** len(cfg["upsample_rates"])) * 7, 1.0)
+    return out
