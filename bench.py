@@ -438,8 +438,11 @@ def measure_vocoder(dev, mel, tgt_mask, nutt, steps=3):
     from oracle import hifigan_oracle as HO
 
     cfg = dict(HO.CONFIG)
+    import contextlib
+
     gen = hifigan.Generator(hifigan.AttrDict(cfg))
-    gen.remove_weight_norm()
+    with contextlib.redirect_stdout(sys.stderr):  # (the reference's remove_weight_norm prints; stdout carries ONE JSON line)
+        gen.remove_weight_norm()
     sd = synthetic.hifigan_state_dict(cfg, seed=3)
     gen.load_state_dict(sd)
     gen = gen.eval().to(dev)

@@ -261,6 +261,14 @@ LFS2_API int lfs2_attention_tc_ex(const void* qkv_hi, const void* qkv_lo, int op
                                   const uint8_t* key_padding_mask, void* ctx_hi, void* ctx_lo, float* ctx_f32,
                                   void* workspace, int batch, int t, int d, int nhead, int npass, const int* row_limit,
                                   int limit_extra, void* stream);
+/* Wide heads (head_dim 256 or 384: the 76 M configuration has d = 768, 2 heads): the same flash attention with the O
+ * accumulator in 128 * (head_dim / 128) tensor-memory columns, Q resident in shared memory (SS-form Q.K^T accumulated
+ * over the head's 128-column chunks) and K / V streamed in [64 keys x 128 columns] slots.  qkv is ONE 16-bit plane
+ * (B, T, 3d): bf16 (compute mode "bf16") or fp16 (compute mode "fp32"); ctx leaves as bf16 hi/lo planes and/or fp32.
+ * No (T x T) tensor reaches HBM.  workspace: lfs2_attention_tc_workspace_bytes(batch). */
+LFS2_API int lfs2_attention_tc_wide(const void* qkv, int operand_format, const uint8_t* key_padding_mask, void* ctx_hi,
+                                    void* ctx_lo, float* ctx_f32, void* workspace, int batch, int t, int d, int nhead,
+                                    const int* row_limit, int limit_extra, void* stream);
 
 /* out = hi + lo (fp32) for n values (n % 4 == 0): the inverse of lfs2_split_bf16 up to 2^-17 relative */
 LFS2_API int lfs2_merge_planes(const void* hi, const void* lo, float* out, long long n, void* stream);

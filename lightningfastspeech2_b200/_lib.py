@@ -40,6 +40,7 @@ SIGNATURES = {
     "lfs2_gemm_tc_ex": [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _vp, _i, _f, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i,
                         _i, _vp, _i, _vp, _vp, _vp],
     "lfs2_attention_tc_ex": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
+    "lfs2_attention_tc_wide": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "lfs2_dwconv1d_planes_limited": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "lfs2_mask_lengths": [_vp, _vp, _i, _i, _vp],
     "lfs2_zero_masked_rows": [_vp, _vp, _ll, _i, _vp],

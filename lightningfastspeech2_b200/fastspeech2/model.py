@@ -133,6 +133,7 @@ class ConformerEncoderLayer(nn.Module):
     # ~6e-5 against the 1e-3 budget, tools/precision_emulation.py; a third of the attention MMAs and half of the qkv
     # traffic); "x3" = q, k, v and P as bf16 hi/lo planes, three passes per product (~1.4e-5).
     attention_operands = "f16"
+    wide_flash_attention = True   # head_dim 256 / 384: lfs2_attention_tc_wide instead of the GEMM-decomposed attention
 
     # -- weight repacks -------------------------------------------------------------------
     def _build_pack_tc(self):
@@ -262,6 +263,14 @@ class ConformerEncoderLayer(nn.Module):
         Returns ctx as Planes."""
         sa, w = self.self_attn, self._packed_tc()
         d = xp.shape[-1]
+        if (d // self.nhead) in (256, 384) and self.wide_flash_attention:
+            # wide heads (76 M configuration: head_dim 384): flash attention on ONE 16-bit plane of q, k, v -- fp16 in
+            # compute mode "fp32" (attention_operands "f16"), bf16 in "bf16" mode; no T x T tensor in HBM
+            f16 = self.compute_mode == "fp32"
+            if not f16 or self.attention_operands == "f16":
+                qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="f16" if f16 else "planes", npass=npass,
+                                  tag="qkv_gemm")
+                return ops.attention_tc_wide(qkv, kpm, self.nhead)[1]
         if (d // self.nhead) % 32 == 0:
             qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="planes", npass=npass, tag="qkv_gemm")
             ctx, _, _ = ops.attention_mat_fwd(qkv, kpm, self.nhead, npass=npass)

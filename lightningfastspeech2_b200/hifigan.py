@@ -114,16 +114,18 @@ class ResBlock(nn.Module):
         for conv in list(self.convs1) + list(self.convs2):
             remove_weight_norm(conv)
 
-    def forward_planes(self, x, xa, pack, row_mask, npass):
+    def forward_planes(self, x, xa, pack, row_mask, npass, row_limit=None):
         """x: Planes (B, T, C); xa = leaky_relu(x) if the caller already has it; -> Planes"""
         k = self.kernel_size
         for m, d in enumerate(self.dilation):
             a = xa if (m == 0 and xa is not None) else ops.lrelu_planes(x, LRELU_SLOPE)
             w1, w2 = pack[m]
             hh = ops.gemm_tc(a, w1, self.convs1[m].bias, taps=k, dilation=d, leaky_slope=LRELU_SLOPE, out="planes",
-                             npass=npass, row_mask=row_mask, tag="hifigan_resblock_conv1")
-            x = ops.gemm_tc(hh, w2, self.convs2[m].bias, taps=k, residual=x, out="planes", npass=npass,
-                            row_mask=row_mask, tag="hifigan_resblock_conv2")
+                             npass=npass, row_mask=row_mask, row_limit=row_limit, tag="hifigan_resblock_conv1")
+            # (x + conv2(.): the residual rides the tensor core as hi/lo identity slabs, which needs the 3-pass stage
+            #  layout -- the residual stream keeps fp32 precision in "bf16" mode as well)
+            x = ops.gemm_tc(hh, w2, self.convs2[m].bias, taps=k, residual=x, out="planes", npass=3,
+                            row_mask=row_mask, row_limit=row_limit, tag="hifigan_resblock_conv2")
         return x
 
 
@@ -206,23 +208,32 @@ class Generator(nn.Module):
                 return None
             return (torch.arange(t * scale, device=dev)[None, :] >= (len32 * scale)[:, None]).contiguous()
 
+        def row_limit(scale):
+            """128-row tiles that start at or after length + 32 rows are skipped altogether: the rows they would write
+            are zeros nobody needs -- a valid sample reads at most 25 rows (k 11, dilation 5) past its utterance's end,
+            rows the last kept tile has written as zeros -- and the element-wise stages may carry anything there"""
+            if len32 is None:
+                return None
+            return ((len32 * scale).contiguous(), 32, {})
+
         xp = ops.mel_to_planes(x, len32, pk["c_in_padded"])
-        mask = row_mask(1)
+        mask, lim = row_mask(1), row_limit(1)
         # conv_pre, with the first stage's leaky ReLU in its epilogue (nothing else reads the un-activated tensor)
         hcur = ops.gemm_tc(xp, pk["pre"], self.conv_pre.bias, taps=7, leaky_slope=LRELU_SLOPE, out="planes", npass=npass,
-                           row_mask=mask, tag="hifigan_conv_pre")
+                           row_mask=mask, row_limit=lim, tag="hifigan_conv_pre")
         scale = 1
         for i, up in enumerate(self.ups):
             u = up.stride[0]
             w_up, b_up = pk["ups"][i]
-            y = ops.gemm_tc(hcur, w_up, b_up, taps=3, out="planes", npass=npass, row_mask=mask, tag="hifigan_upsample")
+            y = ops.gemm_tc(hcur, w_up, b_up, taps=3, out="planes", npass=npass, row_mask=mask, row_limit=lim,
+                            tag="hifigan_upsample")
             scale *= u
             c_out = up.out_channels
             xu = ops.Planes(y.hi.view(bsz, t * scale, c_out), y.lo.view(bsz, t * scale, c_out))
-            mask = row_mask(scale)
+            mask, lim = row_mask(scale), row_limit(scale)
             xa = ops.lrelu_planes(xu, LRELU_SLOPE)  # shared by the first convolution of the stage's three ResBlocks
             outs = [self.resblocks[i * self.num_kernels + j].forward_planes(xu, xa, pk["res"][i * self.num_kernels + j],
-                                                                            mask, npass)
+                                                                            mask, npass, lim)
                     for j in range(self.num_kernels)]
             del xa, xu, y
             last = i + 1 == self.num_upsamples

@@ -534,6 +534,33 @@ def attention_tc(qkv, kpm, nhead, npass=3, want_f32=False, want_planes=True, row
     return ctx, po
 
 
+def attention_tc_wide(qkv, kpm, nhead, want_f32=False, want_planes=True, row_limit=None):
+    """flash attention for head_dim 256 / 384.  qkv: ONE 16-bit tensor (B,T,3d) [q|k|v], torch.bfloat16 or torch.float16
+    (or Planes: the hi plane is used) -> (ctx f32 or None, ctx Planes or None)"""
+    if isinstance(qkv, Planes):
+        qkv = qkv.hi
+    if qkv.dtype not in (torch.bfloat16, torch.float16):
+        raise TypeError("attention_tc_wide: qkv must be a bf16 or fp16 tensor")
+    _chk(qkv, qkv.dtype, "qkv", 3)
+    b, t, d3 = qkv.shape
+    d = d3 // 3
+    if kpm is not None:
+        _chk(kpm, torch.bool, "key_padding_mask", 2)
+    dev = qkv.device
+    ctx = torch.empty(b, t, d, device=dev, dtype=torch.float32) if want_f32 else None
+    po = _empty_planes((b, t, d), dev) if want_planes else None
+    ws = torch.empty(max(1, _lib.lib().lfs2_attention_tc_workspace_bytes(b)), device=dev, dtype=torch.uint8)
+    lim, extra = (row_limit[0], row_limit[1]) if row_limit is not None else (None, 0)
+    fl = 0.0
+    if PROFILE is not None:
+        nkeys = (~kpm).sum(1).double() if kpm is not None else torch.full((b,), float(t), device=dev, dtype=torch.float64)
+        fl = float(4.0 * d * t * nkeys.sum())
+    _launch("lfs2_attention_tc_wide", _p(qkv), 1 if qkv.dtype == torch.float16 else 0, _p(kpm), _p(po.hi if po else None),
+            _p(po.lo if po else None), _p(ctx), _p(ws), b, t, d, nhead, _p(lim), int(extra), _s(),
+            tag="lfs2_attention_tc", flops=fl, nbytes=2.0 * qkv.numel() + 4.0 * b * t * d * (int(want_f32) + int(want_planes)))
+    return ctx, po
+
+
 # ---------------------------------------------------------------------------------------------
 # HiFi-GAN generator glue (the convolutions are gemm_tc launches)
 def lrelu_planes(x, slope):

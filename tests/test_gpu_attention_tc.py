@@ -135,3 +135,50 @@ def test_fp16_operands_row_limit_and_masks():
     for i, n in enumerate(lens):
         keep = min(t, (n + 28 + 127) // 128 * 128)
         assert torch.equal(part[i, :keep], full[i, :keep]), i
+
+
+# ---- wide heads (head_dim 256 / 384: lfs2_attention_tc_wide; the 76 M configuration is d = 768, 2 heads)
+@pytest.mark.parametrize("fmt,tol", [(torch.float16, 2e-3), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("b,t,d,lens", [(2, 200, 768, [200, 77]), (3, 1, 768, None), (2, 700, 768, [700, 333]),
+                                        (4, 257, 768, [257, 256, 65, 3]), (2, 130, 512, [130, 64]), (1, 64, 768, None)])
+def test_wide_heads_match_fp64(b, t, d, lens, fmt, tol):
+    nhead = 2
+    qkv, kpm = make(b, t, d, seed=t + b + d, lens=lens)
+    q16 = qkv.to(fmt)
+    ref = ref_attention(q16.float(), kpm, nhead)      # the rounded plane is the kernel's input
+    ctx, cp = ops.attention_tc_wide(q16.to(DEV), None if kpm is None else kpm.to(DEV), nhead, want_f32=True)
+    err = (ctx.cpu() - ref).abs().max()
+    print(f"wide attention d={d} t={t} {fmt}: max err {float(err):.2e}")
+    assert err < tol, float(err)
+    assert (cp.float().cpu() - ctx.cpu()).abs().max() < 1e-4
+
+
+def test_wide_heads_growing_max_masks_and_row_limit():
+    b, t, d, nhead = 3, 500, 768, 2
+    qkv, _ = make(b, t, d, seed=21, scale=1.6)    # logit std ~ 2.6 * sqrt(384)/sqrt(384): maxima keep growing -> O rescale path
+    g = torch.Generator().manual_seed(1)
+    kpm = torch.rand(b, t, generator=g) < 0.3
+    kpm[1, :70] = True
+    kpm[2, :] = True                              # no valid key at all -> NaN like torch
+    q16 = qkv.half()
+    ref = ref_attention(q16.float(), kpm, nhead)
+    ctx, _ = ops.attention_tc_wide(q16.to(DEV), kpm.to(DEV), nhead, want_f32=True)
+    ctx = ctx.cpu()
+    assert torch.isnan(ref[2]).all() and torch.isnan(ctx[2]).all()
+    assert (ctx[:2] - ref[:2]).abs().max() < 5e-3
+    lens = [500, 100, 333]
+    kpm2 = torch.arange(t)[None, :] >= torch.tensor(lens)[:, None]
+    full, _ = ops.attention_tc_wide(q16.to(DEV), kpm2.to(DEV), nhead, want_f32=True)
+    lim = torch.tensor(lens, dtype=torch.int32, device=DEV)
+    part, _ = ops.attention_tc_wide(q16.to(DEV), kpm2.to(DEV), nhead, want_f32=True, row_limit=(lim, 28))
+    for i, n in enumerate(lens):
+        keep = min(t, (n + 28 + 127) // 128 * 128)
+        assert torch.equal(part[i, :keep], full[i, :keep]), i
+
+
+def test_wide_heads_agree_with_the_gemm_decomposed_attention():
+    qkv, kpm = make(2, 300, 768, seed=22, lens=[300, 190])
+    planes = ops.split_bf16(qkv.to(DEV))
+    ref, _, _ = ops.attention_mat_fwd(planes, kpm.to(DEV), 2, npass=3)
+    ctx, _ = ops.attention_tc_wide(qkv.half().to(DEV), kpm.to(DEV), 2, want_f32=True)
+    assert (ctx - ref).abs().max() < 2e-3
