@@ -686,6 +686,18 @@ class FastSpeech2(_Base):
         _, flat_g = self.flatten_parameters()
         return allreduce_sum_(flat_g, group)
 
+    # Under pl.Trainer: parameters never enter torch's autograd graph (the backward is hand-written and writes p.grad
+    # itself), so torch's DistributedDataParallel wrapper -- Lightning's strategy="ddp" -- has no AccumulateGrad hooks to
+    # ride on and MUST NOT wrap this module.  Data-parallel training = one process per GPU with a strategy that leaves
+    # the module unwrapped, and this hook (Lightning calls it right after loss.backward()) doing the one all-reduce.
+    allreduce_in_hook = False
+
+    def on_after_backward(self):
+        if self.allreduce_in_hook:
+            world = self.allreduce_gradients()
+            if getattr(self, "optimizer", None) is not None and hasattr(self.optimizer, "grad_scale"):
+                self.optimizer.grad_scale = 1.0 / world
+
     # -- train / validation steps (reference :786-807) ---------------------------------------
     def training_step(self, batch, batch_idx, optimizer_idx=0):
         result = self(batch, optimizer_idx)
