@@ -81,6 +81,12 @@ LFS2_API int lfs2_conv1d_dense(const float* x, const float* wp, const float* bia
  * of the reference's (d,1,ksize) weight.  replaces model.py:75-81 and model.py:545-551. */
 LFS2_API int lfs2_dwconv1d(const float* x, const float* wt, const float* bias, float* out,
                   int batch, int t, int d, int ksize, void* stream);
+/* out = LayerNorm(x + y) with x (the residual stream) and the result as bf16 hi/lo planes, y fp32 or NULL: the
+ * FFTBlock of widths without a LayerNorm GEMM epilogue (d != 256) stays in plane form from block to block
+ * (model.py:114-115 at d = 768) */
+LFS2_API int lfs2_add_layernorm_planes(const void* x_hi, const void* x_lo, const float* y, const float* gamma,
+                                       const float* beta, void* out_hi, void* out_lo, int m, int d, float eps,
+                                       void* stream);
 /* same, reading the input as fp32 (x) OR as bf16 hi/lo planes (x_hi, x_lo; x = NULL), and writing
  * the result as fp32 (out, may be NULL) and/or as hi/lo planes (the A operand of the following
  * pointwise lfs2_gemm_tc) */
@@ -191,6 +197,7 @@ LFS2_API int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch,
 #define LFS2_OUT_PLANES 0
 #define LFS2_OUT_F32 1
 #define LFS2_OUT_F16 2
+#define LFS2_OUT_BF16 3 /* out0 = ONE bf16 plane: a result that only feeds single-pass (npass = 1) products */
 LFS2_API int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int t, int d, int taps, int dilation,
                              const void* w_hi, const void* w_lo, int n, const float* bias, int activation, float slope,
                              const void* res_hi, const void* res_lo, const void* ident_hi, const float* gamma,

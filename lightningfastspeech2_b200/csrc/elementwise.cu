@@ -481,6 +481,60 @@ static int launch_dwconv_k(const float* x, const void* x_hi, const void* x_lo, c
   return LFS2_OK;
 }
 
+// out = LayerNorm(x + y) with the residual stream x and the result as bf16 hi/lo planes, y fp32 (a GEMM's fp32 output):
+// the d != 256 FFTBlock (no LayerNorm epilogue in the GEMM) stays in plane form from block to block -- no merge / split
+// passes around the LayerNorm.  One warp per row, statistics in fp32 exactly like add_layernorm_kernel.
+__global__ void add_layernorm_planes_kernel(const uint2* __restrict__ x_hi, const uint2* __restrict__ x_lo,
+                                            const float4* __restrict__ y, const float4* __restrict__ gamma,
+                                            const float4* __restrict__ beta, uint2* __restrict__ out_hi,
+                                            uint2* __restrict__ out_lo, int m, int d4, float eps) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= m) return;
+  const size_t base = (size_t)row * d4;
+  float4 v[kLnMaxVec];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = lane + 32 * i;
+    if (c < d4) {
+      float4 a = planes_to_f4(x_hi[base + c], x_lo[base + c]);
+      if (y) {
+        const float4 b = y[base + c];
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+      }
+      v[i] = a;
+      s += (a.x + a.y) + (a.z + a.w);
+    }
+  }
+  const float inv_d = 1.f / (float)(d4 * 4);
+  const float mean = warp_sum(s) * inv_d;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = lane + 32 * i;
+    if (c < d4) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, dd = v[i].w - mean;
+      q += (a * a + b * b) + (cc * cc + dd * dd);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) * inv_d + eps);
+#pragma unroll
+  for (int i = 0; i < kLnMaxVec; ++i) {
+    const int c = lane + 32 * i;
+    if (c < d4) {
+      const float4 g = gamma[c], bt = beta[c];
+      const float ox = (v[i].x - mean) * rstd * g.x + bt.x, oy = (v[i].y - mean) * rstd * g.y + bt.y;
+      const float oz = (v[i].z - mean) * rstd * g.z + bt.z, ow = (v[i].w - mean) * rstd * g.w + bt.w;
+      uint2 h, l;
+      split_pack2_ew(ox, oy, h.x, l.x);
+      split_pack2_ew(oz, ow, h.y, l.y);
+      out_hi[base + c] = h;
+      out_lo[base + c] = l;
+    }
+  }
+}
+
 // x = hi + lo (fp32) from bf16 planes; one thread per 4 elements
 __global__ void merge_planes_kernel(const uint2* __restrict__ hi, const uint2* __restrict__ lo, float4* __restrict__ out,
                                     size_t n4) {
@@ -597,6 +651,22 @@ int lfs2_add_layernorm_train(const float* x, const float* y, const float* gamma,
       (const float4*)x, (const float4*)y, (const float4*)gamma, (const float4*)beta, (float4*)out, (float4*)z_out,
       (float2*)stats, m, d / 4, eps, make_drop_site(y ? drop_p : 0.f, drop_seed, drop_site));
   LFS2_CHECK_LAUNCH("add_layernorm");
+  return LFS2_OK;
+}
+
+int lfs2_add_layernorm_planes(const void* x_hi, const void* x_lo, const float* y, const float* gamma, const float* beta,
+                              void* out_hi, void* out_lo, int m, int d, float eps, void* stream) {
+  LFS2_REQUIRE(x_hi && x_lo && gamma && beta && out_hi && out_lo, LFS2_ERR_INVALID_ARG, "add_layernorm_planes: null pointer");
+  if (m == 0) return LFS2_OK;
+  LFS2_REQUIRE(d > 0 && d % 4 == 0 && d <= 128 * kLnMaxVec, LFS2_ERR_UNSUPPORTED,
+               "add_layernorm_planes: d=%d must be a multiple of 4 and <= %d", d, 128 * kLnMaxVec);
+  LFS2_REQUIRE(aligned16(x_hi) && aligned16(x_lo) && aligned16(gamma) && aligned16(beta) && aligned16(out_hi) &&
+                   aligned16(out_lo) && (!y || aligned16(y)),
+               LFS2_ERR_INVALID_ARG, "add_layernorm_planes: pointers must be 16-byte aligned");
+  add_layernorm_planes_kernel<<<ceil_div((long long)m * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint2*)x_hi, (const uint2*)x_lo, (const float4*)y, (const float4*)gamma, (const float4*)beta,
+      (uint2*)out_hi, (uint2*)out_lo, m, d / 4, eps);
+  LFS2_CHECK_LAUNCH("add_layernorm_planes");
   return LFS2_OK;
 }
 

@@ -37,7 +37,8 @@ constexpr int kBK = 32;      // k-slab: 32 bf16 = 64 bytes = one SWIZZLE_64B row
 constexpr int kGemmTcThreads = 320;  // TMA + MMA warps, 8 epilogue warps (two per TMEM lane quadrant)
 constexpr int kStageChunk = kBM * 32 * 4;  // one 128 x 32 staging chunk: 16 KB (fp32) or 2 x 8 KB (hi | lo)
 
-enum { kOutPlanes = 0, kOutF32 = 1, kOutF16 = 2 };  // epilogue output: bf16 hi/lo planes | fp32 | ONE fp16 plane
+// epilogue output: bf16 hi/lo planes | fp32 | ONE fp16 plane | ONE bf16 plane
+enum { kOutPlanes = 0, kOutF32 = 1, kOutF16 = 2, kOutBF16 = 3 };
 
 struct GemmTcParams {
   int batch, t, d, taps, half;  // A is (batch, t, d); K = taps * d
@@ -418,10 +419,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           for (int i = 0; i < 8; ++i)
             *reinterpret_cast<float4*>(row + ((i ^ (r & 7)) << 4)) =
                 make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-        } else if (OUT == kOutF16) {  // one 128 rows x 64 B fp16 plane, SWIZZLE_64B
+        } else if (OUT == kOutF16 || OUT == kOutBF16) {  // one 128 rows x 64 B 16-bit plane, SWIZZLE_64B
           uint32_t h[16];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) h[j] = pack_f16_sat(v[2 * j], v[2 * j + 1]);
+          for (int j = 0; j < 16; ++j) {
+            if (OUT == kOutF16) h[j] = pack_f16_sat(v[2 * j], v[2 * j + 1]);
+            else asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));
+          }
           uint8_t* rh = sb + r * 64;
 #pragma unroll
           for (int i = 0; i < 4; ++i)
@@ -589,10 +593,12 @@ static int dispatch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, int npas
   if (npass == 3) {
     if (out_kind == kOutF32) return launch_gemm_tc<N_TILE, 3, LN, kOutF32, MC>(m, p, s);
     if (out_kind == kOutF16) return launch_gemm_tc<N_TILE, 3, LN, kOutF16, MC>(m, p, s);
+    if (out_kind == kOutBF16) return launch_gemm_tc<N_TILE, 3, LN, kOutBF16, MC>(m, p, s);
     return launch_gemm_tc<N_TILE, 3, LN, kOutPlanes, MC>(m, p, s);
   }
   if (out_kind == kOutF32) return launch_gemm_tc<N_TILE, 1, LN, kOutF32, MC>(m, p, s);
   if (out_kind == kOutF16) return launch_gemm_tc<N_TILE, 1, LN, kOutF16, MC>(m, p, s);
+  if (out_kind == kOutBF16) return launch_gemm_tc<N_TILE, 1, LN, kOutBF16, MC>(m, p, s);
   return launch_gemm_tc<N_TILE, 1, LN, kOutPlanes, MC>(m, p, s);
 }
 
@@ -648,8 +654,8 @@ int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int t, int d,
   LFS2_REQUIRE(a_hi && w_hi && out0, LFS2_ERR_INVALID_ARG, "gemm_tc: null operand");
   LFS2_REQUIRE(npass == 1 || npass == 3, LFS2_ERR_INVALID_ARG, "gemm_tc: npass must be 1 or 3");
   LFS2_REQUIRE(npass == 1 || (a_lo && w_lo), LFS2_ERR_INVALID_ARG, "gemm_tc: npass=3 needs the lo planes");
-  LFS2_REQUIRE(out_kind == LFS2_OUT_PLANES || out_kind == LFS2_OUT_F32 || out_kind == LFS2_OUT_F16, LFS2_ERR_INVALID_ARG,
-               "gemm_tc: out_kind must be LFS2_OUT_PLANES, LFS2_OUT_F32 or LFS2_OUT_F16");
+  LFS2_REQUIRE(out_kind >= LFS2_OUT_PLANES && out_kind <= LFS2_OUT_BF16, LFS2_ERR_INVALID_ARG,
+               "gemm_tc: out_kind must be LFS2_OUT_PLANES, LFS2_OUT_F32, LFS2_OUT_F16 or LFS2_OUT_BF16");
   LFS2_REQUIRE(out_kind != LFS2_OUT_PLANES || out1, LFS2_ERR_INVALID_ARG, "gemm_tc: plane output needs out1 (the lo plane)");
   LFS2_REQUIRE(activation >= 0 && activation <= 2, LFS2_ERR_INVALID_ARG, "gemm_tc: activation must be 0, 1 or 2");
   if (batch == 0 || t == 0) return LFS2_OK;

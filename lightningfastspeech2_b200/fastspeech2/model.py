@@ -230,7 +230,7 @@ class ConformerEncoderLayer(nn.Module):
         if row_limit is not None and not self.supports_row_limit(d):
             raise NotImplementedError("row-limited FFTBlock needs d = 256, head_dim 128 and the fused depthwise FFN")
         if d != 256:
-            return ops.planes_of(self._forward_tc_unfused_ln(ops.merge_planes(xp), xp, kpm, npass))
+            return self._forward_tc_unfused_ln(xp, kpm, npass)
         if d // self.nhead == 128:
             f16 = self.compute_mode == "fp32" and self.attention_operands == "f16"
             qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="f16" if f16 else "planes", npass=npass,
@@ -268,7 +268,7 @@ class ConformerEncoderLayer(nn.Module):
             # compute mode "fp32" (attention_operands "f16"), bf16 in "bf16" mode; no T x T tensor in HBM
             f16 = self.compute_mode == "fp32"
             if not f16 or self.attention_operands == "f16":
-                qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="f16" if f16 else "planes", npass=npass,
+                qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="f16" if f16 else "bf16", npass=npass,
                                   tag="qkv_gemm")
                 return ops.attention_tc_wide(qkv, kpm, self.nhead)[1]
         if (d // self.nhead) % 32 == 0:
@@ -278,21 +278,24 @@ class ConformerEncoderLayer(nn.Module):
         qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, npass=npass, tag="qkv_gemm")
         return ops.split_bf16(ops.attention(qkv, kpm, self.nhead))
 
-    def _forward_tc_unfused_ln(self, x, xp, kpm, npass):
-        """d != 256 (e.g. the 76 M config, d = 768): tensor-core GEMMs, LayerNorm as its own kernel."""
+    def _forward_tc_unfused_ln(self, xp, kpm, npass):
+        """d != 256 (e.g. the 76 M config, d = 768): tensor-core GEMMs with fp32 results, LayerNorm as its own kernel
+        that takes the residual stream as planes and hands planes back -- the block is planes in, planes out.
+        In "bf16" mode results that only feed single-pass products (the FFN intermediate) travel as ONE bf16 plane."""
         sa, w, p = self.self_attn, self._packed_tc(), self._packed()
         ctx = self._attention_any_head_dim(xp, kpm, npass)
         a = ops.gemm_tc(ctx, w["out_proj"], sa.out_proj.bias, npass=npass, tag="out_proj_gemm")
-        x1 = ops.add_layernorm(x, a, self.norm1.weight, self.norm1.bias, self.eps)
+        x1p = ops.add_layernorm_planes(xp, a, self.norm1.weight, self.norm1.bias, self.eps)
+        one = "bf16" if npass == 1 else "planes"
         if self.depthwise:
-            up = ops.dwconv1d_planes(x1, p["dw_wt"], self.conv1[0].bias)
-            vp = ops.gemm_tc(up, w["pw1"], self.conv1[1].bias, relu=True, out="planes", npass=npass, tag="ffn1_gemm")
+            up = ops.dwconv1d_planes(x1p, p["dw_wt"], self.conv1[0].bias)
+            vp = ops.gemm_tc(up, w["pw1"], self.conv1[1].bias, relu=True, out=one, npass=npass, tag="ffn1_gemm")
             y = ops.gemm_tc(vp, w["w_eff"], p["b_eff"], npass=npass, tag="ffn2_gemm")
         else:
-            vp = ops.gemm_tc(ops.split_bf16(x1), w["c1"], self.conv1.bias, taps=self.conv1.kernel_size[0], relu=True,
-                             out="planes", npass=npass, tag="ffn1_gemm")
+            vp = ops.gemm_tc(x1p, w["c1"], self.conv1.bias, taps=self.conv1.kernel_size[0], relu=True, out=one,
+                             npass=npass, tag="ffn1_gemm")
             y = ops.gemm_tc(vp, w["c2"], self.conv2.bias, taps=self.conv2.kernel_size[0], npass=npass, tag="ffn2_gemm")
-        return ops.add_layernorm(x1, y, self.norm2.weight, self.norm2.bias, self.eps)
+        return ops.add_layernorm_planes(x1p, y, self.norm2.weight, self.norm2.bias, self.eps)
 
     def _ff_block(self, x):
         p = self._packed()

@@ -186,6 +186,19 @@ def add_layernorm(x, y, gamma, beta, eps=LN_EPS):
     return out
 
 
+def add_layernorm_planes(x, y, gamma, beta, eps=LN_EPS):
+    """LayerNorm(x + y): x Planes (residual stream), y fp32 tensor or None -> Planes"""
+    _chk(x.hi, torch.bfloat16, "layernorm residual planes"); _chk(x.lo, torch.bfloat16, "layernorm residual planes")
+    if y is not None:
+        _chk(y, torch.float32, "layernorm branch")
+    d = x.shape[-1]
+    m = x.hi.numel() // d
+    out = _empty_planes(tuple(x.shape), x.hi.device)
+    _launch("lfs2_add_layernorm_planes", _p(x.hi), _p(x.lo), _p(y), _p(gamma), _p(beta), _p(out.hi), _p(out.lo), m, d,
+            float(eps), _s(), tag="lfs2_add_layernorm", nbytes=4.0 * m * d * (3 if y is not None else 2))
+    return out
+
+
 def rowdot_mask(z, w, bias, mask):
     _chk(z, torch.float32, "predictor hidden", 3)
     b, t, f = z.shape
@@ -386,7 +399,7 @@ def _identity_planes(n, device):
     return _IDENT[key]
 
 
-OUT_KINDS = {"planes": 0, "f32": 1, "f16": 2}
+OUT_KINDS = {"planes": 0, "f32": 1, "f16": 2, "bf16": 3}
 
 
 def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None, eps=LN_EPS, out="f32",
@@ -394,13 +407,14 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
     """a: Planes (B,T,d) [taps>1: Conv1d over T per utterance] or (...,d) for taps == 1;
     w: Planes (n, taps*d); residual: Planes shaped like the output (added on the tensor core).
     out = "f32" -> fp32 tensor, "planes" -> Planes (bf16 hi/lo), "f16" -> Planes(hi = ONE fp16 tensor, lo = None: the
-    operand of the single-pass fp16 attention); shaped like a with last dim n.
+    operand of the single-pass fp16 attention), "bf16" -> Planes(hi = ONE bf16 tensor, lo = None: a result that only
+    feeds npass = 1 products); shaped like a with last dim n.
     dilation: tap spacing (dilated Conv1d); leaky_slope: leaky ReLU instead of ReLU; row_mask (B,T) bool: rows written
     as zeros (PAD frames of a ragged batch)."""
     if not isinstance(a, Planes) or not isinstance(w, Planes):
         raise TypeError("gemm_tc: operands must be Planes (see split_bf16)")
     if out not in OUT_KINDS:
-        raise ValueError("gemm_tc: out must be 'f32', 'planes' or 'f16'")
+        raise ValueError("gemm_tc: out must be 'f32', 'planes', 'f16' or 'bf16'")
     d = a.shape[-1]
     n = w.shape[0]
     if w.shape[1] != taps * d:
@@ -412,15 +426,16 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
             raise ValueError("gemm_tc: conv mode needs a (B,T,d) operand")
         batch, t = a.shape[0], a.shape[1]
     for x_ in (a.hi, a.lo, w.hi, w.lo):
-        _chk(x_, torch.bfloat16, "gemm_tc operand plane")
+        if x_ is not None or npass == 3:  # (single-plane operands: Planes(hi, None) are fine for npass = 1)
+            _chk(x_, torch.bfloat16, "gemm_tc operand plane")
     out_shape = tuple(a.shape[:-1]) + (n,)
     dev = a.hi.device
     # an fp32 result of a row-limited launch is a user-visible tensor: the rows of skipped tiles read as zeros
     of = (torch.zeros if row_limit is not None else torch.empty)(out_shape, device=dev, dtype=torch.float32) \
         if out == "f32" else None
     po = _empty_planes(out_shape, dev) if out == "planes" else None
-    if out == "f16":
-        po = Planes(torch.empty(out_shape, device=dev, dtype=torch.float16), None)
+    if out in ("f16", "bf16"):
+        po = Planes(torch.empty(out_shape, device=dev, dtype=torch.float16 if out == "f16" else torch.bfloat16), None)
     ident = None
     if residual is not None:
         if not isinstance(residual, Planes) or tuple(residual.shape) != out_shape:
@@ -446,7 +461,7 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
             if cache is not None:
                 cache[key] = ws
     act = 0 if not (relu or leaky_slope is not None) else (2 if leaky_slope is not None else 1)
-    out_bytes = {"f32": 4.0, "planes": 4.0, "f16": 2.0}[out]
+    out_bytes = {"f32": 4.0, "planes": 4.0, "f16": 2.0, "bf16": 2.0}[out]
     _launch("lfs2_gemm_tc_ex", _p(a.hi), _p(a.lo), batch, t, d, taps, int(dilation), _p(w.hi), _p(w.lo), n, _p(bias), act,
             float(leaky_slope or 0.0), _p(residual.hi if residual is not None else None),
             _p(residual.lo if residual is not None else None), _p(ident), _p(gamma), _p(beta), float(eps),
