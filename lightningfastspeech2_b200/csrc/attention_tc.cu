@@ -27,6 +27,7 @@
 //   The softmax itself (max, exp2, sum, 1/l) is fp32.  PAD keys (key_padding_mask) and keys
 //   beyond T get -inf; rows whose keys are all masked produce NaN like the reference.
 #include <math.h>
+#include <stdlib.h>
 
 #include "tc_common.cuh"
 
@@ -544,6 +545,21 @@ static int launch_attention_tc(const AttnMaps& m, const AttnTcParams& p, int bat
   return LFS2_OK;
 }
 
+// attention_tc_pp.cu: the single-plane kernel laid out for two CTAs per SM
+int launch_attention_tc_pp(const void* qkv, int f16, const uint8_t* kpm, const int* kend, void* ctx_hi, void* ctx_lo,
+                           float* ctx_f32, int batch, int t, int d, int nhead, const int* row_limit, int limit_extra,
+                           cudaStream_t s);
+
+// LFS2_ATTN_PP=0 selects the one-CTA-per-SM kernel of this file for single-plane operands too (A/B measurements)
+static bool attn_pp_enabled() {
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("LFS2_ATTN_PP");
+    on = (e && e[0] == '0') ? 0 : 1;
+  }
+  return on == 1;
+}
+
 }  // namespace tc
 }  // namespace lfs2
 
@@ -600,6 +616,10 @@ int lfs2_attention_tc_ex(const void* qkv_hi, const void* qkv_lo, int operand_for
   int* kend = reinterpret_cast<int*>(workspace);
   attn_kend_kernel<<<ceil_div((long long)batch * 32, 128), 128, 0, s>>>(key_padding_mask, kend, batch, t);
   LFS2_CHECK_LAUNCH("attn_kend");
+
+  if (npass == 1 && attn_pp_enabled())
+    return launch_attention_tc_pp(qkv_hi, operand_format == LFS2_OPERAND_F16, key_padding_mask, kend, ctx_hi, ctx_lo,
+                                  ctx_f32, batch, t, d, nhead, row_limit, limit_extra, s);
 
   AttnMaps m;
   bool ok = make_tmap_3d(&m.kv_hi, qkv_hi, 3ull * d, t, batch, 32, kAK, 64) &&
