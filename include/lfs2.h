@@ -480,6 +480,26 @@ LFS2_API int lfs2_conv_post_tanh(const void* x_hi, const void* x_lo, const float
                                  const int* lengths, float slope, float* out, int batch, int t, int c, int ksize,
                                  void* stream);
 
+/* ---- FastDiff variance adaptor glue (reference litfass/fastspeech2/fastdiff_variances.py) ----
+ * The noise-predicting networks reuse the predictor-stack kernels (lfs2_dwconv1d_planes + lfs2_gemm_tc with the
+ * ReLU + LayerNorm epilogue + lfs2_rowdot_mask); these are the element-wise pieces around them. */
+/* out (batch, dim) = [sin(steps[b] * e_i) | cos(steps[b] * e_i)], e_i = 10000^(-i / (dim/2 - 1))
+ * (third_party/fastdiff/module/util.py:318-343) */
+LFS2_API int lfs2_diffusion_step_embed(const float* steps, float* out, int batch, int dim, void* stream);
+/* x <- x * sigmoid(x) in place (FastDiff.py swish; fastdiff_variances.py:196-197) */
+LFS2_API int lfs2_swish(float* x, long long n, void* stream);
+/* out[b,t,:] = (xt[b,t] * w_in + b_in + c[b,t,:]) + noise_embed[b,:]: the scalar track lifted to d channels by
+ * Linear(1, d), plus the condition, plus the projected step embedding (fastdiff_variances.py:199-208) */
+LFS2_API int lfs2_diffusion_input(const float* xt, const float* w_in, const float* b_in, const float* c,
+                                  const float* noise_embed, float* out, int batch, int t, int d, void* stream);
+/* out[b,t] = (a[b] * x[b,t] + e[b] * y[b,t]) * s[b] + g[b] * z[b,t] + add with per-utterance coefficient vectors (a, y/e,
+ * s, z/g optional); positions with zero_mask[b,t] != 0 (optional) are written as 0: q(x_t | x_0) = alpha_t x_0 + delta_t z
+ * (:185-190), the DDPM reverse update x <- (x - k eps) / sqrt(1 - beta) + sigma noise (util.py:224-228) and the affine
+ * de-normalisation of the duration track (fastdiff_variances.py:108) */
+LFS2_API int lfs2_diffusion_mix(const float* x, const float* y, const float* z, const float* a, const float* e,
+                                const float* s, const float* g, float add, const uint8_t* zero_mask, float* out,
+                                int batch, int t, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,11 @@ SIGNATURES = {
     "lfs2_mean3_lrelu_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _ll, _f, _f, _vp],
     "lfs2_mel_to_planes": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "lfs2_conv_post_tanh": [_vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _vp],
+    # FastDiff variance adaptor glue
+    "lfs2_diffusion_step_embed": [_vp, _vp, _i, _i, _vp],
+    "lfs2_swish": [_vp, _ll, _vp],
+    "lfs2_diffusion_input": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
+    "lfs2_diffusion_mix": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i, _vp],
     # train-step config
     "lfs2_add_layernorm_train": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _f, ctypes.c_ulonglong, ctypes.c_uint, _vp],
     "lfs2_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],

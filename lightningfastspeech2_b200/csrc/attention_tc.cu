@@ -550,14 +550,16 @@ int launch_attention_tc_pp(const void* qkv, int f16, const uint8_t* kpm, const i
                            float* ctx_f32, int batch, int t, int d, int nhead, const int* row_limit, int limit_extra,
                            cudaStream_t s);
 
-// LFS2_ATTN_PP=0 selects the one-CTA-per-SM kernel of this file for single-plane operands too (A/B measurements)
-static bool attn_pp_enabled() {
-  static int on = -1;
-  if (on < 0) {
+// single-plane operands, head_dim 128: LFS2_ATTN_PP = 1 (default) two CTAs per SM with thread = whole query row
+// (attention_tc_pp.cu); 2 = two CTAs per SM with warp pairs (attention_tc_wide.cu, NC = 1); 0 = the one-CTA-per-SM kernel
+// of this file (A/B measurements)
+static int attn_pp_variant() {
+  static int v = -1;
+  if (v < 0) {
     const char* e = getenv("LFS2_ATTN_PP");
-    on = (e && e[0] == '0') ? 0 : 1;
+    v = e ? atoi(e) : 1;
   }
-  return on == 1;
+  return v;
 }
 
 }  // namespace tc
@@ -617,7 +619,10 @@ int lfs2_attention_tc_ex(const void* qkv_hi, const void* qkv_lo, int operand_for
   attn_kend_kernel<<<ceil_div((long long)batch * 32, 128), 128, 0, s>>>(key_padding_mask, kend, batch, t);
   LFS2_CHECK_LAUNCH("attn_kend");
 
-  if (npass == 1 && attn_pp_enabled())
+  if (npass == 1 && attn_pp_variant() == 2)
+    return lfs2_attention_tc_wide(qkv_hi, operand_format, key_padding_mask, ctx_hi, ctx_lo, ctx_f32, workspace, batch, t, d,
+                                  nhead, row_limit, limit_extra, stream);
+  if (npass == 1 && attn_pp_variant() == 1)
     return launch_attention_tc_pp(qkv_hi, operand_format == LFS2_OPERAND_F16, key_padding_mask, kend, ctx_hi, ctx_lo,
                                   ctx_f32, batch, t, d, nhead, row_limit, limit_extra, s);
 

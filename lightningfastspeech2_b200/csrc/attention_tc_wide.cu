@@ -29,20 +29,30 @@ constexpr int kWSlot = kWK * kWC * 2;     // 16 KB
 constexpr int kWThreads = 352;
 constexpr int kWE = kWK / 2;      // keys per softmax thread and step
 
-template <int NC>
+// CTAS = CTAs that share an SM (1, or 2 for head_dim 128: half the tensor memory and shared memory each, so that two
+// independent CTAs de-phase each other's softmax / MMA phases, see attention_tc_pp.cu)
+template <int NC, int CTAS = 1>
 struct WideCfg {
   static constexpr int kQBytes = NC * kWQ * kWC * 2;                          // 32 KB per chunk
-  // 227 KB per CTA minus the static barriers / exchange buffers (~2.4 KB) and the 1 KB alignment slack
-  static constexpr int kRing = (222 * 1024 - kQBytes) / kWSlot;               // slots available to both rings
+  // 227 KB per SM minus the static barriers / exchange buffers (~2.4 KB per CTA) and the 1 KB alignment slack
+  static constexpr int kBudget = (CTAS == 2 ? 110 : 222) * 1024;
+  static constexpr int kRing = (kBudget - kQBytes) / kWSlot;                  // slots available to both rings
   static constexpr int kKS = kRing / 2 + (kRing & 1), kVS = kRing / 2;        // K ring, V ring
   static constexpr int kSmem = kQBytes + (kKS + kVS) * kWSlot + 1024;
   static constexpr uint32_t kColS = 0, kColO = 128;
-  static_assert(kColO + NC * kWC <= 512, "tensor memory budget");
+  static constexpr uint32_t kTmemCols = CTAS == 2 ? 256 : 512;
+  static_assert(kColO + NC * kWC <= kTmemCols, "tensor memory budget");
   static_assert(kKS >= 2 && kVS >= 2, "rings need at least two slots");
-  static_assert(kSmem + 4096 <= 227 * 1024, "shared memory budget");
+  static_assert(CTAS * (kSmem + 4096) <= 227 * 1024 + (CTAS - 1) * 2048, "shared memory budget");
 };
 constexpr int kWMaxSlots = 8;
-static_assert(WideCfg<2>::kKS <= kWMaxSlots && WideCfg<3>::kKS <= kWMaxSlots, "barrier arrays");
+static_assert(WideCfg<2>::kKS <= kWMaxSlots && WideCfg<3>::kKS <= kWMaxSlots && WideCfg<1, 2>::kKS <= kWMaxSlots,
+              "barrier arrays");
+__device__ __forceinline__ void w_tmem_alloc(uint32_t* smem_out, uint32_t ncols) {  // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ void w_tmem_ld32_nowait(uint32_t taddr, float* v) {
   uint32_t* r = reinterpret_cast<uint32_t*>(v);
@@ -100,11 +110,11 @@ __global__ void wide_kend_kernel(const uint8_t* __restrict__ kpm, int* __restric
   if (lane == 0) kend[b] = last;
 }
 
-template <int NC, int FMT>
-__global__ void __launch_bounds__(kWThreads, 1)
+template <int NC, int FMT, int CTAS>
+__global__ void __launch_bounds__(kWThreads, CTAS)
 attention_tc_wide_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_q,
                          const WideParams p) {
-  using Cfg = WideCfg<NC>;
+  using Cfg = WideCfg<NC, CTAS>;
   constexpr int kKS = Cfg::kKS, kVS = Cfg::kVS;
   constexpr uint32_t kColS = Cfg::kColS, kColO = Cfg::kColO;
   constexpr int kDH = NC * kWC;
@@ -145,7 +155,7 @@ attention_tc_wide_kernel(const __grid_constant__ CUtensorMap map_kv, const __gri
     mbar_init(&o_final, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
+  if (warp == 1) w_tmem_alloc(&tmem_base_smem, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -376,15 +386,15 @@ attention_tc_wide_kernel(const __grid_constant__ CUtensorMap map_kv, const __gri
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, Cfg::kTmemCols);
   }
 }
 
-template <int NC, int FMT>
+template <int NC, int FMT, int CTAS = 1>
 static int launch_wide(const CUtensorMap& kv, const CUtensorMap& q, const WideParams& p, int batch, int nhead,
                        cudaStream_t s) {
-  constexpr int kSmem = WideCfg<NC>::kSmem;
-  auto kern = attention_tc_wide_kernel<NC, FMT>;
+  constexpr int kSmem = WideCfg<NC, CTAS>::kSmem;
+  auto kern = attention_tc_wide_kernel<NC, FMT, CTAS>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) {
@@ -417,8 +427,8 @@ extern "C" int lfs2_attention_tc_wide(const void* qkv, int operand_format, const
   LFS2_REQUIRE(batch > 0 && t > 0 && d > 0 && nhead > 0 && d % nhead == 0, LFS2_ERR_INVALID_ARG,
                "attention_tc_wide: bad shape");
   const int dh = d / nhead;
-  LFS2_REQUIRE(dh == 256 || dh == 384, LFS2_ERR_UNSUPPORTED,
-               "attention_tc_wide: head_dim %d (256 and 384 are implemented; 128 is lfs2_attention_tc)", dh);
+  LFS2_REQUIRE(dh == 128 || dh == 256 || dh == 384, LFS2_ERR_UNSUPPORTED,
+               "attention_tc_wide: head_dim %d (128, 256 and 384 are implemented)", dh);
   LFS2_REQUIRE(batch <= 65535 && nhead <= 65535, LFS2_ERR_UNSUPPORTED, "attention_tc_wide: batch/heads exceed grid limits");
   LFS2_REQUIRE(aligned16(qkv) && (!ctx_hi || (aligned16(ctx_hi) && aligned16(ctx_lo))) && (!ctx_f32 || aligned16(ctx_f32)),
                LFS2_ERR_INVALID_ARG, "attention_tc_wide: pointers must be 16-byte aligned");
@@ -442,6 +452,8 @@ extern "C" int lfs2_attention_tc_wide(const void* qkv, int operand_format, const
   p.row_limit = row_limit;
   p.limit_extra = limit_extra;
   const bool f16 = operand_format == LFS2_OPERAND_F16;
+  if (dh == 128)  // two CTAs per SM, warp pairs (variant 2 of lfs2_attention_tc_ex's single-plane kernels)
+    return f16 ? launch_wide<1, kFmtF16, 2>(kv, q, p, batch, nhead, s) : launch_wide<1, kFmtBF16, 2>(kv, q, p, batch, nhead, s);
   if (dh == 384)
     return f16 ? launch_wide<3, kFmtF16>(kv, q, p, batch, nhead, s) : launch_wide<3, kFmtBF16>(kv, q, p, batch, nhead, s);
   return f16 ? launch_wide<2, kFmtF16>(kv, q, p, batch, nhead, s) : launch_wide<2, kFmtBF16>(kv, q, p, batch, nhead, s);

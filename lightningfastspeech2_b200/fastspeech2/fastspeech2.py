@@ -207,9 +207,6 @@ class FastSpeech2(_Base):
         hp = self.hparams
 
         # -- what the reference would reject or what is outside the hot path ------------------
-        if fastdiff_variances:
-            raise NotImplementedError("fastdiff_variances=True (FastDiff variance adaptor) is out of scope; "
-                                      "pass fastdiff_variances=False for the VarianceAdaptor named by the path")
         if fastdiff_model is not None or fastdiff_speakers:
             raise NotImplementedError("joint FastDiff vocoder / speaker generator")
         if "dvector" not in speaker_type:
@@ -302,6 +299,14 @@ class FastSpeech2(_Base):
 
     def _make_variance_adaptor(self):
         hp = self.hparams
+        if hp.fastdiff_variances:  # reference :302-320
+            from .fastdiff_variances import FastDiffVarianceAdaptor
+
+            return FastDiffVarianceAdaptor(
+                self.stats, hp.variances, hp.variance_nlayers, hp.variance_kernel_size, hp.variance_dropout,
+                hp.variance_filter_size, hp.variance_nbins, hp.variance_depthwise_conv, hp.duration_nlayers,
+                hp.duration_kernel_size, hp.duration_dropout, hp.duration_filter_size, hp.duration_depthwise_conv,
+                hp.encoder_hidden, self._max_frames()).to(self.device)
         return VarianceAdaptor(
             self.stats, hp.variances, hp.variance_levels, hp.variance_transforms, hp.variance_nlayers,
             hp.variance_kernel_size, hp.variance_dropout, hp.variance_filter_size, hp.variance_nbins,
@@ -366,6 +371,8 @@ class FastSpeech2(_Base):
         if dev.type != "cuda":
             raise ops._lib.Lfs2Error("FastSpeech2.forward needs the model on a CUDA device: there is no CPU path")
         hp = self.hparams
+        if hp.fastdiff_variances:
+            return self._forward_fastdiff(targets, inference, force or {})
         if not inference and self.training and torch.is_grad_enabled() and not force and not control:
             return self._forward_train(targets)
         if inference and self.length_buckets > 1 and targets["phones"].shape[0] > 1:
@@ -442,6 +449,55 @@ class FastSpeech2(_Base):
             result[f"variances_{var}"] = variance_output[f"variances_{var}"]
             if f"_bucket_{var}" in variance_output:
                 result[f"_bucket_{var}"] = variance_output[f"_bucket_{var}"]
+        return result
+
+    # -- FastDiff variance adaptor (reference fastdiff_variances.py, fastspeech2.py:302-320, 769-776) ----
+    def _forward_fastdiff(self, targets, inference, force):
+        """Same path with the diffusion adaptor between encoder and decoder.  ``force`` may carry the random draws of a
+        parity run: "noise" (list of tensors in the reference's draw order), "steps" ({name: (B) int64}), "jitter"
+        ((B, Tp)), "N" (reverse steps, default 4) and "duration_rounded"."""
+        dev, hp = self.device, self.hparams
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("training the FastDiff variance adaptor needs backward kernels that are not written; "
+                                      "inference and the teacher-forced forward (eval / no_grad) run on the CUDA path")
+        if self.skip_pad_rows or self.length_buckets > 1:
+            raise NotImplementedError("skip_pad_rows / length_buckets with the FastDiff variance adaptor")
+        phones = targets["phones"].to(dev, non_blocking=True).contiguous()
+        speakers = targets["speaker"].to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+        spk = self.speaker_embedding.project(speakers)
+        pe = self.positional_encoding.pe
+        output, src_mask = ops.embed_pe_spk(phones, self.phone_embedding.weight, pe, spk)
+        output = self.encoder(output, src_key_padding_mask=src_mask)
+        if len(hp.priors):
+            zero_pe = torch.zeros(1, max(output.shape[1], 1), output.shape[2], device=dev)
+            for prior in hp.priors:
+                term, _ = self.prior_embeddings[prior].term(targets[f"priors_{prior}"])
+                ops.add_pe_spk_(output, zero_pe, term)
+        noise = list(force["noise"]) if force.get("noise") is not None else None
+        vo = self.variance_adaptor(output, src_mask, targets, inference=inference, N=force.get("N", 4), noise=noise,
+                                   steps=force.get("steps"), jitter=force.get("jitter"),
+                                   force={k: v for k, v in force.items() if k == "duration_rounded"})
+        tgt_mask = vo["tgt_mask"]
+        output = ops.add_pe_spk_(vo["x"], pe, spk)
+        if self.compute_mode != "simt" and hp.decoder_hidden % 32 == 0 and hp.n_mels % 16 == 0:
+            outp = self.decoder(output, src_key_padding_mask=tgt_mask, return_planes=True)
+            wmel = self._mel_pack.get([self.linear.weight], lambda: ops.split_bf16(self.linear.weight.detach().contiguous()))
+            mel = ops.gemm_tc(outp, wmel, self.linear.bias, npass=3 if self.compute_mode == "fp32" else 1, tag="mel_linear")
+        else:
+            mel = ops.linear(self.decoder(output, src_key_padding_mask=tgt_mask), self.linear.weight, self.linear.bias,
+                             tag="mel_linear")
+        result = {"mel": mel, "duration_prediction": vo["duration_prediction"], "duration_rounded": vo["duration_rounded"],
+                  "src_mask": src_mask, "tgt_mask": tgt_mask}
+        if hasattr(self, "fastdiff_linear") and vo["out"] is not None:
+            zero_pe = torch.zeros(1, mel.shape[1], hp.decoder_hidden, device=dev)
+            h = ops.add_pe_spk_(vo["out"], zero_pe, spk)
+            h = ops.linear(h, self.fastdiff_linear[0].weight, self.fastdiff_linear[0].bias)
+            h = ops.linear(h, self.fastdiff_linear[1].weight, self.fastdiff_linear[1].bias)
+            result["fastdiff_var"] = h * 0.1
+        for var in hp.variances:
+            result[f"variances_{var}"] = vo[f"variances_{var}"]
+            result[f"variances_{var}_z"] = vo[f"variances_{var}_z"]
+        result["duration_z"] = vo["duration_z"]
         return result
 
     # -- PAD-row skipping synthesis (SURVEY 8f N2: "drop PAD-row compute where provably unobservable") ----------

@@ -500,12 +500,15 @@ class LengthRegulator(nn.Module):
 
     def __init__(self, pad_to_multiple_of=None):
         super().__init__()
-        if pad_to_multiple_of is not None:
-            raise NotImplementedError("pad_to_multiple_of (only the FastDiff adaptor uses it)")
         self.pad_to_multiple_of = pad_to_multiple_of
 
     def forward(self, x, durations, max_length=None, scan=None, frames=None):
-        return ops.length_regulate(x.contiguous(), durations.to(x.device), max_length, scan=scan, frames=frames)
+        """pad_to_multiple_of (model.py:356-357, 362-366; the FastDiff adaptor's regulator): the output length
+        min(longest, int(max_length)) is rounded UP to the multiple, and frames up to that rounded length are kept --
+        an utterance longer than int(max_length) keeps its frames up to the rounded length, like the reference's
+        pad_sequence + cut."""
+        return ops.length_regulate(x.contiguous(), durations.to(x.device), max_length, scan=scan, frames=frames,
+                                   pad_to_multiple_of=self.pad_to_multiple_of)
 
 
 class VarianceAdaptor(nn.Module):

@@ -269,7 +269,7 @@ def length_regulate_scatter(x, cum, lengths, l, cap):
     return out, mask
 
 
-def length_regulate(x, durations, max_length, scan=None, frames=None):
+def length_regulate(x, durations, max_length, scan=None, frames=None, pad_to_multiple_of=None):
     """LengthRegulator.forward: x (B,Tp,d) any dtype, durations (B,Tp) int32/int64 ->
     (out (B,L,d), mask (B,L) bool), L = min(longest, int(max_length)).  One host read-back (the maximum length).
     scan = a precomputed length_regulate_scan result; frames = (l, cap) overrides the output length
@@ -280,6 +280,8 @@ def length_regulate(x, durations, max_length, scan=None, frames=None):
     if frames is None:
         longest = int(mx.item())  # the single device->host sync of the path
         l = cap = min(longest, int(max_length)) if max_length is not None else longest
+        if pad_to_multiple_of is not None:
+            l = cap = -(-l // pad_to_multiple_of) * pad_to_multiple_of
     else:
         l, cap = frames
     return length_regulate_scatter(x, cum, lengths, l, cap)
@@ -574,6 +576,49 @@ def attention_tc_wide(qkv, kpm, nhead, want_f32=False, want_planes=True, row_lim
             _p(po.lo if po else None), _p(ctx), _p(ws), b, t, d, nhead, _p(lim), int(extra), _s(),
             tag="lfs2_attention_tc", flops=fl, nbytes=2.0 * qkv.numel() + 4.0 * b * t * d * (int(want_f32) + int(want_planes)))
     return ctx, po
+
+
+# ---------------------------------------------------------------------------------------------
+# FastDiff variance adaptor glue
+def diffusion_step_embed(steps, dim):
+    """steps (B) fp32 -> (B, dim) sin / cos embedding"""
+    _chk(steps, torch.float32, "diffusion steps", 1)
+    out = torch.empty(steps.shape[0], dim, device=steps.device, dtype=torch.float32)
+    _launch("lfs2_diffusion_step_embed", _p(steps), _p(out), steps.shape[0], dim, _s())
+    return out
+
+
+def swish_(x):
+    _chk(x, torch.float32, "swish input")
+    _launch("lfs2_swish", _p(x), x.numel(), _s())
+    return x
+
+
+def diffusion_input(xt, w_in, b_in, c, noise_embed):
+    """xt (B,T), w_in / b_in (d), c (B,T,d), noise_embed (B,d) -> (B,T,d)"""
+    _chk(xt, torch.float32, "noisy track", 2); _chk(c, torch.float32, "condition", 3)
+    b, t, d = c.shape
+    out = torch.empty_like(c)
+    _launch("lfs2_diffusion_input", _p(xt), _p(w_in), _p(b_in), _p(c), _p(noise_embed), _p(out), b, t, d, _s(),
+            nbytes=4.0 * b * t * (2 * d + 1))
+    return out
+
+
+def diffusion_mix(x, a=None, y=None, e=None, s=None, z=None, g=None, add=0.0, zero_mask=None):
+    """(a[b] x + e[b] y) * s[b] + g[b] z + add on (B,T) tracks with (B) coefficient vectors; zero where zero_mask"""
+    _chk(x, torch.float32, "track", 2)
+    for v in (y, z):
+        if v is not None:
+            _chk(v, torch.float32, "track", 2)
+    for v in (a, e, s, g):
+        if v is not None:
+            _chk(v, torch.float32, "per-utterance coefficients", 1)
+    if zero_mask is not None:
+        _chk(zero_mask, torch.bool, "mask", 2)
+    out = torch.empty_like(x)
+    _launch("lfs2_diffusion_mix", _p(x), _p(y), _p(z), _p(a), _p(e), _p(s), _p(g), float(add), _p(zero_mask), _p(out),
+            x.shape[0], x.shape[1], _s())
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
