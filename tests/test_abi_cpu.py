@@ -75,9 +75,21 @@ def test_param_counts_match_survey():
         assert n == count, preset
 
 
+def test_reference_default_kwargs_build_the_fastdiff_adaptor():
+    """the reference's constructor defaults (fastdiff_variances=True, 3 frame-level variances) construct, with the
+    reference's module tree and key names (fastspeech2.py:302-320)"""
+    from lightningfastspeech2_b200.fastspeech2.fastdiff_variances import FastDiffVarianceAdaptor
+
+    stats = {v: {"min": -3.0, "max": 3.0, "mean": 0.0, "std": 1.0} for v in ("pitch", "energy", "snr")}
+    m = FastSpeech2(stats=stats, phone2id={"a": 0}, num_workers=0)
+    assert isinstance(m.variance_adaptor, FastDiffVarianceAdaptor) and m.variance_adaptor.length_regulator.pad_to_multiple_of == 64
+    keys = set(m.state_dict())
+    assert {"variance_adaptor.duration_predictor.linear_in.weight", "variance_adaptor.duration_predictor.fc_t1.weight",
+            "variance_adaptor.encoders.snr.predictor.linear_noise.bias", "variance_adaptor.encoders.pitch.bins",
+            "variance_adaptor.encoders.energy.embedding.weight"} <= keys
+
+
 def test_unsupported_configs_raise():
-    with pytest.raises(NotImplementedError):
-        FastSpeech2(stats={}, phone2id={"a": 0}, num_workers=0)  # reference default fastdiff_variances=True
     with pytest.raises(NotImplementedError):
         FastSpeech2(stats={}, phone2id={"a": 0}, num_workers=0, **dict(configs.C2, speaker_type="id"))
 
