@@ -354,6 +354,19 @@ def measure_c1(dev, steps=30):
         mel, r = once()
         lat.append((time.perf_counter() - t0) * 1e3)
     frames = int((~r["tgt_mask"]).sum())
+    # the same call with model.cuda_graphs = True: the ~100 short launches of a 1-utterance call replayed as two CUDA
+    # graphs (encoder side | one host read-back of the frame count | decoder side); bit-identical results
+    model.cuda_graphs = True
+    for _ in range(4):
+        mel_g, _ = once()
+    lat_g = []
+    for _ in range(steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        mel_g, _ = once()
+        lat_g.append((time.perf_counter() - t0) * 1e3)
+    graphs_identical = bool(torch.equal(mel_g, mel))
+    model.cuda_graphs = False
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     resident = {k: v.to(dev) for k, v in pinned.items()}
     torch.cuda.synchronize()
@@ -379,6 +392,8 @@ def measure_c1(dev, steps=30):
     return {"workload": "C1: dense-conv FastSpeech2 (k=9, d=256, 4+4 FFTBlocks, 24.5M params), 1 utterance x 128 phonemes, "
                         "fp32-parity mode (BASELINE.json configs[0])",
             "latency_ms_e2e_median": ms, "latency_ms_device": dev_ms, "valid_frames": frames,
+            "latency_ms_e2e_median_cuda_graphs": statistics.median(lat_g),
+            "cuda_graphs_bit_identical": graphs_identical,
             "value": frames / (ms * 1e-3), "unit": UNIT, "steps": steps,
             "cpu_baseline": {"latency_ms": cpu_ms, "value": int((~ref["tgt_mask"]).sum()) / (cpu_ms * 1e-3), "unit": UNIT,
                              "cores": os.cpu_count(), "kind": "port", "sample": "the same utterance, median of 3 runs"},
@@ -893,8 +908,9 @@ def run_lfs2(args):
                     "achieved": achieved, "peak": peak, "unit": unit, "frac": achieved / peak,
                     # fp32-parity mode issues 3 bf16 MMA passes (hi.hi + lo.hi + hi.lo) per algorithmic product:
                     # `achieved`/`frac` count each product ONCE; the tensor pipe executes 3x that
-                    "mma_passes": 3 if top["bound"] == "tensor" else None,
-                    "issued_frac": (3 * achieved / peak) if top["bound"] == "tensor" else None,
+                    "mma_passes": round(top["issued_flops"] / top["flops"]) if top["bound"] == "tensor" and top["flops"] else None,
+                    "issued_frac": (top["issued_flops"] / top["launches"] / per_launch_s / 1e12 / peak)
+                    if top["bound"] == "tensor" else None,
                     "traffic": ncu_traffic(top_name),
                     "peak_source": pk["src"] + (" (bf16_tflops_sustained)" if top["bound"] == "tensor" else " (hbm_gbs)"), "us_per_launch": per_launch_s * 1e6,
                     "share_of_step": top["ms"] / total_ms,
@@ -902,11 +918,16 @@ def run_lfs2(args):
                         prof.items(), key=lambda kv: -kv[1]["ms"])},
                     # every kernel of the step against ITS roofline (algorithmic bytes / flops of SURVEY 8d, CUDA
                     # events on the launching stream): frac = max(bytes/t / HBM peak, flops/t / tensor peak)
+                    # frac = algorithmic (each product counted once); frac_issued = against the roofline of the mode the
+                    # kernel runs in: a split-bf16 product is 3 MMA passes, so its tensor roofline is a third of the peak
                     "per_kernel": {k: {"launches": v["launches"], "ms": round(v["ms"], 4), "bound": v["bound"],
                                        "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else 0.0,
                                        "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 1) if v["ms"] > 0 else 0.0,
                                        "frac": round(max(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm"],
                                                          v["flops"] / (v["ms"] * 1e-3) / 1e12 / pk["tensor_sustained"]), 3)
+                                       if v["ms"] > 0 else 0.0,
+                                       "frac_issued": round(max(v["bytes"] / (v["ms"] * 1e-3) / 1e9 / pk["hbm"],
+                                                                v["issued_flops"] / (v["ms"] * 1e-3) / 1e12 / pk["tensor_sustained"]), 3)
                                        if v["ms"] > 0 else 0.0}
                                    for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:12]}}
         # bounded CPU sample of the same workload: grow the sub-batch until one run takes >= ~10 s of CPU work

@@ -377,6 +377,9 @@ class FastSpeech2(_Base):
             return self._forward_train(targets)
         if inference and self.length_buckets > 1 and targets["phones"].shape[0] > 1:
             return self._forward_bucketed(targets, control, force)
+        if inference and self.cuda_graphs and not force and not control and ops.PROFILE is None \
+                and not self._skips_pad_rows(inference):
+            return self._forward_graphed(targets)
         st = self._encode_stage(targets, inference, force, control)
         return self._decode_stage(st, targets, inference, force, control)
 
@@ -565,6 +568,40 @@ class FastSpeech2(_Base):
         entry["graph"].replay()
         ops._lib.CALLS += entry["launches"]
         return entry["out"], True
+
+    # -- whole-call CUDA graphs (small batches are launch-bound: ~100 short kernels, ~15 us of Python + ctypes each) -----
+    # `model.cuda_graphs = True`: an inference call is split at its one host read-back (the LengthRegulator's frame
+    # count) into an encoder-side and a decoder-side kernel sequence; each is captured the second time its shape is seen
+    # and replayed afterwards (same machinery and invalidation rules as the bucketed path).  Results are copied out of
+    # the graphs' static buffers, so they stay valid across calls.  Bit-identical to the eager path.
+    cuda_graphs = False
+
+    def _forward_graphed(self, targets):
+        dev = self.device
+        self._graphs_validate()
+        phones = targets["phones"].to(dev, non_blocking=True).contiguous()
+        speaker = targets["speaker"].to(dev, dtype=torch.float32, non_blocking=True).contiguous()
+
+        def enc_fn(ph, sp):
+            st = self._encode_stage({"phones": ph, "speaker": sp}, True, None, None)
+            st["scan"] = ops.length_regulate_scan(st["duration_rounded"], st["enc"].shape[:2])
+            return st
+
+        key = ("EW", tuple(phones.shape), self.compute_mode)
+        st, replayed = self._graphed(key, enc_fn, [phones, speaker])
+        longest = int(st["scan"][2].item())  # the single device->host sync of the path
+        l = min(longest, int(self.variance_adaptor.max_length))
+
+        def dec_fn(st=st, l=l):
+            return self._decode_stage(st, None, True, None, None, scan=st["scan"], frames=(l, l))
+
+        if replayed:  # the encoder stage's outputs live at fixed addresses: the decoder graph can bake them in
+            r, dec_replayed = self._graphed(("DW", key, self._graphs[key]["gen"], l), dec_fn, [])
+        else:
+            r, dec_replayed = dec_fn(), False
+        if replayed or dec_replayed:  # static buffers are overwritten by the next replay
+            r = {k: (v.clone() if torch.is_tensor(v) else v) for k, v in r.items()}
+        return r
 
     def _halos(self):
         """(encoder side, decoder side): rows beyond an utterance's end that can still influence its valid

@@ -21,14 +21,15 @@ WEIGHTS_EPOCH = 0
 PROFILE = None
 
 
-def _launch(cname, *args, tag=None, flops=0.0, nbytes=0.0):
+def _launch(cname, *args, tag=None, flops=0.0, nbytes=0.0, passes=1):
+    """passes: tensor-core MMA passes issued per algorithmic product (3 for split-bf16 operands, 1 otherwise)"""
     fn = getattr(_lib.lib(), cname)
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         rc = fn(*args)
         e1.record()
-        PROFILE.setdefault(tag or cname, []).append((e0, e1, float(flops), float(nbytes)))
+        PROFILE.setdefault(tag or cname, []).append((e0, e1, float(flops), float(nbytes), float(flops) * passes))
     else:
         rc = fn(*args)
     _lib.CALLS += 1
@@ -57,11 +58,12 @@ def collect_profile(hbm_gbs=None, tensor_tflops=None):
     torch.cuda.synchronize()
     out = {}
     for tag, recs in (PROFILE or {}).items():
-        ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
+        ms = sum(r[0].elapsed_time(r[1]) for r in recs)
         fl = sum(r[2] for r in recs)
         by = sum(r[3] for r in recs)
-        bound = "tensor" if fl / (tensor_tflops * 1e12) > by / (hbm_gbs * 1e9) else "hbm"
-        out[tag] = {"ms": ms, "launches": len(recs), "flops": fl, "bytes": by, "bound": bound}
+        issued = sum(r[4] for r in recs)   # flops the tensor pipe executes (x3 for split-bf16 products)
+        bound = "tensor" if issued / (tensor_tflops * 1e12) > by / (hbm_gbs * 1e9) else "hbm"
+        out[tag] = {"ms": ms, "launches": len(recs), "flops": fl, "bytes": by, "issued_flops": issued, "bound": bound}
     return out
 
 
@@ -469,7 +471,7 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
             _p(residual.lo if residual is not None else None), _p(ident), _p(gamma), _p(beta), float(eps),
             _p(of if of is not None else po.hi), _p(po.lo if out == "planes" else None), OUT_KINDS[out], npass, _p(lim),
             int(extra), _p(ws), _p(row_mask), _s(), tag=tag or f"gemm_tc_n{n}_k{taps * d}",
-            flops=2.0 * m * n * taps * d,
+            flops=2.0 * m * n * taps * d, passes=npass,
             nbytes=4.0 * m * d + 4.0 * n * taps * d + out_bytes * m * n + (4.0 * m * n if residual is not None else 0.0))
     return of if out == "f32" else po
 
@@ -507,7 +509,7 @@ def ffn_fused_tc(u, w1, b1, w2, b2, residual, gamma, beta, eps=LN_EPS, npass=3, 
         m = m * _limited_fraction(row_limit, t)
     _launch("lfs2_ffn_fused_tc_limited", _p(u.hi), _p(u.lo), batch, t, _p(w1.hi), _p(w1.lo), f, _p(b1), _p(w2.hi),
             _p(w2.lo), _p(b2), _p(residual.hi), _p(residual.lo), _p(ident), _p(gamma), _p(beta), float(eps), _p(out.hi),
-            _p(out.lo), npass, _p(lim), int(extra), _p(ws), _s(), tag="ffn_fused", flops=4.0 * m * d * f,
+            _p(out.lo), npass, _p(lim), int(extra), _p(ws), _s(), tag="ffn_fused", flops=4.0 * m * d * f, passes=npass,
             nbytes=4.0 * m * d * 3 + 8.0 * d * f)
     return out
 
@@ -546,7 +548,7 @@ def attention_tc(qkv, kpm, nhead, npass=3, want_f32=False, want_planes=True, row
     in_bytes = (2.0 if f16 else 4.0) * qkv.hi.numel()
     _launch("lfs2_attention_tc_ex", _p(qkv.hi), _p(qkv.lo), 1 if f16 else 0, _p(kpm), _p(po.hi if po else None),
             _p(po.lo if po else None), _p(ctx), _p(ws), b, t, d, nhead, npass, _p(lim), int(extra), _s(),
-            tag="lfs2_attention_tc", flops=fl,
+            tag="lfs2_attention_tc", flops=fl, passes=npass,
             nbytes=(in_bytes + 4.0 * b * t * d * (int(want_f32) + int(want_planes))) * frac)
     return ctx, po
 
@@ -876,7 +878,7 @@ def gemm_tc2(a, a_op, b, b_op, c, ldc, m, n, k, nbatch=1, nhead=1, c_bstride=0, 
     _launch("lfs2_gemm_tc2", _p(a.hi), _p(a.lo if npass == 3 else None), ctypes.byref(a_op), _p(b.hi),
             _p(b.lo if npass == 3 else None), ctypes.byref(b_op), ctypes.c_void_p(c.data_ptr() + 4 * c_offset), ldc,
             c_bstride, c_hstride, m, n, k, nbatch, nhead, npass, int(accumulate), _s(), tag=tag or "gemm_tc2",
-            flops=2.0 * m * n * k * nbatch * nhead, nbytes=4.0 * nbatch * nhead * (m * k + n * k + m * n))
+            flops=2.0 * m * n * k * nbatch * nhead, passes=npass, nbytes=4.0 * nbatch * nhead * (m * k + n * k + m * n))
 
 
 def wgrad_tc_ok(n, k):

@@ -225,3 +225,31 @@ def test_attention_operand_recipes_against_the_fp64_goldens(golden_dir, name):
         ConformerEncoderLayer.attention_operands = "f16"
     print(f"{name}: max |mel - fp64| with fp16 single-pass attention {errs['f16']:.2e}, 3-pass split-bf16 {errs['x3']:.2e}")
     assert errs["x3"] < 1e-4 and errs["f16"] < 2e-4, errs
+
+
+@pytest.mark.parametrize("preset,bsz,lo,hi", [("C1", 1, 128, 128), ("C2", 5, 10, 60)])
+def test_whole_call_cuda_graphs_are_bit_identical(preset, bsz, lo, hi):
+    """model.cuda_graphs = True: the encoder-side and decoder-side kernel sequences of an inference call are replayed
+    as CUDA graphs from the second sighting of a shape on; results are bit-identical to the eager path, survive later
+    calls (copied out of the static buffers) and follow weight updates (graphs are dropped when a parameter changes)"""
+    model, sd, hp = _build(preset, 51, "fp32")
+    batches = [synthetic.make_batch(bsz, lo, hi, seed=60 + i, pad_to=hi) for i in range(3)]
+    with torch.no_grad():
+        eager = [model(b, inference=True) for b in batches]
+        model.cuda_graphs = True
+        kept = []
+        for rep in range(3):          # 1st pass eager, 2nd captures, 3rd replays
+            for b, e in zip(batches, eager):
+                r = model(b, inference=True)
+                for k in ("mel", "tgt_mask", "duration_rounded", "duration_prediction"):
+                    assert torch.equal(r[k], e[k]), (rep, k)
+                kept.append((r, e))
+        for r, e in kept:              # earlier results were not overwritten by later replays
+            assert torch.equal(r["mel"], e["mel"])
+        assert any("graph" in v for v in model._graphs.values())
+        # a weight update invalidates the captured graphs
+        model.linear.bias.add_(1.0)
+        r = model(batches[0], inference=True)
+        assert torch.allclose(r["mel"], eager[0]["mel"] + 1.0, atol=1e-5)
+        model.cuda_graphs = False
+        assert torch.equal(model(batches[0], inference=True)["mel"], r["mel"])
