@@ -204,6 +204,21 @@ LFS2_API int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int 
                              const float* beta, float eps, void* out0, void* out1, int out_kind, int npass,
                              const int* row_limit, int limit_extra, void* workspace, const uint8_t* row_mask,
                              void* stream);
+/* One VarianceConvolutionLayer of a depthwise predictor stack (model.py:524-561, filter = channels = 256) with what
+ * FOLLOWS it fused into the LayerNorm epilogue:  z = LayerNorm(relu(a . w^T + bias)), then
+ *   next_dw_w != NULL: out = depthwise3(z) -- the NEXT layer's k = 3 depthwise conv (next_dw_w (3, 256) tap-major, next_dw_b
+ *                      (256)), rows outside the utterance being zeros like Conv1d's padding -- as bf16 hi/lo planes
+ *                      (z[r-1], z[r+1] come from the neighbouring epilogue threads; tiles advance by 126 rows);
+ *   head_w != NULL:    head_out[b, t] = z . head_w + head_b, 0 where head_mask -- the predictor's Linear(256, 1) + masked_fill
+ *                      (model.py:512-518); z itself is never written.
+ * a = depthwise3(previous layer) as bf16 hi/lo planes (batch, t, 256).  row_limit / limit_extra / workspace as in
+ * lfs2_gemm_tc_limited (workspace: lfs2_predictor_layer_tc_workspace_bytes; the stencil form has its own 126-row tile list). */
+LFS2_API long long lfs2_predictor_layer_tc_workspace_bytes(int batch, int t);
+LFS2_API int lfs2_predictor_layer_tc(const void* a_hi, const void* a_lo, int batch, int t, const void* w_hi,
+                                     const void* w_lo, const float* bias, const float* gamma, const float* beta, float eps,
+                                     int npass, const float* next_dw_w, const float* next_dw_b, void* out_hi, void* out_lo,
+                                     const float* head_w, const float* head_b, const uint8_t* head_mask, float* head_out,
+                                     const int* row_limit, int limit_extra, void* workspace, void* stream);
 /* workspace of lfs2_gemm_tc_limited when row_limit != NULL: the compact list of active row tiles.  A later call with
  * row_limit == NULL and the same workspace reuses that list (same batch, t and limit: the layers of one predictor). */
 LFS2_API long long lfs2_gemm_tc_limited_workspace_bytes(int batch, int t);

@@ -42,6 +42,8 @@ SIGNATURES = {
                         _i, _vp, _i, _vp, _vp, _vp],
     "lfs2_attention_tc_ex": [_vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "lfs2_attention_tc_wide": [_vp, _i, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "lfs2_predictor_layer_tc": [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                _i, _vp, _vp],
     "lfs2_dwconv1d_planes_limited": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "lfs2_mask_lengths": [_vp, _vp, _i, _i, _vp],
     "lfs2_zero_masked_rows": [_vp, _vp, _ll, _i, _vp],
@@ -101,6 +103,7 @@ SIGNATURES = {
 # functions whose return type is not int
 RESTYPES = {"lfs2_attention_bwd_workspace_bytes": (ctypes.c_longlong, [_i, _i, _i]),
             "lfs2_gemm_tc_limited_workspace_bytes": (ctypes.c_longlong, [_i, _i]),
+            "lfs2_predictor_layer_tc_workspace_bytes": (ctypes.c_longlong, [_i, _i]),
             "lfs2_ffn_fused_tc_limited_workspace_bytes": (ctypes.c_longlong, [_i, _i])}
 
 class Operand(ctypes.Structure):

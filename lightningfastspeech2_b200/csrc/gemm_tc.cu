@@ -56,19 +56,36 @@ struct GemmTcParams {
   float eps;
   const int* tile_list;         // null, or [0] = number of active m-tiles, [1..] = their indices (b * m_tiles_per_batch + mt):
                                 //   only those row tiles are processed (lfs2_gemm_tc_limited), dealt round-robin to the CTAs
+  int m_step, t_shift;          // row tile i of an utterance starts at i * m_step + t_shift (128 / 0; 126 / -1 for kEpiStencil)
+  // fused predictor epilogues (lfs2_predictor_layer_tc): see EPI below
+  const float* st_w;            // kEpiStencil: (3, n) taps of the NEXT layer's depthwise conv, tap-major; st_b its bias (n)
+  const float* st_b;
+  const float* dot_w;           // kEpiDot: (n) head weight, dot_b (1) its bias, dot_mask (batch, t) or null, dot_out (batch, t)
+  const float* dot_b;
+  const uint8_t* dot_mask;
+  float* dot_out;
 };
+// EPI: what the LayerNorm epilogue does with the normalised row z
+//   kEpiNone     store it (every other use of the kernel)
+//   kEpiStencil  store u = depthwise3(z) -- the k = 3 depthwise conv of the NEXT predictor layer, rows z[r-1], z[r], z[r+1]
+//                taken from the neighbouring epilogue threads (warp shuffles; the rows at a warp's edges through shared
+//                memory).  A tile's first and last row have no neighbour inside the tile, so tiles advance by 126 rows
+//                and store rows 1..126; z rows outside the utterance are zeros (Conv1d's padding).
+//   kEpiDot      store only out[row] = z . dot_w + dot_b (masked): the predictor head (model.py:512-518)
+enum { kEpiNone = 0, kEpiStencil = 1, kEpiDot = 2 };
 
 // active m-tiles of a row-limited launch: utterance b needs the tiles that start before row_limit[b] + extra
 __global__ void gemm_tile_list_kernel(const int* __restrict__ row_limit, int extra, int batch, int m_tiles_per_batch,
-                                      int* __restrict__ list) {
+                                      int* __restrict__ list, int m_step) {
   for (int i = threadIdx.x; i < batch * m_tiles_per_batch; i += blockDim.x) {
     const int b = i / m_tiles_per_batch, mt = i % m_tiles_per_batch;
-    if (mt * kBM < row_limit[b] + extra) list[1 + atomicAdd(list, 1)] = i;
+    if (mt * m_step < row_limit[b] + extra) list[1 + atomicAdd(list, 1)] = i;
   }
 }
 
-template <int N_TILE, int NPASS, bool LN>
+template <int N_TILE, int NPASS, bool LN, int EPI = 0>
 struct SmemLayout {
+  static constexpr int kEdge = EPI == 1 ? 6 * N_TILE * 4 : 0;  // kEpiStencil: 3 "last row" + 3 "first row" vectors of the quadrants
   static constexpr bool kHasLo = NPASS == 3 || LN;  // LN variants stream residual lo planes even in bf16 mode
   static constexpr int kAPlane = kBM * kBK * 2;     // 8 KB
   static constexpr int kWPlane = N_TILE * kBK * 2;
@@ -76,11 +93,12 @@ struct SmemLayout {
   static constexpr int kOffWHi = kAPlane;
   static constexpr int kOffALo = kAPlane + kWPlane;
   static constexpr int kOffWLo = 2 * kAPlane + kWPlane;
-  static constexpr int kFixed = 4 * kStageChunk + (LN ? 3 * N_TILE * 4 + 2 * 2 * kBM * 8 : 0) + 1024;
+  static constexpr int kFixed = 4 * kStageChunk + (LN ? 3 * N_TILE * 4 + 2 * 2 * kBM * 8 : 0) + kEdge + 1024;
   static constexpr int kStages = (226 * 1024 - kFixed) / kStage > 6 ? 6 : (226 * 1024 - kFixed) / kStage;
   static constexpr int kOffStaging = kStages * kStage;                 // 2 halves x 2 chunks, 1024-aligned
   static constexpr int kOffVec = kOffStaging + 4 * kStageChunk;        // bias | gamma | beta for LN: 3 * N_TILE floats
   static constexpr int kOffStats = kOffVec + 3 * N_TILE * 4;           // LN partial (sum, sumsq): [2 tiles][2 halves][128]
+  static constexpr int kOffEdge = kOffStats + 2 * 2 * kBM * 8;         // kEpiStencil edge rows
   static constexpr int kTotal = kStages * kStage + kFixed;
   static_assert(kStages >= 2, "not enough shared memory for a pipeline");
   static_assert(kStage % 1024 == 0, "stage must keep 1024-byte alignment");
@@ -149,7 +167,7 @@ struct TileWalk {
     if (mi < m_count) {
       const int m_tile = p.tile_list ? __ldg(p.tile_list + 1 + mi) : mi;
       b = m_tile / p.m_tiles_per_batch;
-      t0 = (m_tile % p.m_tiles_per_batch) * kBM;
+      t0 = (m_tile % p.m_tiles_per_batch) * p.m_step + p.t_shift;
     } else {  // no such tile: TMA zero-fills loads and drops stores outside the tensor
       b = p.batch;
       t0 = 0;
@@ -167,14 +185,15 @@ __device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
   return r;
 }
 
-template <int N_TILE, int NPASS, bool LN, int OUT, bool MC>
+template <int N_TILE, int NPASS, bool LN, int OUT, bool MC, int EPI = 0>
 __global__ void __launch_bounds__(kGemmTcThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
                const __grid_constant__ CUtensorMap map_ident, const __grid_constant__ CUtensorMap map_o0,
                const __grid_constant__ CUtensorMap map_o1, const GemmTcParams p) {
-  using L = SmemLayout<N_TILE, NPASS, LN>;
+  static_assert(EPI == kEpiNone || (LN && !MC && OUT == kOutPlanes), "fused predictor epilogues ride the LayerNorm variant");
+  using L = SmemLayout<N_TILE, NPASS, LN, EPI>;
   constexpr int kStages = L::kStages;
   constexpr int kAccCols = (N_TILE <= 32) ? 32 : (N_TILE <= 64) ? 64 : (N_TILE <= 128) ? 128 : 256;
   constexpr uint32_t kTmemCols = 2 * kAccCols;
@@ -376,6 +395,108 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         rstd = rsqrtf(fmaxf(q * (1.f / N_TILE) - mean * mean, 0.f) + p.eps);
       }
 
+      if (EPI == kEpiDot) {
+        // ---- predictor head: out[row] = LayerNorm(z)[row] . dot_w + dot_b, masked positions 0; nothing else is stored ----
+        float acc_dot = 0.f;
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; ++c) {
+          tmem_ld32(taddr + c * 32, v);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = activate(v[j] + vec[c * 32 + j], p.relu, p.slope);
+            const float z = (x - mean) * rstd * vec[N_TILE + c * 32 + j] + vec[2 * N_TILE + c * 32 + j];
+            acc_dot = fmaf(z, __ldg(p.dot_w + c * 32 + j), acc_dot);
+          }
+        }
+        float2* st = stats + (it & 1) * 2 * kBM;
+        named_bar_sync(3, 256);                       // both halves have consumed the statistics of this tile
+        st[half * kBM + r].x = acc_dot;
+        named_bar_sync(3, 256);
+        if (half == 0) {
+          const int trow = t0 + r;
+          if (b < p.batch && trow >= 0 && trow < p.t) {
+            const size_t o = (size_t)b * p.t + trow;
+            const float total = acc_dot + st[kBM + r].x + __ldg(p.dot_b);
+            p.dot_out[o] = (p.dot_mask && p.dot_mask[o]) ? 0.f : total;
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        continue;
+      }
+
+      if (EPI == kEpiStencil) {
+        // ---- u = depthwise3(LayerNorm(z)) of the next layer; rows outside the utterance count as zeros ----
+        float* edge = reinterpret_cast<float*>(smem + L::kOffEdge);  // [0..2]: last row of quadrant q, [3..5]: first row of quadrant q+1
+        const int trow = t0 + r;
+        const bool live = b < p.batch && trow >= 0 && trow < p.t;
+        auto norm = [&](int c, int j) -> float {
+          const float x = activate(v[j] + vec[c * 32 + j], p.relu, p.slope);
+          return live ? (x - mean) * rstd * vec[N_TILE + c * 32 + j] + vec[2 * N_TILE + c * 32 + j] : 0.f;
+        };
+        // the rows at the quadrants' edges, for this half's columns, through shared memory
+        // (tcgen05.ld is warp-collective: every lane loads, lanes 0 and 31 publish)
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; ++c) {
+          tmem_ld32(taddr + c * 32, v);
+          if (lane == 31 && quad < 3) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) edge[quad * N_TILE + c * 32 + j] = norm(c, j);
+          }
+          if (lane == 0 && quad > 0) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) edge[(3 + quad - 1) * N_TILE + c * 32 + j] = norm(c, j);
+          }
+        }
+        named_bar_sync(1 + half, 128);   // the four quadrant warps of this half
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; ++c) {
+          tmem_ld32(taddr + c * 32, v);
+          float u[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float z = norm(c, j);
+            float up = __shfl_up_sync(0xffffffffu, z, 1), dn = __shfl_down_sync(0xffffffffu, z, 1);
+            const int col = c * 32 + j;
+            if (lane == 0) up = quad > 0 ? edge[(quad - 1) * N_TILE + col] : 0.f;
+            if (lane == 31) dn = quad < 3 ? edge[(3 + quad) * N_TILE + col] : 0.f;
+            // same association as dwconv1d_k_kernel: bias, then taps 0, 1, 2
+            u[j] = fmaf(__ldg(p.st_w + 2 * N_TILE + col), dn,
+                        fmaf(__ldg(p.st_w + N_TILE + col), z, fmaf(__ldg(p.st_w + col), up, __ldg(p.st_b + col))));
+          }
+          uint8_t* sb = staging + (chunk_ctr & 1) * kStageChunk;
+          ++chunk_ctr;
+          if (r >= 1 && r <= kBM - 2) {  // rows 1..126 are this tile's outputs, staged as rows 0..125
+            const int rr = r - 1;
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_pack2(u[2 * j], u[2 * j + 1], hi[j], lo[j]);
+            uint8_t* rh = sb + rr * 64;
+            uint8_t* rl = rh + kStageChunk / 2;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int o = (i ^ ((rr >> 1) & 3)) << 4;
+              *reinterpret_cast<uint4*>(rh + o) = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+              *reinterpret_cast<uint4*>(rl + o) = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
+          }
+          fence_proxy_async_smem();
+          if (issuer) tma_store_wait_read0();
+          named_bar_sync(1 + half, 128);
+          if (issuer) {  // maps with 126-row boxes; TMA clips the rows past the utterance's end
+            tma_store_3d(&map_o0, sb, n0 + c * 32, t0 + 1, b);
+            tma_store_3d(&map_o1, sb + kStageChunk / 2, n0 + c * 32, t0 + 1, b);
+            tma_store_commit();
+          }
+        }
+        // (the edge rows are only read before a chunk's staging barrier, so the next tile may overwrite them right away)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        continue;
+      }
+
 #pragma unroll 1
       for (int c = c_begin; c < c_end; ++c) {
         const int col0 = n0 + c * 32;
@@ -550,10 +671,10 @@ struct GemmTcMaps {
   CUtensorMap ah, al, wh, wl, rh, rl, ident, o0, o1;
 };
 
-template <int N_TILE, int NPASS, bool LN, int OUT, bool MC>
+template <int N_TILE, int NPASS, bool LN, int OUT, bool MC, int EPI = 0>
 static int launch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, cudaStream_t s) {
-  using L = SmemLayout<N_TILE, NPASS, LN>;
-  auto kern = gemm_tc_kernel<N_TILE, NPASS, LN, OUT, MC>;
+  using L = SmemLayout<N_TILE, NPASS, LN, EPI>;
+  auto kern = gemm_tc_kernel<N_TILE, NPASS, LN, OUT, MC, EPI>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
@@ -726,6 +847,8 @@ int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int t, int d,
   p.has_residual = res_hi != nullptr;
   p.bias = bias; p.relu = activation; p.slope = slope; p.row_mask = row_mask;
   p.gamma = gamma; p.beta = beta; p.eps = eps;
+  p.m_step = kBM; p.t_shift = 0;
+  p.st_w = p.st_b = p.dot_w = p.dot_b = nullptr; p.dot_mask = nullptr; p.dot_out = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   p.tile_list = nullptr;
   if (!row_limit && workspace) {
@@ -737,7 +860,7 @@ int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int t, int d,
       set_error("gemm_tc: memset failed");
       return LFS2_ERR_CUDA;
     }
-    gemm_tile_list_kernel<<<1, 256, 0, s>>>(row_limit, limit_extra, batch, p.m_tiles_per_batch, list);
+    gemm_tile_list_kernel<<<1, 256, 0, s>>>(row_limit, limit_extra, batch, p.m_tiles_per_batch, list, kBM);
     LFS2_CHECK_LAUNCH("gemm_tile_list");
     p.tile_list = list;
   }
@@ -749,6 +872,81 @@ int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int t, int d,
   if (n_tile == 256) return dispatch_gemm_tc<256, false, false>(m, p, npass, out_kind, s);
   if (n_tile == 128) return dispatch_gemm_tc<128, false, false>(m, p, npass, out_kind, s);
   return dispatch_gemm_tc<64, false, false>(m, p, npass, out_kind, s);
+}
+
+long long lfs2_predictor_layer_tc_workspace_bytes(int batch, int t) {
+  return batch > 0 && t > 0 ? (1 + (long long)batch * ((t + 125) / 126)) * (long long)sizeof(int) : 0;
+}
+
+int lfs2_predictor_layer_tc(const void* a_hi, const void* a_lo, int batch, int t, const void* w_hi, const void* w_lo,
+                            const float* bias, const float* gamma, const float* beta, float eps, int npass,
+                            const float* next_dw_w, const float* next_dw_b, void* out_hi, void* out_lo,
+                            const float* head_w, const float* head_b, const uint8_t* head_mask, float* head_out,
+                            const int* row_limit, int limit_extra, void* workspace, void* stream) {
+  constexpr int d = 256, n = 256;
+  LFS2_REQUIRE(a_hi && w_hi && bias && gamma && beta, LFS2_ERR_INVALID_ARG, "predictor_layer_tc: null operand");
+  LFS2_REQUIRE(npass == 1 || npass == 3, LFS2_ERR_INVALID_ARG, "predictor_layer_tc: npass must be 1 or 3");
+  LFS2_REQUIRE(npass == 1 || (a_lo && w_lo), LFS2_ERR_INVALID_ARG, "predictor_layer_tc: npass=3 needs the lo planes");
+  const bool stencil = next_dw_w != nullptr;
+  LFS2_REQUIRE(stencil != (head_w != nullptr), LFS2_ERR_INVALID_ARG,
+               "predictor_layer_tc: exactly one of the next layer's depthwise conv / the head");
+  LFS2_REQUIRE(!stencil || (next_dw_b && out_hi && out_lo), LFS2_ERR_INVALID_ARG, "predictor_layer_tc: stencil outputs missing");
+  LFS2_REQUIRE(stencil || (head_b && head_out), LFS2_ERR_INVALID_ARG, "predictor_layer_tc: head outputs missing");
+  if (batch == 0 || t == 0) return LFS2_OK;
+  LFS2_REQUIRE(batch > 0 && t > 0, LFS2_ERR_INVALID_ARG, "predictor_layer_tc: bad shape");
+  LFS2_REQUIRE(aligned16(a_hi) && aligned16(w_hi) && (!a_lo || aligned16(a_lo)) && (!w_lo || aligned16(w_lo)) &&
+                   (!out_hi || (aligned16(out_hi) && aligned16(out_lo))),
+               LFS2_ERR_INVALID_ARG, "predictor_layer_tc: pointers must be 16-byte aligned");
+  const int m_step = stencil ? kBM - 2 : kBM;
+  GemmTcMaps m;
+  bool ok = make_tmap_3d(&m.ah, a_hi, d, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.wh, w_hi, d, n, 1, kBK, n, 64);
+  if (npass == 3)
+    ok = ok && make_tmap_3d(&m.al, a_lo, d, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.wl, w_lo, d, n, 1, kBK, n, 64);
+  else {
+    m.al = m.ah;
+    m.wl = m.wh;
+  }
+  m.rh = m.ah;
+  m.rl = m.ah;
+  m.ident = m.wh;
+  if (stencil) {  // 126-row boxes: a tile stores its rows 1..126
+    ok = ok && make_tmap_3d(&m.o0, out_hi, n, t, batch, 32, kBM - 2, 64) && make_tmap_3d(&m.o1, out_lo, n, t, batch, 32, kBM - 2, 64);
+  } else {
+    m.o0 = m.ah;
+    m.o1 = m.ah;
+  }
+  LFS2_REQUIRE(ok, LFS2_ERR_CUDA, "predictor_layer_tc: cuTensorMapEncodeTiled failed");
+  GemmTcParams p;
+  p.batch = batch; p.t = t; p.d = d; p.taps = 1; p.half = 0; p.dil = 1;
+  p.n = n;
+  p.m_step = m_step; p.t_shift = stencil ? -1 : 0;
+  p.m_tiles_per_batch = (t + m_step - 1) / m_step;
+  p.n_tiles = 1;
+  p.total_tiles = batch * p.m_tiles_per_batch;
+  p.has_residual = 0;
+  p.bias = bias; p.relu = 1; p.slope = 0.f; p.row_mask = nullptr;
+  p.gamma = gamma; p.beta = beta; p.eps = eps;
+  p.st_w = next_dw_w; p.st_b = next_dw_b; p.dot_w = head_w; p.dot_b = head_b; p.dot_mask = head_mask; p.dot_out = head_out;
+  cudaStream_t s = (cudaStream_t)stream;
+  p.tile_list = nullptr;
+  if (!row_limit && workspace) {
+    p.tile_list = reinterpret_cast<const int*>(workspace);
+  } else if (row_limit) {
+    LFS2_REQUIRE(workspace, LFS2_ERR_INVALID_ARG, "predictor_layer_tc: a row limit needs the tile-list workspace");
+    int* list = reinterpret_cast<int*>(workspace);
+    if (cudaMemsetAsync(list, 0, sizeof(int), s) != cudaSuccess) {
+      set_error("predictor_layer_tc: memset failed");
+      return LFS2_ERR_CUDA;
+    }
+    gemm_tile_list_kernel<<<1, 256, 0, s>>>(row_limit, limit_extra, batch, p.m_tiles_per_batch, list, m_step);
+    LFS2_CHECK_LAUNCH("gemm_tile_list");
+    p.tile_list = list;
+  }
+  if (stencil)
+    return npass == 3 ? launch_gemm_tc<256, 3, true, kOutPlanes, false, kEpiStencil>(m, p, s)
+                      : launch_gemm_tc<256, 1, true, kOutPlanes, false, kEpiStencil>(m, p, s);
+  return npass == 3 ? launch_gemm_tc<256, 3, true, kOutPlanes, false, kEpiDot>(m, p, s)
+                    : launch_gemm_tc<256, 1, true, kOutPlanes, false, kEpiDot>(m, p, s);
 }
 
 // x (n) fp32 -> hi/lo bf16 planes

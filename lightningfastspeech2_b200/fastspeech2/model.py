@@ -438,6 +438,42 @@ class VariancePredictor(nn.Module):
         self.linear = nn.Linear(filter_size, 1)
 
     skip_pad_tiles = True
+    fused_layers = True   # depthwise k = 3 stacks at width 256: each layer's GEMM epilogue also does the NEXT layer's conv / the head
+
+    def _fusable(self, x):
+        if not (self.fused_layers and not isinstance(x, ops.Planes) and x.dim() == 3 and x.shape[-1] == 256):
+            return False
+        for layer in self.layers:
+            ln = layer.layers[2]
+            if not (layer.depthwise and layer.kernel_size == 3 and layer.compute_mode != "simt"
+                    and ln.weight.shape[0] == 256 and not (layer.training and layer.layers[3].p > 0)):
+                return False
+        return self.linear.weight.shape[1] == 256
+
+    def _forward_fused(self, x, mask, lim):
+        """dwconv(layer 0) as its own kernel, then ONE launch per layer: GEMM + bias + ReLU + LayerNorm + the next layer's
+        depthwise conv (neighbour rows from the neighbouring epilogue threads) -- and, in the last layer, the Linear(256, 1)
+        head + mask instead.  Per layer the activations cross HBM once each way instead of twice."""
+        layers = list(self.layers)
+        packs = []
+        for layer in layers:
+            conv = layer.layers[0].module
+            cp = layer.__dict__.get("_conv_param_list")
+            if cp is None:
+                cp = list(conv.parameters())
+                layer.__dict__["_conv_param_list"] = cp
+            packs.append(layer._pack.get(cp, layer._build_pack))
+        npass = _npass(layers[0].compute_mode)
+        up = ops.dwconv1d_planes(x.contiguous(), packs[0]["dw_wt"], layers[0].layers[0].module[0].bias, row_limit=lim)
+        for i, layer in enumerate(layers):
+            conv, ln = layer.layers[0].module, layer.layers[2]
+            if i + 1 < len(layers):
+                nxt = layers[i + 1].layers[0].module
+                up = ops.predictor_layer_tc(up, packs[i]["pw_planes"], conv[1].bias, ln.weight, ln.bias, ln.eps, npass,
+                                            next_dw=(packs[i + 1]["dw_wt"], nxt[0].bias), row_limit=lim)
+            else:
+                return ops.predictor_layer_tc(up, packs[i]["pw_planes"], conv[1].bias, ln.weight, ln.bias, ln.eps, npass,
+                                              head=(self.linear.weight, self.linear.bias, mask), row_limit=lim)
 
     def forward(self, x, mask=None, return_conv=False):
         """The head masks every PAD position to 0 (model.py:518), so only rows within the conv halo of an utterance's
@@ -449,6 +485,8 @@ class VariancePredictor(nn.Module):
         if (self.skip_pad_tiles and mask is not None and not return_conv and not isinstance(x, ops.Planes)
                 and x.dim() == 3 and all(l.depthwise and l.compute_mode != "simt" for l in self.layers)):
             lim = (ops.mask_lengths(mask), self.halo(), {})  # {} = tile list shared by the layers of this call
+        if not return_conv and self._fusable(x):
+            return self._forward_fused(x, mask, lim)
         for i, layer in enumerate(self.layers):
             z = layer(z, out="planes" if i + 1 < nl else "f32", row_limit=lim)
         if isinstance(z, ops.Planes):

@@ -476,6 +476,52 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
     return of if out == "f32" else po
 
 
+def predictor_layer_tc(a, w, bias, gamma, beta, eps=LN_EPS, npass=3, next_dw=None, head=None, row_limit=None):
+    """One depthwise predictor layer with its successor fused into the LayerNorm epilogue (lfs2_predictor_layer_tc):
+    a Planes (B,T,256) = depthwise3 of the previous layer, w Planes (256,256).
+    next_dw = (wt (3,256), bias (256)) -> Planes: depthwise3 of the NEXT layer applied to LayerNorm(relu(a.w^T + bias));
+    head = (w (1,256) or (256), b (1), mask (B,T) bool or None) -> (B,T) fp32: the Linear(256,1) head, masked."""
+    if (next_dw is None) == (head is None):
+        raise ValueError("predictor_layer_tc: exactly one of next_dw / head")
+    if a.hi.dim() != 3 or a.shape[-1] != 256 or tuple(w.shape) != (256, 256):
+        raise ValueError("predictor_layer_tc: needs (B,T,256) activations and a (256,256) weight")
+    for x_ in (a.hi, a.lo, w.hi, w.lo):
+        _chk(x_, torch.bfloat16, "predictor_layer_tc operand plane")
+    b, t, d = a.shape
+    dev = a.hi.device
+    lim, extra = (row_limit[0], row_limit[1]) if row_limit is not None else (None, 0)
+    ws = None
+    if lim is not None:
+        cache = row_limit[2] if len(row_limit) > 2 else None
+        key = ("pl", b, t, next_dw is not None)   # the stencil form walks 126-row tiles: its own list
+        if cache is not None and key in cache:
+            ws, lim = cache[key], None
+        else:
+            ws = torch.empty(_lib.lib().lfs2_predictor_layer_tc_workspace_bytes(b, t) // 4, device=dev, dtype=torch.int32)
+            if cache is not None:
+                cache[key] = ws
+    m = b * t * _limited_fraction(row_limit, t)
+    po = hout = None
+    dw_w = dw_b = hw = hb = hmask = None
+    if next_dw is not None:
+        dw_w, dw_b = next_dw
+        _chk(dw_w, torch.float32, "next depthwise weight", 2)
+        if tuple(dw_w.shape) != (3, 256):
+            raise ValueError("predictor_layer_tc: the fused depthwise conv has kernel size 3")
+        po = _empty_planes((b, t, 256), dev)
+    else:
+        hw, hb, hmask = head
+        if hmask is not None:
+            _chk(hmask, torch.bool, "head mask", 2)
+        # rows of skipped tiles are PAD positions: the head masks them to 0
+        hout = (torch.zeros if row_limit is not None else torch.empty)(b, t, device=dev, dtype=torch.float32)
+    _launch("lfs2_predictor_layer_tc", _p(a.hi), _p(a.lo), b, t, _p(w.hi), _p(w.lo), _p(bias), _p(gamma), _p(beta),
+            float(eps), npass, _p(dw_w), _p(dw_b), _p(po.hi if po else None), _p(po.lo if po else None), _p(hw), _p(hb),
+            _p(hmask), _p(hout), _p(lim), int(extra), _p(ws), _s(), tag="predictor_pw_ln_gemm", flops=2.0 * m * 256 * 256,
+            passes=npass, nbytes=4.0 * m * 256 + 4.0 * 256 * 256 + (4.0 * m * 256 if po is not None else 4.0 * m))
+    return po if po is not None else hout
+
+
 def ffn_fused_tc(u, w1, b1, w2, b2, residual, gamma, beta, eps=LN_EPS, npass=3, row_limit=None):
     """LayerNorm(residual + relu(u . w1^T + b1) . w2^T + b2) in one kernel, the F-wide intermediate on chip.
     u, residual: Planes (..., 256); w1 Planes (F, 256); w2 Planes (256, F) -> Planes (..., 256).

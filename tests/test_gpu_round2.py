@@ -253,3 +253,52 @@ def test_whole_call_cuda_graphs_are_bit_identical(preset, bsz, lo, hi):
         assert torch.allclose(r["mel"], eager[0]["mel"] + 1.0, atol=1e-5)
         model.cuda_graphs = False
         assert torch.equal(model(batches[0], inference=True)["mel"], r["mel"])
+
+
+@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("bf16", 3e-2)])
+def test_fused_predictor_layers_match_the_unfused_stack_and_the_oracle(mode, tol):
+    """VariancePredictor (5 depthwise layers, k = 3, width 256): every layer's GEMM epilogue also applies the NEXT layer's
+    depthwise conv (lfs2_predictor_layer_tc, 126-row tiles) and the last one the Linear(256,1) head + mask.  Same
+    numbers as the layer-by-layer path, with and without PAD-tile skipping, on ragged batches whose lengths sit on and
+    around the 126 / 128-row tile edges."""
+    from lightningfastspeech2_b200.fastspeech2.model import VariancePredictor
+    import torch.nn.functional as F
+
+    torch.manual_seed(3)
+    vp = VariancePredictor(5, 256, 256, 3, 0.0, depthwise=True).to(DEV).eval()
+    with torch.no_grad():
+        for p in vp.parameters():
+            if p.dim() == 1:
+                p.add_(0.1 * torch.randn_like(p))
+    for m in vp.modules():
+        if hasattr(type(m), "compute_mode"):
+            m.compute_mode = mode
+    lens = [700, 126, 127, 128, 129, 251, 252, 253, 1, 5, 380]
+    t = max(lens)
+    x = torch.randn(len(lens), t, 256, device=DEV)
+    mask = torch.arange(t, device=DEV)[None, :] >= torch.tensor(lens, device=DEV)[:, None]
+    with torch.no_grad():
+        vp.fused_layers = True
+        fused = vp(x, mask)
+        vp.skip_pad_tiles = False
+        fused_all_tiles = vp(x, mask)
+        nomask = vp(x, None)
+        vp.fused_layers = False
+        plain = vp(x, mask)
+        plain_nomask = vp(x, None)
+        vp.skip_pad_tiles = True
+    assert torch.equal(fused, fused_all_tiles)                     # PAD-tile skipping changes no bit
+    assert float(fused[mask].abs().max()) == 0.0
+    err = float((fused - plain).abs().max())
+    err_nomask = float((nomask - plain_nomask).abs().max())
+    print(f"fused predictor [{mode}]: max |fused - layer-by-layer| = {err:.2e} (unmasked, all rows: {err_nomask:.2e})")
+    assert err < tol and err_nomask < tol
+    # and against an fp64 restatement of the stack (model.py:510-561)
+    z = x.double().cpu()
+    for layer in vp.layers:
+        conv, ln = layer.layers[0].module, layer.layers[2]
+        u = F.conv1d(z.transpose(1, 2), conv[0].weight.double().cpu(), conv[0].bias.double().cpu(), padding=1, groups=256)
+        u = F.conv1d(u, conv[1].weight.double().cpu(), conv[1].bias.double().cpu()).transpose(1, 2)
+        z = F.layer_norm(torch.relu(u), (256,), ln.weight.double().cpu(), ln.bias.double().cpu(), ln.eps)
+    ref = F.linear(z, vp.linear.weight.double().cpu(), vp.linear.bias.double().cpu()).squeeze(-1).masked_fill(mask.cpu(), 0)
+    assert (fused.cpu().double() - ref).abs().max() < (1e-4 if mode == "fp32" else 5e-2)
