@@ -85,7 +85,7 @@ __global__ void gemm_tile_list_kernel(const int* __restrict__ row_limit, int ext
 
 template <int N_TILE, int NPASS, bool LN, int EPI = 0>
 struct SmemLayout {
-  static constexpr int kEdge = EPI == 1 ? 6 * N_TILE * 4 : 0;  // kEpiStencil: 3 "last row" + 3 "first row" vectors of the quadrants
+  static constexpr int kEdge = EPI != 0 ? 4 * N_TILE * 4 : 0;  // kEpiStencil: taps w0 | w1 | w2 | bias; kEpiDot: the head weight
   static constexpr bool kHasLo = NPASS == 3 || LN;  // LN variants stream residual lo planes even in bf16 mode
   static constexpr int kAPlane = kBM * kBK * 2;     // 8 KB
   static constexpr int kWPlane = N_TILE * kBK * 2;
@@ -98,7 +98,7 @@ struct SmemLayout {
   static constexpr int kOffStaging = kStages * kStage;                 // 2 halves x 2 chunks, 1024-aligned
   static constexpr int kOffVec = kOffStaging + 4 * kStageChunk;        // bias | gamma | beta for LN: 3 * N_TILE floats
   static constexpr int kOffStats = kOffVec + 3 * N_TILE * 4;           // LN partial (sum, sumsq): [2 tiles][2 halves][128]
-  static constexpr int kOffEdge = kOffStats + 2 * 2 * kBM * 8;         // kEpiStencil edge rows
+  static constexpr int kOffEdge = kOffStats + 2 * 2 * kBM * 8;         // fused-epilogue vectors (kEdge bytes)
   static constexpr int kTotal = kStages * kStage + kFixed;
   static_assert(kStages >= 2, "not enough shared memory for a pipeline");
   static_assert(kStage % 1024 == 0, "stage must keep 1024-byte alignment");
@@ -230,6 +230,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       vec[i] = p.bias ? p.bias[i] : 0.f;
       vec[N_TILE + i] = p.gamma[i];
       vec[2 * N_TILE + i] = p.beta[i];
+    }
+    if (EPI != kEpiNone) {
+      float* ev = reinterpret_cast<float*>(smem + L::kOffEdge);
+      for (int i = threadIdx.x - 64; i < N_TILE; i += 256) {
+        if (EPI == kEpiStencil) {
+          ev[i] = p.st_w[i];
+          ev[N_TILE + i] = p.st_w[N_TILE + i];
+          ev[2 * N_TILE + i] = p.st_w[2 * N_TILE + i];
+          ev[3 * N_TILE + i] = p.st_b[i];
+        } else {
+          ev[i] = p.dot_w[i];
+        }
+      }
     }
   }
   tc_fence_before();
@@ -398,6 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       if (EPI == kEpiDot) {
         // ---- predictor head: out[row] = LayerNorm(z)[row] . dot_w + dot_b, masked positions 0; nothing else is stored ----
         float acc_dot = 0.f;
+        const float* stw_dot = reinterpret_cast<const float*>(smem + L::kOffEdge);
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           tmem_ld32(taddr + c * 32, v);
@@ -405,7 +419,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           for (int j = 0; j < 32; ++j) {
             const float x = activate(v[j] + vec[c * 32 + j], p.relu, p.slope);
             const float z = (x - mean) * rstd * vec[N_TILE + c * 32 + j] + vec[2 * N_TILE + c * 32 + j];
-            acc_dot = fmaf(z, __ldg(p.dot_w + c * 32 + j), acc_dot);
+            acc_dot = fmaf(z, stw_dot[c * 32 + j], acc_dot);
           }
         }
         float2* st = stats + (it & 1) * 2 * kBM;
@@ -428,51 +442,57 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
       if (EPI == kEpiStencil) {
         // ---- u = depthwise3(LayerNorm(z)) of the next layer; rows outside the utterance count as zeros ----
-        float* edge = reinterpret_cast<float*>(smem + L::kOffEdge);  // [0..2]: last row of quadrant q, [3..5]: first row of quadrant q+1
+        // per 32-column chunk: the normalised rows go to one staging buffer as fp32 (swizzled like the fp32 output path);
+        // after a 128-thread barrier every thread reads its two neighbour rows back, computes u, and stages it as hi/lo
+        // planes in the OTHER buffer, which leaves by TMA.  Taps / bias come from shared memory (broadcast 16-byte reads).
+        const float* stw = reinterpret_cast<const float*>(smem + L::kOffEdge);  // w0 | w1 | w2 | bias, N_TILE floats each
         const int trow = t0 + r;
         const bool live = b < p.batch && trow >= 0 && trow < p.t;
-        auto norm = [&](int c, int j) -> float {
-          const float x = activate(v[j] + vec[c * 32 + j], p.relu, p.slope);
-          return live ? (x - mean) * rstd * vec[N_TILE + c * 32 + j] + vec[2 * N_TILE + c * 32 + j] : 0.f;
-        };
-        // the rows at the quadrants' edges, for this half's columns, through shared memory
-        // (tcgen05.ld is warp-collective: every lane loads, lanes 0 and 31 publish)
+        const bool outrow = r >= 1 && r <= kBM - 2;   // rows 1..126 are this tile's outputs, staged as rows 0..125
+        uint8_t* zbuf = staging;                       // fp32 z chunk: 128 rows x 128 B
+        uint8_t* ubuf = staging + kStageChunk;         // u chunk: hi plane | lo plane
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           tmem_ld32(taddr + c * 32, v);
-          if (lane == 31 && quad < 3) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) edge[quad * N_TILE + c * 32 + j] = norm(c, j);
-          }
-          if (lane == 0 && quad > 0) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) edge[(3 + quad - 1) * N_TILE + c * 32 + j] = norm(c, j);
-          }
-        }
-        named_bar_sync(1 + half, 128);   // the four quadrant warps of this half
-#pragma unroll 1
-        for (int c = c_begin; c < c_end; ++c) {
-          tmem_ld32(taddr + c * 32, v);
-          float u[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float z = norm(c, j);
-            float up = __shfl_up_sync(0xffffffffu, z, 1), dn = __shfl_down_sync(0xffffffffu, z, 1);
-            const int col = c * 32 + j;
-            if (lane == 0) up = quad > 0 ? edge[(quad - 1) * N_TILE + col] : 0.f;
-            if (lane == 31) dn = quad < 3 ? edge[(3 + quad) * N_TILE + col] : 0.f;
-            // same association as dwconv1d_k_kernel: bias, then taps 0, 1, 2
-            u[j] = fmaf(__ldg(p.st_w + 2 * N_TILE + col), dn,
-                        fmaf(__ldg(p.st_w + N_TILE + col), z, fmaf(__ldg(p.st_w + col), up, __ldg(p.st_b + col))));
+            const float x = activate(v[j] + vec[c * 32 + j], p.relu, p.slope);
+            v[j] = live ? (x - mean) * rstd * vec[N_TILE + c * 32 + j] + vec[2 * N_TILE + c * 32 + j] : 0.f;
           }
-          uint8_t* sb = staging + (chunk_ctr & 1) * kStageChunk;
-          ++chunk_ctr;
-          if (r >= 1 && r <= kBM - 2) {  // rows 1..126 are this tile's outputs, staged as rows 0..125
-            const int rr = r - 1;
-            uint32_t hi[16], lo[16];
+          {
+            uint8_t* row = zbuf + r * 128;
 #pragma unroll
-            for (int j = 0; j < 16; ++j) split_pack2(u[2 * j], u[2 * j + 1], hi[j], lo[j]);
-            uint8_t* rh = sb + rr * 64;
+            for (int i = 0; i < 8; ++i)
+              *reinterpret_cast<float4*>(row + ((i ^ (r & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          named_bar_sync(1 + half, 128);          // (A) the chunk's 128 rows of z are in shared memory
+          uint32_t hi[16], lo[16];
+          if (outrow) {
+            const uint8_t* rup = zbuf + (r - 1) * 128;
+            const uint8_t* rdn = zbuf + (r + 1) * 128;
+            const float4* w0 = reinterpret_cast<const float4*>(stw + c * 32);
+            const float4* w1 = reinterpret_cast<const float4*>(stw + N_TILE + c * 32);
+            const float4* w2 = reinterpret_cast<const float4*>(stw + 2 * N_TILE + c * 32);
+            const float4* bb = reinterpret_cast<const float4*>(stw + 3 * N_TILE + c * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float4 up = *reinterpret_cast<const float4*>(rup + ((i ^ ((r - 1) & 7)) << 4));
+              const float4 dn = *reinterpret_cast<const float4*>(rdn + ((i ^ ((r + 1) & 7)) << 4));
+              const float4 a0 = w0[i], a1 = w1[i], a2 = w2[i], ab = bb[i];
+              // same association as dwconv1d_k_kernel: bias, then taps 0, 1, 2
+              const float u0 = fmaf(a2.x, dn.x, fmaf(a1.x, v[4 * i], fmaf(a0.x, up.x, ab.x)));
+              const float u1 = fmaf(a2.y, dn.y, fmaf(a1.y, v[4 * i + 1], fmaf(a0.y, up.y, ab.y)));
+              const float u2 = fmaf(a2.z, dn.z, fmaf(a1.z, v[4 * i + 2], fmaf(a0.z, up.z, ab.z)));
+              const float u3 = fmaf(a2.w, dn.w, fmaf(a1.w, v[4 * i + 3], fmaf(a0.w, up.w, ab.w)));
+              split_pack2(u0, u1, hi[2 * i], lo[2 * i]);
+              split_pack2(u2, u3, hi[2 * i + 1], lo[2 * i + 1]);
+            }
+          }
+          if (issuer) tma_store_wait_read0();     // the previous chunk's store has finished reading ubuf
+          named_bar_sync(1 + half, 128);          // (B) ubuf is free, and every thread has read its neighbours from zbuf
+          if (outrow) {
+            const int rr = r - 1;
+            uint8_t* rh = ubuf + rr * 64;
             uint8_t* rl = rh + kStageChunk / 2;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -482,15 +502,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             }
           }
           fence_proxy_async_smem();
-          if (issuer) tma_store_wait_read0();
-          named_bar_sync(1 + half, 128);
+          named_bar_sync(1 + half, 128);          // (C) the u chunk is staged
           if (issuer) {  // maps with 126-row boxes; TMA clips the rows past the utterance's end
-            tma_store_3d(&map_o0, sb, n0 + c * 32, t0 + 1, b);
-            tma_store_3d(&map_o1, sb + kStageChunk / 2, n0 + c * 32, t0 + 1, b);
+            tma_store_3d(&map_o0, ubuf, n0 + c * 32, t0 + 1, b);
+            tma_store_3d(&map_o1, ubuf + kStageChunk / 2, n0 + c * 32, t0 + 1, b);
             tma_store_commit();
           }
         }
-        // (the edge rows are only read before a chunk's staging barrier, so the next tile may overwrite them right away)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);

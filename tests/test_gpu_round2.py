@@ -255,7 +255,7 @@ def test_whole_call_cuda_graphs_are_bit_identical(preset, bsz, lo, hi):
         assert torch.equal(model(batches[0], inference=True)["mel"], r["mel"])
 
 
-@pytest.mark.parametrize("mode,tol", [("fp32", 2e-5), ("bf16", 3e-2)])
+@pytest.mark.parametrize("mode,tol", [("fp32", 5e-5), ("bf16", 3e-2)])
 def test_fused_predictor_layers_match_the_unfused_stack_and_the_oracle(mode, tol):
     """VariancePredictor (5 depthwise layers, k = 3, width 256): every layer's GEMM epilogue also applies the NEXT layer's
     depthwise conv (lfs2_predictor_layer_tc, 126-row tiles) and the last one the Linear(256,1) head + mask.  Same
