@@ -60,8 +60,6 @@ struct GemmTcParams {
   // fused predictor epilogues (lfs2_predictor_layer_tc): see EPI below
   const float* st_w;            // kEpiStencil: (3, n) taps of the NEXT layer's depthwise conv, tap-major; st_b its bias (n)
   const float* st_b;
-  __nv_bfloat16* st_out_hi;     // kEpiStencil: the output planes (batch, t, n), written straight from registers
-  __nv_bfloat16* st_out_lo;
   const float* dot_w;           // kEpiDot: (n) head weight, dot_b (1) its bias, dot_mask (batch, t) or null, dot_out (batch, t)
   const float* dot_b;
   const uint8_t* dot_mask;
@@ -451,13 +449,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int trow = t0 + r;
         const bool live = b < p.batch && trow >= 0 && trow < p.t;
         const bool outrow = r >= 1 && r <= kBM - 2;   // rows 1..126 are this tile's outputs, staged as rows 0..125
-        // z chunks ping-pong between the half's two staging buffers, so ONE barrier per chunk suffices (a thread that
-        // passes chunk c's barrier has finished reading chunk c-1's buffer); u leaves straight from registers
-        // (thread = row: 64-byte pieces per plane)
+        uint8_t* zbuf = staging;                       // fp32 z chunk: 128 rows x 128 B
+        uint8_t* ubuf = staging + kStageChunk;         // u chunk: hi plane | lo plane
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
-          uint8_t* zbuf = staging + (chunk_ctr & 1) * kStageChunk;   // fp32 z chunk: 128 rows x 128 B
-          ++chunk_ctr;
           tmem_ld32(taddr + c * 32, v);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -470,15 +465,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             for (int i = 0; i < 8; ++i)
               *reinterpret_cast<float4*>(row + ((i ^ (r & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
-          named_bar_sync(1 + half, 128);          // the chunk's 128 rows of z are in shared memory
-          if (outrow && live) {
+          named_bar_sync(1 + half, 128);          // (A) the chunk's 128 rows of z are in shared memory
+          uint32_t hi[16], lo[16];
+          if (outrow) {
             const uint8_t* rup = zbuf + (r - 1) * 128;
             const uint8_t* rdn = zbuf + (r + 1) * 128;
             const float4* w0 = reinterpret_cast<const float4*>(stw + c * 32);
             const float4* w1 = reinterpret_cast<const float4*>(stw + N_TILE + c * 32);
             const float4* w2 = reinterpret_cast<const float4*>(stw + 2 * N_TILE + c * 32);
             const float4* bb = reinterpret_cast<const float4*>(stw + 3 * N_TILE + c * 32);
-            uint32_t hi[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const float4 up = *reinterpret_cast<const float4*>(rup + ((i ^ ((r - 1) & 7)) << 4));
@@ -492,14 +487,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               split_pack2(u0, u1, hi[2 * i], lo[2 * i]);
               split_pack2(u2, u3, hi[2 * i + 1], lo[2 * i + 1]);
             }
-            const size_t o = ((size_t)b * p.t + trow) * p.n + n0 + c * 32;
-            uint4* oh = reinterpret_cast<uint4*>(p.st_out_hi + o);
-            uint4* ol = reinterpret_cast<uint4*>(p.st_out_lo + o);
+          }
+          if (issuer) tma_store_wait_read0();     // the previous chunk's store has finished reading ubuf
+          named_bar_sync(1 + half, 128);          // (B) ubuf is free, and every thread has read its neighbours from zbuf
+          if (outrow) {
+            const int rr = r - 1;
+            uint8_t* rh = ubuf + rr * 64;
+            uint8_t* rl = rh + kStageChunk / 2;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-              ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+              const int o = (i ^ ((rr >> 1) & 3)) << 4;
+              *reinterpret_cast<uint4*>(rh + o) = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+              *reinterpret_cast<uint4*>(rl + o) = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
             }
+          }
+          fence_proxy_async_smem();
+          named_bar_sync(1 + half, 128);          // (C) the u chunk is staged
+          if (issuer) {  // maps with 126-row boxes; TMA clips the rows past the utterance's end
+            tma_store_3d(&map_o0, ubuf, n0 + c * 32, t0 + 1, b);
+            tma_store_3d(&map_o1, ubuf + kStageChunk / 2, n0 + c * 32, t0 + 1, b);
+            tma_store_commit();
           }
         }
         tc_fence_before();
@@ -860,7 +867,6 @@ int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int t, int d,
   p.gamma = gamma; p.beta = beta; p.eps = eps;
   p.m_step = kBM; p.t_shift = 0;
   p.st_w = p.st_b = p.dot_w = p.dot_b = nullptr; p.dot_mask = nullptr; p.dot_out = nullptr;
-  p.st_out_hi = p.st_out_lo = nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   p.tile_list = nullptr;
   if (!row_limit && workspace) {
@@ -921,8 +927,12 @@ int lfs2_predictor_layer_tc(const void* a_hi, const void* a_lo, int batch, int t
   m.rh = m.ah;
   m.rl = m.ah;
   m.ident = m.wh;
-  m.o0 = m.ah;  // (neither fused epilogue stores through TMA)
-  m.o1 = m.ah;
+  if (stencil) {  // 126-row boxes: a tile stores its rows 1..126
+    ok = ok && make_tmap_3d(&m.o0, out_hi, n, t, batch, 32, kBM - 2, 64) && make_tmap_3d(&m.o1, out_lo, n, t, batch, 32, kBM - 2, 64);
+  } else {
+    m.o0 = m.ah;
+    m.o1 = m.ah;
+  }
   LFS2_REQUIRE(ok, LFS2_ERR_CUDA, "predictor_layer_tc: cuTensorMapEncodeTiled failed");
   GemmTcParams p;
   p.batch = batch; p.t = t; p.d = d; p.taps = 1; p.half = 0; p.dil = 1;
@@ -934,7 +944,6 @@ int lfs2_predictor_layer_tc(const void* a_hi, const void* a_lo, int batch, int t
   p.has_residual = 0;
   p.bias = bias; p.relu = 1; p.slope = 0.f; p.row_mask = nullptr;
   p.gamma = gamma; p.beta = beta; p.eps = eps;
-  p.st_out_hi = (__nv_bfloat16*)out_hi; p.st_out_lo = (__nv_bfloat16*)out_lo;
   p.st_w = next_dw_w; p.st_b = next_dw_b; p.dot_w = head_w; p.dot_b = head_b; p.dot_mask = head_mask; p.dot_out = head_out;
   cudaStream_t s = (cudaStream_t)stream;
   p.tile_list = nullptr;
