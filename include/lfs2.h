@@ -193,6 +193,9 @@ LFS2_API int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch,
  *   out_kind   LFS2_OUT_PLANES: out0/out1 = bf16 hi/lo planes; LFS2_OUT_F32: out0 = fp32; LFS2_OUT_F16: out0 = ONE
  *              fp16 plane (saturating conversion), the operand format of lfs2_attention_tc_ex(..., fp16)
  *   row_mask   NULL or (batch, t) bytes: rows with a non-zero byte are written as zeros (PAD frames of a ragged batch)
+ *   npass      3: hi.hi + lo.hi + hi.lo; 1: hi.hi; 2: a_hi is ONE fp16 plane of a (a_lo unused) against the bf16 hi/lo
+ *              weight planes, a.w_hi + a.w_lo -- 11 significant bits on the activation side, full weights, two thirds
+ *              of the tensor work (no LayerNorm / residual epilogue in this recipe)
  *   column tiles of 256 / 128 / 64 outputs (n % 16 == 0). */
 #define LFS2_OUT_PLANES 0
 #define LFS2_OUT_F32 1
@@ -226,6 +229,11 @@ LFS2_API int lfs2_dwconv1d_planes_limited(const float* x, const void* x_hi, cons
                                           const float* bias, float* out, void* out_hi, void* out_lo, int batch,
                                           int t, int d, int ksize, const int* row_limit, int limit_extra,
                                           void* stream);
+/* same with one more optional output: out_f16 = the result as ONE fp16 plane (saturating), the activation operand of a
+ * 2-pass GEMM (npass = 2 of lfs2_gemm_tc_ex / lfs2_ffn_fused_tc_ex); odd kernel sizes <= 25 */
+LFS2_API int lfs2_dwconv1d_planes_ex(const float* x, const void* x_hi, const void* x_lo, const float* wt,
+                                     const float* bias, float* out, void* out_hi, void* out_lo, void* out_f16, int batch,
+                                     int t, int d, int ksize, const int* row_limit, int limit_extra, void* stream);
 /* x[r, :] = +0.0 for every row r with mask[r] != 0 (x: (rows, width) fp32, width % 4 == 0): the mel frames the
  * reference's consumers drop with tgt_mask (generator.py:164) after a PAD-row skipping synthesis call. */
 LFS2_API int lfs2_zero_masked_rows(float* x, const uint8_t* mask, long long rows, int width, void* stream);
@@ -252,6 +260,16 @@ LFS2_API int lfs2_ffn_fused_tc_limited(const void* u_hi, const void* u_lo, int b
                                        const float* b2, const void* res_hi, const void* res_lo, const void* ident_hi,
                                        const float* gamma, const float* beta, float eps, void* out_hi, void* out_lo,
                                        int npass, const int* row_limit, int limit_extra, void* workspace, void* stream);
+/* Same with the 2-pass recipe and an extra output.  npass = 2: u_hi is ONE fp16 plane of u (u_lo unused) and the
+ * intermediate is packed as fp16: every product is a.w_hi + a.w_lo (11 significant bits on the activation side, full
+ * weights; two thirds of the tensor work of npass = 3).  out_f16 (or NULL): the output rows also as one fp16 plane, the
+ * activation operand of the next block's 2-pass QKV GEMM (lfs2_gemm_tc_ex, npass = 2). */
+LFS2_API int lfs2_ffn_fused_tc_ex(const void* u_hi, const void* u_lo, int batch, int t, const void* w1_hi,
+                                  const void* w1_lo, int f, const float* b1, const void* w2_hi, const void* w2_lo,
+                                  const float* b2, const void* res_hi, const void* res_lo, const void* ident_hi,
+                                  const float* gamma, const float* beta, float eps, void* out_hi, void* out_lo,
+                                  void* out_f16, int npass, const int* row_limit, int limit_extra, void* workspace,
+                                  void* stream);
 
 /* tensor-core multi-head self attention (head_dim 128) on the bf16 hi/lo planes of the packed
  * qkv (B,T,3d) tensor [q | k | v] written by lfs2_gemm_tc: flash-style streaming softmax,
@@ -297,6 +315,8 @@ LFS2_API int lfs2_merge_planes(const void* hi, const void* lo, float* out, long 
 
 /* hi = bf16(x), lo = bf16(x - hi) for n fp32 values (n % 4 == 0) */
 LFS2_API int lfs2_split_bf16(const float* x, void* hi, void* lo, long long n, void* stream);
+/* same, and (f16 != NULL) the values also as ONE fp16 plane (saturating): the activation operand of npass = 2 GEMMs */
+LFS2_API int lfs2_split_bf16_ex(const float* x, void* hi, void* lo, void* f16, long long n, void* stream);
 
 /* ---- general batched tcgen05 GEMM with per-operand majorness (weight gradients, attention products) ----
  * An operand is a window of a dense row-major bf16 tensor (d2, d1, d0) (d0 innermost, d0 % 8 == 0), given

@@ -45,15 +45,19 @@ SIGNATURES = {
     "lfs2_predictor_layer_tc": [_vp, _vp, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _i, _vp, _vp],
     "lfs2_dwconv1d_planes_limited": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
+    "lfs2_dwconv1d_planes_ex": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp],
     "lfs2_mask_lengths": [_vp, _vp, _i, _i, _vp],
     "lfs2_zero_masked_rows": [_vp, _vp, _ll, _i, _vp],
     "lfs2_ffn_fused_tc": [_vp, _vp, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _vp],
     "lfs2_ffn_fused_tc_limited": [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i,
                                   _vp, _i, _vp, _vp],
+    "lfs2_ffn_fused_tc_ex": [_vp, _vp, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _vp,
+                             _i, _vp, _i, _vp, _vp],
     "lfs2_attention_tc_limited": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _vp],
     "lfs2_attention_tc_workspace_bytes": [_i],
     "lfs2_attention_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "lfs2_split_bf16": [_vp, _vp, _vp, ctypes.c_longlong, _vp],
+    "lfs2_split_bf16_ex": [_vp, _vp, _vp, _vp, ctypes.c_longlong, _vp],
     "lfs2_gemm_tc2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
     "lfs2_attn_softmax_planes": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "lfs2_attn_softmax_planes_drop": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, ctypes.c_ulonglong,

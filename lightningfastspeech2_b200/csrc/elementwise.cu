@@ -363,7 +363,7 @@ template <int K, int NT, int kDwTile, bool IN_PLANES>
 __global__ void __launch_bounds__(kDwCh4 * (kDwTile / NT), 2)
 dwconv1d_k_kernel(const float4* __restrict__ x, const uint2* __restrict__ x_hi, const uint2* __restrict__ x_lo,
                   const float4* __restrict__ wt, const float4* __restrict__ bias, float4* __restrict__ out,
-                  uint2* __restrict__ out_hi, uint2* __restrict__ out_lo, int t, int d4,
+                  uint2* __restrict__ out_hi, uint2* __restrict__ out_lo, uint2* __restrict__ out_f16, int t, int d4,
                   const int* __restrict__ row_limit, int limit_extra) {
   extern __shared__ float4 xs[];  // [kDwTile + K - 1][kDwCh4]
   constexpr int H = (K - 1) / 2;
@@ -449,14 +449,20 @@ dwconv1d_k_kernel(const float4* __restrict__ x, const uint2* __restrict__ x_hi, 
         out_hi[oi] = h;
         out_lo[oi] = l;
       }
+      if (out_f16) {  // ONE fp16 plane (saturating): the activation operand of a 2-pass GEMM
+        uint2 h;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(acc[o].y), "f"(acc[o].x));
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(acc[o].w), "f"(acc[o].z));
+        out_f16[oi] = h;
+      }
     }
   }
 }
 
 template <int K, int NT, int kDwTile>
 static int launch_dwconv_k(const float* x, const void* x_hi, const void* x_lo, const float* wt, const float* bias,
-                           float* out, void* out_hi, void* out_lo, int batch, int t, int d, const int* row_limit,
-                           int limit_extra, cudaStream_t s) {
+                           float* out, void* out_hi, void* out_lo, void* out_f16, int batch, int t, int d,
+                           const int* row_limit, int limit_extra, cudaStream_t s) {
   constexpr int kThreads = kDwCh4 * (kDwTile / NT);
   constexpr int kSmem = (kDwTile + K - 1) * kDwCh4 * 16;
   dim3 grid(ceil_div(t, kDwTile), ceil_div(d / 4, kDwCh4), batch);
@@ -473,11 +479,12 @@ static int launch_dwconv_k(const float* x, const void* x_hi, const void* x_lo, c
   }
   if (x)
     kf<<<grid, kThreads, kSmem, s>>>((const float4*)x, nullptr, nullptr, (const float4*)wt, (const float4*)bias,
-                                     (float4*)out, (uint2*)out_hi, (uint2*)out_lo, t, d / 4, row_limit, limit_extra);
+                                     (float4*)out, (uint2*)out_hi, (uint2*)out_lo, (uint2*)out_f16, t, d / 4, row_limit,
+                                     limit_extra);
   else
     kp<<<grid, kThreads, kSmem, s>>>(nullptr, (const uint2*)x_hi, (const uint2*)x_lo, (const float4*)wt,
-                                     (const float4*)bias, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, t, d / 4,
-                                     row_limit, limit_extra);
+                                     (const float4*)bias, (float4*)out, (uint2*)out_hi, (uint2*)out_lo, (uint2*)out_f16, t,
+                                     d / 4, row_limit, limit_extra);
   return LFS2_OK;
 }
 
@@ -683,7 +690,17 @@ int lfs2_dwconv1d_planes(const float* x, const void* x_hi, const void* x_lo, con
 int lfs2_dwconv1d_planes_limited(const float* x, const void* x_hi, const void* x_lo, const float* wt, const float* bias,
                                  float* out, void* out_hi, void* out_lo, int batch, int t, int d, int ksize,
                                  const int* row_limit, int limit_extra, void* stream) {
-  LFS2_REQUIRE((x || (x_hi && x_lo)) && wt && bias && (out || out_hi), LFS2_ERR_INVALID_ARG, "dwconv1d: null pointer");
+  return lfs2_dwconv1d_planes_ex(x, x_hi, x_lo, wt, bias, out, out_hi, out_lo, nullptr, batch, t, d, ksize, row_limit,
+                                 limit_extra, stream);
+}
+
+int lfs2_dwconv1d_planes_ex(const float* x, const void* x_hi, const void* x_lo, const float* wt, const float* bias,
+                            float* out, void* out_hi, void* out_lo, void* out_f16, int batch, int t, int d, int ksize,
+                            const int* row_limit, int limit_extra, void* stream) {
+  LFS2_REQUIRE((x || (x_hi && x_lo)) && wt && bias && (out || out_hi || out_f16), LFS2_ERR_INVALID_ARG,
+               "dwconv1d: null pointer");
+  LFS2_REQUIRE(!out_f16 || (ksize <= 25 && aligned16(out_f16)), LFS2_ERR_UNSUPPORTED,
+               "dwconv1d: the fp16 output plane needs an odd kernel size <= 25 and a 16-byte aligned pointer");
   LFS2_REQUIRE(!x || !x_hi, LFS2_ERR_INVALID_ARG, "dwconv1d: give the input as fp32 OR as planes");
   LFS2_REQUIRE(!out_hi == !out_lo, LFS2_ERR_INVALID_ARG, "dwconv1d: out_hi and out_lo go together");
   if (batch == 0 || t == 0) return LFS2_OK;
@@ -698,8 +715,8 @@ int lfs2_dwconv1d_planes_limited(const float* x, const void* x_hi, const void* x
   LFS2_REQUIRE(batch <= 65535, LFS2_ERR_UNSUPPORTED, "dwconv1d: batch exceeds the grid limit");
 #define LFS2_DW_CASE(K, TT)                                                                          \
   case K: {                                                                                          \
-    int rc = launch_dwconv_k<K, TT, (K <= 9 ? 64 : 32)>(x, x_hi, x_lo, wt, bias, out, out_hi, out_lo, batch, t, d,       \
-                                                        row_limit, limit_extra, s);                                   \
+    int rc = launch_dwconv_k<K, TT, (K <= 9 ? 64 : 32)>(x, x_hi, x_lo, wt, bias, out, out_hi, out_lo, out_f16, batch, t, \
+                                                        d, row_limit, limit_extra, s);                                \
     if (rc != LFS2_OK) return rc;                                                                    \
   } break;
   switch (ksize) {

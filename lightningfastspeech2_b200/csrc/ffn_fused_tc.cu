@@ -9,12 +9,18 @@
 //         tensor-memory columns (per 32-column block: 16 packed hi columns, 16 packed lo columns)
 //     G2  acc2 (TMEM, fp32 128 x 256) += v[c] . W_eff[:, c]^T        TS form: A = v read from tensor memory
 // tensor-pipe order: G1(0) | G1(1) G2(0) | G1(2) G2(1) | ...
-// then the residual x1 rides the tensor core (hi.I + lo.I, as in gemm_tc.cu), and the epilogue does
-// + b_eff, LayerNorm over the 256 columns and leaves as bf16 hi/lo planes through swizzled staging + TMA stores.
+// then the residual x1 rides the tensor core: per 32-column slab, acc2[:, slab] += R_hi . I32 + R_lo . I32 with ONE
+// 32 x 32 identity block held in shared memory (N = 32 instructions: 1/8 of the work of a full-width identity slab
+// and no identity traffic), and the epilogue does + b_eff, LayerNorm over the 256 columns and leaves as bf16 hi/lo
+// planes (plus, on request, the same rows as ONE fp16 plane for the next block's 2-pass QKV GEMM) through swizzled
+// staging + TMA stores.
 // HBM traffic per row: read u (1 KB) + x1 (1 KB), write out (1 KB) -- the unfused pair moves 11 KB.
 // tcgen05.mma executes in issue order, so G1 of chunk c+1 may be issued right behind G2 of chunk c although it
 // overwrites the columns G2 reads (same pattern as S/P in attention_tc.cu).
-// NPASS = 3: hi.hi + lo.hi + hi.lo for every product (fp32-parity mode); NPASS = 1: hi.hi only.
+// NPASS = 3: hi.hi + lo.hi + hi.lo for every product; NPASS = 1: hi.hi only (bf16 mode);
+// NPASS = 2: the activation operand is ONE fp16 value (u arrives as an fp16 plane, v is packed as fp16 in tensor
+// memory) against the bf16 hi/lo weight planes: a.w_hi + a.w_lo -- 11 significant bits on the activation side, full
+// weights; two thirds of the tensor work (tools/precision_emulation.py has the mel error of this recipe per site).
 // Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue (thread = row, two warps per quadrant).
 #include "tc_common.cuh"
 
@@ -38,6 +44,7 @@ struct FfnParams {
   const float* gamma;
   const float* beta;
   float eps;
+  int out_f16;      // also store the rows as one fp16 plane (map_o_f16)
 };
 
 // work item i of this CTA's stride loop -> 128-row tile
@@ -63,20 +70,24 @@ __global__ void ffn_tile_list_kernel(const int* __restrict__ row_limit, int extr
 template <int NPASS>
 struct FfnSmem {
   // one 32 KB stage, three uses:
-  //   G1       : u_hi 8K | W11_hi 8K | u_lo 8K | W11_lo 8K          (slab = 128 rows x 32 k per operand)
+  //   G1       : u_hi 8K | W11_hi 8K | u_lo 8K | W11_lo 8K          (slab = 128 rows x 32 k per operand; NPASS 2: no u_lo)
   //   G2       : W_eff_hi 16K | W_eff_lo 16K                        (slab = 256 n-rows x 32 k)
-  //   residual : R_hi 8K | R_lo 8K | I_hi 16K
+  //   residual : R_hi 8K | R_lo 8K
   static constexpr int kAPlane = kFM * kFK * 2;   // 8 KB
   static constexpr int kW2Plane = kFD * kFK * 2;  // 16 KB
   static constexpr int kStage = 32 * 1024;
   static constexpr int kG1W1Hi = kAPlane, kG1ALo = 2 * kAPlane, kG1W1Lo = 3 * kAPlane;
   static constexpr int kG2Lo = kW2Plane;
-  static constexpr int kResLo = kAPlane, kResI = 2 * kAPlane;
+  static constexpr int kResLo = kAPlane;
   static constexpr int kMaxF = 2048;
-  static constexpr int kFixed = 4 * kFStageChunk + kMaxF * 4 + 3 * kFD * 4 + 2 * 2 * kFM * 8 + 1024;
+  static constexpr int kI32 = 32 * kFK * 2;       // the 32 x 32 identity block of the residual products (2 KB)
+  static constexpr int kF16Stage = kFM * 32 * 2;  // fp16 output plane: one 8 KB staging buffer per epilogue half
+  static constexpr int kFixed = 4 * kFStageChunk + kI32 + 2 * kF16Stage + kMaxF * 4 + 3 * kFD * 4 + 2 * 2 * kFM * 8 + 1024;
   static constexpr int kStages = (226 * 1024 - kFixed) / kStage > 6 ? 6 : (226 * 1024 - kFixed) / kStage;
   static constexpr int kOffStaging = kStages * kStage;
-  static constexpr int kOffB1 = kOffStaging + 4 * kFStageChunk;   // b1: kMaxF floats
+  static constexpr int kOffI32 = kOffStaging + 4 * kFStageChunk;  // 1024-aligned (swizzled operand tile)
+  static constexpr int kOffF16 = kOffI32 + kI32;
+  static constexpr int kOffB1 = kOffF16 + 2 * kF16Stage;          // b1: kMaxF floats
   static constexpr int kOffVec = kOffB1 + kMaxF * 4;              // b2 | gamma | beta
   static constexpr int kOffStats = kOffVec + 3 * kFD * 4;
   static constexpr int kTotal = kStages * kStage + kFixed;
@@ -107,14 +118,16 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
                     const __grid_constant__ CUtensorMap map_w2_hi, const __grid_constant__ CUtensorMap map_w2_lo,
                     const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
                     const __grid_constant__ CUtensorMap map_ident, const __grid_constant__ CUtensorMap map_o_hi,
-                    const __grid_constant__ CUtensorMap map_o_lo, const FfnParams p) {
+                    const __grid_constant__ CUtensorMap map_o_lo, const __grid_constant__ CUtensorMap map_o_f16,
+                    const FfnParams p) {
   using L = FfnSmem<NPASS>;
   constexpr int kStages = L::kStages;
   constexpr int kSlabs = kFD / kFK;  // 8 k-slabs per product (K = 256 everywhere)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc1_full[2], v_ready[2], acc2_full, acc2_empty;
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc1_full[2], v_ready[2], acc2_full, acc2_empty,
+      ident_bar;
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -136,6 +149,7 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
     }
     mbar_init(&acc2_full, 1);
     mbar_init(&acc2_empty, 8);
+    mbar_init(&ident_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, 512);
@@ -166,17 +180,19 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
           phase ^= 1;
         }
       };
+      if ((int)blockIdx.x < ntiles) {  // the identity block: once per CTA that has work
+        mbar_expect_tx(&ident_bar, L::kI32);
+        tma_load_3d(smem + L::kOffI32, &map_ident, &ident_bar, 0, 0, 0);
+      }
       auto load_g1 = [&](int r0, int c) {  // u slab + W11 slab, 8 slabs
         for (int ks = 0; ks < kSlabs; ++ks) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * L::kStage;
-          mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 4 : 2) * L::kAPlane);
+          mbar_expect_tx(&full_bar[stage], (NPASS + 1) * L::kAPlane);
           tma_load_3d(st, &map_u_hi, &full_bar[stage], ks * kFK, r0, 0);
           tma_load_3d(st + L::kG1W1Hi, &map_w1_hi, &full_bar[stage], ks * kFK, c * kFC, 0);
-          if (NPASS == 3) {
-            tma_load_3d(st + L::kG1ALo, &map_u_lo, &full_bar[stage], ks * kFK, r0, 0);
-            tma_load_3d(st + L::kG1W1Lo, &map_w1_lo, &full_bar[stage], ks * kFK, c * kFC, 0);
-          }
+          if (NPASS == 3) tma_load_3d(st + L::kG1ALo, &map_u_lo, &full_bar[stage], ks * kFK, r0, 0);
+          if (NPASS >= 2) tma_load_3d(st + L::kG1W1Lo, &map_w1_lo, &full_bar[stage], ks * kFK, c * kFC, 0);
           next();
         }
       };
@@ -184,9 +200,9 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
         for (int ks = 0; ks < kFC / kFK; ++ks) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * L::kStage;
-          mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 2 : 1) * L::kW2Plane);
+          mbar_expect_tx(&full_bar[stage], (NPASS >= 2 ? 2 : 1) * L::kW2Plane);
           tma_load_3d(st, &map_w2_hi, &full_bar[stage], c * kFC + ks * kFK, 0, 0);
-          if (NPASS == 3) tma_load_3d(st + L::kG2Lo, &map_w2_lo, &full_bar[stage], c * kFC + ks * kFK, 0, 0);
+          if (NPASS >= 2) tma_load_3d(st + L::kG2Lo, &map_w2_lo, &full_bar[stage], c * kFC + ks * kFK, 0, 0);
           next();
         }
       };
@@ -197,22 +213,24 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
           if (c + 1 < nchunks) load_g1(r0, c + 1);
           load_g2(c);
         }
-        for (int ks = 0; ks < kSlabs; ++ks) {  // residual: R_hi, R_lo against the identity block
+        for (int ks = 0; ks < kSlabs; ++ks) {  // residual: R_hi, R_lo (against the resident identity block)
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * L::kStage;
-          mbar_expect_tx(&full_bar[stage], 2 * L::kAPlane + L::kW2Plane);
+          mbar_expect_tx(&full_bar[stage], 2 * L::kAPlane);
           tma_load_3d(st, &map_r_hi, &full_bar[stage], ks * kFK, r0, 0);
           tma_load_3d(st + L::kResLo, &map_r_lo, &full_bar[stage], ks * kFK, r0, 0);
-          tma_load_3d(st + L::kResI, &map_ident, &full_bar[stage], ks * kFK, 0, 0);
           next();
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr uint32_t idesc1 = make_idesc(kFmtBF16, kFM, kFC, 0, 0);  // G1: M128 x N128
-    constexpr uint32_t idesc2 = make_idesc(kFmtBF16, kFM, kFD, 0, 0);  // G2 / residual: M128 x N256
+    constexpr int kAFmt = NPASS == 2 ? kFmtF16 : kFmtBF16;                     // activation operand: fp16 in the 2-pass recipe
+    constexpr uint32_t idesc1 = make_idesc_ab(kAFmt, kFmtBF16, kFM, kFC);      // G1: M128 x N128
+    constexpr uint32_t idesc2 = make_idesc_ab(kAFmt, kFmtBF16, kFM, kFD);      // G2: M128 x N256
+    constexpr uint32_t idesc_r = make_idesc(kFmtBF16, kFM, 32, 0, 0);          // residual: M128 x N32 per 32-column slab
     const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 512, kSwizzle64);
+    const uint64_t d_i32 = make_smem_desc(smem_u32(smem + L::kOffI32), 16, 512, kSwizzle64);
     int stage = 0;
     uint32_t phase = 0;
     uint32_t chunk_ctr = 0;  // chunks since kernel start: buffer = ctr & 1, barrier parity = (ctr >> 1) & 1
@@ -239,6 +257,8 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
           if (NPASS == 3) {
             umma_f16_c<true>(acc, a_lo, w_hi, idesc1);
             umma_f16_c<true>(acc, desc_advance(a_lo, 32), desc_advance(w_hi, 32), idesc1);
+          }
+          if (NPASS >= 2) {
             umma_f16_c<true>(acc, a_hi, w_lo, idesc1);
             umma_f16_c<true>(acc, desc_advance(a_hi, 32), desc_advance(w_lo, 32), idesc1);
           }
@@ -274,6 +294,8 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
             if (NPASS == 3) {
               umma_f16_ts_c<true>(t_acc2, v_lo, w_hi, idesc2);
               umma_f16_ts_c<true>(t_acc2, v_lo + 8, desc_advance(w_hi, 32), idesc2);
+            }
+            if (NPASS >= 2) {
               umma_f16_ts_c<true>(t_acc2, v_hi, w_lo, idesc2);
               umma_f16_ts_c<true>(t_acc2, v_hi + 8, desc_advance(w_lo, 32), idesc2);
             }
@@ -283,18 +305,19 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
           next();
         }
       }
-      // ---- residual x1 on the tensor core: acc2 += R_hi . I + R_lo . I ----
+      // ---- residual x1 on the tensor core: acc2[:, 32 ks .. 32 ks + 32) += R_hi[ks] . I32 + R_lo[ks] . I32 ----
+      if (it == 0) mbar_wait(&ident_bar, 0);
       for (int ks = 0; ks < kSlabs; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (elect_one()) {
           const uint64_t a_hi = desc_advance(d0, stage * L::kStage);
           const uint64_t a_lo = desc_advance(a_hi, L::kResLo);
-          const uint64_t w_hi = desc_advance(a_hi, L::kResI);
-          umma_f16_c<true>(t_acc2, a_hi, w_hi, idesc2);
-          umma_f16_c<true>(t_acc2, desc_advance(a_hi, 32), desc_advance(w_hi, 32), idesc2);
-          umma_f16_c<true>(t_acc2, a_lo, w_hi, idesc2);
-          umma_f16_c<true>(t_acc2, desc_advance(a_lo, 32), desc_advance(w_hi, 32), idesc2);
+          const uint32_t acc = t_acc2 + 32 * ks;
+          umma_f16_c<true>(acc, a_hi, d_i32, idesc_r);
+          umma_f16_c<true>(acc, desc_advance(a_hi, 32), desc_advance(d_i32, 32), idesc_r);
+          umma_f16_c<true>(acc, a_lo, d_i32, idesc_r);
+          umma_f16_c<true>(acc, desc_advance(a_lo, 32), desc_advance(d_i32, 32), idesc_r);
           umma_commit(&empty_bar[stage]);
           if (ks + 1 == kSlabs) umma_commit(&acc2_full);
         }
@@ -331,7 +354,8 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
 #pragma unroll
           for (int e = 0; e < 16; ++e) {
             const float x0 = fmaxf(v[2 * e] + bb[2 * e], 0.f), x1 = fmaxf(v[2 * e + 1] + bb[2 * e + 1], 0.f);
-            split_pack2(x0, x1, hi[e], lo[e]);
+            if (NPASS == 2) hi[e] = pack_f16_sat(x0, x1);
+            else split_pack2(x0, x1, hi[e], lo[e]);
           }
           f_tmem_st16(ta, hi);
           if (NPASS == 3) f_tmem_st16(ta + 16, lo);
@@ -391,8 +415,21 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
         if (issuer) {
           f_tma_store_3d(&map_o_hi, sb, 32 * j, r0, 0);
           f_tma_store_3d(&map_o_lo, sb + kFStageChunk / 2, 32 * j, r0, 0);
-          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         }
+        if (p.out_f16) {  // single staging buffer per half: every earlier store has been read (wait_group.read above)
+          uint8_t* rf = smem + L::kOffF16 + half * L::kF16Stage + r * 64;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int u = (i ^ ((r >> 1) & 3)) << 4;
+            *reinterpret_cast<uint4*>(rf + u) =
+                make_uint4(pack_f16_sat(v[8 * i], v[8 * i + 1]), pack_f16_sat(v[8 * i + 2], v[8 * i + 3]),
+                           pack_f16_sat(v[8 * i + 4], v[8 * i + 5]), pack_f16_sat(v[8 * i + 6], v[8 * i + 7]));
+          }
+          fence_proxy_async_smem();
+          f_bar_sync(1 + half, 128);
+          if (issuer) f_tma_store_3d(&map_o_f16, smem + L::kOffF16 + half * L::kF16Stage, 32 * j, r0, 0);
+        }
+        if (issuer) asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
       tc_fence_before();
       __syncwarp();
@@ -422,7 +459,7 @@ static int launch_ffn(const CUtensorMap* m, const FfnParams& p, cudaStream_t s) 
     configured = true;
   }
   const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  kern<<<grid, kFThreads, L::kTotal, s>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], p);
+  kern<<<grid, kFThreads, L::kTotal, s>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], p);
   LFS2_CHECK_LAUNCH("ffn_fused_tc");
   return LFS2_OK;
 }
@@ -450,39 +487,50 @@ extern "C" int lfs2_ffn_fused_tc_limited(const void* u_hi, const void* u_lo, int
                                          const float* b2, const void* res_hi, const void* res_lo, const void* ident_hi,
                                          const float* gamma, const float* beta, float eps, void* out_hi, void* out_lo,
                                          int npass, const int* row_limit, int limit_extra, void* workspace, void* stream) {
+  return lfs2_ffn_fused_tc_ex(u_hi, u_lo, batch, t, w1_hi, w1_lo, f, b1, w2_hi, w2_lo, b2, res_hi, res_lo, ident_hi, gamma,
+                              beta, eps, out_hi, out_lo, nullptr, npass, row_limit, limit_extra, workspace, stream);
+}
+
+extern "C" int lfs2_ffn_fused_tc_ex(const void* u_hi, const void* u_lo, int batch, int t, const void* w1_hi,
+                                    const void* w1_lo, int f, const float* b1, const void* w2_hi, const void* w2_lo,
+                                    const float* b2, const void* res_hi, const void* res_lo, const void* ident_hi,
+                                    const float* gamma, const float* beta, float eps, void* out_hi, void* out_lo,
+                                    void* out_f16, int npass, const int* row_limit, int limit_extra, void* workspace,
+                                    void* stream) {
   LFS2_REQUIRE(batch >= 0 && t >= 0 && (long long)batch * t <= 0x7fffffffLL, LFS2_ERR_INVALID_ARG, "ffn_fused_tc: bad shape");
   LFS2_REQUIRE(!row_limit || workspace, LFS2_ERR_INVALID_ARG, "ffn_fused_tc: a row-limited launch needs its workspace");
   const int m = batch * t;
   LFS2_REQUIRE(u_hi && w1_hi && w2_hi && res_hi && res_lo && ident_hi && gamma && beta && out_hi && out_lo,
                LFS2_ERR_INVALID_ARG, "ffn_fused_tc: null pointer");
-  LFS2_REQUIRE(npass == 1 || npass == 3, LFS2_ERR_INVALID_ARG, "ffn_fused_tc: npass must be 1 or 3");
-  LFS2_REQUIRE(npass == 1 || (u_lo && w1_lo && w2_lo), LFS2_ERR_INVALID_ARG, "ffn_fused_tc: npass=3 needs the lo planes");
+  LFS2_REQUIRE(npass >= 1 && npass <= 3, LFS2_ERR_INVALID_ARG, "ffn_fused_tc: npass must be 1, 2 or 3");
+  LFS2_REQUIRE(npass == 1 || (w1_lo && w2_lo), LFS2_ERR_INVALID_ARG, "ffn_fused_tc: npass >= 2 needs the weight lo planes");
+  LFS2_REQUIRE(npass != 3 || u_lo, LFS2_ERR_INVALID_ARG, "ffn_fused_tc: npass=3 needs the lo plane of u");
   if (m == 0) return LFS2_OK;
   LFS2_REQUIRE(m > 0 && f > 0, LFS2_ERR_INVALID_ARG, "ffn_fused_tc: bad shape");
   LFS2_REQUIRE(f % kFC == 0 && f <= FfnSmem<3>::kMaxF, LFS2_ERR_UNSUPPORTED,
                "ffn_fused_tc: hidden width %d must be a multiple of %d and <= %d (model width is fixed at %d)", f, kFC,
                FfnSmem<3>::kMaxF, kFD);
   LFS2_REQUIRE(aligned16(u_hi) && aligned16(w1_hi) && aligned16(w2_hi) && aligned16(res_hi) && aligned16(res_lo) &&
-                   aligned16(out_hi) && aligned16(out_lo) && (!u_lo || aligned16(u_lo)),
+                   aligned16(out_hi) && aligned16(out_lo) && (!u_lo || aligned16(u_lo)) && aligned16(out_f16),
                LFS2_ERR_INVALID_ARG, "ffn_fused_tc: pointers must be 16-byte aligned");
-  CUtensorMap maps[11];
+  CUtensorMap maps[12];
   bool ok = make_tmap_3d(&maps[0], u_hi, kFD, m, 1, kFK, kFM, 64) && make_tmap_3d(&maps[2], w1_hi, kFD, f, 1, kFK, kFC, 64) &&
             make_tmap_3d(&maps[4], w2_hi, f, kFD, 1, kFK, kFD, 64) && make_tmap_3d(&maps[6], res_hi, kFD, m, 1, kFK, kFM, 64) &&
             make_tmap_3d(&maps[7], res_lo, kFD, m, 1, kFK, kFM, 64) &&
-            make_tmap_3d(&maps[8], ident_hi, kFD, kFD, 1, kFK, kFD, 64) &&
+            make_tmap_3d(&maps[8], ident_hi, kFD, kFD, 1, kFK, 32, 64) &&
             make_tmap_3d(&maps[9], out_hi, kFD, m, 1, 32, kFM, 64) && make_tmap_3d(&maps[10], out_lo, kFD, m, 1, 32, kFM, 64);
-  if (npass == 3)
-    ok = ok && make_tmap_3d(&maps[1], u_lo, kFD, m, 1, kFK, kFM, 64) && make_tmap_3d(&maps[3], w1_lo, kFD, f, 1, kFK, kFC, 64) &&
-         make_tmap_3d(&maps[5], w2_lo, f, kFD, 1, kFK, kFD, 64);
-  else {
-    maps[1] = maps[0];
-    maps[3] = maps[2];
-    maps[5] = maps[4];
-  }
+  maps[1] = maps[0];
+  maps[3] = maps[2];
+  maps[5] = maps[4];
+  maps[11] = maps[9];
+  if (npass == 3) ok = ok && make_tmap_3d(&maps[1], u_lo, kFD, m, 1, kFK, kFM, 64);
+  if (npass >= 2)
+    ok = ok && make_tmap_3d(&maps[3], w1_lo, kFD, f, 1, kFK, kFC, 64) && make_tmap_3d(&maps[5], w2_lo, f, kFD, 1, kFK, kFD, 64);
+  if (out_f16) ok = ok && make_tmap_3d(&maps[11], out_f16, kFD, m, 1, 32, kFM, 64);
   LFS2_REQUIRE(ok, LFS2_ERR_CUDA, "ffn_fused_tc: cuTensorMapEncodeTiled failed");
   FfnParams p;
   p.m = m; p.f = f; p.total_tiles = ceil_div(m, kFM);
-  p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta; p.eps = eps;
+  p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta; p.eps = eps; p.out_f16 = out_f16 != nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   p.tile_list = nullptr;
   if (!row_limit && workspace) {
@@ -497,5 +545,5 @@ extern "C" int lfs2_ffn_fused_tc_limited(const void* u_hi, const void* u_lo, int
     LFS2_CHECK_LAUNCH("ffn_tile_list");
     p.tile_list = list;
   }
-  return npass == 3 ? launch_ffn<3>(maps, p, s) : launch_ffn<1>(maps, p, s);
+  return npass == 3 ? launch_ffn<3>(maps, p, s) : (npass == 2 ? launch_ffn<2>(maps, p, s) : launch_ffn<1>(maps, p, s));
 }

@@ -89,14 +89,16 @@ struct SmemLayout {
   static constexpr bool kHasLo = NPASS == 3 || LN;  // LN variants stream residual lo planes even in bf16 mode
   static constexpr int kAPlane = kBM * kBK * 2;     // 8 KB
   static constexpr int kWPlane = N_TILE * kBK * 2;
-  static constexpr int kStage = (kHasLo ? 2 : 1) * kAPlane + (NPASS == 3 ? 2 : 1) * kWPlane;
+  static constexpr int kStage = (kHasLo ? 2 : 1) * kAPlane + (NPASS >= 2 ? 2 : 1) * kWPlane;
   static constexpr int kOffWHi = kAPlane;
   static constexpr int kOffALo = kAPlane + kWPlane;
-  static constexpr int kOffWLo = 2 * kAPlane + kWPlane;
-  static constexpr int kFixed = 4 * kStageChunk + (LN ? 3 * N_TILE * 4 + 2 * 2 * kBM * 8 : 0) + kEdge + 1024;
+  static constexpr int kOffWLo = (kHasLo ? 2 : 1) * kAPlane + kWPlane;
+  static constexpr int kI32 = kHasLo ? 32 * kBK * 2 : 0;               // 32 x 32 identity block of the residual products
+  static constexpr int kFixed = 4 * kStageChunk + kI32 + (LN ? 3 * N_TILE * 4 + 2 * 2 * kBM * 8 : 0) + kEdge + 1024;
   static constexpr int kStages = (226 * 1024 - kFixed) / kStage > 6 ? 6 : (226 * 1024 - kFixed) / kStage;
   static constexpr int kOffStaging = kStages * kStage;                 // 2 halves x 2 chunks, 1024-aligned
-  static constexpr int kOffVec = kOffStaging + 4 * kStageChunk;        // bias | gamma | beta for LN: 3 * N_TILE floats
+  static constexpr int kOffI32 = kOffStaging + 4 * kStageChunk;        // 1024-aligned (swizzled operand tile)
+  static constexpr int kOffVec = kOffI32 + kI32;                       // bias | gamma | beta for LN: 3 * N_TILE floats
   static constexpr int kOffStats = kOffVec + 3 * N_TILE * 4;           // LN partial (sum, sumsq): [2 tiles][2 halves][128]
   static constexpr int kOffEdge = kOffStats + 2 * 2 * kBM * 8;         // fused-epilogue vectors (kEdge bytes)
   static constexpr int kTotal = kStages * kStage + kFixed;
@@ -178,12 +180,6 @@ struct TileWalk {
 __device__ __forceinline__ float activate(float x, int kind, float slope) {
   return kind == 1 ? fmaxf(x, 0.f) : (kind == 2 ? (x > 0.f ? x : x * slope) : x);
 }
-// two fp32 -> packed fp16 pair (element a in the low half), saturating instead of overflowing to inf
-__device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
-  uint32_t r;
-  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
-  return r;
-}
 
 template <int N_TILE, int NPASS, bool LN, int OUT, bool MC, int EPI = 0>
 __global__ void __launch_bounds__(kGemmTcThreads, 1)
@@ -193,6 +189,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                const __grid_constant__ CUtensorMap map_ident, const __grid_constant__ CUtensorMap map_o0,
                const __grid_constant__ CUtensorMap map_o1, const GemmTcParams p) {
   static_assert(EPI == kEpiNone || (LN && !MC && OUT == kOutPlanes), "fused predictor epilogues ride the LayerNorm variant");
+  static_assert(NPASS != 2 || !LN, "the 2-pass recipe (fp16 activation plane) has no LayerNorm / residual build");
   using L = SmemLayout<N_TILE, NPASS, LN, EPI>;
   constexpr int kStages = L::kStages;
   constexpr int kAccCols = (N_TILE <= 32) ? 32 : (N_TILE <= 64) ? 64 : (N_TILE <= 128) ? 128 : 256;
@@ -201,7 +198,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full[2], tmem_empty[2];
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full[2], tmem_empty[2], ident_bar;
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -221,6 +218,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       mbar_init(&tmem_full[i], 1);
       mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
     }
+    mbar_init(&ident_bar, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
@@ -265,6 +263,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (MC) tma_load_3d_mc(dst + w_off, map, bar, c0, c1 + w_row, 0, (uint16_t)3);
         else tma_load_3d(dst, map, bar, c0, c1, 0);
       };
+      if (L::kHasLo && r_slabs > 0 && walk.first < walk.count) {  // the identity block of the residual products: once
+        mbar_expect_tx(&ident_bar, L::kI32);
+        tma_load_3d(smem + L::kOffI32, &map_ident, &ident_bar, 0, 0, 0);
+      }
       for (int tile = walk.first; tile < walk.count; tile += walk.stride) {
         int b, t0, n0;
         walk.coords(p, tile, N_TILE, b, t0, n0);
@@ -276,24 +278,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #ifdef LFS2_DIAG_NO_LO_LOADS  // timing diagnostics only (tools/gemm_ab.py): wrong results
             mbar_expect_tx(&full_bar[stage], L::kAPlane + L::kWPlane);
 #else
-            mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 2 : 1) * (L::kAPlane + L::kWPlane));
+            mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 2 : 1) * L::kAPlane + (NPASS >= 2 ? 2 : 1) * L::kWPlane);
 #endif
             tma_load_3d(st, &map_a_hi, &full_bar[stage], c0, t0 + (tap - p.half) * p.dil, b);
             load_w(st + L::kOffWHi, &map_w_hi, &full_bar[stage], tap * p.d + c0, n0);
 #ifdef LFS2_DIAG_NO_LO_LOADS
             if (false) {
 #else
-            if (NPASS == 3) {
+            if (NPASS >= 2) {
 #endif
-              tma_load_3d(st + L::kOffALo, &map_a_lo, &full_bar[stage], c0, t0 + (tap - p.half) * p.dil, b);
+              if (NPASS == 3) tma_load_3d(st + L::kOffALo, &map_a_lo, &full_bar[stage], c0, t0 + (tap - p.half) * p.dil, b);
               load_w(st + L::kOffWLo, &map_w_lo, &full_bar[stage], tap * p.d + c0, n0);
             }
-          } else if (L::kHasLo) {  // residual slab: R_hi, R_lo against the identity block
+          } else if (L::kHasLo) {  // residual slab: R_hi, R_lo (against the resident 32 x 32 identity block)
             int c0 = n0 + (ks - a_slabs) * kBK;
-            mbar_expect_tx(&full_bar[stage], 2 * L::kAPlane + L::kWPlane);
+            mbar_expect_tx(&full_bar[stage], 2 * L::kAPlane);
             tma_load_3d(st, &map_r_hi, &full_bar[stage], c0, t0, b);
             tma_load_3d(st + L::kOffALo, &map_r_lo, &full_bar[stage], c0, t0, b);
-            load_w(st + L::kOffWHi, &map_ident, &full_bar[stage], c0, n0);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -306,8 +307,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ===================== MMA issuer =====================
     // whole warp runs the uniform control flow (descriptors stay in uniform registers), one
     // elected lane issues; per instruction the descriptor is a 64-bit add on a precomputed base
-    constexpr uint32_t idesc = make_idesc(kFmtBF16, kBM, N_TILE, 0, 0);
+    // NPASS = 2: the activation operand is ONE fp16 plane against the bf16 hi/lo weight planes (a.w_hi + a.w_lo)
+    constexpr uint32_t idesc = make_idesc_ab(NPASS == 2 ? kFmtF16 : kFmtBF16, kFmtBF16, kBM, N_TILE);
+    constexpr uint32_t idesc_r = make_idesc(kFmtBF16, kBM, 32, 0, 0);  // residual: one 32-column block per slab
     const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 512, kSwizzle64);
+    const uint64_t d_i32 = make_smem_desc(smem_u32(smem + L::kOffI32), 16, 512, kSwizzle64);
+    if (L::kHasLo && r_slabs > 0 && walk.first < walk.count) mbar_wait(&ident_bar, 0);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -326,25 +331,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           const uint64_t a_lo = desc_advance(a_hi, L::kOffALo);
           const uint64_t w_lo = desc_advance(a_hi, L::kOffWLo);
           const bool res = ks >= a_slabs;
-          // 16 bf16 = 32 bytes along K inside the 64-byte swizzled row per k16 step
-          if (ks == 0) umma_f16_c<false>(d_tmem, a_hi, w_hi, idesc);
-          else umma_f16_c<true>(d_tmem, a_hi, w_hi, idesc);
-          umma_f16_c<true>(d_tmem, desc_advance(a_hi, 32), desc_advance(w_hi, 32), idesc);
+          if (L::kHasLo && res) {
+            // residual: acc[:, 32 j .. 32 j + 32) += R_hi[j] . I32 + R_lo[j] . I32 -- N = 32 instructions, an eighth of
+            // the tensor work of a full-width identity slab, and the identity never travels again
+            const uint32_t acc_r = d_tmem + 32 * (ks - a_slabs);
+            umma_f16_c<true>(acc_r, a_hi, d_i32, idesc_r);
+            umma_f16_c<true>(acc_r, desc_advance(a_hi, 32), desc_advance(d_i32, 32), idesc_r);
+            umma_f16_c<true>(acc_r, a_lo, d_i32, idesc_r);
+            umma_f16_c<true>(acc_r, desc_advance(a_lo, 32), desc_advance(d_i32, 32), idesc_r);
+          } else {
+            // 16 bf16 = 32 bytes along K inside the 64-byte swizzled row per k16 step
+            if (ks == 0) umma_f16_c<false>(d_tmem, a_hi, w_hi, idesc);
+            else umma_f16_c<true>(d_tmem, a_hi, w_hi, idesc);
+            umma_f16_c<true>(d_tmem, desc_advance(a_hi, 32), desc_advance(w_hi, 32), idesc);
 #ifdef LFS2_DIAG_NO_LO_MMAS
-          if (false) {
+            if (false) {
 #else
-          if (L::kHasLo && (NPASS == 3 || res)) {
+            if (NPASS == 3) {
 #endif
-            umma_f16_c<true>(d_tmem, a_lo, w_hi, idesc);
-            umma_f16_c<true>(d_tmem, desc_advance(a_lo, 32), desc_advance(w_hi, 32), idesc);
-          }
+              umma_f16_c<true>(d_tmem, a_lo, w_hi, idesc);
+              umma_f16_c<true>(d_tmem, desc_advance(a_lo, 32), desc_advance(w_hi, 32), idesc);
+            }
 #ifdef LFS2_DIAG_NO_LO_MMAS
-          if (false) {
+            if (false) {
 #else
-          if (NPASS == 3 && !res) {
+            if (NPASS >= 2) {
 #endif
-            umma_f16_c<true>(d_tmem, a_hi, w_lo, idesc);
-            umma_f16_c<true>(d_tmem, desc_advance(a_hi, 32), desc_advance(w_lo, 32), idesc);
+              umma_f16_c<true>(d_tmem, a_hi, w_lo, idesc);
+              umma_f16_c<true>(d_tmem, desc_advance(a_hi, 32), desc_advance(w_lo, 32), idesc);
+            }
           }
           if (MC) umma_commit_mc(&empty_bar[stage], (uint16_t)3);  // ... in both CTAs: either producer may refill it
           else umma_commit(&empty_bar[stage]);                   // smem slot reusable once these MMAs retire
@@ -735,6 +750,17 @@ static int dispatch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, int npas
     if (out_kind == kOutBF16) return launch_gemm_tc<N_TILE, 3, LN, kOutBF16, MC>(m, p, s);
     return launch_gemm_tc<N_TILE, 3, LN, kOutPlanes, MC>(m, p, s);
   }
+  if (npass == 2) {
+    if constexpr (!LN) {
+      if (out_kind == kOutF32) return launch_gemm_tc<N_TILE, 2, false, kOutF32, MC>(m, p, s);
+      if (out_kind == kOutF16) return launch_gemm_tc<N_TILE, 2, false, kOutF16, MC>(m, p, s);
+      if (out_kind == kOutBF16) return launch_gemm_tc<N_TILE, 2, false, kOutBF16, MC>(m, p, s);
+      return launch_gemm_tc<N_TILE, 2, false, kOutPlanes, MC>(m, p, s);
+    } else {
+      set_error("gemm_tc: npass = 2 has no LayerNorm build");
+      return LFS2_ERR_UNSUPPORTED;
+    }
+  }
   if (out_kind == kOutF32) return launch_gemm_tc<N_TILE, 1, LN, kOutF32, MC>(m, p, s);
   if (out_kind == kOutF16) return launch_gemm_tc<N_TILE, 1, LN, kOutF16, MC>(m, p, s);
   if (out_kind == kOutBF16) return launch_gemm_tc<N_TILE, 1, LN, kOutBF16, MC>(m, p, s);
@@ -791,8 +817,11 @@ int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int t, int d,
                     float eps, void* out0, void* out1, int out_kind, int npass, const int* row_limit, int limit_extra,
                     void* workspace, const uint8_t* row_mask, void* stream) {
   LFS2_REQUIRE(a_hi && w_hi && out0, LFS2_ERR_INVALID_ARG, "gemm_tc: null operand");
-  LFS2_REQUIRE(npass == 1 || npass == 3, LFS2_ERR_INVALID_ARG, "gemm_tc: npass must be 1 or 3");
-  LFS2_REQUIRE(npass == 1 || (a_lo && w_lo), LFS2_ERR_INVALID_ARG, "gemm_tc: npass=3 needs the lo planes");
+  LFS2_REQUIRE(npass >= 1 && npass <= 3, LFS2_ERR_INVALID_ARG, "gemm_tc: npass must be 1, 2 or 3");
+  LFS2_REQUIRE(npass == 1 || w_lo, LFS2_ERR_INVALID_ARG, "gemm_tc: npass >= 2 needs the weight lo plane");
+  LFS2_REQUIRE(npass != 3 || a_lo, LFS2_ERR_INVALID_ARG, "gemm_tc: npass=3 needs the lo plane of a");
+  LFS2_REQUIRE(npass != 2 || (!gamma && !res_hi), LFS2_ERR_UNSUPPORTED,
+               "gemm_tc: npass = 2 (one fp16 activation plane) has no LayerNorm / residual build");
   LFS2_REQUIRE(out_kind >= LFS2_OUT_PLANES && out_kind <= LFS2_OUT_BF16, LFS2_ERR_INVALID_ARG,
                "gemm_tc: out_kind must be LFS2_OUT_PLANES, LFS2_OUT_F32, LFS2_OUT_F16 or LFS2_OUT_BF16");
   LFS2_REQUIRE(out_kind != LFS2_OUT_PLANES || out1, LFS2_ERR_INVALID_ARG, "gemm_tc: plane output needs out1 (the lo plane)");
@@ -831,15 +860,13 @@ int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int t, int d,
   GemmTcMaps m;
   const uint64_t ktot = (uint64_t)taps * d;
   bool ok = make_tmap_3d(&m.ah, a_hi, d, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.wh, w_hi, ktot, n, 1, kBK, w_box, 64);
-  if (npass == 3)
-    ok = ok && make_tmap_3d(&m.al, a_lo, d, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.wl, w_lo, ktot, n, 1, kBK, w_box, 64);
-  else {
-    m.al = m.ah;
-    m.wl = m.wh;
-  }
+  m.al = m.ah;
+  m.wl = m.wh;
+  if (npass == 3) ok = ok && make_tmap_3d(&m.al, a_lo, d, t, batch, kBK, kBM, 64);
+  if (npass >= 2) ok = ok && make_tmap_3d(&m.wl, w_lo, ktot, n, 1, kBK, w_box, 64);
   if (res_hi)
     ok = ok && make_tmap_3d(&m.rh, res_hi, n, t, batch, kBK, kBM, 64) &&
-         make_tmap_3d(&m.rl, res_lo, n, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.ident, ident_hi, n, n, 1, kBK, w_box, 64);
+         make_tmap_3d(&m.rl, res_lo, n, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.ident, ident_hi, n, n, 1, kBK, 32, 64);
   else {
     m.rh = m.ah;
     m.rl = m.ah;
@@ -969,7 +996,7 @@ int lfs2_predictor_layer_tc(const void* a_hi, const void* a_lo, int batch, int t
 
 // x (n) fp32 -> hi/lo bf16 planes
 __global__ void split_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo,
-                                  size_t n4) {
+                                  uint2* __restrict__ f16, size_t n4) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 v = x[i];
@@ -980,16 +1007,22 @@ __global__ void split_bf16_kernel(const float4* __restrict__ x, uint2* __restric
   split_bf16(v.w, h[3], l[3]);
   hi[i] = make_uint2(pack_bf16(h[0], h[1]), pack_bf16(h[2], h[3]));
   lo[i] = make_uint2(pack_bf16(l[0], l[1]), pack_bf16(l[2], l[3]));
+  if (f16) f16[i] = make_uint2(pack_f16_sat(v.x, v.y), pack_f16_sat(v.z, v.w));
 }
 
 int lfs2_split_bf16(const float* x, void* hi, void* lo, long long n, void* stream) {
-  LFS2_REQUIRE(x && hi && lo, LFS2_ERR_INVALID_ARG, "split_bf16: null pointer");
+  return lfs2_split_bf16_ex(x, hi, lo, nullptr, n, stream);
+}
+
+int lfs2_split_bf16_ex(const float* x, void* hi, void* lo, void* f16, long long n, void* stream) {
+  LFS2_REQUIRE(x && hi && lo && aligned16(f16), LFS2_ERR_INVALID_ARG, "split_bf16: null or misaligned pointer");
   if (n == 0) return LFS2_OK;
   LFS2_REQUIRE(n > 0 && n % 4 == 0, LFS2_ERR_UNSUPPORTED, "split_bf16: n must be a positive multiple of 4");
   LFS2_REQUIRE(aligned16(x) && aligned16(hi) && aligned16(lo), LFS2_ERR_INVALID_ARG,
                "split_bf16: pointers must be 16-byte aligned");
   size_t n4 = (size_t)n / 4;
-  split_bf16_kernel<<<ceil_div(n4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)hi, (uint2*)lo, n4);
+  split_bf16_kernel<<<ceil_div(n4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)hi, (uint2*)lo,
+                                                                         (uint2*)f16, n4);
   LFS2_CHECK_LAUNCH("split_bf16");
   return LFS2_OK;
 }

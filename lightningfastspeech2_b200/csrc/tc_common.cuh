@@ -191,6 +191,17 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int m, int n, int a_m
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn_major << 15) |
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
+// A and B in different 16-bit formats (K-major both): an fp16 activation plane against bf16 weight planes
+__host__ __device__ constexpr uint32_t make_idesc_ab(int a_fmt, int b_fmt, int m, int n) {
+  return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
+}
+// two fp32 -> packed fp16 pair (element a in the low half), saturating instead of overflowing to inf
+__device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 
 // ------------------------------------------------------------------ split-bf16 helpers
 // x = hi + lo (+ O(2^-17 |x|)): three bf16 MMAs hi*hi + lo*hi + hi*lo reproduce an fp32

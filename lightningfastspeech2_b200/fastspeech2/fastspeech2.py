@@ -87,7 +87,9 @@ class TransformerStack(nn.Module):
         row_limit = (lengths, extra): rows at or after roundup128(lengths[b] + extra) are neither computed nor
         written by any layer (FastSpeech2.skip_pad_rows)."""
         if mask is None and all(mod.tc_capable(src.shape[-1]) for mod in self.layers):
-            xp = ops.planes_of(src)
+            first = self.layers[0] if len(self.layers) else None
+            xp = ops.planes_of(src, want_f16=first is not None and first.compute_mode == "fp32"
+                               and "qkv" in first.two_pass_sites and src.shape[-1] == 256)
             if row_limit is not None:
                 row_limit = (row_limit[0], row_limit[1], {})  # one tile list per kernel family for the whole stack
             for mod in self.layers:

@@ -134,6 +134,12 @@ class ConformerEncoderLayer(nn.Module):
     # traffic); "x3" = q, k, v and P as bf16 hi/lo planes, three passes per product (~1.4e-5).
     attention_operands = "f16"
     wide_flash_attention = True   # head_dim 256 / 384: lfs2_attention_tc_wide instead of the GEMM-decomposed attention
+    # GEMM sites of compute mode "fp32" (fused d = 256 block) that run the 2-pass recipe: the activation operand as ONE
+    # fp16 plane against the bf16 hi/lo weight planes (a.w_hi + a.w_lo, two thirds of the tensor work of the 3-pass
+    # product).  "qkv": its results are rounded to fp16 for the attention anyway; "ffn": both GEMMs of the fused FFN.
+    # Per-site mel cost in tools/precision_emulation.py (all three: ~1.7e-4 against the 1e-3 budget; the out-projection
+    # alone would add 1.6e-4 and stays 3-pass).  () = every GEMM 3-pass.
+    two_pass_sites = ("qkv", "ffn")
 
     # -- weight repacks -------------------------------------------------------------------
     def _build_pack_tc(self):
@@ -231,9 +237,11 @@ class ConformerEncoderLayer(nn.Module):
             raise NotImplementedError("row-limited FFTBlock needs d = 256, head_dim 128 and the fused depthwise FFN")
         if d != 256:
             return self._forward_tc_unfused_ln(xp, kpm, npass)
+        two = self.two_pass_sites if npass == 3 else ()
         if d // self.nhead == 128:
             f16 = self.compute_mode == "fp32" and self.attention_operands == "f16"
-            qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="f16" if f16 else "planes", npass=npass,
+            qkv_pass = 2 if (f16 and "qkv" in two and xp.h is not None) else npass
+            qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="f16" if f16 else "planes", npass=qkv_pass,
                               tag="qkv_gemm", row_limit=row_limit)
             _, ctx = ops.attention_tc(qkv, kpm, self.nhead, npass=npass, row_limit=row_limit)
         else:
@@ -242,12 +250,16 @@ class ConformerEncoderLayer(nn.Module):
                           beta=self.norm1.bias, eps=self.eps, out="planes", npass=npass, tag="out_proj_ln_gemm",
                           row_limit=row_limit)
         if self.depthwise:
-            up = ops.dwconv1d_planes(x1p, p["dw_wt"], self.conv1[0].bias, row_limit=row_limit)
             fsz = w["pw1"].shape[0]
             if self.fused_ffn and fsz % 256 == 0 and fsz <= 2048:
                 # FFN-1 -> ReLU -> FFN-2 -> + x1 -> LayerNorm in one kernel, the F-wide intermediate in tensor memory
+                ffn_pass = 2 if "ffn" in two else npass
+                up = ops.dwconv1d_planes(x1p, p["dw_wt"], self.conv1[0].bias, row_limit=row_limit,
+                                         out="f16" if ffn_pass == 2 else "planes")
                 return ops.ffn_fused_tc(up, w["pw1"], self.conv1[1].bias, w["w_eff"], p["b_eff"], x1p,
-                                        self.norm2.weight, self.norm2.bias, self.eps, npass=npass, row_limit=row_limit)
+                                        self.norm2.weight, self.norm2.bias, self.eps, npass=ffn_pass, row_limit=row_limit,
+                                        want_f16="qkv" in two)
+            up = ops.dwconv1d_planes(x1p, p["dw_wt"], self.conv1[0].bias, row_limit=row_limit)
             vp = ops.gemm_tc(up, w["pw1"], self.conv1[1].bias, relu=True, out="planes", npass=npass, tag="ffn1_gemm")
             w2, b2, taps2 = w["w_eff"], p["b_eff"], 1
         else:

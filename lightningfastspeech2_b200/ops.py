@@ -292,12 +292,14 @@ def length_regulate(x, durations, max_length, scan=None, frames=None, pad_to_mul
 # ---------------------------------------------------------------------------------------------
 # tensor-core path: bf16 hi/lo planes + tcgen05 GEMM with fused epilogues
 class Planes:
-    """bf16 hi/lo planes of an fp32 tensor (x = hi + lo): the operand format of lfs2_gemm_tc."""
+    """bf16 hi/lo planes of an fp32 tensor (x = hi + lo): the operand format of lfs2_gemm_tc.
+    A single 16-bit plane travels as Planes(hi = fp16 / bf16 tensor, lo = None).  `h` (optional): the same values as ONE
+    fp16 plane next to the hi/lo pair -- the activation operand of the 2-pass GEMM recipe (npass = 2)."""
 
-    __slots__ = ("hi", "lo")
+    __slots__ = ("hi", "lo", "h")
 
-    def __init__(self, hi, lo):
-        self.hi, self.lo = hi, lo
+    def __init__(self, hi, lo, h=None):
+        self.hi, self.lo, self.h = hi, lo, h
 
     @property
     def shape(self):
@@ -326,9 +328,13 @@ def drop_planes(x):
         x._lfs2_planes = None
 
 
-def planes_of(x):
+def planes_of(x, want_f16=False):
+    """the Planes of fp32 tensor x (remembered ones if a kernel already produced them); want_f16: with the fp16 plane
+    (Planes.h) the 2-pass GEMM recipe reads"""
     p = getattr(x, "_lfs2_planes", None)
-    return p if p is not None else split_bf16(x.contiguous())
+    if p is not None and (not want_f16 or p.h is not None):
+        return p
+    return split_bf16(x.contiguous(), want_f16=want_f16)
 
 
 def _limited_fraction(row_limit, t):
@@ -358,7 +364,8 @@ def zero_masked_rows_(x, mask):
 
 
 def dwconv1d_planes(x, wt, bias, out="planes", row_limit=None):
-    """depthwise conv, x (B,T,d) fp32 tensor or Planes, wt (ksize,d) -> Planes (or fp32 if out == "f32").
+    """depthwise conv, x (B,T,d) fp32 tensor or Planes, wt (ksize,d) -> Planes (fp32 if out == "f32"; ONE fp16 plane,
+    Planes(hi = fp16, lo = None), if out == "f16").
     row_limit = (lengths int32 (B), extra): 128-row groups starting at or after lengths[b] + extra are skipped."""
     _chk(wt, torch.float32, "dwconv weight", 2)
     if isinstance(x, Planes):
@@ -370,12 +377,13 @@ def dwconv1d_planes(x, wt, bias, out="planes", row_limit=None):
     b, t, d = shape
     of = torch.empty(shape, device=dev, dtype=torch.float32) if out == "f32" else None
     po = _empty_planes(shape, dev) if out == "planes" else None
+    ph = torch.empty(shape, device=dev, dtype=torch.float16) if out == "f16" else None  # ONE fp16 plane (2-pass GEMMs)
     lim, extra = (row_limit[0], row_limit[1]) if row_limit is not None else (None, 0)
     frac = _limited_fraction(row_limit, t)
-    _launch("lfs2_dwconv1d_planes_limited", _p(xf), _p(xh), _p(xl), _p(wt), _p(bias), _p(of), _p(po.hi if po else None),
-            _p(po.lo if po else None), b, t, d, wt.shape[0], _p(lim), int(extra), _s(), tag="lfs2_dwconv1d",
-            flops=2.0 * b * t * d * wt.shape[0] * frac, nbytes=8.0 * b * t * d * frac)
-    return of if out == "f32" else po
+    _launch("lfs2_dwconv1d_planes_ex", _p(xf), _p(xh), _p(xl), _p(wt), _p(bias), _p(of), _p(po.hi if po else None),
+            _p(po.lo if po else None), _p(ph), b, t, d, wt.shape[0], _p(lim), int(extra), _s(), tag="lfs2_dwconv1d",
+            flops=2.0 * b * t * d * wt.shape[0] * frac, nbytes=(6.0 if out == "f16" else 8.0) * b * t * d * frac)
+    return of if out == "f32" else (Planes(ph, None) if out == "f16" else po)
 
 
 def merge_planes(p):
@@ -386,10 +394,13 @@ def merge_planes(p):
     return attach_planes(out, p)
 
 
-def split_bf16(x):
+def split_bf16(x, want_f16=False):
     _chk(x, torch.float32, "split_bf16 input")
     pl = _empty_planes(x.shape, x.device)
-    _launch("lfs2_split_bf16", _p(x), _p(pl.hi), _p(pl.lo), x.numel(), _s(), nbytes=8.0 * x.numel())
+    if want_f16:
+        pl.h = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    _launch("lfs2_split_bf16_ex", _p(x), _p(pl.hi), _p(pl.lo), _p(pl.h), x.numel(), _s(), tag="lfs2_split_bf16",
+            nbytes=(10.0 if want_f16 else 8.0) * x.numel())
     return pl
 
 
@@ -414,7 +425,9 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
     operand of the single-pass fp16 attention), "bf16" -> Planes(hi = ONE bf16 tensor, lo = None: a result that only
     feeds npass = 1 products); shaped like a with last dim n.
     dilation: tap spacing (dilated Conv1d); leaky_slope: leaky ReLU instead of ReLU; row_mask (B,T) bool: rows written
-    as zeros (PAD frames of a ragged batch)."""
+    as zeros (PAD frames of a ragged batch).
+    npass = 3: hi.hi + lo.hi + hi.lo; 1: hi.hi; 2: a as ONE fp16 plane against the bf16 hi/lo weight planes, a.w_hi +
+    a.w_lo (no LayerNorm / residual epilogue in this recipe)."""
     if not isinstance(a, Planes) or not isinstance(w, Planes):
         raise TypeError("gemm_tc: operands must be Planes (see split_bf16)")
     if out not in OUT_KINDS:
@@ -429,9 +442,17 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
         if a.hi.dim() != 3:
             raise ValueError("gemm_tc: conv mode needs a (B,T,d) operand")
         batch, t = a.shape[0], a.shape[1]
-    for x_ in (a.hi, a.lo, w.hi, w.lo):
-        if x_ is not None or npass == 3:  # (single-plane operands: Planes(hi, None) are fine for npass = 1)
-            _chk(x_, torch.bfloat16, "gemm_tc operand plane")
+    if npass == 2:  # the activation operand of the 2-pass recipe: ONE fp16 plane (a Planes' .h, or Planes(fp16, None))
+        if a.hi.dtype != torch.float16:
+            if a.h is None:
+                raise ValueError("gemm_tc: npass = 2 needs the fp16 plane of a (Planes.h or Planes(fp16, None))")
+            a = Planes(a.h, None)
+        _chk(a.hi, torch.float16, "gemm_tc: a of the 2-pass recipe")
+        _chk(w.hi, torch.bfloat16, "gemm_tc operand plane"); _chk(w.lo, torch.bfloat16, "gemm_tc operand plane")
+    else:
+        for x_ in (a.hi, a.lo, w.hi, w.lo):
+            if x_ is not None or npass == 3:  # (single-plane operands: Planes(hi, None) are fine for npass = 1)
+                _chk(x_, torch.bfloat16, "gemm_tc operand plane")
     out_shape = tuple(a.shape[:-1]) + (n,)
     dev = a.hi.device
     # an fp32 result of a row-limited launch is a user-visible tensor: the rows of skipped tiles read as zeros
@@ -472,7 +493,8 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
             _p(of if of is not None else po.hi), _p(po.lo if out == "planes" else None), OUT_KINDS[out], npass, _p(lim),
             int(extra), _p(ws), _p(row_mask), _s(), tag=tag or f"gemm_tc_n{n}_k{taps * d}",
             flops=2.0 * m * n * taps * d, passes=npass,
-            nbytes=4.0 * m * d + 4.0 * n * taps * d + out_bytes * m * n + (4.0 * m * n if residual is not None else 0.0))
+            nbytes=(2.0 if npass == 2 else 4.0) * m * d + 4.0 * n * taps * d + out_bytes * m * n
+            + (4.0 * m * n if residual is not None else 0.0))
     return of if out == "f32" else po
 
 
@@ -522,19 +544,29 @@ def predictor_layer_tc(a, w, bias, gamma, beta, eps=LN_EPS, npass=3, next_dw=Non
     return po if po is not None else hout
 
 
-def ffn_fused_tc(u, w1, b1, w2, b2, residual, gamma, beta, eps=LN_EPS, npass=3, row_limit=None):
+def ffn_fused_tc(u, w1, b1, w2, b2, residual, gamma, beta, eps=LN_EPS, npass=3, row_limit=None, want_f16=False):
     """LayerNorm(residual + relu(u . w1^T + b1) . w2^T + b2) in one kernel, the F-wide intermediate on chip.
     u, residual: Planes (..., 256); w1 Planes (F, 256); w2 Planes (256, F) -> Planes (..., 256).
+    npass = 2: u is ONE fp16 plane (Planes(hi = fp16, lo = None)), products a.w_hi + a.w_lo.  want_f16: the result also
+    carries its fp16 plane (Planes.h) for the next block's 2-pass QKV GEMM.
     row_limit = (lengths int32 (B), extra[, cache dict]) on (B,T,256) operands: 128-row tiles that hold no row
     t < roundup128(lengths[b] + extra) of any utterance are skipped (their output rows stay unwritten)."""
     d = u.shape[-1]
     f = w1.shape[0]
     if d != 256 or tuple(w1.shape) != (f, 256) or tuple(w2.shape) != (256, f) or tuple(residual.shape) != tuple(u.shape):
         raise ValueError("ffn_fused_tc: shapes must be u/residual (..., 256), w1 (F, 256), w2 (256, F)")
-    for x_ in (u.hi, u.lo, w1.hi, w1.lo, w2.hi, w2.lo, residual.hi, residual.lo):
+    if npass == 2:
+        _chk(u.hi, torch.float16, "ffn_fused_tc: u of the 2-pass recipe (one fp16 plane)")
+    else:
+        _chk(u.hi, torch.bfloat16, "ffn_fused_tc operand plane")
+        if npass == 3:
+            _chk(u.lo, torch.bfloat16, "ffn_fused_tc operand plane")
+    for x_ in (w1.hi, w1.lo, w2.hi, w2.lo, residual.hi, residual.lo):
         _chk(x_, torch.bfloat16, "ffn_fused_tc operand plane")
     m = u.hi.numel() // d
     out = _empty_planes(tuple(u.shape), u.hi.device)
+    if want_f16:
+        out.h = torch.empty(tuple(u.shape), device=u.hi.device, dtype=torch.float16)
     ident = _identity_planes(d, u.hi.device)
     if row_limit is None:
         batch, t, lim, extra, ws = 1, m, None, 0, None
@@ -553,10 +585,11 @@ def ffn_fused_tc(u, w1, b1, w2, b2, residual, gamma, beta, eps=LN_EPS, npass=3, 
             if cache is not None:
                 cache[key] = ws
         m = m * _limited_fraction(row_limit, t)
-    _launch("lfs2_ffn_fused_tc_limited", _p(u.hi), _p(u.lo), batch, t, _p(w1.hi), _p(w1.lo), f, _p(b1), _p(w2.hi),
-            _p(w2.lo), _p(b2), _p(residual.hi), _p(residual.lo), _p(ident), _p(gamma), _p(beta), float(eps), _p(out.hi),
-            _p(out.lo), npass, _p(lim), int(extra), _p(ws), _s(), tag="ffn_fused", flops=4.0 * m * d * f, passes=npass,
-            nbytes=4.0 * m * d * 3 + 8.0 * d * f)
+    _launch("lfs2_ffn_fused_tc_ex", _p(u.hi), _p(u.lo if npass == 3 else None), batch, t, _p(w1.hi), _p(w1.lo), f, _p(b1),
+            _p(w2.hi), _p(w2.lo), _p(b2), _p(residual.hi), _p(residual.lo), _p(ident), _p(gamma), _p(beta), float(eps),
+            _p(out.hi), _p(out.lo), _p(out.h), npass, _p(lim), int(extra), _p(ws), _s(), tag="ffn_fused",
+            flops=4.0 * m * d * f, passes=npass,
+            nbytes=m * d * ((2.0 if npass == 2 else 4.0) + 8.0 + (2.0 if want_f16 else 0.0)) + 8.0 * d * f)
     return out
 
 

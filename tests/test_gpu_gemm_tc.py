@@ -242,3 +242,84 @@ def test_row_mask_writes_zero_rows():
     full = full.view(bsz, t, n)
     assert torch.equal(out[~mask], full[~mask]) and float(out[mask].abs().max()) == 0.0
     assert float(pl.hi[mask].abs().max()) == 0.0 and float(pl.lo[mask].abs().max()) == 0.0
+
+
+# ---- npass = 2: ONE fp16 activation plane against the bf16 hi/lo weight planes (a.w_hi + a.w_lo) -------------------
+def _w_planes_value(w):
+    """what the hi/lo weight planes hold (bf16 hi + bf16 lo), fp64"""
+    hi = w.to(torch.bfloat16)
+    return hi.double() + (w - hi.float()).to(torch.bfloat16).double()
+
+
+@pytest.mark.parametrize("m,n,k,taps", [(300, 768, 256, 1), (129, 80, 256, 1), (20000, 768, 256, 1), (260, 256, 64, 3)])
+@pytest.mark.parametrize("out", ["f32", "f16", "planes"])
+def test_two_pass_fp16_activation_plane(m, n, k, taps, out):
+    """the mixed-format product (A fp16, B bf16) is exact in its operands: result == fp16(a) . (w_hi + w_lo) to the
+    fp32 accumulator's rounding; against the un-rounded product the error is the fp16 rounding of a (2^-12 relative)"""
+    a, w, b = rnd(2, m // 2, k, seed=61), rnd(n, taps * k, seed=62, scale=(taps * k) ** -0.5), rnd(n, seed=63, scale=0.1)
+    a16 = a.half()
+    wv = _w_planes_value(w)
+    x = a16.double()
+    if taps == 1:
+        ref = x @ wv.t() + b.double()
+    else:
+        ref = F.conv1d(x.transpose(1, 2), wv.view(n, taps, k).permute(0, 2, 1).contiguous(), b.double(),
+                       padding=(taps - 1) // 2).transpose(1, 2)
+    ap = ops.split_bf16(a.to(DEV), want_f16=True)
+    assert torch.equal(ap.h.cpu(), a16)
+    got = ops.gemm_tc(ap, ops.split_bf16(w.to(DEV)), b.to(DEV), taps=taps, npass=2, out=out)
+    if out == "f32":
+        assert (got.double().cpu() - ref).abs().max() < 3e-6 * max(1.0, float(ref.abs().max()))
+    elif out == "f16":
+        assert got.lo is None and got.hi.dtype == torch.float16
+        assert ((got.hi.double().cpu() - ref).abs() <= 2.0 ** -11 * ref.abs() + 1e-5).all()
+    else:
+        assert (got.float().double().cpu() - ref).abs().max() < 2.0 ** -15 * max(1.0, float(ref.abs().max()))
+    exact = F.linear(a.double(), w.double(), b.double()) if taps == 1 else None
+    if exact is not None and out == "f32":
+        assert (got.double().cpu() - exact).abs().max() < 1.5e-3   # 11-bit activations, K = 256: ~2^-12 * sqrt(K) * |a||w|
+
+
+def test_two_pass_rejects_layernorm_and_missing_plane():
+    a, w = rnd(128, 256, seed=64), rnd(256, 256, seed=65, scale=1 / 16)
+    ap, wp = ops.split_bf16(a.to(DEV), want_f16=True), ops.split_bf16(w.to(DEV))
+    with pytest.raises(Exception):
+        ops.gemm_tc(ap, wp, None, gamma=torch.ones(256, device=DEV), beta=torch.zeros(256, device=DEV), out="planes", npass=2)
+    with pytest.raises(ValueError):
+        ops.gemm_tc(ops.split_bf16(a.to(DEV)), wp, None, npass=2)
+
+
+@pytest.mark.parametrize("m,f", [(128, 256), (1000, 1024), (40000, 1024), (333, 2048)])
+def test_ffn_fused_tc_two_pass(m, f):
+    """npass = 2: u as one fp16 plane, the intermediate packed as fp16, weights as hi/lo planes -- against an fp64
+    restatement that rounds exactly those operands (tight), and against the un-rounded fp64 result (the recipe's cost);
+    the fp16 output plane is the rounded hi + lo result"""
+    g = torch.Generator().manual_seed(m + f + 1)
+    d = 256
+    u = torch.randn(m, d, generator=g)
+    res = torch.randn(m, d, generator=g)
+    w1 = torch.randn(f, d, generator=g) / d ** 0.5
+    w2 = torch.randn(d, f, generator=g) / f ** 0.5
+    b1, b2 = torch.randn(f, generator=g) * 0.1, torch.randn(d, generator=g) * 0.1
+    gam, bet = 1 + 0.1 * torch.randn(d, generator=g), 0.1 * torch.randn(d, generator=g)
+    ln = lambda z: F.layer_norm(z, (d,), gam.double(), bet.double(), 1e-5)
+    exact = ln(res.double() + torch.relu(u.double() @ w1.double().t() + b1.double()) @ w2.double().t() + b2.double())
+    v = torch.relu(u.half().double() @ _w_planes_value(w1).t() + b1.double())
+    emu = ln(res.double() + v.float().half().double() @ _w_planes_value(w2).t() + b2.double())
+    sp = lambda t: ops.split_bf16(t.to(DEV).contiguous())
+    wt1, bias1 = torch.zeros(1, d, device=DEV), torch.zeros(d, device=DEV)
+    wt1[0] = 1.0
+    up = ops.dwconv1d_planes(u.to(DEV).view(1, m, d), wt1, bias1, out="f16")     # identity depthwise conv -> fp16 plane of u
+    assert up.lo is None and torch.equal(up.hi.view(m, d).cpu(), u.half())
+    up = ops.Planes(up.hi.view(m, d), None)
+    out = ops.ffn_fused_tc(up, sp(w1), b1.to(DEV), sp(w2), b2.to(DEV), sp(res), gam.to(DEV), bet.to(DEV), 1e-5, npass=2,
+                           want_f16=True)
+    got = out.float().cpu().double()
+    e_emu, e_exact = (got - emu).abs().max().item(), (got - exact).abs().max().item()
+    print(f"ffn_fused two-pass m={m} f={f}: vs operand-rounded fp64 {e_emu:.3e}, vs exact {e_exact:.3e}")
+    # v sits at fp16 rounding boundaries in a few places (fp32 accumulation order): allow a handful of 1-ulp flips of v
+    assert e_emu < 2e-4 and e_exact < 3e-3
+    assert torch.equal(out.h.cpu(), out.float().cpu().half())
+    # the 3-pass kernel with the same residual path (32 x 32 identity block) stays at fp32 parity
+    o3 = ops.ffn_fused_tc(sp(u), sp(w1), b1.to(DEV), sp(w2), b2.to(DEV), sp(res), gam.to(DEV), bet.to(DEV), 1e-5, npass=3)
+    assert (o3.float().cpu().double() - exact).abs().max() < 5e-5
