@@ -193,8 +193,8 @@ LFS2_API int lfs2_gemm_tc_limited(const void* a_hi, const void* a_lo, int batch,
  *   out_kind   LFS2_OUT_PLANES: out0/out1 = bf16 hi/lo planes; LFS2_OUT_F32: out0 = fp32; LFS2_OUT_F16: out0 = ONE
  *              fp16 plane (saturating conversion), the operand format of lfs2_attention_tc_ex(..., fp16)
  *   row_mask   NULL or (batch, t) bytes: rows with a non-zero byte are written as zeros (PAD frames of a ragged batch)
- *   npass      3: hi.hi + lo.hi + hi.lo; 1: hi.hi; 2: a_hi is ONE fp16 plane of a (a_lo unused) against the bf16 hi/lo
- *              weight planes, a.w_hi + a.w_lo -- 11 significant bits on the activation side, full weights, two thirds
+ *   npass      3: hi.hi + lo.hi + hi.lo; 1: hi.hi; 2: a_hi is ONE fp16 plane of a (a_lo unused) against fp16 hi/lo
+ *              weight planes (lfs2_split_f16), a.w_hi + a.w_lo -- 11 significant bits on the activation side, full weights, two thirds
  *              of the tensor work (no LayerNorm / residual epilogue in this recipe)
  *   column tiles of 256 / 128 / 64 outputs (n % 16 == 0). */
 #define LFS2_OUT_PLANES 0
@@ -260,8 +260,8 @@ LFS2_API int lfs2_ffn_fused_tc_limited(const void* u_hi, const void* u_lo, int b
                                        const float* b2, const void* res_hi, const void* res_lo, const void* ident_hi,
                                        const float* gamma, const float* beta, float eps, void* out_hi, void* out_lo,
                                        int npass, const int* row_limit, int limit_extra, void* workspace, void* stream);
-/* Same with the 2-pass recipe and an extra output.  npass = 2: u_hi is ONE fp16 plane of u (u_lo unused) and the
- * intermediate is packed as fp16: every product is a.w_hi + a.w_lo (11 significant bits on the activation side, full
+/* Same with the 2-pass recipe and an extra output.  npass = 2: u_hi is ONE fp16 plane of u (u_lo unused), w1 / w2 are
+ * fp16 hi/lo planes (lfs2_split_f16) and the intermediate is packed as fp16: every product is a.w_hi + a.w_lo (11 significant bits on the activation side, full
  * weights; two thirds of the tensor work of npass = 3).  out_f16 (or NULL): the output rows also as one fp16 plane, the
  * activation operand of the next block's 2-pass QKV GEMM (lfs2_gemm_tc_ex, npass = 2). */
 LFS2_API int lfs2_ffn_fused_tc_ex(const void* u_hi, const void* u_lo, int batch, int t, const void* w1_hi,
@@ -315,6 +315,9 @@ LFS2_API int lfs2_merge_planes(const void* hi, const void* lo, float* out, long 
 
 /* hi = bf16(x), lo = bf16(x - hi) for n fp32 values (n % 4 == 0) */
 LFS2_API int lfs2_split_bf16(const float* x, void* hi, void* lo, long long n, void* stream);
+/* hi = fp16(x) (saturating), lo = fp16(x - hi): the WEIGHT planes of the 2-pass recipe (npass = 2), whose activation
+ * operand is one fp16 plane -- a tensor-core instruction cannot mix an fp16 A with a bf16 B */
+LFS2_API int lfs2_split_f16(const float* x, void* hi, void* lo, long long n, void* stream);
 /* same, and (f16 != NULL) the values also as ONE fp16 plane (saturating): the activation operand of npass = 2 GEMMs */
 LFS2_API int lfs2_split_bf16_ex(const float* x, void* hi, void* lo, void* f16, long long n, void* stream);
 

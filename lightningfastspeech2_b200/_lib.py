@@ -58,6 +58,7 @@ SIGNATURES = {
     "lfs2_attention_tc": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp],
     "lfs2_split_bf16": [_vp, _vp, _vp, ctypes.c_longlong, _vp],
     "lfs2_split_bf16_ex": [_vp, _vp, _vp, _vp, ctypes.c_longlong, _vp],
+    "lfs2_split_f16": [_vp, _vp, _vp, ctypes.c_longlong, _vp],
     "lfs2_gemm_tc2": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _ll, _ll, _i, _i, _i, _i, _i, _i, _i, _vp],
     "lfs2_attn_softmax_planes": [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _vp],
     "lfs2_attn_softmax_planes_drop": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _f, ctypes.c_ulonglong,

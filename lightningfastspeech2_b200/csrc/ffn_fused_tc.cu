@@ -19,8 +19,12 @@
 // overwrites the columns G2 reads (same pattern as S/P in attention_tc.cu).
 // NPASS = 3: hi.hi + lo.hi + hi.lo for every product; NPASS = 1: hi.hi only (bf16 mode);
 // NPASS = 2: the activation operand is ONE fp16 value (u arrives as an fp16 plane, v is packed as fp16 in tensor
-// memory) against the bf16 hi/lo weight planes: a.w_hi + a.w_lo -- 11 significant bits on the activation side, full
-// weights; two thirds of the tensor work (tools/precision_emulation.py has the mel error of this recipe per site).
+// memory) against fp16 hi/lo weight planes (lfs2_split_f16; one instruction cannot mix an fp16 A with a bf16 B):
+// a.w_hi + a.w_lo -- 11 significant bits on the activation side, full weights; two thirds of the tensor work
+// (tools/precision_emulation.py has the mel error of this recipe per site).
+// MC: clusters of two CTAs (the kernel is bound by the L2 -> SM stream of the weights, ~2 MB per 128-row tile against
+// ~0.6 MB of activations): the pair works on two row tiles at once, each CTA fetches HALF of every weight slab and
+// multicasts it into both CTAs' shared memory -- half the weight traffic per row (same scheme as gemm_tc.cu).
 // Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue (thread = row, two warps per quadrant).
 #include "tc_common.cuh"
 
@@ -35,6 +39,7 @@ constexpr int kFThreads = 320;
 constexpr int kFStageChunk = kFM * 32 * 4;  // 16 KB staging chunk (hi | lo planes of 128 x 32)
 
 struct FfnParams {
+  int m_pad;        // first row past every tile (an out-of-range tile of an odd pair starts here: TMA fills zeros / drops)
   int m;            // rows
   int f;            // hidden width (multiple of 256)
   int total_tiles;
@@ -111,7 +116,7 @@ __device__ __forceinline__ void f_tmem_st16(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
-template <int NPASS>
+template <int NPASS, bool MC>
 __global__ void __launch_bounds__(kFThreads, 1)
 ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_constant__ CUtensorMap map_u_lo,
                     const __grid_constant__ CUtensorMap map_w1_hi, const __grid_constant__ CUtensorMap map_w1_lo,
@@ -133,6 +138,15 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = p.f / kFC;
   const int ntiles = tile_count(p);
+  // work items: MC -> the pair (cluster) walks tile pairs (2i, 2i + 1), this CTA takes the one of its rank
+  const int rank = MC ? (int)cluster_ctarank() : 0;
+  const int w_first = MC ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int w_stride = MC ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int w_count = MC ? (ntiles + 1) >> 1 : ntiles;
+  auto row0_of = [&](int wi) {
+    const int ti = MC ? 2 * wi + rank : wi;
+    return ti < ntiles ? tile_at(p, ti) * kFM : p.m_pad;
+  };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&map_u_hi);
@@ -141,7 +155,7 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
     prefetch_tmap(&map_o_hi);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], MC ? 2 : 1);  // MC: free when BOTH CTAs' MMAs have read the slot (the peer writes into it too)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&acc1_full[i], 1);
@@ -165,6 +179,7 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
   }
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into this CTA
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const uint32_t t_acc1 = tmem_base, t_acc2 = tmem_base + 256;  // acc1 buffer b: columns [128 b, 128 b + 128)
@@ -180,19 +195,25 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
           phase ^= 1;
         }
       };
-      if ((int)blockIdx.x < ntiles) {  // the identity block: once per CTA that has work
+      if (w_first < w_count) {  // the identity block: once per CTA that has work
         mbar_expect_tx(&ident_bar, L::kI32);
         tma_load_3d(smem + L::kOffI32, &map_ident, &ident_bar, 0, 0, 0);
       }
+      // MC: the weight maps have half-height boxes; this CTA fetches its half of a slab and multicasts it to the same
+      // place in both CTAs (every full barrier still sees a whole slab's bytes)
+      auto load_w = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int c0, int row, int rows, int plane) {
+        if (MC) tma_load_3d_mc(dst + rank * (plane / 2), map, bar, c0, row + rank * (rows / 2), 0, (uint16_t)3);
+        else tma_load_3d(dst, map, bar, c0, row, 0);
+      };
       auto load_g1 = [&](int r0, int c) {  // u slab + W11 slab, 8 slabs
         for (int ks = 0; ks < kSlabs; ++ks) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * L::kStage;
           mbar_expect_tx(&full_bar[stage], (NPASS + 1) * L::kAPlane);
           tma_load_3d(st, &map_u_hi, &full_bar[stage], ks * kFK, r0, 0);
-          tma_load_3d(st + L::kG1W1Hi, &map_w1_hi, &full_bar[stage], ks * kFK, c * kFC, 0);
+          load_w(st + L::kG1W1Hi, &map_w1_hi, &full_bar[stage], ks * kFK, c * kFC, kFC, L::kAPlane);
           if (NPASS == 3) tma_load_3d(st + L::kG1ALo, &map_u_lo, &full_bar[stage], ks * kFK, r0, 0);
-          if (NPASS >= 2) tma_load_3d(st + L::kG1W1Lo, &map_w1_lo, &full_bar[stage], ks * kFK, c * kFC, 0);
+          if (NPASS >= 2) load_w(st + L::kG1W1Lo, &map_w1_lo, &full_bar[stage], ks * kFK, c * kFC, kFC, L::kAPlane);
           next();
         }
       };
@@ -201,13 +222,13 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * L::kStage;
           mbar_expect_tx(&full_bar[stage], (NPASS >= 2 ? 2 : 1) * L::kW2Plane);
-          tma_load_3d(st, &map_w2_hi, &full_bar[stage], c * kFC + ks * kFK, 0, 0);
-          if (NPASS >= 2) tma_load_3d(st + L::kG2Lo, &map_w2_lo, &full_bar[stage], c * kFC + ks * kFK, 0, 0);
+          load_w(st, &map_w2_hi, &full_bar[stage], c * kFC + ks * kFK, 0, kFD, L::kW2Plane);
+          if (NPASS >= 2) load_w(st + L::kG2Lo, &map_w2_lo, &full_bar[stage], c * kFC + ks * kFK, 0, kFD, L::kW2Plane);
           next();
         }
       };
-      for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x) {
-        const int r0 = tile_at(p, ti) * kFM;
+      for (int wi = w_first; wi < w_count; wi += w_stride) {
+        const int r0 = row0_of(wi);
         load_g1(r0, 0);
         for (int c = 0; c < nchunks; ++c) {  // same order as the MMA warp: G1(c+1) is issued before G2(c)
           if (c + 1 < nchunks) load_g1(r0, c + 1);
@@ -225,9 +246,9 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    constexpr int kAFmt = NPASS == 2 ? kFmtF16 : kFmtBF16;                     // activation operand: fp16 in the 2-pass recipe
-    constexpr uint32_t idesc1 = make_idesc_ab(kAFmt, kFmtBF16, kFM, kFC);      // G1: M128 x N128
-    constexpr uint32_t idesc2 = make_idesc_ab(kAFmt, kFmtBF16, kFM, kFD);      // G2: M128 x N256
+    constexpr int kFmt = NPASS == 2 ? kFmtF16 : kFmtBF16;                      // 2-pass recipe: fp16 operands on both sides
+    constexpr uint32_t idesc1 = make_idesc(kFmt, kFM, kFC, 0, 0);              // G1: M128 x N128
+    constexpr uint32_t idesc2 = make_idesc(kFmt, kFM, kFD, 0, 0);              // G2: M128 x N256
     constexpr uint32_t idesc_r = make_idesc(kFmtBF16, kFM, 32, 0, 0);          // residual: M128 x N32 per 32-column slab
     const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 512, kSwizzle64);
     const uint64_t d_i32 = make_smem_desc(smem_u32(smem + L::kOffI32), 16, 512, kSwizzle64);
@@ -240,6 +261,10 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
         stage = 0;
         phase ^= 1;
       }
+    };
+    auto release = [&](uint64_t* bar) {  // smem slot reusable once these MMAs retire (MC: in both CTAs, either may refill it)
+      if (MC) umma_commit_mc(bar, (uint16_t)3);
+      else umma_commit(bar);
     };
     auto issue_g1 = [&](uint32_t ctr) {  // acc1[ctr & 1] = u . W11[chunk]^T
       const uint32_t acc = t_acc1 + 128 * (ctr & 1);
@@ -262,14 +287,14 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
             umma_f16_c<true>(acc, a_hi, w_lo, idesc1);
             umma_f16_c<true>(acc, desc_advance(a_hi, 32), desc_advance(w_lo, 32), idesc1);
           }
-          umma_commit(&empty_bar[stage]);
+          release(&empty_bar[stage]);
           if (ks + 1 == kSlabs) umma_commit(&acc1_full[ctr & 1]);
         }
         __syncwarp();
         next();
       }
     };
-    for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
+    for (int wi = w_first; wi < w_count; wi += w_stride, ++it) {
       issue_g1(chunk_ctr);
       for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
         // G1 of the next chunk goes first: it runs on the tensor pipe while the epilogue warps convert chunk c.
@@ -299,7 +324,7 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
               umma_f16_ts_c<true>(t_acc2, v_hi, w_lo, idesc2);
               umma_f16_ts_c<true>(t_acc2, v_hi + 8, desc_advance(w_lo, 32), idesc2);
             }
-            umma_commit(&empty_bar[stage]);
+            release(&empty_bar[stage]);
           }
           __syncwarp();
           next();
@@ -318,7 +343,7 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
           umma_f16_c<true>(acc, desc_advance(a_hi, 32), desc_advance(d_i32, 32), idesc_r);
           umma_f16_c<true>(acc, a_lo, d_i32, idesc_r);
           umma_f16_c<true>(acc, desc_advance(a_lo, 32), desc_advance(d_i32, 32), idesc_r);
-          umma_commit(&empty_bar[stage]);
+          release(&empty_bar[stage]);
           if (ks + 1 == kSlabs) umma_commit(&acc2_full);
         }
         __syncwarp();
@@ -339,8 +364,8 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
     uint32_t chunk_ctr = 0, st_ctr = 0;
     int it = 0;
     float v[32];
-    for (int ti = blockIdx.x; ti < ntiles; ti += gridDim.x, ++it) {
-      const int r0 = tile_at(p, ti) * kFM;
+    for (int wi = w_first; wi < w_count; wi += w_stride, ++it) {
+      const int r0 = row0_of(wi);
       // ---- E1 per F chunk: acc1 -> relu(acc1 + b1) as bf16 hi/lo pairs, in place ----
       for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
         mbar_wait(&acc1_full[chunk_ctr & 1], (chunk_ctr >> 1) & 1);
@@ -440,16 +465,17 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
 
   tc_fence_before();
   __syncthreads();
+  if (MC) cluster_sync_all();  // the peer may still arrive on this CTA's barriers until it has finished too
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
 }
 
-template <int NPASS>
+template <int NPASS, bool MC>
 static int launch_ffn(const CUtensorMap* m, const FfnParams& p, cudaStream_t s) {
   using L = FfnSmem<NPASS>;
-  auto kern = ffn_fused_tc_kernel<NPASS>;
+  auto kern = ffn_fused_tc_kernel<NPASS, MC>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
@@ -458,8 +484,28 @@ static int launch_ffn(const CUtensorMap* m, const FfnParams& p, cudaStream_t s) 
     }
     configured = true;
   }
-  const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
-  kern<<<grid, kFThreads, L::kTotal, s>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], p);
+  if (!MC) {
+    const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    kern<<<grid, kFThreads, L::kTotal, s>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], p);
+  } else {  // clusters of two CTAs (one per SM): pairs of row tiles share the multicast weight slabs
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kNumSMs & ~1);
+    cfg.blockDim = dim3(kFThreads);
+    cfg.dynamicSmemBytes = L::kTotal;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, kern, m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], p) !=
+        cudaSuccess) {
+      set_error("ffn_fused_tc: cluster launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+      return LFS2_ERR_CUDA;
+    }
+  }
   LFS2_CHECK_LAUNCH("ffn_fused_tc");
   return LFS2_OK;
 }
@@ -513,9 +559,17 @@ extern "C" int lfs2_ffn_fused_tc_ex(const void* u_hi, const void* u_lo, int batc
   LFS2_REQUIRE(aligned16(u_hi) && aligned16(w1_hi) && aligned16(w2_hi) && aligned16(res_hi) && aligned16(res_lo) &&
                    aligned16(out_hi) && aligned16(out_lo) && (!u_lo || aligned16(u_lo)) && aligned16(out_f16),
                LFS2_ERR_INVALID_ARG, "ffn_fused_tc: pointers must be 16-byte aligned");
+  // 2-CTA multicast variant: at least one pair of row tiles per cluster (LFS2_FFN_MULTICAST=0 switches it off: A/B runs)
+  static int mc_on = -1;
+  if (mc_on < 0) {
+    const char* e = getenv("LFS2_FFN_MULTICAST");
+    mc_on = (e && e[0] == '0') ? 0 : 1;
+  }
+  const bool mc = mc_on == 1 && ceil_div(m, kFM) >= 2 * kNumSMs;
+  const uint32_t w1_box = mc ? kFC / 2 : kFC, w2_box = mc ? kFD / 2 : kFD;  // MC: each CTA fetches half a weight slab
   CUtensorMap maps[12];
-  bool ok = make_tmap_3d(&maps[0], u_hi, kFD, m, 1, kFK, kFM, 64) && make_tmap_3d(&maps[2], w1_hi, kFD, f, 1, kFK, kFC, 64) &&
-            make_tmap_3d(&maps[4], w2_hi, f, kFD, 1, kFK, kFD, 64) && make_tmap_3d(&maps[6], res_hi, kFD, m, 1, kFK, kFM, 64) &&
+  bool ok = make_tmap_3d(&maps[0], u_hi, kFD, m, 1, kFK, kFM, 64) && make_tmap_3d(&maps[2], w1_hi, kFD, f, 1, kFK, w1_box, 64) &&
+            make_tmap_3d(&maps[4], w2_hi, f, kFD, 1, kFK, w2_box, 64) && make_tmap_3d(&maps[6], res_hi, kFD, m, 1, kFK, kFM, 64) &&
             make_tmap_3d(&maps[7], res_lo, kFD, m, 1, kFK, kFM, 64) &&
             make_tmap_3d(&maps[8], ident_hi, kFD, kFD, 1, kFK, 32, 64) &&
             make_tmap_3d(&maps[9], out_hi, kFD, m, 1, 32, kFM, 64) && make_tmap_3d(&maps[10], out_lo, kFD, m, 1, 32, kFM, 64);
@@ -525,11 +579,11 @@ extern "C" int lfs2_ffn_fused_tc_ex(const void* u_hi, const void* u_lo, int batc
   maps[11] = maps[9];
   if (npass == 3) ok = ok && make_tmap_3d(&maps[1], u_lo, kFD, m, 1, kFK, kFM, 64);
   if (npass >= 2)
-    ok = ok && make_tmap_3d(&maps[3], w1_lo, kFD, f, 1, kFK, kFC, 64) && make_tmap_3d(&maps[5], w2_lo, f, kFD, 1, kFK, kFD, 64);
+    ok = ok && make_tmap_3d(&maps[3], w1_lo, kFD, f, 1, kFK, w1_box, 64) && make_tmap_3d(&maps[5], w2_lo, f, kFD, 1, kFK, w2_box, 64);
   if (out_f16) ok = ok && make_tmap_3d(&maps[11], out_f16, kFD, m, 1, 32, kFM, 64);
   LFS2_REQUIRE(ok, LFS2_ERR_CUDA, "ffn_fused_tc: cuTensorMapEncodeTiled failed");
   FfnParams p;
-  p.m = m; p.f = f; p.total_tiles = ceil_div(m, kFM);
+  p.m = m; p.f = f; p.total_tiles = ceil_div(m, kFM); p.m_pad = p.total_tiles * kFM;
   p.b1 = b1; p.b2 = b2; p.gamma = gamma; p.beta = beta; p.eps = eps; p.out_f16 = out_f16 != nullptr;
   cudaStream_t s = (cudaStream_t)stream;
   p.tile_list = nullptr;
@@ -545,5 +599,6 @@ extern "C" int lfs2_ffn_fused_tc_ex(const void* u_hi, const void* u_lo, int batc
     LFS2_CHECK_LAUNCH("ffn_tile_list");
     p.tile_list = list;
   }
-  return npass == 3 ? launch_ffn<3>(maps, p, s) : (npass == 2 ? launch_ffn<2>(maps, p, s) : launch_ffn<1>(maps, p, s));
+  if (mc) return npass == 3 ? launch_ffn<3, true>(maps, p, s) : (npass == 2 ? launch_ffn<2, true>(maps, p, s) : launch_ffn<1, true>(maps, p, s));
+  return npass == 3 ? launch_ffn<3, false>(maps, p, s) : (npass == 2 ? launch_ffn<2, false>(maps, p, s) : launch_ffn<1, false>(maps, p, s));
 }

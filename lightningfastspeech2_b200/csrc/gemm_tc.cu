@@ -123,29 +123,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // fetches half of every weight slab and multicasts it into both CTAs' shared memory.  A K = 256 GEMM re-reads its
 // whole weight tile for every 128-row tile (262 KB of the 521 KB a tile moves L2 -> SM in fp32 mode), which is what
 // bounds these kernels; sharing the slab halves that part.
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                               int c2, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                   smem_u32(bar)),
-               "h"(mask)
-               : "memory");
-}
-
 // work items of one CTA: item i -> (utterance b, first row t0, first column n0)
 template <bool MC>
 struct TileWalk {
@@ -307,8 +284,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // ===================== MMA issuer =====================
     // whole warp runs the uniform control flow (descriptors stay in uniform registers), one
     // elected lane issues; per instruction the descriptor is a 64-bit add on a precomputed base
-    // NPASS = 2: the activation operand is ONE fp16 plane against the bf16 hi/lo weight planes (a.w_hi + a.w_lo)
-    constexpr uint32_t idesc = make_idesc_ab(NPASS == 2 ? kFmtF16 : kFmtBF16, kFmtBF16, kBM, N_TILE);
+    // NPASS = 2: the activation operand is ONE fp16 plane against fp16 hi/lo weight planes (a.w_hi + a.w_lo)
+    constexpr uint32_t idesc = make_idesc(NPASS == 2 ? kFmtF16 : kFmtBF16, kBM, N_TILE, 0, 0);
     constexpr uint32_t idesc_r = make_idesc(kFmtBF16, kBM, 32, 0, 0);  // residual: one 32-column block per slab
     const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 512, kSwizzle64);
     const uint64_t d_i32 = make_smem_desc(smem_u32(smem + L::kOffI32), 16, 512, kSwizzle64);
@@ -994,6 +971,24 @@ int lfs2_predictor_layer_tc(const void* a_hi, const void* a_lo, int batch, int t
                     : launch_gemm_tc<256, 1, true, kOutPlanes, false, kEpiDot>(m, p, s);
 }
 
+// x (n) fp32 -> hi/lo fp16 planes: hi = fp16(x) (saturating), lo = fp16(x - hi); hi + lo = x to ~2^-22 |x| (2^-25
+// absolute once lo is subnormal) -- the weight operand of the 2-pass recipe
+__device__ __forceinline__ void split_f16_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = pack_f16_sat(a, b);
+  const __half2 h = *reinterpret_cast<const __half2*>(&hi);
+  lo = pack_f16_sat(a - __low2float(h), b - __high2float(h));
+}
+__global__ void split_f16_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = x[i];
+  uint2 h, l;
+  split_f16_pair(v.x, v.y, h.x, l.x);
+  split_f16_pair(v.z, v.w, h.y, l.y);
+  hi[i] = h;
+  lo[i] = l;
+}
+
 // x (n) fp32 -> hi/lo bf16 planes
 __global__ void split_bf16_kernel(const float4* __restrict__ x, uint2* __restrict__ hi, uint2* __restrict__ lo,
                                   uint2* __restrict__ f16, size_t n4) {
@@ -1012,6 +1007,18 @@ __global__ void split_bf16_kernel(const float4* __restrict__ x, uint2* __restric
 
 int lfs2_split_bf16(const float* x, void* hi, void* lo, long long n, void* stream) {
   return lfs2_split_bf16_ex(x, hi, lo, nullptr, n, stream);
+}
+
+int lfs2_split_f16(const float* x, void* hi, void* lo, long long n, void* stream) {
+  LFS2_REQUIRE(x && hi && lo, LFS2_ERR_INVALID_ARG, "split_f16: null pointer");
+  if (n == 0) return LFS2_OK;
+  LFS2_REQUIRE(n > 0 && n % 4 == 0, LFS2_ERR_UNSUPPORTED, "split_f16: n must be a positive multiple of 4");
+  LFS2_REQUIRE(aligned16(x) && aligned16(hi) && aligned16(lo), LFS2_ERR_INVALID_ARG,
+               "split_f16: pointers must be 16-byte aligned");
+  size_t n4 = (size_t)n / 4;
+  split_f16_kernel<<<ceil_div(n4, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, (uint2*)hi, (uint2*)lo, n4);
+  LFS2_CHECK_LAUNCH("split_f16");
+  return LFS2_OK;
 }
 
 int lfs2_split_bf16_ex(const float* x, void* hi, void* lo, void* f16, long long n, void* stream) {

@@ -158,6 +158,30 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// ------------------------------------------------------------------ 2-CTA clusters: multicast loads / commits
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                               int c2, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+
 // ------------------------------------------------------------------ descriptors
 enum : uint64_t { kSwizzle128 = 2, kSwizzle64 = 4, kSwizzle32 = 6 };
 
@@ -191,11 +215,7 @@ __host__ __device__ constexpr uint32_t make_idesc(int fmt, int m, int n, int a_m
   return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)a_mn_major << 15) |
          ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
-// A and B in different 16-bit formats (K-major both): an fp16 activation plane against bf16 weight planes
-__host__ __device__ constexpr uint32_t make_idesc_ab(int a_fmt, int b_fmt, int m, int n) {
-  return (1u << 4) | ((uint32_t)a_fmt << 7) | ((uint32_t)b_fmt << 10) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(m >> 4) << 24);
-}
+// (A and B must share one format: a kind::f16 instruction with an fp16 A and a bf16 B traps as an illegal instruction)
 // two fp32 -> packed fp16 pair (element a in the low half), saturating instead of overflowing to inf
 __device__ __forceinline__ uint32_t pack_f16_sat(float a, float b) {
   uint32_t r;

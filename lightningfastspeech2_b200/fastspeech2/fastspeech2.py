@@ -92,10 +92,10 @@ class TransformerStack(nn.Module):
                                and "qkv" in first.two_pass_sites and src.shape[-1] == 256)
             if row_limit is not None:
                 row_limit = (row_limit[0], row_limit[1], {})  # one tile list per kernel family for the whole stack
-            for mod in self.layers:
+            for i, mod in enumerate(self.layers):
                 if mod.training and mod.p_drop > 0:
                     raise NotImplementedError("dropout in training mode is not implemented by the CUDA path")
-                xp = mod.forward_planes(xp, src_key_padding_mask, row_limit=row_limit)
+                xp = mod.forward_planes(xp, src_key_padding_mask, row_limit=row_limit, next_f16=i + 1 < len(self.layers))
             return xp if return_planes else ops.merge_planes(xp)
         if row_limit is not None:
             raise NotImplementedError("row limits need the tensor-core path")

@@ -151,6 +151,10 @@ class ConformerEncoderLayer(nn.Module):
         if self.depthwise:
             w["pw1"] = ops.split_bf16(p["pw1_w"])
             w["w_eff"] = ops.split_bf16(p["w_eff"])
+            # fp16 hi/lo planes for the 2-pass recipe (fp16 activation plane; see two_pass_sites)
+            w["in_proj16"] = ops.split_f16(sa.in_proj_weight.detach().contiguous())
+            w["pw1_16"] = ops.split_f16(p["pw1_w"])
+            w["w_eff16"] = ops.split_f16(p["w_eff"])
         else:
             w["c1"] = ops.split_bf16(p["c1_wp"])
             w["c2"] = ops.split_bf16(p["c2_wp"])
@@ -198,7 +202,8 @@ class ConformerEncoderLayer(nn.Module):
         x = src
         sa = self.self_attn
         if self.tc_capable(x.shape[-1]):
-            return ops.merge_planes(self.forward_planes(ops.planes_of(x), src_key_padding_mask))
+            two = self.compute_mode == "fp32" and "qkv" in self.two_pass_sites and x.shape[-1] == 256
+            return ops.merge_planes(self.forward_planes(ops.planes_of(x, want_f16=two), src_key_padding_mask, next_f16=False))
         qkv = ops.linear(x, sa.in_proj_weight, sa.in_proj_bias, tag="qkv_gemm")
         ctx = ops.attention(qkv, src_key_padding_mask, self.nhead)
         a = ops.linear(ctx, sa.out_proj.weight, sa.out_proj.bias, tag="out_proj_gemm")
@@ -223,13 +228,14 @@ class ConformerEncoderLayer(nn.Module):
         fsz = self.conv1[1].weight.shape[0]
         return fsz % 256 == 0 and fsz <= 2048 and self.conv1[0].kernel_size[0] <= 25
 
-    def forward_planes(self, xp, kpm, row_limit=None):
+    def forward_planes(self, xp, kpm, row_limit=None, next_f16=True):
         """tcgen05 path, planes in -> planes out.  Activations travel between kernels only as bf16
         hi/lo planes (x = hi + lo to 2^-17): every GEMM has fused bias/ReLU epilogues, the
         residual add rides the tensor core (identity slabs) and LayerNorm is the epilogue of the
         out-proj and FFN-2 GEMMs; attention keeps Q/P in tensor memory.
         row_limit = (lengths int32 (B), extra, cache dict): every kernel of the block skips the 128-row tiles at or
-        after lengths[b] + extra of utterance b (see FastSpeech2.skip_pad_rows)."""
+        after lengths[b] + extra of utterance b (see FastSpeech2.skip_pad_rows).
+        next_f16: another block follows, so (2-pass QKV recipe) the result also carries its fp16 plane."""
         npass = _npass(self.compute_mode)
         sa, w, p = self.self_attn, self._packed_tc(), self._packed()
         d = xp.shape[-1]
@@ -238,11 +244,12 @@ class ConformerEncoderLayer(nn.Module):
         if d != 256:
             return self._forward_tc_unfused_ln(xp, kpm, npass)
         two = self.two_pass_sites if npass == 3 else ()
+        two = two if "pw1_16" in w else ()
         if d // self.nhead == 128:
             f16 = self.compute_mode == "fp32" and self.attention_operands == "f16"
             qkv_pass = 2 if (f16 and "qkv" in two and xp.h is not None) else npass
-            qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="f16" if f16 else "planes", npass=qkv_pass,
-                              tag="qkv_gemm", row_limit=row_limit)
+            qkv = ops.gemm_tc(xp, w["in_proj16" if qkv_pass == 2 else "in_proj"], sa.in_proj_bias,
+                              out="f16" if f16 else "planes", npass=qkv_pass, tag="qkv_gemm", row_limit=row_limit)
             _, ctx = ops.attention_tc(qkv, kpm, self.nhead, npass=npass, row_limit=row_limit)
         else:
             ctx = self._attention_any_head_dim(xp, kpm, npass)
@@ -256,9 +263,10 @@ class ConformerEncoderLayer(nn.Module):
                 ffn_pass = 2 if "ffn" in two else npass
                 up = ops.dwconv1d_planes(x1p, p["dw_wt"], self.conv1[0].bias, row_limit=row_limit,
                                          out="f16" if ffn_pass == 2 else "planes")
-                return ops.ffn_fused_tc(up, w["pw1"], self.conv1[1].bias, w["w_eff"], p["b_eff"], x1p,
+                w1, w2 = (w["pw1_16"], w["w_eff16"]) if ffn_pass == 2 else (w["pw1"], w["w_eff"])
+                return ops.ffn_fused_tc(up, w1, self.conv1[1].bias, w2, p["b_eff"], x1p,
                                         self.norm2.weight, self.norm2.bias, self.eps, npass=ffn_pass, row_limit=row_limit,
-                                        want_f16="qkv" in two)
+                                        want_f16=next_f16 and "qkv" in two)
             up = ops.dwconv1d_planes(x1p, p["dw_wt"], self.conv1[0].bias, row_limit=row_limit)
             vp = ops.gemm_tc(up, w["pw1"], self.conv1[1].bias, relu=True, out="planes", npass=npass, tag="ffn1_gemm")
             w2, b2, taps2 = w["w_eff"], p["b_eff"], 1

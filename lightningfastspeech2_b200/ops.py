@@ -404,6 +404,14 @@ def split_bf16(x, want_f16=False):
     return pl
 
 
+def split_f16(x):
+    """fp32 -> fp16 hi/lo planes (hi + lo = x to ~2^-22): the weight operand of the 2-pass recipe (npass = 2)"""
+    _chk(x, torch.float32, "split_f16 input")
+    buf = torch.empty((2,) + tuple(x.shape), device=x.device, dtype=torch.float16)
+    _launch("lfs2_split_f16", _p(x), _p(buf[0]), _p(buf[1]), x.numel(), _s(), nbytes=8.0 * x.numel())
+    return Planes(buf[0], buf[1])
+
+
 _IDENT = {}
 
 
@@ -426,8 +434,8 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
     feeds npass = 1 products); shaped like a with last dim n.
     dilation: tap spacing (dilated Conv1d); leaky_slope: leaky ReLU instead of ReLU; row_mask (B,T) bool: rows written
     as zeros (PAD frames of a ragged batch).
-    npass = 3: hi.hi + lo.hi + hi.lo; 1: hi.hi; 2: a as ONE fp16 plane against the bf16 hi/lo weight planes, a.w_hi +
-    a.w_lo (no LayerNorm / residual epilogue in this recipe)."""
+    npass = 3: hi.hi + lo.hi + hi.lo; 1: hi.hi; 2: a as ONE fp16 plane against fp16 hi/lo weight planes (split_f16),
+    a.w_hi + a.w_lo (no LayerNorm / residual epilogue in this recipe)."""
     if not isinstance(a, Planes) or not isinstance(w, Planes):
         raise TypeError("gemm_tc: operands must be Planes (see split_bf16)")
     if out not in OUT_KINDS:
@@ -448,7 +456,8 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
                 raise ValueError("gemm_tc: npass = 2 needs the fp16 plane of a (Planes.h or Planes(fp16, None))")
             a = Planes(a.h, None)
         _chk(a.hi, torch.float16, "gemm_tc: a of the 2-pass recipe")
-        _chk(w.hi, torch.bfloat16, "gemm_tc operand plane"); _chk(w.lo, torch.bfloat16, "gemm_tc operand plane")
+        _chk(w.hi, torch.float16, "gemm_tc: w of the 2-pass recipe (split_f16)")
+        _chk(w.lo, torch.float16, "gemm_tc: w of the 2-pass recipe (split_f16)")
     else:
         for x_ in (a.hi, a.lo, w.hi, w.lo):
             if x_ is not None or npass == 3:  # (single-plane operands: Planes(hi, None) are fine for npass = 1)
@@ -547,7 +556,8 @@ def predictor_layer_tc(a, w, bias, gamma, beta, eps=LN_EPS, npass=3, next_dw=Non
 def ffn_fused_tc(u, w1, b1, w2, b2, residual, gamma, beta, eps=LN_EPS, npass=3, row_limit=None, want_f16=False):
     """LayerNorm(residual + relu(u . w1^T + b1) . w2^T + b2) in one kernel, the F-wide intermediate on chip.
     u, residual: Planes (..., 256); w1 Planes (F, 256); w2 Planes (256, F) -> Planes (..., 256).
-    npass = 2: u is ONE fp16 plane (Planes(hi = fp16, lo = None)), products a.w_hi + a.w_lo.  want_f16: the result also
+    npass = 2: u is ONE fp16 plane (Planes(hi = fp16, lo = None)), w1 / w2 fp16 hi/lo planes (split_f16), products
+    a.w_hi + a.w_lo.  want_f16: the result also
     carries its fp16 plane (Planes.h) for the next block's 2-pass QKV GEMM.
     row_limit = (lengths int32 (B), extra[, cache dict]) on (B,T,256) operands: 128-row tiles that hold no row
     t < roundup128(lengths[b] + extra) of any utterance are skipped (their output rows stay unwritten)."""
@@ -561,8 +571,10 @@ def ffn_fused_tc(u, w1, b1, w2, b2, residual, gamma, beta, eps=LN_EPS, npass=3, 
         _chk(u.hi, torch.bfloat16, "ffn_fused_tc operand plane")
         if npass == 3:
             _chk(u.lo, torch.bfloat16, "ffn_fused_tc operand plane")
-    for x_ in (w1.hi, w1.lo, w2.hi, w2.lo, residual.hi, residual.lo):
-        _chk(x_, torch.bfloat16, "ffn_fused_tc operand plane")
+    for x_ in (w1.hi, w1.lo, w2.hi, w2.lo):
+        _chk(x_, torch.float16 if npass == 2 else torch.bfloat16, "ffn_fused_tc weight plane")
+    for x_ in (residual.hi, residual.lo):
+        _chk(x_, torch.bfloat16, "ffn_fused_tc residual plane")
     m = u.hi.numel() // d
     out = _empty_planes(tuple(u.shape), u.hi.device)
     if want_f16:

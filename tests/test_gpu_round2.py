@@ -202,8 +202,8 @@ def test_fused_adamw_resumes_from_its_state_dict(tmp_path):
 @pytest.mark.parametrize("name", ["c1_infer", "c2_small_infer"])
 def test_attention_operand_recipes_against_the_fp64_goldens(golden_dir, name):
     """compute mode "fp32": q, k, v / P as ONE fp16 plane, single-pass products (default) vs bf16 hi/lo planes, three
-    passes ("x3").  Gate: max |mel - fp64 reference| <= 2e-4, i.e. >= 5x margin to the 1e-3
-    budget, on every position the reference defines."""
+    passes ("x3"), and the 2-pass GEMM sites (ConformerEncoderLayer.two_pass_sites) on top.  Gate (VERDICT round 1
+    item 3): max |mel - fp64 reference| stays >= 3x inside the 1e-3 budget on every position the reference defines."""
     from lightningfastspeech2_b200.fastspeech2.model import ConformerEncoderLayer
 
     g = torch.load(os.path.join(golden_dir, name + ".pt"), weights_only=False)
@@ -215,16 +215,21 @@ def test_attention_operand_recipes_against_the_fp64_goldens(golden_dir, name):
     model = model.eval().to(DEV)
     force = {"duration_rounded": g["out"]["duration_rounded"], "bucket_idx": dict(g["bucket_idx"])}
     errs = {}
+    sites = ConformerEncoderLayer.two_pass_sites
     try:
-        for recipe in ("f16", "x3"):
+        # shipped recipe (fp16 attention + 2-pass QKV / FFN GEMMs) | fp16 attention, every GEMM 3-pass | everything 3-pass
+        for label, recipe, two in (("shipped", "f16", sites), ("f16", "f16", ()), ("x3", "x3", ())):
             ConformerEncoderLayer.attention_operands = recipe
+            ConformerEncoderLayer.two_pass_sites = two
             with torch.no_grad():
                 r = model(g["batch"], inference=True, force=force)
-            errs[recipe] = float((r["mel"].cpu().double() - g["out64_mel"]).abs().max())
+            errs[label] = float((r["mel"].cpu().double() - g["out64_mel"]).abs().max())
     finally:
         ConformerEncoderLayer.attention_operands = "f16"
-    print(f"{name}: max |mel - fp64| with fp16 single-pass attention {errs['f16']:.2e}, 3-pass split-bf16 {errs['x3']:.2e}")
-    assert errs["x3"] < 1e-4 and errs["f16"] < 2e-4, errs
+        ConformerEncoderLayer.two_pass_sites = sites
+    print(f"{name}: max |mel - fp64|: shipped recipe {errs['shipped']:.2e}, fp16 attention with 3-pass GEMMs "
+          f"{errs['f16']:.2e}, all 3-pass split-bf16 {errs['x3']:.2e}")
+    assert errs["x3"] < 1e-4 and errs["f16"] < 2e-4 and errs["shipped"] < 3.3e-4, errs   # >= 3x margin to the 1e-3 budget
 
 
 @pytest.mark.parametrize("preset,bsz,lo,hi", [("C1", 1, 128, 128), ("C2", 5, 10, 60)])
