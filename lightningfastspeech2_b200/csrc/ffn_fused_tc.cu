@@ -116,6 +116,13 @@ __device__ __forceinline__ void f_tmem_st16(uint32_t taddr, const uint32_t* r) {
       : "memory");
 }
 
+#ifdef LFS2_FFN_TIMELINE  // diagnostics build only (tools/ffn_ab.py timeline): per-CTA, per-tile clock64 stamps
+__device__ long long g_ffn_tl[148][16][8];
+#define FFN_TL(slot) do { if (it < 16) g_ffn_tl[blockIdx.x][it][slot] = clock64(); } while (0)
+#else
+#define FFN_TL(slot) do { } while (0)
+#endif
+
 template <int NPASS, bool MC>
 __global__ void __launch_bounds__(kFThreads, 1)
 ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_constant__ CUtensorMap map_u_lo,
@@ -295,6 +302,7 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
       }
     };
     for (int wi = w_first; wi < w_count; wi += w_stride, ++it) {
+      if (lane == 0) FFN_TL(5);
       issue_g1(chunk_ctr);
       for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
         // G1 of the next chunk goes first: it runs on the tensor pipe while the epilogue warps convert chunk c.
@@ -304,6 +312,7 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
         mbar_wait(&v_ready[chunk_ctr & 1], (chunk_ctr >> 1) & 1);
         // the first G2 of a tile overwrites acc2: the previous tile's LayerNorm epilogue must have drained it
         if (c == 0) mbar_wait(&acc2_empty, (it & 1) ^ 1);
+        if (c == 0 && lane == 0) FFN_TL(6);
         tc_fence_after();
         const uint32_t vbase = t_acc1 + 128 * (chunk_ctr & 1);
         for (int ks = 0; ks < kFC / kFK; ++ks) {
@@ -332,6 +341,7 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
       }
       // ---- residual x1 on the tensor core: acc2[:, 32 ks .. 32 ks + 32) += R_hi[ks] . I32 + R_lo[ks] . I32 ----
       if (it == 0) mbar_wait(&ident_bar, 0);
+      if (lane == 0) FFN_TL(7);
       for (int ks = 0; ks < kSlabs; ++ks) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
@@ -366,10 +376,14 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
     float v[32];
     for (int wi = w_first; wi < w_count; wi += w_stride, ++it) {
       const int r0 = row0_of(wi);
+      if (warp == 2 && lane == 0) FFN_TL(0);
       // ---- E1 per F chunk: acc1 -> relu(acc1 + b1) as bf16 hi/lo pairs, in place ----
       for (int c = 0; c < nchunks; ++c, ++chunk_ctr) {
         mbar_wait(&acc1_full[chunk_ctr & 1], (chunk_ctr >> 1) & 1);
         tc_fence_after();
+#ifdef LFS2_FFN_DIAG_NO_E1  // timing diagnostics only (tools/ffn_ab.py): wrong results
+        if (false)
+#endif
 #pragma unroll 1
         for (int j = 2 * half; j < 2 * half + 2; ++j) {  // 4 blocks of 32 columns per chunk, 2 per warp of the pair
           const uint32_t ta = t_acc1 + 128 * (chunk_ctr & 1) + lane_off + 32 * j;
@@ -391,10 +405,15 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
         if (lane == 0) mbar_arrive(&v_ready[chunk_ctr & 1]);
       }
       // ---- final epilogue: acc2 + b2 -> LayerNorm -> hi/lo planes ----
+      if (warp == 2 && lane == 0) FFN_TL(1);
       mbar_wait(&acc2_full, it & 1);
+      if (warp == 2 && lane == 0) FFN_TL(2);
       tc_fence_after();
       const uint32_t ta2 = t_acc2 + lane_off;
       float s = 0.f, q = 0.f;
+#ifdef LFS2_FFN_DIAG_NO_LN
+      if (false)
+#endif
 #pragma unroll 1
       for (int j = 4 * half; j < 4 * half + 4; ++j) {
         tmem_ld32(ta2 + 32 * j, v);
@@ -408,11 +427,15 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
       float2* stt = stats + (it & 1) * 2 * kFM;
       stt[half * kFM + r] = make_float2(s, q);
       f_bar_sync(3, 256);
+      if (warp == 2 && lane == 0) FFN_TL(3);
       const float2 o = stt[(half ^ 1) * kFM + r];
       s += o.x;
       q += o.y;
       const float mean = s * (1.f / kFD);
       const float rstd = rsqrtf(fmaxf(q * (1.f / kFD) - mean * mean, 0.f) + p.eps);
+#ifdef LFS2_FFN_DIAG_NO_LN
+      if (false)
+#endif
 #pragma unroll 1
       for (int j = 4 * half; j < 4 * half + 4; ++j) {
         tmem_ld32(ta2 + 32 * j, v);
@@ -437,6 +460,9 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
         fence_proxy_async_smem();
         if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         f_bar_sync(1 + half, 128);
+#ifdef LFS2_FFN_DIAG_NO_STORES
+        if (false)
+#endif
         if (issuer) {
           f_tma_store_3d(&map_o_hi, sb, 32 * j, r0, 0);
           f_tma_store_3d(&map_o_lo, sb + kFStageChunk / 2, 32 * j, r0, 0);
@@ -458,6 +484,7 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
       }
       tc_fence_before();
       __syncwarp();
+      if (warp == 2 && lane == 0) FFN_TL(4);
       if (lane == 0) mbar_arrive(&acc2_empty);
     }
     if (issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -523,6 +550,12 @@ extern "C" int lfs2_ffn_fused_tc(const void* u_hi, const void* u_lo, int m, cons
   return lfs2_ffn_fused_tc_limited(u_hi, u_lo, 1, m, w1_hi, w1_lo, f, b1, w2_hi, w2_lo, b2, res_hi, res_lo, ident_hi, gamma,
                                    beta, eps, out_hi, out_lo, npass, nullptr, 0, nullptr, stream);
 }
+
+#ifdef LFS2_FFN_TIMELINE
+extern "C" __attribute__((visibility("default"))) int lfs2_ffn_timeline(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_ffn_tl, sizeof(g_ffn_tl)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 extern "C" long long lfs2_ffn_fused_tc_limited_workspace_bytes(int batch, int t) {
   return batch > 0 && t > 0 ? (1 + (long long)ceil_div((long long)batch * t, kFM)) * (long long)sizeof(int) : 0;

@@ -83,17 +83,17 @@ __global__ void gemm_tile_list_kernel(const int* __restrict__ row_limit, int ext
   }
 }
 
-template <int N_TILE, int NPASS, bool LN, int EPI = 0>
+template <int N_TILE, int NPASS, bool LN, int EPI = 0, bool MC = false>
 struct SmemLayout {
   static constexpr int kEdge = EPI != 0 ? 4 * N_TILE * 4 : 0;  // kEpiStencil: taps w0 | w1 | w2 | bias; kEpiDot: the head weight
   static constexpr bool kHasLo = NPASS == 3 || LN;  // LN variants stream residual lo planes even in bf16 mode
   static constexpr int kAPlane = kBM * kBK * 2;     // 8 KB
-  static constexpr int kWPlane = N_TILE * kBK * 2;
+  static constexpr int kWPlane = N_TILE * kBK * 2 / (MC ? 2 : 1);  // CTA pair: each CTA holds half of the weight slab
   static constexpr int kStage = (kHasLo ? 2 : 1) * kAPlane + (NPASS >= 2 ? 2 : 1) * kWPlane;
   static constexpr int kOffWHi = kAPlane;
   static constexpr int kOffALo = kAPlane + kWPlane;
   static constexpr int kOffWLo = (kHasLo ? 2 : 1) * kAPlane + kWPlane;
-  static constexpr int kI32 = kHasLo ? 32 * kBK * 2 : 0;               // 32 x 32 identity block of the residual products
+  static constexpr int kI32 = kHasLo ? 32 * kBK * 2 : 0;               // 32 x 32 identity block of the residual products (pair: 16 rows each)
   static constexpr int kFixed = 4 * kStageChunk + kI32 + (LN ? 3 * N_TILE * 4 + 2 * 2 * kBM * 8 : 0) + kEdge + 1024;
   static constexpr int kStages = (226 * 1024 - kFixed) / kStage > 6 ? 6 : (226 * 1024 - kFixed) / kStage;
   static constexpr int kOffStaging = kStages * kStage;                 // 2 halves x 2 chunks, 1024-aligned
@@ -119,10 +119,12 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// ---- 2-CTA cluster variant (MC): the two CTAs of a cluster work on two row tiles of the SAME column tile, each
-// fetches half of every weight slab and multicasts it into both CTAs' shared memory.  A K = 256 GEMM re-reads its
-// whole weight tile for every 128-row tile (262 KB of the 521 KB a tile moves L2 -> SM in fp32 mode), which is what
-// bounds these kernels; sharing the slab halves that part.
+// ---- CTA-pair variant (MC): the two CTAs of a cluster work on two row tiles of the SAME column tile as ONE
+// tcgen05.mma.cta_group::2 of M = 256 (tc_common.cuh): each CTA fetches its own A rows and HALF of every weight slab
+// (its N_TILE/2 rows), the leader issues the MMAs, each CTA's accumulator rows land in its own tensor memory.  A K = 256
+// GEMM re-reads its whole weight tile for every 128-row tile (262 KB of the 521 KB a tile moves L2 -> SM in fp32 mode),
+// which is what bounds these kernels; the pair halves that part per SM (a multicast of the halves into both CTAs, the
+// round-1 scheme, moved the same bytes into every SM and gained 1 %).
 // work items of one CTA: item i -> (utterance b, first row t0, first column n0)
 template <bool MC>
 struct TileWalk {
@@ -167,7 +169,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                const __grid_constant__ CUtensorMap map_o1, const GemmTcParams p) {
   static_assert(EPI == kEpiNone || (LN && !MC && OUT == kOutPlanes), "fused predictor epilogues ride the LayerNorm variant");
   static_assert(NPASS != 2 || !LN, "the 2-pass recipe (fp16 activation plane) has no LayerNorm / residual build");
-  using L = SmemLayout<N_TILE, NPASS, LN, EPI>;
+  using L = SmemLayout<N_TILE, NPASS, LN, EPI, MC>;
   constexpr int kStages = L::kStages;
   constexpr int kAccCols = (N_TILE <= 32) ? 32 : (N_TILE <= 64) ? 64 : (N_TILE <= 128) ? 128 : 256;
   constexpr uint32_t kTmemCols = 2 * kAccCols;
@@ -189,16 +191,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     prefetch_tmap(&map_o0);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], MC ? 2 : 1);  // MC: a slot is free when BOTH CTAs' MMAs have read it (the peer writes into it too)
+      mbar_init(&empty_bar[s], 1);  // (pair: the leader's commit arrives here in both CTAs)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty[i], MC ? 16 : 8);  // one arrive per epilogue warp (pair: of both CTAs, on the leader's barrier)
     }
     mbar_init(&ident_bar, 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(&tmem_base_smem, kTmemCols);
+  if (MC) cluster_sync_all();  // both CTAs are running and their barriers exist before the pair-wide allocation
+  if (warp == 1) {
+    if (MC) tmem_alloc_pair(&tmem_base_smem, kTmemCols);
+    else tmem_alloc(&tmem_base_smem, kTmemCols);
+  }
   if (LN && warp >= 2) {  // bias | gamma | beta -> shared (broadcast reads in the epilogue)
     float* vec = reinterpret_cast<float*>(smem + L::kOffVec);
     for (int i = threadIdx.x - 64; i < N_TILE; i += 256) {
@@ -222,7 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
-  if (MC) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast into this CTA
+  if (MC) cluster_sync_all();  // the peer's tensor memory is allocated before the leader's MMAs write into it
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   const TileWalk<MC> walk(p);
@@ -232,17 +238,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      // MC: the weight maps have half-height boxes; this CTA fetches rows [rank * N_TILE/2, +N_TILE/2) of a slab
-      // and multicasts them to the same place in both CTAs (each full barrier still sees a whole slab's bytes)
+      // MC (CTA pair): the weight maps have half-height boxes; this CTA fetches rows [rank * N_TILE/2, +N_TILE/2) of a
+      // slab into ITS shared memory; every load of both CTAs completes on the leader's barrier, which expects both shares
       const int w_row = MC ? walk.rank * (N_TILE / 2) : 0;
-      const int w_off = MC ? walk.rank * (L::kWPlane / 2) : 0;
+      const bool leader = !MC || walk.rank == 0;
+      auto load = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+        if (MC) tma_load_3d_pair(dst, map, pair_leader_bar(bar), c0, c1, c2);
+        else tma_load_3d(dst, map, bar, c0, c1, c2);
+      };
       auto load_w = [&](uint8_t* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-        if (MC) tma_load_3d_mc(dst + w_off, map, bar, c0, c1 + w_row, 0, (uint16_t)3);
-        else tma_load_3d(dst, map, bar, c0, c1, 0);
+        load(dst, map, bar, c0, c1 + w_row, 0);
       };
       if (L::kHasLo && r_slabs > 0 && walk.first < walk.count) {  // the identity block of the residual products: once
-        mbar_expect_tx(&ident_bar, L::kI32);
-        tma_load_3d(smem + L::kOffI32, &map_ident, &ident_bar, 0, 0, 0);
+        if (leader) mbar_expect_tx(&ident_bar, L::kI32);           // (pair: 16 of its 32 rows in each CTA)
+        load(smem + L::kOffI32, &map_ident, &ident_bar, 0, MC ? walk.rank * 16 : 0, 0);
       }
       for (int tile = walk.first; tile < walk.count; tile += walk.stride) {
         int b, t0, n0;
@@ -253,25 +262,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           if (ks < a_slabs) {
             int tap = ks / (p.d / kBK), c0 = (ks % (p.d / kBK)) * kBK;
 #ifdef LFS2_DIAG_NO_LO_LOADS  // timing diagnostics only (tools/gemm_ab.py): wrong results
-            mbar_expect_tx(&full_bar[stage], L::kAPlane + L::kWPlane);
+            if (leader) mbar_expect_tx(&full_bar[stage], (MC ? 2 : 1) * (L::kAPlane + L::kWPlane));
 #else
-            mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 2 : 1) * L::kAPlane + (NPASS >= 2 ? 2 : 1) * L::kWPlane);
+            if (leader)
+              mbar_expect_tx(&full_bar[stage],
+                             (MC ? 2 : 1) * ((NPASS == 3 ? 2 : 1) * L::kAPlane + (NPASS >= 2 ? 2 : 1) * L::kWPlane));
 #endif
-            tma_load_3d(st, &map_a_hi, &full_bar[stage], c0, t0 + (tap - p.half) * p.dil, b);
+            load(st, &map_a_hi, &full_bar[stage], c0, t0 + (tap - p.half) * p.dil, b);
             load_w(st + L::kOffWHi, &map_w_hi, &full_bar[stage], tap * p.d + c0, n0);
 #ifdef LFS2_DIAG_NO_LO_LOADS
             if (false) {
 #else
             if (NPASS >= 2) {
 #endif
-              if (NPASS == 3) tma_load_3d(st + L::kOffALo, &map_a_lo, &full_bar[stage], c0, t0 + (tap - p.half) * p.dil, b);
+              if (NPASS == 3) load(st + L::kOffALo, &map_a_lo, &full_bar[stage], c0, t0 + (tap - p.half) * p.dil, b);
               load_w(st + L::kOffWLo, &map_w_lo, &full_bar[stage], tap * p.d + c0, n0);
             }
           } else if (L::kHasLo) {  // residual slab: R_hi, R_lo (against the resident 32 x 32 identity block)
             int c0 = n0 + (ks - a_slabs) * kBK;
-            mbar_expect_tx(&full_bar[stage], 2 * L::kAPlane);
-            tma_load_3d(st, &map_r_hi, &full_bar[stage], c0, t0, b);
-            tma_load_3d(st + L::kOffALo, &map_r_lo, &full_bar[stage], c0, t0, b);
+            if (leader) mbar_expect_tx(&full_bar[stage], (MC ? 2 : 1) * 2 * L::kAPlane);
+            load(st, &map_r_hi, &full_bar[stage], c0, t0, b);
+            load(st + L::kOffALo, &map_r_lo, &full_bar[stage], c0, t0, b);
           }
           if (++stage == kStages) {
             stage = 0;
@@ -280,13 +291,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 1 && (!MC || walk.rank == 0)) {
+    // ===================== MMA issuer (pair: the leader CTA's, for both) =====================
     // whole warp runs the uniform control flow (descriptors stay in uniform registers), one
     // elected lane issues; per instruction the descriptor is a 64-bit add on a precomputed base
     // NPASS = 2: the activation operand is ONE fp16 plane against fp16 hi/lo weight planes (a.w_hi + a.w_lo)
-    constexpr uint32_t idesc = make_idesc(NPASS == 2 ? kFmtF16 : kFmtBF16, kBM, N_TILE, 0, 0);
-    constexpr uint32_t idesc_r = make_idesc(kFmtBF16, kBM, 32, 0, 0);  // residual: one 32-column block per slab
+    constexpr int kM = MC ? 2 * kBM : kBM;  // pair: one instruction covers both CTAs' row tiles
+    constexpr uint32_t idesc = make_idesc(NPASS == 2 ? kFmtF16 : kFmtBF16, kM, N_TILE, 0, 0);
+    constexpr uint32_t idesc_r = make_idesc(kFmtBF16, kM, 32, 0, 0);  // residual: one 32-column block per slab
+    auto mma = [&](bool accumulate, uint32_t d, uint64_t a, uint64_t b, uint32_t id) {
+      if (MC) {
+        if (accumulate) umma_f16_pair<true>(d, a, b, id);
+        else umma_f16_pair<false>(d, a, b, id);
+      } else {
+        if (accumulate) umma_f16_c<true>(d, a, b, id);
+        else umma_f16_c<false>(d, a, b, id);
+      }
+    };
     const uint64_t d0 = make_smem_desc(smem_u32(smem), 16, 512, kSwizzle64);
     const uint64_t d_i32 = make_smem_desc(smem_u32(smem + L::kOffI32), 16, 512, kSwizzle64);
     if (L::kHasLo && r_slabs > 0 && walk.first < walk.count) mbar_wait(&ident_bar, 0);
@@ -312,35 +333,38 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             // residual: acc[:, 32 j .. 32 j + 32) += R_hi[j] . I32 + R_lo[j] . I32 -- N = 32 instructions, an eighth of
             // the tensor work of a full-width identity slab, and the identity never travels again
             const uint32_t acc_r = d_tmem + 32 * (ks - a_slabs);
-            umma_f16_c<true>(acc_r, a_hi, d_i32, idesc_r);
-            umma_f16_c<true>(acc_r, desc_advance(a_hi, 32), desc_advance(d_i32, 32), idesc_r);
-            umma_f16_c<true>(acc_r, a_lo, d_i32, idesc_r);
-            umma_f16_c<true>(acc_r, desc_advance(a_lo, 32), desc_advance(d_i32, 32), idesc_r);
+            mma(true, acc_r, a_hi, d_i32, idesc_r);
+            mma(true, acc_r, desc_advance(a_hi, 32), desc_advance(d_i32, 32), idesc_r);
+            mma(true, acc_r, a_lo, d_i32, idesc_r);
+            mma(true, acc_r, desc_advance(a_lo, 32), desc_advance(d_i32, 32), idesc_r);
           } else {
             // 16 bf16 = 32 bytes along K inside the 64-byte swizzled row per k16 step
-            if (ks == 0) umma_f16_c<false>(d_tmem, a_hi, w_hi, idesc);
-            else umma_f16_c<true>(d_tmem, a_hi, w_hi, idesc);
-            umma_f16_c<true>(d_tmem, desc_advance(a_hi, 32), desc_advance(w_hi, 32), idesc);
+            mma(ks != 0, d_tmem, a_hi, w_hi, idesc);
+            mma(true, d_tmem, desc_advance(a_hi, 32), desc_advance(w_hi, 32), idesc);
 #ifdef LFS2_DIAG_NO_LO_MMAS
             if (false) {
 #else
             if (NPASS == 3) {
 #endif
-              umma_f16_c<true>(d_tmem, a_lo, w_hi, idesc);
-              umma_f16_c<true>(d_tmem, desc_advance(a_lo, 32), desc_advance(w_hi, 32), idesc);
+              mma(true, d_tmem, a_lo, w_hi, idesc);
+              mma(true, d_tmem, desc_advance(a_lo, 32), desc_advance(w_hi, 32), idesc);
             }
 #ifdef LFS2_DIAG_NO_LO_MMAS
             if (false) {
 #else
             if (NPASS >= 2) {
 #endif
-              umma_f16_c<true>(d_tmem, a_hi, w_lo, idesc);
-              umma_f16_c<true>(d_tmem, desc_advance(a_hi, 32), desc_advance(w_lo, 32), idesc);
+              mma(true, d_tmem, a_hi, w_lo, idesc);
+              mma(true, d_tmem, desc_advance(a_hi, 32), desc_advance(w_lo, 32), idesc);
             }
           }
-          if (MC) umma_commit_mc(&empty_bar[stage], (uint16_t)3);  // ... in both CTAs: either producer may refill it
-          else umma_commit(&empty_bar[stage]);                   // smem slot reusable once these MMAs retire
-          if (ks + 1 == k_slabs) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
+          if (MC) {  // pair: the slot is free / the accumulator complete in BOTH CTAs
+            umma_commit_pair(&empty_bar[stage], (uint16_t)3);
+            if (ks + 1 == k_slabs) umma_commit_pair(&tmem_full[acc], (uint16_t)3);
+          } else {
+            umma_commit(&empty_bar[stage]);                        // smem slot reusable once these MMAs retire
+            if (ks + 1 == k_slabs) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
+          }
         }
         __syncwarp();
         if (++stage == kStages) {
@@ -349,7 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
       }
     }
-  } else {
+  } else if (warp >= 2) {
     // ===================== epilogue: warps 2..9 =====================
     // thread = one output row (TMEM lane quadrant = warp & 3); the two warps of a quadrant split
     // the tile's 32-column chunks between them (half 0: first chunks, half 1: the rest), each
@@ -358,6 +382,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int half = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
     const bool issuer = (warp == 2 || warp == 6) && lane == 0;  // issues / retires this half's TMA stores
+    auto release_acc = [&](uint64_t* bar) {  // accumulator drained (pair: the leader's MMA warp waits for both CTAs)
+      if (MC) mbar_arrive_cluster(bar, 0);
+      else mbar_arrive(bar);
+    };
     const float* vec = reinterpret_cast<const float*>(smem + L::kOffVec);
     float2* stats = reinterpret_cast<float2*>(smem + L::kOffStats);
     uint8_t* staging = smem + L::kOffStaging + half * 2 * kStageChunk;
@@ -428,7 +456,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) release_acc(&tmem_empty[acc]);
         continue;
       }
 
@@ -503,7 +531,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) release_acc(&tmem_empty[acc]);
         continue;
       }
 
@@ -590,7 +618,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) release_acc(&tmem_empty[acc]);
     }
     if (issuer) tma_store_wait_all();
   }
@@ -600,7 +628,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
   if (MC) cluster_sync_all();  // the peer may still arrive on this CTA's barriers until it has finished too
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (MC) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
@@ -683,7 +712,7 @@ struct GemmTcMaps {
 
 template <int N_TILE, int NPASS, bool LN, int OUT, bool MC, int EPI = 0>
 static int launch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, cudaStream_t s) {
-  using L = SmemLayout<N_TILE, NPASS, LN, EPI>;
+  using L = SmemLayout<N_TILE, NPASS, LN, EPI, MC>;
   auto kern = gemm_tc_kernel<N_TILE, NPASS, LN, OUT, MC, EPI>;
   static bool configured = false;
   if (!configured) {
@@ -744,7 +773,7 @@ static int dispatch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, int npas
   return launch_gemm_tc<N_TILE, 1, LN, kOutPlanes, MC>(m, p, s);
 }
 
-// LFS2_GEMM_MULTICAST=0 switches the 2-CTA weight multicast off (A/B measurements)
+// LFS2_GEMM_MULTICAST=0 switches the CTA-pair variant off (A/B measurements)
 static bool gemm_multicast_enabled() {
   static int on = -1;
   if (on < 0) {
@@ -843,7 +872,7 @@ int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int t, int d,
   if (npass >= 2) ok = ok && make_tmap_3d(&m.wl, w_lo, ktot, n, 1, kBK, w_box, 64);
   if (res_hi)
     ok = ok && make_tmap_3d(&m.rh, res_hi, n, t, batch, kBK, kBM, 64) &&
-         make_tmap_3d(&m.rl, res_lo, n, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.ident, ident_hi, n, n, 1, kBK, 32, 64);
+         make_tmap_3d(&m.rl, res_lo, n, t, batch, kBK, kBM, 64) && make_tmap_3d(&m.ident, ident_hi, n, n, 1, kBK, mc ? 16 : 32, 64);
   else {
     m.rh = m.ah;
     m.rl = m.ah;
