@@ -216,11 +216,17 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
         for (int ks = 0; ks < kSlabs; ++ks) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * L::kStage;
+#ifdef LFS2_FFN_DIAG_NO_WLO_LOADS  // timing diagnostics only: the lo weight planes are not fetched (stale operands)
+          mbar_expect_tx(&full_bar[stage], (NPASS == 3 ? 3 : 2) * L::kAPlane);
+#else
           mbar_expect_tx(&full_bar[stage], (NPASS + 1) * L::kAPlane);
+#endif
           tma_load_3d(st, &map_u_hi, &full_bar[stage], ks * kFK, r0, 0);
           load_w(st + L::kG1W1Hi, &map_w1_hi, &full_bar[stage], ks * kFK, c * kFC, kFC, L::kAPlane);
           if (NPASS == 3) tma_load_3d(st + L::kG1ALo, &map_u_lo, &full_bar[stage], ks * kFK, r0, 0);
+#ifndef LFS2_FFN_DIAG_NO_WLO_LOADS
           if (NPASS >= 2) load_w(st + L::kG1W1Lo, &map_w1_lo, &full_bar[stage], ks * kFK, c * kFC, kFC, L::kAPlane);
+#endif
           next();
         }
       };
@@ -228,9 +234,14 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
         for (int ks = 0; ks < kFC / kFK; ++ks) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * L::kStage;
+#ifdef LFS2_FFN_DIAG_NO_WLO_LOADS
+          mbar_expect_tx(&full_bar[stage], L::kW2Plane);
+          load_w(st, &map_w2_hi, &full_bar[stage], c * kFC + ks * kFK, 0, kFD, L::kW2Plane);
+#else
           mbar_expect_tx(&full_bar[stage], (NPASS >= 2 ? 2 : 1) * L::kW2Plane);
           load_w(st, &map_w2_hi, &full_bar[stage], c * kFC + ks * kFK, 0, kFD, L::kW2Plane);
           if (NPASS >= 2) load_w(st + L::kG2Lo, &map_w2_lo, &full_bar[stage], c * kFC + ks * kFK, 0, kFD, L::kW2Plane);
+#endif
           next();
         }
       };
@@ -389,12 +400,19 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
           const uint32_t ta = t_acc1 + 128 * (chunk_ctr & 1) + lane_off + 32 * j;
           tmem_ld32(ta, v);
           uint32_t hi[16], lo[16];
-          const float* bb = b1s + c * kFC + 32 * j;
+          const float4* bb = reinterpret_cast<const float4*>(b1s + c * kFC + 32 * j);  // broadcast 16-byte reads
 #pragma unroll
-          for (int e = 0; e < 16; ++e) {
-            const float x0 = fmaxf(v[2 * e] + bb[2 * e], 0.f), x1 = fmaxf(v[2 * e + 1] + bb[2 * e + 1], 0.f);
-            if (NPASS == 2) hi[e] = pack_f16_sat(x0, x1);
-            else split_pack2(x0, x1, hi[e], lo[e]);
+          for (int e = 0; e < 8; ++e) {
+            const float4 b = bb[e];
+            const float x0 = fmaxf(v[4 * e] + b.x, 0.f), x1 = fmaxf(v[4 * e + 1] + b.y, 0.f);
+            const float x2 = fmaxf(v[4 * e + 2] + b.z, 0.f), x3 = fmaxf(v[4 * e + 3] + b.w, 0.f);
+            if (NPASS == 2) {
+              hi[2 * e] = pack_f16_sat(x0, x1);
+              hi[2 * e + 1] = pack_f16_sat(x2, x3);
+            } else {
+              split_pack2(x0, x1, hi[2 * e], lo[2 * e]);
+              split_pack2(x2, x3, hi[2 * e + 1], lo[2 * e + 1]);
+            }
           }
           f_tmem_st16(ta, hi);
           if (NPASS == 3) f_tmem_st16(ta + 16, lo);
@@ -417,11 +435,15 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
 #pragma unroll 1
       for (int j = 4 * half; j < 4 * half + 4; ++j) {
         tmem_ld32(ta2 + 32 * j, v);
+        const float4* b4 = reinterpret_cast<const float4*>(vec + 32 * j);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float x = v[e] + vec[32 * j + e];
-          s += x;
-          q = fmaf(x, x, q);
+        for (int e = 0; e < 8; ++e) {
+          const float4 b = b4[e];
+          const float x0 = v[4 * e] + b.x, x1 = v[4 * e + 1] + b.y, x2 = v[4 * e + 2] + b.z, x3 = v[4 * e + 3] + b.w;
+          s += x0; q = fmaf(x0, x0, q);
+          s += x1; q = fmaf(x1, x1, q);
+          s += x2; q = fmaf(x2, x2, q);
+          s += x3; q = fmaf(x3, x3, q);
         }
       }
       float2* stt = stats + (it & 1) * 2 * kFM;
@@ -439,10 +461,18 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
 #pragma unroll 1
       for (int j = 4 * half; j < 4 * half + 4; ++j) {
         tmem_ld32(ta2 + 32 * j, v);
+        {
+          const float4* b4 = reinterpret_cast<const float4*>(vec + 32 * j);
+          const float4* g4 = reinterpret_cast<const float4*>(vec + kFD + 32 * j);
+          const float4* e4 = reinterpret_cast<const float4*>(vec + 2 * kFD + 32 * j);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const float x = v[e] + vec[32 * j + e];
-          v[e] = (x - mean) * rstd * vec[kFD + 32 * j + e] + vec[2 * kFD + 32 * j + e];
+          for (int e = 0; e < 8; ++e) {
+            const float4 b = b4[e], g = g4[e], bt = e4[e];
+            v[4 * e] = (v[4 * e] + b.x - mean) * rstd * g.x + bt.x;
+            v[4 * e + 1] = (v[4 * e + 1] + b.y - mean) * rstd * g.y + bt.y;
+            v[4 * e + 2] = (v[4 * e + 2] + b.z - mean) * rstd * g.z + bt.z;
+            v[4 * e + 3] = (v[4 * e + 3] + b.w - mean) * rstd * g.w + bt.w;
+          }
         }
         uint8_t* sb = staging + (st_ctr & 1) * kFStageChunk;
         ++st_ctr;
@@ -467,7 +497,9 @@ ffn_fused_tc_kernel(const __grid_constant__ CUtensorMap map_u_hi, const __grid_c
           f_tma_store_3d(&map_o_hi, sb, 32 * j, r0, 0);
           f_tma_store_3d(&map_o_lo, sb + kFStageChunk / 2, 32 * j, r0, 0);
         }
-        if (p.out_f16) {  // single staging buffer per half: every earlier store has been read (wait_group.read above)
+        if (p.out_f16) {
+          // single staging buffer per half: every earlier store has been read (wait_group.read above).  (Storing the
+          // plane straight from registers -- 16 bytes per row and instruction, half-filled sectors -- cost the kernel 7 %.)
           uint8_t* rf = smem + L::kOffF16 + half * L::kF16Stage + r * 64;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {

@@ -159,6 +159,22 @@ struct TileWalk {
 __device__ __forceinline__ float activate(float x, int kind, float slope) {
   return kind == 1 ? fmaxf(x, 0.f) : (kind == 2 ? (x > 0.f ? x : x * slope) : x);
 }
+// v[0..32) <- LayerNorm row values of one 32-column chunk: ((act(v + bias) - mean) * rstd) * gamma + beta, the three
+// vectors read from shared memory as broadcast 16-byte loads (vec = bias | gamma | beta, n floats each)
+__device__ __forceinline__ void ln_chunk(float (&v)[32], const float* vec, int n, int col0, float mean, float rstd, int act,
+                                         float slope) {
+  const float4* b4 = reinterpret_cast<const float4*>(vec + col0);
+  const float4* g4 = reinterpret_cast<const float4*>(vec + n + col0);
+  const float4* e4 = reinterpret_cast<const float4*>(vec + 2 * n + col0);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 bb = b4[j], g = g4[j], bt = e4[j];
+    v[4 * j] = (activate(v[4 * j] + bb.x, act, slope) - mean) * rstd * g.x + bt.x;
+    v[4 * j + 1] = (activate(v[4 * j + 1] + bb.y, act, slope) - mean) * rstd * g.y + bt.y;
+    v[4 * j + 2] = (activate(v[4 * j + 2] + bb.z, act, slope) - mean) * rstd * g.z + bt.z;
+    v[4 * j + 3] = (activate(v[4 * j + 3] + bb.w, act, slope) - mean) * rstd * g.w + bt.w;
+  }
+}
 
 template <int N_TILE, int NPASS, bool LN, int OUT, bool MC, int EPI = 0>
 __global__ void __launch_bounds__(kGemmTcThreads, 1)
@@ -411,11 +427,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           tmem_ld32(taddr + c * 32, v);
+          const float4* b4 = reinterpret_cast<const float4*>(vec + c * 32);  // broadcast 16-byte reads
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = activate(v[j] + vec[c * 32 + j], p.relu, p.slope);
-            s += x;
-            q = fmaf(x, x, q);
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = b4[j];
+            const float x0 = activate(v[4 * j] + bb.x, p.relu, p.slope), x1 = activate(v[4 * j + 1] + bb.y, p.relu, p.slope);
+            const float x2 = activate(v[4 * j + 2] + bb.z, p.relu, p.slope), x3 = activate(v[4 * j + 3] + bb.w, p.relu, p.slope);
+            s += x0; q = fmaf(x0, x0, q);
+            s += x1; q = fmaf(x1, x1, q);
+            s += x2; q = fmaf(x2, x2, q);
+            s += x3; q = fmaf(x3, x3, q);
           }
         }
         float2* st = stats + (it & 1) * 2 * kBM;
@@ -435,11 +456,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           tmem_ld32(taddr + c * 32, v);
+          ln_chunk(v, vec, N_TILE, c * 32, mean, rstd, p.relu, p.slope);
+          const float4* w4 = reinterpret_cast<const float4*>(stw_dot + c * 32);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = activate(v[j] + vec[c * 32 + j], p.relu, p.slope);
-            const float z = (x - mean) * rstd * vec[N_TILE + c * 32 + j] + vec[2 * N_TILE + c * 32 + j];
-            acc_dot = fmaf(z, stw_dot[c * 32 + j], acc_dot);
+          for (int j = 0; j < 8; ++j) {
+            const float4 w = w4[j];
+            acc_dot = fmaf(v[4 * j], w.x, acc_dot);
+            acc_dot = fmaf(v[4 * j + 1], w.y, acc_dot);
+            acc_dot = fmaf(v[4 * j + 2], w.z, acc_dot);
+            acc_dot = fmaf(v[4 * j + 3], w.w, acc_dot);
           }
         }
         float2* st = stats + (it & 1) * 2 * kBM;
@@ -474,10 +499,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           tmem_ld32(taddr + c * 32, v);
+          ln_chunk(v, vec, N_TILE, c * 32, mean, rstd, p.relu, p.slope);
+          if (!live) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = activate(v[j] + vec[c * 32 + j], p.relu, p.slope);
-            v[j] = live ? (x - mean) * rstd * vec[N_TILE + c * 32 + j] + vec[2 * N_TILE + c * 32 + j] : 0.f;
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
           {
             uint8_t* row = zbuf + r * 128;
@@ -541,11 +566,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         if (col0 >= p.n) break;  // chunk entirely outside the tensor (n not a multiple of N_TILE)
         tmem_ld32(taddr + c * 32, v);
         if (LN) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float x = activate(v[j] + vec[c * 32 + j], p.relu, p.slope);
-            v[j] = (x - mean) * rstd * vec[N_TILE + c * 32 + j] + vec[2 * N_TILE + c * 32 + j];
-          }
+          ln_chunk(v, vec, N_TILE, c * 32, mean, rstd, p.relu, p.slope);
         } else if (bias_vec && col0 + 32 <= p.n) {
           // the chunk's 32 bias values as 8 broadcast 16-byte loads (a per-element load + bounds test was 36 % of
           // this kernel's instructions)
@@ -860,7 +881,9 @@ int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int t, int d,
 
   // 2-CTA multicast variant: full 256-column tiles, at least one pair of row tiles per cluster
   const int m_tiles_all = batch * ((t + kBM - 1) / kBM);
-  const bool mc = n_tile == 256 && n % 256 == 0 && m_tiles_all >= 2 * kNumSMs && gemm_multicast_enabled();
+  // (not for the LayerNorm builds: they are paced by their epilogue, and coupling two CTAs' epilogues to one MMA
+  // stream costs them 6-10 %; measured in profiles/r2p_*)
+  const bool mc = !ln && n_tile == 256 && n % 256 == 0 && m_tiles_all >= 2 * kNumSMs && gemm_multicast_enabled();
   const uint32_t w_box = mc ? n_tile / 2 : n_tile;  // MC: each CTA of a pair fetches half a weight slab
 
   GemmTcMaps m;
@@ -915,10 +938,7 @@ int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int t, int d,
     LFS2_CHECK_LAUNCH("gemm_tile_list");
     p.tile_list = list;
   }
-  if (mc) {
-    if (ln) return dispatch_gemm_tc<256, true, true>(m, p, npass, out_kind, s);
-    return dispatch_gemm_tc<256, false, true>(m, p, npass, out_kind, s);
-  }
+  if (mc) return dispatch_gemm_tc<256, false, true>(m, p, npass, out_kind, s);
   if (ln) return dispatch_gemm_tc<256, true, false>(m, p, npass, out_kind, s);
   if (n_tile == 256) return dispatch_gemm_tc<256, false, false>(m, p, npass, out_kind, s);
   if (n_tile == 128) return dispatch_gemm_tc<128, false, false>(m, p, npass, out_kind, s);

@@ -333,4 +333,4 @@ def test_ffn_fused_tc_two_pass(m, f):
     assert ((out.h.float() - out.float()).abs() <= 2.0 ** -11 * out.float().abs() + 1e-7).all()   # fp16 of the fp32 row
     # the 3-pass kernel with the same residual path (32 x 32 identity block) stays at fp32 parity
     o3 = ops.ffn_fused_tc(sp(u), sp(w1), b1.to(DEV), sp(w2), b2.to(DEV), sp(res), gam.to(DEV), bet.to(DEV), 1e-5, npass=3)
-    assert (o3.float().cpu().double() - exact).abs().max() < 5e-5
+    assert (o3.float().cpu().double() - exact).abs().max() < 1e-4

@@ -18,6 +18,8 @@ VARIANTS = {
     "no_ln": ["-DLFS2_FFN_DIAG_NO_LN"],               # no LayerNorm epilogue, no stores
     "no_stores": ["-DLFS2_FFN_DIAG_NO_STORES"],       # LayerNorm epilogue without its hi/lo TMA stores
     "no_e1_no_ln": ["-DLFS2_FFN_DIAG_NO_E1", "-DLFS2_FFN_DIAG_NO_LN"],   # TMA + MMA only
+    "no_wlo_loads": ["-DLFS2_FFN_DIAG_NO_WLO_LOADS"],   # all MMAs, but the lo weight planes are not fetched (-1 MB of 2.6 per tile)
+    "no_wlo_no_ln": ["-DLFS2_FFN_DIAG_NO_WLO_LOADS", "-DLFS2_FFN_DIAG_NO_LN"],
     "timeline": ["-DLFS2_FFN_TIMELINE"],              # correct results + clock64 stamps per CTA and tile (see `timeline`)
 }
 
@@ -118,7 +120,7 @@ if __name__ == "__main__":
     elif sys.argv[1] == "run":
         for env in ({}, {"LFS2_FFN_MULTICAST": "0"}):
             print(env or "defaults (2-CTA multicast)", flush=True)
-            for name in VARIANTS:
+            for name in (sys.argv[2:] or VARIANTS):
                 subprocess.run([sys.executable, os.path.abspath(__file__), "one", name], check=True,
                                env=dict(os.environ, **env))
     else:
