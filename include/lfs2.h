@@ -439,6 +439,15 @@ LFS2_API int lfs2_length_regulate_bwd(const float* dout, const int64_t* cum, flo
  * rows with idx == skip_idx get none (padding_idx; pass -1 for no padding row). */
 LFS2_API int lfs2_embedding_bwd(const float* dx, const int64_t* idx, float* demb, int m, int d, int nrows_emb,
                                 long long skip_idx, void* stream);
+/* Decoder input in one pass (model.py:263-266 for the LAST frame-level variance encoder + fastspeech2.py:716-721 +
+ * lfs2_split_bf16): y[b,t,:] = ((x[b,t,:] + emb[bucket(val[b,t]),:]) + pe[t,:]) + spk[b,:], written only as bf16 hi/lo
+ * planes (and, out_f16 != NULL, one fp16 plane): the operands of the first decoder block.  Arguments val .. acc_mode as
+ * in lfs2_bucket_embed_add (acc receives / accumulates the embedding term); emb == NULL skips the bucket term.  Same
+ * operation order as lfs2_bucket_embed_add -> lfs2_add_pe_spk -> lfs2_split_bf16, so the planes are bit-identical. */
+LFS2_API int lfs2_decoder_input_planes(const float* x, const float* val, float std, float mean, const float* bins,
+                                       int nbins, const float* emb, const int64_t* idx_forced, int64_t* idx_out,
+                                       float* acc, int acc_mode, const float* pe, const float* spk, int batch, int t,
+                                       int d, void* out_hi, void* out_lo, void* out_f16, void* stream);
 /* out-of-place lfs2_bucket_embed_add: x[m,:] = x_in[m,:] + emb[idx,:] (the input stays intact for
  * the predictor's backward pass) */
 LFS2_API int lfs2_bucket_embed_add_oop(const float* x_in, float* x, const float* val, float std, float mean,

@@ -93,6 +93,7 @@ SIGNATURES = {
     "lfs2_attention_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "lfs2_length_regulate_bwd": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "lfs2_embedding_bwd": [_vp, _vp, _vp, _i, _i, _i, _ll, _vp],
+    "lfs2_decoder_input_planes": [_vp, _vp, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp],
     "lfs2_bucket_embed_add_oop": [_vp, _vp, _vp, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "lfs2_rowdot_mask_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "lfs2_sum_over_time": [_vp, _vp, _i, _i, _i, _vp],

@@ -322,6 +322,82 @@ __global__ void bucket_embed_add_kernel(const float4* x_in, float4* x, const flo
   }
 }
 
+__device__ __forceinline__ void split_pack2_ew(float a, float b, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
+  const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - bh), "f"(a - ah));
+}
+
+// Decoder input in ONE pass: y = ((x + emb[bucket(val)]) + pe[t]) + spk[b], written only as the operand planes of the
+// first decoder block's tensor-core GEMMs (bf16 hi/lo, optionally the fp16 plane of the 2-pass recipe) -- the last
+// frame-level variance encoder's embedding add (model.py:263-266), the positional / speaker add (fastspeech2.py:716-
+// 721) and lfs2_split_bf16 fused: 4 + 6 bytes per element instead of 26.  Same operation order as the three kernels it
+// replaces, so the planes are bit-identical.  emb == NULL: no bucket term.  One warp per row.
+__global__ void decoder_input_planes_kernel(const float4* __restrict__ x, const float* __restrict__ val, float stdv,
+                                            float meanv, const float* __restrict__ bins, int nb,
+                                            const float4* __restrict__ emb, const int64_t* __restrict__ idx_forced,
+                                            int64_t* __restrict__ idx_out, float4* __restrict__ acc, int acc_mode,
+                                            const float4* __restrict__ pe, const float4* __restrict__ spk, int t,
+                                            uint2* __restrict__ out_hi, uint2* __restrict__ out_lo,
+                                            uint2* __restrict__ out_f16, int m, int d4) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= m) return;
+  const float4* e = nullptr;
+  if (emb) {
+    int idx;
+    if (idx_forced) {
+      idx = (int)idx_forced[row];
+    } else {
+      float v = __fadd_rn(__fmul_rn(val[row], stdv), meanv);
+      int lo = 0, hi = nb;
+      while (lo < hi) {
+        int mid = lo + ((hi - lo) >> 1);
+        if (!(bins[mid] >= v)) lo = mid + 1;
+        else hi = mid;
+      }
+      idx = lo;
+    }
+    if (lane == 0 && idx_out) idx_out[row] = idx;
+    e = emb + (size_t)idx * d4;
+  }
+  const float4* xr = x + (size_t)row * d4;
+  const float4* pr = pe + (size_t)(row % t) * d4;
+  const float4* sr = spk + (size_t)(row / t) * d4;
+  float4* ar = acc ? acc + (size_t)row * d4 : nullptr;
+  for (int c = lane; c < d4; c += 32) {
+    float4 xv = xr[c];
+    if (e) {
+      const float4 ev = e[c];
+      xv.x += ev.x; xv.y += ev.y; xv.z += ev.z; xv.w += ev.w;
+      if (acc_mode == 1) {
+        ar[c] = ev;
+      } else if (acc_mode == 2) {
+        float4 av = ar[c];
+        av.x += ev.x; av.y += ev.y; av.z += ev.z; av.w += ev.w;
+        ar[c] = av;
+      }
+    }
+    const float4 p = pr[c], sp = sr[c];
+    xv.x = (xv.x + p.x) + sp.x;
+    xv.y = (xv.y + p.y) + sp.y;
+    xv.z = (xv.z + p.z) + sp.z;
+    xv.w = (xv.w + p.w) + sp.w;
+    const size_t o = (size_t)row * d4 + c;
+    uint2 h, l;
+    split_pack2_ew(xv.x, xv.y, h.x, l.x);
+    split_pack2_ew(xv.z, xv.w, h.y, l.y);
+    out_hi[o] = h;
+    out_lo[o] = l;
+    if (out_f16) {
+      uint2 f;
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(f.x) : "f"(xv.y), "f"(xv.x));
+      asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(f.y) : "f"(xv.w), "f"(xv.z));
+      out_f16[o] = f;
+    }
+  }
+}
+
 // PriorEmbedding (reference model.py:146-164): out[b,:] = relu(emb[bucketize(prior[b], bins), :]); one warp per utterance
 __global__ void prior_embed_kernel(const float* __restrict__ prior, const float* __restrict__ bins, int nb,
                                    const float4* __restrict__ emb, float4* __restrict__ out, int64_t* __restrict__ idx_out,
@@ -351,11 +427,6 @@ __global__ void prior_embed_kernel(const float* __restrict__ prior, const float*
 // slides NT consecutive frames of its 4 channels through registers: the K tap weights live in
 // registers and the (input row, output row) -> tap mapping is resolved at compile time, so the
 // inner loop is LDS.128 + FFMA only.  Results leave as fp32 and/or bf16 hi/lo planes.
-__device__ __forceinline__ void split_pack2_ew(float a, float b, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(b), "f"(a));
-  const float ah = __uint_as_float(hi << 16), bh = __uint_as_float(hi & 0xffff0000u);
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - bh), "f"(a - ah));
-}
 
 constexpr int kDwCh4 = 64;    // float4 channel groups per CTA (256 channels)
 
@@ -800,6 +871,28 @@ int lfs2_bucket_embed_add_oop(const float* x_in, float* x, const float* val, flo
       (float4*)acc,
       acc ? acc_mode : 0, m, d / 4);
   LFS2_CHECK_LAUNCH("bucket_embed_add");
+  return LFS2_OK;
+}
+
+int lfs2_decoder_input_planes(const float* x, const float* val, float stdv, float meanv, const float* bins, int nbins,
+                              const float* emb, const int64_t* idx_forced, int64_t* idx_out, float* acc, int acc_mode,
+                              const float* pe, const float* spk, int batch, int t, int d, void* out_hi, void* out_lo,
+                              void* out_f16, void* stream) {
+  LFS2_REQUIRE(x && pe && spk && out_hi && out_lo, LFS2_ERR_INVALID_ARG, "decoder_input_planes: null pointer");
+  LFS2_REQUIRE(!emb || idx_forced || (val && bins), LFS2_ERR_INVALID_ARG, "decoder_input_planes: the bucket term needs val + bins or forced indices");
+  if (batch == 0 || t == 0) return LFS2_OK;
+  LFS2_REQUIRE(batch > 0 && t > 0 && d > 0 && d % 4 == 0 && (!emb || nbins >= 1), LFS2_ERR_UNSUPPORTED, "decoder_input_planes: bad shape");
+  LFS2_REQUIRE((long long)batch * t <= 0x7fffffffLL / 32, LFS2_ERR_UNSUPPORTED, "decoder_input_planes: too many rows");
+  LFS2_REQUIRE(acc_mode == 0 || (acc && emb), LFS2_ERR_INVALID_ARG, "decoder_input_planes: acc_mode without acc / emb");
+  LFS2_REQUIRE(aligned16(x) && aligned16(emb) && aligned16(acc) && aligned16(pe) && aligned16(spk) && aligned16(out_hi) &&
+                   aligned16(out_lo) && aligned16(out_f16),
+               LFS2_ERR_INVALID_ARG, "decoder_input_planes: pointers must be 16-byte aligned");
+  const int m = batch * t, threads = 256;
+  decoder_input_planes_kernel<<<ceil_div((long long)m * 32, threads), threads, 0, (cudaStream_t)stream>>>(
+      (const float4*)x, val, stdv, meanv, bins, nbins - 1, (const float4*)emb, idx_forced, idx_out, (float4*)acc,
+      acc ? acc_mode : 0, (const float4*)pe, (const float4*)spk, t, (uint2*)out_hi, (uint2*)out_lo, (uint2*)out_f16, m,
+      d / 4);
+  LFS2_CHECK_LAUNCH("decoder_input_planes");
   return LFS2_OK;
 }
 

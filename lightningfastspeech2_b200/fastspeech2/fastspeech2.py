@@ -81,15 +81,21 @@ class TransformerStack(nn.Module):
     def supports_row_limit(self, d):
         return all(mod.supports_row_limit(d) for mod in self.layers)
 
+    def tc_capable(self, d):
+        return len(self.layers) > 0 and all(mod.tc_capable(d) for mod in self.layers)
+
+    def wants_f16_plane(self, d):
+        """the first block's QKV GEMM runs the 2-pass recipe: its input Planes should carry the fp16 plane"""
+        first = self.layers[0] if len(self.layers) else None
+        return first is not None and first.compute_mode == "fp32" and "qkv" in first.two_pass_sites and d == 256
+
     def forward(self, src, mask=None, src_key_padding_mask=None, return_planes=False, row_limit=None):
         """return_planes=True (tensor-core path only) hands the result back as bf16 hi/lo planes,
         the operand format of the next GEMM, instead of materialising an fp32 tensor.
         row_limit = (lengths, extra): rows at or after roundup128(lengths[b] + extra) are neither computed nor
         written by any layer (FastSpeech2.skip_pad_rows)."""
         if mask is None and all(mod.tc_capable(src.shape[-1]) for mod in self.layers):
-            first = self.layers[0] if len(self.layers) else None
-            xp = ops.planes_of(src, want_f16=first is not None and first.compute_mode == "fp32"
-                               and "qkv" in first.two_pass_sites and src.shape[-1] == 256)
+            xp = src if isinstance(src, ops.Planes) else ops.planes_of(src, want_f16=self.wants_f16_plane(src.shape[-1]))
             if row_limit is not None:
                 row_limit = (row_limit[0], row_limit[1], {})  # one tile list per kernel family for the whole stack
             for i, mod in enumerate(self.layers):
@@ -99,6 +105,8 @@ class TransformerStack(nn.Module):
             return xp if return_planes else ops.merge_planes(xp)
         if row_limit is not None:
             raise NotImplementedError("row limits need the tensor-core path")
+        if isinstance(src, ops.Planes):
+            raise TypeError("a Planes input needs the tensor-core path")
         out = src
         for mod in self.layers:
             out = mod(out, src_mask=mask, src_key_padding_mask=src_key_padding_mask)
@@ -415,9 +423,14 @@ class FastSpeech2(_Base):
         dev, hp = self.device, self.hparams
         pe, spk, src_mask = self.positional_encoding.pe, st["spk"], st["src_mask"]
         self.variance_adaptor.need_out_val = hasattr(self, "fastdiff_linear")
+        tc_decoder = (self.compute_mode != "simt" and hp.decoder_hidden % 32 == 0 and hp.n_mels % 16 == 0
+                      and self.decoder.tc_capable(hp.decoder_hidden) and not (self.training and hp.decoder_dropout > 0))
+        # tensor-core decoder: its input is only ever read as Planes -- the last variance embedding add, the positional /
+        # speaker add and the plane split are one kernel (ops.decoder_input_planes), no fp32 tensor in between
+        tail = (pe, spk, self.decoder.wants_f16_plane(hp.decoder_hidden)) if tc_decoder else None
         variance_output = self.variance_adaptor.expand(st["enc"], st, targets, inference=inference, force=force,
-                                                       control=control, scan=scan, frames=frames)
-        output = ops.add_pe_spk_(variance_output["x"], pe, spk)
+                                                       control=control, scan=scan, frames=frames, tail=tail)
+        output = variance_output["x_planes"] if tail is not None else ops.add_pe_spk_(variance_output["x"], pe, spk)
         tgt_mask = variance_output["tgt_mask"]
         if self._skips_pad_rows(inference):
             # PAD rows farther than the decoder's conv halo past an utterance's end: never computed, never written

@@ -530,11 +530,21 @@ class VarianceEncoder(nn.Module):
         self.mean = mean
         self.std = std
 
-    def encode_(self, x, tgt, mask, control=1.0, acc=None, acc_init=False, forced_idx=None, want_idx=False):
+    def encode_(self, x, tgt, mask, control=1.0, acc=None, acc_init=False, forced_idx=None, want_idx=False, tail=None):
         """Fused form used by VarianceAdaptor: predicts, bucketizes and does ``x += emb``
-        in place (and ``acc (+)= emb``).  Returns (prediction, bucket indices or None)."""
+        in place (and ``acc (+)= emb``).  Returns (prediction, bucket indices or None).
+        tail = (pe, spk, want_f16): this is the last encoder before the decoder -- x is left untouched and
+        ((x + emb) + pe) + spk is returned as a third value, the decoder's input Planes (ops.decoder_input_planes)."""
         prediction = self.predictor(x, mask)
         val = prediction if tgt is None else tgt.to(device=x.device, dtype=torch.float32).contiguous()
+        if tail is not None:
+            planes, idx = ops.decoder_input_planes(
+                x, tail[0], tail[1], want_f16=tail[2],
+                bucket=dict(val=val, std=self.std, mean=self.mean, bins=self.bins, emb=self.embedding.weight,
+                            idx_forced=forced_idx, acc=acc, acc_init=acc_init, want_idx=want_idx))
+            if tgt is None and control != 1.0:
+                prediction = prediction * control
+            return prediction, idx, planes
         idx = ops.bucket_embed_add_(x, val, self.std, self.mean, self.bins, self.embedding.weight,
                                     idx_forced=forced_idx, acc=acc, acc_init=acc_init, want_idx=want_idx)
         if tgt is None and control != 1.0:
@@ -654,8 +664,11 @@ class VarianceAdaptor(nn.Module):
         return {"duration_prediction": duration_pred, "duration_rounded": duration_rounded, "tf_val": tf_val,
                 "x_phone": x, "out_phone": out_val, "phone_result": result}
 
-    def expand(self, x, st, targets, inference=False, oracles=[], force=None, control=None, scan=None, frames=None):
-        """second half (model.py:311-341): LengthRegulator, then the frame-level variance encoders in sequence"""
+    def expand(self, x, st, targets, inference=False, oracles=[], force=None, control=None, scan=None, frames=None,
+               tail=None):
+        """second half (model.py:311-341): LengthRegulator, then the frame-level variance encoders in sequence.
+        tail = (pe, spk, want_f16): the caller only needs the decoder's input ((x + pe) + spk) as Planes -- the last
+        embedding add, the positional / speaker add and the plane split run as one kernel; result["x_planes"]."""
         force = force or {}
         control = control or {}
         result = dict(st.get("phone_result") or {})
@@ -676,6 +689,8 @@ class VarianceAdaptor(nn.Module):
         else:
             out_val = torch.empty_like(x) if len(self.variances) else None
         nframe = 0
+        frame_vars = [i for i in range(len(self.variances)) if self.variance_levels[i] == "frame"]
+        x_planes = None
         for i, var in enumerate(self.variances):
             if self.variance_levels[i] != "frame":
                 continue
@@ -684,16 +699,22 @@ class VarianceAdaptor(nn.Module):
             forced = force.get("bucket_idx", {}).get(var)
             if forced is not None:
                 forced = self._fit_forced(forced.to(x.device), x.shape[1], self.encoders[var])
-            pred, idx = self.encoders[var].encode_(
+            enc = self.encoders[var].encode_(
                 x, tgt, tgt_mask, control.get(var, 1.0), acc=out_val, acc_init=(nframe == 0 and not have_acc),
                 forced_idx=forced,
-                want_idx=force.get("want_idx", False))
+                want_idx=force.get("want_idx", False), tail=tail if i == frame_vars[-1] else None)
+            pred, idx = enc[0], enc[1]
+            if len(enc) > 2:
+                x_planes = enc[2]
             nframe += 1
             result[f"variances_{var}"] = pred
             if idx is not None:
                 result[f"_bucket_{var}"] = idx
 
+        if tail is not None and x_planes is None:  # no frame-level variance: positional / speaker add + split only
+            x_planes, _ = ops.decoder_input_planes(x, tail[0], tail[1], want_f16=tail[2])
         result["x"] = x
+        result["x_planes"] = x_planes
         result["duration_prediction"] = duration_pred
         result["duration_rounded"] = duration_rounded
         result["tgt_mask"] = tgt_mask

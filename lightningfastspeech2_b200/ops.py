@@ -225,6 +225,34 @@ def bucket_embed_add_(x, val, std, mean, bins, emb, idx_forced=None, acc=None, a
     return idx_out
 
 
+def decoder_input_planes(x, pe, spk, bucket=None, want_f16=False):
+    """((x + emb[bucket(val)]) + pe) + spk as Planes (no fp32 result): lfs2_decoder_input_planes.
+    bucket = None or dict(val, std, mean, bins, emb, idx_forced=None, acc=None, acc_init=False, want_idx=False) -- the
+    arguments of bucket_embed_add_ for the last frame-level variance encoder.  -> (Planes, bucket indices or None)"""
+    _chk(x, torch.float32, "x", 3)
+    b, t, d = x.shape
+    if t > pe.shape[-2]:
+        raise ValueError(f"sequence length {t} exceeds the positional table ({pe.shape[-2]})")
+    out = _empty_planes(x.shape, x.device)
+    if want_f16:
+        out.h = torch.empty(x.shape, device=x.device, dtype=torch.float16)
+    k = bucket or {}
+    forced, acc = k.get("idx_forced"), k.get("acc")
+    if bucket is not None:
+        if forced is not None:
+            _chk(forced, torch.int64, "forced bucket indices")
+        else:
+            _chk(k["val"], torch.float32, "variance values")
+    idx_out = torch.empty(b, t, device=x.device, dtype=torch.int64) if k.get("want_idx") else None
+    mode = 0 if acc is None else (1 if k.get("acc_init") else 2)
+    emb = k.get("emb")
+    _launch("lfs2_decoder_input_planes", _p(x), _p(k.get("val")), float(k.get("std", 1.0)), float(k.get("mean", 0.0)),
+            _p(k.get("bins")), emb.shape[0] if emb is not None else 0, _p(emb), _p(forced), _p(idx_out), _p(acc), mode,
+            _p(pe), _p(spk), b, t, d, _p(out.hi), _p(out.lo), _p(out.h), _s(), tag="lfs2_decoder_input_planes",
+            nbytes=b * t * d * (4.0 + 4.0 + (2.0 if want_f16 else 0.0) + (4.0 if acc is not None else 0.0)))
+    return out, idx_out
+
+
 def prior_embed(prior, bins, emb):
     """PriorEmbedding: prior (B) fp32 -> (relu(emb[bucketize(prior)]) (B,d), bucket indices (B) int64)"""
     _chk(prior, torch.float32, "prior values", 1)

@@ -307,3 +307,37 @@ def test_fused_predictor_layers_match_the_unfused_stack_and_the_oracle(mode, tol
         z = F.layer_norm(torch.relu(u), (256,), ln.weight.double().cpu(), ln.bias.double().cpu(), ln.eps)
     ref = F.linear(z, vp.linear.weight.double().cpu(), vp.linear.bias.double().cpu()).squeeze(-1).masked_fill(mask.cpu(), 0)
     assert (fused.cpu().double() - ref).abs().max() < (1e-4 if mode == "fp32" else 5e-2)
+
+
+@pytest.mark.parametrize("with_bucket,with_acc", [(True, False), (True, True), (False, False)])
+def test_decoder_input_planes_equals_the_three_kernels_it_replaces(with_bucket, with_acc):
+    """ops.decoder_input_planes == bucket_embed_add_ -> add_pe_spk_ -> split_bf16 bit for bit (planes, fp16 plane, bucket
+    indices, accumulated embedding term)"""
+    from lightningfastspeech2_b200 import ops
+
+    g = torch.Generator().manual_seed(5)
+    b, t, d, nb = 3, 77, 256, 32
+    x = torch.randn(b, t, d, generator=g).to(DEV)
+    pe = torch.randn(128, d, generator=g).to(DEV)
+    spk = torch.randn(b, d, generator=g).to(DEV)
+    val = torch.randn(b, t, generator=g).to(DEV)
+    bins = torch.linspace(-2, 2, nb - 1).to(DEV)
+    emb = torch.randn(nb, d, generator=g).to(DEV)
+    acc0 = torch.randn(b, t, d, generator=g).to(DEV)
+    ref_x, ref_acc = x.clone(), acc0.clone()
+    idx_ref = None
+    if with_bucket:
+        idx_ref = ops.bucket_embed_add_(ref_x, val, 1.5, 0.25, bins, emb, acc=ref_acc if with_acc else None, want_idx=True)
+    ops.add_pe_spk_(ref_x, pe, spk)
+    ref = ops.split_bf16(ref_x, want_f16=True)
+    acc = acc0.clone()
+    bucket = dict(val=val, std=1.5, mean=0.25, bins=bins, emb=emb, acc=acc if with_acc else None, want_idx=True) \
+        if with_bucket else None
+    keep = x.clone()
+    got, idx = ops.decoder_input_planes(x, pe, spk, bucket=bucket, want_f16=True)
+    assert torch.equal(x, keep)                                   # the fp32 input is not modified
+    assert torch.equal(got.hi, ref.hi) and torch.equal(got.lo, ref.lo) and torch.equal(got.h, ref.h)
+    if with_bucket:
+        assert torch.equal(idx, idx_ref)
+    if with_acc:
+        assert torch.equal(acc, ref_acc)
