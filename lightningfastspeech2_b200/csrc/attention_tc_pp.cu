@@ -75,6 +75,7 @@ __device__ __forceinline__ uint32_t p_pack16(float a, float b, int fmt) {
 struct PpParams {
   const uint8_t* kpm;   // (B, T) 1 = PAD, or null
   const int* kend;      // (B): 1 + index of the last non-PAD key
+  const int* order;     // (B): utterances by descending kend -- the long ones start first, the grid's tail is short work
   __nv_bfloat16* ctx_hi;
   __nv_bfloat16* ctx_lo;
   float* ctx_f32;
@@ -98,7 +99,7 @@ attention_tc_pp_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kPQ, h = blockIdx.y, b = blockIdx.z;
+  const int q0 = blockIdx.x * kPQ, h = blockIdx.y, b = __ldg(p.order + blockIdx.z);
   if (p.row_limit && q0 >= __ldg(p.row_limit + b) + p.limit_extra) return;
   const int kend = p.kend[b];
   const int ntiles = (kend + kPK - 1) / kPK;
@@ -382,6 +383,7 @@ int launch_attention_tc_pp(const void* qkv, int f16, const uint8_t* kpm, const i
   PpParams p;
   p.kpm = kpm;
   p.kend = kend;
+  p.order = kend + batch;  // second half of the workspace (attn_order_kernel)
   p.ctx_hi = (__nv_bfloat16*)ctx_hi;
   p.ctx_lo = (__nv_bfloat16*)ctx_lo;
   p.ctx_f32 = ctx_f32;
