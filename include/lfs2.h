@@ -448,6 +448,31 @@ LFS2_API int lfs2_decoder_input_planes(const float* x, const float* val, float s
                                        int nbins, const float* emb, const int64_t* idx_forced, int64_t* idx_out,
                                        float* acc, int acc_mode, const float* pe, const float* spk, int batch, int t,
                                        int d, void* out_hi, void* out_lo, void* out_f16, void* stream);
+/* ---- stochastic duration predictor, inference direction (third_party/stochastic_duration_predictor/
+ * sdp.py:11-164, 254-269, 330-349, transforms.py:50-212; model.py:299-309, 463-480) ----------------------------------
+ * Phoneme-level, channels-last (B, T, C) fp32; the 1x1 convolutions between these kernels are lfs2_linear.
+ * lfs2_sdp_dwconv: depthwise Conv1d with a tap dilation, rows whose pad_mask byte is non-zero read as zeros (x * x_mask,
+ *   sdp.py:62); wt (ksize, c) tap-major.
+ * lfs2_sdp_ln_gelu: out = [res +] gelu_erf(LayerNorm_c(y; gamma, beta, eps))   (sdp.py:63-69).
+ * lfs2_sdp_flow_pre: h[m,:] = z[m, channel] * w[:] + bias[:] + g[m,:]          (sdp.py:141-143 with the conditioning).
+ * lfs2_sdp_spline_inverse: one spline coupling flow in reverse, in place on the flow state z (m, 2): channel x1_channel
+ *   goes through the inverse of the 10-bin monotone rational-quadratic spline on [-tail_bound, tail_bound] (identity
+ *   outside) whose 29 parameters are h[m, 0:29] (row stride h_stride; widths and heights divided by sqrt(hidden_channels)),
+ *   PAD rows are zeroed (sdp.py:147-164, transforms.py:50-212 with inverse=True).
+ * lfs2_sdp_affine_reverse: z[m, c ^ flip] = (z[m, c ^ flip] - translation[c]) * exp(-log_scale[c]), PAD rows zero (sdp.py:93-95).
+ * lfs2_sdp_durations: dur = int32(clamp(ceil(exp(logw + 1e-9)), 0)), 0 where logw == 0, and the all-ones guard (model.py:302-309). */
+LFS2_API int lfs2_sdp_dwconv(const float* x, const uint8_t* pad_mask, const float* wt, const float* bias, float* out,
+                             int batch, int t, int c, int ksize, int dilation, void* stream);
+LFS2_API int lfs2_sdp_ln_gelu(const float* y, const float* gamma, const float* beta, float eps, const float* res, float* out,
+                              int m, int c, void* stream);
+LFS2_API int lfs2_sdp_flow_pre(const float* z, int channel, const float* w, const float* bias, const float* g, float* out,
+                               int m, int c, void* stream);
+LFS2_API int lfs2_sdp_spline_inverse(float* z, int x1_channel, const float* h, int h_stride, const uint8_t* pad_mask,
+                                     int hidden_channels, float tail_bound, int m, void* stream);
+LFS2_API int lfs2_sdp_affine_reverse(float* z, const float* translation, const float* log_scale, const uint8_t* pad_mask,
+                                     int flip, int m, void* stream);
+LFS2_API int lfs2_sdp_durations(const float* logw, const uint8_t* src_mask, int32_t* dur, int batch, int tp, void* stream);
+
 /* out-of-place lfs2_bucket_embed_add: x[m,:] = x_in[m,:] + emb[idx,:] (the input stays intact for
  * the predictor's backward pass) */
 LFS2_API int lfs2_bucket_embed_add_oop(const float* x_in, float* x, const float* val, float std, float mean,

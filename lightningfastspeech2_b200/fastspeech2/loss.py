@@ -38,8 +38,12 @@ class FastSpeech2Loss(nn.Module):
         for name in list(variance_losses) + [mel_loss, duration_loss]:
             if name not in ("mse", "l1"):
                 raise NotImplementedError(f"loss '{name}'")
-        if duration_stochastic or fastdiff_loss is not None or fastdiff_variances:
-            raise NotImplementedError("stochastic-duration / FastDiff losses")
+        if fastdiff_loss is not None or fastdiff_variances:
+            raise NotImplementedError("FastDiff losses")
+        # the stochastic duration predictor's loss is its own negative log-likelihood (reference loss.py:181-187), i.e. the
+        # training direction of the flows, which the CUDA path does not implement: such a model synthesises, but
+        # calling the loss raises
+        self.duration_stochastic = bool(duration_stochastic)
         self.variances = list(variances)
         self.variance_levels = list(variance_levels)
         self.variance_transforms = list(variance_transforms)
@@ -50,6 +54,8 @@ class FastSpeech2Loss(nn.Module):
         self.loss_alphas = dict(loss_alphas or {})
 
     def forward(self, result, target, frozen_components=()):
+        if self.duration_stochastic:
+            raise NotImplementedError("loss of the stochastic duration predictor (training direction of the flows)")
         mel = result["mel"]
         if not mel.is_cuda:
             raise ops._lib.Lfs2Error("FastSpeech2Loss needs CUDA results: there is no CPU path")

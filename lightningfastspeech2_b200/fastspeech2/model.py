@@ -440,6 +440,163 @@ class VarianceConvolutionLayer(nn.Module):
         return ops.add_layernorm(h, None, ln.weight, ln.bias, ln.eps)
 
 
+# ---- stochastic duration predictor, inference direction ---------------------------------------------------
+class _LayerNorm2(nn.Module):
+    """parameter container of third_party/stochastic_duration_predictor/normalization.py:5-28 (keys gamma / beta)"""
+
+    def __init__(self, channels, eps=1e-5):
+        super().__init__()
+        self.eps = eps
+        self.gamma = nn.Parameter(torch.ones(channels))
+        self.beta = nn.Parameter(torch.zeros(channels))
+
+
+class DilatedDepthSeparableConv(nn.Module):
+    """sdp.py:11-70: num_layers x [depthwise conv (dilation k^i) -> LN -> GELU -> 1x1 conv -> LN -> GELU -> + x]"""
+
+    def __init__(self, channels, kernel_size, num_layers, dropout_p=0.0):
+        super().__init__()
+        self.num_layers, self.p_drop = num_layers, dropout_p
+        self.convs_sep, self.convs_1x1 = nn.ModuleList(), nn.ModuleList()
+        self.norms_1, self.norms_2 = nn.ModuleList(), nn.ModuleList()
+        for i in range(num_layers):
+            dil = kernel_size ** i
+            self.convs_sep.append(nn.Conv1d(channels, channels, kernel_size, groups=channels, dilation=dil,
+                                            padding=(kernel_size * dil - dil) // 2))
+            self.convs_1x1.append(nn.Conv1d(channels, channels, 1))
+            self.norms_1.append(_LayerNorm2(channels))
+            self.norms_2.append(_LayerNorm2(channels))
+        self._pack = _PackCache()
+
+    def _build_pack(self):
+        return [(c.weight[:, 0, :].t().contiguous(), p.weight[:, :, 0].contiguous()) for c, p in
+                zip(self.convs_sep, self.convs_1x1)]
+
+    def forward(self, x, pad_mask, g=None):
+        """x (B,T,C) fp32 channels-last [, already x + g: the caller adds the conditioning]; PAD rows are read as zeros by
+        every depthwise conv; the reference's trailing `* x_mask` only touches PAD rows, which nothing reads afterwards"""
+        if g is not None:
+            raise NotImplementedError("pass x + g (lfs2_sdp_flow_pre adds the conditioning)")
+        _require_inference(self, self.p_drop, "DilatedDepthSeparableConv")
+        packs = self._pack.get([c.weight for c in self.convs_sep] + [c.weight for c in self.convs_1x1], self._build_pack)
+        for i in range(self.num_layers):
+            sep, pw = self.convs_sep[i], self.convs_1x1[i]
+            y = ops.sdp_dwconv(x, pad_mask, packs[i][0], sep.bias, sep.dilation[0])
+            y = ops.sdp_ln_gelu(y, self.norms_1[i].gamma, self.norms_1[i].beta, self.norms_1[i].eps)
+            y = ops.linear(y, packs[i][1], pw.bias, tag="sdp_1x1")
+            x = ops.sdp_ln_gelu(y, self.norms_2[i].gamma, self.norms_2[i].beta, self.norms_2[i].eps, res=x)
+        return x
+
+
+class ElementwiseAffine(nn.Module):
+    """sdp.py:73-95 (parameter container; the reverse direction is lfs2_sdp_affine_reverse)"""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.translation = nn.Parameter(torch.zeros(channels, 1))
+        self.log_scale = nn.Parameter(torch.zeros(channels, 1))
+
+
+class ConvFlow(nn.Module):
+    """sdp.py:98-164: spline coupling flow; reverse direction only"""
+
+    def __init__(self, in_channels, hidden_channels, kernel_size, num_layers, num_bins=10, tail_bound=5.0):
+        super().__init__()
+        if num_bins != 10 or in_channels != 2:
+            raise NotImplementedError("the spline kernel is built for 2 channels and 10 bins (the reference's only use)")
+        self.num_bins, self.tail_bound, self.hidden_channels = num_bins, tail_bound, hidden_channels
+        self.half_channels = in_channels // 2
+        self.pre = nn.Conv1d(self.half_channels, hidden_channels, 1)
+        self.convs = DilatedDepthSeparableConv(hidden_channels, kernel_size, num_layers, dropout_p=0.0)
+        self.proj = nn.Conv1d(hidden_channels, self.half_channels * (num_bins * 3 - 1), 1)
+        self.proj.weight.data.zero_()
+        self.proj.bias.data.zero_()
+        self._pack = _PackCache()
+
+    def _build_pack(self):
+        n = self.proj.weight.shape[0]                 # 29 spline parameters, padded to 32 output columns for lfs2_linear
+        w = torch.zeros(32, self.hidden_channels, device=self.proj.weight.device)
+        b = torch.zeros(32, device=self.proj.weight.device)
+        w[:n] = self.proj.weight[:, :, 0]
+        b[:n] = self.proj.bias
+        return {"pre_w": self.pre.weight[:, 0, 0].contiguous(), "proj_w": w, "proj_b": b}
+
+    def reverse_(self, z, flip, pad_mask, g):
+        """in place on the flow state z (B,T,2): logical channel 0 (physical `flip`) conditions, logical 1 is transformed"""
+        pk = self._pack.get([self.pre.weight, self.proj.weight, self.proj.bias], self._build_pack)
+        h = ops.sdp_flow_pre(z, flip, pk["pre_w"], self.pre.bias, g)
+        h = self.convs(h, pad_mask)
+        h = ops.linear(h, pk["proj_w"], pk["proj_b"], tag="sdp_proj")
+        ops.sdp_spline_inverse_(z, 1 ^ flip, h, pad_mask, self.hidden_channels, self.tail_bound)
+
+
+class StochasticDurationPredictor(nn.Module):
+    """sdp.py:167-349.  All parameters of the reference module exist (a reference checkpoint loads strictly); the CUDA path
+    implements the INFERENCE direction (reverse=True).  The training direction (variational dequantisation + the flows'
+    negative log-likelihood, sdp.py:271-328) raises NotImplementedError."""
+
+    def __init__(self, in_channels, hidden_channels, kernel_size, dropout_p, num_flows=4, cond_channels=0, language_emb_dim=0):
+        super().__init__()
+        if cond_channels or language_emb_dim:
+            raise NotImplementedError("conditioning / language embeddings (the reference's wrapper never passes them)")
+        self.hidden_channels = hidden_channels
+        self.pre = nn.Conv1d(in_channels, hidden_channels, 1)
+        self.convs = DilatedDepthSeparableConv(hidden_channels, kernel_size, num_layers=3, dropout_p=dropout_p)
+        self.proj = nn.Conv1d(hidden_channels, hidden_channels, 1)
+        self.flows = nn.ModuleList([ElementwiseAffine(2)] +
+                                   [ConvFlow(2, hidden_channels, kernel_size, num_layers=3) for _ in range(num_flows)])
+        self.post_pre = nn.Conv1d(1, hidden_channels, 1)
+        self.post_convs = DilatedDepthSeparableConv(hidden_channels, kernel_size, num_layers=3, dropout_p=dropout_p)
+        self.post_proj = nn.Conv1d(hidden_channels, hidden_channels, 1)
+        self.post_flows = nn.ModuleList([ElementwiseAffine(2)] +
+                                        [ConvFlow(2, hidden_channels, kernel_size, num_layers=3) for _ in range(num_flows)])
+        self._pack = _PackCache()
+
+    def forward(self, x, x_mask, dr=None, g=None, lang_emb=None, reverse=False, noise_scale=1.0, noise=None):
+        """x (B,T,C), x_mask (B,T) bool True = PAD -> log-durations (B,T).  noise (B,2,T): the torch.randn draw of
+        sdp.py:331 (injected for parity runs; drawn on the device otherwise)."""
+        if not reverse or dr is not None:
+            raise NotImplementedError("stochastic duration predictor: only the inference direction runs on the CUDA path")
+        if g is not None or lang_emb is not None:
+            raise NotImplementedError("conditioning inputs")
+        pk = self._pack.get([self.pre.weight, self.proj.weight],
+                            lambda: (self.pre.weight[:, :, 0].contiguous(), self.proj.weight[:, :, 0].contiguous()))
+        b, t, _ = x.shape
+        c = ops.linear(x.contiguous(), pk[0], self.pre.bias, tag="sdp_pre")
+        c = self.convs(c, x_mask)
+        c = ops.linear(c, pk[1], self.proj.bias, tag="sdp_proj")
+        if noise is None:
+            noise = torch.randn(b, 2, t, device=x.device, dtype=torch.float32)
+        z = (noise.to(x.device, torch.float32) * noise_scale).transpose(1, 2).contiguous()   # (B,T,2)
+        order = list(range(len(self.flows)))[::-1]
+        order = order[:-2] + [order[-1]]          # sdp.py:331: "remove a useless vflow"
+        flip = 0
+        for j in order:
+            flip ^= 1                              # torch.flip(z, [1]) before every flow: tracked, not materialised
+            if j == 0:
+                ea = self.flows[0]
+                ops.sdp_affine_reverse_(z, ea.translation, ea.log_scale, x_mask, flip)
+            else:
+                self.flows[j].reverse_(z, flip, x_mask, c)
+        return z[:, :, flip].contiguous()         # logical channel 0
+
+
+class StochasticDurationPredictorWrapper(nn.Module):
+    """reference model.py:463-480 (same constructor; `nlayers` is the number of flows, as in the reference's call)."""
+
+    def __init__(self, nlayers, in_channels, filter_size, kernel_size, dropout):
+        super().__init__()
+        self.sdp = StochasticDurationPredictor(in_channels, filter_size, kernel_size, dropout, nlayers)
+
+    def forward(self, x, mask, tgt=None, sigma=1.0, inference=False, noise=None):
+        if isinstance(x, ops.Planes):
+            x = ops.merge_planes(x)
+        out = self.sdp(x, mask, tgt, reverse=inference, noise_scale=sigma, noise=noise)
+        if mask is not None and inference:
+            pass                                    # PAD rows are already zeros: every flow step writes them as zeros
+        return out
+
+
 class VariancePredictor(nn.Module):
     """reference model.py:482-522."""
 
@@ -593,9 +750,14 @@ class VarianceAdaptor(nn.Module):
         self.duration_stochastic = duration_stochastic
         self.max_length = max_length
         if duration_stochastic:
-            raise NotImplementedError("stochastic duration predictor (RNG-dependent; out of scope)")
-        self.duration_predictor = VariancePredictor(duration_nlayers, encoder_hidden, duration_filter_size,
-                                                    duration_kernel_size, duration_dropout, duration_depthwise_conv)
+            if duration_depthwise_conv:   # reference model.py:197-200
+                raise NotImplementedError("Depthwise convolution not implemented for Flow-Based duration prediction")
+            self.duration_predictor = StochasticDurationPredictorWrapper(duration_nlayers, encoder_hidden,
+                                                                         duration_filter_size, duration_kernel_size,
+                                                                         duration_dropout)
+        else:
+            self.duration_predictor = VariancePredictor(duration_nlayers, encoder_hidden, duration_filter_size,
+                                                        duration_kernel_size, duration_dropout, duration_depthwise_conv)
         self.length_regulator = LengthRegulator()
         encoders = {}
         for i, var in enumerate(variances):
@@ -637,7 +799,14 @@ class VarianceAdaptor(nn.Module):
         """first half of the reference forward (model.py:249-309): duration prediction and the durations used"""
         force = force or {}
         control = control or {}
-        duration_pred = self.duration_predictor(x, src_mask)
+        if not self.duration_stochastic:
+            duration_pred = self.duration_predictor(x, src_mask)
+        elif inference:   # model.py:265-268 (x.detach(): no gradient path exists here anyway)
+            duration_pred = self.duration_predictor(x, src_mask, inference=True, noise=force.get("sdp_noise"),
+                                                    sigma=force.get("sdp_sigma", 1.0))
+        else:
+            raise NotImplementedError("stochastic duration predictor: the training direction (negative log-likelihood of "
+                                      "the flows, sdp.py:271-328) is not implemented on the CUDA path")
         tf_val = np.random.uniform(0, 1) <= tf_ratio  # reference model.py:272
         # phone-level variances act on the encoder output before the LengthRegulator (model.py:277-294)
         result, out_val = {}, None
@@ -659,6 +828,8 @@ class VarianceAdaptor(nn.Module):
             duration_rounded = force["duration_rounded"].to(x.device)
         elif not inference:
             duration_rounded = targets["duration"].to(x.device)
+        elif self.duration_stochastic:
+            duration_rounded = ops.sdp_durations(duration_pred, src_mask)
         else:
             duration_rounded = ops.duration_round_guard(duration_pred, src_mask)
         return {"duration_prediction": duration_pred, "duration_rounded": duration_rounded, "tf_val": tf_val,

@@ -253,6 +253,57 @@ def decoder_input_planes(x, pe, spk, bucket=None, want_f16=False):
     return out, idx_out
 
 
+# ---- stochastic duration predictor, inference direction (csrc/sdp.cu) ----
+def sdp_dwconv(x, pad_mask, wt, bias, dilation):
+    """dilated depthwise conv over T on (B,T,C) fp32, PAD rows read as zeros; wt (k, C)"""
+    _chk(x, torch.float32, "sdp_dwconv input", 3); _chk(wt, torch.float32, "sdp_dwconv weight", 2)
+    b, t, c = x.shape
+    out = torch.empty_like(x)
+    _launch("lfs2_sdp_dwconv", _p(x), _p(pad_mask), _p(wt), _p(bias), _p(out), b, t, c, wt.shape[0], int(dilation), _s(),
+            nbytes=8.0 * x.numel())
+    return out
+
+
+def sdp_ln_gelu(y, gamma, beta, eps=1e-5, res=None):
+    """[res +] gelu(LayerNorm over the last dim)"""
+    _chk(y, torch.float32, "sdp_ln_gelu input")
+    c = y.shape[-1]
+    out = torch.empty_like(y)
+    _launch("lfs2_sdp_ln_gelu", _p(y), _p(gamma), _p(beta), float(eps), _p(res), _p(out), y.numel() // c, c, _s(),
+            nbytes=(12.0 if res is not None else 8.0) * y.numel())
+    return out
+
+
+def sdp_flow_pre(z, channel, w, bias, g):
+    """h = z[..., channel, None] * w + bias + g: z (B,T,2), w / bias (C), g (B,T,C)"""
+    _chk(z, torch.float32, "flow state", 3); _chk(g, torch.float32, "flow conditioning", 3)
+    out = torch.empty_like(g)
+    _launch("lfs2_sdp_flow_pre", _p(z), int(channel), _p(w), _p(bias), _p(g), _p(out), g.numel() // g.shape[-1], g.shape[-1],
+            _s(), nbytes=8.0 * g.numel())
+    return out
+
+
+def sdp_spline_inverse_(z, x1_channel, h, pad_mask, hidden_channels, tail_bound=5.0):
+    """in place on z (B,T,2): channel x1_channel through the inverse spline parameterised by h (B,T,>=29)"""
+    _chk(z, torch.float32, "flow state", 3); _chk(h, torch.float32, "spline parameters", 3)
+    _launch("lfs2_sdp_spline_inverse", _p(z), int(x1_channel), _p(h), h.shape[-1], _p(pad_mask), int(hidden_channels),
+            float(tail_bound), z.numel() // 2, _s())
+    return z
+
+
+def sdp_affine_reverse_(z, translation, log_scale, pad_mask, flip):
+    _chk(z, torch.float32, "flow state", 3)
+    _launch("lfs2_sdp_affine_reverse", _p(z), _p(translation), _p(log_scale), _p(pad_mask), int(flip), z.numel() // 2, _s())
+    return z
+
+
+def sdp_durations(logw, src_mask):
+    _chk(logw, torch.float32, "log-durations", 2); _chk(src_mask, torch.bool, "src_mask", 2)
+    dur = torch.empty(logw.shape, device=logw.device, dtype=torch.int32)
+    _launch("lfs2_sdp_durations", _p(logw), _p(src_mask), _p(dur), logw.shape[0], logw.shape[1], _s())
+    return dur
+
+
 def prior_embed(prior, bins, emb):
     """PriorEmbedding: prior (B) fp32 -> (relu(emb[bucketize(prior)]) (B,d), bucket indices (B) int64)"""
     _chk(prior, torch.float32, "prior values", 1)

@@ -62,6 +62,10 @@ def fill_state_dict(template, seed=0, duration_bias=math.log(6.0), duration_scal
             a = 1.0 + 0.1 * g.standard_normal(shape)
         elif is_ln and leaf == "bias":
             a = 0.1 * g.standard_normal(shape)
+        elif leaf == "gamma":                       # LayerNorm2 of the stochastic duration predictor
+            a = 1.0 + 0.1 * g.standard_normal(shape)
+        elif leaf in ("beta", "translation", "log_scale"):
+            a = 0.1 * g.standard_normal(shape)
         elif "embedding.weight" in name and "speaker_embedding" not in name:
             a = g.standard_normal(shape)
             if name == "phone_embedding.weight":
