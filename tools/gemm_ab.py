@@ -18,6 +18,8 @@ VARIANTS = {
     "no_lo_mmas": ["-DLFS2_DIAG_NO_LO_MMAS"],          # one MMA pass instead of three, all loads kept
     "no_lo_loads": ["-DLFS2_DIAG_NO_LO_LOADS"],        # three MMA passes, only the hi planes are fetched
     "no_lo_at_all": ["-DLFS2_DIAG_NO_LO_MMAS", "-DLFS2_DIAG_NO_LO_LOADS"],
+    "no_epilogue": ["-DLFS2_DIAG_NO_EPILOGUE"],        # accumulators released unread: TMA loads + MMAs only
+    "no_epilogue_no_lo_loads": ["-DLFS2_DIAG_NO_EPILOGUE", "-DLFS2_DIAG_NO_LO_LOADS"],
 }
 
 
@@ -41,30 +43,41 @@ def one(name):
         _lib.LIB_PATH = os.path.join(AB, f"liblfs2_{name}.so")
     from lightningfastspeech2_b200 import ops
     g = torch.Generator().manual_seed(0)
-    x = ops.split_bf16(torch.randn(64, 2635, 256, generator=g).cuda())
+    x = ops.split_bf16(torch.randn(64, 2635, 256, generator=g).cuda(), want_f16=True)
+    ones, zeros = torch.ones(256, device="cuda"), torch.zeros(256, device="cuda")
+    w768 = (torch.randn(768, 256, generator=g) / 16).cuda()
+    w256 = (torch.randn(256, 256, generator=g) / 16).cuda()
+    b768 = torch.zeros(768, device="cuda")
+    dw = ((torch.randn(3, 256, generator=g) / 2).cuda(), zeros)
+    head = ((torch.randn(256, generator=g) / 16).cuda(), torch.zeros(1, device="cuda"), None)
+    wp768, wp768h, wp256 = ops.split_bf16(w768), ops.split_f16(w768), ops.split_bf16(w256)
+    cases = {
+        "qkv x3 planes": lambda: ops.gemm_tc(x, wp768, b768, out="planes"),
+        "qkv 2-pass f16": lambda: ops.gemm_tc(x, wp768h, b768, out="f16", npass=2),
+        "out-proj+res+LN": lambda: ops.gemm_tc(x, wp256, zeros, out="planes", residual=x, gamma=ones, beta=zeros),
+        "pred LN+stencil": lambda: ops.predictor_layer_tc(x, wp256, zeros, ones, zeros, next_dw=dw),
+        "pred LN+head": lambda: ops.predictor_layer_tc(x, wp256, zeros, ones, zeros, head=head),
+    }
     res = []
-    for n, kw in ((768, {}), (256, {"ln": True})):
-        w = ops.split_bf16((torch.randn(n, 256, generator=g) / 16).cuda())
-        b = torch.zeros(n, device="cuda")
-        extra = dict(residual=x, gamma=torch.ones(n, device="cuda"), beta=b) if kw else {}
+    for label, fn in cases.items():
         for _ in range(3):
-            ops.gemm_tc(x, w, b, out="planes", **extra)
+            fn()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(20):
-            ops.gemm_tc(x, w, b, out="planes", **extra)
+            fn()
         e1.record()
         torch.cuda.synchronize()
-        res.append(e0.elapsed_time(e1) / 20)
-    print(f"{name:14s} qkv (n=768) {res[0]:.4f} ms   out-proj + residual + LN (n=256) {res[1]:.4f} ms", flush=True)
+        res.append(f"{label} {e0.elapsed_time(e1) / 20:.4f}")
+    print(f"{name:24s} " + "   ".join(res) + "  (ms)", flush=True)
 
 
 if __name__ == "__main__":
     if sys.argv[1] == "build":
         build()
     elif sys.argv[1] == "run":
-        for name in VARIANTS:
+        for name in (sys.argv[2:] or VARIANTS):
             subprocess.run([sys.executable, os.path.abspath(__file__), "one", name], check=True)
     elif sys.argv[1] == "knobs":  # the shipped library under its environment knobs
         for env in ({}, {"LFS2_GEMM_MULTICAST": "0"}, {"LFS2_GEMM_NTILE": "128"}):
