@@ -134,20 +134,6 @@ __global__ void attn_kend_kernel(const uint8_t* __restrict__ kpm, int* __restric
   if (lane == 0) kend[b] = last;
 }
 
-// order[rank] = b with rank = position of utterance b when sorted by descending kend (ties by index): blocks are
-// dispatched z-major, so the long utterances start first and the grid's tail consists of short work.  One block.
-__global__ void attn_order_kernel(const int* __restrict__ kend, int* __restrict__ order, int batch) {
-  for (int b = threadIdx.x; b < batch; b += blockDim.x) {
-    const int kb = kend[b];
-    int rank = 0;
-    for (int o = 0; o < batch; ++o) {
-      const int ko = kend[o];
-      rank += (ko > kb) || (ko == kb && o < b);
-    }
-    order[rank] = b;
-  }
-}
-
 __device__ __forceinline__ void tma_store_3d_a(const CUtensorMap* map, const void* smem_src, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                    reinterpret_cast<uint64_t>(map)),
@@ -584,7 +570,7 @@ using namespace lfs2::tc;
 
 extern "C" {
 
-int lfs2_attention_tc_workspace_bytes(int batch) { return batch > 0 ? 2 * batch * (int)sizeof(int) : 0; }  // kend | order
+int lfs2_attention_tc_workspace_bytes(int batch) { return batch > 0 ? batch * (int)sizeof(int) : 0; }
 
 int lfs2_mask_lengths(const uint8_t* pad_mask, int* lengths, int batch, int t, void* stream) {
   LFS2_REQUIRE(lengths, LFS2_ERR_INVALID_ARG, "mask_lengths: null pointer");
@@ -632,8 +618,6 @@ int lfs2_attention_tc_ex(const void* qkv_hi, const void* qkv_lo, int operand_for
   int* kend = reinterpret_cast<int*>(workspace);
   attn_kend_kernel<<<ceil_div((long long)batch * 32, 128), 128, 0, s>>>(key_padding_mask, kend, batch, t);
   LFS2_CHECK_LAUNCH("attn_kend");
-  attn_order_kernel<<<1, 256, 0, s>>>(kend, kend + batch, batch);
-  LFS2_CHECK_LAUNCH("attn_order");
 
   if (npass == 1 && attn_pp_variant() == 2)
     return lfs2_attention_tc_wide(qkv_hi, operand_format, key_padding_mask, ctx_hi, ctx_lo, ctx_f32, workspace, batch, t, d,

@@ -87,7 +87,10 @@ __global__ void gemm_tile_list_kernel(const int* __restrict__ row_limit, int ext
 
 template <int N_TILE, int NPASS, bool LN, int EPI = 0, bool MC = false>
 struct SmemLayout {
-  static constexpr int kEdge = EPI != 0 ? 4 * N_TILE * 4 : 0;  // kEpiStencil: taps w0 | w1 | w2 | bias; kEpiDot: the head weight
+  // kEpiStencil: taps w0 | w1 | w2 | bias, then the warp-edge rows of the neighbour exchange: [4 groups][2 chunk
+  // parities][4 quadrants][first | last row][32 floats] = 8 KB; kEpiDot: the head weight
+  static constexpr int kEdgeRows = EPI == 1 ? 4 * 2 * 4 * 2 * 32 * 4 : 0;
+  static constexpr int kEdge = EPI != 0 ? 4 * N_TILE * 4 + kEdgeRows : 0;
   static constexpr bool kHasLo = NPASS == 3 || LN;  // LN variants stream residual lo planes even in bf16 mode
   static constexpr int kAPlane = kBM * kBK * 2;     // 8 KB
   static constexpr int kWPlane = N_TILE * kBK * 2 / (MC ? 2 : 1);  // CTA pair: each CTA holds half of the weight slab
@@ -434,6 +437,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
       // ---- row statistics: every group sums its chunks, the four partial sums meet in shared memory ----
       float s = 0.f, q = 0.f;
+#ifdef LFS2_DIAG_LN_NO_PASS1  // timing diagnostics only: no statistics pass over tensor memory
+      if (false)
+#endif
 #pragma unroll 1
       for (int c = c_begin; c < c_end; ++c) {
         tmem_ld32(taddr + c * 32, v);
@@ -500,10 +506,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 
       if (EPI == kEpiStencil) {
         // ---- u = depthwise3(LayerNorm(z)) of the next layer; rows outside the utterance count as zeros ----
-        // per 32-column chunk the group's staging buffer first holds the normalised rows as fp32 (swizzled like the fp32
-        // output path); after a 128-thread barrier every thread reads its two neighbour rows back, computes u, and -- once
-        // every thread of the group has its neighbours -- stages u as hi/lo planes in the SAME buffer, which leaves by TMA.
+        // The neighbour rows z[r-1], z[r+1] of a thread's 32 columns sit in the adjacent lanes of its warp: 64 shuffles per
+        // chunk; only a warp's first and last row travel through shared memory (8 KB of edge rows, double-buffered by
+        // chunk parity), so one 128-thread barrier per chunk covers the exchange AND "the staging buffer is free again".
+        // (The first version staged all of z in shared memory and read the neighbours back: two more barriers per chunk,
+        // a third of the kernel's time in tools/gemm_ab.py.)  u leaves as hi/lo planes through the staging buffer by TMA.
         const float* stw = reinterpret_cast<const float*>(smem + L::kOffEdge);  // w0 | w1 | w2 | bias, N_TILE floats each
+        float* edge = reinterpret_cast<float*>(smem + L::kOffEdge + 4 * N_TILE * 4);
         const int trow = t0 + r;
         const bool live = b < p.batch && trow >= 0 && trow < p.t;
         const bool outrow = r >= 1 && r <= kBM - 2;   // rows 1..126 are this tile's outputs, staged as rows 0..125
@@ -515,27 +524,35 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
           }
-          if (issuer) tma_store_wait_read0();     // the previous store of this group has finished reading the buffer
-          named_bar_sync(bar_id, 128);
-          {
-            uint8_t* row = sbuf + r * 128;
+          float* eg = edge + ((grp * 2 + (c & 1)) * 4) * 64;   // this group's edge rows of this chunk parity: [quad][2][32]
+          if (lane == 0 || lane == 31) {
+            float4* e4 = reinterpret_cast<float4*>(eg + quad * 64 + (lane == 0 ? 0 : 32));
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<float4*>(row + ((i ^ (r & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < 8; ++i) e4[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
           }
-          named_bar_sync(bar_id, 128);            // (A) the chunk's 128 rows of z are in shared memory
+          if (issuer) tma_store_wait_read0();     // the previous store of this group has finished reading the staging buffer
+          named_bar_sync(bar_id, 128);            // (A) edge rows visible, staging buffer free
           uint32_t hi[16], lo[16];
-          if (outrow) {
-            const uint8_t* rup = sbuf + (r - 1) * 128;
-            const uint8_t* rdn = sbuf + (r + 1) * 128;
+          {
+            const float4* eup = reinterpret_cast<const float4*>(eg + (quad > 0 ? quad - 1 : 0) * 64 + 32);  // last row of the warp above
+            const float4* edn = reinterpret_cast<const float4*>(eg + (quad < 3 ? quad + 1 : 3) * 64);       // first row of the warp below
             const float4* w0 = reinterpret_cast<const float4*>(stw + c * 32);
             const float4* w1 = reinterpret_cast<const float4*>(stw + N_TILE + c * 32);
             const float4* w2 = reinterpret_cast<const float4*>(stw + 2 * N_TILE + c * 32);
             const float4* bb = reinterpret_cast<const float4*>(stw + 3 * N_TILE + c * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              const float4 up = *reinterpret_cast<const float4*>(rup + ((i ^ ((r - 1) & 7)) << 4));
-              const float4 dn = *reinterpret_cast<const float4*>(rdn + ((i ^ ((r + 1) & 7)) << 4));
+              float4 up, dn;
+              up.x = __shfl_up_sync(0xffffffffu, v[4 * i], 1);
+              up.y = __shfl_up_sync(0xffffffffu, v[4 * i + 1], 1);
+              up.z = __shfl_up_sync(0xffffffffu, v[4 * i + 2], 1);
+              up.w = __shfl_up_sync(0xffffffffu, v[4 * i + 3], 1);
+              dn.x = __shfl_down_sync(0xffffffffu, v[4 * i], 1);
+              dn.y = __shfl_down_sync(0xffffffffu, v[4 * i + 1], 1);
+              dn.z = __shfl_down_sync(0xffffffffu, v[4 * i + 2], 1);
+              dn.w = __shfl_down_sync(0xffffffffu, v[4 * i + 3], 1);
+              if (lane == 0) up = eup[i];
+              if (lane == 31) dn = edn[i];
               const float4 a0 = w0[i], a1 = w1[i], a2 = w2[i], ab = bb[i];
               // same association as dwconv1d_k_kernel: bias, then taps 0, 1, 2
               const float u0 = fmaf(a2.x, dn.x, fmaf(a1.x, v[4 * i], fmaf(a0.x, up.x, ab.x)));
@@ -546,7 +563,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
               split_pack2(u2, u3, hi[2 * i + 1], lo[2 * i + 1]);
             }
           }
-          named_bar_sync(bar_id, 128);            // (B) every thread has read its neighbours: the buffer may be rewritten
           if (outrow) {
             const int rr = r - 1;
             uint8_t* rh = sbuf + rr * 64;
@@ -560,11 +576,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
           }
           fence_proxy_async_smem();
           named_bar_sync(bar_id, 128);            // (C) the u chunk is staged
+#ifndef LFS2_DIAG_NO_STORES
           if (issuer) {  // maps with 126-row boxes; TMA clips the rows past the utterance's end
             tma_store_3d(&map_o0, sbuf, n0 + c * 32, t0 + 1, b);
             tma_store_3d(&map_o1, sbuf + kStageChunk / 2, n0 + c * 32, t0 + 1, b);
             tma_store_commit();
           }
+#endif
         }
         tc_fence_before();
         __syncwarp();

@@ -20,14 +20,20 @@ VARIANTS = {
     "no_lo_at_all": ["-DLFS2_DIAG_NO_LO_MMAS", "-DLFS2_DIAG_NO_LO_LOADS"],
     "no_epilogue": ["-DLFS2_DIAG_NO_EPILOGUE"],        # accumulators released unread: TMA loads + MMAs only
     "no_epilogue_no_lo_loads": ["-DLFS2_DIAG_NO_EPILOGUE", "-DLFS2_DIAG_NO_LO_LOADS"],
+    "ln_no_pass1": ["-DLFS2_DIAG_LN_NO_PASS1"],        # LayerNorm builds: no statistics pass over tensor memory
+    "st_no_stencil": ["-DLFS2_DIAG_ST_NO_STENCIL"],    # stencil epilogue: u = z (no z staging, no neighbour reads, 2 barriers less)
+    "st_no_stencil_no_stores": ["-DLFS2_DIAG_ST_NO_STENCIL", "-DLFS2_DIAG_NO_STORES"],
+    "ln_no_pass1_no_stores": ["-DLFS2_DIAG_LN_NO_PASS1", "-DLFS2_DIAG_NO_STORES"],
 }
 
 
-def build():
+def build(only=None):
     os.makedirs(AB, exist_ok=True)
     objs = [os.path.join(CSRC, "build", f) for f in os.listdir(os.path.join(CSRC, "build"))
             if f.endswith(".o") and f != "gemm_tc.o"]
     for name, defs in VARIANTS.items():
+        if only and name not in only:
+            continue
         obj = os.path.join(AB, f"gemm_tc_{name}.o")
         subprocess.run(["nvcc", *FLAGS, *defs, "-c", os.path.join(CSRC, "gemm_tc.cu"), "-o", obj], check=True)
         subprocess.run(["nvcc", "-shared", "-o", os.path.join(AB, f"liblfs2_{name}.so"), obj, *objs, "-gencode",
@@ -75,7 +81,7 @@ def one(name):
 
 if __name__ == "__main__":
     if sys.argv[1] == "build":
-        build()
+        build(sys.argv[2:])
     elif sys.argv[1] == "run":
         for name in (sys.argv[2:] or VARIANTS):
             subprocess.run([sys.executable, os.path.abspath(__file__), "one", name], check=True)
