@@ -35,8 +35,8 @@ namespace tc {
 constexpr int kBM = 128;     // rows per tile (UMMA M)
 constexpr int kBK = 32;      // k-slab: 32 bf16 = 64 bytes = one SWIZZLE_64B row
 constexpr int kGemmTcThreads = 320;    // TMA + MMA warps, 8 epilogue warps (two per TMEM lane quadrant)
-constexpr int kGemmTcThreadsLN = 576;  // LayerNorm builds: 16 epilogue warps (four per quadrant), see the epilogue below
-__host__ __device__ constexpr int gemm_tc_threads(bool ln) { return ln ? kGemmTcThreadsLN : kGemmTcThreads; }
+constexpr int kGemmTcThreadsWide = 576;  // 256-column tiles: 16 epilogue warps (four per quadrant), see the epilogue below
+__host__ __device__ constexpr int gemm_tc_threads(int n_tile) { return n_tile == 256 ? kGemmTcThreadsWide : kGemmTcThreads; }
 constexpr int kStageChunk = kBM * 32 * 4;  // one 128 x 32 staging chunk: 16 KB (fp32) or 2 x 8 KB (hi | lo)
 
 // epilogue output: bf16 hi/lo planes | fp32 | ONE fp16 plane | ONE bf16 plane
@@ -182,7 +182,7 @@ __device__ __forceinline__ void ln_chunk(float (&v)[32], const float* vec, int n
 }
 
 template <int N_TILE, int NPASS, bool LN, int OUT, bool MC, int EPI = 0>
-__global__ void __launch_bounds__(gemm_tc_threads(LN), 1)
+__global__ void __launch_bounds__(gemm_tc_threads(N_TILE), 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
@@ -216,7 +216,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], (LN ? 16 : 8) * (MC ? 2 : 1));  // one arrive per epilogue warp (pair: of both CTAs, on the leader's barrier)
+      mbar_init(&tmem_empty[i], (N_TILE == 256 ? 16 : 8) * (MC ? 2 : 1));  // one arrive per epilogue warp (pair: of both CTAs, on the leader's barrier)
     }
     mbar_init(&ident_bar, 1);
     fence_barrier_init();
@@ -394,14 +394,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
       }
     }
-  } else if (LN && warp >= 2) {
-    // ===================== LayerNorm epilogue: warps 2..17 =====================
+  } else if (N_TILE == 256 && warp >= 2) {
+    // ===================== epilogue of the 256-column tiles (every LayerNorm build): warps 2..17 =====================
     // SIXTEEN warps, four per TMEM lane quadrant (quad = warp & 3): group g = (warp - 2) >> 2 owns the tile's
-    // 32-column chunks [2g, 2g + 2).  The epilogue of these builds is what paces them (knock-out builds,
-    // tools/gemm_ab.py: releasing the accumulator unread takes 30 % off the out-projection and 60 % off the predictor
-    // layers) and it is latency-bound -- tmem load -> normalise -> stage -> barrier -> store chains with two warps
-    // per scheduler -- so the fix is more warps in flight, not fewer instructions.  Each group has ONE 16 KB staging
-    // buffer, its own store-issuing thread and named barrier; row statistics meet in shared memory.
+    // 32-column chunks [2g, 2g + 2).  The epilogue is what paces these builds (knock-out builds, tools/gemm_ab.py:
+    // releasing the accumulator unread takes 23 % off the QKV GEMM, 30 % off the out-projection and 60 % off the
+    // predictor layers) and its chains -- tmem load -> normalise -> stage -> barrier -> store -- hide poorly behind
+    // two warps per scheduler.  Each group has ONE 16 KB staging buffer, its own store-issuing thread and named
+    // barrier; LayerNorm row statistics meet in shared memory.
     static_assert(!LN || N_TILE == 256, "LayerNorm epilogue: one 256-column tile");
     const int quad = warp & 3;
     const int grp = (warp - 2) >> 2;
@@ -418,6 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const float* vec = reinterpret_cast<const float*>(smem + L::kOffVec);
     float2* stats = reinterpret_cast<float2*>(smem + L::kOffStats);
     uint8_t* sbuf = smem + L::kOffStaging + grp * kStageChunk;
+    const bool bias_vec = p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15u) == 0;
     int it = 0;
     for (int tile = walk.first; tile < walk.count; tile += walk.stride, ++it) {
       int b, t0, n0;
@@ -440,6 +441,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #ifdef LFS2_DIAG_LN_NO_PASS1  // timing diagnostics only: no statistics pass over tensor memory
       if (false)
 #endif
+      if (LN)
 #pragma unroll 1
       for (int c = c_begin; c < c_end; ++c) {
         tmem_ld32(taddr + c * 32, v);
@@ -456,18 +458,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         }
       }
       float2* st = stats + (it & 1) * 4 * kBM;
-      st[grp * kBM + r] = make_float2(s, q);
-      named_bar_sync(kAllBar, 512);
-      s = 0.f;
-      q = 0.f;
+      float mean = 0.f, rstd = 1.f;
+      if (LN) {
+        st[grp * kBM + r] = make_float2(s, q);
+        named_bar_sync(kAllBar, 512);
+        s = 0.f;
+        q = 0.f;
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {  // the same order in every group: identical statistics in all of them
-        const float2 o = st[g * kBM + r];
-        s += o.x;
-        q += o.y;
+        for (int g = 0; g < 4; ++g) {  // the same order in every group: identical statistics in all of them
+          const float2 o = st[g * kBM + r];
+          s += o.x;
+          q += o.y;
+        }
+        mean = s * (1.f / N_TILE);
+        rstd = rsqrtf(fmaxf(q * (1.f / N_TILE) - mean * mean, 0.f) + p.eps);
       }
-      const float mean = s * (1.f / N_TILE);
-      const float rstd = rsqrtf(fmaxf(q * (1.f / N_TILE) - mean * mean, 0.f) + p.eps);
 
       if (EPI == kEpiDot) {
         // ---- predictor head: out[row] = LayerNorm(z)[row] . dot_w + dot_b, masked positions 0; nothing else is stored ----
@@ -593,8 +598,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 #pragma unroll 1
       for (int c = c_begin; c < c_end; ++c) {
         const int col0 = n0 + c * 32;
+        if (col0 >= p.n) break;  // chunk entirely outside the tensor (n not a multiple of N_TILE); uniform per group
         tmem_ld32(taddr + c * 32, v);
-        ln_chunk(v, vec, N_TILE, c * 32, mean, rstd, p.relu, p.slope);
+        if (LN) {
+          ln_chunk(v, vec, N_TILE, c * 32, mean, rstd, p.relu, p.slope);
+        } else if (bias_vec && col0 + 32 <= p.n) {
+          // the chunk's 32 bias values as 8 broadcast 16-byte loads
+          const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 bb = __ldg(b4 + j);
+            v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = activate(v[j], p.relu, p.slope);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            int col = col0 + j;
+            v[j] = activate(v[j] + ((p.bias && col < p.n) ? __ldg(p.bias + col) : 0.f), p.relu, p.slope);
+          }
+        }
         if (row_masked) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -1008,12 +1034,12 @@ static int launch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, cudaStream
   }
   int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
   if (!MC) {
-    kern<<<grid, gemm_tc_threads(LN), L::kTotal, s>>>(m.ah, m.al, m.wh, m.wl, m.rh, m.rl, m.ident, m.o0, m.o1, p);
+    kern<<<grid, gemm_tc_threads(N_TILE), L::kTotal, s>>>(m.ah, m.al, m.wh, m.wl, m.rh, m.rl, m.ident, m.o0, m.o1, p);
   } else {  // clusters of two CTAs (one per SM): pairs of row tiles share the multicast weight slabs
     grid &= ~1;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(gemm_tc_threads(LN));
+    cfg.blockDim = dim3(gemm_tc_threads(N_TILE));
     cfg.dynamicSmemBytes = L::kTotal;
     cfg.stream = s;
     cudaLaunchAttribute attr[1];

@@ -1,6 +1,6 @@
 set -x
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_gemm_tc.py tests/test_gpu_round2.py tests/test_gpu_predictors.py -q -m gpu -x -k "layernorm or fused_predictor or predictor" > gpurun_out/r2z_tests_new.log 2>&1; echo "new tests rc=$?"
+timeout 600 python -m pytest tests/test_gpu_gemm_tc.py -q -m gpu -x > gpurun_out/r2z_tests_new.log 2>&1; echo "new tests rc=$?"
 tail -4 gpurun_out/r2z_tests_new.log
 python tools/gemm_ab.py one shipped 2>&1 | tee gpurun_out/r2z_gemm_shipped.txt
 timeout 1500 python -m pytest tests -q -m gpu > gpurun_out/r2z_tests_all.log 2>&1; echo "all tests rc=$?"
