@@ -26,6 +26,9 @@
 // ~0.6 MB of activations): the pair works on two row tiles at once, each CTA fetches HALF of every weight slab and
 // multicasts it into both CTAs' shared memory -- half the weight traffic per row (same scheme as gemm_tc.cu).
 // Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..9 = epilogue (thread = row, two warps per quadrant).
+// (Sixteen epilogue warps -- which help the plain LayerNorm GEMMs of gemm_tc.cu -- made this kernel 3.5 % slower: the
+// register cap of a 576-thread block is 96, both epilogues spill, and the fp16 plane needs two more barriers per chunk
+// once every group has a single staging buffer.)
 #include "tc_common.cuh"
 
 namespace lfs2 {
