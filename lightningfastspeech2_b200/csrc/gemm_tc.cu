@@ -70,7 +70,7 @@ struct GemmTcParams {
 // EPI: what the LayerNorm epilogue does with the normalised row z
 //   kEpiNone     store it (every other use of the kernel)
 //   kEpiStencil  store u = depthwise3(z) -- the k = 3 depthwise conv of the NEXT predictor layer, rows z[r-1], z[r], z[r+1]
-//                taken from the neighbouring epilogue threads (warp shuffles; the rows at a warp's edges through shared
+//                taken from the neighbouring epilogue threads (warp shuffles; a warp's first and last row through shared
 //                memory).  A tile's first and last row have no neighbour inside the tile, so tiles advance by 126 rows
 //                and store rows 1..126; z rows outside the utterance are zeros (Conv1d's padding).
 //   kEpiDot      store only out[row] = z . dot_w + dot_b (masked): the predictor head (model.py:512-518)
@@ -673,10 +673,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     }
     if (issuer) tma_store_wait_all();
   } else if (warp >= 2) {
-    // ===================== epilogue: warps 2..9 =====================
+    // ===================== epilogue of the 128- / 64-column tiles: warps 2..9 =====================
     // thread = one output row (TMEM lane quadrant = warp & 3); the two warps of a quadrant split
     // the tile's 32-column chunks between them (half 0: first chunks, half 1: the rest), each
-    // half with its own staging buffers, store-issuing thread and named barrier.
+    // half with two staging buffers, its own store-issuing thread and named barrier.  (No LayerNorm here: that
+    // epilogue needs the whole 256-column row in one tile.)
+    static_assert(N_TILE == 256 || (!LN && EPI == kEpiNone), "LayerNorm / fused predictor epilogues: 256-column tiles");
     const int quad = warp & 3;
     const int half = (warp - 2) >> 2;
     const int r = quad * 32 + lane;
@@ -685,8 +687,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       if (MC) mbar_arrive_cluster(bar, 0);
       else mbar_arrive(bar);
     };
-    const float* vec = reinterpret_cast<const float*>(smem + L::kOffVec);
-    float2* stats = reinterpret_cast<float2*>(smem + L::kOffStats);
     uint8_t* staging = smem + L::kOffStaging + half * 2 * kStageChunk;
     constexpr int kHalfChunks = kChunks / 2;
     const int c_begin = half * kHalfChunks, c_end = c_begin + kHalfChunks;
@@ -709,154 +709,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
       uint32_t taddr = tmem_base + acc * kAccCols + ((uint32_t)(quad * 32) << 16);
       float v[32];
       const bool row_masked = p.row_mask && b < p.batch && t0 + r < p.t && p.row_mask[(size_t)b * p.t + t0 + r] != 0;
-
-      float mean = 0.f, rstd = 1.f;
-      if (LN) {
-        float s = 0.f, q = 0.f;
-#pragma unroll 1
-        for (int c = c_begin; c < c_end; ++c) {
-          tmem_ld32(taddr + c * 32, v);
-          const float4* b4 = reinterpret_cast<const float4*>(vec + c * 32);  // broadcast 16-byte reads
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 bb = b4[j];
-            const float x0 = activate(v[4 * j] + bb.x, p.relu, p.slope), x1 = activate(v[4 * j + 1] + bb.y, p.relu, p.slope);
-            const float x2 = activate(v[4 * j + 2] + bb.z, p.relu, p.slope), x3 = activate(v[4 * j + 3] + bb.w, p.relu, p.slope);
-            s += x0; q = fmaf(x0, x0, q);
-            s += x1; q = fmaf(x1, x1, q);
-            s += x2; q = fmaf(x2, x2, q);
-            s += x3; q = fmaf(x3, x3, q);
-          }
-        }
-        float2* st = stats + (it & 1) * 2 * kBM;
-        st[half * kBM + r] = make_float2(s, q);
-        named_bar_sync(3, 256);
-        const float2 o = st[(half ^ 1) * kBM + r];
-        s += o.x;
-        q += o.y;
-        mean = s * (1.f / N_TILE);
-        rstd = rsqrtf(fmaxf(q * (1.f / N_TILE) - mean * mean, 0.f) + p.eps);
-      }
-
-      if (EPI == kEpiDot) {
-        // ---- predictor head: out[row] = LayerNorm(z)[row] . dot_w + dot_b, masked positions 0; nothing else is stored ----
-        float acc_dot = 0.f;
-        const float* stw_dot = reinterpret_cast<const float*>(smem + L::kOffEdge);
-#pragma unroll 1
-        for (int c = c_begin; c < c_end; ++c) {
-          tmem_ld32(taddr + c * 32, v);
-          ln_chunk(v, vec, N_TILE, c * 32, mean, rstd, p.relu, p.slope);
-          const float4* w4 = reinterpret_cast<const float4*>(stw_dot + c * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 w = w4[j];
-            acc_dot = fmaf(v[4 * j], w.x, acc_dot);
-            acc_dot = fmaf(v[4 * j + 1], w.y, acc_dot);
-            acc_dot = fmaf(v[4 * j + 2], w.z, acc_dot);
-            acc_dot = fmaf(v[4 * j + 3], w.w, acc_dot);
-          }
-        }
-        float2* st = stats + (it & 1) * 2 * kBM;
-        named_bar_sync(3, 256);                       // both halves have consumed the statistics of this tile
-        st[half * kBM + r].x = acc_dot;
-        named_bar_sync(3, 256);
-        if (half == 0) {
-          const int trow = t0 + r;
-          if (b < p.batch && trow >= 0 && trow < p.t) {
-            const size_t o = (size_t)b * p.t + trow;
-            const float total = acc_dot + st[kBM + r].x + __ldg(p.dot_b);
-            p.dot_out[o] = (p.dot_mask && p.dot_mask[o]) ? 0.f : total;
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) release_acc(&tmem_empty[acc]);
-        continue;
-      }
-
-      if (EPI == kEpiStencil) {
-        // ---- u = depthwise3(LayerNorm(z)) of the next layer; rows outside the utterance count as zeros ----
-        // per 32-column chunk: the normalised rows go to one staging buffer as fp32 (swizzled like the fp32 output path);
-        // after a 128-thread barrier every thread reads its two neighbour rows back, computes u, and stages it as hi/lo
-        // planes in the OTHER buffer, which leaves by TMA.  Taps / bias come from shared memory (broadcast 16-byte reads).
-        const float* stw = reinterpret_cast<const float*>(smem + L::kOffEdge);  // w0 | w1 | w2 | bias, N_TILE floats each
-        const int trow = t0 + r;
-        const bool live = b < p.batch && trow >= 0 && trow < p.t;
-        const bool outrow = r >= 1 && r <= kBM - 2;   // rows 1..126 are this tile's outputs, staged as rows 0..125
-        uint8_t* zbuf = staging;                       // fp32 z chunk: 128 rows x 128 B
-        uint8_t* ubuf = staging + kStageChunk;         // u chunk: hi plane | lo plane
-#pragma unroll 1
-        for (int c = c_begin; c < c_end; ++c) {
-          tmem_ld32(taddr + c * 32, v);
-          ln_chunk(v, vec, N_TILE, c * 32, mean, rstd, p.relu, p.slope);
-          if (!live) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-          }
-          {
-            uint8_t* row = zbuf + r * 128;
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<float4*>(row + ((i ^ (r & 7)) << 4)) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-          }
-          named_bar_sync(1 + half, 128);          // (A) the chunk's 128 rows of z are in shared memory
-          uint32_t hi[16], lo[16];
-          if (outrow) {
-            const uint8_t* rup = zbuf + (r - 1) * 128;
-            const uint8_t* rdn = zbuf + (r + 1) * 128;
-            const float4* w0 = reinterpret_cast<const float4*>(stw + c * 32);
-            const float4* w1 = reinterpret_cast<const float4*>(stw + N_TILE + c * 32);
-            const float4* w2 = reinterpret_cast<const float4*>(stw + 2 * N_TILE + c * 32);
-            const float4* bb = reinterpret_cast<const float4*>(stw + 3 * N_TILE + c * 32);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 up = *reinterpret_cast<const float4*>(rup + ((i ^ ((r - 1) & 7)) << 4));
-              const float4 dn = *reinterpret_cast<const float4*>(rdn + ((i ^ ((r + 1) & 7)) << 4));
-              const float4 a0 = w0[i], a1 = w1[i], a2 = w2[i], ab = bb[i];
-              // same association as dwconv1d_k_kernel: bias, then taps 0, 1, 2
-              const float u0 = fmaf(a2.x, dn.x, fmaf(a1.x, v[4 * i], fmaf(a0.x, up.x, ab.x)));
-              const float u1 = fmaf(a2.y, dn.y, fmaf(a1.y, v[4 * i + 1], fmaf(a0.y, up.y, ab.y)));
-              const float u2 = fmaf(a2.z, dn.z, fmaf(a1.z, v[4 * i + 2], fmaf(a0.z, up.z, ab.z)));
-              const float u3 = fmaf(a2.w, dn.w, fmaf(a1.w, v[4 * i + 3], fmaf(a0.w, up.w, ab.w)));
-              split_pack2(u0, u1, hi[2 * i], lo[2 * i]);
-              split_pack2(u2, u3, hi[2 * i + 1], lo[2 * i + 1]);
-            }
-          }
-          if (issuer) tma_store_wait_read0();     // the previous chunk's store has finished reading ubuf
-          named_bar_sync(1 + half, 128);          // (B) ubuf is free, and every thread has read its neighbours from zbuf
-          if (outrow) {
-            const int rr = r - 1;
-            uint8_t* rh = ubuf + rr * 64;
-            uint8_t* rl = rh + kStageChunk / 2;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int o = (i ^ ((rr >> 1) & 3)) << 4;
-              *reinterpret_cast<uint4*>(rh + o) = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-              *reinterpret_cast<uint4*>(rl + o) = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-            }
-          }
-          fence_proxy_async_smem();
-          named_bar_sync(1 + half, 128);          // (C) the u chunk is staged
-          if (issuer) {  // maps with 126-row boxes; TMA clips the rows past the utterance's end
-            tma_store_3d(&map_o0, ubuf, n0 + c * 32, t0 + 1, b);
-            tma_store_3d(&map_o1, ubuf + kStageChunk / 2, n0 + c * 32, t0 + 1, b);
-            tma_store_commit();
-          }
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) release_acc(&tmem_empty[acc]);
-        continue;
-      }
-
 #pragma unroll 1
       for (int c = c_begin; c < c_end; ++c) {
         const int col0 = n0 + c * 32;
         if (col0 >= p.n) break;  // chunk entirely outside the tensor (n not a multiple of N_TILE)
         tmem_ld32(taddr + c * 32, v);
-        if (LN) {
-          ln_chunk(v, vec, N_TILE, c * 32, mean, rstd, p.relu, p.slope);
-        } else if (bias_vec && col0 + 32 <= p.n) {
+        if (bias_vec && col0 + 32 <= p.n) {
           // the chunk's 32 bias values as 8 broadcast 16-byte loads (a per-element load + bounds test was 36 % of
           // this kernel's instructions)
           const float4* b4 = reinterpret_cast<const float4*>(p.bias + col0);

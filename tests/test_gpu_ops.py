@@ -151,3 +151,39 @@ def test_bucket_embed_add():
     ops.bucket_embed_add_(xg2, None, std, mean, bins.to(DEV), emb.to(DEV), idx_forced=forced.to(DEV), acc=acc)
     assert torch.equal(xg2.cpu(), x + emb[forced])
     assert torch.equal(acc.cpu(), emb[ref_idx] + emb[forced])
+
+
+# ---- long depthwise kernels on large launches: the persistent double-buffered kernel (dwconv1d_pipe_kernel) ----
+@pytest.mark.parametrize("ks", [11, 13, 17, 21, 25])
+@pytest.mark.parametrize("bsz,t,d", [(9, 2203, 256), (3, 2211, 768)])
+def test_dwconv1d_pipelined_long_kernels(bsz, t, d, ks):
+    """>= 2 tiles of 64 rows per SM and K >= 11 take the cp.async-pipelined persistent kernel: fp32 and planes inputs,
+    fp32 / planes / fp16 outputs, ragged T, several channel blocks (d = 768), row limits"""
+    import torch.nn.functional as F
+
+    g = torch.Generator().manual_seed(ks * 1000 + d)
+    x = torch.randn(bsz, t, d, generator=g)
+    w = torch.randn(d, 1, ks, generator=g) * 0.2
+    b = torch.randn(d, generator=g) * 0.1
+    ref = F.conv1d(x.double().transpose(1, 2), w.double(), b.double(), padding=(ks - 1) // 2, groups=d).transpose(1, 2)
+    wt = w[:, 0, :].t().contiguous().to(DEV)
+    xd = x.to(DEV)
+    got = ops.dwconv1d_planes(xd, wt, b.to(DEV), out="f32")
+    assert float((got.cpu().double() - ref).abs().max()) < 2e-5
+    xp = ops.split_bf16(xd)
+    refp = F.conv1d(xp.float().cpu().double().transpose(1, 2), w.double(), b.double(), padding=(ks - 1) // 2,
+                    groups=d).transpose(1, 2)
+    gp = ops.dwconv1d_planes(xp, wt, b.to(DEV))
+    assert float((gp.float().cpu().double() - refp).abs().max()) < 1e-4            # planes out: 2^-16 relative
+    g32 = ops.dwconv1d_planes(xp, wt, b.to(DEV), out="f32")
+    assert float((g32.cpu().double() - refp).abs().max()) < 2e-5
+    gh = ops.dwconv1d_planes(xp, wt, b.to(DEV), out="f16")
+    assert gh.lo is None and torch.equal(gh.hi, g32.half())
+    if d == 256:   # row limits: kept rows are the unlimited run's bit for bit, input rows past the kept tiles read as zeros
+        lens = torch.randint(1, t + 1, (bsz,), generator=g).to(torch.int32).to(DEV)
+        extra = 20
+        part = ops.dwconv1d_planes(xp, wt, b.to(DEV), row_limit=(lens, extra))
+        for i, ln_ in enumerate(lens.tolist()):
+            keep = min(t, (ln_ + extra + 127) // 128 * 128)
+            inner = max(0, keep - (ks - 1) // 2)      # rows whose window stays inside the kept tiles
+            assert torch.equal(part.hi[i, :inner], gp.hi[i, :inner]) and torch.equal(part.lo[i, :inner], gp.lo[i, :inner]), i
