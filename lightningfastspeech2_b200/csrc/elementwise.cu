@@ -530,175 +530,6 @@ dwconv1d_k_kernel(const float4* __restrict__ x, const uint2* __restrict__ x_hi, 
   }
 }
 
-// Depthwise conv for the long kernels (K >= 11: the LightSpeech FFT blocks use 13 ... 25 taps): PERSISTENT CTAs, one per
-// SM, 512 threads, 64-row tiles, the input rows of tile i + 1 arriving by cp.async in the second shared-memory buffer
-// while tile i is computed.  The 32-row tiles of dwconv1d_k_kernel read (32 + K - 1) / 32 = 1.4 ... 1.75 input rows per
-// output row and alternate load and compute phases with only two CTAs per SM to overlap them (the K tap vectors take
-// 100 registers); here the halo costs (64 + K - 1) / 64 and the load of the next tile always runs under the arithmetic.
-// Shared memory holds what arrives from global memory: fp32 rows, or the bf16 hi | lo pairs of 4 channels in one
-// 16-byte slot (converted when read; rows outside [0, t_in) are zero-filled by cp.async itself).
-__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc, bool valid) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  const int n = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-}
-__device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gsrc, bool valid) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  const int n = valid ? 8 : 0;
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(gsrc), "r"(n) : "memory");
-}
-
-constexpr int kDwPipeTile = 64;
-constexpr int kDwPipeNT = 8;
-constexpr int kDwPipeThreads = kDwCh4 * (kDwPipeTile / kDwPipeNT);  // 512
-
-template <int K, bool IN_PLANES>
-__global__ void __launch_bounds__(kDwPipeThreads, 1)
-dwconv1d_pipe_kernel(const float4* __restrict__ x, const uint2* __restrict__ x_hi, const uint2* __restrict__ x_lo,
-                     const float4* __restrict__ wt, const float4* __restrict__ bias, float4* __restrict__ out,
-                     uint2* __restrict__ out_hi, uint2* __restrict__ out_lo, uint2* __restrict__ out_f16, int batch, int t,
-                     int d4, const int* __restrict__ row_limit, int limit_extra) {
-  extern __shared__ float4 xs[];  // [2][kRows][kDwCh4] 16-byte slots
-  constexpr int H = (K - 1) / 2;
-  constexpr int NT = kDwPipeNT;
-  constexpr int kRows = kDwPipeTile + K - 1;
-  const int tiles_t = (t + kDwPipeTile - 1) / kDwPipeTile;
-  const int cblocks = (d4 + kDwCh4 - 1) / kDwCh4;
-  const int items = batch * tiles_t * cblocks;
-  const int c = threadIdx.x % kDwCh4, tg = threadIdx.x / kDwCh4;
-
-  // item -> (utterance, first row, channel block); returns false for tiles the row limit drops
-  auto decode = [&](int item, int& b, int& t0, int& cb, int& t_in) {
-    cb = (item % cblocks) * kDwCh4;
-    const int rest = item / cblocks;
-    t0 = (rest % tiles_t) * kDwPipeTile;
-    b = rest / tiles_t;
-    t_in = t;
-    if (row_limit) {
-      const int lim = __ldg(row_limit + b) + limit_extra;
-      if ((t0 & ~127) >= lim) return false;
-      t_in = min(t, (lim + 127) & ~127);
-    }
-    return true;
-  };
-  auto prefetch = [&](int item, int buf) {  // every thread issues its share of the tile's rows (skipped tiles: nothing)
-    int b, t0, cb, t_in;
-    if (item < items && decode(item, b, t0, cb, t_in)) {
-      const int nch = min(kDwCh4, d4 - cb);
-      const size_t base = (size_t)b * t * d4 + cb;
-      float4* dst = xs + (size_t)buf * kRows * kDwCh4;
-      for (int row = tg; row < kRows; row += kDwPipeTile / NT) {
-        const int ti = t0 - H + row;
-        const bool ok = ti >= 0 && ti < t_in && c < nch;
-        const size_t gi = base + (size_t)(ok ? ti : 0) * d4 + (ok ? c : 0);
-        float4* slot = dst + row * kDwCh4 + c;
-        if (IN_PLANES) {
-          cp_async_8(slot, x_hi + gi, ok);
-          cp_async_8(reinterpret_cast<uint2*>(slot) + 1, x_lo + gi, ok);
-        } else {
-          cp_async_16(slot, x + gi, ok);
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-
-  float4 w[K];
-  int w_cb = -1;
-  float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
-  int buf = 0;
-  prefetch(blockIdx.x, 0);
-  for (int item = blockIdx.x; item < items; item += gridDim.x, buf ^= 1) {
-    prefetch(item + gridDim.x, buf ^ 1);                       // next tile -> other buffer
-    asm volatile("cp.async.wait_group 1;" ::: "memory");        // this tile's rows have landed
-    __syncthreads();
-    int b, t0, cb, t_in;
-    if (decode(item, b, t0, cb, t_in) && c < min(kDwCh4, d4 - cb)) {
-      if (cb != w_cb) {  // tap weights of this channel block (d = 256: loaded once per CTA)
-#pragma unroll
-        for (int j = 0; j < K; ++j) w[j] = wt[(size_t)j * d4 + cb + c];
-        bz = bias[cb + c];
-        w_cb = cb;
-      }
-      float4 acc[NT];
-#pragma unroll
-      for (int o = 0; o < NT; ++o) acc[o] = bz;
-      const float4* xr = xs + (size_t)buf * kRows * kDwCh4 + (size_t)(tg * NT) * kDwCh4 + c;
-#pragma unroll
-      for (int j = 0; j < NT + K - 1; ++j) {
-        float4 xv = xr[j * kDwCh4];
-        if (IN_PLANES) {
-          const uint4 raw = *reinterpret_cast<const uint4*>(&xv);
-          xv = planes_to_f4(make_uint2(raw.x, raw.y), make_uint2(raw.z, raw.w));
-        }
-#pragma unroll
-        for (int o = 0; o < NT; ++o) {
-          const int tap = j - o;  // compile-time after unrolling
-          if (tap >= 0 && tap < K) {
-            acc[o].x = fmaf(w[tap].x, xv.x, acc[o].x);
-            acc[o].y = fmaf(w[tap].y, xv.y, acc[o].y);
-            acc[o].z = fmaf(w[tap].z, xv.z, acc[o].z);
-            acc[o].w = fmaf(w[tap].w, xv.w, acc[o].w);
-          }
-        }
-      }
-      const size_t base = (size_t)b * t * d4 + cb;
-#pragma unroll
-      for (int o = 0; o < NT; ++o) {
-        const int to = t0 + tg * NT + o;
-        if (to < t) {
-          const size_t oi = base + (size_t)to * d4 + c;
-          if (out) out[oi] = acc[o];
-          if (out_hi) {
-            uint2 h, l;
-            split_pack2_ew(acc[o].x, acc[o].y, h.x, l.x);
-            split_pack2_ew(acc[o].z, acc[o].w, h.y, l.y);
-            out_hi[oi] = h;
-            out_lo[oi] = l;
-          }
-          if (out_f16) {
-            uint2 h;
-            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(acc[o].y), "f"(acc[o].x));
-            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(acc[o].w), "f"(acc[o].z));
-            out_f16[oi] = h;
-          }
-        }
-      }
-    }
-    __syncthreads();  // every thread is done with this buffer before the prefetch two tiles ahead overwrites it
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-}
-
-template <int K>
-static int launch_dwconv_pipe(const float* x, const void* x_hi, const void* x_lo, const float* wt, const float* bias,
-                              float* out, void* out_hi, void* out_lo, void* out_f16, int batch, int t, int d,
-                              const int* row_limit, int limit_extra, cudaStream_t s) {
-  constexpr int kSmem = 2 * (kDwPipeTile + K - 1) * kDwCh4 * 16;
-  static bool configured = false;
-  auto kf = dwconv1d_pipe_kernel<K, false>;
-  auto kp = dwconv1d_pipe_kernel<K, true>;
-  if (!configured) {
-    if (cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess ||
-        cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) {
-      set_error("dwconv1d: cannot reserve %d bytes of shared memory", kSmem);
-      return LFS2_ERR_CUDA;
-    }
-    configured = true;
-  }
-  const long long items = (long long)batch * ceil_div(t, kDwPipeTile) * ceil_div(d / 4, kDwCh4);
-  const int grid = (int)(items < kNumSMs ? items : kNumSMs);
-  if (x)
-    kf<<<grid, kDwPipeThreads, kSmem, s>>>((const float4*)x, nullptr, nullptr, (const float4*)wt, (const float4*)bias,
-                                           (float4*)out, (uint2*)out_hi, (uint2*)out_lo, (uint2*)out_f16, batch, t, d / 4,
-                                           row_limit, limit_extra);
-  else
-    kp<<<grid, kDwPipeThreads, kSmem, s>>>(nullptr, (const uint2*)x_hi, (const uint2*)x_lo, (const float4*)wt,
-                                           (const float4*)bias, (float4*)out, (uint2*)out_hi, (uint2*)out_lo,
-                                           (uint2*)out_f16, batch, t, d / 4, row_limit, limit_extra);
-  return LFS2_OK;
-}
-
 template <int K, int NT, int kDwTile>
 static int launch_dwconv_k(const float* x, const void* x_hi, const void* x_lo, const float* wt, const float* bias,
                            float* out, void* out_hi, void* out_lo, void* out_f16, int batch, int t, int d,
@@ -953,27 +784,10 @@ int lfs2_dwconv1d_planes_ex(const float* x, const void* x_hi, const void* x_lo, 
                LFS2_ERR_INVALID_ARG, "dwconv1d: pointers must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   LFS2_REQUIRE(batch <= 65535, LFS2_ERR_UNSUPPORTED, "dwconv1d: batch exceeds the grid limit");
-  // long kernels on launches with at least two 64-row tiles per SM: the persistent double-buffered kernel
-  // (LFS2_DWCONV_PIPE=0 switches it off: A/B runs)
-  static int pipe_on = -1;
-  if (pipe_on < 0) {
-    const char* e = getenv("LFS2_DWCONV_PIPE");
-    pipe_on = (e && e[0] == '0') ? 0 : 1;
-  }
-  const bool pipe = pipe_on == 1 && ksize >= 11 &&
-                    (long long)batch * ceil_div(t, kDwPipeTile) * ceil_div(d / 4, kDwCh4) >= 2LL * kNumSMs;
 #define LFS2_DW_CASE(K, TT)                                                                          \
   case K: {                                                                                          \
-    int rc;                                                                                          \
-    if constexpr (K >= 11) {                                                                         \
-      rc = pipe ? launch_dwconv_pipe<K>(x, x_hi, x_lo, wt, bias, out, out_hi, out_lo, out_f16, batch, t, d, row_limit,   \
-                                        limit_extra, s)                                                               \
-                : launch_dwconv_k<K, TT, 32>(x, x_hi, x_lo, wt, bias, out, out_hi, out_lo, out_f16, batch, t, d,        \
-                                             row_limit, limit_extra, s);                                               \
-    } else {                                                                                         \
-      rc = launch_dwconv_k<K, TT, 64>(x, x_hi, x_lo, wt, bias, out, out_hi, out_lo, out_f16, batch, t, d, row_limit,     \
-                                      limit_extra, s);                                                                \
-    }                                                                                                \
+    int rc = launch_dwconv_k<K, TT, (K <= 9 ? 64 : 32)>(x, x_hi, x_lo, wt, bias, out, out_hi, out_lo, out_f16, batch, t, \
+                                                        d, row_limit, limit_extra, s);                                \
     if (rc != LFS2_OK) return rc;                                                                    \
   } break;
   switch (ksize) {

@@ -153,12 +153,12 @@ def test_bucket_embed_add():
     assert torch.equal(acc.cpu(), emb[ref_idx] + emb[forced])
 
 
-# ---- long depthwise kernels on large launches: the persistent double-buffered kernel (dwconv1d_pipe_kernel) ----
+# ---- long depthwise kernels (the LightSpeech blocks use 13 ... 25 taps) on bench-sized launches ----
 @pytest.mark.parametrize("ks", [11, 13, 17, 21, 25])
 @pytest.mark.parametrize("bsz,t,d", [(9, 2203, 256), (3, 2211, 768)])
-def test_dwconv1d_pipelined_long_kernels(bsz, t, d, ks):
-    """>= 2 tiles of 64 rows per SM and K >= 11 take the cp.async-pipelined persistent kernel: fp32 and planes inputs,
-    fp32 / planes / fp16 outputs, ragged T, several channel blocks (d = 768), row limits"""
+def test_dwconv1d_long_kernels_large_launches(bsz, t, d, ks):
+    """K >= 11 on launches of bench size: fp32 and planes inputs, fp32 / planes / fp16 outputs, ragged T, several channel
+    blocks (d = 768), row limits"""
     import torch.nn.functional as F
 
     g = torch.Generator().manual_seed(ks * 1000 + d)
