@@ -636,19 +636,43 @@ def run_lfs2(args):
     #      (lightningfastspeech2_b200.pipeline.SynthesisStream, depth 2) ----------------------------------------
     from lightningfastspeech2_b200.pipeline import SynthesisStream
 
+    # (a) padded read-back: the whole (B, L, 80) mel + mask, as model(batch) returns them
     pipe = SynthesisStream(model, depth=2)
     for _ in range(4):  # warm-up: both slots allocate their pinned buffers, the allocator reaches its steady state
         pipe.collect(pipe.submit(pinned))
     barrier()
     p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     p0.record()
-    piped_frames, prev = 0, None
+    padded_frames, prev = 0, None
     for _ in range(args.steps):
         tk = pipe.submit(pinned)
         if prev is not None:
-            piped_frames += int((~pipe.collect(prev)["tgt_mask"]).sum())
+            padded_frames += int((~pipe.collect(prev)["tgt_mask"]).sum())
         prev = tk
-    piped_frames += int((~pipe.collect(prev)["tgt_mask"]).sum())
+    padded_frames += int((~pipe.collect(prev)["tgt_mask"]).sum())
+    p1.record()
+    barrier()
+    ms_piped_padded = p0.elapsed_time(p1)
+    # (b) compact read-back (the headline e2e): every utterance's mel cut at its own length -- what the reference's
+    #     caller keeps (synthesis/generator.py:164-170) -- packed on the device, one transfer of sum(frames) rows
+    pipe = SynthesisStream(model, depth=2, compact=True)
+    for _ in range(4):
+        pipe.collect(pipe.submit(pinned))
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    piped_frames, prev, d2h_compact = 0, None, 0
+    for _ in range(args.steps):
+        tk = pipe.submit(pinned)
+        if prev is not None:
+            got = pipe.collect(prev)
+            piped_frames += sum(got["lengths"])
+            d2h_compact = sum(m.numel() for m in got["mel"]) * 4 + 8 * len(got["lengths"])
+        prev = tk
+    got = pipe.collect(prev)
+    piped_frames += sum(got["lengths"])
+    d2h_compact = sum(m.numel() for m in got["mel"]) * 4 + 8 * len(got["lengths"])
+    assert piped_frames == padded_frames, (piped_frames, padded_frames)
     p1.record()
     barrier()
     ms_piped = p0.elapsed_time(p1)
@@ -664,9 +688,9 @@ def run_lfs2(args):
 
     # ---- reduce over ranks ------------------------------------------------------------------
     if world > 1:
-        t = torch.tensor([ms, ms_e2e, ms_piped], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms, ms_e2e, ms_piped, ms_piped_padded], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e, ms_piped = float(t[0]), float(t[1]), float(t[2])
+        ms, ms_e2e, ms_piped, ms_piped_padded = float(t[0]), float(t[1]), float(t[2]), float(t[3])
         c = torch.tensor([frames, e2e_frames, piped_frames], device=dev, dtype=torch.int64)
         dist.all_reduce(c, op=dist.ReduceOp.SUM)
         frames_all, e2e_all, piped_all = int(c[0]), int(c[1]), int(c[2])
@@ -951,13 +975,18 @@ def run_lfs2(args):
             "clocks": clocks,
             # end to end through the public API with HOST buffers: every step copies its inputs from pinned host memory
             # and its mel + mask back to pinned host memory, and the host reads the mask.  `value` = the generation-loop
-            # API (pipeline.SynthesisStream, depth 2: step i's read-back overlaps step i+1's kernels);
-            # `sequential` = the same work with a blocking read-back after every model(batch) call.
+            # API (pipeline.SynthesisStream, depth 2: step i's read-back overlaps step i+1's kernels) reading back every
+            # utterance's mel cut at its own length (compact=True: what the reference's caller keeps, generator.py:164-170);
+            # `padded` = the same stream reading back the whole padded mel + mask; `sequential` = a blocking read-back of
+            # the padded mel after every model(batch) call.
             "e2e": {"value": piped_all / (ms_piped * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in pinned.values()) * world,
-                    "d2h_bytes_per_step": (mel_host.numel() * 4 + mask_host.numel() + 8) * world,
+                    "d2h_bytes_per_step": (d2h_compact + 8 * BATCH) * world,
                     "ms_per_step": ms_piped / args.steps,
-                    "api": "lightningfastspeech2_b200.pipeline.SynthesisStream(model).submit / collect",
+                    "api": "lightningfastspeech2_b200.pipeline.SynthesisStream(model, compact=True).submit / collect",
+                    "padded": {"value": piped_all / (ms_piped_padded * 1e-3), "ms_per_step": ms_piped_padded / args.steps,
+                               "d2h_bytes_per_step": (mel_host.numel() * 4 + mask_host.numel() + 8) * world,
+                               "api": "SynthesisStream(model).submit / collect"},
                     "sequential": {"value": e2e_all / (ms_e2e * 1e-3), "ms_per_step": ms_e2e / args.steps,
                                    "api": "model(batch, inference=True); mel.cpu()"}},
             "gpu_launches": launches,

@@ -152,6 +152,12 @@ LFS2_API int lfs2_length_regulate_scatter_ex(const void* x, const int64_t* cum, 
                                     void* out, uint8_t* mask, int batch, int tp, int l, int cap,
                                     int row_bytes, void* stream);
 
+/* Ragged read-back of a synthesis batch: the valid rows of x (batch, l, width) fp32 (width % 4 == 0) packed back to back
+ * in utterance order into out (sum_b min(lengths[b], l), width): what the reference's caller keeps of a batch
+ * (synthesis/generator.py:164-170 cuts every mel at ~tgt_mask).  lengths = the LengthRegulator's frame counts. */
+LFS2_API int lfs2_pack_valid_rows(const float* x, const int64_t* lengths, float* out, int batch, int l, int width,
+                                  void* stream);
+
 /* ---- tensor-core (tcgen05) GEMM / Conv1d with fused epilogues ---------------------------
  * Operands are bf16 "hi/lo" planes of fp32 values (x = hi + lo, see lfs2_split_bf16):
  *   a_hi/a_lo : (batch, t, d)      row-major bf16   (activations)

@@ -100,6 +100,7 @@ SIGNATURES = {
     "lfs2_sdp_spline_inverse": [_vp, _i, _vp, _i, _vp, _i, _f, _i, _vp],
     "lfs2_sdp_affine_reverse": [_vp, _vp, _vp, _vp, _i, _i, _vp],
     "lfs2_sdp_durations": [_vp, _vp, _vp, _i, _i, _vp],
+    "lfs2_pack_valid_rows": [_vp, _vp, _vp, _i, _i, _i, _vp],
     "lfs2_bucket_embed_add_oop": [_vp, _vp, _vp, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "lfs2_rowdot_mask_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "lfs2_sum_over_time": [_vp, _vp, _i, _i, _i, _vp],

@@ -109,7 +109,36 @@ lr_scatter_kernel(const int4* __restrict__ x, const int64_t* __restrict__ cum, c
 
 using namespace lfs2;
 
+// Ragged read-back: the valid rows of a padded (batch, l, width) fp32 tensor packed back to back in utterance order
+// (what the reference's caller keeps of a synthesis batch: generator.py:164-170 cuts every mel at ~tgt_mask).  Utterance
+// b owns rows [off_b, off_b + n_b) of `out`, n_b = min(lengths[b], l), off_b = n_0 + ... + n_{b-1}.
+__global__ void pack_valid_rows_kernel(const float4* __restrict__ x, const int64_t* __restrict__ lengths,
+                                       float4* __restrict__ out, int l, int w4, int rows_per_block) {
+  const int b = blockIdx.y;
+  long long off = 0;
+  for (int i = 0; i < b; ++i) off += min((long long)lengths[i], (long long)l);   // batch <= a few hundred: trivial
+  const int n = (int)min((long long)lengths[b], (long long)l);
+  const int r0 = blockIdx.x * rows_per_block, r1 = min(r0 + rows_per_block, n);
+  const size_t src = ((size_t)b * l + r0) * w4, dst = ((size_t)off + r0) * w4;
+  const int total = (r1 - r0) * w4;
+  for (int i = threadIdx.x; i < total; i += blockDim.x) out[dst + i] = x[src + i];
+}
+
 extern "C" {
+
+int lfs2_pack_valid_rows(const float* x, const int64_t* lengths, float* out, int batch, int l, int width, void* stream) {
+  LFS2_REQUIRE(x && lengths && out, LFS2_ERR_INVALID_ARG, "pack_valid_rows: null pointer");
+  if (batch == 0 || l == 0) return LFS2_OK;
+  LFS2_REQUIRE(batch > 0 && batch <= 65535 && l > 0 && width > 0 && width % 4 == 0, LFS2_ERR_UNSUPPORTED,
+               "pack_valid_rows: need 0 < batch <= 65535 and width %% 4 == 0");
+  LFS2_REQUIRE(aligned16(x) && aligned16(out), LFS2_ERR_INVALID_ARG, "pack_valid_rows: pointers must be 16-byte aligned");
+  const int rows_per_block = 64;
+  dim3 grid(ceil_div(l, rows_per_block), batch);
+  pack_valid_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)x, lengths, (float4*)out, l, width / 4,
+                                                                 rows_per_block);
+  LFS2_CHECK_LAUNCH("pack_valid_rows");
+  return LFS2_OK;
+}
 
 int lfs2_length_regulate_scan(const void* dur, int dur_is_i64, int64_t* cum, int64_t* lengths, int64_t* max_len,
                               int batch, int tp, void* stream) {

@@ -456,6 +456,8 @@ class FastSpeech2(_Base):
             "duration_rounded": variance_output["duration_rounded"],
             "src_mask": src_mask,
             "tgt_mask": tgt_mask,
+            "frame_lengths": variance_output.get("frame_lengths"),
+            "frame_lengths_host": variance_output.get("frame_lengths_host"),
         }
         if hasattr(self, "fastdiff_linear") and variance_output["out"] is not None:
             zero_pe = torch.zeros(1, mel.shape[1], hp.decoder_hidden, device=dev)

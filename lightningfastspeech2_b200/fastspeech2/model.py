@@ -846,8 +846,12 @@ class VarianceAdaptor(nn.Module):
         duration_pred, duration_rounded, tf_val = st["duration_prediction"], st["duration_rounded"], st["tf_val"]
         if scan is None:
             scan = ops.length_regulate_scan(duration_rounded.to(x.device), x.shape[:2])
+        lens_host = None
         if frames is None:
-            longest = int(scan[2].item())  # the single device->host sync of the path
+            # the single device->host sync of the path: the per-utterance frame counts (B int64; their maximum sizes the
+            # frame-level tensors, the list itself lets a caller read back only the valid frames, pipeline.SynthesisStream)
+            lens_host = scan[1].tolist()
+            longest = max(lens_host) if lens_host else 0
             l = min(longest, int(self.max_length)) if self.max_length is not None else longest
             frames = (l, l)
         x_in = x
@@ -886,6 +890,8 @@ class VarianceAdaptor(nn.Module):
             x_planes, _ = ops.decoder_input_planes(x, tail[0], tail[1], want_f16=tail[2])
         result["x"] = x
         result["x_planes"] = x_planes
+        result["frame_lengths"] = scan[1]            # (B) int64 on the device: frames per utterance before the max_length cut
+        result["frame_lengths_host"] = lens_host     # the same as a Python list when this call did the sync, else None
         result["duration_prediction"] = duration_pred
         result["duration_rounded"] = duration_rounded
         result["tgt_mask"] = tgt_mask

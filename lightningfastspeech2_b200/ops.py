@@ -339,6 +339,16 @@ def length_regulate_scan(durations, batch_first_shape):
     return cum, lengths, mx
 
 
+def pack_valid_rows(x, lengths, total):
+    """x (B,L,W) fp32, lengths (B) int64 on the device, total = sum(min(lengths, L)) (known on the host) ->
+    (total, W): every utterance's valid rows back to back"""
+    _chk(x, torch.float32, "pack_valid_rows input", 3); _chk(lengths, torch.int64, "frame counts", 1)
+    b, l, w = x.shape
+    out = torch.empty(int(total), w, device=x.device, dtype=torch.float32)
+    _launch("lfs2_pack_valid_rows", _p(x), _p(lengths), _p(out), b, l, w, _s(), nbytes=8.0 * int(total) * w)
+    return out
+
+
 def length_regulate_scatter(x, cum, lengths, l, cap):
     """out (B,l,d), mask (B,l): frames below min(lengths[b], cap) copy their phone's row, the rest are PAD (+0)"""
     b, tp, d = x.shape

@@ -7,18 +7,26 @@ of compute, and the device idles while it drains.  ``SynthesisStream`` keeps the
 (every batch's inputs are copied from pinned host memory, every batch's mel and mask are copied back to
 pinned host memory) but puts the device->host copies on a second CUDA stream, double-buffered, so batch
 i's read-back overlaps batch i+1's kernels.  Nothing is skipped or cached across batches.
+
+``compact=True`` reads back what the reference's caller keeps of a batch -- every utterance's mel cut at its own
+length (generator.py:164-170) -- instead of the padded (B, L, 80) tensor: the valid frames are packed back to back on
+the device (lfs2_pack_valid_rows) and one transfer of sum(frames) rows goes to the host (about half the bytes of the
+padded tensor at the bench's length distribution); collect() returns per-utterance views of that buffer.
 """
 import torch
 
+from . import ops
+
 
 class SynthesisStream:
-    def __init__(self, model, depth=2, keys=("mel", "tgt_mask"), pieces=16):
+    def __init__(self, model, depth=2, keys=("mel", "tgt_mask"), pieces=16, compact=False):
         if depth < 1:
             raise ValueError("depth must be >= 1")
         self.model = model
         self.depth = depth
         self.keys = tuple(keys)
         self.pieces = pieces
+        self.compact = bool(compact)
         self.device = model.device
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self._slots = [dict(host={}, done=None, keep=None) for _ in range(depth)]
@@ -26,6 +34,14 @@ class SynthesisStream:
 
     def _host_buffer(self, slot, key, t):
         buf = slot["host"].get(key)
+        if key == "mel_packed":  # ragged: a pinned buffer with headroom, a view of the rows in use
+            cap = slot["host"].get("_packed_cap")
+            if cap is None or cap.shape[0] < t.shape[0] or cap.shape[1:] != t.shape[1:]:
+                cap = torch.empty((int(t.shape[0] * 1.25) + 1,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
+                slot["host"]["_packed_cap"] = cap
+            buf = cap[: t.shape[0]]
+            slot["host"][key] = buf
+            return buf
         if buf is None or buf.shape != t.shape or buf.dtype != t.dtype:
             buf = torch.empty(t.shape, dtype=t.dtype).pin_memory()  # pinned allocations are cached per slot and shape
             slot["host"][key] = buf
@@ -39,22 +55,37 @@ class SynthesisStream:
         compute = torch.cuda.current_stream(self.device)
         with torch.no_grad():
             out = self.model(host_batch, inference=True)  # H2D of phones / speaker happens inside forward
+        lens = None
+        if self.compact:
+            # frames per utterance: known on the host since the forward's one sync (or read back here on the paths that
+            # size their tensors differently), cut at the padded length like tgt_mask
+            lens, fl = out.get("frame_lengths_host"), out.get("frame_lengths")
+            if fl is None:   # (the bucketed path assembles its result itself: count the frames tgt_mask keeps)
+                fl = (~out["tgt_mask"]).sum(1)
+            if lens is None:
+                lens = fl.tolist()
+            width = out["mel"].shape[1]
+            lens = [min(int(n), width) for n in lens]
+            out = dict(out)
+            out["mel_packed"] = ops.pack_valid_rows(out["mel"].contiguous(), fl.contiguous(), sum(lens))
         ready = torch.cuda.Event()
         ready.record(compute)
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(ready)
-            for k in self.keys:
+            for k in (("mel_packed",) if self.compact else self.keys):
                 t = out[k]
                 t.record_stream(self.copy_stream)  # the allocator must not hand the block out while it is being read
                 # in pieces: the forward of the NEXT batch reads 8 bytes back (the LengthRegulator's frame count)
                 # through the same device->host copy engine and must not queue behind one 54 MB transfer
                 hb = self._host_buffer(slot, k, t)
+                if t.shape[0] == 0:
+                    continue
                 n = max(1, min(self.pieces, t.shape[0]))
                 for src, dst in zip(t.chunk(n), hb.chunk(n)):
                     dst.copy_(src, non_blocking=True)
             done = torch.cuda.Event()
             done.record(self.copy_stream)
-        slot["done"], slot["keep"] = done, out
+        slot["done"], slot["keep"], slot["lens"] = done, out, lens
         ticket = self._n
         self._n += 1
         return ticket
@@ -65,4 +96,8 @@ class SynthesisStream:
         slot = self._slots[ticket % self.depth]
         slot["done"].synchronize()
         slot["keep"] = None
+        if self.compact:  # {"mel": [per-utterance (frames_b, n_mels) views of the packed host buffer], "lengths": [...]}
+            lens = slot["lens"]
+            packed = slot["host"]["mel_packed"]
+            return {"mel": list(packed.split(lens)) if lens else [], "lengths": lens}
         return {k: slot["host"][k] for k in self.keys}

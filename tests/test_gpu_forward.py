@@ -339,6 +339,43 @@ def test_synthesis_stream_pipelining_returns_the_same_results():
         assert torch.equal(r["mel"].cpu(), g["mel"]) and torch.equal(r["tgt_mask"].cpu(), g["tgt_mask"])
 
 
+@pytest.mark.parametrize("mode", ["default", "cuda_graphs", "length_buckets", "skip_pad_rows"])
+def test_synthesis_stream_compact_readback_returns_each_utterances_valid_frames(mode):
+    """SynthesisStream(compact=True): per-utterance mels cut at their own length == the padded result cut with tgt_mask
+    (what synthesis/generator.py:164-170 keeps), on every path that sizes the frame tensors differently"""
+    from lightningfastspeech2_b200.pipeline import SynthesisStream
+
+    model, sd, hp = build("C2", 23)
+    batches = [{k: v.pin_memory() for k, v in synthetic.make_batch(5, 10, 60, seed=40 + i, pad_to=60).items()
+                if k in ("phones", "speaker")} for i in range(4)]
+    with torch.no_grad():
+        ref = [model(b, inference=True) for b in batches]
+    if mode == "cuda_graphs":
+        model.cuda_graphs = True
+    elif mode == "length_buckets":
+        model.length_buckets = 2
+    elif mode == "skip_pad_rows":
+        model.skip_pad_rows = True
+    try:
+        pipe = SynthesisStream(model, depth=2, compact=True)
+        got, prev = [], None
+        for b in batches + batches:      # twice: the second round replays graphs / reuses the pinned buffers
+            tk = pipe.submit(b)
+            if prev is not None:
+                g = pipe.collect(prev)
+                got.append({"mel": [m.clone() for m in g["mel"]], "lengths": list(g["lengths"])})
+            prev = tk
+        g = pipe.collect(prev)
+        got.append({"mel": [m.clone() for m in g["mel"]], "lengths": list(g["lengths"])})
+    finally:
+        model.cuda_graphs, model.length_buckets, model.skip_pad_rows = False, 1, False
+    for r, g in zip(ref + ref, got):
+        keep = (~r["tgt_mask"]).cpu()
+        assert g["lengths"] == keep.sum(1).tolist()
+        for i, m in enumerate(g["mel"]):
+            assert torch.equal(m, r["mel"][i].cpu()[keep[i]]), (mode, i)
+
+
 def test_predictor_pad_tile_skipping_is_bit_identical():
     """the variance predictors skip 128-row tiles that lie beyond (last valid row + conv halo): their PAD outputs are
     masked to 0 anyway, so every output bit -- predictions, bucket indices, mel on ALL positions -- must be unchanged"""
