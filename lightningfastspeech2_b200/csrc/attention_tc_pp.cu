@@ -17,7 +17,9 @@
 //   shared memory: Q tile (128 x 128, 32 KB, resident: S = Q.K^T is an SS-form MMA) | K ring | V ring (2 x 16 KB each)
 //   warps: 0 = TMA producer (Q, K ring), 1 = MMA issuer, 2..5 = softmax (TMEM lane quadrant = warp & 3), 6 = TMA producer (V)
 //   tensor-pipe order: QK_0 QK_1 | PV_0 QK_2 | PV_1 QK_3 | ...
-// The normalised O rows leave straight from registers (thread = row: 64-byte pieces per plane).
+// The normalised O rows leave as hi/lo planes through swizzled staging in the (by then idle) K ring and TMA tensor stores.
+// (Straight from registers -- 16 bytes per row and instruction, half-filled sectors -- the epilogue took 9.8 k of a CTA's
+// 58 k cycles: clock64 timeline, tools/attn_timeline.py, profiles/r3f_attn_timeline.txt.)
 #include <math.h>
 #include <stdlib.h>
 
@@ -86,9 +88,19 @@ struct PpParams {
   int limit_extra;
 };
 
+#ifdef LFS2_ATTN_TIMELINE  // diagnostics build only (tools/attn_ab.py timeline): per-CTA clock64 stamps / wait totals
+__device__ long long g_attn_tl[4096][12];
+#define ATL_SET(slot, val) do { const int cid_ = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x; if (cid_ < 4096) g_attn_tl[cid_][slot] = (val); } while (0)
+#define ATL_T() clock64()
+#else
+#define ATL_SET(slot, val) do { } while (0)
+#define ATL_T() 0ll
+#endif
+
 template <int FMT>
 __global__ void __launch_bounds__(kPThreads, 2)
 attention_tc_pp_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_q,
+                       const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
                        const PpParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -101,6 +113,7 @@ attention_tc_pp_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int q0 = blockIdx.x * kPQ, h = blockIdx.y, b = blockIdx.z;
+  const long long tl_start = ATL_T();
   if (p.row_limit && q0 >= __ldg(p.row_limit + b) + p.limit_extra) return;
   const int kend = p.kend[b];
   const int ntiles = (kend + kPK - 1) / kPK;
@@ -191,15 +204,21 @@ attention_tc_pp_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
         __syncwarp();
       };
 
+      long long tl_wait_p = 0, tl_wait_v = 0;
       mbar_wait(&q_full, 0);
+      if (lane == 0) ATL_SET(1, ATL_T() - tl_start);   // Q tile landed
       tc_fence_after();
       issue_qk(0);
       if (ntiles > 1) issue_qk(1);
 #pragma unroll 1
       for (int j = 0; j < ntiles; ++j) {
         const int sb = j & 1, st = j % kPVS;
+        const long long tl_a = ATL_T();
         mbar_wait(&p_full[sb], (j >> 1) & 1);
+        const long long tl_b = ATL_T();
         mbar_wait(&v_full[st], (j / kPVS) & 1);
+        tl_wait_p += tl_b - tl_a;
+        tl_wait_v += ATL_T() - tl_b;
         tc_fence_after();
         if (elect_one()) {
           const uint32_t tp = tmem_base + kPColS + sb * kPK;  // P: packed pairs in the first 32 columns of the buffer
@@ -215,6 +234,11 @@ attention_tc_pp_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
         }
         __syncwarp();
         if (j + 2 < ntiles) issue_qk(j + 2);
+      }
+      if (lane == 0) {
+        ATL_SET(2, tl_wait_p);                         // MMA warp: cycles waiting for P (softmax)
+        ATL_SET(3, tl_wait_v);                         // ... for V tiles
+        ATL_SET(4, ATL_T() - tl_start);                // last PV issued
       }
     }
   } else {
@@ -235,6 +259,7 @@ attention_tc_pp_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
       return v;
     };
     uint32_t next_m0 = ntiles > 0 ? key_masked(0, 0) : 1u, next_m1 = ntiles > 0 ? key_masked(0, 1) : 1u;
+    long long tl_wait_s = 0, tl_first = 0;
 
 #pragma unroll 1
     for (int j = 0; j < ntiles; ++j) {
@@ -245,7 +270,10 @@ attention_tc_pp_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
         next_m0 = key_masked(j + 1, 0);
         next_m1 = key_masked(j + 1, 1);
       }
+      const long long tl_c = ATL_T();
       mbar_wait(&s_full[sb], (j >> 1) & 1);
+      tl_wait_s += ATL_T() - tl_c;
+      if (j == 0) tl_first = ATL_T() - tl_start;
       tc_fence_after();
       const uint32_t ts = tmem_base + kPColS + sb * kPK + lane_off;
       float s[kPK];
@@ -310,11 +338,13 @@ attention_tc_pp_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
       if (lane == 0) mbar_arrive(&p_full[sb]);
     }
 
-    // ---- epilogue: O / l -> ctx, straight from registers ----
+    // ---- epilogue: O / l -> ctx (hi/lo planes: staged, TMA stores; the optional fp32 copy straight from registers) ----
+    const long long tl_loop_end = ATL_T() - tl_start;
     if (ntiles > 0) {
       mbar_wait(&o_final, 0);
       tc_fence_after();
     }
+    const long long tl_ofinal = ATL_T() - tl_start;
     const float inv_l = 1.f / l_run;  // l == 0 (no unmasked key) -> inf -> NaN rows, like the reference
     const size_t orow = ((size_t)b * p.t + tq_row) * p.d + col_q;
     float o[32];
@@ -328,25 +358,61 @@ attention_tc_pp_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] = __int_as_float(0x7fc00000);
       }
+      if (p.ctx_hi) {
+        // hi | lo planes of this 128 x 32 chunk -> swizzled staging (two 16 KB buffers in the idle K ring) -> TMA stores;
+        // rows past the end of the utterance tensor are clipped by the store
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) split_pack2(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
+        uint8_t* sb = sK + (cc & 1) * kPSlot;
+        const bool st_issuer = warp == 2 && lane == 0;
+        if (cc >= 2) {  // the buffer's previous store has finished reading it
+          if (st_issuer) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+        }
+        uint8_t* rh = sb + r * 64;
+        uint8_t* rl = rh + kPSlot / 2;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int u = (i ^ ((r >> 1) & 3)) << 4;
+          *reinterpret_cast<uint4*>(rh + u) = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+          *reinterpret_cast<uint4*>(rl + u) = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (st_issuer) {
+          const uint64_t mh = reinterpret_cast<uint64_t>(&map_o_hi), ml = reinterpret_cast<uint64_t>(&map_o_lo);
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(mh),
+                       "r"(smem_u32(sb)), "r"(col_q + cc * 32), "r"(q0), "r"(b)
+                       : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(ml),
+                       "r"(smem_u32(sb + kPSlot / 2)), "r"(col_q + cc * 32), "r"(q0), "r"(b)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
       if (!row_ok) continue;
       if (p.ctx_f32) {
         float4* of = reinterpret_cast<float4*>(p.ctx_f32 + orow + cc * 32);
 #pragma unroll
         for (int i = 0; i < 8; ++i) of[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
       }
-      if (p.ctx_hi) {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) split_pack2(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
-        uint4* oh = reinterpret_cast<uint4*>(p.ctx_hi + orow + cc * 32);
-        uint4* ol = reinterpret_cast<uint4*>(p.ctx_lo + orow + cc * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-          ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-        }
-      }
     }
+    if (p.ctx_hi && warp == 2 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#ifdef LFS2_ATTN_TIMELINE
+    if (warp == 2 && lane == 0) {
+      ATL_SET(0, (long long)ntiles);
+      ATL_SET(5, tl_first);        // softmax: first S tile seen
+      ATL_SET(6, tl_wait_s);       // softmax: cycles waiting for S
+      ATL_SET(7, tl_loop_end);     // softmax: last P written
+      ATL_SET(8, tl_ofinal);       // O complete
+      ATL_SET(9, ATL_T() - tl_start);   // O rows stored
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      ATL_SET(10, (long long)smid);
+      ATL_SET(11, tl_start);
+    }
+#endif
   }
 
   tc_fence_before();
@@ -357,8 +423,15 @@ attention_tc_pp_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
   }
 }
 
+#ifdef LFS2_ATTN_TIMELINE
+extern "C" __attribute__((visibility("default"))) int lfs2_attn_timeline(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, g_attn_tl, sizeof(g_attn_tl)) == cudaSuccess ? 0 : 1;
+}
+#endif
+
 template <int FMT>
-static int launch_pp(const CUtensorMap& kv, const CUtensorMap& q, const PpParams& p, int batch, int nhead, cudaStream_t s) {
+static int launch_pp(const CUtensorMap& kv, const CUtensorMap& q, const CUtensorMap& oh, const CUtensorMap& ol,
+                     const PpParams& p, int batch, int nhead, cudaStream_t s) {
   auto kern = attention_tc_pp_kernel<FMT>;
   static bool configured = false;
   if (!configured) {
@@ -369,7 +442,7 @@ static int launch_pp(const CUtensorMap& kv, const CUtensorMap& q, const PpParams
     configured = true;
   }
   dim3 grid((p.t + kPQ - 1) / kPQ, nhead, batch);
-  kern<<<grid, kPThreads, kPSmem, s>>>(kv, q, p);
+  kern<<<grid, kPThreads, kPSmem, s>>>(kv, q, oh, ol, p);
   LFS2_CHECK_LAUNCH("attention_tc_pp");
   return LFS2_OK;
 }
@@ -378,8 +451,11 @@ static int launch_pp(const CUtensorMap& kv, const CUtensorMap& q, const PpParams
 int launch_attention_tc_pp(const void* qkv, int f16, const uint8_t* kpm, const int* kend, void* ctx_hi, void* ctx_lo,
                            float* ctx_f32, int batch, int t, int d, int nhead, const int* row_limit, int limit_extra,
                            cudaStream_t s) {
-  CUtensorMap kv, q;
-  const bool ok = make_tmap_3d(&kv, qkv, 3ull * d, t, batch, 32, kPK, 64) && make_tmap_3d(&q, qkv, 3ull * d, t, batch, 32, kPQ, 64);
+  CUtensorMap kv, q, oh, ol;
+  bool ok = make_tmap_3d(&kv, qkv, 3ull * d, t, batch, 32, kPK, 64) && make_tmap_3d(&q, qkv, 3ull * d, t, batch, 32, kPQ, 64);
+  oh = kv;
+  ol = kv;
+  if (ctx_hi) ok = ok && make_tmap_3d(&oh, ctx_hi, d, t, batch, 32, kPQ, 64) && make_tmap_3d(&ol, ctx_lo, d, t, batch, 32, kPQ, 64);
   LFS2_REQUIRE(ok, LFS2_ERR_CUDA, "attention_tc_pp: cuTensorMapEncodeTiled failed");
   PpParams p;
   p.kpm = kpm;
@@ -392,7 +468,7 @@ int launch_attention_tc_pp(const void* qkv, int f16, const uint8_t* kpm, const i
   p.scale_log2e = (float)(1.4426950408889634 / sqrt((double)kPD));
   p.row_limit = row_limit;
   p.limit_extra = limit_extra;
-  return f16 ? launch_pp<kFmtF16>(kv, q, p, batch, nhead, s) : launch_pp<kFmtBF16>(kv, q, p, batch, nhead, s);
+  return f16 ? launch_pp<kFmtF16>(kv, q, oh, ol, p, batch, nhead, s) : launch_pp<kFmtBF16>(kv, q, oh, ol, p, batch, nhead, s);
 }
 
 }  // namespace tc
