@@ -113,6 +113,7 @@ __global__ void wide_kend_kernel(const uint8_t* __restrict__ kpm, int* __restric
 template <int NC, int FMT, int CTAS>
 __global__ void __launch_bounds__(kWThreads, CTAS)
 attention_tc_wide_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_constant__ CUtensorMap map_q,
+                         const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
                          const WideParams p) {
   using Cfg = WideCfg<NC, CTAS>;
   constexpr int kKS = Cfg::kKS, kVS = Cfg::kVS;
@@ -340,7 +341,9 @@ attention_tc_wide_kernel(const __grid_constant__ CUtensorMap map_kv, const __gri
       if (lane == 0) mbar_arrive(&p_full[sb]);
     }
 
-    // ---- epilogue: O / l (this half's columns) -> ctx, straight from registers ----
+    // ---- epilogue: O / l (this half's columns) -> ctx.  The hi/lo planes leave through swizzled staging in the (by then
+    //      idle) Q tile and TMA stores, one or two 16 KB buffers per half (16-byte register stores half-fill their sectors:
+    //      in attention_tc_pp.cu they were 17 % of a CTA's life); the optional fp32 copy goes straight from registers ----
     xch[ntiles & 1][half][r] = l_run;
     w_pair_bar_sync(quad);
     l_run += xch[ntiles & 1][half ^ 1][r];
@@ -351,8 +354,11 @@ attention_tc_wide_kernel(const __grid_constant__ CUtensorMap map_kv, const __gri
     const float inv_l = 1.f / l_run;  // l == 0 (no unmasked key) -> inf -> NaN rows, like the reference
     const size_t orow = ((size_t)b * p.t + tq_row) * p.d + col_q;
     float o[32];
+    constexpr int kStBufs = NC >= 2 ? 2 : 1;             // staging buffers per half inside the Q tile (NC * 32 KB)
+    const bool st_issuer = quad == 0 && lane == 0;        // one thread per half issues / retires its stores
+    int st_k = 0;
 #pragma unroll 1
-    for (int cc = half * kChunksPerHalf; cc < (half + 1) * kChunksPerHalf; ++cc) {
+    for (int cc = half * kChunksPerHalf; cc < (half + 1) * kChunksPerHalf; ++cc, ++st_k) {
       if (ntiles > 0) {
         tmem_ld32(tmem_base + kColO + cc * 32 + lane_off, o);
 #pragma unroll
@@ -361,25 +367,47 @@ attention_tc_wide_kernel(const __grid_constant__ CUtensorMap map_kv, const __gri
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] = __int_as_float(0x7fc00000);
       }
+      if (p.ctx_hi) {
+        uint32_t hi[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) split_pack2(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
+        uint8_t* sb = sQ + (half * kStBufs + (st_k % kStBufs)) * 16384;
+        if (st_k >= kStBufs) {  // the buffer's previous store has finished reading it
+          if (st_issuer) {
+            if (kStBufs == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(8 + half) : "memory");
+        }
+        uint8_t* rh = sb + r * 64;
+        uint8_t* rl = rh + 8192;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int u = (i ^ ((r >> 1) & 3)) << 4;
+          *reinterpret_cast<uint4*>(rh + u) = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+          *reinterpret_cast<uint4*>(rl + u) = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+        }
+        fence_proxy_async_smem();
+        asm volatile("bar.sync %0, 128;" ::"r"(8 + half) : "memory");
+        if (st_issuer) {
+          const uint64_t mh = reinterpret_cast<uint64_t>(&map_o_hi), ml = reinterpret_cast<uint64_t>(&map_o_lo);
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(mh),
+                       "r"(smem_u32(sb)), "r"(col_q + cc * 32), "r"(q0), "r"(b)
+                       : "memory");
+          asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(ml),
+                       "r"(smem_u32(sb + 8192)), "r"(col_q + cc * 32), "r"(q0), "r"(b)
+                       : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
       if (!row_ok) continue;
       if (p.ctx_f32) {
         float4* of = reinterpret_cast<float4*>(p.ctx_f32 + orow + cc * 32);
 #pragma unroll
         for (int i = 0; i < 8; ++i) of[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
       }
-      if (p.ctx_hi) {
-        uint32_t hi[16], lo[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) split_pack2(o[2 * i], o[2 * i + 1], hi[i], lo[i]);
-        uint4* oh = reinterpret_cast<uint4*>(p.ctx_hi + orow + cc * 32);
-        uint4* ol = reinterpret_cast<uint4*>(p.ctx_lo + orow + cc * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          oh[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-          ol[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-        }
-      }
     }
+    if (p.ctx_hi && st_issuer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   tc_fence_before();
@@ -391,8 +419,8 @@ attention_tc_wide_kernel(const __grid_constant__ CUtensorMap map_kv, const __gri
 }
 
 template <int NC, int FMT, int CTAS = 1>
-static int launch_wide(const CUtensorMap& kv, const CUtensorMap& q, const WideParams& p, int batch, int nhead,
-                       cudaStream_t s) {
+static int launch_wide(const CUtensorMap& kv, const CUtensorMap& q, const CUtensorMap& oh, const CUtensorMap& ol,
+                       const WideParams& p, int batch, int nhead, cudaStream_t s) {
   constexpr int kSmem = WideCfg<NC, CTAS>::kSmem;
   auto kern = attention_tc_wide_kernel<NC, FMT, CTAS>;
   static bool configured = false;
@@ -404,7 +432,7 @@ static int launch_wide(const CUtensorMap& kv, const CUtensorMap& q, const WidePa
     configured = true;
   }
   dim3 grid((p.t + kWQ - 1) / kWQ, nhead, batch);
-  kern<<<grid, kWThreads, kSmem, s>>>(kv, q, p);
+  kern<<<grid, kWThreads, kSmem, s>>>(kv, q, oh, ol, p);
   LFS2_CHECK_LAUNCH("attention_tc_wide");
   return LFS2_OK;
 }
@@ -436,9 +464,11 @@ extern "C" int lfs2_attention_tc_wide(const void* qkv, int operand_format, const
   int* kend = reinterpret_cast<int*>(workspace);
   wide_kend_kernel<<<ceil_div((long long)batch * 32, 128), 128, 0, s>>>(key_padding_mask, kend, batch, t);
   LFS2_CHECK_LAUNCH("attn_kend");
-  CUtensorMap kv, q;
-  const bool ok = make_tmap_3d(&kv, qkv, 3ull * d, t, batch, 32, kWK, 64) &&
-                  make_tmap_3d(&q, qkv, 3ull * d, t, batch, 32, kWQ, 64);
+  CUtensorMap kv, q, oh, ol;
+  bool ok = make_tmap_3d(&kv, qkv, 3ull * d, t, batch, 32, kWK, 64) && make_tmap_3d(&q, qkv, 3ull * d, t, batch, 32, kWQ, 64);
+  oh = kv;
+  ol = kv;
+  if (ctx_hi) ok = ok && make_tmap_3d(&oh, ctx_hi, d, t, batch, 32, kWQ, 64) && make_tmap_3d(&ol, ctx_lo, d, t, batch, 32, kWQ, 64);
   LFS2_REQUIRE(ok, LFS2_ERR_CUDA, "attention_tc_wide: cuTensorMapEncodeTiled failed");
   WideParams p;
   p.kpm = key_padding_mask;
@@ -453,8 +483,8 @@ extern "C" int lfs2_attention_tc_wide(const void* qkv, int operand_format, const
   p.limit_extra = limit_extra;
   const bool f16 = operand_format == LFS2_OPERAND_F16;
   if (dh == 128)  // two CTAs per SM, warp pairs (variant 2 of lfs2_attention_tc_ex's single-plane kernels)
-    return f16 ? launch_wide<1, kFmtF16, 2>(kv, q, p, batch, nhead, s) : launch_wide<1, kFmtBF16, 2>(kv, q, p, batch, nhead, s);
+    return f16 ? launch_wide<1, kFmtF16, 2>(kv, q, oh, ol, p, batch, nhead, s) : launch_wide<1, kFmtBF16, 2>(kv, q, oh, ol, p, batch, nhead, s);
   if (dh == 384)
-    return f16 ? launch_wide<3, kFmtF16>(kv, q, p, batch, nhead, s) : launch_wide<3, kFmtBF16>(kv, q, p, batch, nhead, s);
-  return f16 ? launch_wide<2, kFmtF16>(kv, q, p, batch, nhead, s) : launch_wide<2, kFmtBF16>(kv, q, p, batch, nhead, s);
+    return f16 ? launch_wide<3, kFmtF16>(kv, q, oh, ol, p, batch, nhead, s) : launch_wide<3, kFmtBF16>(kv, q, oh, ol, p, batch, nhead, s);
+  return f16 ? launch_wide<2, kFmtF16>(kv, q, oh, ol, p, batch, nhead, s) : launch_wide<2, kFmtBF16>(kv, q, oh, ol, p, batch, nhead, s);
 }
