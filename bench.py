@@ -247,6 +247,46 @@ def measure_train(args, dev, rank, world, barrier):
     ops.PROFILE = None
     loss_vals = model.loss.last_buffer.tolist()
     frames = int(batch["duration"].sum())
+
+    def timed_variant(steps):
+        run_train_steps(model, dbatch, opt, sch, 2, world)
+        barrier()
+        c0 = _lib.CALLS
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        run_train_steps(model, dbatch, opt, sch, steps, world)
+        b.record()
+        barrier()
+        t = a.elapsed_time(b) / steps
+        if world > 1:
+            tt = torch.tensor([t], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t = float(tt[0])
+        return t, (_lib.CALLS - c0) // steps
+
+    # the same step as length-sorted sub-batches (model.train_length_buckets: same losses and gradients, PAD rows beyond
+    # each bucket's longest utterance + conv halo never computed) and in the single-pass bf16 mode
+    variants = {"length_buckets": [], "bf16_mode": None}
+    for nb in args.train_buckets:
+        if nb > 1 and int(batch["phones"].shape[0]) >= 2 * nb:
+            model.train_length_buckets = nb
+            t, c = timed_variant(args.train_steps)
+            variants["length_buckets"].append({"train_length_buckets": nb, "ms_per_step": t, "gpu_launches_per_step": c,
+                                               "total_loss": float(model.loss.last_buffer[-1])})
+    model.train_length_buckets = 1
+    if args.train_mode != "bf16":
+        model.set_compute_mode("bf16")
+        t, c = timed_variant(args.train_steps)
+        variants["bf16_mode"] = {"ms_per_step": t, "gpu_launches_per_step": c,
+                                 "total_loss": float(model.loss.last_buffer[-1])}
+        best = min(variants["length_buckets"], key=lambda r: r["ms_per_step"], default=None)
+        if best is not None:
+            model.train_length_buckets = best["train_length_buckets"]
+            t, c = timed_variant(args.train_steps)
+            variants["bf16_mode"]["with_length_buckets"] = {"train_length_buckets": best["train_length_buckets"],
+                                                            "ms_per_step": t, "gpu_launches_per_step": c}
+            model.train_length_buckets = 1
+        model.set_compute_mode(args.train_mode)
     nparams = sum(p.numel() for p in model.parameters() if p.requires_grad)
     if world > 1:
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
@@ -266,6 +306,13 @@ def measure_train(args, dev, rank, world, barrier):
            "parameters": nparams, "gpu_launches_per_step": launches,
            "allreduce_bytes_per_step": 0 if world == 1 else 4 * nparams,
            "final_losses": {"total": loss_vals[-1]},
+           "length_buckets": {"what": "the same step with model.train_length_buckets = n: n length-sorted sub-batches, each "
+                                      "padded to its own longest utterance + the conv halo; losses and gradients equal the "
+                                      "one-tensor step up to fp32 summation order (tests/test_gpu_round2.py)",
+                              "runs": variants["length_buckets"]},
+           "bf16_mode": dict(variants["bf16_mode"] or {}, what="the same step with model.set_compute_mode('bf16'): single-pass "
+                             "bf16 MMA operands, fp32 accumulation / LayerNorm / softmax / master weights / optimizer (the "
+                             "reference's recipe trains with --precision 16, scripts/train.sh)"),
            "config": {"workload": TRAIN_WORKLOAD, "preset": TRAIN_PRESET, "utterances_rank0": int(batch["phones"].shape[0]),
                       "padded_phones_rank0": int(batch["phones"].shape[1]), "mel_frames_rank0": int(batch["mel"].shape[1]),
                       "parallelism": f"data-parallel x{world}, one NCCL all-reduce of the flat fp32 gradient buffer"},
@@ -1074,6 +1121,8 @@ def main():
                     help="utterances of the timed batch vocoded by the HiFi-GAN generator under 'vocoder_hifigan' (0 = skip)")
     ap.add_argument("--train-steps", type=int, default=5, help="timed C4 train steps reported under 'train' (0 = skip)")
     ap.add_argument("--train-mode", default="fp32", choices=["simt", "fp32", "bf16"])
+    ap.add_argument("--train-buckets", type=int, nargs="*", default=[2, 3, 4],
+                    help="model.train_length_buckets values timed under train.length_buckets")
     ap.add_argument("--train-cpu-utts", type=int, default=2, help="utterances in the CPU train-step sample (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":

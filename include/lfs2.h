@@ -414,6 +414,13 @@ LFS2_API int lfs2_relu_bwd(const float* dy, const float* y, float* dx, long long
 /* dx = y > 0 ? dy * scale : 0: ReLU followed by dropout (model.py:120) in one pass -- y is the saved DROPPED
  * activation, so y > 0 is relu-mask and keep-mask at once and scale = 1/(1-p) */
 LFS2_API int lfs2_relu_bwd_scaled(const float* dy, const float* y, float* dx, long long n, float scale, void* stream);
+/* The same gradient written as bf16 hi/lo planes (the operand format of the input- and weight-gradient GEMMs that
+ * consume it) with the bias gradient in the same pass: dx = y > 0 ? dy * scale : 0, db[c] += sum_r dx[r, c] (db may be
+ * NULL).  y = the ReLU output either as fp32 (y_f32) or as the hi plane of its bf16 split (y_hi) -- exactly one of the
+ * two; rows x cols row-major, cols % 4 == 0.  Replaces relu_bwd + split_bf16 + colsum of the train step
+ * (autograd of F.relu / nn.Dropout / Conv1d bias in reference model.py:117-121, 539-557). */
+LFS2_API int lfs2_relu_bwd_planes(const float* dy, const float* y_f32, const void* y_hi, void* dx_hi, void* dx_lo,
+                                  float* db, int rows, int cols, float scale, void* stream);
 /* dst += src */
 LFS2_API int lfs2_add_inplace(float* dst, const float* src, long long n, void* stream);
 /* out (cols, rows) = in (rows, cols)^T -- transposed weight copies for the input-gradient GEMMs */

@@ -177,8 +177,11 @@ __global__ void transpose_kernel(const float* __restrict__ in, float* __restrict
 //   xhat = (z - mean) * rstd ; g = dy * gamma ; dz = rstd * (g - mean(g) - xhat * mean(g * xhat)) (+ add)
 //   dgamma += sum_rows dy * xhat ; dbeta += sum_rows dy     (register partials, one atomic per lane at the end)
 constexpr int kLnbMaxVec = 8;
-template <int NV>  // float4 column groups per lane: d <= 128 * NV
-__global__ void __launch_bounds__(256)
+// RELOAD (wide rows, NV >= 4): the second pass re-reads dy / z (L1 / L2 hits: the warp has just streamed the row) instead
+// of keeping g and xhat in 8 * NV registers; with the dgamma / dbeta partials that is what held the d = 768 kernel at
+// 139 registers = ONE 256-thread CTA per SM (2.3 TB/s).  Same arithmetic in the same order either way.
+template <int NV, bool RELOAD>  // float4 column groups per lane: d <= 128 * NV
+__global__ void __launch_bounds__(256, RELOAD ? (NV > 6 ? 2 : 3) : 1)
 layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ z, const float2* __restrict__ stats,
                      const float4* __restrict__ gamma, const float4* __restrict__ add, float4* __restrict__ dz,
                      float4* __restrict__ dz_drop, float* __restrict__ dgamma, float* __restrict__ dbeta, int m, int d4,
@@ -196,7 +199,7 @@ layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ z
   for (int row = warp; row < m; row += nwarps) {
     const float2 st = stats[row];
     const float mean = st.x, rstd = st.y;
-    float4 g[NV], xh[NV];
+    float4 g[RELOAD ? 1 : NV], xh[RELOAD ? 1 : NV];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
@@ -212,8 +215,10 @@ layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ z
         gg.x = dv.x * gm.x; gg.y = dv.y * gm.y; gg.z = dv.z * gm.z; gg.w = dv.w * gm.w;
         s1 += (gg.x + gg.y) + (gg.z + gg.w);
         s2 += (gg.x * x.x + gg.y * x.y) + (gg.z * x.z + gg.w * x.w);
-        g[i] = gg;
-        xh[i] = x;
+        if (!RELOAD) {
+          g[i] = gg;
+          xh[i] = x;
+        }
       }
     }
     const float c1 = warp_sum(s1) * inv_d, c2 = warp_sum(s2) * inv_d;
@@ -221,11 +226,20 @@ layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ z
     for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       if (c < d4) {
+        float4 gi, xi;
+        if (RELOAD) {
+          const float4 dv = dy[(size_t)row * d4 + c], zv = z[(size_t)row * d4 + c], gm = __ldg(gamma + c);
+          xi.x = (zv.x - mean) * rstd; xi.y = (zv.y - mean) * rstd; xi.z = (zv.z - mean) * rstd; xi.w = (zv.w - mean) * rstd;
+          gi.x = dv.x * gm.x; gi.y = dv.y * gm.y; gi.z = dv.z * gm.z; gi.w = dv.w * gm.w;
+        } else {
+          gi = g[i];
+          xi = xh[i];
+        }
         float4 o;
-        o.x = rstd * (g[i].x - c1 - xh[i].x * c2);
-        o.y = rstd * (g[i].y - c1 - xh[i].y * c2);
-        o.z = rstd * (g[i].z - c1 - xh[i].z * c2);
-        o.w = rstd * (g[i].w - c1 - xh[i].w * c2);
+        o.x = rstd * (gi.x - c1 - xi.x * c2);
+        o.y = rstd * (gi.y - c1 - xi.y * c2);
+        o.z = rstd * (gi.z - c1 - xi.z * c2);
+        o.w = rstd * (gi.w - c1 - xi.w * c2);
         if (dz_drop) {  // gradient of the dropped branch: z = x + drop(y)  =>  dy = drop(dz) with the forward's mask
           const float4 k = dropout_scale4((size_t)row * d4 + c, drop.threshold, drop.inv_keep, drop.key, drop.site);
           dz_drop[(size_t)row * d4 + c] = make_float4(o.x * k.x, o.y * k.y, o.z * k.z, o.w * k.w);
@@ -599,7 +613,7 @@ int lfs2_layernorm_bwd_drop(const float* dy, const float* z, const float* stats,
   if (blocks < 1) blocks = 1;
   const int nv = ceil_div(d / 4, 32);
 #define LFS2_LNB(NV)                                                                                            \
-  layernorm_bwd_kernel<NV><<<blocks, 256, 0, (cudaStream_t)stream>>>(                                           \
+  layernorm_bwd_kernel<NV, (NV >= 4)><<<blocks, 256, 0, (cudaStream_t)stream>>>(                                \
       (const float4*)dy, (const float4*)z, (const float2*)stats, (const float4*)gamma, (const float4*)add,      \
       (float4*)dz, (float4*)dz_drop, dgamma, dbeta, m, d / 4, drop)
   if (nv <= 1) LFS2_LNB(1);

@@ -723,6 +723,11 @@ class FastSpeech2(_Base):
         return out
 
     # -- train step: forward with saved activations + hand-written backward (training.py) -----
+    # train_length_buckets = n > 1: the train step of a ragged batch runs as n length-sorted sub-batches, each padded to
+    # its own longest utterance + the conv halo (training.forward_train_bucketed); losses and gradients equal the
+    # un-bucketed step up to fp32 summation order, result positions the loss masks come back as zeros.  Off by default.
+    train_length_buckets = 1
+
     def _forward_train(self, targets):
         """Teacher-forced forward (reference :636-784 with inference=False) whose outputs are connected
         to autograd through ONE Function; its backward runs the liblfs2.so gradient kernels and

@@ -57,6 +57,16 @@ class Engine:
         ops.dropout_(x, *tok)
         return tok
 
+    def dropout_any(self, x, p):
+        """dropout of an fp32 tensor (in place) or of Planes (new planes) -> (result, replay token)"""
+        if not isinstance(x, ops.Planes):
+            return x, self.dropout_(x, p)
+        if p <= 0:
+            return x, None
+        self.site += 1
+        tok = (p, self.seed, self.site)
+        return ops.dropout_planes(x, *tok), tok
+
     @staticmethod
     def dropout_bwd(dy, tok, inplace=True):
         """gradient through a dropout site: same mask, same 1/(1-p) scale"""
@@ -154,9 +164,10 @@ class Engine:
         if self.tc and ops.wgrad_tc_ok(n, k):
             ops.gemm_wgrad_tc_(dw, self._planes(dy), self._planes(x), npass=self.npass, tag=tag)
         else:
+            dy = ops.merge_planes(dy) if isinstance(dy, ops.Planes) else dy
             ops.gemm_tn_(dw, dy, ops.merge_planes(x) if isinstance(x, ops.Planes) else x)
         if db is not None:
-            ops.colsum_(db, dy)
+            ops.colsum_(db, ops.merge_planes(dy) if isinstance(dy, ops.Planes) else dy)
 
 
 def _mat(w):
@@ -190,8 +201,10 @@ def fft_fwd(L, E, x, kpm):
     if L.depthwise:
         s["dw_wt"] = ops.transpose(_dwmat(dwc.weight))                    # (k, d)
         s["u"] = E.dwconv(x1, s["dw_wt"], dwc.bias)
-        s["v"] = E.linear(s["u"], _mat(pw.weight), pw.bias, relu=True, tag="ffn1_gemm")
-        s["dropv"] = E.dropout_(s["v"], p)                                # dropout after ReLU (model.py:120)
+        # the F-wide activation only feeds GEMMs (FFN-2 forward, FFN-1 weight gradient) and the ReLU mask of the
+        # backward: on the tensor-core path it exists as bf16 planes only (no fp32 copy, no split pass)
+        s["v"] = E.linear(s["u"], _mat(pw.weight), pw.bias, relu=True, tag="ffn1_gemm", planes_out=E.tc)
+        s["v"], s["dropv"] = E.dropout_any(s["v"], p)                     # dropout after ReLU (model.py:120)
         s["w_eff"], b_eff = ops.fold_pw(_mat(pw2.weight), _mat(gc.weight), gc.bias, pw2.bias)
         y = E.linear(s["v"], s["w_eff"], b_eff, tag="ffn2_gemm")
     else:                                                                  # dense convolutions (model.py:95-106)
@@ -230,9 +243,15 @@ def _ffn_bwd_depthwise(L, E, s, dy, dev):
     ops.fold_pw_bwd_(dw_eff, db_eff, _mat(pw2.weight), _mat(gc.weight), gc.bias, _mat(grad_of(pw2.weight)),
                      _mat(grad_of(gc.weight)), grad_of(gc.bias), grad_of(pw2.bias))
     # ReLU + the dropout behind it in one pass: s["v"] is the dropped activation, so v > 0 is both masks
-    ops.relu_bwd_(dv, s["v"], scale=1.0 / (1.0 - s["dropv"][0]) if s["dropv"] else 1.0)
-    du = E.dgrad(dv, _mat(pw.weight), tag="ffn1_dgrad")
-    E.wgrad_(_mat(grad_of(pw.weight)), grad_of(pw.bias), dv, s["u"], tag="ffn1_wgrad")
+    scale = 1.0 / (1.0 - s["dropv"][0]) if s["dropv"] else 1.0
+    if E.tc:   # the masked gradient as planes (its two consumers are GEMMs) + the bias gradient, one kernel
+        dv = ops.relu_bwd_planes(dv, s["v"], scale=scale, db=grad_of(pw.bias))
+        du = E.dgrad(dv, _mat(pw.weight), tag="ffn1_dgrad")
+        E.wgrad_(_mat(grad_of(pw.weight)), None, dv, s["u"], tag="ffn1_wgrad")
+    else:
+        ops.relu_bwd_(dv, s["v"], scale=scale)
+        du = E.dgrad(dv, _mat(pw.weight), tag="ffn1_dgrad")
+        E.wgrad_(_mat(grad_of(pw.weight)), grad_of(pw.bias), dv, s["u"], tag="ffn1_wgrad")
     return _dwconv_bwd(dwc, s["dw_wt"], du, s["x1"])
 
 
@@ -289,6 +308,12 @@ def vp_bwd(P, E, s, dout):
         conv, ln = layer.layers[0].module, layer.layers[2]
         E.dropout_bwd(dz, sl["drop"])
         dh = ops.layernorm_bwd(dz, sl["h"], sl["st"], ln.weight, grad_of(ln.weight), grad_of(ln.bias))
+        if layer.depthwise and E.tc:
+            dh = ops.relu_bwd_planes(dh, sl["h"], db=grad_of(conv[1].bias))
+            du = E.dgrad(dh, _mat(conv[1].weight), tag="predictor_dgrad")
+            E.wgrad_(_mat(grad_of(conv[1].weight)), None, dh, sl["u"], tag="predictor_wgrad")
+            dz = _dwconv_bwd(conv[0], sl["dw_wt"], du, sl["x"])
+            continue
         ops.relu_bwd_(dh, sl["h"])
         if layer.depthwise:
             du = E.dgrad(dh, _mat(conv[1].weight), tag="predictor_dgrad")
@@ -302,8 +327,10 @@ def vp_bwd(P, E, s, dout):
 
 # ------------------------------------------------------------------------------------------
 # whole model (reference fastspeech2.py:636-784, teacher-forced branch)
-def forward_train(M, targets):
-    """-> (result dict with the reference's keys, saved state for backward_train)"""
+def forward_train(M, targets, frames=None):
+    """-> (result dict with the reference's keys, saved state for backward_train).
+    frames = (l, cap): length of the LengthRegulator output (l >= cap, frames in [cap, l) are PAD) for a length bucket
+    whose tensor ends before / beyond its own longest utterance (forward_train_bucketed); None = the batch's own."""
     hp = M.hparams
     dev = M.device
     E = Engine(M.compute_mode)
@@ -351,7 +378,7 @@ def forward_train(M, targets):
         S["phone_vars"].append((var, s_vp, idx))
         result[f"variances_{var}"] = pred
     duration = targets["duration"].to(dev)
-    x, tgt_mask, S["cum"] = ops.length_regulate_train(x, duration, va.max_length)
+    x, tgt_mask, S["cum"] = ops.length_regulate_train(x, duration, va.max_length, frames=frames)
     S["vars"] = []
     for i, var in enumerate(va.variances):
         if va.variance_levels[i] != "frame":
@@ -436,6 +463,85 @@ def backward_train(M, S, dmel, ddur, dvars):
     ops.colsum_(grad_of(proj.bias), dspk)
 
 
+# ------------------------------------------------------------------------------------------
+# length-bucketed train step (SURVEY 8f N2 carried to the gradient path)
+def forward_train_bucketed(M, targets, ngroups):
+    """The teacher-forced forward of a ragged batch as `ngroups` length-sorted sub-batches, each padded only to ITS
+    longest utterance plus the conv halo (`FastSpeech2._halos`), results scattered back into full-batch tensors.
+
+    Exactness (same argument as `_forward_bucketed`): PAD rows are never attention keys and the loss masks them, so a
+    PAD row reaches the loss only through the FFN / predictor convolutions of the layers above it; rows within the
+    summed conv half-widths of an utterance's end are kept and hold exactly what the reference computes there
+    (PE[t] + speaker term + embedding of the collated target's padding value, ...), rows farther out have a zero
+    gradient and feed nothing.  Losses and parameter gradients therefore equal the un-bucketed step up to fp32
+    summation order; result positions the loss masks come back as zeros instead of the reference's PAD-row values.
+    -> (full-batch result dict, [(index tensor, tp_g, l_g, saved state), ...])"""
+    dev, hp, va = M.device, M.hparams, M.variance_adaptor
+    phones_all, dur_all = targets["phones"], targets["duration"]
+    bsz, tp = phones_all.shape
+    pos = torch.arange(1, tp + 1, device=phones_all.device)
+    nphones = ((phones_all != 0) * pos).amax(1)                                   # last valid phone + 1
+    nphones, nframes = torch.stack([nphones.to(torch.int64),
+                                    dur_all.sum(1).to(nphones.device, torch.int64)]).tolist()    # ONE read-back
+    cap = int(va.max_length)
+    l_full = min(max(nframes), cap)
+    h_enc = sum(layer.halo() for layer in M.encoder.layers) + max(
+        [va.duration_predictor.halo()] + [va.encoders[v].predictor.halo() for i, v in enumerate(va.variances)
+                                          if va.variance_levels[i] == "phone"])
+    h_dec = max([sum(layer.halo() for layer in M.decoder.layers)] +
+                [va.encoders[v].predictor.halo() for i, v in enumerate(va.variances) if va.variance_levels[i] == "frame"])
+    order = sorted(range(bsz), key=lambda i: (-nframes[i], -nphones[i]))
+    ngroups = max(1, min(int(ngroups), bsz))
+    per = (bsz + ngroups - 1) // ngroups
+    parts = []
+    for g0 in range(0, bsz, per):
+        idx = order[g0:g0 + per]
+        tp_g = min(tp, max(nphones[i] for i in idx) + h_enc)
+        cap_g = min(max(nframes[i] for i in idx), cap)
+        frames = (min(cap_g + h_dec, l_full), cap_g)
+        it = {}
+
+        def take(v, it=it, idx=idx):
+            if not (torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == bsz):
+                return v
+            if v.device not in it:
+                it[v.device] = torch.tensor(idx, device=v.device)
+            return v[it[v.device]]
+
+        sub = {k: take(v) for k, v in targets.items()}
+        sub["phones"] = sub["phones"][:, :tp_g].contiguous()
+        sub["duration"] = sub["duration"][:, :tp_g].contiguous()
+        r, s = forward_train(M, sub, frames=frames)
+        parts.append((torch.tensor(idx, device=dev), tp_g, frames[0], r, s))
+    out = {"mel": torch.zeros(bsz, l_full, hp.n_mels, device=dev),
+           "duration_prediction": torch.zeros(bsz, tp, device=dev),
+           "duration_rounded": dur_all.to(dev),
+           "src_mask": phones_all.to(dev) == 0,
+           "tgt_mask": torch.ones(bsz, l_full, device=dev, dtype=torch.bool)}
+    for i, v in enumerate(va.variances):
+        out[f"variances_{v}"] = torch.zeros(bsz, tp if va.variance_levels[i] == "phone" else l_full, device=dev)
+    saved = []
+    for it, tp_g, l_g, r, s in parts:
+        out["mel"][it, :l_g] = r["mel"]
+        out["tgt_mask"][it, :l_g] = r["tgt_mask"]
+        out["duration_prediction"][it, :tp_g] = r["duration_prediction"]
+        for i, v in enumerate(va.variances):
+            w = tp_g if va.variance_levels[i] == "phone" else l_g
+            out[f"variances_{v}"][it, :w] = r[f"variances_{v}"]
+        saved.append((it, tp_g, l_g, s))
+    return out, saved
+
+
+def backward_train_bucketed(M, saved, dmel, ddur, dvars):
+    """gradients of the full-batch results -> one backward_train per length bucket (parameter gradients accumulate)"""
+    va = M.variance_adaptor
+    levels = dict(zip(va.variances, va.variance_levels))
+    for it, tp_g, l_g, s in saved:
+        dv = {v: g[it, :(tp_g if levels[v] == "phone" else l_g)].contiguous() for v, g in dvars.items() if g is not None}
+        backward_train(M, s, None if dmel is None else dmel[it, :l_g].contiguous(),
+                       None if ddur is None else ddur[it, :tp_g].contiguous(), dv)
+
+
 class ForwardTrainFn(torch.autograd.Function):
     """autograd boundary of the train step: tensors out, gradients in; everything between is kernels
     of liblfs2.so.  ``anchor`` is a dummy scalar that requires grad so that autograd calls backward;
@@ -443,7 +549,9 @@ class ForwardTrainFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, anchor, model, targets, keys):
-        result, saved = forward_train(model, targets)
+        nb = int(getattr(model, "train_length_buckets", 1))
+        ctx.bucketed = nb > 1 and targets["phones"].shape[0] > 1
+        result, saved = forward_train_bucketed(model, targets, nb) if ctx.bucketed else forward_train(model, targets)
         ctx.model, ctx.saved, ctx.keys = model, saved, keys
         model._last_train_result = result
         return tuple(result[k] for k in keys)
@@ -452,6 +560,7 @@ class ForwardTrainFn(torch.autograd.Function):
     def backward(ctx, *grads):
         g = dict(zip(ctx.keys, grads))
         dvars = {k[len("variances_"):]: v for k, v in g.items() if k.startswith("variances_")}
-        backward_train(ctx.model, ctx.saved, g.get("mel"), g.get("duration_prediction"), dvars)
+        (backward_train_bucketed if ctx.bucketed else backward_train)(ctx.model, ctx.saved, g.get("mel"),
+                                                                      g.get("duration_prediction"), dvars)
         ctx.saved = None
         return None, None, None, None

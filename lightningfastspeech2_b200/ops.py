@@ -893,6 +893,27 @@ def relu_bwd_(dy, y, scale=1.0):
     return dy
 
 
+def relu_bwd_planes(dy, y, scale=1.0, db=None):
+    """-> Planes of (y > 0 ? dy * scale : 0); db (cols) += its column sums.  y: the ReLU output as an fp32 tensor or as
+    Planes (only the sign of the hi plane is read).  One pass instead of relu_bwd_ + split_bf16 + colsum_."""
+    _chk(dy, torch.float32, "relu_bwd_planes dy")
+    cols = dy.shape[-1]
+    rows = dy.numel() // cols
+    if isinstance(y, Planes):
+        if y.hi.dtype != torch.bfloat16 or tuple(y.hi.shape) != tuple(dy.shape) or not y.hi.is_contiguous():
+            raise ValueError("relu_bwd_planes: y must be contiguous bf16 planes shaped like dy")
+        y32, yhi = None, y.hi
+    else:
+        _chk(y, torch.float32, "relu_bwd_planes y")
+        if tuple(y.shape) != tuple(dy.shape):
+            raise ValueError("relu_bwd_planes: y must be shaped like dy")
+        y32, yhi = y, None
+    out = _empty_planes(dy.shape, dy.device)
+    _launch("lfs2_relu_bwd_planes", _p(dy), _p(y32), _p(yhi), _p(out.hi), _p(out.lo), _p(db), rows, cols, float(scale),
+            _s(), tag="lfs2_relu_bwd", nbytes=(10.0 if yhi is not None else 12.0) * dy.numel())
+    return out
+
+
 def add_(dst, src):
     _launch("lfs2_add_inplace", _p(dst), _p(src), dst.numel(), _s(), nbytes=12.0 * dst.numel())
     drop_planes(dst)
@@ -936,10 +957,10 @@ def attention_bwd(qkv, ctx, dctx, lse, kpm, nhead):
     return dqkv
 
 
-def length_regulate_train(x, durations, max_length):
-    """length_regulate that also returns the prefix sums its backward needs"""
+def length_regulate_train(x, durations, max_length, frames=None):
+    """length_regulate that also returns the prefix sums its backward needs; frames = (l, cap) as in length_regulate"""
     scan = length_regulate_scan(durations, x.shape[:2])
-    out, mask = length_regulate(x, durations, max_length, scan=scan)
+    out, mask = length_regulate(x, durations, max_length, scan=scan, frames=frames)
     return out, mask, scan[0]
 
 

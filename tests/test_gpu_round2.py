@@ -341,3 +341,93 @@ def test_decoder_input_planes_equals_the_three_kernels_it_replaces(with_bucket, 
         assert torch.equal(idx, idx_ref)
     if with_acc:
         assert torch.equal(acc, ref_acc)
+
+
+# ------------------------------------------------------------------------- train step, second pass
+@pytest.mark.parametrize("y_planes", [False, True])
+@pytest.mark.parametrize("rows,cols", [(300, 256), (1031, 3072), (7, 64)])
+def test_relu_bwd_planes_equals_relu_bwd_split_colsum(rows, cols, y_planes):
+    """lfs2_relu_bwd_planes == relu_bwd_ -> split_bf16 bit for bit (planes) and == colsum_ up to summation order"""
+    g = torch.Generator().manual_seed(rows + cols)
+    dy = (torch.randn(rows, cols, generator=g) * 1e-4).to(DEV)
+    y = torch.relu(torch.randn(rows, cols, generator=g)).to(DEV)
+    yp = ops.split_bf16(y)
+    if y_planes:
+        y = ops.merge_planes(yp)     # what the hi plane's sign stands for
+    scale = 1.0 / 0.9
+    db0 = torch.randn(cols, generator=g).to(DEV)
+    db = db0.clone()
+    got = ops.relu_bwd_planes(dy, yp if y_planes else y, scale=scale, db=db)
+    ref = ops.relu_bwd_(dy.clone(), y, scale=scale)
+    want = ops.split_bf16(ref)
+    assert torch.equal(got.hi, want.hi) and torch.equal(got.lo, want.lo)
+    want_db = db0.double() + ref.double().sum(0)
+    assert float((db.double() - want_db).abs().max()) <= 1e-5 * max(1.0, float(want_db.abs().max()))
+    nodb = ops.relu_bwd_planes(dy, yp if y_planes else y, scale=scale)
+    assert torch.equal(nodb.hi, want.hi)
+
+
+@pytest.mark.parametrize("d", [256, 768, 1024])
+def test_layernorm_bwd_wide_rows_match_autograd(d):
+    """the register-light (reload) variant of lfs2_layernorm_bwd that serves d > 256"""
+    m = 517
+    g = torch.Generator().manual_seed(d)
+    z = torch.randn(m, d, generator=g, dtype=torch.float64, requires_grad=True)
+    gamma = torch.randn(d, generator=g, dtype=torch.float64, requires_grad=True)
+    beta = torch.randn(d, generator=g, dtype=torch.float64, requires_grad=True)
+    dy = torch.randn(m, d, generator=g, dtype=torch.float64)
+    torch.nn.functional.layer_norm(z, (d,), gamma, beta, 1e-5).backward(dy)
+    zf = z.detach().float().to(DEV)
+    mean = zf.double().mean(1)
+    rstd = 1.0 / torch.sqrt(zf.double().var(1, unbiased=False) + 1e-5)
+    stats = torch.stack([mean, rstd], 1).float().contiguous()
+    dg, db = torch.zeros(d, device=DEV), torch.zeros(d, device=DEV)
+    dz = ops.layernorm_bwd(dy.float().to(DEV), zf, stats, gamma.detach().float().to(DEV), dg, db)
+    for got, want, name in ((dz, z.grad, "dz"), (dg, gamma.grad, "dgamma"), (db, beta.grad, "dbeta")):
+        err = float((got.double().cpu() - want).abs().max()) / float(want.abs().max())
+        assert err <= 2e-5, (name, err)
+
+
+@pytest.mark.parametrize("preset,mode,nb,tol", [("SMALL_TRAIN", "simt", 2, 2e-5), ("SMALL_TRAIN_PHONE", "simt", 3, 2e-5),
+                                                ("C2_TRAIN", "fp32", 3, 2e-4), ("C4_P0", "fp32", 2, 2e-4)])
+def test_train_length_buckets_equal_the_unbucketed_step(preset, mode, nb, tol):
+    """model.train_length_buckets = n: losses, every parameter gradient and every result position the loss reads equal
+    the one-tensor step (up to fp32 summation order: the buckets add their weight gradients one after the other)"""
+    model, sd, hp = _build(preset, 5, mode, train=True)
+    model.log_losses = False
+    levels = hp["variance_levels"]
+    batch = synthetic.add_train_targets(synthetic.make_batch(7, 9, 60, seed=21), hp["variances"], seed=21, levels=levels)
+    batch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    runs = {}
+    for buckets in (1, nb):
+        model.train_length_buckets = buckets
+        model.zero_grad(set_to_none=True)
+        result = model(batch)
+        losses = model.loss(result, batch)
+        losses["total"].backward()
+        torch.cuda.synchronize()
+        runs[buckets] = ({k: (v.detach().clone() if torch.is_tensor(v) else v) for k, v in result.items()},
+                         model.loss.last_buffer.clone(),
+                         {k: p.grad.detach().clone() for k, p in model.named_parameters() if p.grad is not None})
+    model.train_length_buckets = 1
+    (r1, l1, g1), (rn, ln, gn) = runs[1], runs[nb]
+    assert torch.allclose(l1, ln, rtol=1e-5, atol=1e-6), (l1.tolist(), ln.tolist())
+    assert set(g1) == set(gn)
+    scale = max(float(g.abs().max()) for g in g1.values())
+    worst = ("", 0.0)
+    for k in g1:
+        e = float((g1[k].double() - gn[k].double()).norm()) / max(float(g1[k].double().norm()), 1e-3 * scale * g1[k].numel() ** 0.5)
+        if e > worst[1]:
+            worst = (k, e)
+        assert e <= tol, (k, e)
+    assert torch.equal(r1["tgt_mask"], rn["tgt_mask"]) and torch.equal(r1["src_mask"], rn["src_mask"])
+    valid = ~r1["tgt_mask"]
+    ftol = 1e-5 if mode == "simt" else 1e-4
+    assert float((r1["mel"] - rn["mel"])[valid].abs().max()) <= ftol * max(1.0, float(r1["mel"][valid].abs().max()))
+    assert float(rn["mel"][r1["tgt_mask"]].abs().max()) == 0.0     # masked positions: zeros, not the PAD-row values
+    pv = ~r1["src_mask"]
+    assert float((r1["duration_prediction"] - rn["duration_prediction"])[pv].abs().max()) <= ftol * 10
+    for i, v in enumerate(hp["variances"]):
+        m = pv if levels[i] == "phone" else valid
+        assert float((r1[f"variances_{v}"] - rn[f"variances_{v}"])[m].abs().max()) <= ftol * 10, v
+    print(f"train_length_buckets={nb} [{preset}, {mode}]: worst per-tensor gradient difference {worst[1]:.2e} at {worst[0]}")

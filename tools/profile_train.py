@@ -1,7 +1,9 @@
 """Run a few C4 train steps (bench.py's "train" workload) -- for ncu, or stand-alone to print the
-CUDA-event table of one step: `python tools/profile_train.py [steps] [mode] [preset] [--table]`."""
+CUDA-event table of one step: `python tools/profile_train.py [steps] [mode] [preset] [--table] [--buckets=n]`
+(--buckets: model.train_length_buckets; the host's issue time per step is printed beside the device time)."""
 import os
 import sys
+import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -18,6 +20,9 @@ dev = torch.device("cuda", 0)
 model, sd, hp = bench.build_train_model(dev, preset)
 model.set_compute_mode(mode)
 model.log_losses = False
+for a in sys.argv[1:]:
+    if a.startswith("--buckets="):
+        model.train_length_buckets = int(a.split("=")[1])
 batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in bench.train_batch(hp, 0, 1).items()}
 (opt,), (sch,) = model.configure_optimizers()
 bench.run_train_steps(model, batch, opt, sch["scheduler"], steps, 1)
@@ -25,10 +30,13 @@ torch.cuda.synchronize()
 if "--table" in sys.argv:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    t0 = time.perf_counter()
     bench.run_train_steps(model, batch, opt, sch["scheduler"], 3, 1)
+    t1 = time.perf_counter()
     e1.record()
     torch.cuda.synchronize()
-    print(f"wall per step: {e0.elapsed_time(e1) / 3:.2f} ms")
+    print(f"train_length_buckets = {model.train_length_buckets}, mode {mode}")
+    print(f"wall per step: {e0.elapsed_time(e1) / 3:.2f} ms (host issue time per step: {1e3 * (t1 - t0) / 3:.2f} ms)")
     ops.PROFILE = {}
     bench.run_train_steps(model, batch, opt, sch["scheduler"], 1, 1)
     prof = ops.collect_profile()
