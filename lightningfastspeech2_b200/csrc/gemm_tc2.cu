@@ -18,6 +18,12 @@
 // hi.hi.  Accumulation is fp32 in TMEM.  The contraction can be split across CTAs (grid.y): the
 // epilogue then reduces into C with fp32 vector atomics (weight gradients accumulate into p.grad).
 // Warp roles: 0 = TMA producer, 1 = MMA issuer + TMEM owner, 2..5 = epilogue (thread = output row).
+// MH = 2 (m >= 256): a CTA owns TWO 128-row accumulators of the same column tile (2 x 256 tensor-memory columns) and
+// issues every B slab against both A halves.  With hi/lo planes on both operands a 128 x 256 tile moves 48 KB from L2
+// per 768 MMA cycles = 62 B/clk/SM, above what the L2 delivers per SM (~43 B/clk with all 148 SMs pulling: the weight
+// gradients ran at 53 % of the 3-pass issue rate); 256 x 256 moves 64 KB per 1536 cycles = 42 B/clk.
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace lfs2 {
@@ -43,9 +49,10 @@ struct G2Params {
   int atomic;
 };
 
-template <int N_TILE, int NPASS>
+template <int N_TILE, int NPASS, int MH>
 struct G2Smem {
-  static constexpr int kAPlane = kG2M * kG2K * 2;    // 8 KB
+  static constexpr int kAHalf = kG2M * kG2K * 2;     // 8 KB: one 128-row half of the A slab
+  static constexpr int kAPlane = MH * kAHalf;
   static constexpr int kBPlane = N_TILE * kG2K * 2;  // 8 / 16 KB
   static constexpr int kPlanes = NPASS == 3 ? 2 : 1;
   static constexpr int kStage = kPlanes * (kAPlane + kBPlane);
@@ -70,14 +77,14 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <bool A_MN, bool B_MN, int N_TILE, int NPASS>
+template <bool A_MN, bool B_MN, int N_TILE, int NPASS, int MH>
 __global__ void __launch_bounds__(kG2Threads, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                 const G2Params p) {
-  using L = G2Smem<N_TILE, NPASS>;
+  using L = G2Smem<N_TILE, NPASS, MH>;
   constexpr int kStages = L::kStages;
-  constexpr uint32_t kTmemCols = N_TILE <= 128 ? 128 : 256;
+  constexpr uint32_t kTmemCols = MH * N_TILE <= 128 ? 128 : (MH * N_TILE <= 256 ? 256 : 512);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], acc_full;
@@ -85,7 +92,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x, split = blockIdx.y, z = blockIdx.z;
-  const int m0 = (tile / p.n_tiles) * kG2M, n0 = (tile % p.n_tiles) * N_TILE;
+  const int m0 = (tile / p.n_tiles) * (kG2M * MH), n0 = (tile % p.n_tiles) * N_TILE;
   const int h = z % p.nhead, b = z / p.nhead;
   const int k_begin = split * p.k_per_split;
   const int k_end = min(p.k, k_begin + p.k_per_split);
@@ -118,10 +125,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         uint8_t* st = smem + stage * L::kStage;
         const int k0 = k_begin + ks * kG2K;
         mbar_expect_tx(&full_bar[stage], L::kStage);
-        g2_load<A_MN>(st, &map_a_hi, &full_bar[stage], ca, m0, kG2M, k0, za);
+        g2_load<A_MN>(st, &map_a_hi, &full_bar[stage], ca, m0, kG2M * MH, k0, za);
         g2_load<B_MN>(st + L::kOffBHi, &map_b_hi, &full_bar[stage], cb, n0, N_TILE, k0, zb);
         if (NPASS == 3) {
-          g2_load<A_MN>(st + L::kOffALo, &map_a_lo, &full_bar[stage], ca, m0, kG2M, k0, za);
+          g2_load<A_MN>(st + L::kOffALo, &map_a_lo, &full_bar[stage], ca, m0, kG2M * MH, k0, za);
           g2_load<B_MN>(st + L::kOffBLo, &map_b_lo, &full_bar[stage], cb, n0, N_TILE, k0, zb);
         }
         if (++stage == kStages) {
@@ -147,11 +154,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
         const uint64_t b_lo = desc_advance(db0, stage * L::kStage + L::kOffBLo);
 #pragma unroll
         for (int s = 0; s < kG2K / 16; ++s) {
-          if (ks == 0 && s == 0) umma_f16_c<false>(tmem_base, a_hi, b_hi, idesc);
-          else umma_f16_c<true>(tmem_base, desc_advance(a_hi, s * kStepA), desc_advance(b_hi, s * kStepB), idesc);
-          if (NPASS == 3) {
-            umma_f16_c<true>(tmem_base, desc_advance(a_lo, s * kStepA), desc_advance(b_hi, s * kStepB), idesc);
-            umma_f16_c<true>(tmem_base, desc_advance(a_hi, s * kStepA), desc_advance(b_lo, s * kStepB), idesc);
+#pragma unroll
+          for (int mh = 0; mh < MH; ++mh) {  // both row halves against the same B slab
+            const uint32_t acc = tmem_base + mh * N_TILE;
+            const uint32_t oa = mh * L::kAHalf + s * kStepA;
+            if (ks == 0 && s == 0) umma_f16_c<false>(acc, desc_advance(a_hi, oa), b_hi, idesc);
+            else umma_f16_c<true>(acc, desc_advance(a_hi, oa), desc_advance(b_hi, s * kStepB), idesc);
+            if (NPASS == 3) {
+              umma_f16_c<true>(acc, desc_advance(a_lo, oa), desc_advance(b_hi, s * kStepB), idesc);
+              umma_f16_c<true>(acc, desc_advance(a_hi, oa), desc_advance(b_lo, s * kStepB), idesc);
+            }
           }
         }
         umma_commit(&empty_bar[stage]);
@@ -167,16 +179,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     // ===================== epilogue: warps 2..5, thread = output row =====================
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
-    const int row = m0 + r;
     mbar_wait(&acc_full, 0);
     tc_fence_after();
-    const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16);
-    float* crow = p.c + (long long)b * p.c_bstride + (long long)h * p.c_hstride + (long long)row * p.ldc;
     float v[32];
 #pragma unroll 1
-    for (int c = 0; c < N_TILE / 32; ++c) {
+    for (int cc = 0; cc < MH * (N_TILE / 32); ++cc) {
+      const int mh = cc / (N_TILE / 32), c = cc % (N_TILE / 32);
+      const int row = m0 + mh * kG2M + r;
+      if (m0 + mh * kG2M >= p.m) break;  // warp-uniform: the second half of the last row tile may be empty
+      const uint32_t taddr = tmem_base + mh * N_TILE + ((uint32_t)(quad * 32) << 16);
+      float* crow = p.c + (long long)b * p.c_bstride + (long long)h * p.c_hstride + (long long)row * p.ldc;
       const int col0 = n0 + c * 32;
-      if (col0 >= p.n) break;
+      if (col0 >= p.n) continue;
       tmem_ld32(taddr + c * 32, v);
       if (row < p.m) {
         if (col0 + 32 <= p.n && (p.ldc & 3) == 0) {
@@ -203,10 +217,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   }
 }
 
-template <bool A_MN, bool B_MN, int N_TILE, int NPASS>
+template <bool A_MN, bool B_MN, int N_TILE, int NPASS, int MH>
 static int launch_g2(const CUtensorMap* maps, const G2Params& p, dim3 grid, cudaStream_t s) {
-  using L = G2Smem<N_TILE, NPASS>;
-  auto kern = gemm_tc2_kernel<A_MN, B_MN, N_TILE, NPASS>;
+  using L = G2Smem<N_TILE, NPASS, MH>;
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, N_TILE, NPASS, MH>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
@@ -220,11 +234,31 @@ static int launch_g2(const CUtensorMap* maps, const G2Params& p, dim3 grid, cuda
   return LFS2_OK;
 }
 
-template <bool A_MN, bool B_MN>
-static int dispatch_g2(const CUtensorMap* maps, const G2Params& p, int n_tile, int npass, dim3 grid, cudaStream_t s) {
+template <bool A_MN, bool B_MN, int MH>
+static int dispatch_g2_mh(const CUtensorMap* maps, const G2Params& p, int n_tile, int npass, dim3 grid, cudaStream_t s) {
   if (n_tile == 256)
-    return npass == 3 ? launch_g2<A_MN, B_MN, 256, 3>(maps, p, grid, s) : launch_g2<A_MN, B_MN, 256, 1>(maps, p, grid, s);
-  return npass == 3 ? launch_g2<A_MN, B_MN, 128, 3>(maps, p, grid, s) : launch_g2<A_MN, B_MN, 128, 1>(maps, p, grid, s);
+    return npass == 3 ? launch_g2<A_MN, B_MN, 256, 3, MH>(maps, p, grid, s)
+                      : launch_g2<A_MN, B_MN, 256, 1, MH>(maps, p, grid, s);
+  return npass == 3 ? launch_g2<A_MN, B_MN, 128, 3, MH>(maps, p, grid, s)
+                    : launch_g2<A_MN, B_MN, 128, 1, MH>(maps, p, grid, s);
+}
+
+template <bool A_MN, bool B_MN>
+static int dispatch_g2(const CUtensorMap* maps, const G2Params& p, int n_tile, int npass, int mh, dim3 grid,
+                       cudaStream_t s) {
+  return mh == 2 ? dispatch_g2_mh<A_MN, B_MN, 2>(maps, p, n_tile, npass, grid, s)
+                 : dispatch_g2_mh<A_MN, B_MN, 1>(maps, p, n_tile, npass, grid, s);
+}
+
+// rows per CTA tile = 128 * g2_row_halves(m): two accumulators once the operand has two full row tiles
+// (LFS2_G2_MH=1 in the environment keeps single tiles: A/B runs)
+static int g2_row_halves(int m) {
+  static const int forced = [] {
+    const char* e = getenv("LFS2_G2_MH");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced == 1 || forced == 2) return forced;
+  return m >= 2 * kG2M ? 2 : 1;
 }
 
 }  // namespace tc
@@ -250,6 +284,7 @@ int lfs2_gemm_tc2(const void* a_hi, const void* a_lo, const lfs2_operand* a, con
                LFS2_ERR_INVALID_ARG, "gemm_tc2: pointers must be 16-byte aligned");
   LFS2_REQUIRE((long long)nbatch * nhead <= 65535, LFS2_ERR_UNSUPPORTED, "gemm_tc2: batch * heads exceeds the grid limit");
   const int n_tile = n > 128 ? 256 : 128;
+  const int mh = g2_row_halves(m);
   // K-major operands must not run past their k window into a neighbouring head: k is a multiple of the stage
   LFS2_REQUIRE((a->mn_major || a->hstride == 0 || k % kG2K == 0) && (b->mn_major || b->hstride == 0 || k % kG2K == 0),
                LFS2_ERR_UNSUPPORTED, "gemm_tc2: k=%d must be a multiple of %d for head-windowed K-major operands", k, kG2K);
@@ -259,8 +294,8 @@ int lfs2_gemm_tc2(const void* a_hi, const void* a_lo, const lfs2_operand* a, con
     if (o->mn_major) return make_tmap_3d(out, base, o->d0, o->d1, o->d2, 32, kG2K, 64);
     return make_tmap_3d(out, base, o->d0, o->d1, o->d2, kG2K, rows_tile, 64);
   };
-  bool ok = mk(&maps[0], a_hi, a, kG2M) && mk(&maps[2], b_hi, b, n_tile);
-  if (npass == 3) ok = ok && mk(&maps[1], a_lo, a, kG2M) && mk(&maps[3], b_lo, b, n_tile);
+  bool ok = mk(&maps[0], a_hi, a, kG2M * mh) && mk(&maps[2], b_hi, b, n_tile);
+  if (npass == 3) ok = ok && mk(&maps[1], a_lo, a, kG2M * mh) && mk(&maps[3], b_lo, b, n_tile);
   else {
     maps[1] = maps[0];
     maps[3] = maps[2];
@@ -272,7 +307,7 @@ int lfs2_gemm_tc2(const void* a_hi, const void* a_lo, const lfs2_operand* a, con
   p.a = {a->col0, a->hstride, a->per_z};
   p.b = {b->col0, b->hstride, b->per_z};
   p.c = c; p.c_bstride = c_bstride; p.c_hstride = c_hstride; p.ldc = ldc;
-  const int m_tiles = ceil_div(m, kG2M);
+  const int m_tiles = ceil_div(m, kG2M * mh);
   p.n_tiles = ceil_div(n, n_tile);
   const int z = nbatch * nhead;
   const long long ctas = (long long)m_tiles * p.n_tiles * z;
@@ -291,10 +326,10 @@ int lfs2_gemm_tc2(const void* a_hi, const void* a_lo, const lfs2_operand* a, con
   dim3 grid(m_tiles * p.n_tiles, splits, z);
   cudaStream_t s = (cudaStream_t)stream;
   if (a->mn_major)
-    return b->mn_major ? dispatch_g2<true, true>(maps, p, n_tile, npass, grid, s)
-                       : dispatch_g2<true, false>(maps, p, n_tile, npass, grid, s);
-  return b->mn_major ? dispatch_g2<false, true>(maps, p, n_tile, npass, grid, s)
-                     : dispatch_g2<false, false>(maps, p, n_tile, npass, grid, s);
+    return b->mn_major ? dispatch_g2<true, true>(maps, p, n_tile, npass, mh, grid, s)
+                       : dispatch_g2<true, false>(maps, p, n_tile, npass, mh, grid, s);
+  return b->mn_major ? dispatch_g2<false, true>(maps, p, n_tile, npass, mh, grid, s)
+                     : dispatch_g2<false, false>(maps, p, n_tile, npass, mh, grid, s);
 }
 
 }  // extern "C"

@@ -28,12 +28,51 @@ def grad_of(p):
     return p.grad
 
 
+class WeightCache:
+    """Tensors that depend on the parameters only -- bf16 planes, transposed copies, the folded FFN-2 matrix -- and the
+    per-step accumulators of gradients that take a second kernel to reach the parameters (folded FFN-2 weights, transposed
+    depthwise taps).  Built on first use after the parameters changed, shared by forward and backward and by every length
+    bucket of the step; `flush()` at the end of a backward pass runs the deferred gradient kernels once."""
+
+    def __init__(self):
+        self.key, self.store, self.pending = None, {}, {}
+
+    def validate(self, model):
+        key = (ops.WEIGHTS_EPOCH, model.compute_mode, tuple(p._version for p in model.parameters()))
+        if key != self.key:
+            self.key, self.store, self.pending = key, {}, {}
+
+    def get(self, tag, w, make):
+        """w: a parameter or a view of one (its storage outlives the cache entry, so the address identifies it)"""
+        k = (tag, w.data_ptr(), tuple(w.shape))
+        v = self.store.get(k)
+        if v is None:
+            v = self.store[k] = make()
+        return v
+
+    def accumulator(self, tag, w, make, finish):
+        """-> the step's accumulator for (tag, w), created by make(); finish(acc) runs once in flush()"""
+        k = (tag, w.data_ptr(), tuple(w.shape))
+        acc = self.pending.get(k)
+        if acc is None:
+            acc = make()
+            self.pending[k] = (acc, finish)
+            return acc
+        return acc[0]
+
+    def flush(self):
+        pending, self.pending = self.pending, {}
+        for acc, finish in pending.values():
+            finish(acc)
+
+
 class Engine:
     """GEMM dispatch of one train step: exact-fp32 CUDA-core kernels ("simt") or the tcgen05 kernels
     on bf16 hi/lo split operands ("fp32": 3 passes, "bf16": 1 pass; fp32 accumulation either way)."""
 
-    def __init__(self, mode):
+    def __init__(self, mode, cache=None):
         self.mode = mode
+        self.cache = cache if cache is not None else WeightCache()
         self.tc = mode != "simt"
         self.npass = 3 if mode == "fp32" else 1
         # dropout: one 64-bit seed per forward pass from torch's CPU generator (torch.manual_seed makes runs
@@ -86,6 +125,27 @@ class Engine:
                 ops.attach_planes(x, p)
         return p
 
+    def wplanes(self, w):
+        """planes of a weight matrix (a parameter, a view of one, or a tensor the cache itself holds), once per step"""
+        return self.cache.get("planes", w, lambda: ops.split_bf16(w.contiguous()))
+
+    def wt(self, w):
+        """(rows, cols) weight -> its fp32 transpose, once per step"""
+        return self.cache.get("T", w, lambda: ops.transpose(w))
+
+    def wplanes_t(self, w):
+        return self.cache.get("planesT", w, lambda: ops.split_bf16(self.wt(w)))
+
+    def folded(self, pw2, gc):
+        """(w_eff, b_eff) of conv2.1 . conv2.0 (grouped 1x1), once per step"""
+        return self.cache.get("fold", pw2.weight, lambda: ops.fold_pw(_mat(pw2.weight), _mat(gc.weight), gc.bias, pw2.bias))
+
+    def dw_taps(self, conv, flipped=False):
+        """(k, d) tap-major copy of a depthwise Conv1d weight (d, 1, k); flipped: reversed taps (input gradient)"""
+        if flipped:
+            return self.cache.get("dwTf", conv.weight, lambda: self.dw_taps(conv).flip(0).contiguous())
+        return self.cache.get("dwT", conv.weight, lambda: ops.transpose(_dwmat(conv.weight)))
+
     def attention_fwd(self, qkv, kpm, nhead, p_drop=0.0):
         """-> (ctx, saved)"""
         d = qkv.shape[-1] // 3
@@ -114,7 +174,7 @@ class Engine:
         fp32 tensor (for results that only feed further tensor-core kernels: no fp32 copy, no split pass)."""
         n, k = w.shape
         if self.tc and k % 32 == 0 and n % 16 == 0:
-            return ops.gemm_tc(self._planes(x), self._planes(w), b, relu=relu, npass=self.npass, tag=tag,
+            return ops.gemm_tc(self._planes(x), self.wplanes(w), b, relu=relu, npass=self.npass, tag=tag,
                                out="planes" if planes_out else "f32")
         return ops.linear(x if not isinstance(x, ops.Planes) else ops.merge_planes(x), w, b, relu=relu, tag=tag)
 
@@ -126,7 +186,10 @@ class Engine:
 
     def dgrad(self, dy, w, tag=None):
         """dy (..., n) . w (n, k) -> (..., k): the layer-input gradient of y = x . w^T"""
-        return self.linear(dy, ops.transpose(w), None, tag=tag)
+        n, k = w.shape
+        if self.tc and n % 32 == 0 and k % 16 == 0:
+            return ops.gemm_tc(self._planes(dy), self.wplanes_t(w), None, npass=self.npass, tag=tag)
+        return ops.linear(dy if not isinstance(dy, ops.Planes) else ops.merge_planes(dy), self.wt(w), None, tag=tag)
 
     # -- dense Conv1d(c -> n, k, "same") over (B, T, c), weight in the reference layout (n, c, k) -------------
     def conv(self, x, w, b, relu=False, tag=None):
@@ -199,14 +262,13 @@ def fft_fwd(L, E, x, kpm):
     x1, s["z1"], s["st1"] = ops.add_layernorm_train(x, a, L.norm1.weight, L.norm1.bias, L.eps, drop=s["drop1"])
     s["x1"] = x1
     if L.depthwise:
-        s["dw_wt"] = ops.transpose(_dwmat(dwc.weight))                    # (k, d)
-        s["u"] = E.dwconv(x1, s["dw_wt"], dwc.bias)
+        s["u"] = E.dwconv(x1, E.dw_taps(dwc), dwc.bias)                   # taps as (k, d)
         # the F-wide activation only feeds GEMMs (FFN-2 forward, FFN-1 weight gradient) and the ReLU mask of the
         # backward: on the tensor-core path it exists as bf16 planes only (no fp32 copy, no split pass)
         s["v"] = E.linear(s["u"], _mat(pw.weight), pw.bias, relu=True, tag="ffn1_gemm", planes_out=E.tc)
         s["v"], s["dropv"] = E.dropout_any(s["v"], p)                     # dropout after ReLU (model.py:120)
-        s["w_eff"], b_eff = ops.fold_pw(_mat(pw2.weight), _mat(gc.weight), gc.bias, pw2.bias)
-        y = E.linear(s["v"], s["w_eff"], b_eff, tag="ffn2_gemm")
+        w_eff, b_eff = E.folded(pw2, gc)
+        y = E.linear(s["v"], w_eff, b_eff, tag="ffn2_gemm")
     else:                                                                  # dense convolutions (model.py:95-106)
         s["v"] = E.conv(x1, L.conv1.weight, L.conv1.bias, relu=True, tag="ffn1_gemm")
         s["dropv"] = E.dropout_(s["v"], p)
@@ -236,12 +298,17 @@ def fft_bwd(L, E, s, dx2):
 def _ffn_bwd_depthwise(L, E, s, dy, dev):
     """conv1 = depthwise(k1) + pointwise, conv2 = grouped 1x1 + pointwise (folded): returns d(x1) without the residual"""
     dwc, pw, gc, pw2 = L.conv1[0], L.conv1[1], L.conv2[0], L.conv2[1]
-    dv = E.dgrad(dy, s["w_eff"], tag="ffn2_dgrad")
-    dw_eff = torch.zeros_like(s["w_eff"])
-    db_eff = torch.zeros(s["w_eff"].shape[0], device=dev, dtype=torch.float32)
+    w_eff, _ = E.folded(pw2, gc)
+    dv = E.dgrad(dy, w_eff, tag="ffn2_dgrad")
+
+    def finish(acc):  # chain rule from the folded matrix back to the four reference tensors, once per step
+        ops.fold_pw_bwd_(acc[0], acc[1], _mat(pw2.weight), _mat(gc.weight), gc.bias, _mat(grad_of(pw2.weight)),
+                         _mat(grad_of(gc.weight)), grad_of(gc.bias), grad_of(pw2.bias))
+
+    dw_eff, db_eff = E.cache.accumulator(
+        "d_fold", pw2.weight,
+        lambda: (torch.zeros_like(w_eff), torch.zeros(w_eff.shape[0], device=dev, dtype=torch.float32)), finish)
     E.wgrad_(dw_eff, db_eff, dy, s["v"], tag="ffn2_wgrad")
-    ops.fold_pw_bwd_(dw_eff, db_eff, _mat(pw2.weight), _mat(gc.weight), gc.bias, _mat(grad_of(pw2.weight)),
-                     _mat(grad_of(gc.weight)), grad_of(gc.bias), grad_of(pw2.bias))
     # ReLU + the dropout behind it in one pass: s["v"] is the dropped activation, so v > 0 is both masks
     scale = 1.0 / (1.0 - s["dropv"][0]) if s["dropv"] else 1.0
     if E.tc:   # the masked gradient as planes (its two consumers are GEMMs) + the bias gradient, one kernel
@@ -252,7 +319,7 @@ def _ffn_bwd_depthwise(L, E, s, dy, dev):
         ops.relu_bwd_(dv, s["v"], scale=scale)
         du = E.dgrad(dv, _mat(pw.weight), tag="ffn1_dgrad")
         E.wgrad_(_mat(grad_of(pw.weight)), grad_of(pw.bias), dv, s["u"], tag="ffn1_wgrad")
-    return _dwconv_bwd(dwc, s["dw_wt"], du, s["x1"])
+    return _dwconv_bwd(E, dwc, du, s["x1"])
 
 
 def _attn_bwd(L, E, s, dx1):
@@ -269,14 +336,16 @@ def _attn_bwd(L, E, s, dx1):
     return dx
 
 
-def _dwconv_bwd(conv, dw_wt, du, x_in):
-    """depthwise Conv1d backward: returns d(input); accumulates weight (d,1,k) and bias gradients"""
-    k, d = dw_wt.shape
-    zero_b = torch.zeros(d, device=du.device, dtype=torch.float32)
-    dx = ops.dwconv1d(du, dw_wt.flip(0).contiguous(), zero_b)            # correlation with the reversed taps
-    dwt = torch.zeros_like(dw_wt)
+def _dwconv_bwd(E, conv, du, x_in):
+    """depthwise Conv1d backward: returns d(input); accumulates weight (d,1,k) and bias gradients (the tap-major
+    weight gradient of the step is transposed into the parameter's layout once, in the cache's flush)"""
+    taps = E.dw_taps(conv)
+    k, d = taps.shape
+    zero_b = E.cache.get("zero_bias", conv.bias, lambda: torch.zeros(d, device=du.device, dtype=torch.float32))
+    dx = ops.dwconv1d(du, E.dw_taps(conv, flipped=True), zero_b)         # correlation with the reversed taps
+    dwt = E.cache.accumulator("d_dwT", conv.weight, lambda: torch.zeros_like(taps),
+                              lambda acc: ops.add_(_dwmat(grad_of(conv.weight)), ops.transpose(acc)))
     ops.dwconv1d_bwd_w_(dwt, grad_of(conv.bias), du, x_in)
-    ops.add_(_dwmat(grad_of(conv.weight)), ops.transpose(dwt))
     return dx
 
 
@@ -288,14 +357,13 @@ def vp_fwd(P, E, x, mask):
     for layer in P.layers:
         conv, ln = layer.layers[0].module, layer.layers[2]
         if layer.depthwise:
-            dw_wt = ops.transpose(_dwmat(conv[0].weight))
-            u = E.dwconv(z, dw_wt, conv[0].bias)
+            u = E.dwconv(z, E.dw_taps(conv[0]), conv[0].bias)
             h = E.linear(u, _mat(conv[1].weight), conv[1].bias, relu=True, tag="predictor_pw_gemm")
         else:
-            dw_wt, u = None, None
+            u = None
             h = E.conv(z, conv.weight, conv.bias, relu=True, tag="predictor_conv_gemm")
         zo, _, st = ops.add_layernorm_train(h, None, ln.weight, ln.bias, ln.eps)
-        layers.append({"x": z, "u": u, "h": h, "st": st, "dw_wt": dw_wt, "drop": E.dropout_(zo, layer.layers[3].p)})
+        layers.append({"x": z, "u": u, "h": h, "st": st, "drop": E.dropout_(zo, layer.layers[3].p)})
         z = zo
     out = ops.rowdot_mask(z, P.linear.weight, P.linear.bias, mask)
     return out, {"layers": layers, "z": z, "mask": mask}
@@ -312,13 +380,13 @@ def vp_bwd(P, E, s, dout):
             dh = ops.relu_bwd_planes(dh, sl["h"], db=grad_of(conv[1].bias))
             du = E.dgrad(dh, _mat(conv[1].weight), tag="predictor_dgrad")
             E.wgrad_(_mat(grad_of(conv[1].weight)), None, dh, sl["u"], tag="predictor_wgrad")
-            dz = _dwconv_bwd(conv[0], sl["dw_wt"], du, sl["x"])
+            dz = _dwconv_bwd(E, conv[0], du, sl["x"])
             continue
         ops.relu_bwd_(dh, sl["h"])
         if layer.depthwise:
             du = E.dgrad(dh, _mat(conv[1].weight), tag="predictor_dgrad")
             E.wgrad_(_mat(grad_of(conv[1].weight)), grad_of(conv[1].bias), dh, sl["u"], tag="predictor_wgrad")
-            dz = _dwconv_bwd(conv[0], sl["dw_wt"], du, sl["x"])
+            dz = _dwconv_bwd(E, conv[0], du, sl["x"])
         else:
             dz = E.conv_dgrad(dh, conv.weight, tag="predictor_dgrad")
             E.conv_wgrad_(grad_of(conv.weight), grad_of(conv.bias), dh, sl["x"], tag="predictor_wgrad")
@@ -333,7 +401,9 @@ def forward_train(M, targets, frames=None):
     whose tensor ends before / beyond its own longest utterance (forward_train_bucketed); None = the batch's own."""
     hp = M.hparams
     dev = M.device
-    E = Engine(M.compute_mode)
+    cache = M.__dict__.setdefault("_train_weight_cache", WeightCache())
+    cache.validate(M)
+    E = Engine(M.compute_mode, cache)
     va = M.variance_adaptor
     phones = targets["phones"].to(dev, non_blocking=True).contiguous()
     dvec = targets["speaker"].to(dev, dtype=torch.float32, non_blocking=True).contiguous()
@@ -411,8 +481,9 @@ def forward_train(M, targets, frames=None):
     return result, S
 
 
-def backward_train(M, S, dmel, ddur, dvars):
-    """dmel (B,Tm,80), ddur (B,Tp), dvars {var: (B,Tm)} (any may be None) -> accumulates every parameter gradient"""
+def backward_train(M, S, dmel, ddur, dvars, flush=True):
+    """dmel (B,Tm,80), ddur (B,Tp), dvars {var: (B,Tm)} (any may be None) -> accumulates every parameter gradient.
+    flush=False leaves the deferred gradient kernels (WeightCache.flush) to the caller: one run per step, not per bucket"""
     E = S["E"]
     va = M.variance_adaptor
     dev = M.device
@@ -461,6 +532,8 @@ def backward_train(M, S, dmel, ddur, dvars):
     ops.relu_bwd_(dspk, S["spk"])
     ops.gemm_tn_(grad_of(proj.weight), dspk, S["dvec"])
     ops.colsum_(grad_of(proj.bias), dspk)
+    if flush:
+        E.cache.flush()
 
 
 # ------------------------------------------------------------------------------------------
@@ -539,7 +612,9 @@ def backward_train_bucketed(M, saved, dmel, ddur, dvars):
     for it, tp_g, l_g, s in saved:
         dv = {v: g[it, :(tp_g if levels[v] == "phone" else l_g)].contiguous() for v, g in dvars.items() if g is not None}
         backward_train(M, s, None if dmel is None else dmel[it, :l_g].contiguous(),
-                       None if ddur is None else ddur[it, :tp_g].contiguous(), dv)
+                       None if ddur is None else ddur[it, :tp_g].contiguous(), dv, flush=False)
+    if saved:
+        saved[0][3]["E"].cache.flush()
 
 
 class ForwardTrainFn(torch.autograd.Function):

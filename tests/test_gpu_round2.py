@@ -11,7 +11,7 @@ import os
 import pytest
 import torch
 
-from lightningfastspeech2_b200 import configs, synthetic
+from lightningfastspeech2_b200 import configs, ops, synthetic
 from lightningfastspeech2_b200.fastspeech2.fastspeech2 import FastSpeech2
 from oracle import fs2_oracle as O
 

@@ -441,10 +441,11 @@ def test_wgrad_tc(m, n, k, npass, rel):
     assert err <= rel * ref.abs().max().item(), (err, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("m", [150, 300, 520])   # one 128-row accumulator per CTA / two (m >= 256), ragged last tile
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
-def test_gemm_tc2_batched_head_windows(a_mn, b_mn):
+def test_gemm_tc2_batched_head_windows(a_mn, b_mn, m):
     """operands as column windows of packed (B, T, 3d)-style tensors, z = b*nhead + h"""
-    B, H, m, n, k = 2, 2, 150, 96, 64
+    B, H, n, k = 2, 2, 96, 64
     # A source tensor: K-major -> (B, m, H*k) ; MN-major -> (B, k, H*m')  with m' = m rounded to 8
     mp, np_ = (m + 7) // 8 * 8, (n + 7) // 8 * 8
     a_src = rnd(B, k if a_mn else m, H * (mp if a_mn else k), seed=1)
@@ -464,7 +465,7 @@ def test_gemm_tc2_batched_head_windows(a_mn, b_mn):
 
 
 @pytest.mark.parametrize("mode,rel", [(3, 2e-4), (1, 3e-2)])
-@pytest.mark.parametrize("d,nhead,t", [(128, 2, 70), (256, 2, 203), (768, 2, 90)])
+@pytest.mark.parametrize("d,nhead,t", [(128, 2, 70), (256, 2, 203), (768, 2, 90), (768, 2, 333)])
 def test_attention_mat_forward_backward(d, nhead, t, mode, rel):
     b = 3
     qkv = rnd(b, t, 3 * d, seed=1, scale=0.7).requires_grad_(True)

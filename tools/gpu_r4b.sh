@@ -1,0 +1,8 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_round2.py tests/test_gpu_train.py -q -m gpu -s > gpurun_out/r4b_tests.log 2>&1; echo "tests rc=$?"
+tail -5 gpurun_out/r4b_tests.log; grep -h "train_length_buckets=\|C4_P0 train step" gpurun_out/r4b_tests.log
+for nb in 1 3; do timeout 300 python tools/profile_train.py 3 fp32 C4 --table --buckets=$nb > gpurun_out/r4b_train_c4_b$nb.txt 2>&1; echo "b$nb rc=$?"; head -16 gpurun_out/r4b_train_c4_b$nb.txt | grep -v Warn; done
+LFS2_G2_MH=1 timeout 300 python tools/profile_train.py 3 fp32 C4 --table --buckets=1 > gpurun_out/r4b_train_c4_b1_mh1.txt 2>&1; head -16 gpurun_out/r4b_train_c4_b1_mh1.txt | grep -v Warn
+for nb in 2 4; do timeout 300 python tools/profile_train.py 3 fp32 C4 --table --buckets=$nb > gpurun_out/r4b_train_c4_b$nb.txt 2>&1; head -3 gpurun_out/r4b_train_c4_b$nb.txt | grep -v Warn; done
+timeout 300 python tools/profile_train.py 3 bf16 C4 --table --buckets=3 > gpurun_out/r4b_train_c4_bf16_b3.txt 2>&1; head -3 gpurun_out/r4b_train_c4_bf16_b3.txt
