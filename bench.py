@@ -905,7 +905,7 @@ def run_lfs2(args):
     if args.c3_steps > 0:
         model = None
         torch.cuda.empty_cache()
-        ok3, ms3, fr3, shape3 = True, 0.0, 0, []
+        ok3, ms3, fr3, shape3, buck3 = True, 0.0, 0, [], []
         try:
             m3, sd3, hp3 = build_model(dev, preset="C3")
             m3.set_compute_mode("bf16")
@@ -922,6 +922,17 @@ def run_lfs2(args):
             ms3 /= args.c3_steps
             fr3 = int((~r3["tgt_mask"]).sum())
             shape3 = list(r3["mel"].shape)
+            # the same call as length-sorted sub-batches (model.length_buckets: valid frames bit-identical)
+            for nb3 in (2, 3, 4):
+                m3.length_buckets = nb3
+                for _ in range(3):
+                    step3()
+                t3, rb3 = timed(step3, args.c3_steps)
+                same = bool(torch.equal(rb3["mel"][~r3["tgt_mask"]], r3["mel"][~r3["tgt_mask"]]))
+                buck3.append({"length_buckets": nb3, "ms_per_step": t3 / args.c3_steps,
+                              "value": fr3 / (t3 / args.c3_steps * 1e-3), "unit": UNIT + " (rank 0's shard)",
+                              "valid_frames_bit_identical": same})
+            m3.length_buckets = 1
             if rank == 0 and args.parity_utts > 0:
                 try:
                     parity["c3"] = parity_vs_oracle(m3, sd3, hp3, hb3, max(1, args.parity_utts // 4),
@@ -938,6 +949,8 @@ def run_lfs2(args):
                               "32 utterances per GPU, phoneme len U[32,512] (BASELINE.json configs[2]: 256 utterances over 8 GPUs)",
                   "value": fr3 / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3, "valid_frames_per_step": fr3,
                   "mel_shape_rank0": shape3, "steps": args.c3_steps}
+            if buck3:  # rank 0's own timing of the bucketed variants (no cross-rank reduction)
+                c3["bucketed"] = buck3
 
     train = None
     if args.train_steps > 0:

@@ -49,7 +49,7 @@ struct G2Params {
   int atomic;
 };
 
-template <int N_TILE, int NPASS, int MH>
+template <int N_TILE, int NPASS, int MH, int OCC>
 struct G2Smem {
   static constexpr int kAHalf = kG2M * kG2K * 2;     // 8 KB: one 128-row half of the A slab
   static constexpr int kAPlane = MH * kAHalf;
@@ -59,8 +59,10 @@ struct G2Smem {
   static constexpr int kOffBHi = kAPlane;
   static constexpr int kOffALo = kAPlane + kBPlane;
   static constexpr int kOffBLo = 2 * kAPlane + kBPlane;
-  static constexpr int kStages = (200 * 1024 / kStage) > 8 ? 8 : (200 * 1024 / kStage);
+  static constexpr int kBudget = (OCC == 2 ? 100 : 200) * 1024;  // OCC = 2: two CTAs share the SM (short contractions)
+  static constexpr int kStages = (kBudget / kStage) > 8 ? 8 : (kBudget / kStage);
   static constexpr int kTotal = kStages * kStage + 1024;
+  static_assert(kStages >= 2, "gemm_tc2: the pipeline needs two stages");
 };
 
 template <bool MN>
@@ -77,12 +79,12 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <bool A_MN, bool B_MN, int N_TILE, int NPASS, int MH>
-__global__ void __launch_bounds__(kG2Threads, 1)
+template <bool A_MN, bool B_MN, int N_TILE, int NPASS, int MH, int OCC>
+__global__ void __launch_bounds__(kG2Threads, OCC)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                 const __grid_constant__ CUtensorMap map_b_hi, const __grid_constant__ CUtensorMap map_b_lo,
                 const G2Params p) {
-  using L = G2Smem<N_TILE, NPASS, MH>;
+  using L = G2Smem<N_TILE, NPASS, MH, OCC>;
   constexpr int kStages = L::kStages;
   constexpr uint32_t kTmemCols = MH * N_TILE <= 128 ? 128 : (MH * N_TILE <= 256 ? 256 : 512);
   extern __shared__ uint8_t smem_raw[];
@@ -217,10 +219,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
   }
 }
 
-template <bool A_MN, bool B_MN, int N_TILE, int NPASS, int MH>
+template <bool A_MN, bool B_MN, int N_TILE, int NPASS, int MH, int OCC>
 static int launch_g2(const CUtensorMap* maps, const G2Params& p, dim3 grid, cudaStream_t s) {
-  using L = G2Smem<N_TILE, NPASS, MH>;
-  auto kern = gemm_tc2_kernel<A_MN, B_MN, N_TILE, NPASS, MH>;
+  using L = G2Smem<N_TILE, NPASS, MH, OCC>;
+  auto kern = gemm_tc2_kernel<A_MN, B_MN, N_TILE, NPASS, MH, OCC>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal) != cudaSuccess) {
@@ -234,31 +236,39 @@ static int launch_g2(const CUtensorMap* maps, const G2Params& p, dim3 grid, cuda
   return LFS2_OK;
 }
 
-template <bool A_MN, bool B_MN, int MH>
+template <bool A_MN, bool B_MN, int MH, int OCC>
 static int dispatch_g2_mh(const CUtensorMap* maps, const G2Params& p, int n_tile, int npass, dim3 grid, cudaStream_t s) {
   if (n_tile == 256)
-    return npass == 3 ? launch_g2<A_MN, B_MN, 256, 3, MH>(maps, p, grid, s)
-                      : launch_g2<A_MN, B_MN, 256, 1, MH>(maps, p, grid, s);
-  return npass == 3 ? launch_g2<A_MN, B_MN, 128, 3, MH>(maps, p, grid, s)
-                    : launch_g2<A_MN, B_MN, 128, 1, MH>(maps, p, grid, s);
+    return npass == 3 ? launch_g2<A_MN, B_MN, 256, 3, MH, OCC>(maps, p, grid, s)
+                      : launch_g2<A_MN, B_MN, 256, 1, MH, OCC>(maps, p, grid, s);
+  return npass == 3 ? launch_g2<A_MN, B_MN, 128, 3, MH, OCC>(maps, p, grid, s)
+                    : launch_g2<A_MN, B_MN, 128, 1, MH, OCC>(maps, p, grid, s);
 }
 
+// mh = 2: two row halves per CTA, one CTA per SM (long contractions: weight gradients);
+// mh = 1, occ = 2: single tiles, two CTAs per SM so that one's epilogue runs under the other's MMAs (attention products)
 template <bool A_MN, bool B_MN>
-static int dispatch_g2(const CUtensorMap* maps, const G2Params& p, int n_tile, int npass, int mh, dim3 grid,
+static int dispatch_g2(const CUtensorMap* maps, const G2Params& p, int n_tile, int npass, int mh, int occ, dim3 grid,
                        cudaStream_t s) {
-  return mh == 2 ? dispatch_g2_mh<A_MN, B_MN, 2>(maps, p, n_tile, npass, grid, s)
-                 : dispatch_g2_mh<A_MN, B_MN, 1>(maps, p, n_tile, npass, grid, s);
+  if (mh == 2) return dispatch_g2_mh<A_MN, B_MN, 2, 1>(maps, p, n_tile, npass, grid, s);
+  return occ == 2 ? dispatch_g2_mh<A_MN, B_MN, 1, 2>(maps, p, n_tile, npass, grid, s)
+                  : dispatch_g2_mh<A_MN, B_MN, 1, 1>(maps, p, n_tile, npass, grid, s);
 }
 
-// rows per CTA tile = 128 * g2_row_halves(m): two accumulators once the operand has two full row tiles
-// (LFS2_G2_MH=1 in the environment keeps single tiles: A/B runs)
-static int g2_row_halves(int m) {
-  static const int forced = [] {
-    const char* e = getenv("LFS2_G2_MH");
-    return e ? atoi(e) : 0;
-  }();
-  if (forced == 1 || forced == 2) return forced;
-  return m >= 2 * kG2M ? 2 : 1;
+// Tile shape per launch.  Long contractions (>= 64 stages per CTA: the weight gradients) take two 128-row halves per
+// CTA; short ones (attention products: k = head_dim or T) keep single tiles but let two CTAs share the SM -- there the
+// epilogue (a 128 x 256 fp32 tile leaves through per-row stores) costs as much as the MMAs and has to overlap with them.
+// LFS2_G2_MH = 1|2 / LFS2_G2_OCC = 1|2 in the environment force a shape (A/B runs).
+static int g2_env(const char* name) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : 0;
+}
+static void g2_shape(int m, int k, int* mh, int* occ) {
+  static const int forced_mh = g2_env("LFS2_G2_MH"), forced_occ = g2_env("LFS2_G2_OCC");
+  *mh = (m >= 2 * kG2M && k >= 64 * kG2K) ? 2 : 1;
+  if (forced_mh == 1 || forced_mh == 2) *mh = forced_mh;
+  *occ = *mh == 1 ? 2 : 1;
+  if (*mh == 1 && (forced_occ == 1 || forced_occ == 2)) *occ = forced_occ;
 }
 
 }  // namespace tc
@@ -284,7 +294,8 @@ int lfs2_gemm_tc2(const void* a_hi, const void* a_lo, const lfs2_operand* a, con
                LFS2_ERR_INVALID_ARG, "gemm_tc2: pointers must be 16-byte aligned");
   LFS2_REQUIRE((long long)nbatch * nhead <= 65535, LFS2_ERR_UNSUPPORTED, "gemm_tc2: batch * heads exceeds the grid limit");
   const int n_tile = n > 128 ? 256 : 128;
-  const int mh = g2_row_halves(m);
+  int mh, occ;
+  g2_shape(m, k, &mh, &occ);
   // K-major operands must not run past their k window into a neighbouring head: k is a multiple of the stage
   LFS2_REQUIRE((a->mn_major || a->hstride == 0 || k % kG2K == 0) && (b->mn_major || b->hstride == 0 || k % kG2K == 0),
                LFS2_ERR_UNSUPPORTED, "gemm_tc2: k=%d must be a multiple of %d for head-windowed K-major operands", k, kG2K);
@@ -326,10 +337,10 @@ int lfs2_gemm_tc2(const void* a_hi, const void* a_lo, const lfs2_operand* a, con
   dim3 grid(m_tiles * p.n_tiles, splits, z);
   cudaStream_t s = (cudaStream_t)stream;
   if (a->mn_major)
-    return b->mn_major ? dispatch_g2<true, true>(maps, p, n_tile, npass, mh, grid, s)
-                       : dispatch_g2<true, false>(maps, p, n_tile, npass, mh, grid, s);
-  return b->mn_major ? dispatch_g2<false, true>(maps, p, n_tile, npass, mh, grid, s)
-                     : dispatch_g2<false, false>(maps, p, n_tile, npass, mh, grid, s);
+    return b->mn_major ? dispatch_g2<true, true>(maps, p, n_tile, npass, mh, occ, grid, s)
+                       : dispatch_g2<true, false>(maps, p, n_tile, npass, mh, occ, grid, s);
+  return b->mn_major ? dispatch_g2<false, true>(maps, p, n_tile, npass, mh, occ, grid, s)
+                     : dispatch_g2<false, false>(maps, p, n_tile, npass, mh, occ, grid, s);
 }
 
 }  // extern "C"

@@ -725,7 +725,7 @@ class FastSpeech2(_Base):
     # -- train step: forward with saved activations + hand-written backward (training.py) -----
     # train_length_buckets = n > 1: the train step of a ragged batch runs as n length-sorted sub-batches, each padded to
     # its own longest utterance + the conv halo (training.forward_train_bucketed); losses and gradients equal the
-    # un-bucketed step up to fp32 summation order, result positions the loss masks come back as zeros.  Off by default.
+    # un-bucketed step up to fp32 summation order; result positions past a bucket's own tensor (masked) are zeros.  Off by default.
     train_length_buckets = 1
 
     def _forward_train(self, targets):

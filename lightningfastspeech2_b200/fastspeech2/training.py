@@ -547,7 +547,8 @@ def forward_train_bucketed(M, targets, ngroups):
     summed conv half-widths of an utterance's end are kept and hold exactly what the reference computes there
     (PE[t] + speaker term + embedding of the collated target's padding value, ...), rows farther out have a zero
     gradient and feed nothing.  Losses and parameter gradients therefore equal the un-bucketed step up to fp32
-    summation order; result positions the loss masks come back as zeros instead of the reference's PAD-row values.
+    summation order; result positions beyond a bucket's own tensor (all masked by the loss) come back as zeros instead of
+    the reference's PAD-row values.
     -> (full-batch result dict, [(index tensor, tp_g, l_g, saved state), ...])"""
     dev, hp, va = M.device, M.hparams, M.variance_adaptor
     phones_all, dur_all = targets["phones"], targets["duration"]

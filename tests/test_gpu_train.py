@@ -429,7 +429,8 @@ def test_train_step_with_dropout_directional_derivative():
 
 # ------------------------------------------------------------- tcgen05 general GEMM (gemm_tc2)
 @pytest.mark.parametrize("npass,rel", [(3, 3e-5), (1, 2e-2)])
-@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (304, 200, 1000), (80, 768, 5000), (768, 3072, 777)])
+@pytest.mark.parametrize("m,n,k", [(128, 256, 64), (304, 200, 1000), (80, 768, 5000), (768, 3072, 777),
+                                   (304, 200, 2500), (768, 520, 4100)])   # the last two: 256-row CTA tiles (k >= 2048)
 def test_wgrad_tc(m, n, k, npass, rel):
     """dw (m x n) += dy^T . x with both operands MN-major (contraction over tensor rows), split-K + atomics"""
     rows = k
