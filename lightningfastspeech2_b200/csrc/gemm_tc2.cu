@@ -179,33 +179,48 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_const
     }
   } else if (nstages > 0) {
     // ===================== epilogue: warps 2..5, thread = output row =====================
+    // A lane holds 32 consecutive columns of ITS row after tcgen05.ld; written out like that, every store instruction
+    // touches 32 rows x 16 bytes (half-filled sectors: the T x T logits of the attention products left at 1.5 TB/s).
+    // Each warp transposes its 32 x 32 chunk through a padded shared-memory tile instead -- the pipeline stages are idle
+    // once acc_full has fired (every TMA write landed, every MMA read its operands) -- so that 8 lanes cover 128
+    // contiguous bytes of one row.
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     mbar_wait(&acc_full, 0);
     tc_fence_after();
+    float* stg = reinterpret_cast<float*>(smem) + quad * (32 * 33);
+    float* cbase = p.c + (long long)b * p.c_bstride + (long long)h * p.c_hstride;
+    const int sub = lane >> 3, c4 = (lane & 7) * 4;
     float v[32];
 #pragma unroll 1
     for (int cc = 0; cc < MH * (N_TILE / 32); ++cc) {
       const int mh = cc / (N_TILE / 32), c = cc % (N_TILE / 32);
-      const int row = m0 + mh * kG2M + r;
+      const int rbase = m0 + mh * kG2M + quad * 32;
       if (m0 + mh * kG2M >= p.m) break;  // warp-uniform: the second half of the last row tile may be empty
       const uint32_t taddr = tmem_base + mh * N_TILE + ((uint32_t)(quad * 32) << 16);
-      float* crow = p.c + (long long)b * p.c_bstride + (long long)h * p.c_hstride + (long long)row * p.ldc;
       const int col0 = n0 + c * 32;
       if (col0 >= p.n) continue;
       tmem_ld32(taddr + c * 32, v);
-      if (row < p.m) {
-        if (col0 + 32 <= p.n && (p.ldc & 3) == 0) {
+      if (col0 + 32 <= p.n && (p.ldc & 3) == 0) {  // warp-uniform
+        __syncwarp();
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (p.atomic) red_add_v4(crow + col0 + 4 * i, v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            else *reinterpret_cast<float4*>(crow + col0 + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int j = 0; j < 32; ++j) stg[lane * 33 + j] = v[j];
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int rr = it * 4 + sub;
+          if (rbase + rr < p.m) {
+            const float* sp = stg + rr * 33 + c4;
+            float* dst = cbase + (long long)(rbase + rr) * p.ldc + col0 + c4;
+            if (p.atomic) red_add_v4(dst, sp[0], sp[1], sp[2], sp[3]);
+            else *reinterpret_cast<float4*>(dst) = make_float4(sp[0], sp[1], sp[2], sp[3]);
           }
-        } else {
-          for (int j = 0; j < 32 && col0 + j < p.n; ++j) {
-            if (p.atomic) atomicAdd(crow + col0 + j, v[j]);
-            else crow[col0 + j] = v[j];
-          }
+        }
+      } else if (rbase + lane < p.m) {
+        float* crow = cbase + (long long)(m0 + mh * kG2M + r) * p.ldc;
+        for (int j = 0; j < 32 && col0 + j < p.n; ++j) {
+          if (p.atomic) atomicAdd(crow + col0 + j, v[j]);
+          else crow[col0 + j] = v[j];
         }
       }
     }
