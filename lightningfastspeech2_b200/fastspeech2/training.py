@@ -538,6 +538,28 @@ def backward_train(M, S, dmel, ddur, dvars, flush=True):
 
 # ------------------------------------------------------------------------------------------
 # length-bucketed train step (SURVEY 8f N2 carried to the gradient path)
+def plan_length_buckets(nphones, nframes, ngroups, tp, cap, h_enc, h_dec):
+    """Host-side plan of the length-bucketed step.  nphones[i] / nframes[i]: phones (last valid + 1) and frames (sum of
+    durations) of utterance i; tp: width of the collated phone tensor; cap: the LengthRegulator's max_length;
+    h_enc / h_dec: conv halos of the encoder and decoder side.
+    -> [(utterance indices, phones kept, (frames kept, LengthRegulator cap of the bucket))], longest bucket first.
+    A bucket keeps its longest utterance + the halo, but never more than the full batch's own tensor would hold
+    (that is where the reference's convolutions see their zero padding)."""
+    bsz = len(nphones)
+    cap = int(cap)
+    l_full = min(max(nframes), cap)
+    order = sorted(range(bsz), key=lambda i: (-nframes[i], -nphones[i]))
+    ngroups = max(1, min(int(ngroups), bsz))
+    per = (bsz + ngroups - 1) // ngroups
+    plan = []
+    for g0 in range(0, bsz, per):
+        idx = order[g0:g0 + per]
+        tp_g = min(tp, max(nphones[i] for i in idx) + h_enc)
+        cap_g = min(max(nframes[i] for i in idx), cap)
+        plan.append((idx, tp_g, (min(cap_g + h_dec, l_full), cap_g)))
+    return plan
+
+
 def forward_train_bucketed(M, targets, ngroups):
     """The teacher-forced forward of a ragged batch as `ngroups` length-sorted sub-batches, each padded only to ITS
     longest utterance plus the conv halo (`FastSpeech2._halos`), results scattered back into full-batch tensors.
@@ -564,15 +586,8 @@ def forward_train_bucketed(M, targets, ngroups):
                                           if va.variance_levels[i] == "phone"])
     h_dec = max([sum(layer.halo() for layer in M.decoder.layers)] +
                 [va.encoders[v].predictor.halo() for i, v in enumerate(va.variances) if va.variance_levels[i] == "frame"])
-    order = sorted(range(bsz), key=lambda i: (-nframes[i], -nphones[i]))
-    ngroups = max(1, min(int(ngroups), bsz))
-    per = (bsz + ngroups - 1) // ngroups
     parts = []
-    for g0 in range(0, bsz, per):
-        idx = order[g0:g0 + per]
-        tp_g = min(tp, max(nphones[i] for i in idx) + h_enc)
-        cap_g = min(max(nframes[i] for i in idx), cap)
-        frames = (min(cap_g + h_dec, l_full), cap_g)
+    for idx, tp_g, frames in plan_length_buckets(nphones, nframes, ngroups, tp, cap, h_enc, h_dec):
         it = {}
 
         def take(v, it=it, idx=idx):

@@ -218,3 +218,30 @@ def test_gradients_stay_views_of_the_flat_buffer():
     super(FastSpeech2, model).zero_grad(set_to_none=True)
     model.rehome_gradients()
     assert all(q.grad is not None and q.grad.data_ptr() >= flat_g.data_ptr() for q in params)
+
+
+def test_length_bucket_plan_covers_every_utterance_with_its_halo():
+    """host logic of model.train_length_buckets (training.plan_length_buckets): every utterance lands in exactly one
+    bucket, a bucket keeps its longest utterance + the conv halo but never more than the full batch's tensor, buckets
+    come longest first, the LengthRegulator cap of a bucket is its own longest utterance (capped by max_length)"""
+    import numpy as np
+
+    from lightningfastspeech2_b200.fastspeech2.training import plan_length_buckets
+
+    rng = np.random.default_rng(3)
+    for bsz, ngroups in ((1, 3), (7, 2), (7, 3), (64, 4), (5, 9)):
+        nphones = rng.integers(3, 120, size=bsz).tolist()
+        nframes = [int(p * rng.integers(1, 9)) for p in nphones]
+        tp, cap, h_enc, h_dec = max(nphones), 300, 26, 28
+        plan = plan_length_buckets(nphones, nframes, ngroups, tp, cap, h_enc, h_dec)
+        assert sorted(i for idx, _, _ in plan for i in idx) == list(range(bsz))
+        assert len(plan) <= max(1, min(ngroups, bsz))
+        l_full = min(max(nframes), cap)
+        longest = [max(nframes[i] for i in idx) for idx, _, _ in plan]
+        assert longest == sorted(longest, reverse=True)
+        for idx, tp_g, (l, cap_g) in plan:
+            assert tp_g == min(tp, max(nphones[i] for i in idx) + h_enc)
+            assert cap_g == min(max(nframes[i] for i in idx), cap)
+            assert cap_g <= l <= l_full and l == min(cap_g + h_dec, l_full)
+        # the bucket holding the batch's longest utterance ends exactly where the full tensor ends
+        assert plan[0][2][0] == l_full

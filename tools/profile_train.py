@@ -1,6 +1,7 @@
 """Run a few C4 train steps (bench.py's "train" workload) -- for ncu, or stand-alone to print the
-CUDA-event table of one step: `python tools/profile_train.py [steps] [mode] [preset] [--table] [--buckets=n]`
-(--buckets: model.train_length_buckets; the host's issue time per step is printed beside the device time)."""
+CUDA-event table of one step: `python tools/profile_train.py [steps] [mode] [preset] [--table] [--buckets=n] [--world=w]`
+(--buckets: model.train_length_buckets; --world: time rank 0's shard of a w-rank job on this one GPU; the host's issue
+time per step is printed beside the device time)."""
 import os
 import sys
 import time
@@ -23,7 +24,11 @@ model.log_losses = False
 for a in sys.argv[1:]:
     if a.startswith("--buckets="):
         model.train_length_buckets = int(a.split("=")[1])
-batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in bench.train_batch(hp, 0, 1).items()}
+world = 1
+for a in sys.argv[1:]:
+    if a.startswith("--world="):
+        world = int(a.split("=")[1])
+batch = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in bench.train_batch(hp, 0, world).items()}
 (opt,), (sch,) = model.configure_optimizers()
 bench.run_train_steps(model, batch, opt, sch["scheduler"], steps, 1)
 torch.cuda.synchronize()
