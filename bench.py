@@ -905,7 +905,7 @@ def run_lfs2(args):
     if args.c3_steps > 0:
         model = None
         torch.cuda.empty_cache()
-        ok3, ms3, fr3, shape3, buck3 = True, 0.0, 0, [], []
+        ok3, ms3, fr3, shape3, buck3, skip3 = True, 0.0, 0, [], [], None
         try:
             m3, sd3, hp3 = build_model(dev, preset="C3")
             m3.set_compute_mode("bf16")
@@ -933,6 +933,15 @@ def run_lfs2(args):
                               "value": fr3 / (t3 / args.c3_steps * 1e-3), "unit": UNIT + " (rank 0's shard)",
                               "valid_frames_bit_identical": same})
             m3.length_buckets = 1
+            # and with PAD-row skipping in one launch per kernel (model.skip_pad_rows, the wide row-limited block)
+            m3.skip_pad_rows = True
+            for _ in range(3):
+                step3()
+            t3, rb3 = timed(step3, args.c3_steps)
+            m3.skip_pad_rows = False
+            skip3 = {"ms_per_step": t3 / args.c3_steps, "value": fr3 / (t3 / args.c3_steps * 1e-3),
+                     "unit": UNIT + " (rank 0's shard)",
+                     "valid_frames_bit_identical": bool(torch.equal(rb3["mel"][~r3["tgt_mask"]], r3["mel"][~r3["tgt_mask"]]))}
             if rank == 0 and args.parity_utts > 0:
                 try:
                     parity["c3"] = parity_vs_oracle(m3, sd3, hp3, hb3, max(1, args.parity_utts // 4),
@@ -951,6 +960,8 @@ def run_lfs2(args):
                   "mel_shape_rank0": shape3, "steps": args.c3_steps}
             if buck3:  # rank 0's own timing of the bucketed variants (no cross-rank reduction)
                 c3["bucketed"] = buck3
+            if skip3:
+                c3["pad_skip"] = skip3
 
     train = None
     if args.train_steps > 0:

@@ -87,6 +87,12 @@ LFS2_API int lfs2_dwconv1d(const float* x, const float* wt, const float* bias, f
 LFS2_API int lfs2_add_layernorm_planes(const void* x_hi, const void* x_lo, const float* y, const float* gamma,
                                        const float* beta, void* out_hi, void* out_lo, int m, int d, float eps,
                                        void* stream);
+/* The same over (batch, t, d) tensors with PAD-row skipping: rows of the 128-row groups of utterance b that start at or
+ * after row_limit[b] + limit_extra are neither read nor written (row_limit NULL: every row).  The d != 256 FFTBlock of
+ * FastSpeech2.skip_pad_rows (reference model.py:113-122 on the rows a valid frame can depend on). */
+LFS2_API int lfs2_add_layernorm_planes_limited(const void* x_hi, const void* x_lo, const float* y, const float* gamma,
+                                               const float* beta, void* out_hi, void* out_lo, int batch, int t, int d,
+                                               float eps, const int* row_limit, int limit_extra, void* stream);
 /* same, reading the input as fp32 (x) OR as bf16 hi/lo planes (x_hi, x_lo; x = NULL), and writing
  * the result as fp32 (out, may be NULL) and/or as hi/lo planes (the A operand of the following
  * pointwise lfs2_gemm_tc) */

@@ -27,6 +27,7 @@ SIGNATURES = {
     "lfs2_attention": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "lfs2_add_layernorm": [_vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
     "lfs2_add_layernorm_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
+    "lfs2_add_layernorm_planes_limited": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _f, _vp, _i, _vp],
     "lfs2_rowdot_mask": [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "lfs2_bucket_embed_add": [_vp, _vp, _f, _f, _vp, _i, _vp, _vp, _vp, _vp, _i, _i, _i, _vp],
     "lfs2_prior_embed": [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _vp],

@@ -485,28 +485,63 @@ __global__ void fold_pw_bias_kernel(const float* __restrict__ w21, const float* 
 
 // dW21[n, G*g+o] += sum_i dWe[n, G*g+i] * W20[G*g+o, i] + dbe[n] * b20[G*g+o]
 // dW20[G*g+o, i] += sum_n dWe[n, G*g+i] * W21[n, G*g+o] ; db20[c] += sum_n dbe[n] * W21[n,c] ; db21 += dbe
-__global__ void fold_pw_bwd_kernel(const float* __restrict__ dwe, const float* __restrict__ dbe,
-                                   const float* __restrict__ w21, const float* __restrict__ w20,
-                                   const float* __restrict__ b20, float* __restrict__ dw21, float* __restrict__ dw20,
-                                   float* __restrict__ db20, float* __restrict__ db21, int d_out, int groups, int g) {
-  const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i0 >= d_out * groups) return;
-  const int n = i0 / groups, G = i0 % groups, f = groups * g;
-  const float dbn = dbe[n];
-  float de[kFoldMaxG];
-  for (int i = 0; i < g; ++i) de[i] = dwe[(size_t)n * f + G * g + i];
-  for (int oo = 0; oo < g; ++oo) {
-    const int c = G * g + oo;
-    const float w = w21[(size_t)n * f + c];
-    float s = dbn * b20[c];
-    for (int i = 0; i < g; ++i) {
-      s = fmaf(de[i], w20[(size_t)c * g + i], s);
-      atomicAdd(dw20 + (size_t)c * g + i, de[i] * w);
+// thread = one group G of conv2.0, CTA = 128 groups x a chunk of kFoldRows output rows n: the group's g x g weight
+// gradient and its g bias gradients are summed over the chunk in registers and reach memory as ONE atomic per entry and
+// CTA (one thread per (n, G) used to add straight into dw20 / db20: d_out-way contention on every address, 141 us at
+// d = 768, F = 3072); dw21[n, c] is owned by exactly one thread of the launch (plain accumulate).
+constexpr int kFoldRows = 32;
+__global__ void __launch_bounds__(128)
+fold_pw_bwd_kernel(const float* __restrict__ dwe, const float* __restrict__ dbe, const float* __restrict__ w21,
+                   const float* __restrict__ w20, const float* __restrict__ b20, float* __restrict__ dw21,
+                   float* __restrict__ dw20, float* __restrict__ db20, float* __restrict__ db21, int d_out, int groups,
+                   int g) {
+  const int G = blockIdx.x * blockDim.x + threadIdx.x;
+  if (G >= groups) return;
+  const int f = groups * g;
+  const int n0 = blockIdx.y * kFoldRows, n1 = min(d_out, n0 + kFoldRows);
+  float wg[kFoldMaxG][kFoldMaxG], bg[kFoldMaxG], acc[kFoldMaxG][kFoldMaxG], accb[kFoldMaxG];
+#pragma unroll
+  for (int oo = 0; oo < kFoldMaxG; ++oo) {
+    bg[oo] = oo < g ? b20[G * g + oo] : 0.f;
+    accb[oo] = 0.f;
+#pragma unroll
+    for (int i = 0; i < kFoldMaxG; ++i) {
+      wg[oo][i] = (oo < g && i < g) ? w20[(size_t)(G * g + oo) * g + i] : 0.f;
+      acc[oo][i] = 0.f;
     }
-    atomicAdd(dw21 + (size_t)n * f + c, s);
-    atomicAdd(db20 + c, dbn * w);
   }
-  if (G == 0) atomicAdd(db21 + n, dbn);
+  for (int n = n0; n < n1; ++n) {
+    const float dbn = dbe[n];
+    float de[kFoldMaxG], w[kFoldMaxG];
+#pragma unroll
+    for (int i = 0; i < kFoldMaxG; ++i) {
+      de[i] = i < g ? dwe[(size_t)n * f + G * g + i] : 0.f;
+      w[i] = i < g ? w21[(size_t)n * f + G * g + i] : 0.f;
+    }
+#pragma unroll
+    for (int oo = 0; oo < kFoldMaxG; ++oo) {
+      if (oo < g) {
+        float sum = dbn * bg[oo];
+#pragma unroll
+        for (int i = 0; i < kFoldMaxG; ++i) {
+          sum = fmaf(de[i], wg[oo][i], sum);
+          acc[oo][i] = fmaf(de[i], w[oo], acc[oo][i]);
+        }
+        dw21[(size_t)n * f + G * g + oo] += sum;
+        accb[oo] = fmaf(dbn, w[oo], accb[oo]);
+      }
+    }
+    if (G == 0) atomicAdd(db21 + n, dbn);
+  }
+#pragma unroll
+  for (int oo = 0; oo < kFoldMaxG; ++oo) {
+    if (oo < g) {
+#pragma unroll
+      for (int i = 0; i < kFoldMaxG; ++i)
+        if (i < g) atomicAdd(dw20 + (size_t)(G * g + oo) * g + i, acc[oo][i]);
+      atomicAdd(db20 + G * g + oo, accb[oo]);
+    }
+  }
 }
 
 }  // namespace lfs2
@@ -525,7 +560,7 @@ int lfs2_gemm_tn(const float* a, const float* b, float* c, int m, int n, int k, 
   LFS2_REQUIRE(t > 0 || shift == 0, LFS2_ERR_INVALID_ARG, "gemm_tn: a row shift needs the utterance length t");
   LFS2_REQUIRE(aligned16(a) && aligned16(b), LFS2_ERR_INVALID_ARG, "gemm_tn: operands must be 16-byte aligned");
   const int tiles = ceil_div(k, TN_B) * ceil_div(n, TN_B);
-  int splits = ceil_div(4 * kNumSMs, tiles);
+  int splits = ceil_div(4 * num_sms(), tiles);
   int rows_per = ceil_div(m, splits);
   rows_per = ceil_div(rows_per, TN_R) * TN_R;
   if (rows_per < 4 * TN_R) rows_per = 4 * TN_R;
@@ -543,7 +578,7 @@ int lfs2_colsum(const float* a, float* out, int m, int n, void* stream) {
   LFS2_REQUIRE(m > 0 && n > 0 && n % 4 == 0, LFS2_ERR_UNSUPPORTED, "colsum: n=%d must be a positive multiple of 4", n);
   LFS2_REQUIRE(aligned16(a), LFS2_ERR_INVALID_ARG, "colsum: input must be 16-byte aligned");
   const int cgs = ceil_div(n / 4, 32);
-  int chunks = ceil_div(4 * kNumSMs, cgs);
+  int chunks = ceil_div(4 * num_sms(), cgs);
   int rows_per = ceil_div(m, chunks);
   if (rows_per < 64) rows_per = 64;
   dim3 grid(cgs, ceil_div(m, rows_per));
@@ -609,7 +644,7 @@ int lfs2_layernorm_bwd_drop(const float* dy, const float* z, const float* stats,
                    ((reinterpret_cast<uintptr_t>(stats) & 7u) == 0),
                LFS2_ERR_INVALID_ARG, "layernorm_bwd: pointers must be 16-byte aligned");
   int blocks = ceil_div(m, 8 * 8);  // >= 8 rows per warp
-  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   if (blocks < 1) blocks = 1;
   const int nv = ceil_div(d / 4, 32);
 #define LFS2_LNB(NV)                                                                                            \
@@ -684,7 +719,7 @@ int lfs2_rowdot_mask_bwd(const float* dout, const float* z, const float* w, cons
   LFS2_REQUIRE(aligned16(z) && aligned16(w) && aligned16(dz), LFS2_ERR_INVALID_ARG,
                "rowdot_mask_bwd: pointers must be 16-byte aligned");
   int blocks = ceil_div(m, 8 * 16);
-  if (blocks > 2 * kNumSMs) blocks = 2 * kNumSMs;
+  if (blocks > 2 * num_sms()) blocks = 2 * num_sms();
   if (blocks < 1) blocks = 1;
   rowdot_mask_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dout, (const float4*)z, (const float4*)w, mask,
                                                                  (float4*)dz, dw, db, m, f / 4);
@@ -726,8 +761,9 @@ int lfs2_fold_pw_bwd(const float* dw_eff, const float* db_eff, const float* w21,
                "fold_pw_bwd: null pointer");
   LFS2_REQUIRE(d_out > 0 && groups > 0 && g > 0 && g <= kFoldMaxG, LFS2_ERR_UNSUPPORTED,
                "fold_pw: group size %d not supported (1..%d)", g, kFoldMaxG);
-  fold_pw_bwd_kernel<<<ceil_div((long long)d_out * groups, 256), 256, 0, (cudaStream_t)stream>>>(
-      dw_eff, db_eff, w21, w20, b20, dw21, dw20, db20, db21, d_out, groups, g);
+  dim3 grid(ceil_div(groups, 128), ceil_div(d_out, kFoldRows));
+  fold_pw_bwd_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(dw_eff, db_eff, w21, w20, b20, dw21, dw20, db20, db21, d_out,
+                                                             groups, g);
   LFS2_CHECK_LAUNCH("fold_pw_bwd");
   return LFS2_OK;
 }

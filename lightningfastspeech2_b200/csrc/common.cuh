@@ -34,7 +34,18 @@ void set_error(const char* fmt, ...);
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
-constexpr int kNumSMs = 148;  // B200
+// SM count of the current device (grids of the persistent kernels, split heuristics): queried once per process;
+// 148 on the B200 this library is written for
+static inline int num_sms() {
+  static const int n = [] {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+        v <= 0)
+      return 148;
+    return v;
+  }();
+  return n;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

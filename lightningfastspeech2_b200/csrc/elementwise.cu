@@ -565,10 +565,13 @@ static int launch_dwconv_k(const float* x, const void* x_hi, const void* x_lo, c
 __global__ void add_layernorm_planes_kernel(const uint2* __restrict__ x_hi, const uint2* __restrict__ x_lo,
                                             const float4* __restrict__ y, const float4* __restrict__ gamma,
                                             const float4* __restrict__ beta, uint2* __restrict__ out_hi,
-                                            uint2* __restrict__ out_lo, int m, int d4, float eps) {
+                                            uint2* __restrict__ out_lo, int m, int d4, float eps, int t,
+                                            const int* __restrict__ row_limit, int limit_extra) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= m) return;
+  // rows of the 128-row groups that start at or after row_limit[b] + extra are nobody's input (PAD-row skipping)
+  if (row_limit && ((row % t) & ~127) >= __ldg(row_limit + row / t) + limit_extra) return;
   const size_t base = (size_t)row * d4;
   float4 v[kLnMaxVec];
   float s = 0.f;
@@ -734,7 +737,16 @@ int lfs2_add_layernorm_train(const float* x, const float* y, const float* gamma,
 
 int lfs2_add_layernorm_planes(const void* x_hi, const void* x_lo, const float* y, const float* gamma, const float* beta,
                               void* out_hi, void* out_lo, int m, int d, float eps, void* stream) {
+  return lfs2_add_layernorm_planes_limited(x_hi, x_lo, y, gamma, beta, out_hi, out_lo, 1, m, d, eps, nullptr, 0, stream);
+}
+
+int lfs2_add_layernorm_planes_limited(const void* x_hi, const void* x_lo, const float* y, const float* gamma,
+                                      const float* beta, void* out_hi, void* out_lo, int batch, int t, int d, float eps,
+                                      const int* row_limit, int limit_extra, void* stream) {
   LFS2_REQUIRE(x_hi && x_lo && gamma && beta && out_hi && out_lo, LFS2_ERR_INVALID_ARG, "add_layernorm_planes: null pointer");
+  LFS2_REQUIRE(batch >= 0 && t >= 0 && (long long)batch * t <= 2147483647LL, LFS2_ERR_INVALID_ARG,
+               "add_layernorm_planes: bad shape");
+  const int m = batch * t;
   if (m == 0) return LFS2_OK;
   LFS2_REQUIRE(d > 0 && d % 4 == 0 && d <= 128 * kLnMaxVec, LFS2_ERR_UNSUPPORTED,
                "add_layernorm_planes: d=%d must be a multiple of 4 and <= %d", d, 128 * kLnMaxVec);
@@ -743,7 +755,7 @@ int lfs2_add_layernorm_planes(const void* x_hi, const void* x_lo, const float* y
                LFS2_ERR_INVALID_ARG, "add_layernorm_planes: pointers must be 16-byte aligned");
   add_layernorm_planes_kernel<<<ceil_div((long long)m * 32, 256), 256, 0, (cudaStream_t)stream>>>(
       (const uint2*)x_hi, (const uint2*)x_lo, (const float4*)y, (const float4*)gamma, (const float4*)beta,
-      (uint2*)out_hi, (uint2*)out_lo, m, d / 4, eps);
+      (uint2*)out_hi, (uint2*)out_lo, m, d / 4, eps, t, row_limit, limit_extra);
   LFS2_CHECK_LAUNCH("add_layernorm_planes");
   return LFS2_OK;
 }

@@ -547,11 +547,11 @@ static int launch_ffn(const CUtensorMap* m, const FfnParams& p, cudaStream_t s) 
     configured = true;
   }
   if (!MC) {
-    const int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+    const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     kern<<<grid, kFThreads, L::kTotal, s>>>(m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8], m[9], m[10], m[11], p);
   } else {  // clusters of two CTAs (one per SM): pairs of row tiles share the multicast weight slabs
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kNumSMs & ~1);
+    cfg.gridDim = dim3(num_sms() & ~1);
     cfg.blockDim = dim3(kFThreads);
     cfg.dynamicSmemBytes = L::kTotal;
     cfg.stream = s;
@@ -633,7 +633,7 @@ extern "C" int lfs2_ffn_fused_tc_ex(const void* u_hi, const void* u_lo, int batc
     const char* e = getenv("LFS2_FFN_MULTICAST");
     mc_on = (e && e[0] == '0') ? 0 : 1;
   }
-  const bool mc = mc_on == 1 && ceil_div(m, kFM) >= 2 * kNumSMs;
+  const bool mc = mc_on == 1 && ceil_div(m, kFM) >= 2 * num_sms();
   const uint32_t w1_box = mc ? kFC / 2 : kFC, w2_box = mc ? kFD / 2 : kFD;  // MC: each CTA fetches half a weight slab
   CUtensorMap maps[12];
   bool ok = make_tmap_3d(&maps[0], u_hi, kFD, m, 1, kFK, kFM, 64) && make_tmap_3d(&maps[2], w1_hi, kFD, f, 1, kFK, w1_box, 64) &&

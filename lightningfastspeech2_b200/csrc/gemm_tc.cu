@@ -890,7 +890,7 @@ static int launch_gemm_tc(const GemmTcMaps& m, const GemmTcParams& p, cudaStream
     }
     configured = true;
   }
-  int grid = p.total_tiles < kNumSMs ? p.total_tiles : kNumSMs;
+  int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   if (!MC) {
     kern<<<grid, gemm_tc_threads(N_TILE), L::kTotal, s>>>(m.ah, m.al, m.wh, m.wl, m.rh, m.rl, m.ident, m.o0, m.o1, p);
   } else {  // clusters of two CTAs (one per SM): pairs of row tiles share the multicast weight slabs
@@ -1087,7 +1087,7 @@ int lfs2_gemm_tc_ex(const void* a_hi, const void* a_lo, int batch, int t, int d,
   const int m_tiles_all = batch * ((t + kBM - 1) / kBM);
   // (not for the LayerNorm builds: they are paced by their epilogue, and coupling two CTAs' epilogues to one MMA
   // stream costs them 6-10 %; measured in profiles/r2p_*)
-  const bool mc = !ln && n_tile == 256 && n % 256 == 0 && m_tiles_all >= 2 * kNumSMs && gemm_multicast_enabled();
+  const bool mc = !ln && n_tile == 256 && n % 256 == 0 && m_tiles_all >= 2 * num_sms() && gemm_multicast_enabled();
   const uint32_t w_box = mc ? n_tile / 2 : n_tile;  // MC: each CTA of a pair fetches half a weight slab
 
   GemmTcMaps m;

@@ -338,10 +338,10 @@ int lfs2_gemm_tc2(const void* a_hi, const void* a_lo, const lfs2_operand* a, con
   const int z = nbatch * nhead;
   const long long ctas = (long long)m_tiles * p.n_tiles * z;
   int splits = 1;
-  if (accumulate && ctas < 2 * kNumSMs) {
+  if (accumulate && ctas < 2 * num_sms()) {
     // split the contraction so that the grid fills (at most) two full waves of the 148 SMs: rounding the
     // split count DOWN keeps the CTA count <= 2 * 148 -- rounding up would leave a third, mostly empty wave
-    splits = (int)((2 * kNumSMs) / ctas);
+    splits = (int)((2 * num_sms()) / ctas);
     const int max_splits = ceil_div(k, 8 * kG2K);  // at least 8 stages per split
     if (splits > max_splits) splits = max_splits;
     if (splits < 1) splits = 1;

@@ -150,11 +150,11 @@ int lfs2_masked_loss(const float* pred, const float* target, const int64_t* targ
     return LFS2_ERR_CUDA;
   }
   int cblocks = ceil_div(rows, 256);
-  if (cblocks > kNumSMs) cblocks = kNumSMs;
+  if (cblocks > num_sms()) cblocks = num_sms();
   mask_count_kernel<<<cblocks, 256, 0, s>>>(pad_mask, workspace, rows);
   const size_t total = (size_t)rows * inner;
   int blocks = ceil_div((long long)total, 256 * 4);
-  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   if (blocks < 1) blocks = 1;
   masked_loss_kernel<<<blocks, 256, 0, s>>>(pred, target, target_i64, pad_mask, dpred, workspace, total, inner, kind,
                                             weight);
@@ -167,7 +167,7 @@ int lfs2_scale_by(float* x, const float* scalar, long long n, void* stream) {
   LFS2_REQUIRE(x && scalar, LFS2_ERR_INVALID_ARG, "scale_by: null pointer");
   if (n <= 0) return LFS2_OK;
   int blocks = ceil_div(n, 256 * 4);
-  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   scale_by_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, scalar, (size_t)n);
   LFS2_CHECK_LAUNCH("scale_by");
   return LFS2_OK;
@@ -179,7 +179,7 @@ int lfs2_sumsq(const float* x, float* out, long long n, void* stream) {
   LFS2_REQUIRE(n > 0 && n % 4 == 0 && aligned16(x), LFS2_ERR_UNSUPPORTED, "sumsq: n %% 4 == 0 and 16-byte alignment");
   size_t n4 = (size_t)n / 4;
   int blocks = ceil_div((long long)n4, 256 * 4);
-  if (blocks > 8 * kNumSMs) blocks = 8 * kNumSMs;
+  if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   sumsq_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float4*)x, out, n4);
   LFS2_CHECK_LAUNCH("sumsq");
   return LFS2_OK;

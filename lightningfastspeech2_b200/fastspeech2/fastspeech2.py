@@ -535,8 +535,9 @@ class FastSpeech2(_Base):
         if self.compute_mode == "simt" or hp.n_mels % 16 != 0 or any(lv != "frame" for lv in hp.variance_levels) \
                 or not self.encoder.supports_row_limit(hp.encoder_hidden) \
                 or not self.decoder.supports_row_limit(hp.decoder_hidden):
-            raise NotImplementedError("skip_pad_rows needs the fused tensor-core FFTBlocks (d = 256, head_dim 128, "
-                                      "depthwise FFN, frame-level variances, compute mode fp32 or bf16)")
+            raise NotImplementedError("skip_pad_rows needs tensor-core FFTBlocks with a row-limited path (d = 256 with "
+                                      "head_dim 128 and the fused depthwise FFN, or head_dim 256 / 384 with the depthwise "
+                                      "FFN), frame-level variances, compute mode fp32 or bf16")
         return True
 
     # -- length-bucketed synthesis ---------------------------------------------------

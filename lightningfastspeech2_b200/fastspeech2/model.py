@@ -222,7 +222,11 @@ class ConformerEncoderLayer(nn.Module):
         return self.compute_mode != "simt" and _tc_ok(d, fsz)
 
     def supports_row_limit(self, d):
-        """the PAD-row skipping path exists for the fully fused block: d = 256, head_dim 128, depthwise fused FFN"""
+        """the PAD-row skipping path exists for the fully fused block (d = 256, head_dim 128, depthwise fused FFN) and
+        for the wide block (d != 256 with the flash attention for head_dim 256 / 384: the 76 M configuration)"""
+        if self.depthwise and self.tc_capable(d) and d != 256:
+            return (d // self.nhead) in (256, 384) and self.wide_flash_attention and \
+                (self.compute_mode == "bf16" or self.attention_operands == "f16")
         if not (self.depthwise and self.tc_capable(d) and d == 256 and d // self.nhead == 128 and self.fused_ffn):
             return False
         fsz = self.conv1[1].weight.shape[0]
@@ -240,9 +244,10 @@ class ConformerEncoderLayer(nn.Module):
         sa, w, p = self.self_attn, self._packed_tc(), self._packed()
         d = xp.shape[-1]
         if row_limit is not None and not self.supports_row_limit(d):
-            raise NotImplementedError("row-limited FFTBlock needs d = 256, head_dim 128 and the fused depthwise FFN")
+            raise NotImplementedError("row-limited FFTBlock needs d = 256, head_dim 128 and the fused depthwise FFN, or "
+                                      "the wide block (head_dim 256 / 384, depthwise FFN, flash attention)")
         if d != 256:
-            return self._forward_tc_unfused_ln(xp, kpm, npass)
+            return self._forward_tc_unfused_ln(xp, kpm, npass, row_limit)
         two = self.two_pass_sites if npass == 3 else ()
         two = two if "pw1_16" in w else ()
         if d // self.nhead == 128:
@@ -277,7 +282,7 @@ class ConformerEncoderLayer(nn.Module):
         return ops.gemm_tc(vp, w2, b2, taps=taps2, residual=x1p, gamma=self.norm2.weight, beta=self.norm2.bias,
                            eps=self.eps, out="planes", npass=npass, tag="ffn2_ln_gemm")
 
-    def _attention_any_head_dim(self, xp, kpm, npass):
+    def _attention_any_head_dim(self, xp, kpm, npass, row_limit=None):
         """head_dim != 128 (e.g. 384 of the 76 M config): attention as tcgen05 GEMMs (Q.K^T, P.V through
         lfs2_gemm_tc2) around a row-softmax kernel; head_dim not a multiple of 32: CUDA-core flash kernel.
         Returns ctx as Planes."""
@@ -289,8 +294,10 @@ class ConformerEncoderLayer(nn.Module):
             f16 = self.compute_mode == "fp32"
             if not f16 or self.attention_operands == "f16":
                 qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="f16" if f16 else "bf16", npass=npass,
-                                  tag="qkv_gemm")
-                return ops.attention_tc_wide(qkv, kpm, self.nhead)[1]
+                                  tag="qkv_gemm", row_limit=row_limit)
+                return ops.attention_tc_wide(qkv, kpm, self.nhead, row_limit=row_limit)[1]
+        if row_limit is not None:
+            raise NotImplementedError("row limits need the flash attention kernels")
         if (d // self.nhead) % 32 == 0:
             qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, out="planes", npass=npass, tag="qkv_gemm")
             ctx, _, _ = ops.attention_mat_fwd(qkv, kpm, self.nhead, npass=npass)
@@ -298,24 +305,29 @@ class ConformerEncoderLayer(nn.Module):
         qkv = ops.gemm_tc(xp, w["in_proj"], sa.in_proj_bias, npass=npass, tag="qkv_gemm")
         return ops.split_bf16(ops.attention(qkv, kpm, self.nhead))
 
-    def _forward_tc_unfused_ln(self, xp, kpm, npass):
+    def _forward_tc_unfused_ln(self, xp, kpm, npass, row_limit=None):
         """d != 256 (e.g. the 76 M config, d = 768): tensor-core GEMMs with fp32 results, LayerNorm as its own kernel
         that takes the residual stream as planes and hands planes back -- the block is planes in, planes out.
         In "bf16" mode results that only feed single-pass products (the FFN intermediate) travel as ONE bf16 plane."""
         sa, w, p = self.self_attn, self._packed_tc(), self._packed()
-        ctx = self._attention_any_head_dim(xp, kpm, npass)
-        a = ops.gemm_tc(ctx, w["out_proj"], sa.out_proj.bias, npass=npass, tag="out_proj_gemm")
-        x1p = ops.add_layernorm_planes(xp, a, self.norm1.weight, self.norm1.bias, self.eps)
+        ctx = self._attention_any_head_dim(xp, kpm, npass, row_limit)
+        a = ops.gemm_tc(ctx, w["out_proj"], sa.out_proj.bias, npass=npass, tag="out_proj_gemm", row_limit=row_limit,
+                        zero_skipped=False)
+        x1p = ops.add_layernorm_planes(xp, a, self.norm1.weight, self.norm1.bias, self.eps, row_limit=row_limit)
         one = "bf16" if npass == 1 else "planes"
         if self.depthwise:
-            up = ops.dwconv1d_planes(x1p, p["dw_wt"], self.conv1[0].bias)
-            vp = ops.gemm_tc(up, w["pw1"], self.conv1[1].bias, relu=True, out=one, npass=npass, tag="ffn1_gemm")
-            y = ops.gemm_tc(vp, w["w_eff"], p["b_eff"], npass=npass, tag="ffn2_gemm")
+            up = ops.dwconv1d_planes(x1p, p["dw_wt"], self.conv1[0].bias, row_limit=row_limit)
+            vp = ops.gemm_tc(up, w["pw1"], self.conv1[1].bias, relu=True, out=one, npass=npass, tag="ffn1_gemm",
+                             row_limit=row_limit)
+            y = ops.gemm_tc(vp, w["w_eff"], p["b_eff"], npass=npass, tag="ffn2_gemm", row_limit=row_limit,
+                            zero_skipped=False)
+        elif row_limit is not None:
+            raise NotImplementedError("row limits need the depthwise FFN")
         else:
             vp = ops.gemm_tc(x1p, w["c1"], self.conv1.bias, taps=self.conv1.kernel_size[0], relu=True, out=one,
                              npass=npass, tag="ffn1_gemm")
             y = ops.gemm_tc(vp, w["c2"], self.conv2.bias, taps=self.conv2.kernel_size[0], npass=npass, tag="ffn2_gemm")
-        return ops.add_layernorm_planes(x1p, y, self.norm2.weight, self.norm2.bias, self.eps)
+        return ops.add_layernorm_planes(x1p, y, self.norm2.weight, self.norm2.bias, self.eps, row_limit=row_limit)
 
     def _ff_block(self, x):
         p = self._packed()

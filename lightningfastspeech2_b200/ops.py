@@ -188,16 +188,27 @@ def add_layernorm(x, y, gamma, beta, eps=LN_EPS):
     return out
 
 
-def add_layernorm_planes(x, y, gamma, beta, eps=LN_EPS):
-    """LayerNorm(x + y): x Planes (residual stream), y fp32 tensor or None -> Planes"""
+def add_layernorm_planes(x, y, gamma, beta, eps=LN_EPS, row_limit=None):
+    """LayerNorm(x + y): x Planes (residual stream), y fp32 tensor or None -> Planes.
+    row_limit = (lengths int32 (B), extra, ...) on (B,T,d) operands: rows of the 128-row groups starting at or after
+    lengths[b] + extra are neither read nor written (FastSpeech2.skip_pad_rows)."""
     _chk(x.hi, torch.bfloat16, "layernorm residual planes"); _chk(x.lo, torch.bfloat16, "layernorm residual planes")
     if y is not None:
         _chk(y, torch.float32, "layernorm branch")
     d = x.shape[-1]
     m = x.hi.numel() // d
     out = _empty_planes(tuple(x.shape), x.hi.device)
-    _launch("lfs2_add_layernorm_planes", _p(x.hi), _p(x.lo), _p(y), _p(gamma), _p(beta), _p(out.hi), _p(out.lo), m, d,
-            float(eps), _s(), tag="lfs2_add_layernorm", nbytes=4.0 * m * d * (3 if y is not None else 2))
+    if row_limit is None:
+        _launch("lfs2_add_layernorm_planes", _p(x.hi), _p(x.lo), _p(y), _p(gamma), _p(beta), _p(out.hi), _p(out.lo), m, d,
+                float(eps), _s(), tag="lfs2_add_layernorm", nbytes=4.0 * m * d * (3 if y is not None else 2))
+        return out
+    if x.hi.dim() != 3:
+        raise ValueError("add_layernorm_planes: row limits need (B,T,d) operands")
+    b, t = x.hi.shape[:2]
+    frac = _limited_fraction(row_limit, t)
+    _launch("lfs2_add_layernorm_planes_limited", _p(x.hi), _p(x.lo), _p(y), _p(gamma), _p(beta), _p(out.hi), _p(out.lo), b, t,
+            d, float(eps), _p(row_limit[0]), int(row_limit[1]), _s(), tag="lfs2_add_layernorm",
+            nbytes=4.0 * m * d * (3 if y is not None else 2) * frac)
     return out
 
 
@@ -515,7 +526,7 @@ OUT_KINDS = {"planes": 0, "f32": 1, "f16": 2, "bf16": 3}
 
 
 def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None, eps=LN_EPS, out="f32",
-            npass=3, tag=None, row_limit=None, dilation=1, leaky_slope=None, row_mask=None):
+            npass=3, tag=None, row_limit=None, dilation=1, leaky_slope=None, row_mask=None, zero_skipped=True):
     """a: Planes (B,T,d) [taps>1: Conv1d over T per utterance] or (...,d) for taps == 1;
     w: Planes (n, taps*d); residual: Planes shaped like the output (added on the tensor core).
     out = "f32" -> fp32 tensor, "planes" -> Planes (bf16 hi/lo), "f16" -> Planes(hi = ONE fp16 tensor, lo = None: the
@@ -554,7 +565,9 @@ def gemm_tc(a, w, bias, taps=1, relu=False, residual=None, gamma=None, beta=None
     out_shape = tuple(a.shape[:-1]) + (n,)
     dev = a.hi.device
     # an fp32 result of a row-limited launch is a user-visible tensor: the rows of skipped tiles read as zeros
-    of = (torch.zeros if row_limit is not None else torch.empty)(out_shape, device=dev, dtype=torch.float32) \
+    # (zero_skipped=False: the consumer skips the same rows -- the row-limited LayerNorm of the wide FFTBlock)
+    of = (torch.zeros if row_limit is not None and zero_skipped else torch.empty)(out_shape, device=dev,
+                                                                                  dtype=torch.float32) \
         if out == "f32" else None
     po = _empty_planes(out_shape, dev) if out == "planes" else None
     if out in ("f16", "bf16"):

@@ -140,12 +140,19 @@ def test_pad_row_skipping_host_logic():
     assert m._skips_pad_rows(False) is False                      # teacher-forced forward: every row, like the reference
     m.length_buckets = 2
     assert m._skips_pad_rows(True) is False                      # the bucketed path already cuts the rows
-    for preset in ("C1", "C3"):                                   # dense FFN / d = 768: no row-limited FFTBlock
-        other = _mk(preset).eval()
-        other.skip_pad_rows = True
-        assert not other.decoder.supports_row_limit(other.hparams.decoder_hidden)
-        with pytest.raises(NotImplementedError):
-            other._skips_pad_rows(True)
+    other = _mk("C1").eval()                                      # dense FFN convolutions: no row-limited FFTBlock
+    other.skip_pad_rows = True
+    assert not other.decoder.supports_row_limit(other.hparams.decoder_hidden)
+    with pytest.raises(NotImplementedError):
+        other._skips_pad_rows(True)
+    wide = _mk("C3").eval()                                       # d = 768, head_dim 384: the wide row-limited block
+    wide.skip_pad_rows = True
+    assert wide.encoder.supports_row_limit(768) and wide.decoder.supports_row_limit(768)
+    assert wide._skips_pad_rows(True) is True
+    for layer in wide.decoder.layers:
+        layer.wide_flash_attention = False                        # GEMM-decomposed attention: no row limits
+    with pytest.raises(NotImplementedError):
+        wide._skips_pad_rows(True)
     m.length_buckets, m.skip_pad_rows = 1, True
     m.set_compute_mode("simt")
     with pytest.raises(NotImplementedError):

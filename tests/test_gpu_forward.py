@@ -199,6 +199,31 @@ def test_skip_pad_rows_is_bit_identical_on_valid_frames(bsz, lo, hi, mode):
         assert (pr["mel"].cpu() - ref["mel"])[vr].abs().max() < MEL_TOL
 
 
+@pytest.mark.parametrize("mode", ["bf16", "fp32"])
+def test_skip_pad_rows_wide_block_is_bit_identical_on_valid_frames(mode):
+    """the 76 M configuration (d = 768, head_dim 384: GEMMs + stand-alone LayerNorm + wide flash attention) with
+    model.skip_pad_rows: same contract as the fused d = 256 block"""
+    model, sd, hp = build("C3", 5, mode=mode)
+    batch = synthetic.make_batch(6, 8, 200, seed=5)
+    with torch.no_grad():
+        full = model(batch, inference=True, force={"want_idx": True})
+        model.skip_pad_rows = True
+        part = model(batch, inference=True, force={"want_idx": True})
+        model.skip_pad_rows = False
+    assert torch.equal(full["duration_rounded"], part["duration_rounded"])
+    assert torch.equal(full["duration_prediction"], part["duration_prediction"])
+    assert torch.equal(full["tgt_mask"], part["tgt_mask"]) and torch.equal(full["src_mask"], part["src_mask"])
+    valid = ~full["tgt_mask"]
+    for v in hp["variances"]:
+        assert torch.equal(full[f"variances_{v}"], part[f"variances_{v}"]), v
+    assert torch.equal(full["mel"][valid], part["mel"][valid])
+    assert float(part["mel"][full["tgt_mask"]].abs().max()) == 0.0 and bool(torch.isfinite(part["mel"]).all())
+    lens = valid.sum(1)
+    halo = sum(layer.halo() for layer in model.decoder.layers)
+    kept = torch.clamp((lens + halo + 127) // 128 * 128, max=valid.shape[1]).sum().item()
+    assert kept < 0.85 * valid.numel(), (kept, valid.numel())
+
+
 def test_skip_pad_rows_unsupported_configs_raise():
     model, sd, hp = build("C1", 3)  # dense FFN convolutions: no row-limited path
     model.skip_pad_rows = True

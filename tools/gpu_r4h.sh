@@ -1,0 +1,14 @@
+set -x
+mkdir -p gpurun_out
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/r4h_bench_n2.json 2> gpurun_out/r4h_bench_n2.err; echo "bench n2 rc=$?"
+tail -3 gpurun_out/r4h_bench_n2.err
+python - <<'PY'
+import json
+d=json.loads([l for l in open('gpurun_out/r4h_bench_n2.json') if l.startswith('{')][-1])
+print('value',d['value'],'e2e',d['e2e']['value'], 'n', d['n_gpus'])
+t=d.get('train',{})
+print('train',t.get('ms_per_step'),json.dumps(t.get('length_buckets',{}).get('runs'))[:500],json.dumps(t.get('bf16_mode'))[:300])
+print('c3',d.get('c3_bf16',{}).get('value'))
+print('errors',d.get('errors'))
+PY
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tools/parity_2gpu.py > gpurun_out/r4h_parity_2gpu.log 2>&1; echo "parity rc=$?"; tail -12 gpurun_out/r4h_parity_2gpu.log
