@@ -107,3 +107,35 @@ def test_no_cpu_path():
     gen = hifigan.Generator(hifigan.AttrDict(HO.CONFIG))
     with pytest.raises(Exception, match="CUDA"):
         gen(torch.zeros(1, 80, 4))
+
+
+def test_synthesis_stream_vocodes_each_batch_like_the_per_utterance_caller(golden):
+    """SynthesisStream(model, vocoder=generator): mel -> int16 waveform on the device for the whole ragged batch ==
+    the reference's caller, which vocodes every utterance's own mel (synthesis/generator.py:160-170)"""
+    from lightningfastspeech2_b200 import configs
+    from lightningfastspeech2_b200.fastspeech2.fastspeech2 import FastSpeech2
+    from lightningfastspeech2_b200.pipeline import SynthesisStream
+
+    kw = configs.PRESETS["C2"]
+    hp = configs.resolve(kw)
+    st = {v: {"min": -3.0, "max": 3.0, "mean": 0.0, "std": 1.0} for v in hp["variances"]}
+    model = FastSpeech2(stats=st, phone2id={f"p{i}": i for i in range(80)}, num_workers=0, **kw)
+    model.load_state_dict(synthetic.fill_state_dict(model.state_dict(), seed=9))
+    model = model.eval().to(DEV)
+    gen, _ = build(golden["config"], golden["seed"])
+    for compact in (False, True):
+        stream = SynthesisStream(model, vocoder=gen, compact=compact)
+        batches = [synthetic.make_batch(3, 6, 30, seed=40 + i) for i in range(3)]
+        tickets = [stream.submit({k: b[k] for k in ("phones", "speaker")}) for b in batches[:2]]
+        results = [stream.collect(t) for t in tickets]
+        results.append(stream.collect(stream.submit({k: batches[2][k] for k in ("phones", "speaker")})))
+        for res in results:
+            assert res["hop"] == 256 and len(res["wav"]) == 3
+            for i, n in enumerate(res["lengths"]):
+                mel_i = res["mel"][i] if compact else res["mel"][i, :n]
+                assert res["wav"][i].dtype == torch.int16 and res["wav"][i].shape == (n * 256,)
+                with torch.no_grad():
+                    ref = gen(mel_i.T.unsqueeze(0).to(DEV))[0, 0].cpu()
+                ref16 = (ref.numpy() * 32768.0).astype("int16")
+                diff = np.abs(res["wav"][i].numpy().astype(np.int32) - ref16.astype(np.int32))
+                assert diff.max() <= 33, (i, int(diff.max()))     # 1e-3 of full scale: ragged batch vs single utterance
