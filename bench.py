@@ -522,6 +522,19 @@ def measure_vocoder(dev, mel, tgt_mask, nutt, steps=3):
         torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
     frames = int(lens.sum())
+    # the same call in "bf16" mode (single-pass conv1 MMAs; the residual stream stays fp32-exact)
+    gen.compute_mode = "bf16"
+    with torch.no_grad():
+        wav16 = gen(x, lens)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(steps):
+            wav16 = gen(x, lens)
+        e1.record()
+        torch.cuda.synchronize()
+    ms16 = e0.elapsed_time(e1) / steps
+    err16 = float((wav16 - wav).abs().max())
+    gen.compute_mode = "fp32"
     # CPU port on the shortest utterance (bounded), and parity on it
     i = int(lens.argmin())
     n = int(lens[i])
@@ -551,7 +564,9 @@ def measure_vocoder(dev, mel, tgt_mask, nutt, steps=3):
             "achieved_tflops": flops_per_frame * frames / (ms * 1e-3) / 1e12,
             "cpu_baseline": {"value": n / cpu_s, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                              "sample": f"the shortest of those utterances ({n} frames), one run of {cpu_s:.1f} s"},
-            "max_abs_wav_err_vs_oracle": err}
+            "max_abs_wav_err_vs_oracle": err,
+            "bf16_mode": {"ms_per_batch": ms16, "value": frames / (ms16 * 1e-3), "unit": UNIT,
+                          "max_abs_wav_diff_vs_fp32_mode": err16}}
 
 
 def run_reference(args):
