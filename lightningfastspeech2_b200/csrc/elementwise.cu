@@ -11,6 +11,15 @@
 #include "common.cuh"
 
 namespace lfs2 {
+namespace tc {
+// dwconv_tma.cu: 0 = launched, 1 = not its case (fall back to dwconv1d_k_kernel), < 0 = error
+int launch_dwconv_tma(const void* x_hi, const void* x_lo, const float* wt, const float* bias, float* out, void* out_hi,
+                      void* out_lo, void* out_f16, int batch, int t, int d, int ksize, const int* row_limit,
+                      int limit_extra, cudaStream_t s);
+}  // namespace tc
+}  // namespace lfs2
+
+namespace lfs2 {
 
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
@@ -796,6 +805,15 @@ int lfs2_dwconv1d_planes_ex(const float* x, const void* x_hi, const void* x_lo, 
                LFS2_ERR_INVALID_ARG, "dwconv1d: pointers must be 16-byte aligned");
   cudaStream_t s = (cudaStream_t)stream;
   LFS2_REQUIRE(batch <= 65535, LFS2_ERR_UNSUPPORTED, "dwconv1d: batch exceeds the grid limit");
+  if (x_hi) {  // long kernels on plane-form input: tiles staged by TMA through a two-stage ring (dwconv_tma.cu)
+    const int rc = tc::launch_dwconv_tma(x_hi, x_lo, wt, bias, out, out_hi, out_lo, out_f16, batch, t, d, ksize, row_limit,
+                                         limit_extra, s);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      LFS2_CHECK_LAUNCH("dwconv1d");
+      return LFS2_OK;
+    }
+  }
 #define LFS2_DW_CASE(K, TT)                                                                          \
   case K: {                                                                                          \
     int rc = launch_dwconv_k<K, TT, (K <= 9 ? 64 : 32)>(x, x_hi, x_lo, wt, bias, out, out_hi, out_lo, out_f16, batch, t, \

@@ -858,6 +858,7 @@ bool make_tmap_3d_ex(CUtensorMap* out, const void* base, int elem_bytes, uint64_
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMapSwizzle sw = swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                           : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                          : swizzle_bytes == 0  ? CU_TENSOR_MAP_SWIZZLE_NONE   // dense rows (dwconv_tma.cu)
                                                 : CU_TENSOR_MAP_SWIZZLE_32B;
   CUresult r = enc(out, elem_bytes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3,
                    const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,

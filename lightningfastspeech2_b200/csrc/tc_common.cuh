@@ -311,7 +311,8 @@ EncodeTiledFn get_encode_tiled();
 // zero fill outside the tensor.  swizzle_bytes in {64, 128} must equal box0 * 2.
 bool make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t box0,
                   uint32_t box1, int swizzle_bytes);
-// same for 2- or 4-byte elements (fp32 maps are used by the TMA tensor stores of the GEMM epilogue)
+// same for 2- or 4-byte elements (fp32 maps are used by the TMA tensor stores of the GEMM epilogue); swizzle_bytes = 0:
+// no swizzle (dense box rows)
 bool make_tmap_3d_ex(CUtensorMap* out, const void* base, int elem_bytes, uint64_t d0, uint64_t d1, uint64_t d2,
                      uint32_t box0, uint32_t box1, int swizzle_bytes);
 

@@ -41,6 +41,9 @@ class WeightCache:
         key = (ops.WEIGHTS_EPOCH, model.compute_mode, tuple(p._version for p in model.parameters()))
         if key != self.key:
             self.key, self.store, self.pending = key, {}, {}
+        # no backward pass is in flight when a forward starts (every backward ends in flush()): accumulators left behind
+        # by a backward that raised must not leak into the next one
+        self.pending = {}
 
     def get(self, tag, w, make):
         """w: a parameter or a view of one (its storage outlives the cache entry, so the address identifies it)"""

@@ -154,8 +154,8 @@ def test_bucket_embed_add():
 
 
 # ---- long depthwise kernels (the LightSpeech blocks use 13 ... 25 taps) on bench-sized launches ----
-@pytest.mark.parametrize("ks", [11, 13, 17, 21, 25])
-@pytest.mark.parametrize("bsz,t,d", [(9, 2203, 256), (3, 2211, 768)])
+@pytest.mark.parametrize("ks", [11, 13, 17, 21, 23, 25])
+@pytest.mark.parametrize("bsz,t,d", [(9, 2203, 256), (3, 2211, 768), (5, 70, 256), (2, 64, 256)])
 def test_dwconv1d_long_kernels_large_launches(bsz, t, d, ks):
     """K >= 11 on launches of bench size: fp32 and planes inputs, fp32 / planes / fp16 outputs, ragged T, several channel
     blocks (d = 768), row limits"""
@@ -179,6 +179,10 @@ def test_dwconv1d_long_kernels_large_launches(bsz, t, d, ks):
     assert float((g32.cpu().double() - refp).abs().max()) < 2e-5
     gh = ops.dwconv1d_planes(xp, wt, b.to(DEV), out="f16")
     assert gh.lo is None and torch.equal(gh.hi, g32.half())
+    # plane-form input of the 11 .. 23-tap kernels goes through the TMA-staged kernel (dwconv_tma.cu), fp32 input through
+    # the per-thread-load kernel: same operations in the same order => the same bits
+    same = ops.dwconv1d_planes(ops.merge_planes(xp), wt, b.to(DEV), out="f32")
+    assert torch.equal(same, g32)
     if d == 256:   # row limits: kept rows are the unlimited run's bit for bit, input rows past the kept tiles read as zeros
         lens = torch.randint(1, t + 1, (bsz,), generator=g).to(torch.int32).to(DEV)
         extra = 20
