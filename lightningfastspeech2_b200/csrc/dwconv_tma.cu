@@ -1,5 +1,5 @@
-// Depthwise conv of the LightSpeech FFN blocks for the long kernels (k = 11 .. 23) on plane-form activations, with the
-// input tiles staged by TMA (north_star: "TMA staging of (B, T, d_model) tiles into shared memory").
+// Depthwise conv of the LightSpeech FFN blocks for the 11 .. 19-tap kernels on plane-form activations, with the input
+// tiles staged by TMA (north_star: "TMA staging of (B, T, d_model) tiles into shared memory").
 //
 // dwconv1d_k_kernel (elementwise.cu) loads a tile with per-thread global loads, converts it to fp32 in shared memory
 // and only then starts its arithmetic: with 32-row tiles and 20 halo rows the load phase (~2 us of latency) is longer
@@ -10,7 +10,10 @@
 // current one, so the copy engine, not the warps, waits for memory.  The threads read the bf16 planes straight from the
 // ring (a warp's lanes cover 256 contiguous bytes per row and plane), rebuild fp32 as hi + lo and slide NT frames of
 // their 4 channels through registers exactly like dwconv1d_k_kernel: same operations in the same order, so the two
-// kernels agree bit for bit (tests/test_gpu_ops.py).
+// kernels agree bit for bit (tests/test_gpu_ops.py).  Measured at the C2 decoder's launch size (profiles/r4l_dwconv_ab.txt,
+// fp16 plane out): k = 13 88 -> 73 us, k = 17 92 -> 87 us; at k >= 21 the ring version is 14 % SLOWER (112 vs 98 us: the
+// kernel is issue-bound there -- 4 k tap registers under the 128-register cap of two CTAs per SM, conversions on every
+// read -- and the copy latency it hides was already covered by the second CTA), so those stay on dwconv1d_k_kernel.
 #include <stdlib.h>
 
 #include "tc_common.cuh"
@@ -22,7 +25,9 @@ constexpr int kDtCh4 = 64;          // float4 channel groups per CTA: 256 channe
 constexpr int kDtTile = 32;         // output frames per tile
 constexpr int kDtNT = 8;            // frames per thread
 constexpr int kDtThreads = kDtCh4 * (kDtTile / kDtNT);  // 256
-constexpr int kDtTilesPerCta = 4;
+// ring depth S = 2 with two CTAs per SM.  (S = 4 with one CTA per SM -- three tiles in flight instead of two -- was
+// 25-40 % slower at k >= 17: eight warps do not cover the arithmetic's latencies; profiles/r4l_dwconv_ab.txt.)
+__host__ __device__ constexpr int dt_tiles_per_cta(int stages) { return stages == 2 ? 4 : 8; }
 constexpr int kDtRowBytes = kDtCh4 * 4 * 2;             // one plane row of the CTA's channels: 512 B
 
 __device__ __forceinline__ float4 dt_planes_to_f4(uint2 h, uint2 l) {
@@ -34,8 +39,8 @@ __device__ __forceinline__ float4 dt_planes_to_f4(uint2 h, uint2 l) {
   return r;
 }
 
-template <int K>
-__global__ void __launch_bounds__(kDtThreads, 2)
+template <int K, int S>
+__global__ void __launch_bounds__(kDtThreads, S == 2 ? 2 : 1)
 dwconv1d_tma_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo,
                     const float4* __restrict__ wt, const float4* __restrict__ bias, float4* __restrict__ out,
                     uint2* __restrict__ out_hi, uint2* __restrict__ out_lo, uint2* __restrict__ out_f16, int t, int d4,
@@ -46,7 +51,8 @@ dwconv1d_tma_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   constexpr int kStage = 2 * kPlane;           // hi | lo
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
-  __shared__ __align__(8) uint64_t full_bar[2];
+  __shared__ __align__(8) uint64_t full_bar[S];
+  constexpr int kDtTilesPerCta = dt_tiles_per_cta(S);
 
   const int cb = blockIdx.y * kDtCh4;  // first float4 channel group of this CTA
   const int b = blockIdx.z;
@@ -67,30 +73,30 @@ dwconv1d_tma_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_hi);
     prefetch_tmap(&map_lo);
-    mbar_init(&full_bar[0], 1);
-    mbar_init(&full_bar[1], 1);
+    for (int q = 0; q < S; ++q) mbar_init(&full_bar[q], 1);
     fence_barrier_init();
   }
   __syncthreads();
-  auto issue = [&](int i) {  // tile tile0 + i -> stage i & 1
-    uint8_t* st = smem + (i & 1) * kStage;
-    uint64_t* bar = &full_bar[i & 1];
+  auto issue = [&](int i) {  // tile tile0 + i -> stage i % S
+    uint8_t* st = smem + (i % S) * kStage;
+    uint64_t* bar = &full_bar[i % S];
     const int row0 = (tile0 + i) * kDtTile - H;
     mbar_expect_tx(bar, kStage);
     tma_load_3d(st, &map_hi, bar, cb * 4, row0, b);
     tma_load_3d(st + kPlane, &map_lo, bar, cb * 4, row0, b);
   };
-  if (threadIdx.x == 0) issue(0);
+  if (threadIdx.x == 0)
+    for (int i = 0; i < S - 1 && i < ntiles; ++i) issue(i);
 
   const int c = threadIdx.x % kDtCh4, tg = threadIdx.x / kDtCh4;
   const size_t base = (size_t)b * t * d4 + cb;
 
 #pragma unroll 1
   for (int i = 0; i < ntiles; ++i) {
-    // the stage the next tile lands in was read in iteration i - 1; every thread has passed that iteration's barrier
-    if (threadIdx.x == 0 && i + 1 < ntiles) {
+    // the stage tile i + S - 1 lands in was read in iteration i - 1; every thread has passed that iteration's barrier
+    if (threadIdx.x == 0 && i + S - 1 < ntiles) {
       fence_proxy_async_smem();
-      issue(i + 1);
+      issue(i + S - 1);
     }
     // (the taps are re-read per tile -- L1 hits -- instead of living in 4 K registers across the loop: at k >= 21 that
     //  is the difference between 118 registers and spills under the two-CTAs-per-SM cap)
@@ -98,8 +104,8 @@ dwconv1d_tma_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
 #pragma unroll
     for (int j = 0; j < K; ++j) w[j] = __ldg(wt + (size_t)j * d4 + cb + c);
     const float4 bz = __ldg(bias + cb + c);
-    mbar_wait(&full_bar[i & 1], (i >> 1) & 1);
-    const uint8_t* st = smem + (i & 1) * kStage;
+    mbar_wait(&full_bar[i % S], (i / S) & 1);
+    const uint8_t* st = smem + (i % S) * kStage;
     const int t0 = (tile0 + i) * kDtTile;
     float4 acc[kDtNT];
 #pragma unroll
@@ -143,16 +149,16 @@ dwconv1d_tma_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
         }
       }
     }
-    __syncthreads();  // all reads of stage i & 1 are done before tile i + 2 is copied into it
+    __syncthreads();  // all reads of stage i % S are done before tile i + S is copied into it
   }
 }
 
-template <int K>
+template <int K, int S>
 static int launch_dwconv_tma_k(const CUtensorMap& mh, const CUtensorMap& ml, const float* wt, const float* bias, float* out,
                                void* out_hi, void* out_lo, void* out_f16, int batch, int t, int d, const int* row_limit,
                                int limit_extra, cudaStream_t s) {
-  constexpr int kSmem = 2 * 2 * (kDtTile + K - 1) * kDtRowBytes + 128;
-  auto kern = dwconv1d_tma_kernel<K>;
+  constexpr int kSmem = S * 2 * (kDtTile + K - 1) * kDtRowBytes + 128;
+  auto kern = dwconv1d_tma_kernel<K, S>;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem) != cudaSuccess) {
@@ -162,7 +168,7 @@ static int launch_dwconv_tma_k(const CUtensorMap& mh, const CUtensorMap& ml, con
     configured = true;
   }
   const int tiles = ceil_div(t, kDtTile);
-  dim3 grid(ceil_div(tiles, kDtTilesPerCta), d / 4 / kDtCh4, batch);
+  dim3 grid(ceil_div(tiles, dt_tiles_per_cta(S)), d / 4 / kDtCh4, batch);
   kern<<<grid, kDtThreads, kSmem, s>>>(mh, ml, (const float4*)wt, (const float4*)bias, (float4*)out, (uint2*)out_hi,
                                        (uint2*)out_lo, (uint2*)out_f16, t, d / 4, row_limit, limit_extra);
   return LFS2_OK;
@@ -176,16 +182,16 @@ int launch_dwconv_tma(const void* x_hi, const void* x_lo, const float* wt, const
     const char* e = getenv("LFS2_DWCONV_TMA");  // A/B knob (tools): 0 keeps the per-thread-load kernel
     return e ? atoi(e) : 1;
   }();
-  if (!enabled || ksize < 11 || ksize > 23 || d % (4 * kDtCh4) != 0 || t < 64) return 1;
+  if (!enabled || ksize < 11 || ksize > 19 || d % (4 * kDtCh4) != 0 || t < 64) return 1;
   CUtensorMap mh, ml;
   const uint32_t rows = kDtTile + ksize - 1;
   if (!make_tmap_3d_ex(&mh, x_hi, 2, d, t, batch, 4 * kDtCh4, rows, 0) ||
       !make_tmap_3d_ex(&ml, x_lo, 2, d, t, batch, 4 * kDtCh4, rows, 0))
     return 1;
 #define LFS2_DT_CASE(K) \
-  case K: return launch_dwconv_tma_k<K>(mh, ml, wt, bias, out, out_hi, out_lo, out_f16, batch, t, d, row_limit, limit_extra, s);
+  case K: return launch_dwconv_tma_k<K, 2>(mh, ml, wt, bias, out, out_hi, out_lo, out_f16, batch, t, d, row_limit, limit_extra, s);
   switch (ksize) {
-    LFS2_DT_CASE(11) LFS2_DT_CASE(13) LFS2_DT_CASE(15) LFS2_DT_CASE(17) LFS2_DT_CASE(19) LFS2_DT_CASE(21) LFS2_DT_CASE(23)
+    LFS2_DT_CASE(11) LFS2_DT_CASE(13) LFS2_DT_CASE(15) LFS2_DT_CASE(17) LFS2_DT_CASE(19)
   }
 #undef LFS2_DT_CASE
   return 1;
