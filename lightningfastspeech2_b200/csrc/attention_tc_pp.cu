@@ -287,15 +287,17 @@ attention_tc_pp_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
           if ((mbits1 >> i) & 1u) s[32 + i] = -INFINITY;
         }
       }
-      float t0 = s[0], t1 = s[1], t2 = s[2], t3 = s[3];
+      // row maximum: four chains of three-input maxima (FMNMX3: two new logits per issue slot)
+      float t0 = fmaxf(s[0], s[4]), t1 = fmaxf(s[1], s[5]), t2 = fmaxf(s[2], s[6]), t3 = fmaxf(s[3], s[7]);
+      static_assert(kPK % 8 == 0, "row maximum: the chains take eight logits per step");
 #pragma unroll
-      for (int i = 4; i < kPK; i += 4) {
-        t0 = fmaxf(t0, s[i]);
-        t1 = fmaxf(t1, s[i + 1]);
-        t2 = fmaxf(t2, s[i + 2]);
-        t3 = fmaxf(t3, s[i + 3]);
+      for (int i = 8; i < kPK; i += 8) {
+        t0 = fmax3(t0, s[i], s[i + 4]);
+        t1 = fmax3(t1, s[i + 1], s[i + 5]);
+        t2 = fmax3(t2, s[i + 2], s[i + 6]);
+        t3 = fmax3(t3, s[i + 3], s[i + 7]);
       }
-      const float tmax = fmaxf(fmaxf(t0, t1), fmaxf(t2, t3));
+      const float tmax = fmax3(fmaxf(t0, t1), t2, t3);
       // lazy rescale: the exponent reference only moves (and O, l are rescaled) when some row's logits outgrow it by 2^8
       const bool grow = (j > 0) && ((tmax - m_run) * c > 8.f);
       if (j == 0) {
@@ -319,21 +321,25 @@ attention_tc_pp_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
       }
       const float mc = (m_run == -INFINITY) ? 0.f : m_run * c;
       uint32_t ph[kPK / 2];
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
+      // These warps are bound by issue slots and dependent-instruction latency, not by the MUFU pipe (one exponential in
+      // four as a Cody-Waite + degree-4 polynomial on the FMA pipe: 1430 -> 2340 cycles per key tile).  The scale-and-
+      // shift and the row sums therefore run as packed pairs (FFMA2 / FADD2: half the issue slots, the same bits).
+      const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
+      float2 l01 = make_float2(0.f, 0.f), l23 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < kPK / 4; ++i) {
-        const float p0 = ex2_approx(fmaf(s[4 * i], c, -mc));
-        const float p1 = ex2_approx(fmaf(s[4 * i + 1], c, -mc));
-        const float p2 = ex2_approx(fmaf(s[4 * i + 2], c, -mc));
-        // (one exponential in four as a Cody-Waite + degree-4 polynomial on the FMA pipe, to take load off MUFU: the
-        // softmax phase went from 1430 to 2340 cycles per key tile -- these warps are bound by issue slots and
-        // dependent-instruction latency, not by the MUFU pipe)
-        const float p3 = ex2_approx(fmaf(s[4 * i + 3], c, -mc));
-        l0 += p0; l1 += p1; l2 += p2; l3 += p3;
+        const float2 e01 = ffma2(make_float2(s[4 * i], s[4 * i + 1]), c2, nmc2);
+        const float2 e23 = ffma2(make_float2(s[4 * i + 2], s[4 * i + 3]), c2, nmc2);
+        const float p0 = ex2_approx(e01.x);
+        const float p1 = ex2_approx(e01.y);
+        const float p2 = ex2_approx(e23.x);
+        const float p3 = ex2_approx(e23.y);
+        l01 = fadd2(l01, make_float2(p0, p1));
+        l23 = fadd2(l23, make_float2(p2, p3));
         ph[2 * i] = p_pack16(p0, p1, FMT);
         ph[2 * i + 1] = p_pack16(p2, p3, FMT);
       }
-      l_run += (l0 + l1) + (l2 + l3);
+      l_run += (l01.x + l01.y) + (l23.x + l23.y);
       p_tmem_st32_u(ts, ph);
       tmem_wait_st();
       tc_fence_before();
@@ -356,7 +362,11 @@ attention_tc_pp_kernel(const __grid_constant__ CUtensorMap map_kv, const __grid_
       if (ntiles > 0) {
         tmem_ld32(tmem_base + kPColO + cc * 32 + lane_off, o);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] *= inv_l;
+        for (int i = 0; i < 32; i += 2) {
+          const float2 v = fmul2(make_float2(o[i], o[i + 1]), make_float2(inv_l, inv_l));
+          o[i] = v.x;
+          o[i + 1] = v.y;
+        }
       } else {
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] = __int_as_float(0x7fc00000);

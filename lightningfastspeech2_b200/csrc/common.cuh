@@ -47,6 +47,59 @@ static inline int num_sms() {
   return n;
 }
 
+// acc += w * x on all four lanes of a float4 as two packed fp32 FMAs (sm_100 FFMA2: two IEEE fused multiply-adds per
+// issue slot, bit-identical to four fmaf).  The stencil loops of the depthwise conv are issue-bound, not FMA-pipe-bound.
+__device__ __forceinline__ void fma4(float4& acc, const float4& w, const float4& x) {
+  unsigned long long a0, a1, w0, w1, x0, x1;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a0) : "f"(acc.x), "f"(acc.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a1) : "f"(acc.z), "f"(acc.w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(w0) : "f"(w.x), "f"(w.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(w1) : "f"(w.z), "f"(w.w));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x0) : "f"(x.x), "f"(x.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x1) : "f"(x.z), "f"(x.w));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a0) : "l"(w0), "l"(x0));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(a1) : "l"(w1), "l"(x1));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.x), "=f"(acc.y) : "l"(a0));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(acc.z), "=f"(acc.w) : "l"(a1));
+}
+
+// packed fp32 pairs (sm_100 FFMA2 / FADD2 / FMUL2): two IEEE operations per issue slot, bit-identical to the scalar forms
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ua, ub, uc;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(uc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(uc) : "l"(ua), "l"(ub));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(uc));
+  return r;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  unsigned long long ua, ub;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(ua) : "l"(ub));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(ua));
+  return r;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  unsigned long long ua, ub;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ua) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ub) : "f"(b.x), "f"(b.y));
+  asm("mul.rn.f32x2 %0, %0, %1;" : "+l"(ua) : "l"(ub));
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(ua));
+  return r;
+}
+
+// max(a, b, c) in one instruction (sm_100 FMNMX3)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -121,10 +121,7 @@ dwconv1d_tma_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_con
       for (int o = 0; o < kDtNT; ++o) {
         const int tap = j - o;  // compile-time after unrolling
         if (tap >= 0 && tap < K) {
-          acc[o].x = fmaf(w[tap].x, xv.x, acc[o].x);
-          acc[o].y = fmaf(w[tap].y, xv.y, acc[o].y);
-          acc[o].z = fmaf(w[tap].z, xv.z, acc[o].z);
-          acc[o].w = fmaf(w[tap].w, xv.w, acc[o].w);
+          fma4(acc[o], w[tap], xv);
         }
       }
     }
@@ -182,7 +179,7 @@ int launch_dwconv_tma(const void* x_hi, const void* x_lo, const float* wt, const
     const char* e = getenv("LFS2_DWCONV_TMA");  // A/B knob (tools): 0 keeps the per-thread-load kernel
     return e ? atoi(e) : 1;
   }();
-  if (!enabled || ksize < 11 || ksize > 19 || d % (4 * kDtCh4) != 0 || t < 64) return 1;
+  if (!enabled || ksize < 11 || ksize > (enabled == 3 ? 23 : 19) || d % (4 * kDtCh4) != 0 || t < 64) return 1;  // (3: A/B)
   CUtensorMap mh, ml;
   const uint32_t rows = kDtTile + ksize - 1;
   if (!make_tmap_3d_ex(&mh, x_hi, 2, d, t, batch, 4 * kDtCh4, rows, 0) ||
@@ -191,7 +188,7 @@ int launch_dwconv_tma(const void* x_hi, const void* x_lo, const float* wt, const
 #define LFS2_DT_CASE(K) \
   case K: return launch_dwconv_tma_k<K, 2>(mh, ml, wt, bias, out, out_hi, out_lo, out_f16, batch, t, d, row_limit, limit_extra, s);
   switch (ksize) {
-    LFS2_DT_CASE(11) LFS2_DT_CASE(13) LFS2_DT_CASE(15) LFS2_DT_CASE(17) LFS2_DT_CASE(19)
+    LFS2_DT_CASE(11) LFS2_DT_CASE(13) LFS2_DT_CASE(15) LFS2_DT_CASE(17) LFS2_DT_CASE(19) LFS2_DT_CASE(21) LFS2_DT_CASE(23)
   }
 #undef LFS2_DT_CASE
   return 1;

@@ -195,11 +195,8 @@ __global__ void dwconv1d_kernel(const float4* __restrict__ x, const uint2* __res
     for (int o = 0; o < kDwT; ++o) {
       int tap = j - o;
       if (tap >= 0 && tap < ksize) {
-        float4 w = wt[(size_t)tap * d4 + c];
-        acc[o].x = fmaf(w.x, xv.x, acc[o].x);
-        acc[o].y = fmaf(w.y, xv.y, acc[o].y);
-        acc[o].z = fmaf(w.z, xv.z, acc[o].z);
-        acc[o].w = fmaf(w.w, xv.w, acc[o].w);
+        const float4 w = wt[(size_t)tap * d4 + c];
+        fma4(acc[o], w, xv);
       }
     }
   }
@@ -509,10 +506,7 @@ dwconv1d_k_kernel(const float4* __restrict__ x, const uint2* __restrict__ x_hi, 
     for (int o = 0; o < NT; ++o) {
       const int tap = j - o;  // compile-time after unrolling
       if (tap >= 0 && tap < K) {
-        acc[o].x = fmaf(w[tap].x, xv.x, acc[o].x);
-        acc[o].y = fmaf(w[tap].y, xv.y, acc[o].y);
-        acc[o].z = fmaf(w[tap].z, xv.z, acc[o].z);
-        acc[o].w = fmaf(w[tap].w, xv.w, acc[o].w);
+        fma4(acc[o], w[tap], xv);
       }
     }
   }
