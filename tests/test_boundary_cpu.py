@@ -245,3 +245,57 @@ def test_length_bucket_plan_covers_every_utterance_with_its_halo():
             assert cap_g <= l <= l_full and l == min(cap_g + h_dec, l_full)
         # the bucket holding the batch's longest utterance ends exactly where the full tensor ends
         assert plan[0][2][0] == l_full
+
+
+def test_train_weight_cache_lifecycle():
+    """training.WeightCache (host logic of the train step's per-step weight pack): entries are built once per weight state
+    and shared; accumulators are created once per backward and finished exactly once by flush(); a parameter change (its
+    _version, or ops.WEIGHTS_EPOCH for writes through raw pointers) drops everything; a forward start drops accumulators an
+    aborted backward left behind"""
+    import torch
+
+    from lightningfastspeech2_b200 import ops
+    from lightningfastspeech2_b200.fastspeech2.training import WeightCache
+
+    model = torch.nn.Linear(4, 3)
+    model.compute_mode = "fp32"
+    cache = WeightCache()
+    cache.validate(model)
+    built = []
+    w = model.weight
+
+    def make():
+        built.append(1)
+        return w.detach().clone()
+
+    a = cache.get("planes", w, make)
+    b = cache.get("planes", w.view(3, 4), make)          # a view of the parameter: same storage, same shape -> same entry
+    assert a is b and len(built) == 1
+    assert cache.get("planesT", w, make) is not a and len(built) == 2   # another tag is another entry
+    finished = []
+    acc1 = cache.accumulator("d_fold", w, lambda: torch.zeros(3), lambda acc: finished.append(acc))
+    acc2 = cache.accumulator("d_fold", w, lambda: torch.ones(3), lambda acc: finished.append(acc))
+    assert acc1 is acc2                                   # the second bucket adds into the first one's accumulator
+    cache.flush()
+    assert len(finished) == 1 and finished[0] is acc1
+    cache.flush()
+    assert len(finished) == 1                             # nothing pending any more
+    cache.validate(model)
+    assert cache.get("planes", w, make) is a and len(built) == 2        # same weights: still cached
+    with torch.no_grad():
+        w.add_(1.0)                                       # torch-side update: _version moves
+    cache.validate(model)
+    assert cache.get("planes", w, make) is not a and len(built) == 3
+    epoch = ops.WEIGHTS_EPOCH
+    try:
+        ops.WEIGHTS_EPOCH += 1                            # what the fused optimizer does after writing through raw pointers
+        cache.validate(model)
+        cache.get("planes", w, make)
+        assert len(built) == 4
+    finally:
+        ops.WEIGHTS_EPOCH = epoch
+    cache.validate(model)
+    cache.accumulator("d_fold", w, lambda: torch.zeros(3), lambda acc: finished.append(acc))   # a backward that raised ...
+    cache.validate(model)                                 # ... must not leak into the next step
+    cache.flush()
+    assert len(finished) == 1
