@@ -324,16 +324,18 @@ attention_tc_wide_kernel(const __grid_constant__ CUtensorMap map_kv, const __gri
       }
       const float mc = (m_run == -INFINITY) ? 0.f : m_run * c;
       uint32_t ph[kWE / 2];
-      float lsum0 = 0.f, lsum1 = 0.f;
+      // scale-and-shift and the row sums as packed pairs (FFMA2 / FADD2: half the issue slots, the same bits)
+      const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
+      float2 lsum = make_float2(0.f, 0.f);
 #pragma unroll
       for (int i = 0; i < kWE / 2; ++i) {
-        const float p0 = ex2_approx(fmaf(s[2 * i], c, -mc));
-        const float p1 = ex2_approx(fmaf(s[2 * i + 1], c, -mc));
-        lsum0 += p0;
-        lsum1 += p1;
+        const float2 e = ffma2(make_float2(s[2 * i], s[2 * i + 1]), c2, nmc2);
+        const float p0 = ex2_approx(e.x);
+        const float p1 = ex2_approx(e.y);
+        lsum = fadd2(lsum, make_float2(p0, p1));
         ph[i] = w_pack16(p0, p1, FMT);
       }
-      l_run += lsum0 + lsum1;
+      l_run += lsum.x + lsum.y;
       w_tmem_st16_u(ts + half * (kWE / 2), ph);
       tmem_wait_st();
       tc_fence_before();
