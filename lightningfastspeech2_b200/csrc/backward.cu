@@ -643,7 +643,11 @@ int lfs2_layernorm_bwd_drop(const float* dy, const float* z, const float* stats,
   LFS2_REQUIRE(aligned16(dy) && aligned16(z) && aligned16(gamma) && aligned16(dz) && (!add || aligned16(add)) &&
                    ((reinterpret_cast<uintptr_t>(stats) & 7u) == 0),
                LFS2_ERR_INVALID_ARG, "layernorm_bwd: pointers must be 16-byte aligned");
-  int blocks = ceil_div(m, 8 * 8);  // >= 8 rows per warp
+  // 8 rows per warp on large launches (fewer dgamma / dbeta atomics), down to 2 when that would leave CTA slots empty
+  // (three 256-thread CTAs fit per SM: a data-parallel rank's 10 k rows used 160 of 444 slots)
+  int rows_per_warp = ceil_div(m, 3 * num_sms() * 8);
+  rows_per_warp = rows_per_warp < 2 ? 2 : (rows_per_warp > 8 ? 8 : rows_per_warp);
+  int blocks = ceil_div(m, 8 * rows_per_warp);
   if (blocks > 8 * num_sms()) blocks = 8 * num_sms();
   if (blocks < 1) blocks = 1;
   const int nv = ceil_div(d / 4, 32);
