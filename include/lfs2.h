@@ -427,6 +427,23 @@ LFS2_API int lfs2_relu_bwd_scaled(const float* dy, const float* y, float* dx, lo
  * (autograd of F.relu / nn.Dropout / Conv1d bias in reference model.py:117-121, 539-557). */
 LFS2_API int lfs2_relu_bwd_planes(const float* dy, const float* y_f32, const void* y_hi, void* dx_hi, void* dx_lo,
                                   float* db, int rows, int cols, float scale, void* stream);
+/* Per-step weight re-formatting of the train step in one launch.  Each entry describes one fp32 weight matrix
+ * (rows, cols; row-major) and where its operand forms go: bf16 hi/lo planes of W (same layout; hi == NULL: skip) and of
+ * W^T ((cols, rows) row-major; hi_t == NULL: skip) -- what lfs2_split_bf16(W) and lfs2_split_bf16(lfs2_transpose(W))
+ * produce, i.e. the forward and the input-gradient operand of Linear / 1x1 Conv1d weights (autograd of reference
+ * model.py:82,92,111-114,552).  tile_begin = index of the entry's first 32 x 32 tile in the launch (entries sorted by it,
+ * the first one 0); total_tiles = sum of ceil(rows/32) * ceil(cols/32).  `entries` is DEVICE memory. */
+typedef struct lfs2_prep_entry {
+  const float* src;
+  void* hi;
+  void* lo;
+  void* hi_t;
+  void* lo_t;
+  int rows, cols;
+  int tile_begin;
+  int reserved;
+} lfs2_prep_entry;
+LFS2_API int lfs2_weight_planes_batched(const lfs2_prep_entry* entries, int n_entries, int total_tiles, void* stream);
 /* dst += src */
 LFS2_API int lfs2_add_inplace(float* dst, const float* src, long long n, void* stream);
 /* out (cols, rows) = in (rows, cols)^T -- transposed weight copies for the input-gradient GEMMs */

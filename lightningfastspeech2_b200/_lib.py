@@ -88,6 +88,7 @@ SIGNATURES = {
     "lfs2_relu_bwd": [_vp, _vp, _vp, _ll, _vp],
     "lfs2_relu_bwd_scaled": [_vp, _vp, _vp, _ll, _f, _vp],
     "lfs2_relu_bwd_planes": [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp],
+    "lfs2_weight_planes_batched": [_vp, _i, _i, _vp],
     "lfs2_add_inplace": [_vp, _vp, _ll, _vp],
     "lfs2_transpose": [_vp, _vp, _i, _i, _vp],
     "lfs2_dwconv1d_bwd_w": [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp],

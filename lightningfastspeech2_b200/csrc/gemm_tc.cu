@@ -1009,6 +1009,56 @@ relu_bwd_planes_kernel(const float4* __restrict__ dy, const void* __restrict__ y
   }
 }
 
+// One launch for the per-step re-formatting of every GEMM weight of the train step: bf16 hi/lo planes of W (rows, cols)
+// and of W^T (cols, rows) for a table of matrices (lfs2_prep_entry, include/lfs2.h).  CTA = one 32 x 32 tile of one
+// entry, found by binary search over the entries' first-tile indices.  Same values as split_bf16(W) and
+// split_bf16(transpose(W)), which it replaces (~210 launches of a few microseconds each per step).
+__global__ void __launch_bounds__(256)
+weight_prep_kernel(const lfs2_prep_entry* __restrict__ entries, int n) {
+  __shared__ float tile[32][33];
+  const int tid = blockIdx.x;
+  int lo_i = 0, hi_i = n - 1;
+  while (lo_i < hi_i) {
+    const int mid = (lo_i + hi_i + 1) >> 1;
+    if (entries[mid].tile_begin <= tid) lo_i = mid;
+    else hi_i = mid - 1;
+  }
+  const lfs2_prep_entry en = entries[lo_i];
+  const int tiles_x = (en.cols + 31) >> 5;
+  const int lt = tid - en.tile_begin;
+  const int r0 = (lt / tiles_x) << 5, c0 = (lt % tiles_x) << 5;
+  __nv_bfloat16* hi = reinterpret_cast<__nv_bfloat16*>(en.hi);
+  __nv_bfloat16* lo = reinterpret_cast<__nv_bfloat16*>(en.lo);
+  __nv_bfloat16* hi_t = reinterpret_cast<__nv_bfloat16*>(en.hi_t);
+  __nv_bfloat16* lo_t = reinterpret_cast<__nv_bfloat16*>(en.lo_t);
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    float v = 0.f;
+    if (r < en.rows && c < en.cols) {
+      v = en.src[(size_t)r * en.cols + c];
+      if (hi) {
+        __nv_bfloat16 h, l;
+        split_bf16(v, h, l);
+        hi[(size_t)r * en.cols + c] = h;
+        lo[(size_t)r * en.cols + c] = l;
+      }
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (hi_t) {
+    for (int i = threadIdx.y; i < 32; i += 8) {
+      const int c = c0 + i, r = r0 + threadIdx.x;
+      if (r < en.rows && c < en.cols) {
+        __nv_bfloat16 h, l;
+        split_bf16(tile[threadIdx.x][i], h, l);
+        hi_t[(size_t)c * en.rows + r] = h;
+        lo_t[(size_t)c * en.rows + r] = l;
+      }
+    }
+  }
+}
+
 }  // namespace tc
 }  // namespace lfs2
 
@@ -1278,6 +1328,15 @@ int lfs2_relu_bwd_planes(const float* dy, const float* y_f32, const void* y_hi, 
     relu_bwd_planes_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>((const float4*)dy, y_hi, (uint2*)dx_hi,
                                                                            (uint2*)dx_lo, db, rows, n4, rows_per_cta, scale);
   LFS2_CHECK_LAUNCH("relu_bwd_planes");
+  return LFS2_OK;
+}
+
+int lfs2_weight_planes_batched(const lfs2_prep_entry* entries, int n_entries, int total_tiles, void* stream) {
+  LFS2_REQUIRE(entries, LFS2_ERR_INVALID_ARG, "weight_planes_batched: null table");
+  if (n_entries == 0 || total_tiles == 0) return LFS2_OK;
+  LFS2_REQUIRE(n_entries > 0 && total_tiles > 0, LFS2_ERR_INVALID_ARG, "weight_planes_batched: bad counts");
+  weight_prep_kernel<<<total_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(entries, n_entries);
+  LFS2_CHECK_LAUNCH("weight_planes_batched");
   return LFS2_OK;
 }
 

@@ -34,13 +34,19 @@ class WeightCache:
     depthwise taps).  Built on first use after the parameters changed, shared by forward and backward and by every length
     bucket of the step; `flush()` at the end of a backward pass runs the deferred gradient kernels once."""
 
+    batched_prep = True   # refill the planes of every GEMM weight with ONE launch per step (see _prefill)
+
     def __init__(self):
         self.key, self.store, self.pending = None, {}, {}
+        self.seen, self.plan = {}, None
 
     def validate(self, model):
         key = (ops.WEIGHTS_EPOCH, model.compute_mode, tuple(p._version for p in model.parameters()))
         if key != self.key:
+            seen, self.seen = self.seen, {}
             self.key, self.store, self.pending = key, {}, {}
+            if self.batched_prep and seen and model.compute_mode != "simt":
+                self._prefill(seen)
         # no backward pass is in flight when a forward starts (every backward ends in flush()): accumulators left behind
         # by a backward that raised must not leak into the next one
         self.pending = {}
@@ -51,7 +57,37 @@ class WeightCache:
         v = self.store.get(k)
         if v is None:
             v = self.store[k] = make()
+        if tag in ("planes", "planesT"):
+            self.seen[k] = w
         return v
+
+    def _prefill(self, seen):
+        """The weights changed (optimizer step): every (planes, planesT) entry the LAST step asked for is rebuilt by one
+        lfs2_weight_planes_batched launch into persistent buffers, instead of one split / transpose + split launch per
+        matrix as the step reaches it.  Only sources that are parameters (or views of parameters) take part: tensors the
+        cache derives itself (the folded FFN-2 matrix) do not exist yet for the new weights and stay on the lazy path."""
+        want = {}
+        for (tag, ptr, shape), w in seen.items():
+            derived = not isinstance(w, torch.nn.Parameter) and w._base is None
+            if derived or w.dim() != 2 or w.dtype != torch.float32 or not w.is_contiguous() or not w.is_cuda:
+                continue
+            e = want.setdefault((ptr, shape), [w, False, False])
+            e[1 if tag == "planes" else 2] = True
+        if not want:
+            return
+        sources = [(w, p, t) for w, p, t in want.values()]
+        sig = tuple((w.data_ptr(), tuple(w.shape), p, t) for w, p, t in sources)
+        if self.plan is None or self.plan.signature != sig:
+            self.plan = ops.WeightPrepPlan(sources)
+        self.plan.run()
+        for (w, p, t), pl, pt in zip(sources, self.plan.planes, self.plan.planes_t):
+            k = (w.data_ptr(), tuple(w.shape))
+            if pl is not None:
+                self.store[("planes",) + k] = pl
+                self.seen[("planes",) + k] = w
+            if pt is not None:
+                self.store[("planesT",) + k] = pt
+                self.seen[("planesT",) + k] = w
 
     def accumulator(self, tag, w, make, finish):
         """-> the step's accumulator for (tag, w), created by make(); finish(acc) runs once in flush()"""

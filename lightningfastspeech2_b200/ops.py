@@ -927,6 +927,50 @@ def relu_bwd_planes(dy, y, scale=1.0, db=None):
     return out
 
 
+class WeightPrepPlan:
+    """Persistent buffers + device table of one lfs2_weight_planes_batched launch: sources = [(fp32 (rows, cols) tensor,
+    want planes of W, want planes of W^T)].  `planes[i]` / `planes_t[i]` are the Planes the launch fills (or None)."""
+
+    def __init__(self, sources):
+        import numpy as np
+
+        dev = sources[0][0].device
+        pad = lambda n: (n + 63) // 64 * 64   # every plane starts on a 128-byte boundary (TMA operands)
+        total = sum(pad(w.numel()) * (2 * int(p) + 2 * int(t)) for w, p, t in sources)
+        self.buf = torch.empty(total, device=dev, dtype=torch.bfloat16)
+        dt = np.dtype([("src", "<u8"), ("hi", "<u8"), ("lo", "<u8"), ("hi_t", "<u8"), ("lo_t", "<u8"), ("rows", "<i4"),
+                       ("cols", "<i4"), ("tile_begin", "<i4"), ("reserved", "<i4")])
+        tab = np.zeros(len(sources), dtype=dt)
+        self.planes, self.planes_t, self.sources = [], [], [w for w, _, _ in sources]
+        off = tiles = 0
+        for i, (w, want_p, want_t) in enumerate(sources):
+            _chk(w, torch.float32, "weight_prep source", 2)
+            rows, cols = w.shape
+            n = rows * cols
+
+            def take(shape):
+                nonlocal off
+                v = self.buf[off:off + n].view(shape)
+                off += pad(n)
+                return v
+
+            pl = Planes(take((rows, cols)), take((rows, cols))) if want_p else None
+            pt = Planes(take((cols, rows)), take((cols, rows))) if want_t else None
+            self.planes.append(pl)
+            self.planes_t.append(pt)
+            tab[i] = (w.data_ptr(), pl.hi.data_ptr() if pl else 0, pl.lo.data_ptr() if pl else 0,
+                      pt.hi.data_ptr() if pt else 0, pt.lo.data_ptr() if pt else 0, rows, cols, tiles, 0)
+            tiles += ((rows + 31) // 32) * ((cols + 31) // 32)
+        self.n, self.tiles = len(sources), tiles
+        self.table = torch.from_numpy(tab.view(np.uint8).copy()).to(dev)
+        self.signature = tuple((w.data_ptr(), tuple(w.shape), p, t) for w, p, t in sources)
+
+    def run(self):
+        """(re)fill every output from the sources' current values: one launch"""
+        _launch("lfs2_weight_planes_batched", _p(self.table), self.n, self.tiles, _s(), tag="lfs2_weight_prep",
+                nbytes=float(sum(w.numel() for w in self.sources)) * 4.0 + 2.0 * self.buf.numel())
+
+
 def add_(dst, src):
     _launch("lfs2_add_inplace", _p(dst), _p(src), dst.numel(), _s(), nbytes=12.0 * dst.numel())
     drop_planes(dst)

@@ -460,3 +460,50 @@ def test_bf16_train_step_tracks_the_fp64_gradient():
     assert rel <= 5e-2 and cos >= 0.999, (rel, cos)
     print(f"bf16 train step: loss {total:.5f} (fp64 {float(losses['total']):.5f}), whole gradient rel L2 {rel:.2e}, cosine "
           f"{cos:.5f}; worst tensor cosine {worst[1]:.4f} at {worst[0]}")
+
+
+def test_batched_weight_planes_equal_split_and_transpose():
+    """lfs2_weight_planes_batched (ops.WeightPrepPlan) == split_bf16(W) / split_bf16(transpose(W)) bit for bit, ragged
+    shapes included, and refills from the sources' current values"""
+    g = torch.Generator().manual_seed(7)
+    ws = [torch.randn(r, c, generator=g).to(DEV) for r, c in ((768, 2304), (80, 768), (33, 70), (256, 256), (3072, 768))]
+    plan = ops.WeightPrepPlan([(ws[0], True, True), (ws[1], True, False), (ws[2], True, True), (ws[3], False, True),
+                               (ws[4], True, True)])
+    for rnd_ in range(2):
+        plan.run()
+        for w, pl, pt in zip(ws, plan.planes, plan.planes_t):
+            if pl is not None:
+                ref = ops.split_bf16(w)
+                assert torch.equal(pl.hi, ref.hi) and torch.equal(pl.lo, ref.lo)
+            if pt is not None:
+                ref = ops.split_bf16(ops.transpose(w))
+                assert torch.equal(pt.hi, ref.hi) and torch.equal(pt.lo, ref.lo)
+        for w in ws:
+            w.mul_(1.7).add_(0.01)      # an optimizer step: same addresses, new values
+
+
+def test_train_steps_with_and_without_the_batched_weight_prep_agree():
+    """three optimizer steps with training.WeightCache.batched_prep on / off: the same parameters bit for bit (the planes
+    the GEMMs read are the same values either way)"""
+    from lightningfastspeech2_b200.fastspeech2 import training
+
+    outs = []
+    for flag in (True, False):
+        old = training.WeightCache.batched_prep
+        training.WeightCache.batched_prep = flag
+        try:
+            torch.manual_seed(0)
+            model, sd, hp = _build("C2_TRAIN", 3, "fp32", train=True)
+            model.log_losses = False
+            batch = synthetic.add_train_targets(synthetic.make_batch(4, 10, 40, seed=3), hp["variances"], seed=3)
+            batch = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in batch.items()}
+            (opt,), _ = model.configure_optimizers()
+            for _ in range(3):
+                model.training_step(batch, 0).backward()
+                opt.step()
+            torch.cuda.synchronize()
+            outs.append({k: p.detach().clone() for k, p in model.named_parameters()})
+        finally:
+            training.WeightCache.batched_prep = old
+    worst = max(float((outs[0][k] - outs[1][k]).abs().max()) / max(float(outs[1][k].abs().max()), 1e-12) for k in outs[0])
+    assert worst <= 1e-5, worst   # (fp32 atomics in the weight-gradient reductions: not bitwise)
