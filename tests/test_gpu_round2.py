@@ -466,7 +466,7 @@ def test_batched_weight_planes_equal_split_and_transpose():
     """lfs2_weight_planes_batched (ops.WeightPrepPlan) == split_bf16(W) / split_bf16(transpose(W)) bit for bit, ragged
     shapes included, and refills from the sources' current values"""
     g = torch.Generator().manual_seed(7)
-    ws = [torch.randn(r, c, generator=g).to(DEV) for r, c in ((768, 2304), (80, 768), (33, 70), (256, 256), (3072, 768))]
+    ws = [torch.randn(r, c, generator=g).to(DEV) for r, c in ((768, 2304), (80, 768), (33, 72), (256, 256), (3072, 768))]
     plan = ops.WeightPrepPlan([(ws[0], True, True), (ws[1], True, False), (ws[2], True, True), (ws[3], False, True),
                                (ws[4], True, True)])
     for rnd_ in range(2):
