@@ -14,6 +14,12 @@ so gradient PARITY is checked with every ``*_dropout = 0`` and dropo
 statistics and by directional derivatives.  Attention-probability dropout needs the tensor-core
 attention path.  Dense-conv (non-depthwise) stacks train too (forward / input gradients on the tensor
 cores as k shifted GEMMs, per-tap weight gradients on the exact-fp32 CUDA-core kernel).
+
+Per optimizer step the operand forms of the weights (bf16 planes, transposed planes, the folded FFN-2 matrix, tap-major
+depthwise weights) are derived once (``WeightCache``; after the first step by ONE batched launch) and shared by forward,
+backward and -- with ``model.train_length_buckets = n`` -- by the n length-sorted sub-batches the step is cut into
+(``forward_train_bucketed``: PAD rows beyond each bucket's longest utterance + conv halo are never computed; losses and
+gradients equal the one-tensor step).
 """
 import numpy as np
 import torch
