@@ -492,7 +492,7 @@ def measure_c5(dev, hbm_peak, steps=20):
 
 
 
-def measure_vocoder(dev, mel, tgt_mask, nutt, steps=3):
+def measure_vocoder(dev, mel, tgt_mask, nutt, steps=3, model=None, pinned=None):
     """the HiFi-GAN generator behind the path (reference synthesis/generator.py:160-170 vocodes every
     utterance of the batch, one call each): the first `nutt` utterances of the timed batch's mel output, valid frames
     only, as ONE ragged batch; seeded weights of the reference architecture (the bundled checkpoint cannot travel)."""
@@ -535,6 +535,30 @@ def measure_vocoder(dev, mel, tgt_mask, nutt, steps=3):
     ms16 = e0.elapsed_time(e1) / steps
     err16 = float((wav16 - wav).abs().max())
     gen.compute_mode = "fp32"
+    # the generation loop end to end: phonemes in pinned host memory -> mel -> waveform on the device -> int16 samples of
+    # every utterance in pinned host memory (pipeline.SynthesisStream(vocoder=...)), first `nutt` utterances per batch
+    stream_res = None
+    if model is not None and pinned is not None:
+        from lightningfastspeech2_b200.pipeline import SynthesisStream
+
+        sub = {k: v[:nutt].contiguous().pin_memory() for k, v in pinned.items()}
+        stream = SynthesisStream(model, vocoder=gen, compact=True)
+        stream.collect(stream.submit(sub))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tickets = []
+        nsamp = nfr = 0
+        for i in range(steps + 1):
+            if i < steps:
+                tickets.append(stream.submit(sub))
+            if i > 0:
+                got = stream.collect(tickets[i - 1])
+                nsamp += sum(int(w.numel()) for w in got["wav"])
+                nfr += sum(got["lengths"])
+        dt = time.perf_counter() - t0
+        stream_res = {"api": "SynthesisStream(model, vocoder=generator, compact=True).submit / collect", "utterances": nutt,
+                      "ms_per_batch": 1e3 * dt / steps, "value": nfr / dt, "unit": UNIT, "samples_per_s": nsamp / dt,
+                      "d2h_bytes_per_step": 2 * nsamp // steps + 4 * 80 * nfr // steps}
     # CPU port on the shortest utterance (bounded), and parity on it
     i = int(lens.argmin())
     n = int(lens[i])
@@ -566,7 +590,8 @@ def measure_vocoder(dev, mel, tgt_mask, nutt, steps=3):
                              "sample": f"the shortest of those utterances ({n} frames), one run of {cpu_s:.1f} s"},
             "max_abs_wav_err_vs_oracle": err,
             "bf16_mode": {"ms_per_batch": ms16, "value": frames / (ms16 * 1e-3), "unit": UNIT,
-                          "max_abs_wav_diff_vs_fp32_mode": err16}}
+                          "max_abs_wav_diff_vs_fp32_mode": err16},
+            "stream_mel_and_wav": stream_res}
 
 
 def run_reference(args):
@@ -909,7 +934,7 @@ def run_lfs2(args):
         try:
             with torch.no_grad():
                 rv = model(resident, inference=True)
-            vocoder = measure_vocoder(dev, rv["mel"], rv["tgt_mask"], args.vocoder_utts)
+            vocoder = measure_vocoder(dev, rv["mel"], rv["tgt_mask"], args.vocoder_utts, model=model, pinned=pinned)
             del rv
         except Exception as exc:  # noqa: BLE001
             errors["vocoder"] = repr(exc)[:300]
