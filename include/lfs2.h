@@ -406,6 +406,12 @@ LFS2_API int lfs2_layernorm_bwd_drop(const float* dy, const float* z, const floa
                                      const float* add, float* dz, float* dz_drop, float* dgamma, float* dbeta,
                                      int m, int d, float drop_p, unsigned long long drop_seed,
                                      unsigned int drop_site, void* stream);
+/* same with the incoming gradient given as two summands, dy + dy2 (dy2 may be NULL): the residual joins of the FFTBlock
+ * backward (x + sublayer(x), model.py:113-115) are added on load instead of by a kernel of their own */
+LFS2_API int lfs2_layernorm_bwd_ex(const float* dy, const float* dy2, const float* z, const float* stats,
+                                   const float* gamma, const float* add, float* dz, float* dz_drop, float* dgamma,
+                                   float* dbeta, int m, int d, float drop_p, unsigned long long drop_seed,
+                                   unsigned int drop_site, void* stream);
 
 /* weight gradient of Linear / pointwise Conv1d / one tap of a dense Conv1d:
  *   c[n,k] += sum_r a[r, n] * b[r + shift, k]      (r over m rows; a is dY, b is the layer input)

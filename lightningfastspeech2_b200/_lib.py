@@ -83,6 +83,8 @@ SIGNATURES = {
     "lfs2_layernorm_bwd": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp],
     "lfs2_layernorm_bwd_drop": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, ctypes.c_ulonglong, ctypes.c_uint,
                                 _vp],
+    "lfs2_layernorm_bwd_ex": [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, ctypes.c_ulonglong,
+                              ctypes.c_uint, _vp],
     "lfs2_gemm_tn": [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp],
     "lfs2_colsum": [_vp, _vp, _i, _i, _vp],
     "lfs2_relu_bwd": [_vp, _vp, _vp, _ll, _vp],

@@ -182,7 +182,8 @@ constexpr int kLnbMaxVec = 8;
 // 139 registers = ONE 256-thread CTA per SM (2.3 TB/s).  Same arithmetic in the same order either way.
 template <int NV, bool RELOAD>  // float4 column groups per lane: d <= 128 * NV
 __global__ void __launch_bounds__(256, RELOAD ? (NV > 6 ? 2 : 3) : 1)
-layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ z, const float2* __restrict__ stats,
+layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ dy2, const float4* __restrict__ z,
+                     const float2* __restrict__ stats,
                      const float4* __restrict__ gamma, const float4* __restrict__ add, float4* __restrict__ dz,
                      float4* __restrict__ dz_drop, float* __restrict__ dgamma, float* __restrict__ dbeta, int m, int d4,
                      DropSite drop) {
@@ -205,7 +206,12 @@ layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ z
     for (int i = 0; i < NV; ++i) {
       const int c = lane + 32 * i;
       if (c < d4) {
-        const float4 dv = dy[(size_t)row * d4 + c], zv = z[(size_t)row * d4 + c], gm = __ldg(gamma + c);
+        float4 dv = dy[(size_t)row * d4 + c];
+        if (dy2) {  // the incoming gradient as two summands (a residual join upstream): added on load
+          const float4 e = dy2[(size_t)row * d4 + c];
+          dv.x += e.x; dv.y += e.y; dv.z += e.z; dv.w += e.w;
+        }
+        const float4 zv = z[(size_t)row * d4 + c], gm = __ldg(gamma + c);
         float4 x;
         x.x = (zv.x - mean) * rstd; x.y = (zv.y - mean) * rstd; x.z = (zv.z - mean) * rstd; x.w = (zv.w - mean) * rstd;
         gacc[i].x = fmaf(dv.x, x.x, gacc[i].x); gacc[i].y = fmaf(dv.y, x.y, gacc[i].y);
@@ -228,7 +234,12 @@ layernorm_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ z
       if (c < d4) {
         float4 gi, xi;
         if (RELOAD) {
-          const float4 dv = dy[(size_t)row * d4 + c], zv = z[(size_t)row * d4 + c], gm = __ldg(gamma + c);
+          float4 dv = dy[(size_t)row * d4 + c];
+          if (dy2) {
+            const float4 e = dy2[(size_t)row * d4 + c];
+            dv.x += e.x; dv.y += e.y; dv.z += e.z; dv.w += e.w;
+          }
+          const float4 zv = z[(size_t)row * d4 + c], gm = __ldg(gamma + c);
           xi.x = (zv.x - mean) * rstd; xi.y = (zv.y - mean) * rstd; xi.z = (zv.z - mean) * rstd; xi.w = (zv.w - mean) * rstd;
           gi.x = dv.x * gm.x; gi.y = dv.y * gm.y; gi.z = dv.z * gm.z; gi.w = dv.w * gm.w;
         } else {
@@ -633,7 +644,15 @@ int lfs2_layernorm_bwd(const float* dy, const float* z, const float* stats, cons
 int lfs2_layernorm_bwd_drop(const float* dy, const float* z, const float* stats, const float* gamma, const float* add,
                             float* dz, float* dz_drop, float* dgamma, float* dbeta, int m, int d, float drop_p,
                             unsigned long long drop_seed, unsigned int drop_site, void* stream) {
+  return lfs2_layernorm_bwd_ex(dy, nullptr, z, stats, gamma, add, dz, dz_drop, dgamma, dbeta, m, d, drop_p, drop_seed,
+                               drop_site, stream);
+}
+
+int lfs2_layernorm_bwd_ex(const float* dy, const float* dy2, const float* z, const float* stats, const float* gamma,
+                          const float* add, float* dz, float* dz_drop, float* dgamma, float* dbeta, int m, int d,
+                          float drop_p, unsigned long long drop_seed, unsigned int drop_site, void* stream) {
   LFS2_REQUIRE(dy && z && stats && gamma && dz && dgamma && dbeta, LFS2_ERR_INVALID_ARG, "layernorm_bwd: null pointer");
+  LFS2_REQUIRE(aligned16(dy2), LFS2_ERR_INVALID_ARG, "layernorm_bwd: dy2 must be 16-byte aligned");
   LFS2_REQUIRE(drop_p >= 0.f && drop_p < 1.f && (!dz_drop || aligned16(dz_drop)), LFS2_ERR_INVALID_ARG,
                "layernorm_bwd: bad dropout arguments");
   const DropSite drop = make_drop_site(drop_p, drop_seed, drop_site);
@@ -653,7 +672,8 @@ int lfs2_layernorm_bwd_drop(const float* dy, const float* z, const float* stats,
   const int nv = ceil_div(d / 4, 32);
 #define LFS2_LNB(NV)                                                                                            \
   layernorm_bwd_kernel<NV, (NV >= 4)><<<blocks, 256, 0, (cudaStream_t)stream>>>(                                \
-      (const float4*)dy, (const float4*)z, (const float2*)stats, (const float4*)gamma, (const float4*)add,      \
+      (const float4*)dy, (const float4*)dy2, (const float4*)z, (const float2*)stats, (const float4*)gamma,      \
+      (const float4*)add,                                                                                       \
       (float4*)dz, (float4*)dz_drop, dgamma, dbeta, m, d / 4, drop)
   if (nv <= 1) LFS2_LNB(1);
   else if (nv <= 2) LFS2_LNB(2);

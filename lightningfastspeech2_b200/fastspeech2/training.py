@@ -323,10 +323,13 @@ def fft_fwd(L, E, x, kpm):
     return x2, s
 
 
-def fft_bwd(L, E, s, dx2):
+def fft_bwd(L, E, s, dx2, dx2b=None):
+    """gradient of the block's output, given as dx2 (+ dx2b: the two summands of the residual join of the block above)
+    -> (dx, dxb): the gradient of the block's input as two summands as well -- the joins are added on load by the next
+    LayerNorm backward (ops.layernorm_bwd dy2) instead of by add kernels; callers at a stack's end add them up"""
     dev = dx2.device
     dz2 = ops.layernorm_bwd(dx2, s["z2"], s["st2"], L.norm2.weight, grad_of(L.norm2.weight), grad_of(L.norm2.bias),
-                            drop=s["drop2"])
+                            drop=s["drop2"], dy2=dx2b)
     dz2, dy = dz2 if s["drop2"] else (dz2, dz2)                          # dy = dropout2's backward of dz2 (same kernel)
     if L.depthwise:
         dx1 = _ffn_bwd_depthwise(L, E, s, dy, dev)
@@ -336,8 +339,7 @@ def fft_bwd(L, E, s, dx2):
         ops.relu_bwd_(dv, s["v"], scale=1.0 / (1.0 - s["dropv"][0]) if s["dropv"] else 1.0)
         dx1 = E.conv_dgrad(dv, L.conv1.weight, tag="ffn1_dgrad")
         E.conv_wgrad_(grad_of(L.conv1.weight), grad_of(L.conv1.bias), dv, s["x1"], tag="ffn1_wgrad")
-    ops.add_(dx1, dz2)                                                   # residual around the FFN
-    return _attn_bwd(L, E, s, dx1)
+    return _attn_bwd(L, E, s, dx1, dz2)                                  # (dz2: the residual around the FFN)
 
 
 def _ffn_bwd_depthwise(L, E, s, dy, dev):
@@ -367,18 +369,17 @@ def _ffn_bwd_depthwise(L, E, s, dy, dev):
     return _dwconv_bwd(E, dwc, du, s["x1"])
 
 
-def _attn_bwd(L, E, s, dx1):
+def _attn_bwd(L, E, s, dx1, dx1b):
     sa = L.self_attn
     dz1 = ops.layernorm_bwd(dx1, s["z1"], s["st1"], L.norm1.weight, grad_of(L.norm1.weight), grad_of(L.norm1.bias),
-                            drop=s["drop1"])
+                            drop=s["drop1"], dy2=dx1b)
     dz1, da = dz1 if s["drop1"] else (dz1, dz1)
     dctx = E.dgrad(da, sa.out_proj.weight, tag="out_proj_dgrad")
     E.wgrad_(grad_of(sa.out_proj.weight), grad_of(sa.out_proj.bias), da, s["ctx"], tag="out_proj_wgrad")
     dqkv = E.attention_bwd(s["qkv"], s["ctx"], dctx, s["att"], s["kpm"], L.nhead)
     dx = E.dgrad(dqkv, sa.in_proj_weight, tag="qkv_dgrad")
     E.wgrad_(grad_of(sa.in_proj_weight), grad_of(sa.in_proj_bias), dqkv, s["x"], tag="qkv_wgrad")
-    ops.add_(dx, dz1)                                                    # residual around the attention
-    return dx
+    return dx, dz1                                                       # (dz1: the residual around the attention)
 
 
 def _dwconv_bwd(E, conv, du, x_in):
@@ -541,8 +542,11 @@ def backward_train(M, S, dmel, ddur, dvars, flush=True):
         dmel = dmel.contiguous()
         dx = E.dgrad(dmel, M.linear.weight, tag="mel_dgrad")
         E.wgrad_(grad_of(M.linear.weight), grad_of(M.linear.bias), dmel, S["dec_out"], tag="mel_wgrad")
+        dxb = None
         for L, s in zip(reversed(list(M.decoder.layers)), reversed(S["dec"])):
-            dx = fft_bwd(L, E, s, dx)
+            dx, dxb = fft_bwd(L, E, s, dx, dxb)
+        if dxb is not None:
+            ops.add_(dx, dxb)
         ops.sum_over_time_(dspk, dx)                                     # "+ spk" at Tm (fastspeech2.py:707)
         E.dropout_bwd(dx, S["drop_dec"])
     else:
@@ -567,8 +571,11 @@ def backward_train(M, S, dmel, ddur, dvars, flush=True):
         ops.sum_over_time_(g, dx)
         ops.relu_bwd_(g, term)
         ops.embedding_bwd_(grad_of(M.prior_embeddings[prior].embedding.weight), g, idx)
+    dxb = None
     for L, s in zip(reversed(list(M.encoder.layers)), reversed(S["enc"])):
-        dx = fft_bwd(L, E, s, dx)
+        dx, dxb = fft_bwd(L, E, s, dx, dxb)
+    if dxb is not None:
+        ops.add_(dx, dxb)
     ops.sum_over_time_(dspk, dx)                                         # "+ spk" at Tp (fastspeech2.py:658)
     E.dropout_bwd(dx, S["drop_enc"])
     ops.embedding_bwd_(grad_of(M.phone_embedding.weight), dx, S["phones"], skip_idx=0)

@@ -871,17 +871,22 @@ def add_layernorm_train(x, y, gamma, beta, eps=LN_EPS, drop=None):
     return out, z, stats
 
 
-def layernorm_bwd(dy, z, stats, gamma, dgamma, dbeta, add=None, drop=None):
-    """-> dz, or (dz, dropout(dz)) when drop = (p, seed, site) of the branch dropout fused into the forward"""
+def layernorm_bwd(dy, z, stats, gamma, dgamma, dbeta, add=None, drop=None, dy2=None):
+    """-> dz, or (dz, dropout(dz)) when drop = (p, seed, site) of the branch dropout fused into the forward.
+    dy2: a second summand of the incoming gradient (a residual join upstream), added on load."""
     _chk(dy, torch.float32, "layernorm_bwd dy"); _chk(z, torch.float32, "layernorm_bwd z")
+    if dy2 is not None:
+        _chk(dy2, torch.float32, "layernorm_bwd dy2")
+        if tuple(dy2.shape) != tuple(dy.shape):
+            raise ValueError("layernorm_bwd: dy2 must be shaped like dy")
     d = z.shape[-1]
     m = z.numel() // d
     dz = torch.empty_like(z)
     dzd = torch.empty_like(z) if drop is not None else None
     dp, dseed, dsite = drop if drop is not None else (0.0, 0, 0)
-    _launch("lfs2_layernorm_bwd_drop", _p(dy), _p(z), _p(stats), _p(gamma), _p(add), _p(dz), _p(dzd), _p(dgamma),
+    _launch("lfs2_layernorm_bwd_ex", _p(dy), _p(dy2), _p(z), _p(stats), _p(gamma), _p(add), _p(dz), _p(dzd), _p(dgamma),
             _p(dbeta), m, d, float(dp), int(dseed), int(dsite), _s(), tag="lfs2_layernorm_bwd",
-            nbytes=4.0 * m * d * (3 + (add is not None) + (drop is not None)))
+            nbytes=4.0 * m * d * (3 + (add is not None) + (drop is not None) + (dy2 is not None)))
     return dz if drop is None else (dz, dzd)
 
 
